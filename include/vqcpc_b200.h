@@ -1,0 +1,133 @@
+/* vqcpc_b200 — C ABI of libvqcpc_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the VQ-CPC encoder-training hot path of SonyCSLParis/vqcpc-bach.  The reference is pure
+ * Python/PyTorch and has no FFI of its own; these entry points are what its Python classes bind (through ctypes,
+ * see INTEGRATION.md) in place of the ATen calls cited next to each function (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; every pointer is DEVICE memory unless marked "host";
+ *   - the caller owns all buffers, kernels never allocate (one lazily allocated 8 KB scratch in vqcpc_grad_sumsq);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered;
+ *   - return value: 0 = ok, <0 = error (VQ_ERR_*); vqcpc_last_error() returns the message (thread local);
+ *   - "ACCUMULATED" outputs are += targets (gradient buffers); all others are overwritten;
+ *   - matrices are row-major fp32 unless stated; `ld*` are leading dimensions in elements.
+ */
+#ifndef VQCPC_B200_H
+#define VQCPC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ_OK 0
+#define VQ_ERR_INVALID (-1)
+#define VQ_ERR_CUDA (-2)
+#define VQ_ERR_DRIVER (-3)
+
+/* GEMM epilogue flags */
+#define VQ_EPI_BIAS 1        /* + bias[n] */
+#define VQ_EPI_RELU 2        /* max(x, 0) */
+#define VQ_EPI_ACCUMULATE 4  /* C += result */
+#define VQ_EPI_RESIDUAL 8    /* + residual[m, n] */
+#define VQ_EPI_RELU_MASK 16  /* * (residual[m, n] > 0): ReLU backward fused into the data-gradient GEMM */
+#define VQ_EPI_SCALE_COLS 64 /* columns n < scale_ncols multiplied by alpha after the bias */
+
+/* ---- runtime ------------------------------------------------------------------------------------------------ */
+const char* vqcpc_last_error(void);
+int vqcpc_abi_version(void);
+int vqcpc_device_info(int* sm_count /*host*/, int* cc_major /*host*/, int* cc_minor /*host*/);
+
+/* ---- data processor: per-voice nn.Embedding lookup, voice = position % V -------------------------------------- */
+/* VQCPCB/data_processor/bach_cpc_data_processor.py:42-68, data_processor.py:26-32.
+ * tokens (n) int64; tables: host array of V device pointers, table v is (rows[v], E); out (n, E). */
+int vqcpc_embed_fwd(const int64_t* tokens, int64_t n, int V, const float* const* tables /*host*/, const int* rows /*host*/,
+                    int E, float* out, void* stream);
+/* d_table[v][tok] += d_out — grads: host array of V device pointers, ACCUMULATED. */
+int vqcpc_embed_bwd(const int64_t* tokens, int64_t n, int V, float* const* grads /*host*/, const int* rows /*host*/, int E,
+                    const float* d_out, void* stream);
+
+/* ---- downscaler pieces ------------------------------------------------------------------------------------- */
+/* VQCPCB/downscalers/relative_transformer_downscaler.py:106-112: h[m, col0 + j] = chan[(m%S)%V][j] (j < pe) |
+ * evt[(m%S)/V][j - pe]; chan (V, pe), evt (S/V, pe).  The backward ACCUMULATES d_chan / d_evt. */
+int vqcpc_posemb_fill(float* h, int ld, int col0, const float* chan, const float* evt, int64_t M, int S, int V, int pe,
+                      void* stream);
+int vqcpc_posemb_bwd(const float* dh, int ld, int col0, float* d_chan, float* d_evt, int64_t M, int S, int V, int pe,
+                     void* stream);
+/* nn.LayerNorm(d), eps inside the sqrt (transformer/transformer_custom.py:261-262, :283, :289); mean/rstd (M) saved. */
+int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
+                        int64_t M, int d, float eps, void* stream);
+/* d_y overwritten; d_gamma / d_beta ACCUMULATED. */
+int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
+                        float* d_y, float* d_gamma, float* d_beta, int64_t M, int d, void* stream);
+/* relative_transformer_downscaler.py:124 `output[::downscaling]` in blocks-major layout: x (P*L, d) -> out (P*L/f, d). */
+int vqcpc_subsample_fwd(const float* x, float* out, int64_t P, int L, int factor, int d, void* stream);
+int vqcpc_subsample_bwd(const float* d_out, float* d_x, int64_t P, int L, int factor, int d, void* stream);
+/* bias gradients: out[n] += sum_m x[m, n]  (ACCUMULATED). */
+int vqcpc_colsum(const float* x, int ld, float* out, int64_t M, int N, void* stream);
+/* nn.SELU of the MLP upscaler (upscalers/mlp_upscaler.py:21-26). */
+int vqcpc_selu_fwd(const float* x, float* out, int64_t n, void* stream);
+int vqcpc_selu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* out[0] = scale * sum(x[0..n)) in a fixed order (deterministic). */
+int vqcpc_reduce_sum(const float* x, int64_t n, float* out, float scale, void* stream);
+
+/* ---- GEMMs (F.linear / matmul call sites: multihead_attention_custom.py:171,346; transformer_custom.py:285;
+ *      relative_transformer_downscaler.py:104,132; mlp_upscaler.py:21-26; vqcpc_helper.py:69 and their backward) -------
+ * C[M,N] = epi(sum_k A(m,k) B(k,n));  a_kmajor: A(m,k)=A[m*lda+k] else A[k*lda+m];  b_kmajor: B(k,n)=B[n*ldb+k] else
+ * B[k*ldb+n].  epi: +bias -> scale cols -> +residual -> relu -> relu-mask; ksplit > 1 = split-K via fp32 atomics. */
+int vqcpc_gemm_f32(int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, const float* bias, const float* residual, int ldr, int flags, float alpha,
+                   int scale_ncols, int ksplit, void* stream);
+/* fp32 (rows, cols; ldx) -> bf16 hi, lo (ldo) with x ~= hi + lo: operand preparation for vqcpc_gemm_bf16x3. */
+int vqcpc_split_bf16(const float* x, int ldx, void* hi, void* lo, int ldo, int64_t rows, int cols, void* stream);
+/* tcgen05/TMEM/TMA tensor-core GEMM on pre-split bf16 operands; passes = 3 (hi.hi + hi.lo + lo.hi, parity mode) or
+ * 1 (hi.hi, fast mode); fp32 accumulation and fp32 C; same layout/epilogue semantics as vqcpc_gemm_f32. */
+int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
+                      const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, const float* bias,
+                      const float* residual, int ldr, int flags, float alpha, int scale_ncols, int passes, int ksplit,
+                      void* stream);
+
+/* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +
+ *      subsampled_relative_attention.py:30-122) ---------------------------------------------------------------------
+ * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64); out (P*L, H*64); probs (P, H, L, L) or NULL. */
+int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L, int H,
+                   int head_dim, void* stream);
+/* d_qkv overwritten (q third = q_scale * dq~); d_e1 / d_e2 ACCUMULATED. */
+int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
+                   float* d_qkv, float* d_e1, float* d_e2, int64_t P, int L, int H, int head_dim, float q_scale,
+                   void* stream);
+
+/* ---- vector quantizer (quantizer/vector_quantizer.py:85-159) --------------------------------------------------
+ * x (n, D); books: host array of ncb device pointers, each (Kc, D/ncb); idx (n, ncb) int64. */
+int vqcpc_vq_search(const float* x, int64_t n, int D, const float* const* books /*host*/, int ncb, int Kc, int64_t* idx,
+                    void* stream);
+/* q = E[idx]; loss (n) = q_latent + beta * e_latent (:72-83); z_sg = x + (q - x) (:148); counts (ncb*Kc) int32
+ * usage histogram ACCUMULATED (may be NULL). */
+int vqcpc_vq_gather(const float* x, int64_t n, int D, const float* const* books /*host*/, int ncb, int Kc,
+                    const int64_t* idx, float beta, int squared, float* z_sg, float* loss, int* counts, void* stream);
+/* d_x overwritten = g_zsg + g_loss * dloss/dx; d_books[cb] ACCUMULATED (host array, entries may be NULL). */
+int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* books /*host*/, float* const* d_books /*host*/,
+                 int ncb, int Kc, const int64_t* idx, float beta, int squared, const float* g_zsg, const float* g_loss,
+                 float* d_x, void* stream);
+
+/* ---- fused InfoNCE (vqcpc_helper.py:5-29, :79-98; vqcpc_encoder_trainer.py:240-272) ---------------------------
+ * c (B, cd); W (zd, cd, KR); y_pos (B, KR, zd); y_neg (B, N, KR, zd).  Outputs: u (B, KR, zd), pos (B, KR),
+ * neg (B, KR, N), lse (B, KR), nll = lse - pos (B, KR), correct (B, KR) int32 = [pos > max_n neg]. */
+int vqcpc_infonce_fwd(const float* c, const float* W, const float* y_pos, const float* y_neg, int B, int N, int KR, int zd,
+                      int cd, float* u, float* pos, float* neg, float* lse, float* nll, int* correct, void* stream);
+/* gradient of sum(nll) scaled by scale * g_dev[0] (g_dev device scalar or NULL); d_c, d_W ACCUMULATED. */
+int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos, const float* y_neg, const float* u,
+                      const float* pos, const float* neg, const float* lse, const float* g_dev, float scale, int B, int N,
+                      int KR, int zd, int cd, float* d_c, float* d_W, float* d_ypos, float* d_yneg, void* stream);
+
+/* ---- optimizer tail (clip_grad_norm_(…, 5) + Adam: vqcpc_encoder_trainer.py:92, :313-314) ----------------------
+ * out[0] = ||grad_scale * g||_2^2 (device scalar, deterministic). */
+int vqcpc_grad_sumsq(const float* g, int64_t n, float grad_scale, float* out, void* stream);
+/* p, m, v updated in place from grad_scale * g clipped by min(1, max_norm / (sqrt(gnorm_sq[0]) + 1e-6)); step >= 1. */
+int vqcpc_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* gnorm_sq, float max_norm,
+                    float grad_scale, float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQCPC_B200_H */

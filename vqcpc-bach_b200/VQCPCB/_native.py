@@ -1,0 +1,80 @@
+"""ctypes binding of libvqcpc_b200.so (the C-ABI declared in include/vqcpc_b200.h).
+
+The library is built in-tree by ``tools/build.sh`` / ``__graft_entry__.build()``.  There is no fallback: if the
+shared object is missing or a call fails, a RuntimeError is raised (no CPU path, no Triton, no torch eager path).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvqcpc_b200.so')
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> argtypes (all functions return int status except the two marked below)
+SIGNATURES = {
+    'vqcpc_device_info': [_P, _P, _P],
+    'vqcpc_embed_fwd': [_P, _L, _I, _P, _P, _I, _P, _P],
+    'vqcpc_embed_bwd': [_P, _L, _I, _P, _P, _I, _P, _P],
+    'vqcpc_posemb_fill': [_P, _I, _I, _P, _P, _L, _I, _I, _I, _P],
+    'vqcpc_posemb_bwd': [_P, _I, _I, _P, _P, _L, _I, _I, _I, _P],
+    'vqcpc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    'vqcpc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
+    'vqcpc_subsample_fwd': [_P, _P, _L, _I, _I, _I, _P],
+    'vqcpc_subsample_bwd': [_P, _P, _L, _I, _I, _I, _P],
+    'vqcpc_colsum': [_P, _I, _P, _L, _I, _P],
+    'vqcpc_selu_fwd': [_P, _P, _L, _P],
+    'vqcpc_selu_bwd': [_P, _P, _P, _L, _P],
+    'vqcpc_split_bf16': [_P, _I, _P, _P, _I, _L, _I, _P],
+    'vqcpc_reduce_sum': [_P, _L, _P, _F, _P],
+    'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],
+    'vqcpc_gemm_bf16x3': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
+    'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
+    'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
+    'vqcpc_vq_search': [_P, _L, _I, _P, _I, _I, _P, _P],
+    'vqcpc_vq_gather': [_P, _L, _I, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
+    'vqcpc_vq_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
+    'vqcpc_infonce_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'vqcpc_infonce_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    'vqcpc_grad_sumsq': [_P, _L, _F, _P, _P],
+    'vqcpc_clip_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _I, _P],
+}
+_SPECIAL = {'vqcpc_last_error': (_c.c_char_p, []), 'vqcpc_abi_version': (_I, [])}
+
+_lib = None
+launch_count = 0   # number of kernel-launching C-ABI calls made through this module (bench.py reports it)
+
+
+def load():
+    """Load the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with tools/build.sh (or __graft_entry__.build()). '
+            'vqcpc_b200 has no CPU/eager fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _I
+    for name, (res, args) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise RuntimeError with the library's message on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        msg = lib.vqcpc_last_error().decode(errors='replace')
+        raise RuntimeError(f'{name} failed (code {rc}): {msg}')
+    return rc

@@ -1,0 +1,119 @@
+"""Encoder (data_processor -> downscaler -> quantizer -> upscaler) and the base trainer loop.
+
+Class surface of VQCPCB/encoder.py: ``Encoder`` (:14-110; forward :76-95, save/load :47-74, merge_codes :97-110) and
+``EncoderTrainer.train_model/plot`` (:231-325).  The cluster-visualisation helpers of the reference (:112-228) need
+music21/matplotlib and are outside the hot path.
+"""
+import os
+
+import torch
+from torch import nn
+
+from . import ops
+from .utils import dict_pretty_print, flatten
+
+
+class Encoder(nn.Module):
+    def __init__(self, model_dir, data_processor, downscaler, quantizer, upscaler):
+        super().__init__()
+        self.data_processor = data_processor
+        self.downscaler = downscaler
+        self.quantizer = quantizer
+        self.upscaler = upscaler
+        self.model_dir = model_dir
+
+    def _dir(self, early_stopped):
+        return f'{self.model_dir}/early_stopped' if early_stopped else f'{self.model_dir}/overfitted'
+
+    def save(self, early_stopped):
+        d = self._dir(early_stopped)
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.data_processor.state_dict(), f'{d}/data_processor')
+        torch.save(self.downscaler.state_dict(), f'{d}/downscaler')
+        torch.save(self.quantizer.state_dict(), f'{d}/quantizer')
+        if self.upscaler is not None:
+            torch.save(self.upscaler.state_dict(), f'{d}/upscaler')
+
+    def load(self, early_stopped, device):
+        print(f'Loading models {self.__repr__()}')
+        d = self._dir(early_stopped)
+        if not os.path.exists(d):          # older checkpoints were saved flat in model_dir
+            d = self.model_dir
+        loc = torch.device(device)
+        # in-place copies keep the parameters' storage (they may alias the trainer's flat buffer)
+        self.data_processor.load_state_dict(torch.load(f'{d}/data_processor', map_location=loc))
+        self.downscaler.load_state_dict(torch.load(f'{d}/downscaler', map_location=loc))
+        self.quantizer.load_state_dict(torch.load(f'{d}/quantizer', map_location=loc))
+        if self.upscaler:
+            self.upscaler.load_state_dict(torch.load(f'{d}/upscaler', map_location=loc))
+        ops.bump_weight_version()
+
+    def forward(self, x, corrupt_labels=False):
+        """x as produced by the dataloader (..., ticks, voices) ->
+        (z_quantized (b, nb, z_dim), encoding_indices (b, nb, num_codebooks) | None, quantization_loss (b, nb))."""
+        x_proc = self.data_processor.preprocess(x)
+        x_embed = self.data_processor.embed(x_proc)
+        x_flat = flatten(x_embed)
+        z = self.downscaler.forward(x_flat)
+        z_quantized, encoding_indices, quantization_loss = self.quantizer.forward(z, corrupt_labels=corrupt_labels)
+        if self.upscaler is not None:
+            z_quantized = self.upscaler(z_quantized)
+        return z_quantized, encoding_indices, quantization_loss
+
+    def merge_codes(self, codes):
+        """Pack the indices of a product quantizer into one integer per position (encoder.py:97-110)."""
+        _, _, num_codebooks = codes.shape
+        ret = codes[:, :, 0].clone()
+        for i in range(1, num_codebooks):
+            ret += codes[:, :, i] * (self.quantizer.codebook_size ** i)
+        return ret
+
+
+class EncoderTrainer(nn.Module):
+    """Epoch loop, checkpointing, early stopping on -accuracy, TensorBoard scalars (encoder.py:231-325)."""
+
+    def __init__(self, dataloader_generator):
+        super().__init__()
+        self.dataloader_generator = dataloader_generator
+
+    def train_model(self, batch_size, num_batches, num_epochs, lr, corrupt_labels, schedule_lr, plot=False,
+                    num_workers=0, **kwargs):
+        if plot:
+            from torch.utils.tensorboard import SummaryWriter
+            self.writer = SummaryWriter(f'{self.model_dir}')
+        best_val = 1e8
+        self.init_optimizers(lr=lr, schedule_lr=schedule_lr)
+        for epoch_id in range(num_epochs):
+            gen_train, gen_val, _ = self.dataloader_generator.dataloaders(batch_size=batch_size, num_workers=num_workers)
+            train_q = self.epoch(data_loader=gen_train, train=True, num_batches=num_batches, corrupt_labels=corrupt_labels)
+            del gen_train
+            val_q = self.epoch(data_loader=gen_val, train=False,
+                               num_batches=num_batches // 2 if num_batches is not None else None,
+                               corrupt_labels=corrupt_labels)
+            del gen_val
+            if getattr(self, 'is_main_process', True):
+                print(f'======= Epoch {epoch_id} =======')
+                print('---Train---')
+                dict_pretty_print(train_q, endstr=' ' * 5)
+                print()
+                print('---Val---')
+                dict_pretty_print(val_q, endstr=' ' * 5)
+                print('\n')
+                self.save(early_stopped=False)
+                if val_q['loss_monitor'] < best_val:
+                    self.save(early_stopped=True)
+                    best_val = val_q['loss_monitor']
+                if plot:
+                    self.plot(epoch_id, train_q, val_q)
+
+    def plot(self, epoch_id, monitored_quantities_train, monitored_quantities_val, index_encoder=None):
+        suffix = f'_{index_encoder})' if index_encoder is not None else ''
+        for split, q in (('train', monitored_quantities_train), ('val', monitored_quantities_val)):
+            if q is None:
+                continue
+            for k, v in q.items():
+                if isinstance(v, list):
+                    for i, e in enumerate(v):
+                        self.writer.add_scalar(f'{k}_{i}{suffix}/{split}', e, epoch_id)
+                else:
+                    self.writer.add_scalar(f'{k}{suffix}/{split}', v, epoch_id)

@@ -1,0 +1,114 @@
+"""String-keyed factories for the encoder-training path (mirror of VQCPCB/getters.py:24-218, :431-516).
+
+Only the branches reachable from ``main_encoder.py -t`` with ``training_method='vqcpc'`` are built; the student /
+decoder / prior branches raise NotImplementedError with a pointer to SURVEY.md §8f.  Config keys that several shipped
+configs omit (``c_net_kwargs['bidirectional']``, ``schedule_lr``) get the reference's de-facto defaults.
+"""
+from .data_processor.bach_cpc_data_processor import BachCPCDataProcessor
+from .data_processor.bach_data_processor import BachDataProcessor
+from .dataloaders.synthetic_cpc_dataloader import SyntheticCPCDataloaderGenerator
+from .downscalers.relative_transformer_downscaler import RelativeTransformerDownscaler
+from .encoder import Encoder
+from .quantizer.vector_quantizer import ProductVectorQuantizer, NoQuantization
+from .upscalers.mlp_upscaler import MlpUpscaler
+from .vqcpc_encoder_trainer import VQCPCEncoderTrainer
+
+_NEXT = 'is outside the VQ-CPC encoder-training hot path built so far (SURVEY.md §8f "next" rows)'
+
+
+def get_dataloader_generator(dataset, training_method, dataloader_generator_kwargs):
+    """'bach' needs the music21 chorale corpus (absent offline); 'synthetic' is the in-scope producer with the same
+    batch-dict contract."""
+    kw = dataloader_generator_kwargs
+    if training_method.lower() != 'vqcpc':
+        raise NotImplementedError(f'training_method={training_method!r} {_NEXT}')
+    if dataset.lower() in ('synthetic', 'bach_synthetic'):
+        return SyntheticCPCDataloaderGenerator(
+            num_tokens_per_block=kw['num_tokens_per_block'], num_blocks_left=kw['num_blocks_left'],
+            num_blocks_right=kw['num_blocks_right'], negative_sampling_method=kw['negative_sampling_method'],
+            num_negative_samples=kw['num_negative_samples'], sequences_size=kw.get('sequences_size', 1),
+            vocab_size=kw.get('vocab_size', 64), seed=kw.get('seed', 1234))
+    if dataset.lower() == 'bach':
+        raise NotImplementedError('dataset="bach" needs music21 and the chorale corpus, which are not available here; '
+                                  'use dataset="synthetic" (same batch contract) or plug a generator exposing '
+                                  'dataloaders()/num_blocks_right/dataset_positive')
+    raise NotImplementedError('If you want to use your own datasets, you need to implement a datasets, '
+                              'data_processor and dataloader')
+
+
+def get_downscaler(downscaler_type, downscaler_kwargs):
+    kw = downscaler_kwargs
+    if downscaler_type == 'relative_transformer_downscaler':
+        return RelativeTransformerDownscaler(
+            input_dim=kw['input_dim'], output_dim=kw['output_dim'], downscale_factors=kw['downscale_factors'],
+            num_channels=kw['num_channels'], d_model=kw['d_model'], n_head=kw['n_head'],
+            list_of_num_layers=kw['list_of_num_layers'], dim_feedforward=kw['dim_feedforward'], dropout=kw['dropout'])
+    if downscaler_type in ('relative_transformer_downscaler_linear', 'lstm_downscaler'):
+        raise NotImplementedError(f'downscaler_type={downscaler_type!r} {_NEXT}')
+    raise NotImplementedError
+
+
+def get_upscaler(upscaler_type, upscaler_kwargs):
+    if upscaler_type == 'mlp_upscaler':
+        return MlpUpscaler(input_dim=upscaler_kwargs['input_dim'], output_dim=upscaler_kwargs['output_dim'],
+                           hidden_size=upscaler_kwargs['hidden_size'], dropout=upscaler_kwargs['dropout'])
+    if upscaler_type is None:
+        return None
+    raise NotImplementedError
+
+
+def get_data_processor(dataloader_generator, data_processor_type, data_processor_kwargs):
+    if data_processor_type == 'bach':
+        ds = dataloader_generator.dataset
+        return BachDataProcessor(embedding_size=data_processor_kwargs['embedding_size'],
+                                 num_events=ds.sequences_size * ds.subdivision,
+                                 num_tokens_per_channel=[len(d) for d in ds.index2note_dicts])
+    if data_processor_type == 'bach_cpc':
+        ds = dataloader_generator.dataset_positive
+        dp = BachCPCDataProcessor(embedding_size=data_processor_kwargs['embedding_size'],
+                                  num_events=ds.sequences_size * ds.subdivision,
+                                  num_channels=dataloader_generator.num_channels,
+                                  num_tokens_per_channel=[len(d) for d in ds.index2note_dicts],
+                                  num_tokens_per_block=dataloader_generator.num_tokens_per_block)
+        assert dataloader_generator.num_channels == dp.num_channels
+        return dp
+    raise NotImplementedError
+
+
+def get_encoder(model_dir, dataloader_generator, config):
+    method = config['training_method'].lower()
+    if method != 'vqcpc':
+        raise NotImplementedError(f'training_method={method!r} {_NEXT}')
+    qk = config['quantizer_kwargs']
+    dk = config['downscaler_kwargs']
+    data_processor = get_data_processor(dataloader_generator, config['data_processor_type'], config['data_processor_kwargs'])
+    # runtime-injected keys (getters.py:138-141, :161)
+    dk['input_dim'] = data_processor.embedding_size
+    dk['output_dim'] = qk['codebook_dim']
+    dk['num_tokens'] = data_processor.num_events * data_processor.num_channels
+    dk['num_channels'] = data_processor.num_channels
+    downscaler = get_downscaler(config['downscaler_type'], dk)
+    if config['quantizer_type'] == 'commitment':
+        quantizer = ProductVectorQuantizer(
+            codebook_size=qk['codebook_size'], num_codebooks=qk['num_codebooks'], codebook_dim=qk['codebook_dim'],
+            initialize=qk.get('initialize', True), squared_l2_norm=qk['squared_l2_norm'],
+            use_batch_norm=qk['use_batch_norm'], commitment_cost=qk['commitment_cost'])
+    elif config['quantizer_type'] is None:
+        quantizer = NoQuantization(codebook_dim=qk['codebook_dim'])
+    else:
+        raise NotImplementedError(f"quantizer_type={config['quantizer_type']!r}")
+    upscaler = None
+    if config['upscaler_type'] is not None:
+        uk = config['upscaler_kwargs']
+        uk['input_dim'] = qk['codebook_dim']
+        upscaler = get_upscaler(config['upscaler_type'], uk)
+    return Encoder(model_dir=model_dir, data_processor=data_processor, downscaler=downscaler, quantizer=quantizer,
+                   upscaler=upscaler)
+
+
+def get_encoder_trainer(model_dir, dataloader_generator, training_method, encoder, auxiliary_networks_kwargs):
+    if training_method.lower() == 'vqcpc':
+        return VQCPCEncoderTrainer(model_dir=model_dir, dataloader_generator=dataloader_generator, encoder=encoder,
+                                   c_net_kwargs=auxiliary_networks_kwargs['c_net_kwargs'],
+                                   quantization_weighting=auxiliary_networks_kwargs['quantization_weighting'])
+    raise NotImplementedError(f'training_method={training_method!r} {_NEXT}')

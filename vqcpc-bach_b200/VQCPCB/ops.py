@@ -1,0 +1,397 @@
+"""Thin PyTorch-side wrappers over the C-ABI kernels (libvqcpc_b200.so) + the autograd Functions built on them.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every numeric op of the hot path is one
+of the hand-written sm_100a kernels.  Nothing here has a CPU or eager fallback: tensors must live on a CUDA device.
+
+GEMM arithmetic modes (``set_gemm_mode``):
+  'fp32'   exact fp32 FMA on CUDA cores (vqcpc_gemm_f32)
+  'bf16x3' tcgen05 tensor cores, operands split into bf16 hi+lo, 3 MMAs per tile, fp32 TMEM accumulation (parity mode)
+  'bf16'   tcgen05, single pass on the hi halves (fast mode; misses the 1e-4 parity bar, reported separately)
+Small / oddly shaped GEMMs (K < 32, N < 32, unaligned leading dimensions) always run the fp32 kernel.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+EPI_BIAS, EPI_RELU, EPI_ACCUMULATE, EPI_RESIDUAL, EPI_RELU_MASK, EPI_SCALE_COLS = 1, 2, 4, 8, 16, 64
+
+_GEMM_MODE = 'bf16x3'
+_WSPLIT_CACHE = {}          # id(param storage) -> (version, hi, lo)
+
+
+def set_gemm_mode(mode):
+    global _GEMM_MODE
+    assert mode in ('fp32', 'bf16x3', 'bf16'), mode
+    _GEMM_MODE = mode
+    _WSPLIT_CACHE.clear()
+
+
+def get_gemm_mode():
+    return _GEMM_MODE
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError('vqcpc_b200 ops need CUDA tensors (there is no CPU fallback)')
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def split_bf16(x2d):
+    """(rows, cols) fp32 (row stride = x2d.stride(0)) -> contiguous bf16 (hi, lo) with x ~= hi + lo."""
+    rows, cols = x2d.shape
+    assert x2d.stride(1) == 1
+    hi = torch.empty(rows, cols, dtype=torch.bfloat16, device=x2d.device)
+    lo = torch.empty(rows, cols, dtype=torch.bfloat16, device=x2d.device)
+    _native.call('vqcpc_split_bf16', _p(x2d), x2d.stride(0), _p(hi), _p(lo), cols, rows, cols, _stream())
+    return hi, lo
+
+
+def weight_split(w):
+    """Cached bf16 split of a parameter (invalidated by the in-place optimizer update via ``bump_weight_version``)."""
+    key = (w.data_ptr(), tuple(w.shape))
+    ent = _WSPLIT_CACHE.get(key)
+    if ent is not None and ent[0] == _WEIGHT_VERSION[0]:
+        return ent[1], ent[2]
+    w2 = w.detach().reshape(w.shape[0], -1)
+    hi, lo = split_bf16(w2)
+    _WSPLIT_CACHE[key] = (_WEIGHT_VERSION[0], hi, lo)
+    return hi, lo
+
+
+_WEIGHT_VERSION = [0]
+
+
+def bump_weight_version():
+    """Call after parameters change (optimizer step / load_state_dict) so cached bf16 splits are rebuilt."""
+    _WEIGHT_VERSION[0] += 1
+    if len(_WSPLIT_CACHE) > 256:
+        _WSPLIT_CACHE.clear()
+
+
+def _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor):
+    if _GEMM_MODE == 'fp32':
+        return False
+    if K < 32 or N < 32 or M < 1:
+        return False
+    # TMA needs 16-byte aligned leading dimensions of the (contiguous) bf16 copies
+    a_cols = K if a_kmajor else M
+    b_cols = K if b_kmajor else N
+    return a_cols % 8 == 0 and b_cols % 8 == 0 and a_cols % 4 == 0 and b_cols % 4 == 0
+
+
+def gemm(a, b, M, N, K, a_kmajor=True, b_kmajor=True, out=None, bias=None, residual=None, relu=False, relu_mask=None,
+         accumulate=False, scale_cols=None, ksplit=1, b_is_weight=False, a_split=None, b_split=None):
+    """C[M,N] = epi(A.B).  a/b are 2-D fp32 views whose unit-stride dim is K (kmajor) or M/N (not kmajor).
+
+    epilogue: +bias[N] -> (cols < n) *= alpha  [scale_cols=(alpha, n)] -> +residual[M,N] -> relu -> *(relu_mask > 0)
+    accumulate: C += result.  ksplit > 1: split-K with fp32 atomics (linear epilogues only)."""
+    _chk(a, b, out, bias, residual, relu_mask)
+    dev = a.device
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    assert out.stride(1) == 1
+    flags = 0
+    if bias is not None:
+        flags |= EPI_BIAS
+    if relu:
+        flags |= EPI_RELU
+    if accumulate:
+        flags |= EPI_ACCUMULATE
+    res = residual
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+        assert relu_mask is None
+    if relu_mask is not None:
+        flags |= EPI_RELU_MASK
+        res = relu_mask
+    alpha, ncols = 1.0, 0
+    if scale_cols is not None:
+        flags |= EPI_SCALE_COLS
+        alpha, ncols = scale_cols
+    ldr = res.stride(0) if res is not None else 0
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor):
+        if a_split is None:
+            a_split = split_bf16(a)
+        if b_split is None:
+            b_split = weight_split(b) if b_is_weight else split_bf16(b)
+        passes = 3 if _GEMM_MODE == 'bf16x3' else 1
+        _native.call('vqcpc_gemm_bf16x3', int(a_kmajor), int(b_kmajor), M, N, K, _p(a_split[0]), _p(a_split[1]),
+                     a_split[0].stride(0), _p(b_split[0]), _p(b_split[1]), b_split[0].stride(0), _p(out), out.stride(0),
+                     _p(bias), _p(res), ldr, flags, float(alpha), int(ncols), passes, int(ksplit), _stream())
+    else:
+        _native.call('vqcpc_gemm_f32', int(a_kmajor), int(b_kmajor), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0),
+                     _p(out), out.stride(0), _p(bias), _p(res), ldr, flags, float(alpha), int(ncols), int(ksplit), _stream())
+    return out
+
+
+def _wgrad_ksplit(M_red, n_out_tiles):
+    """split-K factor for a weight-gradient GEMM (reduction over M_red rows) so that ~2 waves of CTAs are busy."""
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    want = max(1, (2 * sms) // max(1, n_out_tiles))
+    return int(max(1, min(want, M_red // 256 if M_red >= 256 else 1)))
+
+
+def linear_fwd(x2d, w, b, relu=False, residual=None, scale_cols=None, out=None):
+    """y = x @ w.T + b  (nn.Linear weight layout (N, K))."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    return gemm(x2d, w, M, N, K, True, True, out=out, bias=b, relu=relu, residual=residual, scale_cols=scale_cols,
+                b_is_weight=True)
+
+
+def linear_bwd(x2d, w, dy, dw, db, need_dx=True, dx_residual=None, relu_mask=None, dx_out=None):
+    """Gradients of y = x @ w.T + b.  dw/db are ACCUMULATED in place (flat-gradient-buffer views).
+    dx = dy @ w (+ dx_residual) (* relu_mask > 0)."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    dx = None
+    if need_dx:
+        dx = gemm(dy, w, M, K, N, True, False, out=dx_out, residual=dx_residual, relu_mask=relu_mask, b_is_weight=True)
+    if dw is not None:
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        gemm(dy, x2d, N, K, M, False, False, out=dw.view(N, K), accumulate=True, ksplit=_wgrad_ksplit(M, tiles))
+    if db is not None:
+        colsum(dy, db)
+    return dx
+
+
+def colsum(x2d, out_accum):
+    _native.call('vqcpc_colsum', _p(x2d), x2d.stride(0), _p(out_accum), x2d.shape[0], x2d.shape[1], _stream())
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else 0 for t in tensors])
+    return arr
+
+
+def embed_fwd(tokens_flat, tables):
+    n = tokens_flat.numel()
+    E = tables[0].shape[1]
+    out = torch.empty(n, E, dtype=torch.float32, device=tokens_flat.device)
+    rows = (ctypes.c_int * len(tables))(*[t.shape[0] for t in tables])
+    _native.call('vqcpc_embed_fwd', _p(tokens_flat), n, len(tables), _ptr_array(tables), rows, E, _p(out), _stream())
+    return out
+
+
+def embed_bwd(tokens_flat, dout, grads):
+    n = tokens_flat.numel()
+    E = dout.shape[-1]
+    rows = (ctypes.c_int * len(grads))(*[g.shape[0] for g in grads])
+    _native.call('vqcpc_embed_bwd', _p(tokens_flat), n, len(grads), _ptr_array(grads), rows, E, _p(dout), _stream())
+
+
+def layernorm_fwd(y, gamma, beta, eps=1e-5):
+    M, d = y.shape
+    out = torch.empty_like(y)
+    mean = torch.empty(M, dtype=torch.float32, device=y.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=y.device)
+    _native.call('vqcpc_layernorm_fwd', _p(y), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), M, d, float(eps), _stream())
+    return out, mean, rstd
+
+
+def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta):
+    M, d = y.shape
+    dy = torch.empty_like(y)
+    _native.call('vqcpc_layernorm_bwd', _p(dout), _p(y), _p(mean), _p(rstd), _p(gamma), _p(dy), _p(dgamma), _p(dbeta), M, d,
+                 _stream())
+    return dy
+
+
+def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True):
+    M = P * L
+    out = torch.empty(M, H * hd, dtype=torch.float32, device=qkv.device)
+    probs = torch.empty(P, H, L, L, dtype=torch.float32, device=qkv.device) if need_probs else None
+    _native.call('vqcpc_attn_fwd', _p(qkv), _p(e1), _p(e2), _p(out), _p(probs), P, L, H, hd, _stream())
+    return out, probs
+
+
+def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale):
+    dqkv = torch.empty_like(qkv)
+    _native.call('vqcpc_attn_bwd', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(de1), _p(de2), P, L, H, hd,
+                 float(q_scale), _stream())
+    return dqkv
+
+
+def reduce_sum(x, scale=1.0):
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    _native.call('vqcpc_reduce_sum', _p(x), x.numel(), _p(out), float(scale), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ autograd Functions
+def _grad_buf(p):
+    """Gradient accumulator of a leaf parameter (allocated zeroed on first use; kernels accumulate in place)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+class _ParamGradSink:
+    """Kernels accumulate parameter gradients directly into ``param.grad`` (which the trainer aliases to a flat
+    buffer); autograd is told the gradient is None.  ``enabled`` lets tests ask for returned gradients instead."""
+    direct = True
+
+
+class EmbedFn(torch.autograd.Function):
+    """data_processor/bach_cpc_data_processor.py:42-68 — per-voice embedding lookup."""
+
+    @staticmethod
+    def forward(ctx, tokens, *tables):
+        flat = tokens.reshape(-1).contiguous()
+        out = embed_fwd(flat, [t.detach() for t in tables])
+        ctx.save_for_backward(flat)
+        ctx.tables = tables
+        return out.view(*tokens.shape, tables[0].shape[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        (flat,) = ctx.saved_tensors
+        tables = ctx.tables
+        dout = _f32c(dout).view(-1, dout.shape[-1])
+        grads = [torch.zeros_like(t) for t in tables]
+        embed_bwd(flat, dout, grads)
+        return (None, *grads)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the hand-written GEMMs (used by the upscaler MLP and the c-net output layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x2 = _f32c(x).view(-1, x.shape[-1])
+        y = linear_fwd(x2, w.detach(), None if b is None else b.detach())
+        ctx.save_for_backward(x2, w, b)
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, b = ctx.saved_tensors
+        dy2 = _f32c(dy).view(-1, dy.shape[-1])
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros_like(b) if (b is not None and ctx.needs_input_grad[2]) else None
+        dx = linear_bwd(x2, w.detach(), dy2, dw, db, need_dx=ctx.needs_input_grad[0])
+        return (dx.view(ctx.xshape) if dx is not None else None), dw, db
+
+
+class SeluFn(torch.autograd.Function):
+    """upscalers/mlp_upscaler.py:24 nn.SELU."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        out = torch.empty_like(x)
+        _native.call('vqcpc_selu_fwd', _p(x), _p(out), x.numel(), _stream())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(x)
+        _native.call('vqcpc_selu_bwd', _p(x), _p(dy), _p(dx), x.numel(), _stream())
+        return dx
+
+
+class QuantizeFn(torch.autograd.Function):
+    """quantizer/vector_quantizer.py:104-157 — search (or given indices), gather, loss, straight-through output."""
+
+    @staticmethod
+    def forward(ctx, z, given_idx, beta, squared, counts, *books):
+        shp = z.shape
+        D = shp[-1]
+        z2 = _f32c(z).view(-1, D)
+        n = z2.shape[0]
+        ncb = len(books)
+        Kc = books[0].shape[0]
+        bk = [b.detach() for b in books]
+        arr = _ptr_array(bk)
+        if given_idx is None:
+            idx = torch.empty(n, ncb, dtype=torch.int64, device=z.device)
+            _native.call('vqcpc_vq_search', _p(z2), n, D, arr, ncb, Kc, _p(idx), _stream())
+        else:
+            idx = given_idx.reshape(n, ncb).contiguous()
+        zsg = torch.empty_like(z2)
+        loss = torch.empty(n, dtype=torch.float32, device=z.device)
+        _native.call('vqcpc_vq_gather', _p(z2), n, D, arr, ncb, Kc, _p(idx), float(beta), int(squared), _p(zsg), _p(loss),
+                     _p(counts), _stream())
+        ctx.save_for_backward(z2, idx, *books)
+        ctx.meta = (shp, beta, squared, ncb, Kc)
+        idx_out = idx.view(*shp[:-1], ncb)
+        ctx.mark_non_differentiable(idx_out)
+        return zsg.view(shp), idx_out, loss.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, g_zsg, _g_idx, g_loss):
+        z2, idx, *books = ctx.saved_tensors
+        shp, beta, squared, ncb, Kc = ctx.meta
+        n, D = z2.shape
+        gz = None if g_zsg is None else _f32c(g_zsg).view(n, D)
+        gl = None if g_loss is None else _f32c(g_loss).reshape(n)
+        dbooks = [torch.zeros_like(b) for b in books]
+        dx = torch.empty_like(z2)
+        _native.call('vqcpc_vq_bwd', _p(z2), n, D, _ptr_array([b.detach() for b in books]), _ptr_array(dbooks), ncb, Kc,
+                     _p(idx), float(beta), int(squared), _p(gz), _p(gl), _p(dx), _stream())
+        return (dx.view(shp), None, None, None, None, *dbooks)
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """Fused Fks scoring + log-sum-exp.  Returns (sum_{b,k} (lse - pos), pos, neg, correct); only the first is
+    differentiable.  vqcpc_helper.py:79-98, :5-29; vqcpc_encoder_trainer.py:240-272."""
+
+    @staticmethod
+    def forward(ctx, c, W, y_pos, y_neg):
+        c, W, y_pos, y_neg = _f32c(c), _f32c(W), _f32c(y_pos), _f32c(y_neg)
+        B, cd = c.shape
+        zd, cd2, KR = W.shape
+        N = y_neg.shape[1]
+        assert cd2 == cd and y_pos.shape == (B, KR, zd) and y_neg.shape == (B, N, KR, zd)
+        dev = c.device
+        u = torch.empty(B, KR, zd, dtype=torch.float32, device=dev)
+        pos = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        neg = torch.empty(B, KR, N, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        correct = torch.empty(B, KR, dtype=torch.int32, device=dev)
+        nll = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        _native.call('vqcpc_infonce_fwd', _p(c), _p(W), _p(y_pos), _p(y_neg), B, N, KR, zd, cd, _p(u), _p(pos), _p(neg), _p(lse),
+                     _p(nll), _p(correct), _stream())
+        total = reduce_sum(nll).reshape(())   # deterministic fixed-order sum
+        ctx.save_for_backward(c, W, y_pos, y_neg, u, pos, neg, lse)
+        ctx.mark_non_differentiable(pos, neg, correct)
+        return total, pos, neg, correct
+
+    @staticmethod
+    def backward(ctx, g_total, *_):
+        c, W, y_pos, y_neg, u, pos, neg, lse = ctx.saved_tensors
+        B, cd = c.shape
+        zd, _, KR = W.shape
+        N = y_neg.shape[1]
+        dc = torch.zeros_like(c)
+        dW = torch.zeros_like(W)
+        dyp = torch.empty_like(y_pos)
+        dyn = torch.empty_like(y_neg)
+        g = _f32c(g_total).reshape(1)         # upstream gradient stays on the device (no host sync)
+        _native.call('vqcpc_infonce_bwd', _p(c), _p(W), _p(y_pos), _p(y_neg), _p(u), _p(pos), _p(neg), _p(lse), _p(g), 1.0, B, N, KR,
+                     zd, cd, _p(dc), _p(dW), _p(dyp), _p(dyn), _stream())
+        return dc, dW, dyp, dyn

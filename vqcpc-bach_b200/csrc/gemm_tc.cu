@@ -1,0 +1,444 @@
+// Tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators, persistent and warp-specialised.
+//
+//   C[M,N] = epi( A . B ) with A, B given as PRE-SPLIT bf16 pairs (hi, lo), x ~= hi + lo (see vqcpc_split_bf16):
+//     passes = 3 ("bf16x3", parity mode): D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (fp32 accumulation in TMEM;
+//                 drops only the lo.lo term: relative error ~2^-16 per product, measured 7e-6 end to end)
+//     passes = 1 ("bf16",  fast mode)   : D += A_hi.B_hi
+//   Operand layouts (same convention as vqcpc_gemm_f32):
+//     a_kmajor=1: A(m,k)=A[m*lda+k]   a_kmajor=0: A(m,k)=A[k*lda+m]   (tcgen05 "MN-major", used by weight gradients)
+//     b_kmajor=1: B(k,n)=B[n*ldb+k]   b_kmajor=0: B(k,n)=B[k*ldb+n]   (data gradients read the weight untransposed)
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2..5 = epilogue
+// (TMEM -> registers -> fused bias/scale/residual/ReLU/mask -> global).  Tile 128 x 128 x 64, kStages-deep smem ring
+// (full/empty mbarriers), two TMEM accumulator stages (tmem_full/tmem_empty) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Grid = min(#work items, #SMs); work item = (m tile, n tile, k split).
+// Split-K partials are reduced with fp32 atomics (red.global.add) into C.
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_ACC = 2;
+constexpr int TMEM_COLS = NUM_ACC * BN;           // 256 (power of two)
+constexpr int TILE_A_BYTES = BM * BK * 2;         // 16 KB
+constexpr int TILE_B_BYTES = BN * BK * 2;         // 16 KB
+constexpr int THREADS = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("vqcpc gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format: version=1 at bit 46, layout type at bits 61..63; SWIZZLE_128B = 2).
+//   K-major  tile [rows][64 bf16] (128 B rows, 8-row swizzle atoms): SBO = 1024 B, LBO unused (=16 B)
+//   MN-major tile = chunks of [64 k-rows][64 mn] (8 KB each, one TMA box): LBO = 8192 B between 64-wide mn chunks,
+//                   SBO = 1024 B between groups of 8 k-rows
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool kmajor) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  uint32_t lbo = kmajor ? 16u : 8192u;
+  uint32_t sbo = 1024u;
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(bool a_kmajor, bool b_kmajor) {
+  return (1u << 4)                         // D format: f32
+         | (1u << 7)                       // A format: bf16
+         | (1u << 10)                      // B format: bf16
+         | ((a_kmajor ? 0u : 1u) << 15)    // A major: 0 = K, 1 = MN
+         | ((b_kmajor ? 0u : 1u) << 16)    // B major
+         | ((uint32_t)(BN >> 3) << 17)     // N
+         | ((uint32_t)(BM >> 4) << 24);    // M
+}
+
+struct TcParams {
+  int M, N, K;
+  float* C;
+  int ldc;
+  EpilogueParams ep;
+  int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
+};
+
+template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + NUM_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NUM_ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = p.m_tiles * p.n_tiles * p.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);     // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int ks = item / (p.m_tiles * p.n_tiles);
+        const int rem = item % (p.m_tiles * p.n_tiles);
+        const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+        const int kb0 = ks * p.kblocks_per_split;
+        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(st), b_hi = smem_u32(st + TILE_A_BYTES);
+          const uint32_t a_lo = smem_u32(st + TILE_A_BYTES + TILE_B_BYTES), b_lo = a_lo + TILE_A_BYTES;
+          const int k0 = kb * BK;
+          if (A_KMAJOR) {
+            tma_load_2d(a_hi, &tmA_hi, fb, k0, m0);
+            if (PASSES == 3) tma_load_2d(a_lo, &tmA_lo, fb, k0, m0);
+          } else {
+            tma_load_2d(a_hi, &tmA_hi, fb, m0, k0);
+            tma_load_2d(a_hi + 8192, &tmA_hi, fb, m0 + 64, k0);
+            if (PASSES == 3) {
+              tma_load_2d(a_lo, &tmA_lo, fb, m0, k0);
+              tma_load_2d(a_lo + 8192, &tmA_lo, fb, m0 + 64, k0);
+            }
+          }
+          if (B_KMAJOR) {
+            tma_load_2d(b_hi, &tmB_hi, fb, k0, n0);
+            if (PASSES == 3) tma_load_2d(b_lo, &tmB_lo, fb, k0, n0);
+          } else {
+            tma_load_2d(b_hi, &tmB_hi, fb, n0, k0);
+            tma_load_2d(b_hi + 8192, &tmB_hi, fb, n0 + 64, k0);
+            if (PASSES == 3) {
+              tma_load_2d(b_lo, &tmB_lo, fb, n0, k0);
+              tma_load_2d(b_lo + 8192, &tmB_lo, fb, n0 + 64, k0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_KMAJOR, B_KMAJOR);
+      constexpr uint32_t A_STEP = A_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per K=16 step inside a stage
+      constexpr uint32_t B_STEP = B_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int ks = item / (p.m_tiles * p.n_tiles);
+        const int kb0 = ks * p.kblocks_per_split;
+        const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(st), b_hi = smem_u32(st + TILE_A_BYTES);
+          const uint32_t a_lo = smem_u32(st + TILE_A_BYTES + TILE_B_BYTES), b_lo = a_lo + TILE_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da_hi = make_desc(a_hi + k * A_STEP, A_KMAJOR);
+            const uint64_t db_hi = make_desc(b_hi + k * B_STEP, B_KMAJOR);
+            const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (PASSES == 3) {
+              const uint64_t da_lo = make_desc(a_lo + k * A_STEP, A_KMAJOR);
+              const uint64_t db_lo = make_desc(b_lo + k * B_STEP, B_KMAJOR);
+              umma_bf16(tmem_d, da_lo, db_hi, idesc, first);
+              umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_bf16(tmem_d, da_hi, db_hi, idesc, first);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));           // accumulator complete -> epilogue
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int ks = item / (p.m_tiles * p.n_tiles);
+      const int rem = item % (p.m_tiles * p.n_tiles);
+      const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+      const bool first_split = (ks == 0);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + ch * 32;
+        if (row < p.M && col0 < p.N) {
+          float* dst = p.C + (size_t)row * p.ldc + col0;
+          const bool full = (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+          if (full && !(p.ep.flags & EPI_ATOMIC)) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 o;
+              o.x = epilogue_apply(__uint_as_float(r[v * 4 + 0]), row, col0 + v * 4 + 0, p.ep, first_split);
+              o.y = epilogue_apply(__uint_as_float(r[v * 4 + 1]), row, col0 + v * 4 + 1, p.ep, first_split);
+              o.z = epilogue_apply(__uint_as_float(r[v * 4 + 2]), row, col0 + v * 4 + 2, p.ep, first_split);
+              o.w = epilogue_apply(__uint_as_float(r[v * 4 + 3]), row, col0 + v * 4 + 3, p.ep, first_split);
+              if (p.ep.flags & EPI_ACCUMULATE) {
+                float4 c = ld4(dst + v * 4);
+                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+              }
+              st4(dst + v * 4, o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                float v = epilogue_apply(__uint_as_float(r[j]), row, col0 + j, p.ep, first_split);
+                if (p.ep.flags & EPI_ATOMIC) atomicAdd(dst + j, v);
+                else if (p.ep.flags & EPI_ACCUMULATE) dst[j] += v;
+                else dst[j] = v;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return VQ_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    vq_set_error("gemm_bf16x3: cuTensorMapEncodeTiled driver entry point unavailable (%s)", cudaGetErrorString(e));
+    return VQ_ERR_DRIVER;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return VQ_OK;
+}
+
+// 2-D bf16 tensor map over a row-major [rows][cols] matrix (leading dimension ld elements), 128B swizzle.
+// box = 64 columns (128 bytes) x box_rows rows.
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vq_set_error("gemm_bf16x3: cuTensorMapEncodeTiled failed (CUresult %d; rows=%llu cols=%llu ld=%llu)", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return VQ_ERR_DRIVER;
+  }
+  return VQ_OK;
+}
+
+template <bool AK, bool BK_, int PASSES>
+int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+  constexpr int STAGES = PASSES == 3 ? 3 : 6;
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool done = false;
+  if (!done) {
+    VQ_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK_, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    done = true;
+  }
+  int items = p.m_tiles * p.n_tiles * p.ksplit;
+  int grid = std::min(items, vq_sm_count());
+  gemm_tc_kernel<AK, BK_, PASSES, STAGES><<<grid, THREADS, SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  VQ_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
+  return VQ_OK;
+}
+
+}  // namespace
+
+VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
+                             const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, const float* bias,
+                             const float* residual, int ldr, int flags, float alpha, int scale_ncols, int passes, int ksplit,
+                             void* stream) {
+  VQ_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_bf16x3: bad shape M=%d N=%d K=%d", M, N, K);
+  VQ_CHECK_ARG(passes == 1 || passes == 3, "gemm_bf16x3: passes must be 1 or 3");
+  VQ_CHECK_ARG(A_hi && B_hi && C && (passes == 1 || (A_lo && B_lo)), "gemm_bf16x3: null operand");
+  VQ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16x3: leading dimensions must be multiples of 8 bf16 (lda=%d ldb=%d)", lda, ldb);
+  VQ_CHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0 && ((uintptr_t)A_lo & 15) == 0 && ((uintptr_t)B_lo & 15) == 0,
+               "gemm_bf16x3: operands must be 16-byte aligned");
+  VQ_CHECK_ARG(!(flags & (EPI_RESIDUAL | EPI_RELU_MASK)) || residual, "gemm_bf16x3: residual/mask flag without pointer");
+  VQ_CHECK_ARG(!(flags & EPI_BIAS) || bias, "gemm_bf16x3: bias flag without pointer");
+  if (M == 0) return VQ_OK;
+  int rc = get_encode();
+  if (rc != VQ_OK) return rc;
+
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
+  p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
+  p.m_tiles = (int)vq_cdiv(M, BM);
+  p.n_tiles = (int)vq_cdiv(N, BN);
+  p.kblocks_total = (int)vq_cdiv(K, BK);
+  if (ksplit < 1) ksplit = 1;
+  p.kblocks_per_split = (int)vq_cdiv(p.kblocks_total, ksplit);
+  p.ksplit = (int)vq_cdiv(p.kblocks_total, p.kblocks_per_split);
+  cudaStream_t st = vq_stream(stream);
+  if (p.ksplit > 1) {
+    VQ_CHECK_ARG(!(flags & (EPI_RELU | EPI_RELU_MASK)), "gemm_bf16x3: split-K cannot fuse a non-linear epilogue");
+    p.ep.flags |= EPI_ATOMIC;
+    if (!(flags & EPI_ACCUMULATE))
+      VQ_CUDA_CALL(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+  }
+
+  CUtensorMap maps[4];
+  const void* alo = passes == 3 ? A_lo : A_hi;
+  const void* blo = passes == 3 ? B_lo : B_hi;
+  if (a_kmajor) {   // [M rows][K cols]
+    if ((rc = make_map(&maps[0], A_hi, M, K, lda, BM)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[1], alo, M, K, lda, BM)) != VQ_OK) return rc;
+  } else {          // [K rows][M cols]
+    if ((rc = make_map(&maps[0], A_hi, K, M, lda, BK)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[1], alo, K, M, lda, BK)) != VQ_OK) return rc;
+  }
+  if (b_kmajor) {   // [N rows][K cols]
+    if ((rc = make_map(&maps[2], B_hi, N, K, ldb, BN)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[3], blo, N, K, ldb, BN)) != VQ_OK) return rc;
+  } else {          // [K rows][N cols]
+    if ((rc = make_map(&maps[2], B_hi, K, N, ldb, BK)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[3], blo, K, N, ldb, BK)) != VQ_OK) return rc;
+  }
+
+#define VQ_TC(AK, BKM)                                                             \
+  (passes == 3 ? launch_tc<AK, BKM, 3>(maps, p, st) : launch_tc<AK, BKM, 1>(maps, p, st))
+  if (a_kmajor && b_kmajor) return VQ_TC(true, true);
+  if (a_kmajor && !b_kmajor) return VQ_TC(true, false);
+  if (!a_kmajor && b_kmajor) return VQ_TC(false, true);
+  return VQ_TC(false, false);
+#undef VQ_TC
+}
