@@ -1,0 +1,271 @@
+"""Benchmark of the VQ-CPC encoder-training hot path (BASELINE.json metric: encoder training samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode bf16x3|bf16|fp32]
+
+One "step" = one full training step (3 encoder passes, quantizer, upscaler, GRU context, InfoNCE, backward, global-norm
+clip + Adam) on one synthetic batch of B windows per GPU.  N=1 workload = BASELINE.json configs[1]
+("K=512 codebook, synthetic 4-voice seq 256, batch 4096, 1xB200"); N>1 = configs[2] (same per GPU, weak scaling, one
+NCCL all-reduce of [grads | counts | stats] per step).  Prints ONE JSON line on rank 0.
+
+  value     samples/s, inputs already resident in HBM, timed with CUDA events, max over ranks
+  e2e       same metric through the public call (trainer.step on a HOST batch dict): pinned-host -> device copy of the
+            step's tokens and a device -> host read of the step's loss inside the timed region
+  roofline  dominant kernel (the tcgen05 GEMM): algorithmic FLOPs (2MNK per launch) / CUDA-event time of those
+            launches inside the timed region, against MEASURED_PEAKS.json (sustained bf16)
+  cpu_baseline  the CPU oracle port of the reference trainer step timed on the host cores (bounded sample, rank 0, N=1)
+
+--impl reference times that same CPU port (the reference is pure Python and cannot travel to the GPU box; the oracle is
+its restatement pinned by tests/golden) with all host threads, as samples/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'vqcpc-bach_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = 'vqcpc_encoder_training_samples_per_sec'
+UNIT = 'samples/s'
+KL = KR = 8
+NNEG = 15
+CODEBOOK = 512
+FLOPS_PER_SAMPLE = 103.8e9          # fwd+bwd algorithmic (SURVEY.md §8a FLOP accounting), no recompute / dead-row skipping
+
+
+def workload_name(B):
+    return f'encoder_vqcpc K={CODEBOOK} D=3 seq256 (KL=KR=8) N=15 batch {B}/GPU, transformer downscaler [4,4]/[2,2]/512/8/2048, dropout 0'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d.get('bf16_tflops_sustained', 1386.1), tflops_burst=d.get('bf16_tflops', 1645.3),
+                    hbm=d.get('hbm_gbs', 6547.2), src='MEASURED_PEAKS.json (sustained bf16)')
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples if len(s) > 2 + i)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return dict(sm_mhz=mhz[len(mhz) // 2] if mhz else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle leg
+def cpu_port_samples_per_sec(B_cpu=16, steps=2, warmup=1):
+    """The reference trainer step as restated by the oracle, on the host cores, at the benchmark shapes with a
+    CPU-sized batch (one fp32 activation at B=4096 would be 18 GB; CPU throughput is ~batch independent)."""
+    from oracle import params as P, vqcpc_oracle as O
+    cfg = O.default_cfg(codebook_size=CODEBOOK, KL=KL, KR=KR, N=NNEG)
+    prm = P.make_params(cfg, 0)
+    m = v = None
+    t_total = 0.0
+    for i in range(warmup + steps):
+        batch = P.make_batch(cfg, B_cpu, seed=100 + i)
+        t0 = time.perf_counter()
+        out, grads, gnorm, prm, m, v = O.trainer_step(batch, prm, cfg, m, v, step=i + 1, lr=1e-4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            t_total += dt
+    return B_cpu * steps / t_total, dict(cores=torch.get_num_threads(), kind='port',
+                                         sample=f'{steps} steps of B={B_cpu} at the benchmark shapes (seq 256, K={CODEBOOK}, N=15), '
+                                                f'{warmup} warm-up, torch {torch.__version__} CPU fp32, oracle/vqcpc_oracle.trainer_step')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    val, info = cpu_port_samples_per_sec(B_cpu=16, steps=steps, warmup=1)
+    line = dict(metric=METRIC, value=val, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps, warmup=1,
+                ms_per_step=1000.0 * 16 / val, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=dict(workload=workload_name(args.batch), note='CPU port of the reference step; B=16 sample'),
+                cpu_baseline=dict(value=val, unit=UNIT, **info),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU leg
+def build_trainer(B, seed):
+    from VQCPCB.getters import get_dataloader_generator, get_encoder, get_encoder_trainer
+    import importlib.util
+    os.environ['VQCPC_BATCH'] = str(B)
+    os.environ['VQCPC_BLOCKS'] = str(KL)
+    os.environ['VQCPC_CODEBOOK'] = str(CODEBOOK)
+    path = os.path.join(ROOT, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'encoder_vqcpc.py')
+    spec = importlib.util.spec_from_file_location('bench_cfg', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    config = mod.config
+    config['quantizer_kwargs']['initialize'] = True            # data-dependent codebook init, as in a fresh run
+    config['dataloader_generator_kwargs']['seed'] = seed
+    torch.manual_seed(0)                                        # identical random-init weights on every rank
+    gen = get_dataloader_generator(config['dataset'], config['training_method'], config['dataloader_generator_kwargs'])
+    enc = get_encoder('/tmp/vqcpc_bench', gen, config)
+    tr = get_encoder_trainer('/tmp/vqcpc_bench', gen, config['training_method'], enc, config['auxiliary_networks_kwargs'])
+    tr.to('cuda')
+    tr.init_optimizers(config['lr'], config['schedule_lr'])
+    tr.train()
+    return tr, gen, config
+
+
+def run_ours(args):
+    from VQCPCB import distributed as vq_dist, ops, _native
+    rank, world, local = vq_dist.init_from_env()
+    torch.cuda.set_device(local)
+    ops.set_gemm_mode(args.mode)
+    B = args.batch
+    tr, gen, config = build_trainer(B, seed=1234 + rank)
+    train_loader, _, _ = gen.dataloaders(batch_size=B)
+    n_batches = 2
+    host_batches = [next(train_loader) for _ in range(n_batches)]                       # pinned host memory
+    dev_batches = [{k: v.cuda() for k, v in b.items()} for b in host_batches]           # resident in HBM
+    h2d = sum(host_batches[0][k].numel() * 8 for k in ('x_left', 'x_right', 'negative_samples'))
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        vq_dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also performs the one-time codebook init + TMA/func-attribute setup)
+    for i in range(args.warmup):
+        tr.step(dev_batches[i % n_batches], True, False)
+    barrier()
+
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE_GEMM = []
+    launches0 = _native.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        st = tr.step(dev_batches[i % n_batches], True, False)
+    e1.record()
+    barrier()
+    launches = _native.launch_count - launches0
+    prof = ops.PROFILE_GEMM
+    ops.PROFILE_GEMM = None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = t.item()
+    loss_val = float(st['loss'].item())
+
+    # ---- timed: end to end through the public call with HOST buffers + D2H loss read every step
+    e2e_steps = max(1, min(args.steps, 2))
+    tr.step(host_batches[0], True, False)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(e2e_steps):
+        st = tr.step(host_batches[i % n_batches], True, False)
+        _ = st['loss'].item()                                   # device -> host read of the step's result
+    e3.record()
+    barrier()
+    ms2 = e2.elapsed_time(e3)
+    t2 = torch.tensor([ms2], dtype=torch.float64, device='cuda')
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    ms2 = t2.item()
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    value = world * B * args.steps / (ms / 1000.0)
+    e2e_value = world * B * e2e_steps / (ms2 / 1000.0)
+    # dominant kernel: tensor-core GEMM launches profiled with CUDA events inside the timed region
+    tc = [(fl, a.elapsed_time(b)) for (kind, fl, a, b) in prof if kind == 'tc']
+    tc_ms = sum(x[1] for x in tc)
+    tc_flops = sum(x[0] for x in tc)
+    passes = 3 if args.mode == 'bf16x3' else 1
+    roof = None
+    if tc:
+        ach = tc_flops / (tc_ms / 1000.0) / 1e12
+        roof = dict(bound='tensor', kernel='gemm_tc_kernel (tcgen05 bf16x3)' if passes == 3 else 'gemm_tc_kernel (tcgen05 bf16)',
+                    achieved=ach, peak=pk['tflops'], unit='TFLOP/s', frac=ach / pk['tflops'], traffic=None,
+                    peak_source=pk['src'], launches=len(tc), avg_launch_ms=tc_ms / len(tc),
+                    share_of_step=tc_ms / ms, tensor_pipe_tflops=ach * passes,
+                    note=f'algorithmic 2MNK FLOPs; the tensor pipe executes {passes}x that (bf16 split passes)')
+    cpu_val, cpu_info = (None, None)
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_val, cpu_info = cpu_port_samples_per_sec(B_cpu=16, steps=2, warmup=1)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='bf16x3 (bf16 hi/lo split on tcgen05, fp32 accumulate; fp32 elsewhere)' if args.mode == 'bf16x3' else args.mode,
+                data='synthetic',
+                config=dict(workload=workload_name(B), global_batch=world * B, parallelism=f'dp{world}',
+                            gemm_mode=args.mode, l2='per-step working set (>10 GB of activations) far exceeds the 126 MB L2',
+                            blocks_per_pass=tr.max_blocks_per_pass, loss=loss_val),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, steps=e2e_steps),
+                gpu_launches=launches, clocks=sampler.summary(),
+                step_tensor_frac=dict(achieved_tflops=value / world * FLOPS_PER_SAMPLE / 1e12, peak=pk['tflops'],
+                                      frac=value / world * FLOPS_PER_SAMPLE / 1e12 / pk['tflops'],
+                                      note='whole step: samples/s/GPU x 103.8 GFLOP algorithmic / sustained bf16 peak'))
+    if roof:
+        line['roofline'] = roof
+    if cpu_val is not None:
+        line['cpu_baseline'] = dict(value=cpu_val, unit=UNIT, **cpu_info)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=4096)
+    ap.add_argument('--mode', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py --impl ours needs a CUDA device (no CPU fallback on the product path)')
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,129 @@
+"""GPU: the two GEMM kernels against an fp64 torch reference, every layout and fused epilogue, through the C-ABI."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_k, b_k, bias=None, residual=None, relu=False, mask=None, scale=None):
+    A = a.double() if a_k else a.double().t()
+    Bm = b.double().t() if b_k else b.double()
+    c = A @ Bm
+    if bias is not None:
+        c = c + bias.double()
+    if scale is not None:
+        c[:, :scale[1]] *= scale[0]
+    if residual is not None:
+        c = c + residual.double()
+    if relu:
+        c = c.clamp_min(0)
+    if mask is not None:
+        c = c * (mask > 0)
+    return c
+
+
+def _mk(M, N, K, a_k, b_k, gen):
+    a = torch.randn((M, K) if a_k else (K, M), generator=gen, device='cuda')
+    b = torch.randn((N, K) if b_k else (K, N), generator=gen, device='cuda')
+    return a, b
+
+
+LAYOUTS = [(True, True), (True, False), (False, False), (False, True)]
+SHAPES = [(128, 128, 64), (256, 384, 512), (200, 96, 136), (1, 32, 32), (515, 160, 72), (130, 1536, 512)]
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('a_k,b_k', LAYOUTS)
+def test_gemm_layouts_and_shapes(mode, a_k, b_k):
+    from VQCPCB import ops
+    ops.set_gemm_mode(mode)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(1)
+    tol = {'fp32': 2e-6, 'bf16x3': 3e-5, 'bf16': 1.5e-2}[mode]
+    worst = 0.0
+    for (M, N, K) in SHAPES:
+        a, b = _mk(M, N, K, a_k, b_k, gen)
+        out = ops.gemm(a, b, M, N, K, a_k, b_k)
+        torch.cuda.synchronize()
+        ref = _ref(a, b, a_k, b_k)
+        err = ((out.double() - ref).norm() / ref.norm()).item()
+        mx = ((out.double() - ref).abs().max() / ref.abs().max()).item()
+        print(f'{mode} a_k={a_k} b_k={b_k} {M}x{N}x{K}: rel {err:.2e} max {mx:.2e}')
+        worst = max(worst, err)
+        assert err < tol, (mode, a_k, b_k, M, N, K, err)
+    ops.set_gemm_mode('bf16x3')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_gemm_epilogues(mode):
+    from VQCPCB import ops
+    ops.set_gemm_mode(mode)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(2)
+    tol = 2e-6 if mode == 'fp32' else 3e-5
+    M, N, K = 300, 256, 192
+    a, b = _mk(M, N, K, True, True, gen)
+    bias = torch.randn(N, generator=gen, device='cuda')
+    res = torch.randn(M, N, generator=gen, device='cuda')
+    mask = torch.randn(M, N, generator=gen, device='cuda')
+
+    def check(name, out, ref):
+        torch.cuda.synchronize()
+        err = ((out.double() - ref).norm() / ref.norm()).item()
+        print(f'{mode} epilogue {name}: {err:.2e}')
+        assert err < tol, (name, err)
+
+    check('bias', ops.gemm(a, b, M, N, K, bias=bias), _ref(a, b, True, True, bias=bias))
+    check('bias+relu', ops.gemm(a, b, M, N, K, bias=bias, relu=True), _ref(a, b, True, True, bias=bias, relu=True))
+    check('bias+residual', ops.gemm(a, b, M, N, K, bias=bias, residual=res), _ref(a, b, True, True, bias=bias, residual=res))
+    check('relu_mask', ops.gemm(a, b, M, N, K, relu_mask=mask), _ref(a, b, True, True, mask=mask))
+    check('bias+scale_cols', ops.gemm(a, b, M, N, K, bias=bias, scale_cols=(0.125, 128)),
+          _ref(a, b, True, True, bias=bias, scale=(0.125, 128)))
+    # strided output (ldc > N) as used by the input projection
+    big = torch.full((M, N + 16), 7.0, device='cuda')
+    ops.gemm(a, b, M, N, K, out=big[:, :N], bias=bias)
+    check('strided out', big[:, :N], _ref(a, b, True, True, bias=bias))
+    assert bool((big[:, N:] == 7.0).all())
+    # accumulate and split-K (weight-gradient style: reduction over many rows)
+    a2, b2 = _mk(160, 192, 4096, False, False, gen)
+    base = torch.randn(160, 192, generator=gen, device='cuda')
+    acc = base.clone()
+    ops.gemm(a2, b2, 160, 192, 4096, False, False, out=acc, accumulate=True, ksplit=8)
+    check('splitk accumulate', acc, _ref(a2, b2, False, False) + base.double())
+    fresh = torch.full((160, 192), 3.0, device='cuda')
+    ops.gemm(a2, b2, 160, 192, 4096, False, False, out=fresh, ksplit=5)
+    check('splitk overwrite', fresh, _ref(a2, b2, False, False))
+    ops.set_gemm_mode('bf16x3')
+
+
+def test_bf16x3_split_reconstructs_fp32():
+    from VQCPCB import ops
+    x = torch.randn(257, 96, device='cuda') * 3
+    hi, lo = ops.split_bf16(x)
+    torch.cuda.synchronize()
+    assert hi.dtype == torch.bfloat16 and torch.equal(hi, x.to(torch.bfloat16))
+    rec = hi.float() + lo.float()
+    assert ((rec - x).abs() <= x.abs() * 2 ** -15).all()
+    # strided source (a column slice)
+    big = torch.randn(64, 512, device='cuda')
+    hi2, lo2 = ops.split_bf16(big[:, :496])
+    assert torch.equal(hi2, big[:, :496].to(torch.bfloat16))
+
+
+def test_gemm_large_m_persistent_schedule():
+    """More tiles than SMs x accumulator stages: exercises the smem ring / TMEM double buffering wrap-around."""
+    from VQCPCB import ops
+    ops.set_gemm_mode('bf16x3')
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(3)
+    M, N, K = 128 * 700 + 37, 512, 512
+    a, b = _mk(M, N, K, True, True, gen)
+    bias = torch.randn(N, generator=gen, device='cuda')
+    out = ops.gemm(a, b, M, N, K, bias=bias, relu=True)
+    torch.cuda.synchronize()
+    idx = torch.randint(0, M, (4096,), device='cuda')
+    ref = (a[idx].double() @ b.double().t() + bias.double()).clamp_min(0)
+    err = ((out[idx].double() - ref).norm() / ref.norm()).item()
+    print('large-M bf16x3 rel err', err)
+    assert err < 3e-5
+    assert torch.isfinite(out).all()

@@ -1,0 +1,218 @@
+"""GPU: every non-GEMM kernel through the C-ABI against the oracle / torch autograd on the same seeded inputs."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vqcpc_oracle as O
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_embed_fwd_bwd():
+    from VQCPCB import ops
+    torch.manual_seed(0)
+    tables = [torch.randn(65, 32, device='cuda', requires_grad=True) for _ in range(4)]
+    tok = torch.randint(0, 64, (37, 3, 16), device='cuda')
+    out = ops.EmbedFn.apply(tok, *tables)
+    ref = O.embed(tok.cpu(), [t.detach().cpu() for t in tables])
+    assert torch.equal(out.cpu(), ref)                               # pure gather: bit-exact
+    g = torch.randn_like(out)
+    out.backward(g)
+    tc = [t.detach().cpu().requires_grad_(True) for t in tables]
+    O.embed(tok.cpu(), tc).backward(g.cpu())
+    for a, b in zip(tables, tc):
+        assert rel_err(a.grad, b.grad) < 1e-5
+
+
+def test_posemb_fill_and_bwd():
+    from VQCPCB import ops
+    M, d, pe, S, V = 16 * 50, 512, 8, 16, 4
+    h = torch.zeros(M, d, device='cuda')
+    chan = torch.randn(V, pe, device='cuda')
+    evt = torch.randn(S // V, pe, device='cuda')
+    ops._native.call('vqcpc_posemb_fill', ops._p(h), d, d - 2 * pe, ops._p(chan), ops._p(evt), M, S, V, pe, ops._stream())
+    t = torch.arange(M, device='cuda') % S
+    assert torch.equal(h[:, d - 2 * pe:d - pe], chan[t % V]) and torch.equal(h[:, d - pe:], evt[t // V])
+    assert h[:, :d - 2 * pe].abs().sum() == 0
+    dh = torch.randn(M, d, device='cuda')
+    dchan, devt = torch.zeros_like(chan), torch.zeros_like(evt)
+    ops._native.call('vqcpc_posemb_bwd', ops._p(dh), d, d - 2 * pe, ops._p(dchan), ops._p(devt), M, S, V, pe, ops._stream())
+    rc = torch.zeros_like(chan).index_add_(0, t % V, dh[:, d - 2 * pe:d - pe])
+    re = torch.zeros_like(evt).index_add_(0, t // V, dh[:, d - pe:])
+    assert rel_err(dchan, rc) < 1e-5 and rel_err(devt, re) < 1e-5
+
+
+@pytest.mark.parametrize('M', [1, 77, 4099])
+def test_layernorm_fwd_bwd(M):
+    from VQCPCB import ops
+    torch.manual_seed(1)
+    d = 512
+    y = (torch.randn(M, d, device='cuda') * 2 + 0.5).requires_grad_(True)
+    g = (1 + 0.1 * torch.randn(d, device='cuda')).requires_grad_(True)
+    b = (0.1 * torch.randn(d, device='cuda')).requires_grad_(True)
+    out, mean, rstd = ops.layernorm_fwd(y.detach(), g.detach(), b.detach())
+    ref = F.layer_norm(y.double(), (d,), g.double(), b.double(), 1e-5)
+    assert rel_err(out, ref) < 1e-6
+    go = torch.randn(M, d, device='cuda')
+    ref.backward(go.double())
+    dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    dy = ops.layernorm_bwd(go, y.detach(), mean, rstd, g.detach(), dg, db)
+    assert rel_err(dy, y.grad) < 2e-6 and rel_err(dg, g.grad) < 2e-6 and rel_err(db, b.grad) < 2e-6
+
+
+def test_subsample_colsum_selu_reduce():
+    from VQCPCB import ops
+    P, L, f, d = 33, 16, 4, 512
+    x = torch.randn(P * L, d, device='cuda')
+    out = torch.empty(P * L // f, d, device='cuda')
+    ops._native.call('vqcpc_subsample_fwd', ops._p(x), ops._p(out), P, L, f, d, ops._stream())
+    assert torch.equal(out.view(P, L // f, d), x.view(P, L, d)[:, ::f])
+    dx = torch.empty_like(x)
+    ops._native.call('vqcpc_subsample_bwd', ops._p(out), ops._p(dx), P, L, f, d, ops._stream())
+    ref = torch.zeros(P, L, d, device='cuda')
+    ref[:, ::f] = out.view(P, L // f, d)
+    assert torch.equal(dx.view(P, L, d), ref)
+    acc = torch.ones(d, device='cuda')
+    ops.colsum(x, acc)
+    assert rel_err(acc, 1 + x.double().sum(0)) < 1e-5
+    xs = torch.randn(1000, 37, device='cuda').requires_grad_(True)
+    y = ops.SeluFn.apply(xs)
+    assert rel_err(y, F.selu(xs.double())) < 1e-6
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xd = xs.detach().double().requires_grad_(True)
+    F.selu(xd).backward(gy.double())
+    assert rel_err(xs.grad, xd.grad) < 1e-6
+    v = torch.randn(100003, device='cuda')
+    assert abs(ops.reduce_sum(v, 0.5).item() - 0.5 * v.double().sum().item()) < 1e-3
+
+
+@pytest.mark.parametrize('L,P', [(16, 37), (4, 37), (4, 3), (8, 5), (2, 9), (1, 11)])
+def test_attention_fwd_bwd_vs_oracle(L, P):
+    from VQCPCB import ops
+    torch.manual_seed(L * 100 + P)
+    H, hd = 8, 64
+    d = H * hd
+    qkv = torch.randn(P * L, 3 * d, device='cuda') * 0.7
+    e1 = torch.randn(H * L, hd, device='cuda') * 0.5
+    e2 = torch.randn(H * L, hd, device='cuda') * 0.5
+    out, probs = ops.attn_fwd(qkv, e1, e2, P, L, H, hd)
+    torch.cuda.synchronize()
+
+    def oracle(qkv_, e1_, e2_):
+        q, k, v = qkv_.view(P, L, 3, H, hd).unbind(2)
+        q, k, v = (t.transpose(1, 2) for t in (q, k, v))            # (P, H, L, hd); q already "scaled"
+        s = q @ k.transpose(-1, -2) + O.rel_bias(q, e1_, e2_)
+        a = torch.softmax(s, -1)
+        return (a @ v).transpose(1, 2).reshape(P * L, d), a
+
+    qd, e1d, e2d = (t.detach().double().cpu().requires_grad_(True) for t in (qkv, e1, e2))
+    ro, ra = oracle(qd, e1d, e2d)
+    assert rel_err(out, ro) < 2e-6, rel_err(out, ro)
+    assert rel_err(probs, ra) < 2e-6
+    go = torch.randn(P * L, d, device='cuda')
+    ro.backward(go.double().cpu())
+    de1, de2 = torch.zeros_like(e1), torch.zeros_like(e2)
+    q_scale = 0.125
+    dqkv = ops.attn_bwd(qkv, e1, e2, probs, go, de1, de2, P, L, H, hd, q_scale)
+    torch.cuda.synchronize()
+    ref = qd.grad.clone().view(P * L, 3, d)
+    ref[:, 0] *= q_scale                                              # kernel returns grad wrt the unscaled projection
+    assert rel_err(dqkv, ref.view(P * L, 3 * d)) < 5e-6, rel_err(dqkv, ref.view(P * L, 3 * d))
+    assert rel_err(de1, e1d.grad) < 5e-6 and rel_err(de2, e2d.grad) < 5e-6
+
+
+def test_quantizer_bit_exact_vs_reference_golden(golden_dir):
+    from VQCPCB.quantizer.vector_quantizer import ProductVectorQuantizer
+    gold = torch.load(os.path.join(golden_dir, 'quantizer.pt'), weights_only=False)
+    for name, c in gold.items():
+        vq = ProductVectorQuantizer(c['Kc'], c['D'], 0.25, c['ncb'], False, False, c['squared']).cuda()
+        vq.load_state_dict({f'embeddings.{i}': b for i, b in enumerate(c['books'])}, strict=True)
+        vq.eval()
+        vq.track_usage(True)
+        x = c['x'].cuda().requires_grad_(True)
+        zsg, idx, loss = vq(x)
+        assert torch.equal(idx.cpu(), c['idx'].long()), f'{name}: code indices differ from the reference'
+        assert torch.equal(zsg.detach().cpu(), c['zsg']), f'{name}: straight-through output not bit-exact'
+        assert rel_err(loss, c['loss']) < 1e-6
+        ((loss * c['gl'].cuda()).sum() + (zsg * c['gz'].cuda()).sum()).backward()
+        assert rel_err(x.grad, c['dx']) < 1e-5
+        for p, db in zip(vq.embeddings, c['dbooks']):
+            assert rel_err(p.grad, db) < 1e-4
+        counts = vq.usage_counts.view(c['ncb'], c['Kc']).cpu()
+        for cb in range(c['ncb']):
+            assert torch.equal(counts[cb], torch.bincount(c['idx'].long()[..., cb].reshape(-1), minlength=c['Kc']).int())
+
+
+def test_quantizer_full_size_properties():
+    """BASELINE size (557 056 vectors, K=512, D=3): idempotence (codes quantise to themselves, zero loss) and the
+    histogram sums to the vector count."""
+    from VQCPCB.quantizer.vector_quantizer import ProductVectorQuantizer
+    torch.manual_seed(0)
+    n, Kc, D = 557056, 512, 3
+    vq = ProductVectorQuantizer(Kc, D, 0.25, 1, False, False, True).cuda().eval()
+    vq.track_usage(True)
+    x = torch.randn(n // 8, 8, D, device='cuda') * 3
+    zsg, idx, loss = vq(x)
+    assert int(vq.usage_counts.sum()) == n
+    q = vq.embeddings[0][idx.view(-1)].view_as(x)
+    d_best = ((x - q) ** 2).sum(-1)
+    probe = torch.randint(0, Kc, (n // 8, 8), device='cuda')
+    d_probe = ((x - vq.embeddings[0][probe]) ** 2).sum(-1)
+    assert bool((d_best <= d_probe + 1e-6).all())                      # no probed code is closer than the chosen one
+    z2, idx2, loss2 = vq(q.detach())
+    assert torch.equal(idx2, idx) or bool((loss2 == 0).all())          # duplicates may re-route, distance stays 0
+    assert float(loss2.abs().max()) == 0.0
+
+
+def test_infonce_fwd_bwd_vs_oracle():
+    from VQCPCB import ops
+    torch.manual_seed(3)
+    B, N, KR, zd, cd = 19, 15, 8, 32, 32
+    c = torch.randn(B, cd, device='cuda', requires_grad=True)
+    W = (torch.randn(zd, cd, KR, device='cuda') * 0.25).requires_grad_(True)
+    yp = torch.randn(B, KR, zd, device='cuda', requires_grad=True)
+    yn = torch.randn(B, N, KR, zd, device='cuda')
+    yn[3, 5] = yp[3].detach()                                            # exact tie: negative == positive
+    yn.requires_grad_(True)
+    total, pos, neg, correct = ops.InfoNCEFn.apply(c, W, yp, yn)
+    (total / B).backward()
+    cd_, Wd, ypd, ynd = (t.detach().double().cpu().requires_grad_(True) for t in (c, W, yp, yn))
+    rpos = O.fks(cd_, ypd, Wd)
+    rneg = torch.stack([O.fks(cd_, ynd[:, n], Wd) for n in range(N)], 2)
+    rl = O.nce_loss(rpos, rneg)
+    rl.backward()
+    assert abs((total / B).item() - rl.item()) < 1e-5 * abs(rl.item())
+    assert rel_err(pos, rpos) < 1e-6 and rel_err(neg, rneg) < 1e-6
+    assert not bool(correct[3].any())                                    # ties are never "correct"
+    rc = (rpos > rneg.max(2)[0])
+    near = (rpos - rneg.max(2)[0]).abs() < 1e-5
+    assert bool(((correct.cpu() != 0) == rc)[~near].all())
+    for a, b in ((c, cd_), (W, Wd), (yp, ypd), (yn, ynd)):
+        assert rel_err(a.grad, b.grad) < 2e-5, rel_err(a.grad, b.grad)
+
+
+def test_clip_adam_matches_oracle():
+    from VQCPCB.optim import FlatParams, FusedClipAdam
+    torch.manual_seed(5)
+    ps = [torch.nn.Parameter(torch.randn(300, 7, device='cuda')), torch.nn.Parameter(torch.randn(1001, device='cuda'))]
+    prm = {str(i): p.detach().cpu().clone() for i, p in enumerate(ps)}
+    opt = FusedClipAdam(FlatParams(ps), lr=1e-3)
+    m = v = None
+    for step in range(1, 4):
+        grads = {str(i): torch.randn_like(p).cpu() * (10.0 if step == 1 else 0.01) for i, p in enumerate(ps)}
+        opt.zero_grad()
+        for i, p in enumerate(ps):
+            p.grad.copy_(grads[str(i)])
+        opt.step(max_norm=5.0)
+        clipped, gn = O.clip_grad_norm(grads, 5.0)
+        if m is None:
+            m = {k: torch.zeros_like(t) for k, t in prm.items()}
+            v = {k: torch.zeros_like(t) for k, t in prm.items()}
+        prm, m, v = O.adam_step(prm, clipped, m, v, step, 1e-3)
+        assert abs(opt.gnorm_sq.item() ** 0.5 - gn.item()) < 1e-4 * gn.item()
+        for i, p in enumerate(ps):
+            assert rel_err(p, prm[str(i)]) < 1e-6, (step, i)

@@ -18,6 +18,7 @@ from . import _native
 EPI_BIAS, EPI_RELU, EPI_ACCUMULATE, EPI_RESIDUAL, EPI_RELU_MASK, EPI_SCALE_COLS = 1, 2, 4, 8, 16, 64
 
 _GEMM_MODE = 'bf16x3'
+PROFILE_GEMM = None         # bench.py sets this to a list: every GEMM launch is bracketed by CUDA events on its stream
 _WSPLIT_CACHE = {}          # id(param storage) -> (version, hi, lo)
 
 
@@ -128,7 +129,17 @@ def gemm(a, b, M, N, K, a_kmajor=True, b_kmajor=True, out=None, bias=None, resid
         alpha, ncols = scale_cols
     ldr = res.stride(0) if res is not None else 0
     assert a.stride(1) == 1 and b.stride(1) == 1
-    if _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor):
+    prof = PROFILE_GEMM
+    use_tc = _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor)
+    if prof is not None and use_tc:
+        if a_split is None:
+            a_split = split_bf16(a)
+        if b_split is None:
+            b_split = weight_split(b) if b_is_weight else split_bf16(b)
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    if use_tc:
         if a_split is None:
             a_split = split_bf16(a)
         if b_split is None:
@@ -140,6 +151,10 @@ def gemm(a, b, M, N, K, a_kmajor=True, b_kmajor=True, out=None, bias=None, resid
     else:
         _native.call('vqcpc_gemm_f32', int(a_kmajor), int(b_kmajor), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0),
                      _p(out), out.stride(0), _p(bias), _p(res), ldr, flags, float(alpha), int(ncols), int(ksplit), _stream())
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append(('tc' if use_tc else 'simt', 2.0 * M * N * K, ev0, ev1))
     return out
 
 
