@@ -167,7 +167,7 @@ assert torch.allclose(sums, torch.tensor([1.5, 3.0, 4.5])) and torch.allclose(co
 assert counts.tolist() == [3, 0, 6, 0]
 assert vq_dist.shard_seed(1234) == 1234 + rank
 vq_dist.barrier()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank{rank}ok\n"); sys.stdout.flush()
 '''
 
 
@@ -180,4 +180,4 @@ def test_data_parallel_allreduce_gloo_world2(tmp_path):
            '--master-port', str(port), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
+    assert 'rank0ok' in r.stdout and 'rank1ok' in r.stdout
