@@ -50,7 +50,7 @@ def build_reference(R, cfg, prm, model_dir='/tmp/vqcpc_golden'):
     gen = types.SimpleNamespace(num_blocks_right=cfg.KR)
     tr = R['Trainer'](model_dir, gen, enc,
                       dict(output_dim=cfg.c_dim, hidden_size=cfg.c_hidden, num_layers=cfg.c_layers, dropout=0.0,
-                           bidirectional=False), cfg.quantization_weighting)
+                           bidirectional=bool(cfg.get('bidirectional', False))), cfg.quantization_weighting)
     files = P.split_by_file(prm)
     dp.load_state_dict(files['data_processor'], strict=True)
     down.load_state_dict(files['downscaler'], strict=True)
@@ -59,6 +59,9 @@ def build_reference(R, cfg, prm, model_dir='/tmp/vqcpc_golden'):
         up.load_state_dict(files['upscaler'], strict=True)
     tr.c_module.load_state_dict(files['c_module'], strict=True)
     tr.fks_module.load_state_dict(files['fks_module'], strict=True)
+    if cfg.get('bidirectional', False):
+        tr.c_module_back.load_state_dict(files['c_module_back'], strict=True)
+        tr.fks_module_back.load_state_dict(files['fks_module_back'], strict=True)
     return enc, tr
 
 
@@ -66,7 +69,8 @@ def ref_named_params(enc, tr):
     out = {}
     for f, mod in [('data_processor', enc.data_processor), ('downscaler', enc.downscaler),
                    ('quantizer', enc.quantizer), ('upscaler', enc.upscaler),
-                   ('c_module', tr.c_module), ('fks_module', tr.fks_module)]:
+                   ('c_module', tr.c_module), ('fks_module', tr.fks_module),
+                   ('c_module_back', tr.c_module_back), ('fks_module_back', getattr(tr, 'fks_module_back', None))]:
         if mod is None:
             continue
         for k, p in mod.named_parameters():
@@ -92,6 +96,8 @@ CASES = {
     # (num_codebooks must be 1 here: the reference trainer's index .view at vqcpc_encoder_trainer.py:207 raises otherwise)
     'noup_d32': dict(cfg=dict(codebook_size=16, codebook_dim=32, num_codebooks=1, upscaler=False, KL=2, KR=2,
                               squared_l2_norm=False), B=4),
+    # bidirectional c-net (encoder_random_16C.py style) incl. the reference's backward-negative indexing (quirk Q1)
+    'cfg1_bidir': dict(cfg=dict(codebook_size=16, KL=2, KR=2, bidirectional=True), B=6),
 }
 
 

@@ -72,16 +72,17 @@ def param_shapes(cfg):
         out['upscaler.mlp.3.bias'] = ((cfg.z_dim,), ('uniform', 1 / math.sqrt(cfg.up_hidden)))
         zd = cfg.z_dim
     Hh = cfg.c_hidden
-    for l in range(cfg.c_layers):
-        inp = zd if l == 0 else Hh
-        b = 1 / math.sqrt(Hh)
-        out[f'c_module.g_ar_fwd.weight_ih_l{l}'] = ((3 * Hh, inp), ('uniform', b))
-        out[f'c_module.g_ar_fwd.weight_hh_l{l}'] = ((3 * Hh, Hh), ('uniform', b))
-        out[f'c_module.g_ar_fwd.bias_ih_l{l}'] = ((3 * Hh,), ('uniform', b))
-        out[f'c_module.g_ar_fwd.bias_hh_l{l}'] = ((3 * Hh,), ('uniform', b))
-    out['c_module.output_linear.weight'] = ((cfg.c_dim, Hh), ('uniform', 1 / math.sqrt(Hh)))
-    out['c_module.output_linear.bias'] = ((cfg.c_dim,), ('uniform', 1 / math.sqrt(Hh)))
-    out['fks_module.W'] = ((zd, cfg.c_dim, cfg.KR), ('normal', 0.25))
+    for suffix in (['', '_back'] if cfg.get('bidirectional', False) else ['']):
+        for l in range(cfg.c_layers):
+            inp = zd if l == 0 else Hh
+            b = 1 / math.sqrt(Hh)
+            out[f'c_module{suffix}.g_ar_fwd.weight_ih_l{l}'] = ((3 * Hh, inp), ('uniform', b))
+            out[f'c_module{suffix}.g_ar_fwd.weight_hh_l{l}'] = ((3 * Hh, Hh), ('uniform', b))
+            out[f'c_module{suffix}.g_ar_fwd.bias_ih_l{l}'] = ((3 * Hh,), ('uniform', b))
+            out[f'c_module{suffix}.g_ar_fwd.bias_hh_l{l}'] = ((3 * Hh,), ('uniform', b))
+        out[f'c_module{suffix}.output_linear.weight'] = ((cfg.c_dim, Hh), ('uniform', 1 / math.sqrt(Hh)))
+        out[f'c_module{suffix}.output_linear.bias'] = ((cfg.c_dim,), ('uniform', 1 / math.sqrt(Hh)))
+        out[f'fks_module{suffix}.W'] = ((zd, cfg.c_dim, cfg.KR), ('normal', 0.25))
     return out
 
 

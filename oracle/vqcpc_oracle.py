@@ -41,7 +41,7 @@ def default_cfg(**over):
         codebook_size=16, codebook_dim=3, num_codebooks=1, commitment_cost=0.25, squared_l2_norm=True,
         upscaler=True, up_hidden=512, z_dim=32,
         c_hidden=512, c_layers=2, c_dim=32,
-        KL=2, KR=2, N=15, quantization_weighting=0.5,
+        KL=2, KR=2, N=15, quantization_weighting=0.5, bidirectional=False,
     )
     c.update(over)
     return c
@@ -276,10 +276,23 @@ def trainer_forward(batch, prm, cfg):
     negs = torch.stack([fks(c, zn[:, n], W) for n in range(N)], dim=2)                # :245-263 (B, KR, N)
     correct = pos > negs.max(2)[0]                                                    # :269
     nce = nce_loss(pos, negs)                                                         # :272
-    # quantization_loss vqcpc_helper.py:32-51: mean over cat[left.sum(1), right.sum(1), neg.sum(all)] (3B rows)
-    ql = torch.cat([ql_l.sum(1), ql_r.sum(1), ql_n.view(B, -1).sum(1)], 0).mean()
-    loss = nce + cfg.quantization_weighting * ql                                      # :307
     acc = correct.sum(0).float() / B                                                  # :337
+    ql_parts = [ql_l.sum(1), ql_r.sum(1), ql_n.view(B, -1).sum(1)]
+    if cfg.get('bidirectional', False):                                               # :277-296
+        znb, idx_nb, ql_nb = encoder_forward(batch['negative_samples_back'].reshape(B * N * KR, T, V), prm, cfg)  # :211-225
+        c_back = gru_c(zr.flip(dims=[1]), prm, cfg, pre='c_module_back.')             # :278-279
+        Wb = prm['fks_module_back.W']
+        pos_b = fks(c_back, zl, Wb)                                                   # :283 (left codes NOT flipped)
+        # quirk Q1: the (B, N, KR, 1, z) tensor goes into FksModule as is -> viewed (N*B, KR, z) b-major while
+        # c_back.repeat(N, 1) is n-major (:285-286, vqcpc_helper.py:96); then .view(N, B, KR).permute(1, 2, 0) (:288-291)
+        f = fks(c_back.repeat(N, 1), znb.reshape(B * N, KR, -1), Wb)
+        negs_b = f.view(N, B, KR).permute(1, 2, 0)
+        nce = nce + nce_loss(pos_b, negs_b)                                           # :296
+        acc = (acc + (pos_b > negs_b.max(2)[0]).sum(0).float() / B) / 2                # :338-339
+        ql_parts.append(ql_nb.view(B, -1).sum(1))
+    # quantization_loss vqcpc_helper.py:32-51: mean over cat[left.sum(1), right.sum(1), neg.sum(all) (, neg_back)]
+    ql = torch.cat(ql_parts, 0).mean()
+    loss = nce + cfg.quantization_weighting * ql                                      # :307
     return dict(loss=loss, nce=nce, qloss=ql, accuracy=acc, pos=pos, neg=negs, c=c,
                 idx_left=idx_l, idx_right=idx_r, idx_negative=idx_n,
                 z_left=zl, z_right=zr, z_negative=zn)

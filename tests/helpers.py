@@ -22,7 +22,9 @@ def build_product_encoder(cfg, model_dir='/tmp/vqcpc_b200_test'):
     return Encoder(model_dir, dp, down, vq, up)
 
 
-def build_product_trainer(cfg, model_dir='/tmp/vqcpc_b200_test', bidirectional=False, device='cuda'):
+def build_product_trainer(cfg, model_dir='/tmp/vqcpc_b200_test', bidirectional=None, device='cuda'):
+    if bidirectional is None:
+        bidirectional = bool(cfg.get('bidirectional', False))
     from VQCPCB.vqcpc_encoder_trainer import VQCPCEncoderTrainer
     enc = build_product_encoder(cfg, model_dir)
     gen = types.SimpleNamespace(num_blocks_right=cfg.KR)
@@ -37,7 +39,8 @@ def product_named_params(trainer):
     enc = trainer.encoder
     out = {}
     for f, mod in [('data_processor', enc.data_processor), ('downscaler', enc.downscaler), ('quantizer', enc.quantizer),
-                   ('upscaler', enc.upscaler), ('c_module', trainer.c_module), ('fks_module', trainer.fks_module)]:
+                   ('upscaler', enc.upscaler), ('c_module', trainer.c_module), ('fks_module', trainer.fks_module),
+                   ('c_module_back', trainer.c_module_back), ('fks_module_back', getattr(trainer, 'fks_module_back', None))]:
         if mod is None:
             continue
         for k, p in mod.named_parameters():
@@ -51,7 +54,8 @@ def load_params_into(trainer, prm):
     enc = trainer.encoder
     dev = trainer.fks_module.W.device
     mods = {'data_processor': enc.data_processor, 'downscaler': enc.downscaler, 'quantizer': enc.quantizer,
-            'upscaler': enc.upscaler, 'c_module': trainer.c_module, 'fks_module': trainer.fks_module}
+            'upscaler': enc.upscaler, 'c_module': trainer.c_module, 'fks_module': trainer.fks_module,
+            'c_module_back': trainer.c_module_back, 'fks_module_back': getattr(trainer, 'fks_module_back', None)}
     for f, sd in files.items():
         mods[f].load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
     from VQCPCB import ops
