@@ -144,15 +144,17 @@ def test_training_step_vs_reference_and_oracle(golden_dir, name, mode):
         worst = max(worst, (e_cuda, k))
         assert e_cuda <= max(2e-3, 4 * e_o32), f'{k}: cuda {e_cuda:.2e} vs oracle32 {e_o32:.2e}'
     print(f'[{name}/{mode}] worst grad rel err vs fp64 oracle: {worst[0]:.2e} ({worst[1]})')
-    # Adam update (clip 5.0 inside): compare the parameter deltas with the fp32 oracle's
+    # Adam update (clip 5.0 inside).  A first Adam step moves every element by ~lr * sign(g): compare the deltas on the
+    # elements whose gradient is not vanishing (sign flips of ~0 gradients are noise), element-wise.
     for k, p in named.items():
         d_cuda = (p.detach() - before[k]).cpu()
         d_ref = newp32[k] - prm[k]
-        if g64[k].norm() < 1e-6 * gn64.item():
+        gk = g64[k].float()
+        mask = gk.abs() > 1e-2 * gk.abs().max().clamp_min(1e-30)
+        if mask.sum() == 0:
             continue
-        # sign(g) * lr for a first Adam step: elements whose gradient is ~0 may flip; compare in norm
-        assert rel_err(d_cuda, d_ref) < 5e-2, (k, rel_err(d_cuda, d_ref))
-        assert abs(d_cuda.abs().max().item() - lr) < 0.05 * lr
+        assert rel_err(d_cuda[mask], d_ref[mask]) < 2e-2, (k, rel_err(d_cuda[mask], d_ref[mask]))
+        assert d_cuda.abs().max().item() <= 1.001 * lr
     ops.set_gemm_mode('bf16x3')
 
 
