@@ -22,6 +22,20 @@ from .. import ops
 _LAYER_KEYS = ('wqkv', 'bqkv', 'wo', 'bo', 'e1', 'e2', 'w1', 'b1', 'w2', 'b2', 'g1', 'be1', 'g2', 'be2')
 
 
+def _subsample(x, P, L, factor, d):
+    """rows (block, token) -> rows (block, token // factor) keeping token % factor == 0."""
+    out = torch.empty(P * (L // factor), d, dtype=torch.float32, device=x.device)
+    ops._native.call('vqcpc_subsample_fwd', ops._p(x), ops._p(out), P, L, factor, d, ops._stream())
+    return out
+
+
+def _subsample_bwd(dout, P, L, factor, d):
+    """adjoint of ``_subsample``: scatter into all L rows, zeros elsewhere."""
+    dx = torch.empty(P * L, d, dtype=torch.float32, device=dout.device)
+    ops._native.call('vqcpc_subsample_bwd', ops._p(dout), ops._p(dx), P, L, factor, d, ops._stream())
+    return dx
+
+
 class EncoderStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb2d, meta, *params):
@@ -45,23 +59,32 @@ class EncoderStackFn(torch.autograd.Function):
         x, L, li = h, S, 0
         q_scale = float(hd) ** -0.5
         for factor, nl in zip(factors, layers_per_stack):
-            M = P * L
-            for _ in range(nl):
+            for layer_in_stack in range(nl):
                 lp = dict(zip(_LAYER_KEYS, layer_params[li * 14:(li + 1) * 14]))
                 li += 1
+                # Exact dead-row elimination: after the LAST layer of a stack only every ``factor``-th token survives
+                # (relative_transformer_downscaler.py:124), and a token's post-attention path (out-proj, LN, FFN, LN)
+                # is row-wise, so that layer runs it on the surviving rows only.  K/V (hence the in-proj and the
+                # attention itself) still see all L tokens.  Saves ~31 % of the encoder FLOPs with identical results.
+                last = (layer_in_stack == nl - 1) and factor > 1
                 qkv = ops.linear_fwd(x, lp['wqkv'], lp['bqkv'], scale_cols=(q_scale, d))
                 o, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train)
-                y1 = ops.linear_fwd(o, lp['wo'], lp['bo'], residual=x)
+                if last:
+                    o_k = _subsample(o, P, L, factor, d)
+                    x_k = _subsample(x, P, L, factor, d)
+                else:
+                    o_k, x_k = o, x
+                y1 = ops.linear_fwd(o_k, lp['wo'], lp['bo'], residual=x_k)
                 x1, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'])
                 hm = ops.linear_fwd(x1, lp['w1'], lp['b1'], relu=True)
                 y2 = ops.linear_fwd(hm, lp['w2'], lp['b2'], residual=x1)
                 x2, mean2, rstd2 = ops.layernorm_fwd(y2, lp['g2'], lp['be2'])
                 if train:
-                    saved.append((x, qkv, probs, o, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, L))
+                    saved.append((x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, L, last))
                 x = x2
-            xs = torch.empty(P * (L // factor), d, dtype=torch.float32, device=dev)
-            ops._native.call('vqcpc_subsample_fwd', ops._p(x), ops._p(xs), P, L, factor, d, ops._stream())
-            x, L = xs, L // factor
+            if nl == 0 or factor == 1:
+                x = _subsample(x, P, L, factor, d) if factor > 1 else x
+            L = L // factor
         assert L == 1, 'the product of downscale_factors must equal the block length'
         z = ops.linear_fwd(x, w_out, b_out)
 
@@ -93,15 +116,16 @@ class EncoderStackFn(torch.autograd.Function):
         li = len(ctx.saved)
         for factor, nl in reversed(list(zip(factors, layers_per_stack))):
             Lf = L * factor
-            dfull = torch.empty(P * Lf, d, dtype=torch.float32, device=dz.device)
-            ops._native.call('vqcpc_subsample_bwd', ops._p(dx), ops._p(dfull), P, Lf, factor, d, ops._stream())
-            dx, L = dfull, Lf
+            if nl == 0 and factor > 1:
+                dx = _subsample_bwd(dx, P, Lf, factor, d)
+            L = Lf
             for _ in range(nl):
                 li -= 1
                 lp = dict(zip(_LAYER_KEYS, layer_params[li * 14:(li + 1) * 14]))
                 gp = dict(zip(_LAYER_KEYS, g_layers[li * 14:(li + 1) * 14]))
-                x, qkv, probs, o, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls = ctx.saved[li]
+                x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls, last = ctx.saved[li]
                 assert Ls == L
+                # (for a stack's last layer everything down to the out-proj lives on the surviving rows only)
                 # LN2 -> dy2 (flows to the FFN branch and, as the residual, to x1)
                 dy2 = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'])
                 # FFN2: dhm = (dy2 W2) * (hm > 0)
@@ -111,7 +135,10 @@ class EncoderStackFn(torch.autograd.Function):
                 del dhm
                 dy1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'])
                 # out-proj
-                do = ops.linear_bwd(o, lp['wo'], dy1, gp['wo'], gp['bo'])
+                do = ops.linear_bwd(o_k, lp['wo'], dy1, gp['wo'], gp['bo'])
+                if last:                       # scatter back to all L rows (zeros for the dropped query rows)
+                    do = _subsample_bwd(do, P, L, factor, d)
+                    dy1 = _subsample_bwd(dy1, P, L, factor, d)
                 dqkv = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale)
                 # in-proj: dx = dqkv Wqkv + dy1 (residual path)
                 dx = ops.linear_bwd(x, lp['wqkv'], dqkv, gp['wqkv'], gp['bqkv'], dx_residual=dy1)
