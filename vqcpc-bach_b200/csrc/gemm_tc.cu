@@ -128,8 +128,11 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_kmajor, bool b_kmajor) 
 
 struct TcParams {
   int M, N, K;
-  float* C;
+  float* C;                       // may be NULL when only the split outputs are wanted
   int ldc;
+  __nv_bfloat16* out_hi;          // optional fused split of the result (operand of the next GEMM), may be NULL
+  __nv_bfloat16* out_lo;
+  int ldo;
   EpilogueParams ep;
   int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
 };
@@ -283,30 +286,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tmem_ld_wait();
         const int col0 = n0 + ch * 32;
         if (row < p.M && col0 < p.N) {
-          float* dst = p.C + (size_t)row * p.ldc + col0;
-          const bool full = (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-          if (full && !(p.ep.flags & EPI_ATOMIC)) {
+          float* dst = p.C ? p.C + (size_t)row * p.ldc + col0 : nullptr;
+          const int fl = p.ep.flags;
+          const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                               (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                              ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                               (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                               (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                                (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+          if (col0 + 32 <= p.N && aligned && !(fl & EPI_ATOMIC)) {
+            // ---- fast path: 32 contiguous columns of one row per thread, all accesses 16-byte vectors
+            float v[32];
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 o;
-              o.x = epilogue_apply(__uint_as_float(r[v * 4 + 0]), row, col0 + v * 4 + 0, p.ep, first_split);
-              o.y = epilogue_apply(__uint_as_float(r[v * 4 + 1]), row, col0 + v * 4 + 1, p.ep, first_split);
-              o.z = epilogue_apply(__uint_as_float(r[v * 4 + 2]), row, col0 + v * 4 + 2, p.ep, first_split);
-              o.w = epilogue_apply(__uint_as_float(r[v * 4 + 3]), row, col0 + v * 4 + 3, p.ep, first_split);
-              if (p.ep.flags & EPI_ACCUMULATE) {
-                float4 c = ld4(dst + v * 4);
-                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (first_split && (fl & EPI_BIAS)) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + q4);
+                v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
               }
-              st4(dst + v * 4, o);
+            }
+            if (fl & EPI_SCALE_COLS) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.ep.scale_ncols) ? v[j] * p.ep.alpha : v[j];
+            }
+            if (first_split && (fl & EPI_RESIDUAL)) {
+              const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 b = __ldg(rp + q4);
+                v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
+              }
+            }
+            if (fl & EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (fl & EPI_RELU_MASK) {
+              if (fl & EPI_MASK_BF16) {
+                const uint4* mp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                  uint4 mv = __ldg(mp + q8);
+                  const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                  for (int h = 0; h < 4; ++h) {
+                    // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                    uint32_t lo16 = w[h] & 0xFFFFu, hi16 = w[h] >> 16;
+                    if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2] = 0.f;
+                    if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2 + 1] = 0.f;
+                  }
+                }
+              } else {
+                const float4* mp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                  float4 b = __ldg(mp + q4);
+                  if (!(b.x > 0.f)) v[q4 * 4] = 0.f;
+                  if (!(b.y > 0.f)) v[q4 * 4 + 1] = 0.f;
+                  if (!(b.z > 0.f)) v[q4 * 4 + 2] = 0.f;
+                  if (!(b.w > 0.f)) v[q4 * 4 + 3] = 0.f;
+                }
+              }
+            }
+            if (dst) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 o = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+                if (fl & EPI_ACCUMULATE) {
+                  float4 c = ld4(dst + q4 * 4);
+                  o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                  v[q4 * 4] = o.x; v[q4 * 4 + 1] = o.y; v[q4 * 4 + 2] = o.z; v[q4 * 4 + 3] = o.w;
+                }
+                st4(dst + q4 * 4, o);
+              }
+            }
+            if (p.out_hi) {
+              uint32_t hw[16], lw[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              uint4* hp = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldo + col0);
+              uint4* lp = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldo + col0);
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                hp[q8] = make_uint4(hw[q8 * 4], hw[q8 * 4 + 1], hw[q8 * 4 + 2], hw[q8 * 4 + 3]);
+                lp[q8] = make_uint4(lw[q8 * 4], lw[q8 * 4 + 1], lw[q8 * 4 + 2], lw[q8 * 4 + 3]);
+              }
             }
           } else {
+            // ---- edge / split-K path: element-wise
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (col0 + j < p.N) {
                 float v = epilogue_apply(__uint_as_float(r[j]), row, col0 + j, p.ep, first_split);
-                if (p.ep.flags & EPI_ATOMIC) atomicAdd(dst + j, v);
-                else if (p.ep.flags & EPI_ACCUMULATE) dst[j] += v;
-                else dst[j] = v;
+                if (dst) {
+                  if (fl & EPI_ATOMIC) atomicAdd(dst + j, v);
+                  else if (fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
+                  else dst[j] = v;
+                }
+                if (p.out_hi) {
+                  __nv_bfloat16 h = __float2bfloat16_rn(v);
+                  p.out_hi[(size_t)row * p.ldo + col0 + j] = h;
+                  p.out_lo[(size_t)row * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
               }
             }
           }
@@ -383,13 +472,19 @@ int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 
 }  // namespace
 
-VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
-                             const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, const float* bias,
-                             const float* residual, int ldr, int flags, float alpha, int scale_ncols, int passes, int ksplit,
-                             void* stream) {
+// Extended form: additionally (or instead of C, which may then be NULL) writes the result pre-split into bf16
+// (out_hi, out_lo; leading dimension ldo) so that the next GEMM consumes it without a separate split pass.
+// `residual` is void*: fp32 for VQ_EPI_RESIDUAL / VQ_EPI_RELU_MASK, bf16 when VQ_EPI_MASK_BF16 is also set.
+VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
+                                const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, void* out_hi, void* out_lo,
+                                int ldo, const float* bias, const void* residual_v, int ldr, int flags, float alpha,
+                                int scale_ncols, int passes, int ksplit, void* stream) {
+  const float* residual = reinterpret_cast<const float*>(residual_v);
   VQ_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_bf16x3: bad shape M=%d N=%d K=%d", M, N, K);
   VQ_CHECK_ARG(passes == 1 || passes == 3, "gemm_bf16x3: passes must be 1 or 3");
-  VQ_CHECK_ARG(A_hi && B_hi && C && (passes == 1 || (A_lo && B_lo)), "gemm_bf16x3: null operand");
+  VQ_CHECK_ARG(A_hi && B_hi && (C || out_hi) && (passes == 1 || (A_lo && B_lo)), "gemm_bf16x3: null operand");
+  VQ_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "gemm_bf16x3: out_hi/out_lo must be given together");
+  VQ_CHECK_ARG(!(flags & EPI_MASK_BF16) || (flags & EPI_RELU_MASK), "gemm_bf16x3: MASK_BF16 needs RELU_MASK");
   VQ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16x3: leading dimensions must be multiples of 8 bf16 (lda=%d ldb=%d)", lda, ldb);
   VQ_CHECK_ARG(((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)B_hi & 15) == 0 && ((uintptr_t)A_lo & 15) == 0 && ((uintptr_t)B_lo & 15) == 0,
                "gemm_bf16x3: operands must be 16-byte aligned");
@@ -401,6 +496,7 @@ VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, co
 
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
   p.m_tiles = (int)vq_cdiv(M, BM);
   p.n_tiles = (int)vq_cdiv(N, BN);
@@ -410,7 +506,7 @@ VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, co
   p.ksplit = (int)vq_cdiv(p.kblocks_total, p.kblocks_per_split);
   cudaStream_t st = vq_stream(stream);
   if (p.ksplit > 1) {
-    VQ_CHECK_ARG(!(flags & (EPI_RELU | EPI_RELU_MASK)), "gemm_bf16x3: split-K cannot fuse a non-linear epilogue");
+    VQ_CHECK_ARG(!(flags & (EPI_RELU | EPI_RELU_MASK)) && !out_hi && C, "gemm_bf16x3: split-K cannot fuse a non-linear epilogue or split outputs");
     p.ep.flags |= EPI_ATOMIC;
     if (!(flags & EPI_ACCUMULATE))
       VQ_CUDA_CALL(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
@@ -441,4 +537,13 @@ VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, co
   if (!a_kmajor && b_kmajor) return VQ_TC(false, true);
   return VQ_TC(false, false);
 #undef VQ_TC
+}
+
+VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
+                             const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, const float* bias,
+                             const float* residual, int ldr, int flags, float alpha, int scale_ncols, int passes, int ksplit,
+                             void* stream) {
+  VQ_CHECK_ARG(C != nullptr, "gemm_bf16x3: null output");
+  return vqcpc_gemm_bf16x3_ex(a_kmajor, b_kmajor, M, N, K, A_hi, A_lo, lda, B_hi, B_lo, ldb, C, ldc, nullptr, nullptr, 0, bias,
+                              residual, ldr, flags, alpha, scale_ncols, passes, ksplit, stream);
 }
