@@ -32,6 +32,7 @@ extern "C" {
 #define VQ_EPI_RESIDUAL 8    /* + residual[m, n] */
 #define VQ_EPI_RELU_MASK 16  /* * (residual[m, n] > 0): ReLU backward fused into the data-gradient GEMM */
 #define VQ_EPI_SCALE_COLS 64 /* columns n < scale_ncols multiplied by alpha after the bias */
+#define VQ_EPI_MASK_BF16 128 /* with VQ_EPI_RELU_MASK: the mask source is a bf16 matrix (hi half of a split activation) */
 
 /* ---- runtime ------------------------------------------------------------------------------------------------ */
 const char* vqcpc_last_error(void);
@@ -55,16 +56,20 @@ int vqcpc_posemb_fill(float* h, int ld, int col0, const float* chan, const float
 int vqcpc_posemb_bwd(const float* dh, int ld, int col0, float* d_chan, float* d_evt, int64_t M, int S, int V, int pe,
                      void* stream);
 /* nn.LayerNorm(d), eps inside the sqrt (transformer/transformer_custom.py:261-262, :283, :289); mean/rstd (M) saved. */
-int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
-                        int64_t M, int d, float eps, void* stream);
-/* d_y overwritten; d_gamma / d_beta ACCUMULATED. */
+/* out (fp32) and/or (out_hi, out_lo) = the result pre-split into bf16 for the next tensor-core GEMM (either may be NULL). */
+int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, float* out, void* out_hi, void* out_lo,
+                        float* mean, float* rstd, int64_t M, int d, float eps, void* stream);
+/* d_y overwritten (+ optional bf16 split d_y_hi/d_y_lo); d_gamma / d_beta ACCUMULATED. */
 int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
-                        float* d_y, float* d_gamma, float* d_beta, int64_t M, int d, void* stream);
+                        float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, int64_t M, int d,
+                        void* stream);
 /* relative_transformer_downscaler.py:124 `output[::downscaling]` in blocks-major layout: x (P*L, d) -> out (P*L/f, d). */
 int vqcpc_subsample_fwd(const float* x, float* out, int64_t P, int L, int factor, int d, void* stream);
 int vqcpc_subsample_bwd(const float* d_out, float* d_x, int64_t P, int L, int factor, int d, void* stream);
 /* bias gradients: out[n] += sum_m x[m, n]  (ACCUMULATED). */
 int vqcpc_colsum(const float* x, int ld, float* out, int64_t M, int N, void* stream);
+/* same on a bf16 (hi, lo) split matrix: out[n] += sum_m (hi + lo)[m, n]. */
+int vqcpc_colsum_split(const void* x_hi, const void* x_lo, int ld, float* out, int64_t M, int N, void* stream);
 /* nn.SELU of the MLP upscaler (upscalers/mlp_upscaler.py:21-26). */
 int vqcpc_selu_fwd(const float* x, float* out, int64_t n, void* stream);
 int vqcpc_selu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
@@ -87,15 +92,24 @@ int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const voi
                       const float* residual, int ldr, int flags, float alpha, int scale_ncols, int passes, int ksplit,
                       void* stream);
 
+/* extended form: also (or only, C == NULL) writes the result pre-split into bf16 (out_hi, out_lo; ldo) for the next GEMM;
+ * `residual` is fp32, or bf16 when VQ_EPI_MASK_BF16 accompanies VQ_EPI_RELU_MASK. */
+int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
+                         const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, void* out_hi, void* out_lo, int ldo,
+                         const float* bias, const void* residual, int ldr, int flags, float alpha, int scale_ncols,
+                         int passes, int ksplit, void* stream);
+
 /* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +
  *      subsampled_relative_attention.py:30-122) ---------------------------------------------------------------------
- * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64); out (P*L, H*64); probs (P, H, L, L) or NULL. */
-int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L, int H,
-                   int head_dim, void* stream);
-/* d_qkv overwritten (q third = q_scale * dq~); d_e1 / d_e2 ACCUMULATED. */
+ * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64).  Only the query rows with token % keep == 0 are
+ * computed (keep = 1: all; keep = downscale factor in a stack's last layer = exact dead-row elimination) and stored
+ * compacted: out fp32 and/or bf16 split (out_hi, out_lo), (P*L/keep, H*64); probs (P, H, L, L) or NULL. */
+int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo, float* probs,
+                   int64_t P, int L, int H, int head_dim, int keep, void* stream);
+/* d_out (P*L/keep, H*64); d_qkv fp32 and/or its bf16 split overwritten (q third = q_scale * dq~); d_e1 / d_e2 ACCUMULATED. */
 int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
-                   float* d_qkv, float* d_e1, float* d_e2, int64_t P, int L, int H, int head_dim, float q_scale,
-                   void* stream);
+                   float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
+                   int head_dim, float q_scale, int keep, void* stream);
 
 /* ---- vector quantizer (quantizer/vector_quantizer.py:85-159) --------------------------------------------------
  * x (n, D); books: host array of ncb device pointers, each (Kc, D/ncb); idx (n, ncb) int64. */

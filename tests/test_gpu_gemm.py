@@ -127,3 +127,40 @@ def test_gemm_large_m_persistent_schedule():
     print('large-M bf16x3 rel err', err)
     assert err < 3e-5
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize('mode', ['bf16x3'])
+def test_gemm_presplit_operands_split_outputs_and_bf16_mask(mode):
+    """Fused-split data flow: operands given as (hi, lo), result written as fp32 and/or (hi, lo), ReLU mask read from the
+    bf16 hi half of a split activation."""
+    from VQCPCB import ops
+    ops.set_gemm_mode(mode)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(9)
+    M, N, K = 333, 2048, 512
+    a, b = _mk(M, N, K, True, True, gen)
+    bias = torch.randn(N, generator=gen, device='cuda')
+    asp = ops.split_bf16(a)
+    ref = _ref(a, b, True, True, bias=bias, relu=True)
+    c, sp = ops.gemm(None, b, M, N, K, bias=bias, relu=True, a_split=asp, b_is_weight=False, b_split=ops.split_bf16(b),
+                     out_split=True)
+    torch.cuda.synchronize()
+    assert ((c.double() - ref).norm() / ref.norm()).item() < 3e-5
+    assert torch.equal(sp[0], c.to(torch.bfloat16))
+    assert ((sp[0].double() + sp[1].double() - c.double()).norm() / c.double().norm()).item() < 1e-5
+    none_c, sp2 = ops.gemm(None, b, M, N, K, bias=bias, relu=True, a_split=asp, b_split=ops.split_bf16(b), want_c=False,
+                           out_split=True)
+    assert none_c is None and torch.equal(sp2[0], sp[0]) and torch.equal(sp2[1], sp[1])
+    # dgrad with the mask taken from the bf16 hi half:  d = (g @ W) * (h > 0)
+    g = torch.randn(M, 512, generator=gen, device='cuda')
+    w = torch.randn(512, N, generator=gen, device='cuda')          # (N_out=512, K_in=2048) weight, read untransposed
+    d_ref = (g.double() @ w.double()) * (c.double() > 0)
+    _, dsp = ops.gemm(g, w, M, N, 512, True, False, relu_mask=sp[0], want_c=False, out_split=True)
+    d = dsp[0].double() + dsp[1].double()
+    assert ((d - d_ref).norm() / d_ref.norm()).item() < 3e-5
+    # wgrad from two split operands (both MN-major), accumulated with split-K
+    acc = torch.zeros(512, N, device='cuda')
+    ops.gemm(None, None, 512, N, M, False, False, out=acc, accumulate=True, ksplit=2, a_split=ops.split_bf16(g), b_split=sp)
+    w_ref = g.double().t() @ c.double()
+    assert ((acc.double() - w_ref).norm() / w_ref.norm()).item() < 3e-5
+    ops.set_gemm_mode('bf16x3')

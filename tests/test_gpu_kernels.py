@@ -216,3 +216,54 @@ def test_clip_adam_matches_oracle():
         assert abs(opt.gnorm_sq.item() ** 0.5 - gn.item()) < 1e-4 * gn.item()
         for i, p in enumerate(ps):
             assert rel_err(p, prm[str(i)]) < 1e-6, (step, i)
+
+
+def _unsplit(sp):
+    return sp[0].float() + sp[1].float()
+
+
+def test_split_outputs_of_layernorm_attention_colsum():
+    """Producers can emit their result pre-split into bf16 (hi, lo): hi == bf16(x), hi + lo == x to 2^-16."""
+    from VQCPCB import ops
+    torch.manual_seed(11)
+    M, d = 777, 512
+    y = torch.randn(M, d, device='cuda')
+    g, b = torch.randn(d, device='cuda'), torch.randn(d, device='cuda')
+    out, sp, mean, rstd = ops.layernorm_fwd(y, g, b, want_split=True)
+    assert torch.equal(sp[0], out.to(torch.bfloat16)) and ((_unsplit(sp) - out).abs() <= out.abs() * 2 ** -15 + 1e-30).all()
+    none_out, sp2, _, _ = ops.layernorm_fwd(y, g, b, want_fp32=False, want_split=True)
+    assert none_out is None and torch.equal(sp2[0], sp[0]) and torch.equal(sp2[1], sp[1])
+    dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    go = torch.randn(M, d, device='cuda')
+    dy, dsp = ops.layernorm_bwd(go, y, mean, rstd, g, dg, db, want_split=True)
+    assert torch.equal(dsp[0], dy.to(torch.bfloat16)) and rel_err(_unsplit(dsp), dy) < 1e-5
+    acc = torch.zeros(d, device='cuda')
+    ops._native.call('vqcpc_colsum_split', ops._p(dsp[0]), ops._p(dsp[1]), d, ops._p(acc), M, d, ops._stream())
+    assert rel_err(acc, _unsplit(dsp).double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('L,keep,P', [(16, 4, 21), (4, 4, 21), (16, 1, 5), (8, 2, 7)])
+def test_attention_kept_rows_and_split_io(L, keep, P):
+    """keep > 1 (dead-row elimination): outputs / dO live on the rows with token % keep == 0 only, compacted; results
+    must equal the full computation restricted to those rows, and gradients the full backward with zero dO elsewhere."""
+    from VQCPCB import ops
+    torch.manual_seed(L * 10 + keep)
+    H, hd = 8, 64
+    d = H * hd
+    qkv = torch.randn(P * L, 3 * d, device='cuda') * 0.7
+    e1 = torch.randn(H * L, hd, device='cuda') * 0.5
+    e2 = torch.randn(H * L, hd, device='cuda') * 0.5
+    full, probs_full = ops.attn_fwd(qkv, e1, e2, P, L, H, hd)
+    out, sp, probs = ops.attn_fwd(qkv, e1, e2, P, L, H, hd, keep=keep, want_split=True)
+    ref = full.view(P, L, d)[:, ::keep].reshape(-1, d)
+    assert torch.equal(out, ref)
+    assert torch.equal(sp[0], ref.to(torch.bfloat16)) and rel_err(_unsplit(sp), ref) < 1e-5
+    go = torch.randn(P * (L // keep), d, device='cuda')
+    go_full = torch.zeros(P, L, d, device='cuda')
+    go_full[:, ::keep] = go.view(P, L // keep, d)
+    a1, a2 = torch.zeros_like(e1), torch.zeros_like(e2)
+    b1, b2 = torch.zeros_like(e1), torch.zeros_like(e2)
+    ref_dqkv = ops.attn_bwd(qkv, e1, e2, probs_full, go_full.view(-1, d), a1, a2, P, L, H, hd, 0.125)
+    dqkv, dsp = ops.attn_bwd(qkv, e1, e2, probs, go, b1, b2, P, L, H, hd, 0.125, keep=keep, want_split=True)
+    assert rel_err(dqkv, ref_dqkv) < 1e-6 and rel_err(b1, a1) < 1e-5 and rel_err(b2, a2) < 1e-5
+    assert torch.equal(dsp[0], dqkv.to(torch.bfloat16)) and rel_err(_unsplit(dsp), dqkv) < 1e-5

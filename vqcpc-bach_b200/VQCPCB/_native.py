@@ -19,19 +19,21 @@ SIGNATURES = {
     'vqcpc_embed_bwd': [_P, _L, _I, _P, _P, _I, _P, _P],
     'vqcpc_posemb_fill': [_P, _I, _I, _P, _P, _L, _I, _I, _I, _P],
     'vqcpc_posemb_bwd': [_P, _I, _I, _P, _P, _L, _I, _I, _I, _P],
-    'vqcpc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
-    'vqcpc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
+    'vqcpc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    'vqcpc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     'vqcpc_subsample_fwd': [_P, _P, _L, _I, _I, _I, _P],
     'vqcpc_subsample_bwd': [_P, _P, _L, _I, _I, _I, _P],
     'vqcpc_colsum': [_P, _I, _P, _L, _I, _P],
+    'vqcpc_colsum_split': [_P, _P, _I, _P, _L, _I, _P],
     'vqcpc_selu_fwd': [_P, _P, _L, _P],
     'vqcpc_selu_bwd': [_P, _P, _P, _L, _P],
     'vqcpc_split_bf16': [_P, _I, _P, _P, _I, _L, _I, _P],
     'vqcpc_reduce_sum': [_P, _L, _P, _F, _P],
     'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],
     'vqcpc_gemm_bf16x3': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
-    'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
-    'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
+    'vqcpc_gemm_bf16x3_ex': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
+    'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     'vqcpc_vq_search': [_P, _L, _I, _P, _I, _I, _P, _P],
     'vqcpc_vq_gather': [_P, _L, _I, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
     'vqcpc_vq_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],

@@ -56,7 +56,8 @@ class EncoderStackFn(torch.autograd.Function):
         ops._native.call('vqcpc_posemb_fill', ops._p(h), d, d - 2 * pe, ops._p(chan), ops._p(evt), M0, S, V, pe, ops._stream())
 
         saved = []
-        x, L, li = h, S, 0
+        tc = ops.tensor_core_mode()
+        x, x_sp, L, li = h, None, S, 0
         q_scale = float(hd) ** -0.5
         for factor, nl in zip(factors, layers_per_stack):
             for layer_in_stack in range(nl):
@@ -67,13 +68,33 @@ class EncoderStackFn(torch.autograd.Function):
                 # is row-wise, so that layer runs it on the surviving rows only.  K/V (hence the in-proj and the
                 # attention itself) still see all L tokens.  Saves ~31 % of the encoder FLOPs with identical results.
                 last = (layer_in_stack == nl - 1) and factor > 1
+                keep = factor if last else 1
+                if tc:
+                    # tensor-core path: every GEMM operand travels as a bf16 (hi, lo) pair written by its PRODUCER
+                    # (LayerNorm / attention / GEMM epilogues) - no separate split passes, fp32 copies only where an
+                    # elementwise consumer needs them (residuals, LayerNorm inputs, the attention kernel's q/k/v).
+                    if x_sp is None:
+                        x_sp = ops.split_bf16(x)
+                    qkv = ops.gemm(None, lp['wqkv'], P * L, 3 * d, d, bias=lp['bqkv'], scale_cols=(q_scale, d),
+                                   b_is_weight=True, a_split=x_sp)
+                    _, o_sp, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep,
+                                                  want_fp32=False, want_split=True)
+                    x_k = _subsample(x, P, L, factor, d) if last else x
+                    Mk = P * (L // keep)
+                    y1 = ops.gemm(None, lp['wo'], Mk, d, d, bias=lp['bo'], residual=x_k, b_is_weight=True, a_split=o_sp)
+                    x1, x1_sp, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'], want_split=True)
+                    Fh = lp['w1'].shape[0]
+                    _, hm_sp = ops.gemm(None, lp['w1'], Mk, Fh, d, bias=lp['b1'], relu=True, b_is_weight=True, a_split=x1_sp,
+                                        want_c=False, out_split=True)
+                    y2 = ops.gemm(None, lp['w2'], Mk, d, Fh, bias=lp['b2'], residual=x1, b_is_weight=True, a_split=hm_sp)
+                    x2, x2_sp, mean2, rstd2 = ops.layernorm_fwd(y2, lp['g2'], lp['be2'], want_split=True)
+                    if train:
+                        saved.append((x_sp, qkv, probs, o_sp, y1, mean1, rstd1, x1_sp, hm_sp, y2, mean2, rstd2, L, last))
+                    x, x_sp = x2, x2_sp
+                    continue
                 qkv = ops.linear_fwd(x, lp['wqkv'], lp['bqkv'], scale_cols=(q_scale, d))
-                o, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train)
-                if last:
-                    o_k = _subsample(o, P, L, factor, d)
-                    x_k = _subsample(x, P, L, factor, d)
-                else:
-                    o_k, x_k = o, x
+                o_k, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep)
+                x_k = _subsample(x, P, L, factor, d) if last else x
                 y1 = ops.linear_fwd(o_k, lp['wo'], lp['bo'], residual=x_k)
                 x1, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'])
                 hm = ops.linear_fwd(x1, lp['w1'], lp['b1'], relu=True)
@@ -90,6 +111,7 @@ class EncoderStackFn(torch.autograd.Function):
 
         ctx.meta = meta
         ctx.params = params
+        ctx.tc = tc
         ctx.saved = saved
         ctx.emb2d = emb2d if train else None
         ctx.x_last = x if train else None
@@ -125,7 +147,31 @@ class EncoderStackFn(torch.autograd.Function):
                 gp = dict(zip(_LAYER_KEYS, g_layers[li * 14:(li + 1) * 14]))
                 x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls, last = ctx.saved[li]
                 assert Ls == L
+                keep = factor if last else 1
+                Mk = P * (L // keep)
                 # (for a stack's last layer everything down to the out-proj lives on the surviving rows only)
+                if ctx.tc:
+                    # x, o_k, x1, hm are bf16 (hi, lo) pairs saved by the forward; gradients that feed GEMMs are produced
+                    # pre-split by the LayerNorm-backward / attention-backward kernels and the GEMM epilogues.
+                    Fh = lp['w1'].shape[0]
+                    dy2, dy2_sp = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'], want_split=True)
+                    # FFN2: dhm = (dy2 W2) * (hm > 0) -> only its split is needed (dgrad + wgrad of FFN1)
+                    _, dhm_sp = ops.linear_bwd(None, lp['w2'], dy2, gp['w2'], gp['b2'], relu_mask=hm[0], x_split=hm,
+                                               dy_split=dy2_sp, dx_want_c=False, dx_out_split=True, shape=(Mk, Fh))
+                    # FFN1: dx1 = dhm W1 + dy2
+                    dx1 = ops.linear_bwd(None, lp['w1'], None, gp['w1'], gp['b1'], dx_residual=dy2, x_split=x1,
+                                         dy_split=dhm_sp, shape=(Mk, d))
+                    del dhm_sp
+                    dy1, dy1_sp = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'], want_split=True)
+                    do = ops.linear_bwd(None, lp['wo'], dy1, gp['wo'], gp['bo'], x_split=o_k, dy_split=dy1_sp, shape=(Mk, d))
+                    _, dqkv_sp = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale,
+                                              keep=keep, want_fp32=False, want_split=True)
+                    if last:
+                        dy1 = _subsample_bwd(dy1, P, L, factor, d)
+                    dx = ops.linear_bwd(None, lp['wqkv'], None, gp['wqkv'], gp['bqkv'], dx_residual=dy1, x_split=x,
+                                        dy_split=dqkv_sp, shape=(P * L, d))
+                    ctx.saved[li] = None
+                    continue
                 # LN2 -> dy2 (flows to the FFN branch and, as the residual, to x1)
                 dy2 = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'])
                 # FFN2: dhm = (dy2 W2) * (hm > 0)
@@ -134,12 +180,11 @@ class EncoderStackFn(torch.autograd.Function):
                 dx1 = ops.linear_bwd(x1, lp['w1'], dhm, gp['w1'], gp['b1'], dx_residual=dy2)
                 del dhm
                 dy1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'])
-                # out-proj
+                # out-proj (its dgrad is the gradient of the kept query rows' attention output)
                 do = ops.linear_bwd(o_k, lp['wo'], dy1, gp['wo'], gp['bo'])
-                if last:                       # scatter back to all L rows (zeros for the dropped query rows)
-                    do = _subsample_bwd(do, P, L, factor, d)
+                dqkv = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale, keep=keep)
+                if last:                       # residual path: scatter back to all L rows (zeros for the dropped rows)
                     dy1 = _subsample_bwd(dy1, P, L, factor, d)
-                dqkv = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale)
                 # in-proj: dx = dqkv Wqkv + dy1 (residual path)
                 dx = ops.linear_bwd(x, lp['wqkv'], dqkv, gp['wqkv'], gp['bqkv'], dx_residual=dy1)
                 ctx.saved[li] = None

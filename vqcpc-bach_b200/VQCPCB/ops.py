@@ -15,7 +15,7 @@ import torch
 
 from . import _native
 
-EPI_BIAS, EPI_RELU, EPI_ACCUMULATE, EPI_RESIDUAL, EPI_RELU_MASK, EPI_SCALE_COLS = 1, 2, 4, 8, 16, 64
+EPI_BIAS, EPI_RELU, EPI_ACCUMULATE, EPI_RESIDUAL, EPI_RELU_MASK, EPI_SCALE_COLS, EPI_MASK_BF16 = 1, 2, 4, 8, 16, 64, 128
 
 _GEMM_MODE = 'bf16x3'
 PROFILE_GEMM = None         # bench.py sets this to a list: every GEMM launch is bracketed by CUDA events on its stream
@@ -98,17 +98,30 @@ def _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor):
     return a_cols % 8 == 0 and b_cols % 8 == 0 and a_cols % 4 == 0 and b_cols % 4 == 0
 
 
+def tensor_core_mode():
+    return _GEMM_MODE != 'fp32'
+
+
 def gemm(a, b, M, N, K, a_kmajor=True, b_kmajor=True, out=None, bias=None, residual=None, relu=False, relu_mask=None,
-         accumulate=False, scale_cols=None, ksplit=1, b_is_weight=False, a_split=None, b_split=None):
-    """C[M,N] = epi(A.B).  a/b are 2-D fp32 views whose unit-stride dim is K (kmajor) or M/N (not kmajor).
+         accumulate=False, scale_cols=None, ksplit=1, b_is_weight=False, a_split=None, b_split=None, want_c=True,
+         out_split=False):
+    """C[M,N] = epi(A.B).  a/b are 2-D fp32 views whose unit-stride dim is K (kmajor) or M/N (not kmajor); alternatively
+    pass the operand already split into bf16 (a_split / b_split = (hi, lo)) and leave a / b None.
 
     epilogue: +bias[N] -> (cols < n) *= alpha  [scale_cols=(alpha, n)] -> +residual[M,N] -> relu -> *(relu_mask > 0)
-    accumulate: C += result.  ksplit > 1: split-K with fp32 atomics (linear epilogues only)."""
+    (relu_mask may be fp32 or the bf16 hi half of a split activation).  accumulate: C += result.
+    ksplit > 1: split-K with fp32 atomics (linear epilogues only).
+    out_split: additionally return the result split into bf16 (hi, lo) written by the epilogue (tensor-core path only);
+    want_c=False skips the fp32 result.  Returns C, or (C | None, (hi, lo)) when out_split."""
     _chk(a, b, out, bias, residual, relu_mask)
-    dev = a.device
-    if out is None:
+    dev = (a if a is not None else a_split[0]).device
+    use_tc = (a is None or b is None) or _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor)
+    if out_split or not want_c:
+        assert use_tc, 'split outputs need the tensor-core GEMM'
+    if out is None and want_c:
         out = torch.empty(M, N, dtype=torch.float32, device=dev)
-    assert out.stride(1) == 1
+    if out is not None:
+        assert out.stride(1) == 1
     flags = 0
     if bias is not None:
         flags |= EPI_BIAS
@@ -122,39 +135,45 @@ def gemm(a, b, M, N, K, a_kmajor=True, b_kmajor=True, out=None, bias=None, resid
         assert relu_mask is None
     if relu_mask is not None:
         flags |= EPI_RELU_MASK
+        if relu_mask.dtype == torch.bfloat16:
+            flags |= EPI_MASK_BF16
         res = relu_mask
     alpha, ncols = 1.0, 0
     if scale_cols is not None:
         flags |= EPI_SCALE_COLS
         alpha, ncols = scale_cols
     ldr = res.stride(0) if res is not None else 0
-    assert a.stride(1) == 1 and b.stride(1) == 1
     prof = PROFILE_GEMM
-    use_tc = _tc_ok(M, N, K, a, b, a_kmajor, b_kmajor)
-    if prof is not None and use_tc:
+    if use_tc:
         if a_split is None:
+            assert a.stride(1) == 1
             a_split = split_bf16(a)
         if b_split is None:
+            assert b.stride(1) == 1
             b_split = weight_split(b) if b_is_weight else split_bf16(b)
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
+    oh = ol = None
     if use_tc:
-        if a_split is None:
-            a_split = split_bf16(a)
-        if b_split is None:
-            b_split = weight_split(b) if b_is_weight else split_bf16(b)
         passes = 3 if _GEMM_MODE == 'bf16x3' else 1
-        _native.call('vqcpc_gemm_bf16x3', int(a_kmajor), int(b_kmajor), M, N, K, _p(a_split[0]), _p(a_split[1]),
-                     a_split[0].stride(0), _p(b_split[0]), _p(b_split[1]), b_split[0].stride(0), _p(out), out.stride(0),
-                     _p(bias), _p(res), ldr, flags, float(alpha), int(ncols), passes, int(ksplit), _stream())
+        if out_split:
+            oh = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            ol = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        _native.call('vqcpc_gemm_bf16x3_ex', int(a_kmajor), int(b_kmajor), M, N, K, _p(a_split[0]), _p(a_split[1]),
+                     a_split[0].stride(0), _p(b_split[0]), _p(b_split[1]), b_split[0].stride(0), _p(out),
+                     out.stride(0) if out is not None else 0, _p(oh), _p(ol), N, _p(bias), _p(res), ldr, flags,
+                     float(alpha), int(ncols), passes, int(ksplit), _stream())
     else:
+        assert a.stride(1) == 1 and b.stride(1) == 1
         _native.call('vqcpc_gemm_f32', int(a_kmajor), int(b_kmajor), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0),
                      _p(out), out.stride(0), _p(bias), _p(res), ldr, flags, float(alpha), int(ncols), int(ksplit), _stream())
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
         prof.append(('tc' if use_tc else 'simt', 2.0 * M * N * K, ev0, ev1))
+    if out_split:
+        return out, (oh, ol)
     return out
 
 
@@ -173,19 +192,26 @@ def linear_fwd(x2d, w, b, relu=False, residual=None, scale_cols=None, out=None):
                 b_is_weight=True)
 
 
-def linear_bwd(x2d, w, dy, dw, db, need_dx=True, dx_residual=None, relu_mask=None, dx_out=None):
+def linear_bwd(x2d, w, dy, dw, db, need_dx=True, dx_residual=None, relu_mask=None, dx_out=None, x_split=None,
+               dy_split=None, dx_want_c=True, dx_out_split=False, shape=None):
     """Gradients of y = x @ w.T + b.  dw/db are ACCUMULATED in place (flat-gradient-buffer views).
-    dx = dy @ w (+ dx_residual) (* relu_mask > 0)."""
-    M, K = x2d.shape
+    dx = dy @ w (+ dx_residual) (* relu_mask > 0).  x / dy may be given pre-split (x_split / dy_split, with
+    shape=(M, K)); db then comes from the split (hi + lo) unless an fp32 dy is also given."""
+    M, K = shape if shape is not None else x2d.shape
     N = w.shape[0]
     dx = None
     if need_dx:
-        dx = gemm(dy, w, M, K, N, True, False, out=dx_out, residual=dx_residual, relu_mask=relu_mask, b_is_weight=True)
+        dx = gemm(dy if dy_split is None else None, w, M, K, N, True, False, out=dx_out, residual=dx_residual,
+                  relu_mask=relu_mask, b_is_weight=True, a_split=dy_split, want_c=dx_want_c, out_split=dx_out_split)
     if dw is not None:
         tiles = ((N + 127) // 128) * ((K + 127) // 128)
-        gemm(dy, x2d, N, K, M, False, False, out=dw.view(N, K), accumulate=True, ksplit=_wgrad_ksplit(M, tiles))
+        gemm(dy if dy_split is None else None, x2d if x_split is None else None, N, K, M, False, False, out=dw.view(N, K),
+             accumulate=True, ksplit=_wgrad_ksplit(M, tiles), a_split=dy_split, b_split=x_split)
     if db is not None:
-        colsum(dy, db)
+        if dy is not None:
+            colsum(dy, db)
+        else:
+            _native.call('vqcpc_colsum_split', _p(dy_split[0]), _p(dy_split[1]), dy_split[0].stride(0), _p(db), M, N, _stream())
     return dx
 
 
@@ -215,35 +241,55 @@ def embed_bwd(tokens_flat, dout, grads):
     _native.call('vqcpc_embed_bwd', _p(tokens_flat), n, len(grads), _ptr_array(grads), rows, E, _p(dout), _stream())
 
 
-def layernorm_fwd(y, gamma, beta, eps=1e-5):
+def _split_buffers(rows, cols, dev):
+    return (torch.empty(rows, cols, dtype=torch.bfloat16, device=dev), torch.empty(rows, cols, dtype=torch.bfloat16, device=dev))
+
+
+def layernorm_fwd(y, gamma, beta, eps=1e-5, want_fp32=True, want_split=False):
+    """-> (out fp32 | None, (hi, lo) | None, mean, rstd)"""
     M, d = y.shape
-    out = torch.empty_like(y)
+    out = torch.empty_like(y) if want_fp32 else None
+    sp = _split_buffers(M, d, y.device) if want_split else (None, None)
     mean = torch.empty(M, dtype=torch.float32, device=y.device)
     rstd = torch.empty(M, dtype=torch.float32, device=y.device)
-    _native.call('vqcpc_layernorm_fwd', _p(y), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), M, d, float(eps), _stream())
+    _native.call('vqcpc_layernorm_fwd', _p(y), _p(gamma), _p(beta), _p(out), _p(sp[0]), _p(sp[1]), _p(mean), _p(rstd), M, d,
+                 float(eps), _stream())
+    if want_split:
+        return out, sp, mean, rstd
     return out, mean, rstd
 
 
-def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta):
+def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta, want_split=False):
     M, d = y.shape
     dy = torch.empty_like(y)
-    _native.call('vqcpc_layernorm_bwd', _p(dout), _p(y), _p(mean), _p(rstd), _p(gamma), _p(dy), _p(dgamma), _p(dbeta), M, d,
-                 _stream())
+    sp = _split_buffers(M, d, y.device) if want_split else (None, None)
+    _native.call('vqcpc_layernorm_bwd', _p(dout), _p(y), _p(mean), _p(rstd), _p(gamma), _p(dy), _p(sp[0]), _p(sp[1]), _p(dgamma),
+                 _p(dbeta), M, d, _stream())
+    if want_split:
+        return dy, sp
     return dy
 
 
-def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True):
-    M = P * L
-    out = torch.empty(M, H * hd, dtype=torch.float32, device=qkv.device)
+def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, want_split=False):
+    """-> (out fp32 | None, probs) or (out | None, (hi, lo), probs) when want_split; rows = P * L / keep."""
+    Mo = P * (L // keep)
+    out = torch.empty(Mo, H * hd, dtype=torch.float32, device=qkv.device) if want_fp32 else None
+    sp = _split_buffers(Mo, H * hd, qkv.device) if want_split else (None, None)
     probs = torch.empty(P, H, L, L, dtype=torch.float32, device=qkv.device) if need_probs else None
-    _native.call('vqcpc_attn_fwd', _p(qkv), _p(e1), _p(e2), _p(out), _p(probs), P, L, H, hd, _stream())
+    _native.call('vqcpc_attn_fwd', _p(qkv), _p(e1), _p(e2), _p(out), _p(sp[0]), _p(sp[1]), _p(probs), P, L, H, hd, int(keep),
+                 _stream())
+    if want_split:
+        return out, sp, probs
     return out, probs
 
 
-def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale):
-    dqkv = torch.empty_like(qkv)
-    _native.call('vqcpc_attn_bwd', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(de1), _p(de2), P, L, H, hd,
-                 float(q_scale), _stream())
+def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False):
+    dqkv = torch.empty_like(qkv) if want_fp32 else None
+    sp = _split_buffers(qkv.shape[0], qkv.shape[1], qkv.device) if want_split else (None, None)
+    _native.call('vqcpc_attn_bwd', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(sp[0]), _p(sp[1]), _p(de1), _p(de2),
+                 P, L, H, hd, float(q_scale), int(keep), _stream())
+    if want_split:
+        return dqkv, sp
     return dqkv
 
 

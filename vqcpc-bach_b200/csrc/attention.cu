@@ -38,6 +38,35 @@ __device__ __forceinline__ void load_tile(float* s, const float* __restrict__ g,
   }
 }
 
+// same, but the source holds only the rows with (token % keep == 0), compacted; other rows are zero
+__device__ __forceinline__ void load_tile_compact(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld,
+                                                  int lane, int L, int keep) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    int r = it * 2 + (lane >> 4);
+    int c = (lane & 15) * 4;
+    int64_t gr = row0 + r;
+    int i = (int)(gr % L);
+    float4 v = make_float4(0, 0, 0, 0);
+    if (gr < M && (i % keep) == 0) v = ld4(g + ((gr / L) * (L / keep) + i / keep) * ld + c);
+    st4(s + r * TS + c, v);
+  }
+}
+
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
+  __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                h3 = __float2bfloat16_rn(v.w);
+  __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+  uint2 hv, lv;
+  hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lv.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lv.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(hi) = hv;
+  *reinterpret_cast<uint2*>(lo) = lv;
+}
+
 template <int L>
 __device__ __forceinline__ const float* bias_row(const float* e1s, const float* e2s, int i, int j) {
   return (j <= i) ? (e1s + (L - 1 - (i - j)) * TS) : (e2s + (j - i) * TS);
@@ -47,7 +76,8 @@ __device__ __forceinline__ const float* bias_row(const float* e1s, const float* 
 template <int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
-                float* __restrict__ out, float* __restrict__ probs, int64_t M, int H, int64_t ntiles) {
+                float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                float* __restrict__ probs, int64_t M, int H, int64_t ntiles, int keep) {
   extern __shared__ __align__(16) float smem[];
   float* e1s = smem;
   float* e2s = e1s + L * TS;
@@ -66,6 +96,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 
   const int r = lane >> 1, jh = lane & 1;
   const int g = r / L, i = r % L;
+  const bool kept = (i % keep) == 0;       // dead-row elimination: only these query rows produce output
   for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
     const int64_t row0 = tile * TR;
     __syncwarp();
@@ -77,6 +108,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
     float s[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) s[jj] = 0.f;
+    if (kept)
 #pragma unroll 4
     for (int d4 = 0; d4 < 16; ++d4) {
       float4 q4 = ld4(qs + r * TS + d4 * 4);
@@ -112,7 +144,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
       a_all[jj] = jh == 0 ? a : o;     // selects, not dynamic register indexing
       a_all[8 + jj] = jh == 0 ? o : a;
       int c = jh * 8 + jj;
-      if (probs != nullptr && gr < M && c / L == g) {
+      if (probs != nullptr && kept && gr < M && c / L == g) {
         int64_t p = gr / L;
         probs[((p * H + h) * L + i) * L + (c % L)] = a;
       }
@@ -121,6 +153,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
     float4 o4[8];
 #pragma unroll
     for (int x = 0; x < 8; ++x) o4[x] = make_float4(0, 0, 0, 0);
+    if (kept)
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       float a = a_all[c];
@@ -129,9 +162,14 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
         for (int x = 0; x < 8; ++x) fma4(o4[x], a, ld4(vs + c * TS + jh * 32 + x * 4));
       }
     }
-    if (gr < M) {
+    if (kept && gr < M) {
+      const int64_t orow = (gr / L) * (L / keep) + i / keep;
 #pragma unroll
-      for (int x = 0; x < 8; ++x) st4(out + gr * d + h * HD + jh * 32 + x * 4, o4[x]);
+      for (int x = 0; x < 8; ++x) {
+        const int64_t off = orow * d + h * HD + jh * 32 + x * 4;
+        if (out) st4(out + off, o4[x]);
+        if (out_hi) store_split4(out_hi + off, out_lo + off, o4[x]);
+      }
     }
   }
 }
@@ -144,7 +182,8 @@ template <int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
                 const float* __restrict__ probs, const float* __restrict__ dout, float* __restrict__ dqkv,
-                float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale) {
+                __nv_bfloat16* __restrict__ dqkv_hi, __nv_bfloat16* __restrict__ dqkv_lo,
+                float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale, int keep) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PS = 17;   // padded stride of the 16x16 matrices
   constexpr int PER_WARP = 4 * TR * TS + 2 * TR * PS;
@@ -180,13 +219,15 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
     load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
     load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
     load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
-    load_tile(gs, dout + h * HD, row0, M, d, lane);
+    if (keep == 1) load_tile(gs, dout + h * HD, row0, M, d, lane);
+    else load_tile_compact(gs, dout + h * HD, row0, M, d, lane, L, keep);     // dO exists for the kept query rows only
+    const bool kept = (i % keep) == 0;
     float a[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       int c = jh * 8 + jj;
       float v = 0.f;
-      if (gr < M && c / L == g) v = probs[(((gr / L) * H + h) * L + i) * L + (c % L)];
+      if (kept && gr < M && c / L == g) v = probs[(((gr / L) * H + h) * L + i) * L + (c % L)];
       a[jj] = v;
       As[r * PS + c] = v;
     }
@@ -240,7 +281,9 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
         for (int x = 0; x < 8; ++x) {
           float4 v = o4[x];
           v.x *= q_scale; v.y *= q_scale; v.z *= q_scale; v.w *= q_scale;
-          st4(dqkv + gr * 3 * d + h * HD + jh * 32 + x * 4, v);
+          const int64_t off = gr * 3 * d + h * HD + jh * 32 + x * 4;
+          if (dqkv) st4(dqkv + off, v);
+          if (dqkv_hi) store_split4(dqkv_hi + off, dqkv_lo + off, v);
         }
       }
     }
@@ -264,8 +307,9 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
       if (gr < M) {
 #pragma unroll
         for (int x = 0; x < 8; ++x) {
-          st4(dqkv + gr * 3 * d + d + h * HD + jh * 32 + x * 4, k4[x]);
-          st4(dqkv + gr * 3 * d + 2 * d + h * HD + jh * 32 + x * 4, v4[x]);
+          const int64_t offk = gr * 3 * d + d + h * HD + jh * 32 + x * 4, offv = offk + d;
+          if (dqkv) { st4(dqkv + offk, k4[x]); st4(dqkv + offv, v4[x]); }
+          if (dqkv_hi) { store_split4(dqkv_hi + offk, dqkv_lo + offk, k4[x]); store_split4(dqkv_hi + offv, dqkv_lo + offv, v4[x]); }
         }
       }
     }
@@ -313,7 +357,8 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 }
 
 template <int L>
-int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t M, int H, cudaStream_t st) {
+int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+               float* probs, int64_t M, int H, int keep, cudaStream_t st) {
   constexpr int WARPS = 8;
   int64_t ntiles = vq_cdiv(M, TR);
   size_t smem = (size_t)(2 * L * TS + WARPS * 3 * TR * TS) * sizeof(float);
@@ -323,14 +368,15 @@ int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, f
     done = true;
   }
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 4);
-  attn_fwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, probs, M, H, ntiles);
+  attn_fwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, out_hi, out_lo, probs, M, H, ntiles, keep);
   VQ_CUDA_LAUNCH_CHECK("attn_fwd_kernel");
   return VQ_OK;
 }
 
 template <int L>
 int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* dout, float* dqkv,
-               float* de1, float* de2, int64_t M, int H, float q_scale, cudaStream_t st) {
+               __nv_bfloat16* dqkv_hi, __nv_bfloat16* dqkv_lo, float* de1, float* de2, int64_t M, int H, float q_scale, int keep,
+               cudaStream_t st) {
   constexpr int WARPS = 4;
   int64_t ntiles = vq_cdiv(M, TR);
   size_t smem = (size_t)(2 * L * TS + WARPS * (4 * TR * TS + 2 * TR * 17)) * sizeof(float);
@@ -341,7 +387,7 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
     done = true;
   }
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 2);
-  attn_bwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, de1, de2, M, H, ntiles, q_scale);
+  attn_bwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep);
   VQ_CUDA_LAUNCH_CHECK("attn_bwd_kernel");
   return VQ_OK;
 }
@@ -349,41 +395,52 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
 }  // namespace
 
 // qkv: (P*L, 3*H*64) with the q third already multiplied by hd^-0.5 (done in the in-proj GEMM epilogue);
-// out: (P*L, H*64); probs: (P, H, L, L) saved for backward (may be NULL for inference).
-VQ_API int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L,
-                          int H, int head_dim, void* stream) {
+// out (fp32) and/or (out_hi, out_lo) (bf16 split, operand of the out-proj GEMM): (P*L/keep, H*64) — only the query rows
+// with token % keep == 0 are computed and stored, compacted (keep = 1: all rows; keep = downscale factor in the last
+// layer of a stack = exact dead-row elimination); probs: (P, H, L, L) saved for backward (kept rows only; may be NULL).
+VQ_API int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                          float* probs, int64_t P, int L, int H, int head_dim, int keep, void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_fwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_fwd: bad head count %d", H);
+  VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_fwd: keep=%d must divide L=%d", keep, L);
+  VQ_CHECK_ARG((out || out_hi) && ((out_hi == nullptr) == (out_lo == nullptr)), "attn_fwd: need out and/or (out_hi, out_lo)");
   if (P == 0) return VQ_OK;
   cudaStream_t st = vq_stream(stream);
   int64_t M = P * L;
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   switch (L) {
-    case 16: return launch_fwd<16>(qkv, e1, e2, out, probs, M, H, st);
-    case 8: return launch_fwd<8>(qkv, e1, e2, out, probs, M, H, st);
-    case 4: return launch_fwd<4>(qkv, e1, e2, out, probs, M, H, st);
-    case 2: return launch_fwd<2>(qkv, e1, e2, out, probs, M, H, st);
-    case 1: return launch_fwd<1>(qkv, e1, e2, out, probs, M, H, st);
+    case 16: return launch_fwd<16>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
+    case 8: return launch_fwd<8>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
+    case 4: return launch_fwd<4>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
+    case 2: return launch_fwd<2>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
+    case 1: return launch_fwd<1>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
     default: VQ_CHECK_ARG(false, "attn_fwd: block length L must be 1, 2, 4, 8 or 16 (got %d)", L);
   }
   return VQ_OK;
 }
 
-// d_qkv (P*L, 3*H*64) is overwritten (its q third is the gradient wrt the UNscaled projection: q_scale * dq~);
+// d_out: (P*L/keep, H*64) gradient of the kept query rows (see vqcpc_attn_fwd).  d_qkv (fp32, P*L x 3*H*64) and/or its
+// bf16 split (d_qkv_hi, d_qkv_lo) are overwritten (q third = gradient wrt the UNscaled projection: q_scale * dq~);
 // d_e1 / d_e2 (H*L, 64) are ACCUMULATED.
 VQ_API int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
-                          float* d_qkv, float* d_e1, float* d_e2, int64_t P, int L, int H, int head_dim, float q_scale,
-                          void* stream) {
+                          float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
+                          int head_dim, float q_scale, int keep, void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_bwd: bad head count %d", H);
+  VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_bwd: keep=%d must divide L=%d", keep, L);
+  VQ_CHECK_ARG((d_qkv || d_qkv_hi) && ((d_qkv_hi == nullptr) == (d_qkv_lo == nullptr)), "attn_bwd: need d_qkv and/or its split");
   if (P == 0) return VQ_OK;
   cudaStream_t st = vq_stream(stream);
   int64_t M = P * L;
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d_qkv_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d_qkv_lo);
   switch (L) {
-    case 16: return launch_bwd<16>(qkv, e1, e2, probs, d_out, d_qkv, d_e1, d_e2, M, H, q_scale, st);
-    case 8: return launch_bwd<8>(qkv, e1, e2, probs, d_out, d_qkv, d_e1, d_e2, M, H, q_scale, st);
-    case 4: return launch_bwd<4>(qkv, e1, e2, probs, d_out, d_qkv, d_e1, d_e2, M, H, q_scale, st);
-    case 2: return launch_bwd<2>(qkv, e1, e2, probs, d_out, d_qkv, d_e1, d_e2, M, H, q_scale, st);
-    case 1: return launch_bwd<1>(qkv, e1, e2, probs, d_out, d_qkv, d_e1, d_e2, M, H, q_scale, st);
+    case 16: return launch_bwd<16>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
+    case 8: return launch_bwd<8>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
+    case 4: return launch_bwd<4>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
+    case 2: return launch_bwd<2>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
+    case 1: return launch_bwd<1>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
     default: VQ_CHECK_ARG(false, "attn_bwd: block length L must be 1, 2, 4, 8 or 16 (got %d)", L);
   }
   return VQ_OK;

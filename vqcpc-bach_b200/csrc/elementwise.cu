@@ -5,6 +5,21 @@
 
 namespace {
 
+// (hi, lo) bf16 split of 4 floats, stored as two 8-byte vectors
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
+  __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                h3 = __float2bfloat16_rn(v.w);
+  __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+  uint2 hv, lv;
+  hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lv.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lv.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(hi) = hv;
+  *reinterpret_cast<uint2*>(lo) = lv;
+}
+
 constexpr int MAX_VOICES = 8;
 struct TablePtrs {
   const float* t[MAX_VOICES];
@@ -102,7 +117,8 @@ __global__ void posemb_bwd_kernel(const float* __restrict__ dh, int ld, int col0
 template <int VPL>   // float4 per lane; d = 128 * VPL
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, int64_t M, float eps) {
+                     float* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd, int64_t M, float eps,
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   const int d = 128 * VPL;
   int lane = threadIdx.x & 31;
   int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -137,7 +153,8 @@ layernorm_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamm
       o.y = (x[i].y - mu) * rs * g[i].y + b[i].y;
       o.z = (x[i].z - mu) * rs * g[i].z + b[i].z;
       o.w = (x[i].w - mu) * rs * g[i].w + b[i].w;
-      st4(out + r * d + (i * 32 + lane) * 4, o);
+      if (out) st4(out + r * d + (i * 32 + lane) * 4, o);
+      if (out_hi) store_split4(out_hi + r * d + (i * 32 + lane) * 4, out_lo + r * d + (i * 32 + lane) * 4, o);
     }
     if (lane == 0) {
       mean[r] = mu;
@@ -150,7 +167,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dy,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M,
+                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
   const int d = 128 * VPL;
   __shared__ float red[2][8][128 * VPL];   // [dgamma|dbeta][warp][col]   (VPL=4: 32 KB)
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -187,6 +205,7 @@ layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y
       o.z = (go[i].z - c1 - xh[i].z * c2) * rs;
       o.w = (go[i].w - c1 - xh[i].w * c2) * rs;
       st4(dy + r * d + (i * 32 + lane) * 4, o);
+      if (dy_hi) store_split4(dy_hi + r * d + (i * 32 + lane) * 4, dy_lo + r * d + (i * 32 + lane) * 4, o);
     }
   }
 #pragma unroll
@@ -239,8 +258,47 @@ __global__ void scatter_rows_kernel(const float* __restrict__ dout, float* __res
 // ----------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[n] += sum_m x[m, n]
 // ----------------------------------------------------------------------------------------------
+// each warp covers 128 columns (float4 per lane); 8 warps stride over the rows of the CTA's row range.
+// SPLIT: x is given as bf16 (hi, lo) and summed as hi + lo.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int64_t M, int N, int64_t rows_per_cta) {
+colsum_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int ld,
+              float* __restrict__ out, int64_t M, int N, int64_t rows_per_cta) {
+  __shared__ float4 red[8][32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int col = blockIdx.x * 128 + lane * 4;
+  int64_t r0 = blockIdx.y * rows_per_cta;
+  int64_t r1 = min(M, r0 + rows_per_cta);
+  float4 a = make_float4(0, 0, 0, 0);
+  if (col < N) {
+    for (int64_t r = r0 + w; r < r1; r += 8) {
+      float4 v;
+      if (SPLIT) {
+        uint2 h = *reinterpret_cast<const uint2*>(xh + r * ld + col);
+        uint2 l = *reinterpret_cast<const uint2*>(xl + r * ld + col);
+        v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+        v.y = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+        v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+        v.w = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+      } else {
+        v = ld4(x + r * ld + col);
+      }
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && col < N) {
+    float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s.x += red[i][lane].x; s.y += red[i][lane].y; s.z += red[i][lane].z; s.w += red[i][lane].w; }
+    atomicAdd(out + col, s.x); atomicAdd(out + col + 1, s.y); atomicAdd(out + col + 2, s.z); atomicAdd(out + col + 3, s.w);
+  }
+}
+
+// generic (any N / ld) scalar fallback
+__global__ void __launch_bounds__(256)
+colsum_scalar_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int64_t M, int N, int64_t rows_per_cta) {
   __shared__ float red[8][32];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int col = blockIdx.x * 32 + lane;
@@ -404,17 +462,20 @@ VQ_API int vqcpc_posemb_bwd(const float* dh, int ld, int col0, float* dchan, flo
 }
 
 // transformer/transformer_custom.py:283,289 (nn.LayerNorm(d_model), eps=1e-5); saves mean / rstd for backward
-VQ_API int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
-                               int64_t M, int d, float eps, void* stream) {
+VQ_API int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, float* out, void* out_hi, void* out_lo,
+                               float* mean, float* rstd, int64_t M, int d, float eps, void* stream) {
   VQ_CHECK_ARG(d == 128 || d == 256 || d == 512 || d == 1024, "layernorm: d_model must be 128/256/512/1024 (got %d)", d);
+  VQ_CHECK_ARG((out || out_hi) && ((out_hi == nullptr) == (out_lo == nullptr)), "layernorm: need out and/or (out_hi, out_lo)");
   if (M == 0) return VQ_OK;
   int grid = grid_for(M, 8, 8);
   cudaStream_t st = vq_stream(stream);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   switch (d / 128) {
-    case 1: layernorm_fwd_kernel<1><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps); break;
-    case 2: layernorm_fwd_kernel<2><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps); break;
-    case 4: layernorm_fwd_kernel<4><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps); break;
-    default: layernorm_fwd_kernel<8><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps); break;
+    case 1: layernorm_fwd_kernel<1><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps, oh, ol); break;
+    case 2: layernorm_fwd_kernel<2><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps, oh, ol); break;
+    case 4: layernorm_fwd_kernel<4><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps, oh, ol); break;
+    default: layernorm_fwd_kernel<8><<<grid, 256, 0, st>>>(y, gamma, beta, out, mean, rstd, M, eps, oh, ol); break;
   }
   VQ_CUDA_LAUNCH_CHECK("layernorm_fwd_kernel");
   return VQ_OK;
@@ -422,15 +483,19 @@ VQ_API int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* 
 
 // d_y = LN backward wrt its input; d_gamma / d_beta are ACCUMULATED (+=)
 VQ_API int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
-                               float* d_y, float* d_gamma, float* d_beta, int64_t M, int d, void* stream) {
+                               float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, int64_t M, int d,
+                               void* stream) {
   VQ_CHECK_ARG(d == 128 || d == 256 || d == 512, "layernorm_bwd: d_model must be 128/256/512 (got %d)", d);
+  VQ_CHECK_ARG((d_y_hi == nullptr) == (d_y_lo == nullptr), "layernorm_bwd: d_y_hi/d_y_lo must be given together");
   if (M == 0) return VQ_OK;
   int grid = grid_for(M, 8 * 16, 4);
   cudaStream_t st = vq_stream(stream);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d_y_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d_y_lo);
   switch (d / 128) {
-    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M); break;
-    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M); break;
-    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M); break;
+    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
+    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
+    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
   }
   VQ_CUDA_LAUNCH_CHECK("layernorm_bwd_kernel");
   return VQ_OK;
@@ -454,17 +519,34 @@ VQ_API int vqcpc_subsample_bwd(const float* d_out, float* d_x, int64_t P, int L,
   return VQ_OK;
 }
 
-// bias gradients: out[n] += sum_m x[m, n]
-VQ_API int vqcpc_colsum(const float* x, int ld, float* out, int64_t M, int N, void* stream) {
+static int colsum_launch(const float* x, const void* xh, const void* xl, int ld, float* out, int64_t M, int N, cudaStream_t st) {
   if (M == 0) return VQ_OK;
-  int gx = (int)vq_cdiv(N, 32);
+  bool vec = (N % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x ? (const void*)x : xh) & 15) == 0 || xh);
+  if (xh) VQ_CHECK_ARG(N % 4 == 0 && ld % 4 == 0, "colsum_split: N and ld must be multiples of 4");
+  int gx = (int)vq_cdiv(N, vec ? 128 : 32);
   int64_t want_y = std::max<int64_t>(1, (int64_t)vq_sm_count() * 4 / gx);
   int64_t rows_per_cta = std::max<int64_t>(64, vq_cdiv(M, want_y));
   int gy = (int)vq_cdiv(M, rows_per_cta);
   VQ_CHECK_ARG(gy <= 65535, "colsum: grid too large");
-  colsum_kernel<<<dim3(gx, gy), 256, 0, vq_stream(stream)>>>(x, ld, out, M, N, rows_per_cta);
+  if (xh)
+    colsum_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(nullptr, reinterpret_cast<const __nv_bfloat16*>(xh),
+                                                      reinterpret_cast<const __nv_bfloat16*>(xl), ld, out, M, N, rows_per_cta);
+  else if (vec)
+    colsum_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(x, nullptr, nullptr, ld, out, M, N, rows_per_cta);
+  else
+    colsum_scalar_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, ld, out, M, N, rows_per_cta);
   VQ_CUDA_LAUNCH_CHECK("colsum_kernel");
   return VQ_OK;
+}
+
+// bias gradients: out[n] += sum_m x[m, n]
+VQ_API int vqcpc_colsum(const float* x, int ld, float* out, int64_t M, int N, void* stream) {
+  return colsum_launch(x, nullptr, nullptr, ld, out, M, N, vq_stream(stream));
+}
+// same on a bf16 (hi, lo) split matrix: out[n] += sum_m (hi + lo)[m, n]
+VQ_API int vqcpc_colsum_split(const void* x_hi, const void* x_lo, int ld, float* out, int64_t M, int N, void* stream) {
+  VQ_CHECK_ARG(x_hi && x_lo, "colsum_split: null input");
+  return colsum_launch(nullptr, x_hi, x_lo, ld, out, M, N, vq_stream(stream));
 }
 
 // upscalers/mlp_upscaler.py:21-26 nn.SELU
