@@ -99,6 +99,9 @@ int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K, const 
                          const float* bias, const void* residual, int ldr, int flags, float alpha, int scale_ncols,
                          int passes, int ksplit, void* stream);
 
+/* tuning / test hook: force the tcgen05 tile configuration (0 = 128x128x64, 1 = 128x256x32, -1 = automatic by N). */
+int vqcpc_gemm_set_tile_config(int cfg);
+
 /* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +
  *      subsampled_relative_attention.py:30-122) ---------------------------------------------------------------------
  * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64).  Only the query rows with token % keep == 0 are

@@ -32,6 +32,7 @@ SIGNATURES = {
     'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],
     'vqcpc_gemm_bf16x3': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
     'vqcpc_gemm_bf16x3_ex': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
+    'vqcpc_gemm_set_tile_config': [_I],
     'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     'vqcpc_vq_search': [_P, _L, _I, _P, _I, _I, _P, _P],

@@ -10,6 +10,7 @@ GEMM arithmetic modes (``set_gemm_mode``):
 Small / oddly shaped GEMMs (K < 32, N < 32, unaligned leading dimensions) always run the fp32 kernel.
 """
 import ctypes
+import os
 
 import torch
 
@@ -20,6 +21,15 @@ EPI_BIAS, EPI_RELU, EPI_ACCUMULATE, EPI_RESIDUAL, EPI_RELU_MASK, EPI_SCALE_COLS,
 _GEMM_MODE = 'bf16x3'
 PROFILE_GEMM = None         # bench.py sets this to a list: every GEMM launch is bracketed by CUDA events on its stream
 _WSPLIT_CACHE = {}          # id(param storage) -> (version, hi, lo)
+
+
+def set_tile_config(cfg):
+    """Force the tcgen05 tile configuration: 0 = 128x128x64, 1 = 128x256x32, -1 = automatic (by N)."""
+    _native.call('vqcpc_gemm_set_tile_config', int(cfg))
+
+
+if os.environ.get('VQCPC_GEMM_TILE') is not None:
+    set_tile_config(int(os.environ['VQCPC_GEMM_TILE']))
 
 
 def set_gemm_mode(mode):

@@ -19,13 +19,15 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128;
 constexpr int UMMA_K = 16;
 constexpr int NUM_ACC = 2;
-constexpr int TMEM_COLS = NUM_ACC * BN;           // 256 (power of two)
-constexpr int TILE_A_BYTES = BM * BK * 2;         // 16 KB
-constexpr int TILE_B_BYTES = BN * BK * 2;         // 16 KB
 constexpr int THREADS = 192;
+// Tile configurations (template parameters BN, BK):
+//   128 x 128 x 64, 3 stages  - narrow N; every MMA reads 8 KB of smem per 64 cycles (at the 128 B/clk smem limit)
+//   128 x 256 x 32, 4 stages  - default for N >= 256: 12 KB per 128 cycles, and a deeper ring to hide TMA latency
+// K-major operand tiles use the swizzle whose span equals the tile row (BK*2 bytes: 128B or 64B);
+// MN-major tiles are chunks of [BK k-rows][64 mn] with the 128B swizzle.
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,18 +106,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  tile [rows][64 bf16] (128 B rows, 8-row swizzle atoms): SBO = 1024 B, LBO unused (=16 B)
 //   MN-major tile = chunks of [64 k-rows][64 mn] (8 KB each, one TMA box): LBO = 8192 B between 64-wide mn chunks,
 //                   SBO = 1024 B between groups of 8 k-rows
+template <int BK>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool kmajor) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  uint32_t lbo = kmajor ? 16u : 8192u;
-  uint32_t sbo = 1024u;
+  // K-major: rows of BK*2 bytes, 8-row swizzle atoms -> SBO = 8 * BK * 2; LBO unused.
+  // MN-major: 64-wide (128 B) mn chunks of BK k-rows each -> LBO = BK * 128 between chunks, SBO = 1024 (8 k-rows).
+  uint32_t lbo = kmajor ? 16u : (uint32_t)(BK * 128);
+  uint32_t sbo = kmajor ? (uint32_t)(16 * BK) : 1024u;
+  uint32_t layout = (kmajor && BK == 32) ? 4u : 2u;       // SWIZZLE_64B : SWIZZLE_128B
   d |= (uint64_t)(lbo >> 4) << 16;
   d |= (uint64_t)(sbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
+template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc(bool a_kmajor, bool b_kmajor) {
   return (1u << 4)                         // D format: f32
          | (1u << 7)                       // A format: bf16
@@ -137,10 +144,14 @@ struct TcParams {
   int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES>
+template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
+  constexpr int TILE_A_BYTES = BM * BK * 2;
+  constexpr int TILE_B_BYTES = BN * BK * 2;
+  constexpr int TMEM_COLS = NUM_ACC * BN;                  // 256 or 512 (power of two)
+  constexpr int CHUNK_BYTES = BK * 128;                    // one MN-major TMA box: [BK k-rows][64 mn]
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
@@ -193,29 +204,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, STAGE_BYTES);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), b_hi = smem_u32(st + TILE_A_BYTES);
-          const uint32_t a_lo = smem_u32(st + TILE_A_BYTES + TILE_B_BYTES), b_lo = a_lo + TILE_A_BYTES;
+          const uint32_t a_hi = smem_u32(st), b_hi = a_hi + TILE_A_BYTES;
+          const uint32_t a_lo = b_hi + TILE_B_BYTES, b_lo = a_lo + TILE_A_BYTES;
           const int k0 = kb * BK;
           if (A_KMAJOR) {
             tma_load_2d(a_hi, &tmA_hi, fb, k0, m0);
             if (PASSES == 3) tma_load_2d(a_lo, &tmA_lo, fb, k0, m0);
           } else {
-            tma_load_2d(a_hi, &tmA_hi, fb, m0, k0);
-            tma_load_2d(a_hi + 8192, &tmA_hi, fb, m0 + 64, k0);
-            if (PASSES == 3) {
-              tma_load_2d(a_lo, &tmA_lo, fb, m0, k0);
-              tma_load_2d(a_lo + 8192, &tmA_lo, fb, m0 + 64, k0);
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) {
+              tma_load_2d(a_hi + c * CHUNK_BYTES, &tmA_hi, fb, m0 + c * 64, k0);
+              if (PASSES == 3) tma_load_2d(a_lo + c * CHUNK_BYTES, &tmA_lo, fb, m0 + c * 64, k0);
             }
           }
           if (B_KMAJOR) {
             tma_load_2d(b_hi, &tmB_hi, fb, k0, n0);
             if (PASSES == 3) tma_load_2d(b_lo, &tmB_lo, fb, k0, n0);
           } else {
-            tma_load_2d(b_hi, &tmB_hi, fb, n0, k0);
-            tma_load_2d(b_hi + 8192, &tmB_hi, fb, n0 + 64, k0);
-            if (PASSES == 3) {
-              tma_load_2d(b_lo, &tmB_lo, fb, n0, k0);
-              tma_load_2d(b_lo + 8192, &tmB_lo, fb, n0 + 64, k0);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) {
+              tma_load_2d(b_hi + c * CHUNK_BYTES, &tmB_hi, fb, n0 + c * 64, k0);
+              if (PASSES == 3) tma_load_2d(b_lo + c * CHUNK_BYTES, &tmB_lo, fb, n0 + c * 64, k0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -225,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_KMAJOR, B_KMAJOR);
+      constexpr uint32_t idesc = make_idesc<BN>(A_KMAJOR, B_KMAJOR);
       constexpr uint32_t A_STEP = A_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per K=16 step inside a stage
       constexpr uint32_t B_STEP = B_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);
       int stage = 0, acc = 0;
@@ -241,16 +250,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tcgen05_fence_after();
           uint8_t* st = smem + stage * STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), b_hi = smem_u32(st + TILE_A_BYTES);
-          const uint32_t a_lo = smem_u32(st + TILE_A_BYTES + TILE_B_BYTES), b_lo = a_lo + TILE_A_BYTES;
+          const uint32_t a_hi = smem_u32(st), b_hi = a_hi + TILE_A_BYTES;
+          const uint32_t a_lo = b_hi + TILE_B_BYTES, b_lo = a_lo + TILE_A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da_hi = make_desc(a_hi + k * A_STEP, A_KMAJOR);
-            const uint64_t db_hi = make_desc(b_hi + k * B_STEP, B_KMAJOR);
+            const uint64_t da_hi = make_desc<BK>(a_hi + k * A_STEP, A_KMAJOR);
+            const uint64_t db_hi = make_desc<BK>(b_hi + k * B_STEP, B_KMAJOR);
             const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
             if (PASSES == 3) {
-              const uint64_t da_lo = make_desc(a_lo + k * A_STEP, A_KMAJOR);
-              const uint64_t db_lo = make_desc(b_lo + k * B_STEP, B_KMAJOR);
+              const uint64_t da_lo = make_desc<BK>(a_lo + k * A_STEP, A_KMAJOR);
+              const uint64_t db_lo = make_desc<BK>(b_lo + k * B_STEP, B_KMAJOR);
               umma_bf16(tmem_d, da_lo, db_hi, idesc, first);
               umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
               umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
@@ -437,13 +446,15 @@ int get_encode() {
 
 // 2-D bf16 tensor map over a row-major [rows][cols] matrix (leading dimension ld elements), 128B swizzle.
 // box = 64 columns (128 bytes) x box_rows rows.
-int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+             uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;   // span = box row bytes
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     vq_set_error("gemm_bf16x3: cuTensorMapEncodeTiled failed (CUresult %d; rows=%llu cols=%llu ld=%llu)", (int)r,
@@ -453,21 +464,38 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return VQ_OK;
 }
 
-template <bool AK, bool BK_, int PASSES>
-int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
-  constexpr int STAGES = PASSES == 3 ? 3 : 6;
-  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
+template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES>
+int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK * 2 + BN * BK * 2);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   static bool done = false;
   if (!done) {
-    VQ_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<AK, BK_, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VQ_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     done = true;
   }
   int items = p.m_tiles * p.n_tiles * p.ksplit;
   int grid = std::min(items, vq_sm_count());
-  gemm_tc_kernel<AK, BK_, PASSES, STAGES><<<grid, THREADS, SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES><<<grid, THREADS, SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   VQ_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
   return VQ_OK;
+}
+
+// tile configuration ids: 0 = 128x128x64 (3 / 6 stages), 1 = 128x256x32 (4 / 8 stages)
+int g_force_cfg = -1;
+inline int pick_cfg(int N) {
+  if (g_force_cfg >= 0) return g_force_cfg;
+  return N >= 256 ? 1 : 0;
+}
+
+template <bool AK, bool BKM>
+int launch_tc(int cfg, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+  if (cfg == 1) {
+    if (passes == 3) return launch_cfg<AK, BKM, 3, 256, 32, 4>(maps, p, st);
+    return launch_cfg<AK, BKM, 1, 256, 32, 8>(maps, p, st);
+  }
+  if (passes == 3) return launch_cfg<AK, BKM, 3, 128, 64, 3>(maps, p, st);
+  return launch_cfg<AK, BKM, 1, 128, 64, 6>(maps, p, st);
 }
 
 }  // namespace
@@ -498,6 +526,8 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
+  const int cfg = pick_cfg(N);
+  const int BN = cfg == 1 ? 256 : 128, BK = cfg == 1 ? 32 : 64;
   p.m_tiles = (int)vq_cdiv(M, BM);
   p.n_tiles = (int)vq_cdiv(N, BN);
   p.kblocks_total = (int)vq_cdiv(K, BK);
@@ -515,28 +545,32 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   CUtensorMap maps[4];
   const void* alo = passes == 3 ? A_lo : A_hi;
   const void* blo = passes == 3 ? B_lo : B_hi;
-  if (a_kmajor) {   // [M rows][K cols]
-    if ((rc = make_map(&maps[0], A_hi, M, K, lda, BM)) != VQ_OK) return rc;
-    if ((rc = make_map(&maps[1], alo, M, K, lda, BM)) != VQ_OK) return rc;
-  } else {          // [K rows][M cols]
-    if ((rc = make_map(&maps[0], A_hi, K, M, lda, BK)) != VQ_OK) return rc;
-    if ((rc = make_map(&maps[1], alo, K, M, lda, BK)) != VQ_OK) return rc;
+  if (a_kmajor) {   // [M rows][K cols]: box = BK cols x 128 rows
+    if ((rc = make_map(&maps[0], A_hi, M, K, lda, BK, BM)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[1], alo, M, K, lda, BK, BM)) != VQ_OK) return rc;
+  } else {          // [K rows][M cols]: box = 64 cols x BK rows
+    if ((rc = make_map(&maps[0], A_hi, K, M, lda, 64, BK)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[1], alo, K, M, lda, 64, BK)) != VQ_OK) return rc;
   }
   if (b_kmajor) {   // [N rows][K cols]
-    if ((rc = make_map(&maps[2], B_hi, N, K, ldb, BN)) != VQ_OK) return rc;
-    if ((rc = make_map(&maps[3], blo, N, K, ldb, BN)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[2], B_hi, N, K, ldb, BK, BN)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[3], blo, N, K, ldb, BK, BN)) != VQ_OK) return rc;
   } else {          // [K rows][N cols]
-    if ((rc = make_map(&maps[2], B_hi, K, N, ldb, BK)) != VQ_OK) return rc;
-    if ((rc = make_map(&maps[3], blo, K, N, ldb, BK)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[2], B_hi, K, N, ldb, 64, BK)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[3], blo, K, N, ldb, 64, BK)) != VQ_OK) return rc;
   }
 
-#define VQ_TC(AK, BKM)                                                             \
-  (passes == 3 ? launch_tc<AK, BKM, 3>(maps, p, st) : launch_tc<AK, BKM, 1>(maps, p, st))
-  if (a_kmajor && b_kmajor) return VQ_TC(true, true);
-  if (a_kmajor && !b_kmajor) return VQ_TC(true, false);
-  if (!a_kmajor && b_kmajor) return VQ_TC(false, true);
-  return VQ_TC(false, false);
-#undef VQ_TC
+  if (a_kmajor && b_kmajor) return launch_tc<true, true>(cfg, passes, maps, p, st);
+  if (a_kmajor && !b_kmajor) return launch_tc<true, false>(cfg, passes, maps, p, st);
+  if (!a_kmajor && b_kmajor) return launch_tc<false, true>(cfg, passes, maps, p, st);
+  return launch_tc<false, false>(cfg, passes, maps, p, st);
+}
+
+// Testing / tuning hook: force a tile configuration (0 = 128x128x64, 1 = 128x256x32, -1 = automatic by N).
+VQ_API int vqcpc_gemm_set_tile_config(int cfg) {
+  VQ_CHECK_ARG(cfg >= -1 && cfg <= 1, "gemm_set_tile_config: cfg must be -1, 0 or 1");
+  g_force_cfg = cfg;
+  return VQ_OK;
 }
 
 VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
