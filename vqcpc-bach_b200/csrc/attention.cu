@@ -175,9 +175,58 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward: given dO, recomputes nothing but reads the saved probabilities.
-//   dV = A^T dO ; dA = dO V^T ; dS = A * (dA - rowsum(A*dA)) ; dq~ = dS (K + E) ; dK = dS^T q~ ;
-//   dE1[h][L-1-(i-j)] += dS[i][j] q~_i (j<=i) ; dE2[h][j-i] += dS[i][j] q~_i (j>i) ; dq = q_scale * dq~.
+// backward: reads the saved probabilities A (nothing is recomputed).
+//   dA = dO V^T ; dS = A * (dA - rowsum(A*dA)) ; dQ~ = dS K + T1 e1 + T2 e2 ; dK = dS^T Q~ ; dV = A^T dO ;
+//   dE1 = T1^T Q~ ; dE2 = T2^T Q~ ; dq = q_scale * dq~
+// where T1 / T2 are dS "skewed" onto the relative index: T1[i][L-1-(i-j)] = dS[i][j] (j <= i), T2[i][j-i] = dS[i][j]
+// (j > i).  With that, every product is a small dense matmul over the 16-row tile, evaluated with register-blocked
+// FMAs: 16x16 results use a (2 rows x 4 cols) tile per lane, 16x64 results a (4 rows x 8 cols) tile per lane with the
+// reduction index vectorised by 4 -> ~10 FMA per shared-memory load instead of ~4.
+constexpr int PS = 20;   // padded stride of the 16x16 matrices (rows 16-byte aligned)
+
+// acc[4][8] += sum_k Msm[row(rg,ri)][k] * Bsm[k][dg*8 .. +8]   for k in [0, 16): "rows x reduction" coefficient matrix
+__device__ __forceinline__ void mm_rows(float (&acc)[4][8], const float* __restrict__ Msm, const float* __restrict__ Bsm,
+                                        int rg, int dg) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    float4 m[4];
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) m[ri] = ld4(Msm + (rg * 4 + ri) * PS + k4 * 4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float4 b0 = ld4(Bsm + (k4 * 4 + kk) * TS + dg * 8);
+      float4 b1 = ld4(Bsm + (k4 * 4 + kk) * TS + dg * 8 + 4);
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        float w = kk == 0 ? m[ri].x : (kk == 1 ? m[ri].y : (kk == 2 ? m[ri].z : m[ri].w));
+        acc[ri][0] = fmaf(w, b0.x, acc[ri][0]); acc[ri][1] = fmaf(w, b0.y, acc[ri][1]);
+        acc[ri][2] = fmaf(w, b0.z, acc[ri][2]); acc[ri][3] = fmaf(w, b0.w, acc[ri][3]);
+        acc[ri][4] = fmaf(w, b1.x, acc[ri][4]); acc[ri][5] = fmaf(w, b1.y, acc[ri][5]);
+        acc[ri][6] = fmaf(w, b1.z, acc[ri][6]); acc[ri][7] = fmaf(w, b1.w, acc[ri][7]);
+      }
+    }
+  }
+}
+
+// acc[4][8] += sum_r Msm[r][cg*4 + ci] * Bsm[r][dg*8 .. +8]   for r in [0, 16): transposed coefficient matrix
+__device__ __forceinline__ void mm_cols(float (&acc)[4][8], const float* __restrict__ Msm, const float* __restrict__ Bsm,
+                                        int cg, int dg) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float4 m = ld4(Msm + r * PS + cg * 4);
+    float4 b0 = ld4(Bsm + r * TS + dg * 8);
+    float4 b1 = ld4(Bsm + r * TS + dg * 8 + 4);
+    const float w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      acc[ci][0] = fmaf(w[ci], b0.x, acc[ci][0]); acc[ci][1] = fmaf(w[ci], b0.y, acc[ci][1]);
+      acc[ci][2] = fmaf(w[ci], b0.z, acc[ci][2]); acc[ci][3] = fmaf(w[ci], b0.w, acc[ci][3]);
+      acc[ci][4] = fmaf(w[ci], b1.x, acc[ci][4]); acc[ci][5] = fmaf(w[ci], b1.y, acc[ci][5]);
+      acc[ci][6] = fmaf(w[ci], b1.z, acc[ci][6]); acc[ci][7] = fmaf(w[ci], b1.w, acc[ci][7]);
+    }
+  }
+}
+
 template <int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
@@ -185,172 +234,178 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
                 __nv_bfloat16* __restrict__ dqkv_hi, __nv_bfloat16* __restrict__ dqkv_lo,
                 float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale, int keep) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int PS = 17;   // padded stride of the 16x16 matrices
-  constexpr int PER_WARP = 4 * TR * TS + 2 * TR * PS;
-  float* e1s = smem;
-  float* e2s = e1s + L * TS;
+  constexpr int PER_WARP = 4 * TR * TS + 4 * TR * PS;
+  float* e1s = smem;                     // [16][TS], rows >= L are zero
+  float* e2s = e1s + TR * TS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* qs = e2s + L * TS + warp * PER_WARP;
+  float* qs = e2s + TR * TS + warp * PER_WARP;
   float* ks = qs + TR * TS;
   float* vs = ks + TR * TS;
-  float* gs = vs + TR * TS;          // dO tile
-  float* As = gs + TR * TS;          // probabilities [16][17] (zero outside the block)
-  float* Ds = As + TR * PS;          // dS
+  float* gs = vs + TR * TS;              // dO tile
+  float* As = gs + TR * TS;              // probabilities [16][PS] (zero outside the block / for dropped rows)
+  float* Ds = As + TR * PS;              // dS
+  float* T1 = Ds + TR * PS;              // dS skewed onto the causal table index
+  float* T2 = T1 + TR * PS;              // ... anticausal
   const int h = blockIdx.y;
   const int d = H * HD;
-  for (int i = threadIdx.x; i < L * 16; i += blockDim.x) {
+  for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
     int r = i / 16, c = (i % 16) * 4;
-    st4(e1s + r * TS + c, ld4(e1 + ((size_t)h * L + r) * HD + c));
-    st4(e2s + r * TS + c, ld4(e2 + ((size_t)h * L + r) * HD + c));
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if (r < L) {
+      a = ld4(e1 + ((size_t)h * L + r) * HD + c);
+      b = ld4(e2 + ((size_t)h * L + r) * HD + c);
+    }
+    st4(e1s + r * TS + c, a);
+    st4(e2s + r * TS + c, b);
   }
   __syncthreads();
 
-  const int r = lane >> 1, jh = lane & 1;
-  const int g = r / L, i = r % L;
-  // relative-table gradient accumulators: lane (idx = lane/2, half = lane%2) owns 32 columns of row idx
-  float4 acc1[8], acc2[8];
+  // lane tilings
+  const int r2 = (lane >> 2) * 2, c4 = (lane & 3) * 4;      // 16x16 products: rows r2, r2+1; cols c4..c4+3
+  const int rg = lane >> 3, dg = lane & 7;                   // 16x64 products: rows rg*4..+3; cols dg*8..+7
+  const int sr = lane >> 1, sh = lane & 1;                   // skew step: row sr, table indices sh*8..+7
+  float acc_e1[4][8], acc_e2[4][8];                          // dE1 / dE2 rows rg*4..+3 (table index), cols dg*8..+7
 #pragma unroll
-  for (int x = 0; x < 8; ++x) { acc1[x] = make_float4(0, 0, 0, 0); acc2[x] = make_float4(0, 0, 0, 0); }
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { acc_e1[a][b] = 0.f; acc_e2[a][b] = 0.f; }
 
   for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
     const int64_t row0 = tile * TR;
-    const int64_t gr = row0 + r;
     __syncwarp();
     load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
     load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
     load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
     if (keep == 1) load_tile(gs, dout + h * HD, row0, M, d, lane);
     else load_tile_compact(gs, dout + h * HD, row0, M, d, lane, L, keep);     // dO exists for the kept query rows only
-    const bool kept = (i % keep) == 0;
-    float a[8];
+    // probabilities of this lane's 2x4 patch
+    float a[2][4];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      int c = jh * 8 + jj;
-      float v = 0.f;
-      if (kept && gr < M && c / L == g) v = probs[(((gr / L) * H + h) * L + i) * L + (c % L)];
-      a[jj] = v;
-      As[r * PS + c] = v;
+    for (int ri = 0; ri < 2; ++ri) {
+      const int r = r2 + ri;
+      const int64_t gr = row0 + r;
+      const int i = r % L;
+      const bool rowok = gr < M && (i % keep) == 0;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = c4 + ci;
+        float v = 0.f;
+        if (rowok && c / L == r / L) v = probs[(((gr / L) * H + h) * L + i) * L + (c % L)];
+        a[ri][ci] = v;
+      }
+      st4(As + r * PS + c4, make_float4(a[ri][0], a[ri][1], a[ri][2], a[ri][3]));
     }
     __syncwarp();
 
-    // dA[r][c] = dO[r] . v[c]
-    float da[8];
+    // ---- dA = dO V^T on the 2x4 patch, then dS
+    float da[2][4];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) da[jj] = 0.f;
+    for (int ri = 0; ri < 2; ++ri)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) da[ri][ci] = 0.f;
 #pragma unroll 4
     for (int d4 = 0; d4 < 16; ++d4) {
-      float4 g4 = ld4(gs + r * TS + d4 * 4);
+      float4 g0 = ld4(gs + r2 * TS + d4 * 4), g1 = ld4(gs + (r2 + 1) * TS + d4 * 4);
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        int c = jh * 8 + jj;
-        if (c / L == g) da[jj] += dot4(g4, ld4(vs + c * TS + d4 * 4));
+      for (int ci = 0; ci < 4; ++ci) {
+        float4 v4 = ld4(vs + (c4 + ci) * TS + d4 * 4);
+        da[0][ci] += dot4(g0, v4);
+        da[1][ci] += dot4(g1, v4);
       }
     }
-    float rd = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) rd += a[jj] * da[jj];
-    rd += __shfl_xor_sync(0xffffffffu, rd, 1);
-    float ds_all[16];
+    for (int ri = 0; ri < 2; ++ri) {
+      float rd = a[ri][0] * da[ri][0] + a[ri][1] * da[ri][1] + a[ri][2] * da[ri][2] + a[ri][3] * da[ri][3];
+      rd += __shfl_xor_sync(0xffffffffu, rd, 1);
+      rd += __shfl_xor_sync(0xffffffffu, rd, 2);
+      st4(Ds + (r2 + ri) * PS + c4, make_float4(a[ri][0] * (da[ri][0] - rd), a[ri][1] * (da[ri][1] - rd),
+                                                a[ri][2] * (da[ri][2] - rd), a[ri][3] * (da[ri][3] - rd)));
+    }
+    __syncwarp();
+    // ---- skew dS onto the relative-table index
+    {
+      const int i = sr % L, gb = (sr / L) * L;
+      float t1[8], t2[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      float v = a[jj] * (da[jj] - rd);
-      float o = __shfl_xor_sync(0xffffffffu, v, 1);
-      ds_all[jj] = jh == 0 ? v : o;
-      ds_all[8 + jj] = jh == 0 ? o : v;
-      Ds[r * PS + jh * 8 + jj] = v;
+      for (int x = 0; x < 8; ++x) {
+        const int idx = sh * 8 + x;
+        const int j1 = i - (L - 1 - idx);            // e1 row idx <-> key j = i - (L-1-idx) <= i
+        const int j2 = i + idx;                      // e2 row idx (>= 1) <-> key j = i + idx > i
+        t1[x] = (idx < L && j1 >= 0) ? Ds[sr * PS + gb + j1] : 0.f;
+        t2[x] = (idx >= 1 && idx < L && j2 < L) ? Ds[sr * PS + gb + j2] : 0.f;
+      }
+      st4(T1 + sr * PS + sh * 8, make_float4(t1[0], t1[1], t1[2], t1[3]));
+      st4(T1 + sr * PS + sh * 8 + 4, make_float4(t1[4], t1[5], t1[6], t1[7]));
+      st4(T2 + sr * PS + sh * 8, make_float4(t2[0], t2[1], t2[2], t2[3]));
+      st4(T2 + sr * PS + sh * 8 + 4, make_float4(t2[4], t2[5], t2[6], t2[7]));
     }
     __syncwarp();
 
-    // dq~[r][jh*32..+32) = sum_c dS[r][c] (k[c] + E(i,j))
-    {
-      float4 o4[8];
+    float acc[4][8];
+    // ---- dQ~ = dS K + T1 e1 + T2 e2   (rows rg*4..+3)
 #pragma unroll
-      for (int x = 0; x < 8; ++x) o4[x] = make_float4(0, 0, 0, 0);
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        if (c / L == g) {
-          float w = ds_all[c];
-          const float* er = bias_row<L>(e1s, e2s, i, c % L);
+      for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+    mm_rows(acc, Ds, ks, rg, dg);
+    mm_rows(acc, T1, e1s, rg, dg);
+    mm_rows(acc, T2, e2s, rg, dg);
 #pragma unroll
-          for (int x = 0; x < 8; ++x)
-            fma4(o4[x], w, add4(ld4(ks + c * TS + jh * 32 + x * 4), ld4(er + jh * 32 + x * 4)));
-        }
-      }
+    for (int ri = 0; ri < 4; ++ri) {
+      const int64_t gr = row0 + rg * 4 + ri;
       if (gr < M) {
+        const int64_t off = gr * 3 * d + h * HD + dg * 8;
+        float4 o0 = make_float4(acc[ri][0] * q_scale, acc[ri][1] * q_scale, acc[ri][2] * q_scale, acc[ri][3] * q_scale);
+        float4 o1 = make_float4(acc[ri][4] * q_scale, acc[ri][5] * q_scale, acc[ri][6] * q_scale, acc[ri][7] * q_scale);
+        if (dqkv) { st4(dqkv + off, o0); st4(dqkv + off + 4, o1); }
+        if (dqkv_hi) { store_split4(dqkv_hi + off, dqkv_lo + off, o0); store_split4(dqkv_hi + off + 4, dqkv_lo + off + 4, o1); }
+      }
+    }
+    // ---- dK = dS^T Q~ ; dV = A^T dO   (rows = key index rg*4..+3)
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          float4 v = o4[x];
-          v.x *= q_scale; v.y *= q_scale; v.z *= q_scale; v.w *= q_scale;
-          const int64_t off = gr * 3 * d + h * HD + jh * 32 + x * 4;
-          if (dqkv) st4(dqkv + off, v);
-          if (dqkv_hi) store_split4(dqkv_hi + off, dqkv_lo + off, v);
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+      if (pass == 0) mm_cols(acc, Ds, qs, rg, dg);
+      else mm_cols(acc, As, gs, rg, dg);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int64_t gr = row0 + rg * 4 + ci;
+        if (gr < M) {
+          const int64_t off = gr * 3 * d + (pass + 1) * d + h * HD + dg * 8;
+          float4 o0 = make_float4(acc[ci][0], acc[ci][1], acc[ci][2], acc[ci][3]);
+          float4 o1 = make_float4(acc[ci][4], acc[ci][5], acc[ci][6], acc[ci][7]);
+          if (dqkv) { st4(dqkv + off, o0); st4(dqkv + off + 4, o1); }
+          if (dqkv_hi) { store_split4(dqkv_hi + off, dqkv_lo + off, o0); store_split4(dqkv_hi + off + 4, dqkv_lo + off + 4, o1); }
         }
       }
     }
-    // dK[c][..] = sum_r dS[r][c] q~[r] ; dV[c][..] = sum_r A[r][c] dO[r]     (lane owns column c = lane/2)
-    {
-      const int c = r;                 // reuse the (lane/2, lane%2) mapping with the row index read as a column
-      float4 k4[8], v4[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) { k4[x] = make_float4(0, 0, 0, 0); v4[x] = make_float4(0, 0, 0, 0); }
-#pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
-        if (rr / L == g) {             // c's block == rr's block
-          float wk = Ds[rr * PS + c], wv = As[rr * PS + c];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            fma4(k4[x], wk, ld4(qs + rr * TS + jh * 32 + x * 4));
-            fma4(v4[x], wv, ld4(gs + rr * TS + jh * 32 + x * 4));
-          }
-        }
-      }
-      if (gr < M) {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          const int64_t offk = gr * 3 * d + d + h * HD + jh * 32 + x * 4, offv = offk + d;
-          if (dqkv) { st4(dqkv + offk, k4[x]); st4(dqkv + offv, v4[x]); }
-          if (dqkv_hi) { store_split4(dqkv_hi + offk, dqkv_lo + offk, k4[x]); store_split4(dqkv_hi + offv, dqkv_lo + offv, v4[x]); }
-        }
-      }
-    }
-    // relative tables: lane (idx = lane/2 < L, half)   dE1[idx] += sum_rows dS[row][j = i-(L-1-idx)] q~[row]
-    {
-      const int idx = r;
-      if (idx < L) {
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          int ii = rr % L, gb = (rr / L) * L;
-          int j1 = ii - (L - 1 - idx);          // causal table e1
-          int j2 = ii + idx;                    // anticausal table e2 (idx >= 1)
-          float w1 = (j1 >= 0) ? Ds[rr * PS + gb + j1] : 0.f;
-          float w2 = (idx >= 1 && j2 < L) ? Ds[rr * PS + gb + j2] : 0.f;
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            float4 q4 = ld4(qs + rr * TS + jh * 32 + x * 4);
-            fma4(acc1[x], w1, q4);
-            fma4(acc2[x], w2, q4);
-          }
-        }
-      }
+    // ---- relative tables: dE1 += T1^T Q~ ; dE2 += T2^T Q~   (rows = table index rg*4..+3; only < L are non-zero)
+    if (rg * 4 < L) {
+      mm_cols(acc_e1, T1, qs, rg, dg);
+      mm_cols(acc_e2, T2, qs, rg, dg);
     }
   }
 
   // reduce the table gradients over the CTA's warps, then one atomic per element per CTA
   __syncthreads();
-  float* red = e2s + L * TS;           // reuse the per-warp staging area: [WARPS][2][L][64]
-  if (r < L) {
+  float* red = e2s + TR * TS;           // reuse the per-warp staging area: [WARPS][2][16][64]
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      st4(red + ((warp * 2 + 0) * L + r) * HD + jh * 32 + x * 4, acc1[x]);
-      st4(red + ((warp * 2 + 1) * L + r) * HD + jh * 32 + x * 4, acc2[x]);
-    }
+  for (int ci = 0; ci < 4; ++ci) {
+    const int idx = rg * 4 + ci;
+    st4(red + ((warp * 2 + 0) * TR + idx) * HD + dg * 8, make_float4(acc_e1[ci][0], acc_e1[ci][1], acc_e1[ci][2], acc_e1[ci][3]));
+    st4(red + ((warp * 2 + 0) * TR + idx) * HD + dg * 8 + 4, make_float4(acc_e1[ci][4], acc_e1[ci][5], acc_e1[ci][6], acc_e1[ci][7]));
+    st4(red + ((warp * 2 + 1) * TR + idx) * HD + dg * 8, make_float4(acc_e2[ci][0], acc_e2[ci][1], acc_e2[ci][2], acc_e2[ci][3]));
+    st4(red + ((warp * 2 + 1) * TR + idx) * HD + dg * 8 + 4, make_float4(acc_e2[ci][4], acc_e2[ci][5], acc_e2[ci][6], acc_e2[ci][7]));
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * L * HD; e += blockDim.x) {
+    const int which = e / (L * HD), rem = e % (L * HD);       // rem = idx * 64 + col, idx < L
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) s += red[w * 2 * L * HD + e];
-    int which = e / (L * HD), rem = e % (L * HD);
+    for (int w = 0; w < WARPS; ++w) s += red[(w * 2 + which) * TR * HD + rem];
     float* dst = (which == 0 ? de1 : de2) + (size_t)h * L * HD + rem;
     atomicAdd(dst, s);
   }
@@ -379,8 +434,8 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
                cudaStream_t st) {
   constexpr int WARPS = 4;
   int64_t ntiles = vq_cdiv(M, TR);
-  size_t smem = (size_t)(2 * L * TS + WARPS * (4 * TR * TS + 2 * TR * 17)) * sizeof(float);
-  static_assert(WARPS * (4 * TR * TS + 2 * TR * 17) >= WARPS * 2 * 16 * HD, "reduction scratch must fit");
+  size_t smem = (size_t)(2 * TR * TS + WARPS * (4 * TR * TS + 4 * TR * PS)) * sizeof(float);
+  static_assert(4 * TR * TS + 4 * TR * PS >= 2 * TR * HD, "reduction scratch must fit in the per-warp staging area");
   static bool done = false;
   if (!done) {
     VQ_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
