@@ -142,6 +142,86 @@ def build_trainer(B, seed):
     return tr, gen, config
 
 
+def bench_quantizer_infonce(B, iters=30, nsets=5):
+    """Stand-alone roofline measurement of the fused quantizer + InfoNCE path at the full batch (BASELINE metric (ii)):
+    one vqcpc_vq_fused_fwd over all P = B*(KL+KR+N*KR) vectors (search + loss + table upscale) followed by one
+    vqcpc_infonce_fwd, back to back over rotating buffer sets larger than L2; and the matching backward pair.
+    Algorithmic bytes: SURVEY.md §8d (36 704 B/sample forward)."""
+    import ctypes
+    from VQCPCB import _native, ops
+    dev = 'cuda'
+    D, zd, cd, Kc = 3, 32, 32, CODEBOOK
+    P = B * (KL + KR + NNEG * KR)
+    n_neg = B * NNEG * KR
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    E = torch.randn(Kc, D, device=dev, generator=g) * 2
+    T = torch.randn(Kc, zd, device=dev, generator=g)
+    J = torch.randn(Kc, zd, D, device=dev, generator=g)
+    W = torch.randn(zd, cd, KR, device=dev, generator=g) * 0.25
+    sets = []
+    for _ in range(nsets):
+        d = dict(z=torch.randn(P, D, device=dev, generator=g) * 2, c=torch.randn(B, cd, device=dev, generator=g),
+                 idx=torch.empty(P, dtype=torch.int64, device=dev), loss=torch.empty(P, device=dev),
+                 y=torch.empty(P, zd, device=dev), u=torch.empty(B, KR, zd, device=dev), pos=torch.empty(B, KR, device=dev),
+                 neg=torch.empty(B, KR, NNEG, device=dev), lse=torch.empty(B, KR, device=dev), nll=torch.empty(B, KR, device=dev),
+                 correct=torch.empty(B, KR, dtype=torch.int32, device=dev), counts=torch.zeros(Kc, dtype=torch.int32, device=dev),
+                 dy=torch.empty(P, zd, device=dev), dz=torch.empty(P, D, device=dev), dc=torch.zeros(B, cd, device=dev),
+                 dW=torch.zeros_like(W), dT=torch.zeros(Kc, zd, device=dev), dE=torch.zeros(Kc, D, device=dev),
+                 gl=torch.full((P,), 1.0 / (3 * B), device=dev))
+        sets.append(d)
+    p_, st = ops._p, ops._stream
+
+    def fwd(d):
+        _native.call('vqcpc_vq_fused_fwd', p_(d['z']), P, D, p_(E), p_(T), Kc, zd, 0.25, 1, p_(d['idx']), p_(d['loss']), None,
+                     p_(d['y']), p_(d['counts']), st())
+        y = d['y']
+        ypos = y[n_neg + B * KL:]                                   # right blocks
+        _native.call('vqcpc_infonce_fwd', p_(d['c']), p_(W), p_(ypos), p_(y), B, NNEG, KR, zd, cd, p_(d['u']), p_(d['pos']),
+                     p_(d['neg']), p_(d['lse']), p_(d['nll']), p_(d['correct']), st())
+
+    def bwd(d):
+        y, dy = d['y'], d['dy']
+        _native.call('vqcpc_infonce_bwd', p_(d['c']), p_(W), p_(y[n_neg + B * KL:]), p_(y), p_(d['u']), p_(d['pos']), p_(d['neg']),
+                     p_(d['lse']), None, 1.0 / B, B, NNEG, KR, zd, cd, p_(d['dc']), p_(d['dW']), p_(dy[n_neg + B * KL:]), p_(dy),
+                     st())
+        _native.call('vqcpc_vq_fused_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(dy), p_(d['gl']),
+                     p_(d['dz']), p_(d['dT']), p_(d['dE']), st())
+
+    def timeit(fn):
+        for d in sets:
+            fn(d)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(sets[i % nsets])
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / iters      # us
+
+    for d in sets:
+        d['dy'].normal_()
+    us_f = timeit(fwd)
+    us_b = timeit(bwd)
+    pk = peaks()
+    vec = KL + KR + NNEG * KR
+    bytes_f = B * (vec * (4 * D + 8 + 4 + 4 * zd) + (KR + NNEG * KR) * 4 * zd + 4 * cd + 8 * KR)        # SURVEY §8d
+    # backward: read dy-producing inputs (y for right+neg, u, scores) and write dy for right+neg; then per vector read
+    # dy (4 zd) + idx (8) + z (4 D) + g_loss (4), write dz (4 D)
+    bytes_b = B * ((KR + NNEG * KR) * 8 * zd + vec * (4 * zd + 8 + 8 * D + 4))
+    search_instr = P * Kc * 12.0                                   # exact direct-form search: ~12 fp32 instr per (vector, code)
+    alu_us = search_instr / (148 * 128 * 1.9e9) * 1e6
+    return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
+                kernels='vq_fused_fwd_kernel + infonce_fwd_kernel (forward); infonce_bwd_kernel + vq_fused_bwd_kernel (backward)',
+                batch=B, vectors=P, algorithmic_bytes_fwd=bytes_f, us_fwd=us_f, achieved=bytes_f / us_f / 1e3,
+                frac=bytes_f / us_f / 1e3 / pk['hbm'], algorithmic_bytes_bwd=bytes_b, us_bwd=us_b,
+                achieved_bwd=bytes_b / us_b / 1e3, frac_bwd=bytes_b / us_b / 1e3 / pk['hbm'],
+                fp32_alu_bound_us_exact_search=alu_us,
+                note='bit-exact direct-form search = ~12 fp32 instr per (vector, code): ALU bound %.0f us at 148 SMs x 128 lanes '
+                     'x 1.9 GHz, above the %.0f us HBM bound; buffers rotate over %d sets (> L2)' % (alu_us, bytes_f / pk['hbm'] / 1e3, nsets))
+
+
 def run_ours(args):
     from VQCPCB import distributed as vq_dist, ops, _native
     rank, world, local = vq_dist.init_from_env()
@@ -209,6 +289,11 @@ def run_ours(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    qi = None
+    if rank == 0 and world == 1 and not args.no_path_roofline:
+        del dev_batches
+        torch.cuda.empty_cache()
+        qi = bench_quantizer_infonce(B)
     if rank != 0:
         return
     pk = peaks()
@@ -246,6 +331,8 @@ def run_ours(args):
         line['roofline'] = roof
     if cpu_val is not None:
         line['cpu_baseline'] = dict(value=cpu_val, unit=UNIT, **cpu_info)
+    if qi is not None:
+        line['roofline_quantizer_infonce'] = qi
     print(json.dumps(line))
 
 
@@ -258,6 +345,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--mode', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-path-roofline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

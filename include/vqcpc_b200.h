@@ -127,6 +127,17 @@ int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* books /*h
                  int ncb, int Kc, const int64_t* idx, float beta, int squared, const float* g_zsg, const float* g_loss,
                  float* d_x, void* stream);
 
+/* Fused single-codebook bottleneck with a dropout-free MLP upscaler folded into a table T = upscaler(E) (Kc, zd):
+ * one pass: exact search -> idx (n) int64, loss (n), optional z_sg (n, D), y = T[idx] (n, zd) (T and y may both be NULL),
+ * counts (Kc) ACCUMULATED or NULL.  Replaces vector_quantizer.py:104-157 + mlp_upscaler.py:21-35 on every vector. */
+int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                       int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, void* stream);
+/* backward: d_x = J[idx]^T dy + g_loss * dloss/dx (J (Kc, zd, D) = upscaler Jacobian at each code; straight-through);
+ * d_T[idx] += dy and d_E[idx] += g_loss * dloss/dq are ACCUMULATED. */
+int vqcpc_vq_fused_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,
+                       float beta, int squared, const float* dy, const float* g_loss, float* d_x, float* d_T, float* d_E,
+                       void* stream);
+
 /* ---- fused InfoNCE (vqcpc_helper.py:5-29, :79-98; vqcpc_encoder_trainer.py:240-272) ---------------------------
  * c (B, cd); W (zd, cd, KR); y_pos (B, KR, zd); y_neg (B, N, KR, zd).  Outputs: u (B, KR, zd), pos (B, KR),
  * neg (B, KR, N), lse (B, KR), nll = lse - pos (B, KR), correct (B, KR) int32 = [pos > max_n neg]. */

@@ -226,3 +226,31 @@ def test_first_call_codebook_init_from_negatives():
     st = tr.step(batch, True, False)
     assert q.initialize is False and torch.isfinite(st['loss'])
     assert float(st['loss_quantize']) >= 0
+
+
+def test_fused_bottleneck_matches_unfused():
+    """Quantizer + upscaler folded into a per-code table (one kernel) vs the per-vector path: same indices, outputs to
+    ulp level (upscale(q) vs upscale(z + (q - z))), gradients to 1e-5."""
+    from VQCPCB import ops
+    ops.set_gemm_mode('fp32')
+    cfg = O.default_cfg(codebook_size=64, KL=2, KR=2)
+    prm = P.make_params(cfg, 0)
+    batch = P.make_batch(cfg, 6, seed=11)
+    res = []
+    for fuse in (False, True):
+        tr = build_product_trainer(cfg)
+        load_params_into(tr, prm)
+        tr.encoder.fuse_bottleneck = fuse
+        tr.encoder.quantizer.track_usage(True)
+        tr.init_optimizers(1e-4, False)
+        tr.train()
+        assert tr.encoder._fusable(False) == fuse
+        zq, idx, ql = tr.encoder(batch['x_right'])
+        st = tr.step(batch, True, False)
+        res.append((zq.detach(), idx, ql.detach(), st, tr.optimizer.flat.grad.clone(), tr.encoder.quantizer.usage_counts.clone()))
+    (z0, i0, q0, s0, g0, c0), (z1, i1, q1, s1, g1, c1) = res
+    assert torch.equal(i0, i1) and torch.equal(c0, c1)
+    assert rel_err(z1, z0) < 1e-6 and rel_err(q1, q0) < 1e-6
+    assert abs(s0['loss'].item() - s1['loss'].item()) < 1e-6 * abs(s0['loss'].item())
+    assert rel_err(g1, g0) < 2e-5, rel_err(g1, g0)
+    ops.set_gemm_mode('bf16x3')

@@ -55,10 +55,34 @@ class Encoder(nn.Module):
         x_embed = self.data_processor.embed(x_proc)
         x_flat = flatten(x_embed)
         z = self.downscaler.forward(x_flat)
+        if self._fusable(corrupt_labels):
+            return self._fused_bottleneck(z)
         z_quantized, encoding_indices, quantization_loss = self.quantizer.forward(z, corrupt_labels=corrupt_labels)
         if self.upscaler is not None:
             z_quantized = self.upscaler(z_quantized)
         return z_quantized, encoding_indices, quantization_loss
+
+    # ---- fused quantizer + upscaler (one kernel over all vectors, the MLP evaluated on the Kc code vectors only) ----
+    fuse_bottleneck = True
+
+    def _fusable(self, corrupt_labels):
+        from .quantizer.vector_quantizer import ProductVectorQuantizer
+        from .upscalers.mlp_upscaler import MlpUpscaler
+        q, u = self.quantizer, self.upscaler
+        return (self.fuse_bottleneck and isinstance(q, ProductVectorQuantizer) and isinstance(u, MlpUpscaler)
+                and q.num_codebooks == 1 and q.codebook_dim in (3, 4, 8, 16, 32) and not q.use_batch_norm
+                and not (self.training and (corrupt_labels or u.dropout > 0))
+                and q.codebook_size * (u.output_dim + 5) * 4 <= 190 * 1024)
+
+    def _fused_bottleneck(self, z):
+        q, u = self.quantizer, self.upscaler
+        if q.initialize:                      # data-dependent codebook init from this very batch (quirk Q5)
+            q._initialize(z.reshape(-1, q.codebook_dim))
+        codebook = q.embeddings[0]
+        table, jac = u.code_table_and_jacobian(codebook)
+        y, idx, loss = ops.FusedVQUpscaleFn.apply(z, codebook, table, jac, q._commitment_cost, q.squared_l2_norm,
+                                                  q.usage_counts)
+        return y, idx, loss
 
     def merge_codes(self, codes):
         """Pack the indices of a product quantizer into one integer per position (encoder.py:97-110)."""

@@ -427,6 +427,48 @@ class QuantizeFn(torch.autograd.Function):
         return (dx.view(shp), None, None, None, None, *dbooks)
 
 
+class FusedVQUpscaleFn(torch.autograd.Function):
+    """Single-codebook quantizer with the (dropout-free) MLP upscaler folded into a per-code table:
+    y = T[argmin_k ||z - E_k||^2],  T = upscaler(E) (Kc, zd).  One kernel forward, one backward.
+
+    Gradients: dz = J[idx]^T dy + commitment term (straight-through: vector_quantizer.py:148 feeds z + (q - z).detach()
+    to the upscaler, so d y / d z is the upscaler Jacobian at q);  dE from the quantisation loss only (q is detached
+    on the upscaler side);  dT[idx] += dy flows on through the autograd graph of T into the upscaler weights."""
+
+    @staticmethod
+    def forward(ctx, z, E, T, J, beta, squared, counts):
+        shp = z.shape
+        D = shp[-1]
+        z2 = _f32c(z).view(-1, D)
+        n = z2.shape[0]
+        Kc, zd = T.shape
+        Ed, Td = _f32c(E.detach()), _f32c(T.detach())
+        idx = torch.empty(n, dtype=torch.int64, device=z.device)
+        loss = torch.empty(n, dtype=torch.float32, device=z.device)
+        y = torch.empty(n, zd, dtype=torch.float32, device=z.device)
+        _native.call('vqcpc_vq_fused_fwd', _p(z2), n, D, _p(Ed), _p(Td), Kc, zd, float(beta), int(squared), _p(idx), _p(loss),
+                     None, _p(y), _p(counts), _stream())
+        ctx.save_for_backward(z2, Ed, J, idx)
+        ctx.meta = (shp, beta, squared, Kc, zd)
+        idx_out = idx.view(*shp[:-1], 1)
+        ctx.mark_non_differentiable(idx_out)
+        return y.view(*shp[:-1], zd), idx_out, loss.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, g_y, _g_idx, g_loss):
+        z2, Ed, J, idx = ctx.saved_tensors
+        shp, beta, squared, Kc, zd = ctx.meta
+        n, D = z2.shape
+        gy = torch.zeros(n, zd, dtype=torch.float32, device=z2.device) if g_y is None else _f32c(g_y).view(n, zd)
+        gl = None if g_loss is None else _f32c(g_loss).reshape(n)
+        dx = torch.empty_like(z2)
+        dT = torch.zeros(Kc, zd, dtype=torch.float32, device=z2.device)
+        dE = torch.zeros_like(Ed)
+        _native.call('vqcpc_vq_fused_bwd', _p(z2), n, D, _p(Ed), _p(J), Kc, zd, _p(idx), float(beta), int(squared), _p(gy), _p(gl),
+                     _p(dx), _p(dT), _p(dE), _stream())
+        return dx.view(shp), dE, dT, None, None, None, None
+
+
 class InfoNCEFn(torch.autograd.Function):
     """Fused Fks scoring + log-sum-exp.  Returns (sum_{b,k} (lse - pos), pos, neg, correct); only the first is
     differentiable.  vqcpc_helper.py:79-98, :5-29; vqcpc_encoder_trainer.py:240-272."""

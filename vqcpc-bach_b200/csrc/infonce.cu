@@ -55,15 +55,32 @@ infonce_fwd_kernel(const float* __restrict__ c, const float* __restrict__ W, con
       return warp_sum(a);
     };
     float p = score(ypos + ((size_t)b * KR + k) * zd);
-    // online log-sum-exp over [neg_0 .. neg_{N-1}, pos]; every lane carries the same running (max, sum)
+    // online log-sum-exp over [neg_0 .. neg_{N-1}, pos]; every lane carries the same running (max, sum).
+    // Negatives are fetched 8 at a time (independent 128-byte loads in flight) before the dependent reduce chain.
     float mx = p, se = 1.f, nmax = -INFINITY;
-    for (int n = 0; n < N; ++n) {
-      float s = score(yneg + (((size_t)b * N + n) * KR + k) * zd);
-      nmax = fmaxf(nmax, s);
-      if (lane == 0) neg_out[((size_t)b * KR + k) * N + n] = s;
-      float m2 = fmaxf(mx, s);
-      se = se * expf(mx - m2) + expf(s - m2);
-      mx = m2;
+    for (int n0 = 0; n0 < N; n0 += 8) {
+      float yv[8][ZPL];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < ZPL; ++t) {
+          int z = lane + 32 * t;
+          yv[j][t] = (n0 + j < N && z < zd) ? yneg[(((size_t)b * N + n0 + j) * KR + k) * zd + z] : 0.f;
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n0 + j < N) {
+          float a = 0.f;
+#pragma unroll
+          for (int t = 0; t < ZPL; ++t) a = fmaf(u[t], yv[j][t], a);     // same fma order as score()
+          float s = warp_sum(a);
+          nmax = fmaxf(nmax, s);
+          if (lane == 0) neg_out[((size_t)b * KR + k) * N + n0 + j] = s;
+          float m2 = fmaxf(mx, s);
+          se = se * expf(mx - m2) + expf(s - m2);
+          mx = m2;
+        }
+      }
     }
     if (lane == 0) {
       pos_out[(size_t)b * KR + k] = p;
@@ -114,15 +131,29 @@ infonce_bwd_kernel(const float* __restrict__ c, const float* __restrict__ W, con
       du[t] = (z < zd) ? dpos * ypos[bk * zd + z] : 0.f;
       if (z < zd) dypos[bk * zd + z] = dpos * u[t];
     }
-    for (int n = 0; n < N; ++n) {
-      float dn = expf(neg_in[bk * N + n] - lse) * scale;
-      size_t off = (((size_t)b * N + n) * KR + k) * zd;
+    for (int n0 = 0; n0 < N; n0 += 8) {
+      float yv[8][ZPL], dn[8];
 #pragma unroll
-      for (int t = 0; t < ZPL; ++t) {
-        int z = lane + 32 * t;
-        if (z < zd) {
-          du[t] = fmaf(dn, yneg[off + z], du[t]);
-          dyneg[off + z] = dn * u[t];
+      for (int j = 0; j < 8; ++j) {
+        dn[j] = (n0 + j < N) ? expf(neg_in[bk * N + n0 + j] - lse) * scale : 0.f;
+#pragma unroll
+        for (int t = 0; t < ZPL; ++t) {
+          int z = lane + 32 * t;
+          yv[j][t] = (n0 + j < N && z < zd) ? yneg[(((size_t)b * N + n0 + j) * KR + k) * zd + z] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n0 + j < N) {
+          size_t off = (((size_t)b * N + n0 + j) * KR + k) * zd;
+#pragma unroll
+          for (int t = 0; t < ZPL; ++t) {
+            int z = lane + 32 * t;
+            if (z < zd) {
+              du[t] = fmaf(dn[j], yv[j][t], du[t]);
+              dyneg[off + z] = dn[j] * u[t];
+            }
+          }
         }
       }
     }

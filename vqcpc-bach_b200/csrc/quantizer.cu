@@ -169,6 +169,154 @@ vq_bwd_kernel(const float* __restrict__ x, Books books, int Kc, int D, int ds, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused bottleneck for the common single-codebook case with a dropout-free upscaler:
+//   one pass over z: exact search -> idx, loss, usage histogram, and y = T[idx], where T = upscaler(codebook) is a
+//   (Kc, zd) table computed once per call on the Kc code vectors (the upscaled output of every vector assigned to code
+//   k is the same row).  Algorithmic traffic per vector: 4*D in, 8 (idx) + 4 (loss) + 4*zd (y) out = 152 B for D=3,
+//   zd=32 (SURVEY §8d stage A).  The direct-form exact search costs ~12 fp32 instructions per (vector, code) and is the
+//   binding limit for Kc = 512 (fp32-ALU bound, not HBM bound).
+template <int DS>
+__global__ void __launch_bounds__(256)
+vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, const float* __restrict__ T, int Kc, int zd,
+                    int64_t n, float beta, int squared, int64_t* __restrict__ idx, float* __restrict__ loss,
+                    float* __restrict__ zsg, float* __restrict__ y, int* __restrict__ counts) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int CS = (DS == 3) ? 4 : DS;          // padded code stride (one LDS.128 per code for D = 3)
+  float* cb = sm;                                  // [Kc][CS]
+  float* Ts = cb + Kc * CS;                        // [Kc][zd]   (only if T != nullptr)
+  int* hist = reinterpret_cast<int*>(Ts + (T ? Kc * zd : 0));   // [Kc]
+  for (int i = threadIdx.x; i < Kc * CS; i += blockDim.x) {
+    int k = i / CS, dd = i % CS;
+    cb[i] = dd < DS ? E[k * DS + dd] : 0.f;
+  }
+  if (T)
+    for (int i = threadIdx.x; i < Kc * zd; i += blockDim.x) Ts[i] = T[i];
+  for (int i = threadIdx.x; i < Kc; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // whole warps stay in the loop together (the y write-out below is warp-cooperative)
+  for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); v0 < n; v0 += stride) {
+    const int64_t v = v0 + lane;
+    const bool ok = v < n;
+    float xr[DS];
+#pragma unroll
+    for (int dd = 0; dd < DS; ++dd) xr[dd] = ok ? x[v * DS + dd] : 0.f;
+    float best = INFINITY;
+    int bi = 0;
+#pragma unroll 4
+    for (int k = 0; k < Kc; ++k) {
+      float dd = dist_fixed<DS>(xr, cb + k * CS);
+      if (dd < best || k == 0) { best = dd; bi = k; }
+    }
+    if (ok) {
+      // loss / straight-through output exactly as vq_gather_kernel
+      float acc[8];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < DS; ++dd) {
+        float df = __fsub_rn(cb[bi * CS + dd], xr[dd]);
+        if (zsg) zsg[v * DS + dd] = __fadd_rn(xr[dd], df);
+        if (!squared) df = __fadd_rn(df, 1e-5f);
+        acc[dd & 7] = __fadd_rn(acc[dd & 7], __fmul_rn(df, df));
+      }
+      float s = acc[0];
+#pragma unroll
+      for (int l = 1; l < 8; ++l) s = __fadd_rn(s, acc[l]);
+      float ql = squared ? s : sqrtf(s);
+      loss[v] = __fadd_rn(ql, __fmul_rn(beta, ql));
+      idx[v] = bi;
+      if (counts) atomicAdd(&hist[bi], 1);
+    }
+    if (y) {
+      for (int sft = 0; sft < 32; ++sft) {
+        const int b = __shfl_sync(0xffffffffu, bi, sft);
+        if (v0 + sft < n)
+          for (int j = lane; j < zd; j += 32) y[(v0 + sft) * zd + j] = Ts[b * zd + j];
+      }
+    }
+  }
+  __syncthreads();
+  if (counts)
+    for (int i = threadIdx.x; i < Kc; i += blockDim.x)
+      if (hist[i]) atomicAdd(counts + i, hist[i]);
+}
+
+// backward of the fused path.  J (Kc, zd, D) = d upscaler / d input evaluated at each code vector.
+//   dx[v]      = J[idx]^T dy[v] + g_loss[v] * d loss / d x           (straight-through + commitment)
+//   dT[idx]   += dy[v]   (CTA-private smem table, one atomic flush)  -> upscaler weight gradients via the Kc-row MLP
+//   dE[idx]   += g_loss[v] * d loss / d q
+template <int DS>
+__global__ void __launch_bounds__(256)
+vq_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ E, const float* __restrict__ J, int Kc, int zd,
+                    int64_t n, const int64_t* __restrict__ idx, float beta, int squared, const float* __restrict__ dy,
+                    const float* __restrict__ g_loss, float* __restrict__ dx, float* __restrict__ dT, float* __restrict__ dE) {
+  extern __shared__ __align__(16) float sm[];
+  float* dTs = sm;                                 // [Kc][zd]
+  float* dEs = dTs + Kc * zd;                      // [Kc][DS]
+  for (int i = threadIdx.x; i < Kc * (zd + DS); i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); v0 < n; v0 += stride) {
+    const int64_t v = v0 + lane;
+    const bool ok = v < n;
+    const int k = ok ? (int)idx[v] : 0;
+    float gx[DS];
+#pragma unroll
+    for (int dd = 0; dd < DS; ++dd) gx[dd] = 0.f;
+    // warp-cooperative: for each vector of the warp, lanes span the zd features
+    for (int sft = 0; sft < 32; ++sft) {
+      const int kb = __shfl_sync(0xffffffffu, k, sft);
+      const bool vok = (v0 + sft) < n;
+      float part[DS];
+#pragma unroll
+      for (int dd = 0; dd < DS; ++dd) part[dd] = 0.f;
+      if (vok) {
+        for (int j = lane; j < zd; j += 32) {
+          const float g = dy[(v0 + sft) * zd + j];
+          atomicAdd(&dTs[kb * zd + j], g);
+#pragma unroll
+          for (int dd = 0; dd < DS; ++dd) part[dd] = fmaf(g, __ldg(J + ((size_t)kb * zd + j) * DS + dd), part[dd]);
+        }
+      }
+#pragma unroll
+      for (int dd = 0; dd < DS; ++dd) {
+        float t = warp_sum(part[dd]);
+        if (lane == sft) gx[dd] = t;
+      }
+    }
+    if (ok) {
+      const float gl = g_loss ? g_loss[v] : 0.f;
+      float inv_norm = 0.f;
+      if (!squared) {
+        float s = 0.f;
+#pragma unroll
+        for (int dd = 0; dd < DS; ++dd) {
+          float df = E[k * DS + dd] - x[v * DS + dd] + 1e-5f;
+          s += df * df;
+        }
+        inv_norm = 1.f / sqrtf(s);
+      }
+#pragma unroll
+      for (int dd = 0; dd < DS; ++dd) {
+        const float df = E[k * DS + dd] - x[v * DS + dd];
+        const float dq = squared ? 2.f * df : (df + 1e-5f) * inv_norm;
+        dx[v * DS + dd] = gx[dd] - gl * beta * dq;
+        if (gl != 0.f) atomicAdd(&dEs[k * DS + dd], gl * dq);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Kc * zd; i += blockDim.x)
+    if (dTs[i] != 0.f) atomicAdd(dT + i, dTs[i]);
+  if (dE)
+    for (int i = threadIdx.x; i < Kc * DS; i += blockDim.x)
+      if (dEs[i] != 0.f) atomicAdd(dE + i, dEs[i]);
+}
+
 int fill_books(Books& b, int ncb, const float* const* e, float* const* g) {
   if (ncb < 1 || ncb > MAX_CB) return -1;
   for (int i = 0; i < ncb; ++i) {
@@ -240,5 +388,63 @@ VQ_API int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* bo
   if (n == 0) return VQ_OK;
   vq_bwd_kernel<<<vec_grid(n), 256, 0, vq_stream(stream)>>>(x, b, Kc, D, D / ncb, ncb, n, idx, beta, squared, g_zsg, g_loss, d_x);
   VQ_CUDA_LAUNCH_CHECK("vq_bwd_kernel");
+  return VQ_OK;
+}
+
+// Fused single-codebook bottleneck with the upscaler folded into a table: see vq_fused_fwd_kernel.
+//   x (n, D); E (Kc, D); T (Kc, zd) = upscaler(E) or NULL (then y is not written); idx (n) int64; loss (n);
+//   z_sg (n, D) optional; y (n, zd) optional; counts (Kc) int32 ACCUMULATED, optional.
+VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                              int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, void* stream) {
+  VQ_CHECK_ARG(D == 3 || D == 4 || D == 8 || D == 16 || D == 32, "vq_fused_fwd: D must be 3, 4, 8, 16 or 32 (got %d)", D);
+  VQ_CHECK_ARG((T == nullptr) == (y == nullptr), "vq_fused_fwd: T and y go together");
+  if (n == 0) return VQ_OK;
+  const int cs = D == 3 ? 4 : D;
+  size_t smem = ((size_t)Kc * cs + (T ? (size_t)Kc * zd : 0) + Kc) * sizeof(float);
+  VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_fwd: codebook + table (%zu B) do not fit in shared memory", smem);
+  cudaStream_t st = vq_stream(stream);
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * (smem > 100 * 1024 ? 1 : 2)));
+#define VQ_FL(DSV)                                                                                                          \
+  do {                                                                                                                      \
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_fwd_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    vq_fused_fwd_kernel<DSV><<<grid, 256, smem, st>>>(x, E, T, Kc, zd, n, beta, squared, idx, loss, z_sg, y, counts);       \
+  } while (0)
+  switch (D) {
+    case 3: VQ_FL(3); break;
+    case 4: VQ_FL(4); break;
+    case 8: VQ_FL(8); break;
+    case 16: VQ_FL(16); break;
+    default: VQ_FL(32); break;
+  }
+#undef VQ_FL
+  VQ_CUDA_LAUNCH_CHECK("vq_fused_fwd_kernel");
+  return VQ_OK;
+}
+
+// Backward of the fused path: d_x (n, D) overwritten; d_T (Kc, zd) and d_E (Kc, D) ACCUMULATED.
+// J (Kc, zd, D): Jacobian of the upscaler at each code vector; dy (n, zd); g_loss (n) or NULL.
+VQ_API int vqcpc_vq_fused_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd,
+                              const int64_t* idx, float beta, int squared, const float* dy, const float* g_loss, float* d_x,
+                              float* d_T, float* d_E, void* stream) {
+  VQ_CHECK_ARG(D == 3 || D == 4 || D == 8 || D == 16 || D == 32, "vq_fused_bwd: D must be 3, 4, 8, 16 or 32 (got %d)", D);
+  if (n == 0) return VQ_OK;
+  size_t smem = (size_t)Kc * (zd + D) * sizeof(float);
+  VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_bwd: gradient tables (%zu B) do not fit in shared memory", smem);
+  cudaStream_t st = vq_stream(stream);
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * (smem > 100 * 1024 ? 1 : 2)));
+#define VQ_BL(DSV)                                                                                                          \
+  do {                                                                                                                      \
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_bwd_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    vq_fused_bwd_kernel<DSV><<<grid, 256, smem, st>>>(x, E, J, Kc, zd, n, idx, beta, squared, dy, g_loss, d_x, d_T, d_E);   \
+  } while (0)
+  switch (D) {
+    case 3: VQ_BL(3); break;
+    case 4: VQ_BL(4); break;
+    case 8: VQ_BL(8); break;
+    case 16: VQ_BL(16); break;
+    default: VQ_BL(32); break;
+  }
+#undef VQ_BL
+  VQ_CUDA_LAUNCH_CHECK("vq_fused_bwd_kernel");
   return VQ_OK;
 }
