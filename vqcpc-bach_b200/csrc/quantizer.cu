@@ -184,14 +184,12 @@ vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, co
   extern __shared__ __align__(16) float sm[];
   constexpr int CS = (DS == 3) ? 4 : DS;          // padded code stride (one LDS.128 per code for D = 3)
   float* cb = sm;                                  // [Kc][CS]
-  float* Ts = cb + Kc * CS;                        // [Kc][zd]   (only if T != nullptr)
-  int* hist = reinterpret_cast<int*>(Ts + (T ? Kc * zd : 0));   // [Kc]
+  int* hist = reinterpret_cast<int*>(cb + Kc * CS);   // [Kc]
+  // (the (Kc, zd) table T stays in global memory: 64 KB, L1/L2 resident, read as whole 128-byte rows)
   for (int i = threadIdx.x; i < Kc * CS; i += blockDim.x) {
     int k = i / CS, dd = i % CS;
     cb[i] = dd < DS ? E[k * DS + dd] : 0.f;
   }
-  if (T)
-    for (int i = threadIdx.x; i < Kc * zd; i += blockDim.x) Ts[i] = T[i];
   for (int i = threadIdx.x; i < Kc; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -234,7 +232,7 @@ vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, co
       for (int sft = 0; sft < 32; ++sft) {
         const int b = __shfl_sync(0xffffffffu, bi, sft);
         if (v0 + sft < n)
-          for (int j = lane; j < zd; j += 32) y[(v0 + sft) * zd + j] = Ts[b * zd + j];
+          for (int j = lane; j < zd; j += 32) y[(v0 + sft) * zd + j] = __ldg(T + (size_t)b * zd + j);
       }
     }
   }
@@ -400,10 +398,11 @@ VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, 
   VQ_CHECK_ARG((T == nullptr) == (y == nullptr), "vq_fused_fwd: T and y go together");
   if (n == 0) return VQ_OK;
   const int cs = D == 3 ? 4 : D;
-  size_t smem = ((size_t)Kc * cs + (T ? (size_t)Kc * zd : 0) + Kc) * sizeof(float);
-  VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_fwd: codebook + table (%zu B) do not fit in shared memory", smem);
+  size_t smem = ((size_t)Kc * cs + Kc) * sizeof(float);
+  VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_fwd: codebook (%zu B) does not fit in shared memory", smem);
   cudaStream_t st = vq_stream(stream);
-  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * (smem > 100 * 1024 ? 1 : 2)));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * per_sm));
 #define VQ_FL(DSV)                                                                                                          \
   do {                                                                                                                      \
     VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_fwd_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
