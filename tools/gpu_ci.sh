@@ -22,6 +22,8 @@ for g in $groups; do
     gemm_tc)   run gemm_tc tests/test_gpu_gemm.py "not fp32" ;;
     gemm_tc0)  VQCPC_GEMM_TILE=0 run gemm_tc0 tests/test_gpu_gemm.py "not fp32" ;;
     gemm_tc1)  VQCPC_GEMM_TILE=1 run gemm_tc1 tests/test_gpu_gemm.py "not fp32" ;;
+    gemm_tc2)  VQCPC_GEMM_TILE=2 run gemm_tc2 tests/test_gpu_gemm.py "not fp32" ;;
+    gemm_tc3)  VQCPC_GEMM_TILE=3 run gemm_tc3 tests/test_gpu_gemm.py "not fp32" ;;
     enc_fp32)  run enc_fp32 tests/test_gpu_encoder.py "fp32 or micro or eval or first_call or fused" ;;
     enc_tc)    run enc_tc tests/test_gpu_encoder.py "bf16x3" ;;
   esac

@@ -52,6 +52,11 @@ class Encoder(nn.Module):
         """x as produced by the dataloader (..., ticks, voices) ->
         (z_quantized (b, nb, z_dim), encoding_indices (b, nb, num_codebooks) | None, quantization_loss (b, nb))."""
         x_proc = self.data_processor.preprocess(x)
+        return self.forward_tokens(x_proc, corrupt_labels=corrupt_labels)
+
+    def forward_tokens(self, x_proc, corrupt_labels=False):
+        """Same as ``forward`` from already preprocessed tokens (b, num_blocks, tokens_per_block) on the device.  The
+        trainer uses it to push the negatives / left / right blocks of a pass through ONE encoder launch sequence."""
         x_embed = self.data_processor.embed(x_proc)
         x_flat = flatten(x_embed)
         z = self.downscaler.forward(x_flat)

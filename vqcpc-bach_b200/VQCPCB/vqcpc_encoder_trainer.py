@@ -170,14 +170,36 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         for b0 in range(0, B, bs):
             sl = slice(b0, b0 + bs)
             neg = neg_all[sl].reshape(bs * N * KR, T, V)
-            z_neg, idx_neg, ql_neg = enc(neg, corrupt_labels=corrupt_labels)              # :197-201
-            zd = z_neg.shape[-1]
-            z_neg = z_neg.view(bs, N, KR, zd)                                              # nb == 1
-            if bidir:
-                nb_ = neg_back_all[sl].reshape(bs * N * KR, T, V)
-                z_nb, idx_nb, ql_nb = enc(nb_, corrupt_labels=corrupt_labels)              # :211-225
-            z_left, idx_left, ql_left = enc(x_left_all[sl], corrupt_labels=False)          # :227
-            z_right, idx_right, ql_right = enc(x_right_all[sl], corrupt_labels=False)      # :230
+            merged = (not corrupt_labels) and not getattr(q, 'initialize', False)
+            if merged:
+                # blocks are independent, so the reference's separate Encoder.forward calls (:201, :219, :227, :230) are
+                # one pass over the concatenated blocks (bigger GEMMs, 3-4x fewer launches); results are identical.
+                dp = enc.data_processor
+                toks = [dp.preprocess(neg), dp.preprocess(x_left_all[sl]), dp.preprocess(x_right_all[sl])]
+                if bidir:
+                    toks.append(dp.preprocess(neg_back_all[sl].reshape(bs * N * KR, T, V)))
+                S_tok = toks[0].shape[-1]
+                counts = [t.numel() // S_tok for t in toks]
+                allt = torch.cat([t.reshape(-1, S_tok) for t in toks], 0).unsqueeze(0)
+                z_all, idx_all, ql_all = enc.forward_tokens(allt)
+                zd = z_all.shape[-1]
+                z_parts = z_all[0].split(counts, 0)
+                ql_parts = ql_all[0].split(counts, 0)
+                idx_parts = idx_all[0].split(counts, 0) if idx_all is not None else [None] * len(counts)
+                z_neg, idx_neg, ql_neg = z_parts[0].reshape(bs, N, KR, zd), idx_parts[0], ql_parts[0]
+                z_left, idx_left, ql_left = z_parts[1].reshape(bs, KL, zd), idx_parts[1], ql_parts[1]
+                z_right, idx_right, ql_right = z_parts[2].reshape(bs, KR, zd), idx_parts[2], ql_parts[2]
+                if bidir:
+                    z_nb, idx_nb, ql_nb = z_parts[3].reshape(bs * N * KR, 1, zd), idx_parts[3], ql_parts[3]
+            else:
+                z_neg, idx_neg, ql_neg = enc(neg, corrupt_labels=corrupt_labels)          # :197-201
+                zd = z_neg.shape[-1]
+                z_neg = z_neg.view(bs, N, KR, zd)                                          # nb == 1
+                if bidir:
+                    nb_ = neg_back_all[sl].reshape(bs * N * KR, T, V)
+                    z_nb, idx_nb, ql_nb = enc(nb_, corrupt_labels=corrupt_labels)          # :211-225
+                z_left, idx_left, ql_left = enc(x_left_all[sl], corrupt_labels=False)      # :227
+                z_right, idx_right, ql_right = enc(x_right_all[sl], corrupt_labels=False)  # :230
 
             c = self.c_module(z_left, None)                                                # :237
             nll_sum, pos, negs, corr = self.fks_module.fused_nce(c, z_right, z_neg)        # :240-272

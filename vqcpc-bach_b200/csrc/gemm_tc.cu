@@ -75,10 +75,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, multicast: the box lands at the same smem offset in every CTA of `mask` and completes tx on the mbarrier at
+// the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once the previously issued MMAs have retired
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -144,7 +166,11 @@ struct TcParams {
   int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int BN, int BK, int STAGES>
+// CL = cluster size along M (1, 2 or 4): the CL CTAs of a cluster work on CL consecutive m-tiles of the SAME n-tile and
+// k-range in lock step; each loads its own A tile and 1/CL of the B tile, which it TMA-multicasts to all of them.
+// L2 -> SM operand traffic per tile drops from A + B to A + B/CL (B is the larger tile at BN = 256): the 1-CTA kernel
+// was bound by L2 bandwidth (~17 TB/s demanded at full tensor rate), not by the tensor pipe.
+template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int BN, int BK, int STAGES, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
@@ -164,12 +190,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NUM_ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = p.m_tiles * p.n_tiles * p.ksplit;
+  // work items are per CLUSTER: (k split, group of CL m-tiles, n tile)
+  const int m_groups = (p.m_tiles + CL - 1) / CL;
+  const int total_items = m_groups * p.n_tiles * p.ksplit;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), CL);       // every CTA of the cluster must have drained the slot
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
@@ -183,6 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                   // peers' barriers are initialised before anything targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -193,10 +225,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int ks = item / (p.m_tiles * p.n_tiles);
-        const int rem = item % (p.m_tiles * p.n_tiles);
-        const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+      for (int item = cluster_id; item < total_items; item += num_clusters) {
+        const int ks = item / (m_groups * p.n_tiles);
+        const int rem = item % (m_groups * p.n_tiles);
+        const int m0 = ((rem / p.n_tiles) * CL + crank) * BM, n0 = (rem % p.n_tiles) * BN;
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -217,14 +249,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (PASSES == 3) tma_load_2d(a_lo + c * CHUNK_BYTES, &tmA_lo, fb, m0 + c * 64, k0);
             }
           }
-          if (B_KMAJOR) {
-            tma_load_2d(b_hi, &tmB_hi, fb, k0, n0);
-            if (PASSES == 3) tma_load_2d(b_lo, &tmB_lo, fb, k0, n0);
-          } else {
+          if (CL == 1) {
+            if (B_KMAJOR) {
+              tma_load_2d(b_hi, &tmB_hi, fb, k0, n0);
+              if (PASSES == 3) tma_load_2d(b_lo, &tmB_lo, fb, k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) {
-              tma_load_2d(b_hi + c * CHUNK_BYTES, &tmB_hi, fb, n0 + c * 64, k0);
-              if (PASSES == 3) tma_load_2d(b_lo + c * CHUNK_BYTES, &tmB_lo, fb, n0 + c * 64, k0);
+              for (int c = 0; c < BN / 64; ++c) {
+                tma_load_2d(b_hi + c * CHUNK_BYTES, &tmB_hi, fb, n0 + c * 64, k0);
+                if (PASSES == 3) tma_load_2d(b_lo + c * CHUNK_BYTES, &tmB_lo, fb, n0 + c * 64, k0);
+              }
+            }
+          } else {
+            // this CTA fetches slice `crank` of the B tile (BN / CL rows of n) and multicasts it to the whole cluster
+            constexpr int SL = BN / CL;
+            if (B_KMAJOR) {
+              const uint32_t off = (uint32_t)(crank * SL * BK * 2);
+              tma_load_2d_mc(b_hi + off, &tmB_hi, fb, k0, n0 + crank * SL, CMASK);
+              if (PASSES == 3) tma_load_2d_mc(b_lo + off, &tmB_lo, fb, k0, n0 + crank * SL, CMASK);
+            } else {
+#pragma unroll
+              for (int c = 0; c < SL / 64; ++c) {
+                const int cc = crank * (SL / 64) + c;
+                tma_load_2d_mc(b_hi + cc * CHUNK_BYTES, &tmB_hi, fb, n0 + cc * 64, k0, CMASK);
+                if (PASSES == 3) tma_load_2d_mc(b_lo + cc * CHUNK_BYTES, &tmB_lo, fb, n0 + cc * 64, k0, CMASK);
+              }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -239,8 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t B_STEP = B_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int ks = item / (p.m_tiles * p.n_tiles);
+      for (int item = cluster_id; item < total_items; item += num_clusters) {
+        const int ks = item / (m_groups * p.n_tiles);
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
@@ -267,7 +316,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               umma_bf16(tmem_d, da_hi, db_hi, idesc, first);
             }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when these MMAs retire
+          if (CL == 1) umma_commit(smem_u32(&empty_bar[stage]));   // frees the smem slot when these MMAs retire
+          else umma_commit_mc(smem_u32(&empty_bar[stage]), CMASK);  // ... in every CTA of the cluster (they all write it)
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));           // accumulator complete -> epilogue
@@ -279,10 +329,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int ks = item / (p.m_tiles * p.n_tiles);
-      const int rem = item % (p.m_tiles * p.n_tiles);
-      const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+    for (int item = cluster_id; item < total_items; item += num_clusters) {
+      const int ks = item / (m_groups * p.n_tiles);
+      const int rem = item % (m_groups * p.n_tiles);
+      const int m0 = ((rem / p.n_tiles) * CL + crank) * BM, n0 = (rem % p.n_tiles) * BN;
       const bool first_split = (ks == 0);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
@@ -419,6 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                   // nobody exits while a peer may still multicast into / signal it
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -464,38 +515,74 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return VQ_OK;
 }
 
-template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES>
+template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES, int CL>
 int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK * 2 + BN * BK * 2);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
+  auto kern = gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES, CL>;
   static bool done = false;
   if (!done) {
-    VQ_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VQ_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     done = true;
   }
-  int items = p.m_tiles * p.n_tiles * p.ksplit;
-  int grid = std::min(items, vq_sm_count());
-  gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES><<<grid, THREADS, SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], p);
-  VQ_CUDA_LAUNCH_CHECK("gemm_tc_kernel");
+  const int m_groups = (p.m_tiles + CL - 1) / CL;
+  const int items = m_groups * p.n_tiles * p.ksplit;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent grid = the number of clusters that can be co-resident (GPC boundaries can strand SMs for CL = 4)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((unsigned)(vq_sm_count() / CL * CL));
+    int n = 0;
+    if (CL > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    else max_clusters = vq_sm_count() / CL;
+    (void)cudaGetLastError();
+  }
+  const int clusters = std::max(1, std::min(items, max_clusters));
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p);
+  if (e != cudaSuccess) {
+    vq_set_error("gemm_tc_kernel: launch failed: %s", cudaGetErrorString(e));
+    return VQ_ERR_CUDA;
+  }
   return VQ_OK;
 }
 
-// tile configuration ids: 0 = 128x128x64 (3 / 6 stages), 1 = 128x256x32 (4 / 8 stages)
+// tile configuration ids: 0 = 128x128x64 (3 / 6 stages, no cluster), 1 = 128x256x32 (4 / 8 stages, no cluster),
+//                         2 = 128x256x32 with the B tile multicast over a cluster of 2 CTAs along M, 3 = cluster of 4
 int g_force_cfg = -1;
-inline int pick_cfg(int N) {
-  if (g_force_cfg >= 0) return g_force_cfg;
-  return N >= 256 ? 1 : 0;
+inline int pick_cfg(int M, int N) {
+  if (g_force_cfg >= 0) return (N < 256 && g_force_cfg > 0) ? 0 : g_force_cfg;
+  if (N < 256) return 0;
+  return M >= 4 * BM ? 3 : (M >= 2 * BM ? 2 : 1);
 }
 
 template <bool AK, bool BKM>
 int launch_tc(int cfg, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
-  if (cfg == 1) {
-    if (passes == 3) return launch_cfg<AK, BKM, 3, 256, 32, 4>(maps, p, st);
-    return launch_cfg<AK, BKM, 1, 256, 32, 8>(maps, p, st);
+  if (cfg == 3) {
+    if (passes == 3) return launch_cfg<AK, BKM, 3, 256, 32, 4, 4>(maps, p, st);
+    return launch_cfg<AK, BKM, 1, 256, 32, 8, 4>(maps, p, st);
   }
-  if (passes == 3) return launch_cfg<AK, BKM, 3, 128, 64, 3>(maps, p, st);
-  return launch_cfg<AK, BKM, 1, 128, 64, 6>(maps, p, st);
+  if (cfg == 2) {
+    if (passes == 3) return launch_cfg<AK, BKM, 3, 256, 32, 4, 2>(maps, p, st);
+    return launch_cfg<AK, BKM, 1, 256, 32, 8, 2>(maps, p, st);
+  }
+  if (cfg == 1) {
+    if (passes == 3) return launch_cfg<AK, BKM, 3, 256, 32, 4, 1>(maps, p, st);
+    return launch_cfg<AK, BKM, 1, 256, 32, 8, 1>(maps, p, st);
+  }
+  if (passes == 3) return launch_cfg<AK, BKM, 3, 128, 64, 3, 1>(maps, p, st);
+  return launch_cfg<AK, BKM, 1, 128, 64, 6, 1>(maps, p, st);
 }
 
 }  // namespace
@@ -526,8 +613,9 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
-  const int cfg = pick_cfg(N);
-  const int BN = cfg == 1 ? 256 : 128, BK = cfg == 1 ? 32 : 64;
+  const int cfg = pick_cfg(M, N);
+  const int BN = cfg >= 1 ? 256 : 128, BK = cfg >= 1 ? 32 : 64;
+  const int CLh = cfg == 3 ? 4 : (cfg == 2 ? 2 : 1);          // cluster size: B K-major boxes cover BN / CL rows
   p.m_tiles = (int)vq_cdiv(M, BM);
   p.n_tiles = (int)vq_cdiv(N, BN);
   p.kblocks_total = (int)vq_cdiv(K, BK);
@@ -553,8 +641,8 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
     if ((rc = make_map(&maps[1], alo, K, M, lda, 64, BK)) != VQ_OK) return rc;
   }
   if (b_kmajor) {   // [N rows][K cols]
-    if ((rc = make_map(&maps[2], B_hi, N, K, ldb, BK, BN)) != VQ_OK) return rc;
-    if ((rc = make_map(&maps[3], blo, N, K, ldb, BK, BN)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[2], B_hi, N, K, ldb, BK, BN / CLh)) != VQ_OK) return rc;
+    if ((rc = make_map(&maps[3], blo, N, K, ldb, BK, BN / CLh)) != VQ_OK) return rc;
   } else {          // [K rows][N cols]
     if ((rc = make_map(&maps[2], B_hi, K, N, ldb, 64, BK)) != VQ_OK) return rc;
     if ((rc = make_map(&maps[3], blo, K, N, ldb, 64, BK)) != VQ_OK) return rc;
@@ -566,9 +654,10 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   return launch_tc<false, false>(cfg, passes, maps, p, st);
 }
 
-// Testing / tuning hook: force a tile configuration (0 = 128x128x64, 1 = 128x256x32, -1 = automatic by N).
+// Testing / tuning hook: force a tile configuration (0 = 128x128x64, 1 = 128x256x32, 2 / 3 = 128x256x32 with the B tile
+// multicast over a cluster of 2 / 4 CTAs, -1 = automatic).
 VQ_API int vqcpc_gemm_set_tile_config(int cfg) {
-  VQ_CHECK_ARG(cfg >= -1 && cfg <= 1, "gemm_set_tile_config: cfg must be -1, 0 or 1");
+  VQ_CHECK_ARG(cfg >= -1 && cfg <= 3, "gemm_set_tile_config: cfg must be -1 .. 3");
   g_force_cfg = cfg;
   return VQ_OK;
 }
