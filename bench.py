@@ -172,21 +172,33 @@ def bench_quantizer_infonce(B, iters=30, nsets=5):
         sets.append(d)
     p_, st = ops._p, ops._stream
 
-    def fwd(d):
+    def vq_fwd(d):
         _native.call('vqcpc_vq_fused_fwd', p_(d['z']), P, D, p_(E), p_(T), Kc, zd, 0.25, 1, p_(d['idx']), p_(d['loss']), None,
                      p_(d['y']), p_(d['counts']), st())
+
+    def nce_fwd(d):
         y = d['y']
         ypos = y[n_neg + B * KL:]                                   # right blocks
         _native.call('vqcpc_infonce_fwd', p_(d['c']), p_(W), p_(ypos), p_(y), B, NNEG, KR, zd, cd, p_(d['u']), p_(d['pos']),
                      p_(d['neg']), p_(d['lse']), p_(d['nll']), p_(d['correct']), st())
 
-    def bwd(d):
+    def nce_bwd(d):
         y, dy = d['y'], d['dy']
         _native.call('vqcpc_infonce_bwd', p_(d['c']), p_(W), p_(y[n_neg + B * KL:]), p_(y), p_(d['u']), p_(d['pos']), p_(d['neg']),
                      p_(d['lse']), None, 1.0 / B, B, NNEG, KR, zd, cd, p_(d['dc']), p_(d['dW']), p_(dy[n_neg + B * KL:]), p_(dy),
                      st())
-        _native.call('vqcpc_vq_fused_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(dy), p_(d['gl']),
+
+    def vq_bwd(d):
+        _native.call('vqcpc_vq_fused_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(d['dy']), p_(d['gl']),
                      p_(d['dz']), p_(d['dT']), p_(d['dE']), st())
+
+    def fwd(d):
+        vq_fwd(d)
+        nce_fwd(d)
+
+    def bwd(d):
+        nce_bwd(d)
+        vq_bwd(d)
 
     def timeit(fn):
         for d in sets:
@@ -204,21 +216,23 @@ def bench_quantizer_infonce(B, iters=30, nsets=5):
         d['dy'].normal_()
     us_f = timeit(fwd)
     us_b = timeit(bwd)
+    per_kernel = dict(vq_fused_fwd_us=timeit(vq_fwd), infonce_fwd_us=timeit(nce_fwd), infonce_bwd_us=timeit(nce_bwd),
+                      vq_fused_bwd_us=timeit(vq_bwd))
     pk = peaks()
     vec = KL + KR + NNEG * KR
     bytes_f = B * (vec * (4 * D + 8 + 4 + 4 * zd) + (KR + NNEG * KR) * 4 * zd + 4 * cd + 8 * KR)
     # backward: read dy-producing inputs (y for right+neg, u, scores) and write dy for right+neg; then per vector read
     # dy (4 zd) + idx (8) + z (4 D) + g_loss (4), write dz (4 D)
     bytes_b = B * ((KR + NNEG * KR) * 8 * zd + vec * (4 * zd + 8 + 8 * D + 4))
-    search_instr = P * Kc * 12.0                                   # exact direct-form search: ~12 fp32 instr per (vector, code)
+    search_instr = P * Kc * 11.0                                   # exact direct-form search: 11 fp32 instr per (vector, code)
     alu_us = search_instr / (148 * 128 * 1.9e9) * 1e6
     return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
                 kernels='vq_fused_fwd_kernel + infonce_fwd_kernel (forward); infonce_bwd_kernel + vq_fused_bwd_kernel (backward)',
                 batch=B, vectors=P, algorithmic_bytes_fwd=bytes_f, us_fwd=us_f, achieved=bytes_f / us_f / 1e3,
                 frac=bytes_f / us_f / 1e3 / pk['hbm'], algorithmic_bytes_bwd=bytes_b, us_bwd=us_b,
                 achieved_bwd=bytes_b / us_b / 1e3, frac_bwd=bytes_b / us_b / 1e3 / pk['hbm'],
-                fp32_alu_bound_us_exact_search=alu_us,
-                note='bit-exact direct-form search = ~12 fp32 instr per (vector, code): ALU bound %.0f us at 148 SMs x 128 lanes '
+                fp32_alu_bound_us_exact_search=alu_us, per_kernel_us=per_kernel,
+                note='bit-exact direct-form search = 11 fp32 instr per (vector, code): ALU bound %.0f us at 148 SMs x 128 lanes '
                      'x 1.9 GHz, above the %.0f us HBM bound; buffers rotate over %d sets (> L2)' % (alu_us, bytes_f / pk['hbm'] / 1e3, nsets))
 
 

@@ -144,6 +144,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool kmajor) {
   return d;
 }
 
+// The descriptor's high word and the LBO half of the low word are compile-time constants; per MMA only the 14-bit start
+// address changes, so the issuing thread (which must stay ahead of a 64..128-cycle MMA) does one add per operand.
+template <int BK>
+__host__ __device__ constexpr uint32_t desc_hi32(bool kmajor) {
+  return (uint32_t)((kmajor ? 16 * BK : 1024) >> 4) | (1u << 14) | (((kmajor && BK == 32) ? 4u : 2u) << 29);
+}
+template <int BK>
+__host__ __device__ constexpr uint32_t desc_lo32_const(bool kmajor) {
+  return (uint32_t)(((kmajor ? 16 : BK * 128) >> 4)) << 16;
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc(bool a_kmajor, bool b_kmajor) {
   return (1u << 4)                         // D format: f32
@@ -286,6 +302,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t idesc = make_idesc<BN>(A_KMAJOR, B_KMAJOR);
       constexpr uint32_t A_STEP = A_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per K=16 step inside a stage
       constexpr uint32_t B_STEP = B_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);
+      constexpr uint32_t A_HI_C = desc_hi32<BK>(A_KMAJOR), B_HI_C = desc_hi32<BK>(B_KMAJOR);
+      constexpr uint32_t A_LO_C = desc_lo32_const<BK>(A_KMAJOR), B_LO_C = desc_lo32_const<BK>(B_KMAJOR);
+      const uint32_t smem_base_u32 = smem_u32(smem);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -298,17 +317,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tcgen05_fence_after();
-          uint8_t* st = smem + stage * STAGE_BYTES;
-          const uint32_t a_hi = smem_u32(st), b_hi = a_hi + TILE_A_BYTES;
+          const uint32_t a_hi = smem_base_u32 + (uint32_t)(stage * STAGE_BYTES), b_hi = a_hi + TILE_A_BYTES;
           const uint32_t a_lo = b_hi + TILE_B_BYTES, b_lo = a_lo + TILE_A_BYTES;
+          // low descriptor words at k = 0 (start address in 16-byte units; smem addresses are < 256 KB)
+          const uint32_t la_hi = A_LO_C | (a_hi >> 4), lb_hi = B_LO_C | (b_hi >> 4);
+          const uint32_t la_lo = A_LO_C | (a_lo >> 4), lb_lo = B_LO_C | (b_lo >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da_hi = make_desc<BK>(a_hi + k * A_STEP, A_KMAJOR);
-            const uint64_t db_hi = make_desc<BK>(b_hi + k * B_STEP, B_KMAJOR);
+            const uint64_t da_hi = pack_desc(la_hi + k * (A_STEP >> 4), A_HI_C);
+            const uint64_t db_hi = pack_desc(lb_hi + k * (B_STEP >> 4), B_HI_C);
             const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;
             if (PASSES == 3) {
-              const uint64_t da_lo = make_desc<BK>(a_lo + k * A_STEP, A_KMAJOR);
-              const uint64_t db_lo = make_desc<BK>(b_lo + k * B_STEP, B_KMAJOR);
+              const uint64_t da_lo = pack_desc(la_lo + k * (A_STEP >> 4), A_HI_C);
+              const uint64_t db_lo = pack_desc(lb_lo + k * (B_STEP >> 4), B_HI_C);
               umma_bf16(tmem_d, da_lo, db_hi, idesc, first);
               umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
               umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);

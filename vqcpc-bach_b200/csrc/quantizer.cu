@@ -201,12 +201,12 @@ vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, co
     float xr[DS];
 #pragma unroll
     for (int dd = 0; dd < DS; ++dd) xr[dd] = ok ? x[v * DS + dd] : 0.f;
-    float best = INFINITY;
+    float best = dist_fixed<DS>(xr, cb);        // code 0 seeds the running minimum; strict '<' keeps the lowest index
     int bi = 0;
 #pragma unroll 4
-    for (int k = 0; k < Kc; ++k) {
+    for (int k = 1; k < Kc; ++k) {
       float dd = dist_fixed<DS>(xr, cb + k * CS);
-      if (dd < best || k == 0) { best = dd; bi = k; }
+      if (dd < best) { best = dd; bi = k; }
     }
     if (ok) {
       // loss / straight-through output exactly as vq_gather_kernel
