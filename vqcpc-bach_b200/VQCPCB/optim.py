@@ -74,6 +74,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(flat.data)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
+        self.distributed = True          # False: never all-reduce (single-process reference inside a multi-rank job)
 
     def zero_grad(self, set_to_none=False):
         # the .grad views must stay alive (kernels accumulate into them): always zero in place
@@ -85,7 +86,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         (1 / world_size) the update must apply.  ``stats`` tensors are replaced by their cross-rank mean, ``counts``
         (int32 code-usage histogram) by its cross-rank sum.  No-op (scale 1) in a single process."""
         flat = self.flat
-        world = vq_dist.world_size()
+        world = vq_dist.world_size() if getattr(self, 'distributed', True) else 1
         if world <= 1:
             return 1.0
         tail = flat.tail

@@ -357,87 +357,98 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * CL + crank) * BM, n0 = (rem % p.n_tiles) * BN;
       const bool first_split = (ks == 0);
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tcgen05_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const int fl = p.ep.flags;
+      // all alignment conditions of the vector path are tile-invariant (columns advance by 32 floats)
+      const bool aligned = (!p.C || ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 3) == 0)) &&
+                           (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                          ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                           (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                           (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                            (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0))) &&
+                           !(fl & EPI_ATOMIC);
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+      const bool do_bias = first_split && (fl & EPI_BIAS);
+      const bool do_res = first_split && (fl & EPI_RESIDUAL);
+      const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
+      const bool mask_b16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
+      const bool do_acc = (fl & EPI_ACCUMULATE) && p.C;
+
+      // Operand prefetch for one 32-column chunk in the coalesced layout (8 lanes x 16 B per row, 4 rows per access):
+      // bias, residual / mask / running C.  Issued one chunk AHEAD (and for chunk 0 before the accumulator is even
+      // ready), so the global-memory latency is hidden behind the previous chunk instead of being paid 8x per tile.
+      struct Pre { float4 bias; float4 aux[8]; uint2 auxh[8]; };
+      auto prefetch = [&](int ch, Pre& pf) {
+        const int gcol = n0 + ch * 32 + c4;
+        pf.bias = make_float4(0, 0, 0, 0);
+        if (!(aligned && n0 + ch * 32 + 32 <= p.N)) return;
+        if (do_bias) pf.bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + gcol));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = m0 + q * 32 + it * 4 + rsub;
+          pf.aux[it] = make_float4(0, 0, 0, 0);
+          pf.auxh[it] = make_uint2(0, 0);
+          if (grow < p.M) {
+            if (do_res || mask_f32) pf.aux[it] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)grow * p.ep.ldr + gcol));
+            if (mask_b16)
+              pf.auxh[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) +
+                                                                 (size_t)grow * p.ep.ldr + gcol));
+            if (do_acc) {
+              float4 c = ld4(p.C + (size_t)grow * p.ldc + gcol);
+              if (do_res) { pf.aux[it].x += c.x; pf.aux[it].y += c.y; pf.aux[it].z += c.z; pf.aux[it].w += c.w; }
+              else pf.aux[it] = c;
+            }
+          }
+        }
+      };
+      Pre cur, nxt;
+      prefetch(0, cur);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tcgen05_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
+        if (ch + 1 < BN / 32) prefetch(ch + 1, nxt);
         tmem_ld_wait();
         const int col0 = n0 + ch * 32;
-        const int fl = p.ep.flags;
-        float* crow0 = p.C ? p.C + (size_t)(m0 + q * 32) * p.ldc + col0 : nullptr;
-        const bool aligned = ((reinterpret_cast<uintptr_t>(crow0) & 15) == 0) && ((p.ldc & 3) == 0 || !p.C) &&
-                             (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
-                                            ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
-                             (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
-                             (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
-                              (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
-        if (col0 + 32 <= p.N && aligned && !(fl & EPI_ATOMIC)) {
-          // ---- fast path.  TMEM hands every thread 32 columns of ONE row; storing that directly makes each warp store
-          // touch 32 different 128-byte lines.  Transpose through a padded per-warp smem tile so that 8 lanes cover one
-          // row's 128 bytes: every global access of the epilogue (C, residual, mask, split outputs) is then a fully
-          // coalesced 16-byte-per-lane vector access, 4 rows per instruction.
+        if (col0 + 32 <= p.N && aligned) {
+          // ---- fast path.  TMEM hands every thread 32 columns of ONE row; storing that directly would make each warp
+          // store touch 32 different 128-byte lines.  Transpose through a padded per-warp smem tile so that 8 lanes cover
+          // one row's 128 bytes: every global access of the epilogue is a coalesced 16-byte-per-lane vector access.
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
-          const int c4 = (lane & 7) * 4, rsub = lane >> 3;
           const int gcol = col0 + c4;
-          float4 bias4 = make_float4(0, 0, 0, 0);
-          if (first_split && (fl & EPI_BIAS)) bias4 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + gcol));
-          const bool do_res = first_split && (fl & EPI_RESIDUAL);
-          const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
-          const bool mask_b16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
-          float4 aux[8];          // residual or fp32 mask rows, fetched up front (8 independent 16-byte loads in flight)
-          uint2 auxh[8];          // bf16 mask rows
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = m0 + q * 32 + it * 4 + rsub;
-            aux[it] = make_float4(0, 0, 0, 0);
-            auxh[it] = make_uint2(0, 0);
-            if (grow < p.M) {
-              if (do_res || mask_f32) aux[it] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)grow * p.ep.ldr + gcol));
-              if (mask_b16)
-                auxh[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) +
-                                                                (size_t)grow * p.ep.ldr + gcol));
-              if ((fl & EPI_ACCUMULATE) && p.C) {
-                float4 c = ld4(p.C + (size_t)grow * p.ldc + gcol);
-                if (do_res) { aux[it].x += c.x; aux[it].y += c.y; aux[it].z += c.z; aux[it].w += c.w; }
-                else if (!mask_f32) aux[it] = c;
-              }
-            }
-          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
             const int grow = m0 + q * 32 + rr;
             float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            v.x += cur.bias.x; v.y += cur.bias.y; v.z += cur.bias.z; v.w += cur.bias.w;
             if (fl & EPI_SCALE_COLS) {
               if (gcol + 0 < p.ep.scale_ncols) v.x *= p.ep.alpha;
               if (gcol + 1 < p.ep.scale_ncols) v.y *= p.ep.alpha;
               if (gcol + 2 < p.ep.scale_ncols) v.z *= p.ep.alpha;
               if (gcol + 3 < p.ep.scale_ncols) v.w *= p.ep.alpha;
             }
-            if (do_res) { v.x += aux[it].x; v.y += aux[it].y; v.z += aux[it].z; v.w += aux[it].w; }
+            if (do_res || (do_acc && !mask_f32)) { v.x += cur.aux[it].x; v.y += cur.aux[it].y; v.z += cur.aux[it].z; v.w += cur.aux[it].w; }
             if (fl & EPI_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             if (mask_f32) {
-              if (!(aux[it].x > 0.f)) v.x = 0.f;
-              if (!(aux[it].y > 0.f)) v.y = 0.f;
-              if (!(aux[it].z > 0.f)) v.z = 0.f;
-              if (!(aux[it].w > 0.f)) v.w = 0.f;
+              if (!(cur.aux[it].x > 0.f)) v.x = 0.f;
+              if (!(cur.aux[it].y > 0.f)) v.y = 0.f;
+              if (!(cur.aux[it].z > 0.f)) v.z = 0.f;
+              if (!(cur.aux[it].w > 0.f)) v.w = 0.f;
             }
             if (mask_b16) {          // bf16 > 0  <=>  sign clear and magnitude non-zero
-              const uint32_t w0 = auxh[it].x, w1 = auxh[it].y;
+              const uint32_t w0 = cur.auxh[it].x, w1 = cur.auxh[it].y;
               if (!(((w0 & 0x8000u) == 0) && ((w0 & 0x7FFFu) != 0))) v.x = 0.f;
               if (!(((w0 >> 16 & 0x8000u) == 0) && ((w0 >> 16 & 0x7FFFu) != 0))) v.y = 0.f;
               if (!(((w1 & 0x8000u) == 0) && ((w1 & 0x7FFFu) != 0))) v.z = 0.f;
               if (!(((w1 >> 16 & 0x8000u) == 0) && ((w1 >> 16 & 0x7FFFu) != 0))) v.w = 0.f;
             }
-            if ((fl & EPI_ACCUMULATE) && p.C && !do_res && !mask_f32) { v.x += aux[it].x; v.y += aux[it].y; v.z += aux[it].z; v.w += aux[it].w; }
             if (grow < p.M) {
               if (p.C) st4(p.C + (size_t)grow * p.ldc + gcol, v);
               if (p.out_hi) {
@@ -476,6 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
+        cur = nxt;
       }
       tcgen05_fence_before();
       __syncwarp();
