@@ -32,6 +32,8 @@ def main():
     ap.add_argument('--rows', type=int, default=278528)
     ap.add_argument('--cfgs', default='1,2')
     ap.add_argument('--mode', default='bf16x3')
+    ap.add_argument('--only', type=int, default=-1, help='run a single case index (for ncu)')
+    ap.add_argument('--iters', type=int, default=10)
     args = ap.parse_args()
     ops.set_gemm_mode(args.mode)
     M, d, F = args.rows, 512, 2048
@@ -66,8 +68,10 @@ def main():
         ops.set_tile_config(cfg)
         print(f'--- tile config {cfg} mode {args.mode} rows {M} ---')
         tot_t = tot_f = 0.0
-        for (name, _, _, fn), fl in zip(cases, flops):
-            ms = timeit(fn)
+        for ci, ((name, _, _, fn), fl) in enumerate(zip(cases, flops)):
+            if args.only >= 0 and ci != args.only:
+                continue
+            ms = timeit(fn, args.iters)
             tot_t += ms
             tot_f += fl
             print(f'{name} {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s alg  {passes * fl / ms / 1e9:8.1f} tensor')

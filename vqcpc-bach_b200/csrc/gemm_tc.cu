@@ -349,7 +349,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
-    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 36);   // 32 x (32+4) floats
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -357,137 +356,131 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * CL + crank) * BM, n0 = (rem % p.n_tiles) * BN;
       const bool first_split = (ks == 0);
-      const int row = m0 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      const int fl = p.ep.flags;
-      // all alignment conditions of the vector path are tile-invariant (columns advance by 32 floats)
-      const bool aligned = (!p.C || ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 3) == 0)) &&
-                           (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
-                                          ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
-                           (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
-                           (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
-                            (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0))) &&
-                           !(fl & EPI_ATOMIC);
-      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-      const bool do_bias = first_split && (fl & EPI_BIAS);
-      const bool do_res = first_split && (fl & EPI_RESIDUAL);
-      const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
-      const bool mask_b16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
-      const bool do_acc = (fl & EPI_ACCUMULATE) && p.C;
-
-      // Operand prefetch for one 32-column chunk in the coalesced layout (8 lanes x 16 B per row, 4 rows per access):
-      // bias, residual / mask / running C.  Issued one chunk AHEAD (and for chunk 0 before the accumulator is even
-      // ready), so the global-memory latency is hidden behind the previous chunk instead of being paid 8x per tile.
-      struct Pre { float4 bias; float4 aux[8]; uint2 auxh[8]; };
-      auto prefetch = [&](int ch, Pre& pf) {
-        const int gcol = n0 + ch * 32 + c4;
-        pf.bias = make_float4(0, 0, 0, 0);
-        if (!(aligned && n0 + ch * 32 + 32 <= p.N)) return;
-        if (do_bias) pf.bias = __ldg(reinterpret_cast<const float4*>(p.ep.bias + gcol));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int grow = m0 + q * 32 + it * 4 + rsub;
-          pf.aux[it] = make_float4(0, 0, 0, 0);
-          pf.auxh[it] = make_uint2(0, 0);
-          if (grow < p.M) {
-            if (do_res || mask_f32) pf.aux[it] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)grow * p.ep.ldr + gcol));
-            if (mask_b16)
-              pf.auxh[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) +
-                                                                 (size_t)grow * p.ep.ldr + gcol));
-            if (do_acc) {
-              float4 c = ld4(p.C + (size_t)grow * p.ldc + gcol);
-              if (do_res) { pf.aux[it].x += c.x; pf.aux[it].y += c.y; pf.aux[it].z += c.z; pf.aux[it].w += c.w; }
-              else pf.aux[it] = c;
-            }
-          }
-        }
-      };
-      Pre cur, nxt;
-      prefetch(0, cur);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
-        if (ch + 1 < BN / 32) prefetch(ch + 1, nxt);
         tmem_ld_wait();
         const int col0 = n0 + ch * 32;
-        if (col0 + 32 <= p.N && aligned) {
-          // ---- fast path.  TMEM hands every thread 32 columns of ONE row; storing that directly would make each warp
-          // store touch 32 different 128-byte lines.  Transpose through a padded per-warp smem tile so that 8 lanes cover
-          // one row's 128 bytes: every global access of the epilogue is a coalesced 16-byte-per-lane vector access.
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 36 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          const int gcol = col0 + c4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const int grow = m0 + q * 32 + rr;
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + c4);
-            v.x += cur.bias.x; v.y += cur.bias.y; v.z += cur.bias.z; v.w += cur.bias.w;
-            if (fl & EPI_SCALE_COLS) {
-              if (gcol + 0 < p.ep.scale_ncols) v.x *= p.ep.alpha;
-              if (gcol + 1 < p.ep.scale_ncols) v.y *= p.ep.alpha;
-              if (gcol + 2 < p.ep.scale_ncols) v.z *= p.ep.alpha;
-              if (gcol + 3 < p.ep.scale_ncols) v.w *= p.ep.alpha;
-            }
-            if (do_res || (do_acc && !mask_f32)) { v.x += cur.aux[it].x; v.y += cur.aux[it].y; v.z += cur.aux[it].z; v.w += cur.aux[it].w; }
-            if (fl & EPI_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (mask_f32) {
-              if (!(cur.aux[it].x > 0.f)) v.x = 0.f;
-              if (!(cur.aux[it].y > 0.f)) v.y = 0.f;
-              if (!(cur.aux[it].z > 0.f)) v.z = 0.f;
-              if (!(cur.aux[it].w > 0.f)) v.w = 0.f;
-            }
-            if (mask_b16) {          // bf16 > 0  <=>  sign clear and magnitude non-zero
-              const uint32_t w0 = cur.auxh[it].x, w1 = cur.auxh[it].y;
-              if (!(((w0 & 0x8000u) == 0) && ((w0 & 0x7FFFu) != 0))) v.x = 0.f;
-              if (!(((w0 >> 16 & 0x8000u) == 0) && ((w0 >> 16 & 0x7FFFu) != 0))) v.y = 0.f;
-              if (!(((w1 & 0x8000u) == 0) && ((w1 & 0x7FFFu) != 0))) v.z = 0.f;
-              if (!(((w1 >> 16 & 0x8000u) == 0) && ((w1 >> 16 & 0x7FFFu) != 0))) v.w = 0.f;
-            }
-            if (grow < p.M) {
-              if (p.C) st4(p.C + (size_t)grow * p.ldc + gcol, v);
-              if (p.out_hi) {
-                __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                              h3 = __float2bfloat16_rn(v.w);
-                __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                              l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-                uint2 hv, lv;
-                hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-                lv.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                lv.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
-                *reinterpret_cast<uint2*>(p.out_hi + (size_t)grow * p.ldo + gcol) = hv;
-                *reinterpret_cast<uint2*>(p.out_lo + (size_t)grow * p.ldo + gcol) = lv;
-              }
-            }
-          }
-          __syncwarp();          // staging tile is reused by the next chunk
-        } else if (row < p.M && col0 < p.N) {
-          // ---- edge / split-K path: element-wise, one row per thread
+        if (row < p.M && col0 < p.N) {
           float* dst = p.C ? p.C + (size_t)row * p.ldc + col0 : nullptr;
+          const int fl = p.ep.flags;
+          const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                               (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                              ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                               (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                               (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                                (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+          if (col0 + 32 <= p.N && aligned && !(fl & EPI_ATOMIC)) {
+            // ---- fast path: 32 contiguous columns of one row per thread, all accesses 16-byte vectors
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-              float v = epilogue_apply(__uint_as_float(r[j]), row, col0 + j, p.ep, first_split);
-              if (dst) {
-                if (fl & EPI_ATOMIC) atomicAdd(dst + j, v);
-                else if (fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
-                else dst[j] = v;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (first_split && (fl & EPI_BIAS)) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + q4);
+                v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
               }
-              if (p.out_hi) {
-                __nv_bfloat16 h = __float2bfloat16_rn(v);
-                p.out_hi[(size_t)row * p.ldo + col0 + j] = h;
-                p.out_lo[(size_t)row * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+            if (fl & EPI_SCALE_COLS) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.ep.scale_ncols) ? v[j] * p.ep.alpha : v[j];
+            }
+            if (first_split && (fl & EPI_RESIDUAL)) {
+              const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 b = __ldg(rp + q4);
+                v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
+              }
+            }
+            if (fl & EPI_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (fl & EPI_RELU_MASK) {
+              if (fl & EPI_MASK_BF16) {
+                const uint4* mp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                  uint4 mv = __ldg(mp + q8);
+                  const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                  for (int h = 0; h < 4; ++h) {
+                    // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                    uint32_t lo16 = w[h] & 0xFFFFu, hi16 = w[h] >> 16;
+                    if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2] = 0.f;
+                    if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2 + 1] = 0.f;
+                  }
+                }
+              } else {
+                const float4* mp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                  float4 b = __ldg(mp + q4);
+                  if (!(b.x > 0.f)) v[q4 * 4] = 0.f;
+                  if (!(b.y > 0.f)) v[q4 * 4 + 1] = 0.f;
+                  if (!(b.z > 0.f)) v[q4 * 4 + 2] = 0.f;
+                  if (!(b.w > 0.f)) v[q4 * 4 + 3] = 0.f;
+                }
+              }
+            }
+            if (dst) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 o = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+                if (fl & EPI_ACCUMULATE) {
+                  float4 c = ld4(dst + q4 * 4);
+                  o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                  v[q4 * 4] = o.x; v[q4 * 4 + 1] = o.y; v[q4 * 4 + 2] = o.z; v[q4 * 4 + 3] = o.w;
+                }
+                st4(dst + q4 * 4, o);
+              }
+            }
+            if (p.out_hi) {
+              uint32_t hw[16], lw[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+                __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+                hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              uint4* hp = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldo + col0);
+              uint4* lp = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldo + col0);
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                hp[q8] = make_uint4(hw[q8 * 4], hw[q8 * 4 + 1], hw[q8 * 4 + 2], hw[q8 * 4 + 3]);
+                lp[q8] = make_uint4(lw[q8 * 4], lw[q8 * 4 + 1], lw[q8 * 4 + 2], lw[q8 * 4 + 3]);
+              }
+            }
+          } else {
+            // ---- edge / split-K path: element-wise
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                float v = epilogue_apply(__uint_as_float(r[j]), row, col0 + j, p.ep, first_split);
+                if (dst) {
+                  if (fl & EPI_ATOMIC) atomicAdd(dst + j, v);
+                  else if (fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
+                  else dst[j] = v;
+                }
+                if (p.out_hi) {
+                  __nv_bfloat16 h = __float2bfloat16_rn(v);
+                  p.out_hi[(size_t)row * p.ldo + col0 + j] = h;
+                  p.out_lo[(size_t)row * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
               }
             }
           }
         }
-        cur = nxt;
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -547,7 +540,7 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
 template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES, int CL>
 int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK * 2 + BN * BK * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES, CL>;
   static bool done = false;
