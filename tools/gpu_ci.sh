@@ -24,6 +24,7 @@ for g in $groups; do
     gemm_tc1)  VQCPC_GEMM_TILE=1 run gemm_tc1 tests/test_gpu_gemm.py "not fp32" ;;
     gemm_tc2)  VQCPC_GEMM_TILE=2 run gemm_tc2 tests/test_gpu_gemm.py "not fp32" ;;
     gemm_tc3)  VQCPC_GEMM_TILE=3 run gemm_tc3 tests/test_gpu_gemm.py "not fp32" ;;
+    gemm_tc4)  VQCPC_GEMM_TILE=4 run gemm_tc4 tests/test_gpu_gemm.py "not fp32" ;;
     enc_fp32)  run enc_fp32 tests/test_gpu_encoder.py "fp32 or micro or eval or first_call or fused" ;;
     enc_tc)    run enc_tc tests/test_gpu_encoder.py "bf16x3" ;;
   esac
