@@ -45,8 +45,8 @@ def main():
         print(f'[ddp_check] world={world} identical parameters across ranks: {same}')
         ref = build_product_trainer(cfg)
         load_params_into(ref, prm)
+        ref.distributed = False                # no collectives at all in the single-process reference
         ref.init_optimizers(1e-3, False)
-        ref.optimizer.distributed = False
         ref.train()
         ref_stats = []
         for s in range(2):
@@ -55,7 +55,6 @@ def main():
         torch.cuda.synchronize()
         a, b = tr.optimizer.flat.data, ref.optimizer.flat.data
         rel = ((a - b).double().norm() / b.double().norm()).item()
-        upd = (b - torch.cat([p.reshape(-1) for p in []]) if False else None)
         moved = (b.double() - _flat_of(prm, ref).double()).norm().item()
         drift = (a - b).double().norm().item() / max(moved, 1e-30)
         l_ddp = float(stats[1]['loss'])            # averaged over ranks by the all-reduce tail

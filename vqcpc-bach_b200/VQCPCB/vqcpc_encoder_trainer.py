@@ -64,6 +64,7 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         self.max_blocks_per_pass = int(os.environ.get('VQCPC_MAX_BLOCKS_PER_PASS', 17408))
         self.is_main_process = vq_dist.rank() == 0
         self.last_grad_norm_sq = None
+        self.distributed = True     # False: ignore an initialised process group (single-process reference runs)
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _modules_in_order(self):
@@ -78,10 +79,11 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         params = []
         for m in self._modules_in_order():
             params += list(m.parameters())
-        if vq_dist.world_size() > 1:
+        if self.distributed and vq_dist.world_size() > 1:
             vq_dist.broadcast_parameters(params)          # replicas must start identical
         self.flat = FlatParams(params)
         self.optimizer = FusedClipAdam(self.flat, lr=lr, extra_tail=self._tail_size())
+        self.optimizer.distributed = self.distributed
         ops.bump_weight_version()
         if schedule_lr:
             warmup_steps, lo, hi = 10000, 0.1, 1.0
