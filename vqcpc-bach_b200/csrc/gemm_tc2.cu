@@ -19,7 +19,7 @@ using namespace vqtc;
 namespace {
 
 constexpr int BN2 = 256;        // tile columns (128 per CTA of the B operand)
-constexpr int BK2 = 32;
+constexpr int BK2 = 64;
 constexpr int HALF_N = BN2 / 2;
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
@@ -197,6 +197,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else {
     // =============================== epilogue (warps 2..5, both CTAs, own 128 rows) ===============================
     const int q = warp & 3;
+    float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -204,10 +205,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * 2 + crank) * BM, n0 = (rem % p.n_tiles) * BN2;
       const bool first_split = (ks == 0);
+      // operands that do not depend on the accumulator are fetched before it is awaited
+      const EpiCtx ec = epi_ctx(p, m0, q, lane, first_split);
+      epi_stage_bias<BN2>(p, ec, n0, lane, bias_s);
+      EpiOperand eo;
+      epi_fetch(p, ec, n0, eo);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
-      epilogue_tile<BN2>(p, taddr, m0, n0, q, lane, first_split);
+      epilogue_tile<BN2>(p, ec, taddr, n0, first_split, bias_s, eo);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // leader's barrier
@@ -227,7 +233,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 template <bool AK, bool BKM, int PASSES, int STAGES>
 int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK2 * 2 + HALF_N * BK2 * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES>;
   static bool done = false;
@@ -263,8 +269,8 @@ int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 // Tile configuration 4 of vqcpc_gemm_bf16x3_ex: CTA pairs, 256 x 256 x 32 tiles.  `p` carries m_tiles in units of 128
 // rows and n_tiles in units of 256 columns; maps[2..3] (B) must use boxes of 128 rows (K-major) / 64 x 32 (MN-major).
 int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
-  if (a_kmajor && b_kmajor) return passes == 3 ? launch_pair<true, true, 3, 6>(maps, p, st) : launch_pair<true, true, 1, 12>(maps, p, st);
-  if (a_kmajor && !b_kmajor) return passes == 3 ? launch_pair<true, false, 3, 6>(maps, p, st) : launch_pair<true, false, 1, 12>(maps, p, st);
-  if (!a_kmajor && b_kmajor) return passes == 3 ? launch_pair<false, true, 3, 6>(maps, p, st) : launch_pair<false, true, 1, 12>(maps, p, st);
-  return passes == 3 ? launch_pair<false, false, 3, 6>(maps, p, st) : launch_pair<false, false, 1, 12>(maps, p, st);
+  if (a_kmajor && b_kmajor) return passes == 3 ? launch_pair<true, true, 3, 3>(maps, p, st) : launch_pair<true, true, 1, 6>(maps, p, st);
+  if (a_kmajor && !b_kmajor) return passes == 3 ? launch_pair<true, false, 3, 3>(maps, p, st) : launch_pair<true, false, 1, 6>(maps, p, st);
+  if (!a_kmajor && b_kmajor) return passes == 3 ? launch_pair<false, true, 3, 3>(maps, p, st) : launch_pair<false, true, 1, 6>(maps, p, st);
+  return passes == 3 ? launch_pair<false, false, 3, 3>(maps, p, st) : launch_pair<false, false, 1, 6>(maps, p, st);
 }
