@@ -187,7 +187,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                               // TMEM lane quadrant this warp may access
-    float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -195,15 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * CL + crank) * BM, n0 = (rem % p.n_tiles) * BN;
       const bool first_split = (ks == 0);
-      // operands that do not depend on the accumulator are fetched before it is awaited
-      const EpiCtx ec = epi_ctx(p, m0, q, lane, first_split);
-      epi_stage_bias<BN>(p, ec, n0, lane, bias_s);
-      EpiOperand eo;
-      epi_fetch(p, ec, n0, eo);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(p, ec, taddr, n0, first_split, bias_s, eo);
+      epilogue_tile<BN>(p, taddr, m0, n0, q, lane, first_split);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -266,7 +260,7 @@ namespace {
 template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES, int CL>
 int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK * 2 + BN * BK * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES, CL>;
   static bool done = false;
@@ -310,10 +304,13 @@ int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 //                         2 = 128x256x32 with the B tile multicast over a cluster of 2 CTAs along M, 3 = cluster of 4,
 //                         4 = CTA pairs (tcgen05.mma.cta_group::2), 256x256x32 tiles, 6 / 12 stages (gemm_tc2.cu)
 int g_force_cfg = -1;
-inline int pick_cfg(int M, int N) {
+inline int pick_cfg(int M, int N, bool b_kmajor) {
   if (g_force_cfg >= 0) return (N < 256 && g_force_cfg > 0) ? 0 : g_force_cfg;
   if (N < 256) return 0;
-  return M >= 4 * BM ? 3 : (M >= 2 * BM ? 2 : 1);
+  if (M < 2 * BM) return 1;
+  // measured on the encoder shapes (profiles/r01_gemm_bench_*.txt): the CTA-pair kernel wins when B is K-major
+  // (forward GEMMs), the multicast kernel when B is MN-major (data / weight gradients)
+  return b_kmajor ? 4 : 2;
 }
 
 template <bool AK, bool BKM>
@@ -363,7 +360,7 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
-  const int cfg = pick_cfg(M, N);
+  const int cfg = pick_cfg(M, N, b_kmajor != 0);
   const int BN = cfg >= 1 ? 256 : 128, BK = (cfg >= 1 && cfg <= 3) ? 32 : 64;
   const int CLh = cfg == 3 ? 4 : (cfg == 2 || cfg == 4 ? 2 : 1);   // B K-major boxes cover BN / CL rows (pair: own half)
   p.m_tiles = (int)vq_cdiv(M, BM);

@@ -1,4 +1,4 @@
-// CTA-pair variant of the tensor-core GEMM: tcgen05.mma.cta_group::2 on 256 x 256 x 32 tiles.
+// CTA-pair variant of the tensor-core GEMM: tcgen05.mma.cta_group::2 on 256 x 256 x 64 tiles.
 //
 // Two CTAs of a cluster (same TPC) form one MMA: CTA r owns rows [r*128, r*128+128) of the 256-row tile (its half of
 // the accumulator lives in its own TMEM) and columns [r*128, r*128+128) of the B tile; the tensor cores of the pair
@@ -19,7 +19,7 @@ using namespace vqtc;
 namespace {
 
 constexpr int BN2 = 256;        // tile columns (128 per CTA of the B operand)
-constexpr int BK2 = 64;
+constexpr int BK2 = 64;        // 128-byte rows: SWIZZLE_128B for K-major tiles (measured faster than 64B/BK=32 here)
 constexpr int HALF_N = BN2 / 2;
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
@@ -197,7 +197,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else {
     // =============================== epilogue (warps 2..5, both CTAs, own 128 rows) ===============================
     const int q = warp & 3;
-    float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -205,15 +204,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * 2 + crank) * BM, n0 = (rem % p.n_tiles) * BN2;
       const bool first_split = (ks == 0);
-      // operands that do not depend on the accumulator are fetched before it is awaited
-      const EpiCtx ec = epi_ctx(p, m0, q, lane, first_split);
-      epi_stage_bias<BN2>(p, ec, n0, lane, bias_s);
-      EpiOperand eo;
-      epi_fetch(p, ec, n0, eo);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
-      epilogue_tile<BN2>(p, ec, taddr, n0, first_split, bias_s, eo);
+      epilogue_tile<BN2>(p, taddr, m0, n0, q, lane, first_split);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // leader's barrier
@@ -233,7 +227,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 template <bool AK, bool BKM, int PASSES, int STAGES>
 int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK2 * 2 + HALF_N * BK2 * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES>;
   static bool done = false;

@@ -171,174 +171,133 @@ struct TcParams {
   int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// Epilogue of one 128 x BN accumulator tile held in TMEM (lane quadrant q of this warp): 32-column chunks,
-// tcgen05.ld -> fused bias / scale / residual / ReLU / mask -> fp32 and / or bf16-split stores (atomics for split-K).
-// Every thread owns one output row (TMEM lane) and 32 consecutive columns per chunk (128 contiguous bytes).
-//
-// Global-memory latency is kept off the per-chunk critical path (ncu showed the epilogue warps stalled on the bias /
-// residual loads of every chunk): the tile's bias row is staged once in a per-warp smem buffer BEFORE the accumulator
-// is awaited, and the residual / mask operands of chunk c+1 are fetched while chunk c is being processed.
-constexpr int EPI_SMEM_BYTES = 4 * 256 * 4;     // 4 epilogue warps x 256 bias floats
-
-struct EpiOperand {       // residual (fp32) or ReLU-mask (fp32 / bf16) values of one 32-column chunk of this thread's row
-  float4 f[8];
-  uint4 h[4];
-};
-
-struct EpiCtx {
-  int row, fl;
-  bool vec, do_bias, do_res, mask_f32, mask_b16, do_acc;
-};
-
-__device__ __forceinline__ EpiCtx epi_ctx(const TcParams& p, int m0, int q, int lane, bool first_split) {
-  EpiCtx c;
-  c.row = m0 + q * 32 + lane;
-  c.fl = p.ep.flags;
-  // vector-path alignment conditions are tile invariant (columns advance by 32 floats)
-  c.vec = (!p.C || ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 3) == 0)) &&
-          (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
-          (!(c.fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
-           (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0))) &&
-          !(c.fl & EPI_ATOMIC);
-  c.do_bias = first_split && (c.fl & EPI_BIAS);
-  c.do_res = first_split && (c.fl & EPI_RESIDUAL);
-  c.mask_f32 = (c.fl & EPI_RELU_MASK) && !(c.fl & EPI_MASK_BF16);
-  c.mask_b16 = (c.fl & EPI_RELU_MASK) && (c.fl & EPI_MASK_BF16);
-  c.do_acc = (c.fl & EPI_ACCUMULATE) && p.C;
-  return c;
-}
-
-// stage bias[n0 .. n0+BN) in this warp's smem buffer (zeros beyond N / without bias)
+// Epilogue of one 128 x BN accumulator tile held in TMEM at `taddr` (lane quadrant q of this warp): 32-column chunks,
+// tcgen05.ld -> fused bias / scale / residual / ReLU / mask -> fp32 and / or bf16-split stores (or atomics for split-K).
 template <int BN>
-__device__ __forceinline__ void epi_stage_bias(const TcParams& p, const EpiCtx& c, int n0, int lane, float* bias_s) {
-  __syncwarp();          // every lane is done reading the previous tile's bias
-#pragma unroll
-  for (int j = lane; j < BN; j += 32) bias_s[j] = (c.do_bias && n0 + j < p.N) ? __ldg(p.ep.bias + n0 + j) : 0.f;
-  __syncwarp();
-}
-
-__device__ __forceinline__ void epi_fetch(const TcParams& p, const EpiCtx& c, int col0, EpiOperand& o) {
-  if (!(c.vec && col0 + 32 <= p.N && c.row < p.M)) return;
-  if (c.do_res || c.mask_f32) {
-    const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)c.row * p.ep.ldr + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o.f[j] = __ldg(rp + j);
-  }
-  if (c.mask_b16) {
-    const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)c.row * p.ep.ldr + col0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o.h[j] = __ldg(mp + j);
-  }
-  if (c.do_acc) {
-    const float4* cp = reinterpret_cast<const float4*>(p.C + (size_t)c.row * p.ldc + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 v = cp[j];
-      if (c.do_res) { o.f[j].x += v.x; o.f[j].y += v.y; o.f[j].z += v.z; o.f[j].w += v.w; }
-      else o.f[j] = v;
-    }
-  }
-}
-
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, const EpiCtx& c, uint32_t taddr, int n0, bool first_split,
-                                              const float* bias_s, EpiOperand& cur) {
-  EpiOperand nxt;
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane, bool first_split) {
+  const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-  for (int ch = 0; ch < BN / 32; ++ch) {
-    uint32_t r[32];
-    tmem_ld32(taddr + ch * 32, r);
-    if (ch + 1 < BN / 32) epi_fetch(p, c, n0 + (ch + 1) * 32, nxt);      // next chunk's operands fly during this chunk
-    tmem_ld_wait();
-    const int col0 = n0 + ch * 32;
-    if (c.row < p.M && col0 < p.N) {
-      if (c.vec && col0 + 32 <= p.N) {
-        float v[32];
+for (int ch = 0; ch < BN / 32; ++ch) {
+  uint32_t r[32];
+  tmem_ld32(taddr + ch * 32, r);
+  tmem_ld_wait();
+  const int col0 = n0 + ch * 32;
+  if (row < p.M && col0 < p.N) {
+    float* dst = p.C ? p.C + (size_t)row * p.ldc + col0 : nullptr;
+    const int fl = p.ep.flags;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                         (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                        ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                         (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                         (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                          (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+    if (col0 + 32 <= p.N && aligned && !(fl & EPI_ATOMIC)) {
+      // ---- fast path: 32 contiguous columns of one row per thread, all accesses 16-byte vectors
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[ch * 32 + j];
-        if (c.fl & EPI_SCALE_COLS) {
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (first_split && (fl & EPI_BIAS)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.ep.scale_ncols) ? v[j] * p.ep.alpha : v[j];
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + q4);
+          v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
         }
-        if (c.do_res || (c.do_acc && !c.mask_f32)) {
+      }
+      if (fl & EPI_SCALE_COLS) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += cur.f[j].x; v[4 * j + 1] += cur.f[j].y; v[4 * j + 2] += cur.f[j].z; v[4 * j + 3] += cur.f[j].w;
-          }
-        }
-        if (c.fl & EPI_RELU) {
+        for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.ep.scale_ncols) ? v[j] * p.ep.alpha : v[j];
+      }
+      if (first_split && (fl & EPI_RESIDUAL)) {
+        const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 b = __ldg(rp + q4);
+          v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
         }
-        if (c.mask_f32) {
+      }
+      if (fl & EPI_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (!(cur.f[j].x > 0.f)) v[4 * j] = 0.f;
-            if (!(cur.f[j].y > 0.f)) v[4 * j + 1] = 0.f;
-            if (!(cur.f[j].z > 0.f)) v[4 * j + 2] = 0.f;
-            if (!(cur.f[j].w > 0.f)) v[4 * j + 3] = 0.f;
-          }
-        }
-        if (c.mask_b16) {
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (fl & EPI_RELU_MASK) {
+        if (fl & EPI_MASK_BF16) {
+          const uint4* mp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0);
 #pragma unroll
           for (int q8 = 0; q8 < 4; ++q8) {
-            const uint32_t w[4] = {cur.h[q8].x, cur.h[q8].y, cur.h[q8].z, cur.h[q8].w};
+            uint4 mv = __ldg(mp + q8);
+            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {      // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              const uint32_t lo16 = w[hh] & 0xFFFFu, hi16 = w[hh] >> 16;
-              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + hh * 2] = 0.f;
-              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + hh * 2 + 1] = 0.f;
+            for (int h = 0; h < 4; ++h) {
+              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+              uint32_t lo16 = w[h] & 0xFFFFu, hi16 = w[h] >> 16;
+              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2] = 0.f;
+              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2 + 1] = 0.f;
             }
           }
-        }
-        if (p.C) {
-          float* dst = p.C + (size_t)c.row * p.ldc + col0;
+        } else {
+          const float4* mp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) st4(dst + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-        }
-        if (p.out_hi) {
-          uint32_t hw[16], lw[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-            __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-            __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-            hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          uint4* hp = reinterpret_cast<uint4*>(p.out_hi + (size_t)c.row * p.ldo + col0);
-          uint4* lp = reinterpret_cast<uint4*>(p.out_lo + (size_t)c.row * p.ldo + col0);
-#pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            hp[q8] = make_uint4(hw[q8 * 4], hw[q8 * 4 + 1], hw[q8 * 4 + 2], hw[q8 * 4 + 3]);
-            lp[q8] = make_uint4(lw[q8 * 4], lw[q8 * 4 + 1], lw[q8 * 4 + 2], lw[q8 * 4 + 3]);
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float4 b = __ldg(mp + q4);
+            if (!(b.x > 0.f)) v[q4 * 4] = 0.f;
+            if (!(b.y > 0.f)) v[q4 * 4 + 1] = 0.f;
+            if (!(b.z > 0.f)) v[q4 * 4 + 2] = 0.f;
+            if (!(b.w > 0.f)) v[q4 * 4 + 3] = 0.f;
           }
         }
-      } else {
-        // ---- edge / split-K path: element-wise
-        float* dst = p.C ? p.C + (size_t)c.row * p.ldc + col0 : nullptr;
+      }
+      if (dst) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j < p.N) {
-            float v = epilogue_apply(__uint_as_float(r[j]), c.row, col0 + j, p.ep, first_split);
-            if (dst) {
-              if (c.fl & EPI_ATOMIC) atomicAdd(dst + j, v);
-              else if (c.fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
-              else dst[j] = v;
-            }
-            if (p.out_hi) {
-              __nv_bfloat16 h = __float2bfloat16_rn(v);
-              p.out_hi[(size_t)c.row * p.ldo + col0 + j] = h;
-              p.out_lo[(size_t)c.row * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
-            }
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 o = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          if (fl & EPI_ACCUMULATE) {
+            float4 c = ld4(dst + q4 * 4);
+            o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            v[q4 * 4] = o.x; v[q4 * 4 + 1] = o.y; v[q4 * 4 + 2] = o.z; v[q4 * 4 + 3] = o.w;
+          }
+          st4(dst + q4 * 4, o);
+        }
+      }
+      if (p.out_hi) {
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+          __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+          __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+          hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        uint4* hp = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldo + col0);
+        uint4* lp = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldo + col0);
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          hp[q8] = make_uint4(hw[q8 * 4], hw[q8 * 4 + 1], hw[q8 * 4 + 2], hw[q8 * 4 + 3]);
+          lp[q8] = make_uint4(lw[q8 * 4], lw[q8 * 4 + 1], lw[q8 * 4 + 2], lw[q8 * 4 + 3]);
+        }
+      }
+    } else {
+      // ---- edge / split-K path: element-wise
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < p.N) {
+          float v = epilogue_apply(__uint_as_float(r[j]), row, col0 + j, p.ep, first_split);
+          if (dst) {
+            if (fl & EPI_ATOMIC) atomicAdd(dst + j, v);
+            else if (fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
+            else dst[j] = v;
+          }
+          if (p.out_hi) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            p.out_hi[(size_t)row * p.ldo + col0 + j] = h;
+            p.out_lo[(size_t)row * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
           }
         }
       }
     }
-    cur = nxt;
   }
+}
 }
 
 // host helpers shared by both kernels (defined in gemm_tc.cu)
