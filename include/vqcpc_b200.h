@@ -132,6 +132,14 @@ int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* books /*h
  * counts (Kc) ACCUMULATED or NULL.  Replaces vector_quantizer.py:104-157 + mlp_upscaler.py:21-35 on every vector. */
 int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
                        int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, void* stream);
+/* Same, with the search algorithm selectable: algo 0 = automatic, 1 = direct-form scan on the CUDA cores (the
+ * reference's arithmetic for every (vector, code) pair), 2 = tcgen05 tensor-core ranking of z.e - |e|^2/2 followed by
+ * exact re-evaluation of the codes within the error margin (D in {3, 4}, Kc <= 2048).  Indices are bit-identical between
+ * the two.  dbg_scores (n, ceil(Kc/256)*256) and stats[4098] (exact group re-evaluations, full-scan fallbacks, then 8
+ * clock64 stamps per CTA) are test / profiling hooks of algo 2 and are NULL in production. */
+int vqcpc_vq_fused_fwd_ex(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                          int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, int algo,
+                          float* dbg_scores, int* stats, void* stream);
 /* backward: d_x = J[idx]^T dy + g_loss * dloss/dx (J (Kc, zd, D) = upscaler Jacobian at each code; straight-through);
  * d_T[idx] += dy and d_E[idx] += g_loss * dloss/dq are ACCUMULATED. */
 int vqcpc_vq_fused_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,

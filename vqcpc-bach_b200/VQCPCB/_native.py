@@ -39,6 +39,7 @@ SIGNATURES = {
     'vqcpc_vq_gather': [_P, _L, _I, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
     'vqcpc_vq_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
     'vqcpc_vq_fused_fwd': [_P, _L, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
+    'vqcpc_vq_fused_fwd_ex': [_P, _L, _I, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     'vqcpc_vq_fused_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],

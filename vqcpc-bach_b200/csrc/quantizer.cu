@@ -11,6 +11,9 @@
 // Algorithmic traffic per vector (D=3, one codebook): 12 B in, 12 + 8 + 4 B out -> HBM-bound; the codebook tile is
 // staged once per CTA in shared memory and read as warp-wide broadcasts.
 #include "common.cuh"
+#include "vq_dist.cuh"
+#include "vq_tc.h"
+#include <cstdlib>
 
 namespace {
 
@@ -19,30 +22,6 @@ struct Books {
   const float* e[MAX_CB];
   float* g[MAX_CB];
 };
-
-// sum of (x_d - e_d)^2 over d in torch-CPU order (see header); x in registers when DS is a compile-time constant
-template <int DS>
-__device__ __forceinline__ float dist_fixed(const float* x, const float* __restrict__ e) {
-  constexpr int W = (DS % 32 == 0) ? 32 : 8;
-  float acc[W];
-#pragma unroll
-  for (int l = 0; l < W; ++l) acc[l] = 0.f;
-#pragma unroll
-  for (int d = 0; d < DS; ++d) {
-    float df = __fsub_rn(x[d], e[d]);
-    float sq = __fmul_rn(df, df);
-    acc[d % W] = (d < W) ? sq : __fadd_rn(acc[d % W], sq);
-  }
-  if (W == 32) {
-#pragma unroll
-    for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[l], acc[8 + l]), acc[16 + l]), acc[24 + l]);
-  }
-  float s = acc[0];
-#pragma unroll
-  for (int l = 1; l < 8; ++l)
-    if (l < DS) s = __fadd_rn(s, acc[l]);
-  return s;
-}
 
 __device__ __forceinline__ float dist_generic(const float* __restrict__ x, const float* __restrict__ e, int DS) {
   const int W = (DS % 32 == 0) ? 32 : 8;
@@ -389,18 +368,16 @@ VQ_API int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* bo
   return VQ_OK;
 }
 
-// Fused single-codebook bottleneck with the upscaler folded into a table: see vq_fused_fwd_kernel.
+// Fused single-codebook bottleneck with the upscaler folded into a table: see vq_fused_fwd_kernel / vq_tc.cu.
 //   x (n, D); E (Kc, D); T (Kc, zd) = upscaler(E) or NULL (then y is not written); idx (n) int64; loss (n);
 //   z_sg (n, D) optional; y (n, zd) optional; counts (Kc) int32 ACCUMULATED, optional.
-VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
-                              int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, void* stream) {
-  VQ_CHECK_ARG(D == 3 || D == 4 || D == 8 || D == 16 || D == 32, "vq_fused_fwd: D must be 3, 4, 8, 16 or 32 (got %d)", D);
-  VQ_CHECK_ARG((T == nullptr) == (y == nullptr), "vq_fused_fwd: T and y go together");
-  if (n == 0) return VQ_OK;
+//   algo: 0 = automatic, 1 = direct-form scan on the CUDA cores, 2 = tcgen05 score + exact verification (vq_tc.cu).
+//   Both algorithms return bit-identical indices.  dbg_scores / stats: test hooks of algo 2 (NULL in production).
+static int vq_fused_fwd_direct(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                               int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, cudaStream_t st) {
   const int cs = D == 3 ? 4 : D;
   size_t smem = ((size_t)Kc * cs + Kc) * sizeof(float);
   VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_fwd: codebook (%zu B) does not fit in shared memory", smem);
-  cudaStream_t st = vq_stream(stream);
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * per_sm));
 #define VQ_FL(DSV)                                                                                                          \
@@ -418,6 +395,31 @@ VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, 
 #undef VQ_FL
   VQ_CUDA_LAUNCH_CHECK("vq_fused_fwd_kernel");
   return VQ_OK;
+}
+
+VQ_API int vqcpc_vq_fused_fwd_ex(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                                 int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, int algo,
+                                 float* dbg_scores, int* stats, void* stream) {
+  VQ_CHECK_ARG(D == 3 || D == 4 || D == 8 || D == 16 || D == 32, "vq_fused_fwd: D must be 3, 4, 8, 16 or 32 (got %d)", D);
+  VQ_CHECK_ARG((T == nullptr) == (y == nullptr), "vq_fused_fwd: T and y go together");
+  VQ_CHECK_ARG(algo >= 0 && algo <= 2, "vq_fused_fwd: algo must be 0 (auto), 1 (direct) or 2 (tensor) (got %d)", algo);
+  if (n == 0) return VQ_OK;
+  cudaStream_t st = vq_stream(stream);
+  if (algo == 0) {
+    // the tensor-core search pays off once the direct scan costs more than a few microseconds
+    algo = (vq_tc_supported(D, Kc) && Kc >= 64 && n * (int64_t)Kc >= ((int64_t)1 << 22)) ? 2 : 1;
+  }
+  if (algo == 2) {
+    VQ_CHECK_ARG(vq_tc_supported(D, Kc), "vq_fused_fwd: tensor-core search supports D in {3, 4}, Kc <= 2048 (got D=%d Kc=%d)", D, Kc);
+    static const int variant = getenv("VQCPC_VQTC_LAYOUT") ? atoi(getenv("VQCPC_VQTC_LAYOUT")) : 0;
+    return vq_tc_fused_fwd(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, counts, dbg_scores, stats, variant, st);
+  }
+  return vq_fused_fwd_direct(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, counts, st);
+}
+
+VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                              int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, void* stream) {
+  return vqcpc_vq_fused_fwd_ex(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, counts, 0, nullptr, nullptr, stream);
 }
 
 // Backward of the fused path: d_x (n, D) overwritten; d_T (Kc, zd) and d_E (Kc, D) ACCUMULATED.
