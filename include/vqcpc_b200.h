@@ -151,6 +151,8 @@ int vqcpc_vq_fused_bwd(const float* x, int64_t n, int D, const float* E, const f
  * neg (B, KR, N), lse (B, KR), nll = lse - pos (B, KR), correct (B, KR) int32 = [pos > max_n neg]. */
 int vqcpc_infonce_fwd(const float* c, const float* W, const float* y_pos, const float* y_neg, int B, int N, int KR, int zd,
                       int cd, float* u, float* pos, float* neg, float* lse, float* nll, int* correct, void* stream);
+/* tuning / test hook: forward kernel choice, 0 = automatic, 1 = warp per (b, k), 2 = streaming cp.async.bulk ring. */
+int vqcpc_infonce_set_algo(int algo);
 /* gradient of sum(nll) scaled by scale * g_dev[0] (g_dev device scalar or NULL); d_c, d_W ACCUMULATED. */
 int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos, const float* y_neg, const float* u,
                       const float* pos, const float* neg, const float* lse, const float* g_dev, float scale, int B, int N,

@@ -17,6 +17,7 @@
 namespace {
 
 constexpr int MAXZ = 128;   // zd <= 128 (4 floats per lane)
+int g_nce_algo = 0;         // 0 = automatic, 1 = warp-per-(b,k) kernel, 2 = streaming kernel (test / tuning hook)
 
 template <int ZPL>   // z elements per lane: zd <= 32*ZPL
 __global__ void __launch_bounds__(256)
@@ -181,18 +182,274 @@ infonce_bwd_kernel(const float* __restrict__ c, const float* __restrict__ W, con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Streaming forward: the scoring is a batched GEMV at ~0.5 FLOP/B, i.e. purely HBM-bound (16.6 KB per sample at
+// KR = 8, N = 15, zd = 32).  Persistent CTAs pull GROUPS of 8/KR samples through rings of shared-memory stages with
+// cp.async.bulk (three 1-D TMA copies per group: the contiguous negatives, positives and context vectors;
+// completion on an mbarrier), so several stages (>= 100 KB per SM) are always in flight and no thread ever waits on a
+// global load:
+//   U phase: u[k, z] = sum_c W[z, c, k] c[c]           (thread per (k, z); its W row stays in registers)
+//   S phase: score[k, n] = sum_z u[k, z] y[n, k, z]    (thread per (k, n); n = N is the positive), then the
+//            log-sum-exp / accuracy bit of a (sample, k) with shuffles among its 16 lanes
+// Every row block starts at bank 0, so lane l walks the 16-byte chunks of its row in the rotated order (j + l) mod 8;
+// the chunk partial sums are combined by the rotation-invariant tree ((p0+p4)+(p2+p6))+((p1+p5)+(p3+p7)) (generalised to
+// 8 chunks), so every lane computes the SAME floating-point expression of its row whatever its rotation: identical
+// vectors give bit-equal scores and a negative equal to the positive is never counted "correct".
+__device__ __forceinline__ uint32_t nce_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nce_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void nce_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nce_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void nce_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (it > (1u << 26)) { printf("vqcpc infonce: mbarrier wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void nce_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// The streaming kernel is specialised for the shapes every shipped configuration uses - zd = cd = 32 (upscaler output,
+// c_net output), N = 15 negatives - and KR in {2, 4, 8}.  A CTA is NCE_TEAMS independent teams of 128 threads; each team
+// streams its own sample groups (8 / KR samples = 8 (sample, k) rows x 16 scores = one score per thread, 256 u values =
+// two per thread) through its own ring and synchronises on its own named barrier, so the load -> fma -> shuffle
+// latency chains of different teams overlap.  Other shapes use infonce_fwd_kernel.
+constexpr int NCE_TEAMS = 4, NCE_TT = 128, NCE_THREADS = NCE_TEAMS * NCE_TT;
+constexpr int NCE_ZD = 32, NCE_CD = 32, NCE_GRP = 16, NCE_N = NCE_GRP - 1, NCE_NC = NCE_ZD / 4;
+
+struct NceParams {
+  const float *c, *W, *ypos, *yneg;
+  int B, nst;
+  float *u, *pos, *neg, *lse, *nll;
+  int* correct;
+};
+
+// dot product of two rows of NC 16-byte chunks, chunk order rotated by `rot`, rotation-invariant combination (see above)
+template <int NC>
+__device__ __forceinline__ float rot_dot(const float* __restrict__ uv, const float* __restrict__ yv, int rot) {
+  float q[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int ch = (j + rot) & (NC - 1);
+    const float4 y4 = *reinterpret_cast<const float4*>(yv + ch * 4);
+    const float4 u4 = *reinterpret_cast<const float4*>(uv + ch * 4);
+    q[j] = fmaf(u4.w, y4.w, fmaf(u4.z, y4.z, fmaf(u4.y, y4.y, u4.x * y4.x)));
+  }
+  // pairs (j, j + NC/2), then (j, j + NC/4), ...: each level is mapped onto itself by a cyclic shift of the indices
+#pragma unroll
+  for (int h = NC / 2; h >= 1; h >>= 1)
+#pragma unroll
+    for (int j = 0; j < h; ++j) q[j] = q[j] + q[j + h];
+  return q[0];
+}
+
+template <int KR>
+struct NceShape {
+  static constexpr int SPS = 8 / KR;                          // samples per stage
+  static constexpr int ROWB = KR * NCE_ZD;                    // floats per (sample, n) row block
+  static constexpr int NEG_F = NCE_N * ROWB;                  // floats of negatives per sample
+  static constexpr int STAGE_F = SPS * (NEG_F + ROWB + NCE_CD);   // [SPS][N][KR][zd] | [SPS][KR][zd] | [SPS][cd]
+  static constexpr int TEAM_US = 8 * NCE_ZD;                  // u of the 8 (sample, k) rows of the current stage
+  static size_t smem(int nst) { return (size_t)NCE_TEAMS * ((size_t)nst * STAGE_F + TEAM_US) * 4 + NCE_TEAMS * 2 * (size_t)nst * 8 + 16; }
+};
+
+template <int KR>
+__global__ void __launch_bounds__(NCE_THREADS, 1)
+infonce_stream_fwd_kernel(NceParams p) {
+  using S = NceShape<KR>;
+  extern __shared__ __align__(16) uint8_t nce_smem[];
+  const int team = threadIdx.x / NCE_TT, tt = threadIdx.x % NCE_TT, lane = threadIdx.x & 31;
+  float* stg = reinterpret_cast<float*>(nce_smem) + (size_t)team * ((size_t)p.nst * S::STAGE_F + S::TEAM_US);   // [nst][STAGE_F]
+  float* us = stg + (size_t)p.nst * S::STAGE_F;                                                                 // [8][zd]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(nce_smem) +
+                                               (size_t)NCE_TEAMS * ((size_t)p.nst * S::STAGE_F + S::TEAM_US)) + team * 2 * p.nst;
+  const uint32_t bar0 = nce_smem_u32(bars);            // full[nst], empty[nst] of this team
+
+  if (tt == 0) {
+    for (int i = 0; i < 2 * p.nst; ++i) nce_mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // sample groups are dealt round-robin to (CTA, team) streams
+  const int ngroups = (p.B + S::SPS - 1) / S::SPS;
+  const int stream = blockIdx.x * NCE_TEAMS + team, nstreams = gridDim.x * NCE_TEAMS;
+  const int my = stream < ngroups ? (ngroups - stream + nstreams - 1) / nstreams : 0;
+  // thread 0 of the team issues the three copies of its group i into ring slot i % nst
+  auto issue = [&](int i) {
+    if (i >= my) return;
+    const int slot = i % p.nst;
+    if (i >= p.nst) nce_mbar_wait(bar0 + 8u * (p.nst + slot), ((i / p.nst) & 1) ^ 1);
+    const int b0 = (stream + i * nstreams) * S::SPS;
+    const uint32_t ns = (uint32_t)min(S::SPS, p.B - b0);
+    const uint32_t fb = bar0 + 8u * slot;
+    float* d = stg + (size_t)slot * S::STAGE_F;
+    nce_mbar_expect_tx(fb, ns * (uint32_t)(S::NEG_F + S::ROWB + NCE_CD) * 4u);
+    nce_bulk_g2s(nce_smem_u32(d), p.yneg + (size_t)b0 * S::NEG_F, ns * (uint32_t)S::NEG_F * 4u, fb);
+    nce_bulk_g2s(nce_smem_u32(d + S::SPS * S::NEG_F), p.ypos + (size_t)b0 * S::ROWB, ns * (uint32_t)S::ROWB * 4u, fb);
+    nce_bulk_g2s(nce_smem_u32(d + S::SPS * (S::NEG_F + S::ROWB)), p.c + (size_t)b0 * NCE_CD, ns * (uint32_t)NCE_CD * 4u, fb);
+  };
+  // roles: U phase - rows ru and ru + 4 of the 8 (sample, k) rows, column zu (the W rows of the thread never change: they
+  // live in registers for the whole kernel);  S phase - row rs, score nn (15 = positive)
+  const int ru = tt >> 5, zu = tt & 31;
+  const int rs = tt >> 4, nn = tt & 15;
+  constexpr bool TWO_K = KR == 8;                      // rows ru and ru + 4 belong to different k only when KR = 8
+  float w0[NCE_CD], w1[TWO_K ? NCE_CD : 1];
+  {
+    // W (zd, cd, KR) is read once per CTA with coalesced loads - issued BEFORE the first bulk copies, so they do not
+    // queue behind megabytes of streaming traffic - into the ring slots the prologue does not fill (slot nst - 1 of
+    // every team holds a quarter of it); then each thread picks its strided rows out of shared memory
+    constexpr int W_F = NCE_ZD * NCE_CD * KR, QUART = W_F / NCE_TEAMS, PER = W_F / 4 / NCE_THREADS;
+    static_assert(QUART + 8 + 24 <= S::STAGE_F && NCE_ZD == 8 * NCE_TEAMS, "W quarter (8 z rows) must fit in a ring slot");
+    static_assert(W_F % (4 * NCE_THREADS) == 0, "W must split evenly over the CTA");
+    float4 wv[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(p.W) + threadIdx.x + j * NCE_THREADS);
+    __syncthreads();                                   // barriers initialised
+    if (tt == 0)
+      for (int i = 0; i < p.nst - 1; ++i) issue(i);
+    // quarter q of W (z rows 8q .. 8q+7, each cd * KR floats + one word of padding so that the 32 lanes of a warp - 32
+    // different z - read 32 different banks; quarters are skewed by 8 words for the same reason) sits in slot nst - 1 of team q
+    constexpr int ROW = NCE_CD * KR, ROWP = ROW + 1;
+    float* base = reinterpret_cast<float*>(nce_smem) + (size_t)(p.nst - 1) * S::STAGE_F;
+    const int team_f = p.nst * S::STAGE_F + S::TEAM_US;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = (threadIdx.x + j * NCE_THREADS) * 4;              // 4 consecutive floats of one z row
+      const int z = i / ROW, w = i % ROW;
+      float* d = base + (z >> 3) * team_f + (z >> 3) * 8 + (z & 7) * ROWP + w;
+      d[0] = wv[j].x; d[1] = wv[j].y; d[2] = wv[j].z; d[3] = wv[j].w;
+    }
+    __syncthreads();
+    const float* wr = base + (zu >> 3) * team_f + (zu >> 3) * 8 + (zu & 7) * ROWP;    // bank of lane zu: zu + const
+#pragma unroll
+    for (int cc = 0; cc < NCE_CD; ++cc) {
+      w0[cc] = wr[cc * KR + (ru % KR)];
+      if (TWO_K) w1[cc] = wr[cc * KR + ((ru + 4) % KR)];
+    }
+    __syncthreads();                                   // slots nst - 1 may now be overwritten by the first in-loop issue
+  }
+  const int bar_id = 1 + team;
+
+  for (int it = 0; it < my; ++it) {
+    if (tt == 0) issue(it + p.nst - 1);
+    const int slot = it % p.nst;
+    const int b0 = (stream + it * nstreams) * S::SPS;
+    const int ns = min(S::SPS, p.B - b0);
+    nce_mbar_wait(bar0 + 8u * slot, (it / p.nst) & 1);
+    const float* st = stg + (size_t)slot * S::STAGE_F;
+    const float* st_pos = st + S::SPS * S::NEG_F;
+    const float* st_c = st_pos + S::SPS * S::ROWB;
+    // ---- U phase: u[row][z] = sum_c W[z][c][k] c[sample][c]   (four partial sums per output: short dependency chains)
+    {
+      const int r0 = ru, r1 = ru + 4;
+      const float* c0 = st_c + (r0 / KR) * NCE_CD;
+      const float* c1 = st_c + (r1 / KR) * NCE_CD;
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int cc = 0; cc < NCE_CD; cc += 4) {
+        const float4 ca = *reinterpret_cast<const float4*>(c0 + cc);
+        const float4 cb = *reinterpret_cast<const float4*>(c1 + cc);
+        const float* wb = TWO_K ? w1 : w0;
+        a0[0] = fmaf(ca.x, w0[cc], a0[0]); a0[1] = fmaf(ca.y, w0[cc + 1], a0[1]);
+        a0[2] = fmaf(ca.z, w0[cc + 2], a0[2]); a0[3] = fmaf(ca.w, w0[cc + 3], a0[3]);
+        a1[0] = fmaf(cb.x, wb[cc], a1[0]); a1[1] = fmaf(cb.y, wb[cc + 1], a1[1]);
+        a1[2] = fmaf(cb.z, wb[cc + 2], a1[2]); a1[3] = fmaf(cb.w, wb[cc + 3], a1[3]);
+      }
+      const float u0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), u1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      us[r0 * NCE_ZD + zu] = u0;
+      us[r1 * NCE_ZD + zu] = u1;
+      float* ug = p.u + (size_t)b0 * S::ROWB;
+      if (r0 / KR < ns) ug[r0 * NCE_ZD + zu] = u0;
+      if (r1 / KR < ns) ug[r1 * NCE_ZD + zu] = u1;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NCE_TT) : "memory");
+    // ---- S phase: one score per thread, then log-sum-exp / accuracy among the 16 lanes of a (sample, k) row
+    {
+      const int sI = rs / KR, k = rs % KR;
+      const bool act = sI < ns;
+      const float* yv = (nn < NCE_N) ? st + sI * S::NEG_F + nn * S::ROWB + k * NCE_ZD : st_pos + sI * S::ROWB + k * NCE_ZD;
+      const float a = act ? rot_dot<NCE_NC>(us + rs * NCE_ZD, yv, lane) : 0.f;
+      const size_t bk = (size_t)(b0 + sI) * KR + k;
+      if (act) {
+        if (nn < NCE_N) p.neg[bk * NCE_N + nn] = a;
+        else p.pos[bk] = a;
+      }
+      const float pv = __shfl_sync(0xffffffffu, a, (lane & 16) + NCE_N);
+      float nm = (nn < NCE_N) ? a : -INFINITY;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) nm = fmaxf(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+      const float mx = fmaxf(nm, pv);
+      float se = expf(a - mx);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      if (act && nn == NCE_N) {
+        const float l = mx + logf(se);
+        p.lse[bk] = l;
+        p.nll[bk] = l - pv;                         // -(pos - lse): summed by the caller (vqcpc_reduce_sum)
+        p.correct[bk] = (pv > nm) ? 1 : 0;
+      }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NCE_TT) : "memory");
+    if (tt == 0) nce_mbar_arrive(bar0 + 8u * (p.nst + slot));       // every read of the stage is done
+  }
+}
+
+template <int KR>
+int nce_stream_launch(NceParams p, cudaStream_t st) {
+  using S = NceShape<KR>;
+  int nst = 0;
+  for (int t = 4; t >= 2; --t)
+    if (S::smem(t) <= 220 * 1024) { nst = t; break; }
+  if (!nst) return 1;
+  p.nst = nst;
+  const size_t sm = S::smem(nst);
+  VQ_CUDA_CALL(cudaFuncSetAttribute(infonce_stream_fwd_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int ngroups = (p.B + S::SPS - 1) / S::SPS;
+  const int grid = std::max(1, std::min((ngroups + NCE_TEAMS - 1) / NCE_TEAMS, vq_sm_count()));
+  infonce_stream_fwd_kernel<KR><<<grid, NCE_THREADS, sm, st>>>(p);
+  VQ_CUDA_LAUNCH_CHECK("infonce_stream_fwd_kernel");
+  return VQ_OK;
+}
+
 }  // namespace
+
+/* tuning / test hook: 0 = automatic, 1 = warp-per-(b, k) kernel, 2 = streaming (cp.async.bulk ring) kernel */
+VQ_API int vqcpc_infonce_set_algo(int algo) {
+  g_nce_algo = (algo == 1 || algo == 2) ? algo : 0;
+  return VQ_OK;
+}
 
 VQ_API int vqcpc_infonce_fwd(const float* c, const float* W, const float* y_pos, const float* y_neg, int B, int N, int KR,
                              int zd, int cd, float* u, float* pos, float* neg, float* lse, float* nll, int* correct, void* stream) {
   VQ_CHECK_ARG(zd >= 1 && zd <= MAXZ, "infonce_fwd: z_dim must be in 1..%d (got %d)", MAXZ, zd);
   VQ_CHECK_ARG(KR >= 1 && KR <= 65535 && N >= 1, "infonce_fwd: bad KR=%d / N=%d", KR, N);
   if (B == 0) return VQ_OK;
+  cudaStream_t st = vq_stream(stream);
+  // streaming kernel: 16-byte granular rows, at least two ring stages in shared memory, enough samples to fill the GPU
+  const bool aligned = (((uintptr_t)c | (uintptr_t)y_pos | (uintptr_t)y_neg) & 15) == 0;
+  if (g_nce_algo != 1 && aligned && zd == NCE_ZD && cd == NCE_CD && N == NCE_N && (KR == 2 || KR == 4 || KR == 8) &&
+      (g_nce_algo == 2 || B >= 64)) {
+    NceParams p{c, W, y_pos, y_neg, B, 0, u, pos, neg, lse, nll, correct};
+    return KR == 8 ? nce_stream_launch<8>(p, st) : KR == 4 ? nce_stream_launch<4>(p, st) : nce_stream_launch<2>(p, st);
+  }
+  VQ_CHECK_ARG(g_nce_algo != 2, "infonce_fwd: the streaming kernel needs 16-byte aligned inputs, zd = cd = 32, N = 15 and KR in {2, 4, 8}");
   size_t smem = (size_t)zd * (cd + 1) * sizeof(float);
   VQ_CHECK_ARG(smem <= 48 * 1024, "infonce_fwd: W[:, :, k] tile (%zu B) exceeds 48 KB", smem);
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(B, 8), (int64_t)vq_sm_count() * 8 / KR + 1));
   dim3 grid(gx, KR);
-  cudaStream_t st = vq_stream(stream);
   int zpl = (zd + 31) / 32;
   if (zpl == 1) infonce_fwd_kernel<1><<<grid, 256, smem, st>>>(c, W, y_pos, y_neg, B, N, KR, zd, cd, u, pos, neg, lse, nll, correct);
   else if (zpl == 2) infonce_fwd_kernel<2><<<grid, 256, smem, st>>>(c, W, y_pos, y_neg, B, N, KR, zd, cd, u, pos, neg, lse, nll, correct);
