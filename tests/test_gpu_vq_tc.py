@@ -125,3 +125,41 @@ def test_vq_tc_data_init_codebook():
     r1, r2 = run_fused(z, E, T, 1), run_fused(z, E, T, 2)
     for k in ('idx', 'loss', 'y', 'counts'):
         assert torch.equal(r1[k], r2[k]), f'{k} differs'
+
+
+@pytest.mark.parametrize('D,n,Kc,squared', [(3, 100, 64, 1), (3, 5000, 512, 1), (4, 70001, 512, 1), (3, 9000, 300, 0), (3, 557056, 512, 1)])
+def test_vq_fused_bwd_matches_autograd(D, n, Kc, squared):
+    """Backward of the fused bottleneck (both kernels: per-warp reduction for small n, streaming + cluster reduction
+    from 4096 vectors) against torch autograd in fp64 on  y = T[idx],  loss = (1 + beta) ||q - z||^2  (or the norm form):
+    dz = J[idx]^T dy + g_loss dloss/dz,  dT[idx] += dy,  dE[idx] += g_loss dloss/dq."""
+    from VQCPCB import _native, ops
+    g = torch.Generator(device='cuda')
+    g.manual_seed(n + D)
+    zd, beta = 32, 0.25
+    E = torch.randn(Kc, D, device='cuda', generator=g) * 2
+    z = torch.randn(n, D, device='cuda', generator=g) * 2
+    J = torch.randn(Kc, zd, D, device='cuda', generator=g)
+    dy = torch.randn(n, zd, device='cuda', generator=g)
+    gl = torch.rand(n, device='cuda', generator=g) / n
+    idx = ((z[:, None, :] - E[None]) ** 2).sum(-1).argmin(1) if n * Kc < 5e7 else torch.randint(0, Kc, (n,), device='cuda', generator=g)
+    dz = torch.full((n, D), float('nan'), device='cuda')
+    dT = torch.zeros(Kc, zd, device='cuda')
+    dE = torch.zeros(Kc, D, device='cuda')
+    _native.call('vqcpc_vq_fused_bwd', ops._p(z), n, D, ops._p(E), ops._p(J), Kc, zd, ops._p(idx), beta, squared, ops._p(dy), ops._p(gl),
+                 ops._p(dz), ops._p(dT), ops._p(dE), ops._stream())
+    torch.cuda.synchronize()
+    # fp64 reference
+    zr, Er = z.double().requires_grad_(True), E.double().requires_grad_(True)
+    q = Er[idx]
+    if squared:
+        loss = ((q.detach() - zr) ** 2).sum(-1) * beta + ((q - zr.detach()) ** 2).sum(-1)
+    else:
+        loss = ((q.detach() - zr) + 1e-5).norm(dim=-1) * beta + ((q - zr.detach()) + 1e-5).norm(dim=-1)
+    (loss * gl.double()).sum().backward()
+    dz_ref = zr.grad + torch.einsum('njd,nj->nd', J.double()[idx], dy.double())
+    dT_ref = torch.zeros(Kc, zd, dtype=torch.float64, device='cuda').index_add_(0, idx, dy.double())
+    def rel(a, b):
+        return float((a.double() - b).norm() / b.norm().clamp_min(1e-30))
+    assert rel(dz, dz_ref) < 1e-5, rel(dz, dz_ref)
+    assert rel(dT, dT_ref) < 1e-5, rel(dT, dT_ref)
+    assert rel(dE, Er.grad) < 1e-4, rel(dE, Er.grad)

@@ -294,6 +294,208 @@ vq_fused_bwd_kernel(const float* __restrict__ x, const float* __restrict__ E, co
       if (dEs[i] != 0.f) atomicAdd(dE + i, dEs[i]);
 }
 
+// Streaming backward of the fused path for zd == 32 (the upscaler width every configuration uses).
+// dT[idx_v] += dy[v] is a scatter-add of 128-byte rows into a Kc x 32 table.  Floating-point atomics on shared memory are
+// CAS loops on sm_100 (ATOMS.CAST.SPIN: measured 325 us for 557 056 rows), vector reductions straight to the L2-resident
+// table saturate the L2 atomic units (170 us), and warp-cooperative segmented sums drown in shuffles (157 us).  So the
+// scatter is turned into a gather: every CTA takes a contiguous block of at most VB_SUB vectors, counting-sorts their
+// indices by code in shared memory (native 32-bit ATOMS.ADD), then
+// four threads (adjacent lanes) per task - a code's rows, at most 16 at a time, prefetched four deep - walk those rows, each with a quarter of the features and of the code's
+// 32 x DS upscaler Jacobian in registers:
+//   dT_smem[k] += sum rows;   dx[v] = J[k]^T dy[v] + g_loss[v] dloss/dx (two shuffle steps inside the quad);
+//   dE_smem[k] += sum g_loss dloss/dq.
+// Table words have one writer, except for the codes popular enough to be split over several tasks (shared CAS atomics).  The per-CTA tables are summed across the
+// 4 CTAs of a thread-block cluster through distributed shared memory before the global atomics (4x fewer red.global).
+constexpr int VB_SUB = 4096;          // vectors per sorted sub-block (local indices fit in 16 bits)
+constexpr int VB_THREADS = 512;
+constexpr int VB_ROWS = 16;           // rows per task: popular codes are split so that no quad walks a long segment alone
+constexpr int VB_TS = 33;             // padded row of the shared dT table (conflict-free per-thread row writes)
+
+template <int DS>
+__global__ void __launch_bounds__(VB_THREADS, 1)
+vq_fused_bwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ E, const float* __restrict__ J, int Kc,
+                           int64_t n, const int64_t* __restrict__ idx, float beta, int squared, const float* __restrict__ dy,
+                           const float* __restrict__ g_loss, float* __restrict__ dx, float* __restrict__ dT,
+                           float* __restrict__ dE) {
+  constexpr int ZD = 32;
+  extern __shared__ __align__(16) float sm[];
+  float* dTs = sm;                                 // [Kc][33]
+  float* dEs = dTs + Kc * VB_TS;                   // [Kc][DS]
+  int* hist = reinterpret_cast<int*>(dEs + Kc * DS);      // [Kc + 1] counts, then exclusive offsets
+  int* cursor = hist + Kc + 1;                            // [Kc]
+  int* toff = cursor + Kc;                                // [Kc + 1] first task of each code
+  int* task = toff + Kc + 1;                              // [Kc + VB_SUB / VB_ROWS] (code | chunk << 16)
+  unsigned short* perm = reinterpret_cast<unsigned short*>(task + Kc + VB_SUB / VB_ROWS);     // [VB_SUB] local vector index, sorted by code
+  const int tsz = Kc * (VB_TS + DS);
+  for (int i = threadIdx.x; i < tsz; i += VB_THREADS) sm[i] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // contiguous range of this CTA, walked in sub-blocks
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo_v = min(n, per * blockIdx.x), hi_v = min(n, lo_v + per);
+  for (int64_t base = lo_v; base < hi_v; base += VB_SUB) {
+    const int cnt = (int)min((int64_t)VB_SUB, hi_v - base);
+    __syncthreads();                               // previous sub-block fully consumed (perm / hist reuse)
+    for (int i = threadIdx.x; i <= Kc; i += VB_THREADS) hist[i] = 0;
+    __syncthreads();
+    constexpr int PER_T = VB_SUB / VB_THREADS;
+    int kreg[PER_T];
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int i = threadIdx.x + j * VB_THREADS;
+      int k = i < cnt ? (int)idx[base + i] : 0;
+      kreg[j] = k < 0 ? 0 : (k >= Kc ? Kc - 1 : k);
+    }
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j)
+      if (threadIdx.x + j * VB_THREADS < cnt) atomicAdd(&hist[kreg[j]], 1);
+    __syncthreads();
+    if (warp == 0) {                               // exclusive scans: rows -> hist (offsets), cursor; tasks -> toff
+      int carry = 0, tcarry = 0;
+      for (int k0 = 0; k0 < Kc; k0 += 32) {
+        const int c = (k0 + lane < Kc) ? hist[k0 + lane] : 0;
+        const int nt = (c + VB_ROWS - 1) / VB_ROWS;
+        int incl = c, tincl = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          const int tt = __shfl_up_sync(0xffffffffu, tincl, o);
+          if (lane >= o) { incl += t; tincl += tt; }
+        }
+        if (k0 + lane < Kc) {
+          hist[k0 + lane] = carry + incl - c;
+          cursor[k0 + lane] = carry + incl - c;
+          toff[k0 + lane] = tcarry + tincl - nt;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        tcarry += __shfl_sync(0xffffffffu, tincl, 31);
+      }
+      if (lane == 0) { hist[Kc] = carry; toff[Kc] = tcarry; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int i = threadIdx.x + j * VB_THREADS;
+      if (i < cnt) perm[atomicAdd(&cursor[kreg[j]], 1)] = (unsigned short)i;
+    }
+    for (int k = threadIdx.x; k < Kc; k += VB_THREADS)
+      for (int t = toff[k], c = 0; t < toff[k + 1]; ++t, ++c) task[t] = k | (c << 16);
+    __syncthreads();
+    // ---- four threads per code (adjacent lanes; a quarter of the features and of the Jacobian each -> one 128-byte line
+    // per row and quad), rows prefetched four deep.  Lane q < DS of the quad also owns dimension q of x / dx / dE.
+    const int ntask = toff[Kc];
+    for (int t = threadIdx.x >> 2; t < ntask; t += VB_THREADS / 4) {
+      const int k = task[t] & 0xFFFF, qd = threadIdx.x & 3;
+      const int s0 = hist[k] + (task[t] >> 16) * VB_ROWS, s1 = min(hist[k + 1], s0 + VB_ROWS);
+      const bool shared_code = hist[k + 1] - hist[k] > VB_ROWS;        // several tasks add into the same table row
+      const unsigned qmask = 0xFu << (lane & ~3);
+      const float ek = (qd < DS) ? __ldg(E + (size_t)k * DS + qd) : 0.f;
+      float jq[8 * DS];                             // J[k][8 qd .. 8 qd + 7][0 .. DS-1]
+      {
+        const float4* jr = reinterpret_cast<const float4*>(J + ((size_t)k * ZD + qd * 8) * DS);     // 8 * DS floats, 16-byte aligned
+#pragma unroll
+        for (int q = 0; q < 2 * DS; ++q) {
+          const float4 t4 = __ldg(jr + q);
+          jq[4 * q] = t4.x; jq[4 * q + 1] = t4.y; jq[4 * q + 2] = t4.z; jq[4 * q + 3] = t4.w;
+        }
+      }
+      float acc[8], de = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      constexpr int PF = 4;
+      float4 buf[PF][2];
+      float bx[PF], bg[PF];
+      int bv[PF];
+      auto fetch = [&](int slot, int i) {
+        if (i < s1) {
+          const int pl = perm[i];
+          const int64_t v = base + pl;
+          const float4* r = reinterpret_cast<const float4*>(dy + v * ZD) + qd * 2;
+          buf[slot][0] = r[0];
+          buf[slot][1] = r[1];
+          bv[slot] = pl;
+          if (qd < DS) {
+            bx[slot] = x[v * DS + qd];
+            bg[slot] = g_loss ? g_loss[v] : 0.f;
+          }
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < PF; ++u) fetch(u, s0 + u);
+      for (int i0 = s0; i0 < s1; i0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          if (i0 + u < s1) {
+            const float4 a = buf[u][0], c = buf[u][1];
+            const float row[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+            float gx[DS];
+#pragma unroll
+            for (int d = 0; d < DS; ++d) gx[d] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[j] += row[j];
+#pragma unroll
+              for (int d = 0; d < DS; ++d) gx[d] = fmaf(row[j], jq[j * DS + d], gx[d]);
+            }
+            const float df = (qd < DS) ? ek - bx[u] : 0.f;
+            float s2 = (qd < DS) ? (df + 1e-5f) * (df + 1e-5f) : 0.f;
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+#pragma unroll
+              for (int d = 0; d < DS; ++d) gx[d] += __shfl_xor_sync(qmask, gx[d], o);
+              if (!squared) s2 += __shfl_xor_sync(qmask, s2, o);
+            }
+            if (qd < DS) {
+              float gsel = gx[0];
+#pragma unroll
+              for (int d = 1; d < DS; ++d) gsel = (qd == d) ? gx[d] : gsel;
+              const float dq = squared ? 2.f * df : (df + 1e-5f) / sqrtf(s2);
+              dx[(base + bv[u]) * DS + qd] = gsel - bg[u] * beta * dq;
+              de += bg[u] * dq;
+            }
+          }
+          fetch(u, i0 + PF + u);
+        }
+      }
+      if (shared_code) {                            // rare: (CAS) atomics only where a popular code was split
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&dTs[k * VB_TS + qd * 8 + j], acc[j]);
+        if (qd < DS) atomicAdd(&dEs[k * DS + qd], de);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dTs[k * VB_TS + qd * 8 + j] += acc[j];
+        if (qd < DS) dEs[k * DS + qd] += de;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- cluster reduction of the tables, then one global atomic per word and cluster
+  unsigned crank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const int nwords = Kc * (ZD + DS);                // logical words: dT (Kc x 32) then dE (Kc x DS)
+  const int slice = (nwords + (int)csize - 1) / (int)csize;
+  const int lo = (int)crank * slice, hi = min(nwords, lo + slice);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
+  for (int i = lo + threadIdx.x; i < hi; i += VB_THREADS) {
+    const int off = i < Kc * ZD ? (i / ZD) * VB_TS + (i % ZD) : Kc * VB_TS + (i - Kc * ZD);
+    float acc = 0.f;
+    for (unsigned r = 0; r < csize; ++r) {
+      uint32_t ra;
+      float t;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sbase + 4u * (uint32_t)off), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t) : "r"(ra));
+      acc += t;
+    }
+    if (acc != 0.f) {
+      if (i < Kc * ZD) atomicAdd(dT + i, acc);
+      else if (dE) atomicAdd(dE + (i - Kc * ZD), acc);
+    }
+  }
+  // nobody leaves while a peer may still read its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 int fill_books(Books& b, int ncb, const float* const* e, float* const* g) {
   if (ncb < 1 || ncb > MAX_CB) return -1;
   for (int i = 0; i < ncb; ++i) {
@@ -433,6 +635,36 @@ VQ_API int vqcpc_vq_fused_bwd(const float* x, int64_t n, int D, const float* E, 
   size_t smem = (size_t)Kc * (zd + D) * sizeof(float);
   VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_bwd: gradient tables (%zu B) do not fit in shared memory", smem);
   cudaStream_t st = vq_stream(stream);
+  if (zd == 32 && (D == 3 || D == 4) && n >= 4096 && (((uintptr_t)dy | (uintptr_t)J) & 15) == 0) {
+    // streaming kernel: one CTA per SM, clusters of 4 (148 = 4 x 37 on B200; any SM count that is a multiple of 4)
+    int sms = vq_sm_count();
+    int grid = (int)std::min<int64_t>(vq_cdiv(n, 512), sms) / 4 * 4;
+    VQ_CHECK_ARG(Kc <= 65535, "vq_fused_bwd: Kc=%d too large", Kc);
+    if (grid >= 4) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(VB_THREADS);
+      const size_t smem2 = (size_t)Kc * (VB_TS + D) * 4 + (size_t)(4 * Kc + 2 + VB_SUB / VB_ROWS) * 4 + VB_SUB * 2 + 16;
+      cfg.dynamicSmemBytes = smem2;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 4;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (D == 3) {
+        VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_bwd_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, vq_fused_bwd_stream_kernel<3>, x, E, J, Kc, n, idx, beta, squared, dy, g_loss, d_x, d_T, d_E));
+      } else {
+        VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_bwd_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, vq_fused_bwd_stream_kernel<4>, x, E, J, Kc, n, idx, beta, squared, dy, g_loss, d_x, d_T, d_E));
+      }
+      VQ_CUDA_LAUNCH_CHECK("vq_fused_bwd_stream_kernel");
+      return VQ_OK;
+    }
+  }
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 256), (int64_t)vq_sm_count() * (smem > 100 * 1024 ? 1 : 2)));
 #define VQ_BL(DSV)                                                                                                          \
   do {                                                                                                                      \
