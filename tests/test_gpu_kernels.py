@@ -168,7 +168,7 @@ def test_quantizer_full_size_properties():
     assert float(loss2.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('algo,B', [(1, 19), (2, 19), (2, 2), (2, 301), (0, 128)])
+@pytest.mark.parametrize('algo,B', [(1, 19), (2, 19), (2, 2), (2, 301), (0, 128), (2, 4096)])
 def test_infonce_fwd_bwd_vs_oracle(algo, B):
     """Both forward kernels (warp per (b, k); streaming cp.async.bulk ring) against the fp64 oracle, odd batch sizes
     (ragged last stage), and an exact tie between a negative and the positive."""
@@ -185,9 +185,9 @@ def test_infonce_fwd_bwd_vs_oracle(algo, B):
     ops._native.call('vqcpc_infonce_set_algo', algo)
     try:
         total, pos, neg, correct = ops.InfoNCEFn.apply(c, W, yp, yn)
+        (total / B).backward()                                           # the same switch selects the backward kernel
     finally:
         ops._native.call('vqcpc_infonce_set_algo', 0)
-    (total / B).backward()
     cd_, Wd, ypd, ynd = (t.detach().double().cpu().requires_grad_(True) for t in (c, W, yp, yn))
     rpos = O.fks(cd_, ypd, Wd)
     rneg = torch.stack([O.fks(cd_, ynd[:, n], Wd) for n in range(N)], 2)
@@ -214,14 +214,19 @@ def test_infonce_streaming_matches_warp_kernel(N, KR, zd, cd, B):
     W = torch.randn(zd, cd, KR, device='cuda', generator=g) * 0.25
     yp = torch.randn(B, KR, zd, device='cuda', generator=g)
     yn = torch.randn(B, N, KR, zd, device='cuda', generator=g)
-    outs = []
+    outs, grads = [], []
     for algo in (1, 2):
+        leaves = [t.clone().requires_grad_(True) for t in (c, W, yp, yn)]
         ops._native.call('vqcpc_infonce_set_algo', algo)
         try:
-            total, pos, neg, correct = ops.InfoNCEFn.apply(c, W, yp, yn)
+            total, pos, neg, correct = ops.InfoNCEFn.apply(*leaves)
+            (total / B).backward()
         finally:
             ops._native.call('vqcpc_infonce_set_algo', 0)
-        outs.append((total, pos, neg, correct))
+        outs.append((total.detach(), pos, neg, correct))
+        grads.append([t.grad for t in leaves])
+    for ga, gb in zip(*grads):
+        assert rel_err(ga, gb) < 2e-5, rel_err(ga, gb)
     (t1, p1, n1, c1), (t2, p2, n2, c2) = outs
     assert rel_err(p1, p2) < 1e-6 and rel_err(n1, n2) < 1e-6
     assert abs(t1.item() - t2.item()) < 1e-5 * abs(t1.item())

@@ -407,6 +407,327 @@ infonce_stream_fwd_kernel(NceParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Streaming backward (same shapes, same team / ring structure as the forward).  Nothing saved by the forward is read:
+// u, the scores and the log-sum-exp are recomputed from the staged rows with the forward's own code (a few hundred
+// flops per sample against 32 KB of traffic), so the kernel streams y once and writes dy once:
+//   U, S phases as in the forward; coefficient of score n of row (sample, k):  pi_n * scale for a negative,
+//                                  -(1 - pi_pos) * scale for the positive                     (pi = softmax of the row)
+//   G phase (thread per (row, z)): du[z] = sum_n coef_n y[n][z];  dy[n][z] = coef_n u[z]  (coalesced 128-byte stores);
+//                                  dW[k][z][:] += du[z] c[sample][:]  in REGISTERS for the whole kernel
+//   C phase (thread per (c, pair of rows)): dc[sample][c] = sum_{k,z} W[z][c][k] du[k][z], W resident in shared memory
+// End: the per-thread dW blocks are summed over the 4 teams in shared memory, over the 4 CTAs of a cluster through
+// distributed shared memory, and only then added to global memory (the L2 atomic units sustain ~16 red/clk: per-thread
+// reds would cost more than the whole stream).
+struct NceBwdParams {
+  const float *c, *W, *ypos, *yneg, *g_dev;
+  float scale;
+  int B, nst;
+  float *dc, *dW, *dypos, *dyneg;
+};
+
+template <int KR>
+struct NceBwdShape {
+  using F = NceShape<KR>;
+  static constexpr int WS = NCE_CD + 4;                       // padded W row: Wsm[k][z][c]
+  static constexpr int W_F = KR * NCE_ZD * WS;
+  static constexpr int TEAM_X = 8 * NCE_ZD + 8 * NCE_GRP + 8 * NCE_ZD + 4 * NCE_CD;   // us, cf, dus, dcp
+  static constexpr int RED_F = KR * NCE_CD * NCE_ZD;          // one team's dW block [k][c][z]
+  __host__ __device__ static constexpr int team_f(int nst) { return (nst * F::STAGE_F > RED_F ? nst * F::STAGE_F : RED_F) + TEAM_X; }
+  static size_t smem(int nst) { return ((size_t)W_F + (size_t)NCE_TEAMS * team_f(nst)) * 4 + NCE_TEAMS * 2 * (size_t)nst * 8 + 16; }
+};
+
+template <int KR>
+__global__ void __launch_bounds__(NCE_THREADS, 1)
+infonce_stream_bwd_kernel(NceBwdParams p) {
+  using S = NceShape<KR>;
+  using SB = NceBwdShape<KR>;
+  extern __shared__ __align__(16) uint8_t nce_smem[];
+  const int team = threadIdx.x / NCE_TT, tt = threadIdx.x % NCE_TT, lane = threadIdx.x & 31;
+  const int team_f = SB::team_f(p.nst);
+  float* Wsm = reinterpret_cast<float*>(nce_smem);                          // [KR][zd][cd + 4]
+  float* tbase = Wsm + SB::W_F + (size_t)team * team_f;
+  float* stg = tbase;                                                        // [nst][STAGE_F] (later: dW block of the team)
+  float* us = tbase + team_f - SB::TEAM_X;                                   // [8][zd]
+  float* cf = us + 8 * NCE_ZD;                                               // [8][16] coefficients
+  float* dus = cf + 8 * NCE_GRP;                                             // [8][zd]
+  float* dcp = dus + 8 * NCE_ZD;                                             // [4 parts][cd]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wsm + SB::W_F + (size_t)NCE_TEAMS * team_f) + team * 2 * p.nst;
+  const uint32_t bar0 = nce_smem_u32(bars);            // full[nst], empty[nst] of this team
+
+  if (tt == 0) {
+    for (int i = 0; i < 2 * p.nst; ++i) nce_mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int ngroups = (p.B + S::SPS - 1) / S::SPS;
+  const int stream = blockIdx.x * NCE_TEAMS + team, nstreams = gridDim.x * NCE_TEAMS;
+  const int my = stream < ngroups ? (ngroups - stream + nstreams - 1) / nstreams : 0;
+  auto issue = [&](int i) {
+    if (i >= my) return;
+    const int slot = i % p.nst;
+    if (i >= p.nst) nce_mbar_wait(bar0 + 8u * (p.nst + slot), ((i / p.nst) & 1) ^ 1);
+    const int b0 = (stream + i * nstreams) * S::SPS;
+    const uint32_t ns = (uint32_t)min(S::SPS, p.B - b0);
+    const uint32_t fb = bar0 + 8u * slot;
+    float* d = stg + (size_t)slot * S::STAGE_F;
+    nce_mbar_expect_tx(fb, ns * (uint32_t)(S::NEG_F + S::ROWB + NCE_CD) * 4u);
+    nce_bulk_g2s(nce_smem_u32(d), p.yneg + (size_t)b0 * S::NEG_F, ns * (uint32_t)S::NEG_F * 4u, fb);
+    nce_bulk_g2s(nce_smem_u32(d + S::SPS * S::NEG_F), p.ypos + (size_t)b0 * S::ROWB, ns * (uint32_t)S::ROWB * 4u, fb);
+    nce_bulk_g2s(nce_smem_u32(d + S::SPS * (S::NEG_F + S::ROWB)), p.c + (size_t)b0 * NCE_CD, ns * (uint32_t)NCE_CD * 4u, fb);
+  };
+  {
+    // W (zd, cd, KR) -> Wsm[k][z][c]: coalesced float4 loads issued before the first bulk copies, scattered stores
+    constexpr int W_N = NCE_ZD * NCE_CD * KR, PER = W_N / 4 / NCE_THREADS;
+    static_assert(W_N % (4 * NCE_THREADS) == 0 && (KR % 4 == 0 || KR == 2), "W must split evenly over the CTA");
+    float4 wv[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(p.W) + threadIdx.x + j * NCE_THREADS);
+    __syncthreads();                                   // barriers initialised
+    if (tt == 0)
+      for (int i = 0; i < p.nst - 1; ++i) issue(i);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const float v4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (threadIdx.x + j * NCE_THREADS) * 4 + e;
+        const int k = i % KR, cc = (i / KR) % NCE_CD, z = i / (KR * NCE_CD);
+        Wsm[(k * NCE_ZD + z) * SB::WS + cc] = v4[e];
+      }
+    }
+    __syncthreads();
+  }
+  const float scale = p.scale * (p.g_dev ? __ldg(p.g_dev) : 1.f);
+  const int ru = tt >> 5, zu = tt & 31;                // G phase: rows ru, ru + 4, column zu
+  const int rs = tt >> 4, nn = tt & 15;                // S phase: row rs, score nn (15 = positive)
+  constexpr bool TWO_K = KR == 8;                      // rows ru and ru + 4 belong to different k only when KR = 8
+  const int k0 = ru % KR, k1 = (ru + 4) % KR;
+  float dw0[NCE_CD], dw1[TWO_K ? NCE_CD : 1];
+#pragma unroll
+  for (int cc = 0; cc < NCE_CD; ++cc) { dw0[cc] = 0.f; if (TWO_K) dw1[cc] = 0.f; }
+  const int bar_id = 1 + team;
+#define TEAM_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NCE_TT) : "memory")
+
+  for (int it = 0; it < my; ++it) {
+    if (tt == 0) issue(it + p.nst - 1);
+    const int slot = it % p.nst;
+    const int b0 = (stream + it * nstreams) * S::SPS;
+    const int ns = min(S::SPS, p.B - b0);
+    nce_mbar_wait(bar0 + 8u * slot, (it / p.nst) & 1);
+    const float* st = stg + (size_t)slot * S::STAGE_F;
+    const float* st_pos = st + S::SPS * S::NEG_F;
+    const float* st_c = st_pos + S::SPS * S::ROWB;
+    const int r0 = ru, r1 = ru + 4;
+    const int s0 = r0 / KR, s1 = r1 / KR;
+    // ---- U phase (same arithmetic as the forward)
+    float u0, u1;
+    {
+      const float* w0 = Wsm + (k0 * NCE_ZD + zu) * SB::WS;
+      const float* w1 = Wsm + (k1 * NCE_ZD + zu) * SB::WS;
+      const float* c0 = st_c + s0 * NCE_CD;
+      const float* c1 = st_c + s1 * NCE_CD;
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int cc = 0; cc < NCE_CD; cc += 4) {
+        const float4 wa = *reinterpret_cast<const float4*>(w0 + cc);
+        const float4 wb = TWO_K ? *reinterpret_cast<const float4*>(w1 + cc) : wa;
+        const float4 ca = *reinterpret_cast<const float4*>(c0 + cc);
+        const float4 cb = *reinterpret_cast<const float4*>(c1 + cc);
+        a0[0] = fmaf(ca.x, wa.x, a0[0]); a0[1] = fmaf(ca.y, wa.y, a0[1]); a0[2] = fmaf(ca.z, wa.z, a0[2]); a0[3] = fmaf(ca.w, wa.w, a0[3]);
+        a1[0] = fmaf(cb.x, wb.x, a1[0]); a1[1] = fmaf(cb.y, wb.y, a1[1]); a1[2] = fmaf(cb.z, wb.z, a1[2]); a1[3] = fmaf(cb.w, wb.w, a1[3]);
+      }
+      u0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+      u1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      us[r0 * NCE_ZD + zu] = u0;
+      us[r1 * NCE_ZD + zu] = u1;
+    }
+    TEAM_SYNC();
+    // ---- S phase: score, softmax of the row, coefficient
+    {
+      const int sI = rs / KR, k = rs % KR;
+      const bool act = sI < ns;
+      const float* yv = (nn < NCE_N) ? st + sI * S::NEG_F + nn * S::ROWB + k * NCE_ZD : st_pos + sI * S::ROWB + k * NCE_ZD;
+      const float a = act ? rot_dot<NCE_NC>(us + rs * NCE_ZD, yv, lane) : 0.f;
+      const float pv = __shfl_sync(0xffffffffu, a, (lane & 16) + NCE_N);
+      float nm = (nn < NCE_N) ? a : -INFINITY;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) nm = fmaxf(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+      const float mx = fmaxf(nm, pv);
+      const float ex = expf(a - mx);
+      float se = ex;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float pi = expf(a - (mx + logf(se)));      // exp(score - lse), as the warp-per-(b, k) kernel computes it
+      cf[rs * NCE_GRP + nn] = act ? ((nn < NCE_N) ? pi * scale : -(1.f - pi) * scale) : 0.f;
+    }
+    TEAM_SYNC();
+    // ---- G phase
+    {
+      const float* cf0 = cf + r0 * NCE_GRP;
+      const float* cf1 = cf + r1 * NCE_GRP;
+      float du0 = 0.f, du1 = 0.f;
+      float* dn0 = p.dyneg + ((size_t)(b0 + s0) * NCE_N * KR + k0) * NCE_ZD + zu;     // + n * KR * zd
+      float* dn1 = p.dyneg + ((size_t)(b0 + s1) * NCE_N * KR + k1) * NCE_ZD + zu;
+      const float* y0 = st + s0 * S::NEG_F + k0 * NCE_ZD + zu;                         // + n * ROWB
+      const float* y1 = st + s1 * S::NEG_F + k1 * NCE_ZD + zu;
+      const bool a0 = s0 < ns, a1 = s1 < ns;
+#pragma unroll
+      for (int n4 = 0; n4 < NCE_GRP; n4 += 4) {
+        const float4 q0 = *reinterpret_cast<const float4*>(cf0 + n4);
+        const float4 q1 = *reinterpret_cast<const float4*>(cf1 + n4);
+        const float e0[4] = {q0.x, q0.y, q0.z, q0.w}, e1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = n4 + e;
+          if (n < NCE_N) {
+            du0 = fmaf(e0[e], y0[n * S::ROWB], du0);
+            du1 = fmaf(e1[e], y1[n * S::ROWB], du1);
+            if (a0) dn0[(size_t)n * KR * NCE_ZD] = e0[e] * u0;
+            if (a1) dn1[(size_t)n * KR * NCE_ZD] = e1[e] * u1;
+          } else {
+            du0 = fmaf(e0[e], st_pos[s0 * S::ROWB + k0 * NCE_ZD + zu], du0);
+            du1 = fmaf(e1[e], st_pos[s1 * S::ROWB + k1 * NCE_ZD + zu], du1);
+            if (a0) p.dypos[((size_t)(b0 + s0) * KR + k0) * NCE_ZD + zu] = e0[e] * u0;
+            if (a1) p.dypos[((size_t)(b0 + s1) * KR + k1) * NCE_ZD + zu] = e1[e] * u1;
+          }
+        }
+      }
+      if (!a0) du0 = 0.f;                              // rows past the batch end hold stale shared memory
+      if (!a1) du1 = 0.f;
+      dus[r0 * NCE_ZD + zu] = du0;
+      dus[r1 * NCE_ZD + zu] = du1;
+      const float* c0 = st_c + s0 * NCE_CD;
+      const float* c1 = st_c + s1 * NCE_CD;
+#pragma unroll
+      for (int cc = 0; cc < NCE_CD; cc += 4) {
+        const float4 ca = *reinterpret_cast<const float4*>(c0 + cc);
+        const float4 cb = *reinterpret_cast<const float4*>(c1 + cc);
+        dw0[cc] = fmaf(du0, ca.x, dw0[cc]); dw0[cc + 1] = fmaf(du0, ca.y, dw0[cc + 1]);
+        dw0[cc + 2] = fmaf(du0, ca.z, dw0[cc + 2]); dw0[cc + 3] = fmaf(du0, ca.w, dw0[cc + 3]);
+        float* d1 = TWO_K ? dw1 : dw0;
+        d1[cc] = fmaf(du1, cb.x, d1[cc]); d1[cc + 1] = fmaf(du1, cb.y, d1[cc + 1]);
+        d1[cc + 2] = fmaf(du1, cb.z, d1[cc + 2]); d1[cc + 3] = fmaf(du1, cb.w, d1[cc + 3]);
+      }
+    }
+    TEAM_SYNC();
+    if (tt == 0) nce_mbar_arrive(bar0 + 8u * (p.nst + slot));       // every read of the stage is done
+    // ---- C phase: thread (c, part): rows 2 part, 2 part + 1
+    {
+      const int cc = tt & 31, part = tt >> 5;
+      float acc = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = 2 * part + rr;
+        const float* wk = Wsm + (size_t)((r % KR) * NCE_ZD) * SB::WS + cc;
+        const float* dr = dus + r * NCE_ZD;
+#pragma unroll
+        for (int z = 0; z < NCE_ZD; z += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dr + z);
+          acc = fmaf(wk[(z + 0) * SB::WS], d4.x, acc);
+          acc = fmaf(wk[(z + 1) * SB::WS], d4.y, acc);
+          acc = fmaf(wk[(z + 2) * SB::WS], d4.z, acc);
+          acc = fmaf(wk[(z + 3) * SB::WS], d4.w, acc);
+        }
+      }
+      dcp[part * NCE_CD + cc] = acc;
+    }
+    TEAM_SYNC();
+    if (tt < S::SPS * NCE_CD) {
+      const int sI = tt >> 5, cc = tt & 31;
+      if (sI < ns) {
+        constexpr int PPS = KR / 2;                    // parts per sample
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < PPS; ++q) acc += dcp[(sI * PPS + q) * NCE_CD + cc];
+        p.dc[(size_t)(b0 + sI) * NCE_CD + cc] += acc;   // this team owns the sample: plain read-modify-write
+      }
+    }
+    // (dcp / cf / us / dus are next written after barriers of the next iteration that these threads also pass)
+  }
+
+  // ---- dW: registers -> team block [k][c][z] (reusing the ring), sum over teams, over the cluster, one red per word
+  __syncthreads();                                     // every stage of every team consumed, no bulk copy in flight
+  {
+    float* blk = tbase;                                // RED_F floats
+    constexpr int ROUNDS = KR >= 4 ? 1 : 4 / KR;       // warps of a team that share k take turns
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      if (ru / KR == rd || KR >= 4) {
+#pragma unroll
+        for (int cc = 0; cc < NCE_CD; ++cc) {
+          float* d = blk + (k0 * NCE_CD + cc) * NCE_ZD + zu;
+          if (rd == 0) *d = dw0[cc]; else *d += dw0[cc];
+          if (TWO_K) blk[(k1 * NCE_CD + cc) * NCE_ZD + zu] = dw1[cc];
+        }
+      }
+      TEAM_SYNC();
+    }
+  }
+  __syncthreads();
+  float* red0 = Wsm + SB::W_F;                         // team 0's block becomes the CTA's block
+  for (int i = threadIdx.x; i < SB::RED_F; i += NCE_THREADS) {
+    float a = red0[i];
+#pragma unroll
+    for (int t = 1; t < NCE_TEAMS; ++t) a += red0[(size_t)t * team_f + i];
+    red0[i] = a;
+  }
+  unsigned crank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
+    const int slice = (SB::RED_F + (int)csize - 1) / (int)csize;
+    const int lo = (int)crank * slice, hi = min((int)SB::RED_F, lo + slice);
+    const uint32_t sbase = nce_smem_u32(red0);
+    for (int i = lo + threadIdx.x; i < hi; i += NCE_THREADS) {
+      float acc = 0.f;
+      for (unsigned r = 0; r < csize; ++r) {
+        uint32_t ra;
+        float t;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sbase + 4u * (uint32_t)i), "r"(r));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t) : "r"(ra));
+        acc += t;
+      }
+      const int z = i % NCE_ZD, cc = (i / NCE_ZD) % NCE_CD, k = i / (NCE_ZD * NCE_CD);
+      if (acc != 0.f) atomicAdd(p.dW + ((size_t)z * NCE_CD + cc) * KR + k, acc);
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#undef TEAM_SYNC
+}
+
+template <int KR>
+int nce_stream_bwd_launch(NceBwdParams p, cudaStream_t st) {
+  using S = NceShape<KR>;
+  using SB = NceBwdShape<KR>;
+  int nst = 0;
+  for (int t = 3; t >= 2; --t)
+    if (SB::smem(t) <= 220 * 1024) { nst = t; break; }
+  if (!nst) return 1;
+  p.nst = nst;
+  const size_t sm = SB::smem(nst);
+  VQ_CUDA_CALL(cudaFuncSetAttribute(infonce_stream_bwd_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int ngroups = (p.B + S::SPS - 1) / S::SPS;
+  int grid = std::min((ngroups + NCE_TEAMS - 1) / NCE_TEAMS, vq_sm_count());
+  const int cl = grid >= 4 ? 4 : 1;
+  grid = std::max(1, grid / cl * cl);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NCE_THREADS);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, infonce_stream_bwd_kernel<KR>, p));
+  VQ_CUDA_LAUNCH_CHECK("infonce_stream_bwd_kernel");
+  return VQ_OK;
+}
+
 template <int KR>
 int nce_stream_launch(NceParams p, cudaStream_t st) {
   using S = NceShape<KR>;
@@ -466,6 +787,16 @@ VQ_API int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos,
                              int cd, float* d_c, float* d_W, float* d_ypos, float* d_yneg, void* stream) {
   VQ_CHECK_ARG(zd >= 1 && zd <= MAXZ, "infonce_bwd: z_dim must be in 1..%d (got %d)", MAXZ, zd);
   if (B == 0) return VQ_OK;
+  {
+    const bool aligned = (((uintptr_t)c | (uintptr_t)y_pos | (uintptr_t)y_neg | (uintptr_t)W) & 15) == 0;
+    if (g_nce_algo != 1 && aligned && zd == NCE_ZD && cd == NCE_CD && N == NCE_N && (KR == 2 || KR == 4 || KR == 8) &&
+        (g_nce_algo == 2 || B >= 64)) {
+      NceBwdParams p{c, W, y_pos, y_neg, g_dev, scale, B, 0, d_c, d_W, d_ypos, d_yneg};
+      cudaStream_t st2 = vq_stream(stream);
+      return KR == 8 ? nce_stream_bwd_launch<8>(p, st2) : KR == 4 ? nce_stream_bwd_launch<4>(p, st2) : nce_stream_bwd_launch<2>(p, st2);
+    }
+    VQ_CHECK_ARG(g_nce_algo != 2, "infonce_bwd: the streaming kernel needs 16-byte aligned inputs, zd = cd = 32, N = 15 and KR in {2, 4, 8}");
+  }
   size_t smem = (size_t)2 * zd * (cd + 1) * sizeof(float);
   VQ_CHECK_ARG(smem <= 48 * 1024, "infonce_bwd: W tile (%zu B) exceeds 48 KB", smem);
   int gx = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(B, 8), (int64_t)vq_sm_count() * 4 / KR + 1));
