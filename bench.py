@@ -253,7 +253,7 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
     alu_us = search_instr / (148 * 128 * 1.9e9) * 1e6
     return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
                 kernels='vq_tc_fwd_kernel (tcgen05 score + exact verify) + infonce_stream_fwd_kernel (forward); '
-                        'infonce_bwd_kernel + vq_fused_bwd_kernel (backward)',
+                        'infonce_stream_bwd_kernel + vq_fused_bwd_stream_kernel (backward)',
                 timing='CUDA-graph replay of the launch sequence over %d rotating buffer sets (> L2); us_fwd_eager = same '
                        'launches issued one by one from Python' % nsets, us_fwd_eager=us_f_launch,
                 batch=B, vectors=P, algorithmic_bytes_fwd=bytes_f, us_fwd=us_f, achieved=bytes_f / us_f / 1e3,

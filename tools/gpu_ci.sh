@@ -14,10 +14,11 @@ run() {  # name file kexpr
   echo "$name rc=$rc $(tail -n 1 gpurun_out/$name.log)" | tee -a gpurun_out/summary.txt
   [ $rc -ne 0 ] && status=1
 }
-groups=${*:-kernels gemm_fp32 gemm_tc enc_fp32 enc_tc}
+groups=${*:-kernels vq_tc gemm_fp32 gemm_tc enc_fp32 enc_tc}
 for g in $groups; do
   case $g in
     kernels)   run kernels tests/test_gpu_kernels.py "test" ;;
+    vq_tc)     run vq_tc tests/test_gpu_vq_tc.py "test" ;;
     gemm_fp32) run gemm_fp32 tests/test_gpu_gemm.py "fp32" ;;
     gemm_tc)   run gemm_tc tests/test_gpu_gemm.py "not fp32" ;;
     gemm_tc0)  VQCPC_GEMM_TILE=0 run gemm_tc0 tests/test_gpu_gemm.py "not fp32" ;;
