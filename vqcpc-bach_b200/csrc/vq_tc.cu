@@ -12,20 +12,24 @@
 //        A row (vector):  [ z1 | z1 | z2 | 1  1  1  | 0 ]        z = z1 + z2 + O(2^-18 |z|)
 //        B row (code)  :  [ e1 | e2 | e1 | n1 n2 n3 | 0 ]        n = -|e|^2/2 = n1 + n2 + n3
 //     products of bf16 are exact in the fp32 accumulator, so |S^ - S| <= ~2^-16 (sum_d |z_d| max_k|e_kd| + max_k |n_k|).
-//   epilogue (8 warps, thread == vector, TMEM lane == vector): tcgen05.ld the 256 scores of a chunk, 3-input max down to
-//     32 group maxima (8 codes each) and the chunk maximum; every group whose maximum is within `margin` of the running
-//     maximum is re-evaluated EXACTLY (dist_fixed: the reference's fp32 direct form, torch summation order, strict '<'
-//     in ascending code order = lowest index on ties).  margin = 2 * (score error bound) + (rounding bound of the
-//     reference distance), so the reference argmin is always among the candidates -> indices are bit-identical to the
-//     direct kernel (tests/test_gpu_kernels.py::test_vq_tc_*), at ~1.3 instead of 11 instructions per pair.
-//   Rows whose bound is not finite (inf / NaN / overflow) fall back to scanning every code exactly.
+//   epilogue (thread == vector, TMEM lane == vector): tcgen05.ld the 512 scores of a tile, 3-input max (FMNMX3) down to
+//     64 group maxima (8 codes each) and the row maximum; every group whose maximum is within `margin` of the row
+//     maximum is re-evaluated EXACTLY (dist_fixed: the reference's fp32 direct form, torch summation order, a tournament
+//     that keeps the lower index on ties).  margin = 2 * (score error bound) + (rounding bound of the reference
+//     distance), so the reference argmin is always among the candidates -> indices are bit-identical to the direct
+//     kernel (tests/test_gpu_vq_tc.py), at ~1.5 instead of 11 instructions per (vector, code) pair; on average 1.03
+//     groups per vector are re-evaluated.  Rows whose bound is not finite (inf / NaN / overflow) scan every code.
 //
-// CTA = 384 threads (3 warpgroups), persistent over 128-vector tiles, one CTA per SM (all 512 TMEM columns = two
-// 256-column accumulator stages).  Warp 0: builds the A tile in shared memory (SWIZZLE_32B K-major rows written with generic stores +
-// fence.proxy.async), one lane issues the MMAs and commits to mbarriers.  Warps 1-4 (group 0) consume accumulator stage 0
-// (code chunks 0, 2, ..), warps 5-8 (group 1) stage 1 (chunks 1, 3, ..); warp w and w+4 own the same 32 vectors (same TMEM
-// lane quadrant) and merge their (distance, index) through shared memory + a 64-thread named barrier, alternating which
-// of the two writes the outputs (idx, loss, histogram, y = T[idx] as coalesced 128-byte rows).
+// CTA = 384 threads = 3 warpgroups, persistent over 128-vector tiles, one CTA per SM (all 512 TMEM columns = two
+// 256-column accumulator stages = one tile of 512 codes; larger codebooks cycle through the stages in chunk pairs).
+//   warpgroup 0 (setmaxnreg 56): warp 0 streams the z tiles into a 4-slot shared-memory ring with cp.async.bulk (one
+//     1-D TMA copy per tile, mbarrier completion); all four warps build the SWIZZLE_32B K-major A tile from it (generic
+//     stores + fence.proxy.async); one lane issues the MMAs and commits to mbarriers.
+//   warpgroups 1, 2 (setmaxnreg 224): the two epilogue sets alternate tiles, so the score reduction of tile i+1 (TMEM
+//     reads) overlaps the verification and output of tile i (shared memory + HBM writes: idx, loss, histogram,
+//     y = T[idx] from the shared-memory copy of the table as coalesced 128-byte rows).
+// Shared memory: operands, the exact fp32 codebook (padded against bank conflicts), the (Kc, zd) table (one bulk copy,
+// overlapped with the set-up), the z ring, the usage histogram.
 #include "gemm_tc_common.cuh"
 #include "vq_dist.cuh"
 #include "vq_tc.h"
@@ -34,7 +38,9 @@ using namespace vqtc;
 
 namespace {
 
-constexpr int VT_THREADS = 384;           // warpgroup 0: producer / MMA; warpgroups 1, 2: the two epilogue sets
+constexpr int VT_SETS = 2;                 // epilogue warpgroups; tile i of a CTA belongs to set i % VT_SETS (three sets
+                                          // were measured slower: ptxas caps a 512-thread kernel at 128 registers -> spills)
+constexpr int VT_THREADS = 128 * (1 + VT_SETS);    // warpgroup 0: producer / MMA; warpgroups 1..: the epilogue sets
 constexpr int NABUF = 3;                  // A-operand buffers (see the reuse argument in the producer loop)
 constexpr int CH = 256;               // codes per MMA / accumulator stage (two stages = all 512 TMEM columns)
 constexpr int GROUP = 8;              // codes per group maximum
@@ -135,8 +141,8 @@ __device__ __forceinline__ void write_krow(uint8_t* base, uint32_t slab_bytes, i
 __device__ __forceinline__ int cb_off(int k, int cs) { return k * cs + ((k >> 3) << 2); }
 
 // mbarrier indices
-enum { BAR_FULL = 0 /*[set][stage]*/, BAR_EMPTY = 4 /*[set][stage]*/, BAR_ZFULL = 8 /*[ZS]*/, BAR_ZEMPTY = 8 + ZS /*[ZS]*/,
-       BAR_T = 8 + 2 * ZS, BAR_COUNT = 9 + 2 * ZS };
+enum { BAR_FULL = 0 /*[set][stage]*/, BAR_EMPTY = 2 * VT_SETS /*[set][stage]*/, BAR_ZFULL = 4 * VT_SETS /*[ZS]*/,
+       BAR_ZEMPTY = 4 * VT_SETS + ZS /*[ZS]*/, BAR_T = 4 * VT_SETS + 2 * ZS, BAR_COUNT = 4 * VT_SETS + 2 * ZS + 1 };
 
 // DBG: instantiation with the score dump and the clock / counter instrumentation (tests, tools/vq_bench.py --prof)
 template <int DS, bool DBG>
@@ -170,7 +176,7 @@ vq_tc_fwd_kernel(VtParams p) {
 
   // ------------------------------------------------------------------ set-up (all threads)
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2 * VT_SETS; ++i) {
       mbar_init(BAR(BAR_FULL + i), 1);
       mbar_init(BAR(BAR_EMPTY + i), 4);
     }
@@ -266,7 +272,7 @@ vq_tc_fwd_kernel(VtParams p) {
     const int rl = warp * 32 + lane;               // the operand row this thread builds
     for (int it = 0; it < my_tiles; ++it) {
       if (warp == 0) fetch(it + ZS - 1);
-      const int slot = it % ZS, set = it & 1;
+      const int slot = it % ZS, set = it % VT_SETS;
       mbar_wait(BAR(BAR_ZFULL + slot), (it / ZS) & 1);
       const int64_t row = (blockIdx.x + (int64_t)it * gridDim.x) * 128 + rl;
       // A(it) goes to buffer it % 3, last read by the MMAs of tile it-3: warp 0 saw them retire (accumulator waits) while
@@ -306,7 +312,8 @@ vq_tc_fwd_kernel(VtParams p) {
     }
   } else {
     // ============================== score reduction + exact verification ==============================
-    // set 0 (warpgroup 1) owns the even tiles of this CTA, set 1 (warpgroup 2) the odd ones; thread == vector
+    // set s (warpgroup 1 + s) owns the tiles s, s + VT_SETS, ... of this CTA; thread == vector.
+    // Register budget: 128 x 56 (producers) + 256 x 224 (two sets) <= 64 K
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int set = (warp >> 2) - 1;
     const int q = warp & 3;                        // TMEM lane quadrant
@@ -322,7 +329,7 @@ vq_tc_fwd_kernel(VtParams p) {
     int n_exact = 0, n_full = 0;
     bool t_ready = !p.t_smem;
     const int rl = q * 32 + lane;
-    for (int it = set; it < my_tiles; it += 2) {
+    for (int it = set; it < my_tiles; it += VT_SETS) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t row = tile * 128 + rl;
       const bool ok = row < p.n;
