@@ -251,7 +251,11 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
     bytes_b = B * ((KR + NNEG * KR) * 8 * zd + vec * (4 * zd + 8 + 8 * D + 4))
     search_instr = P * Kc * 11.0                                   # exact direct-form search: 11 fp32 instr per (vector, code)
     alu_us = search_instr / (148 * 128 * 1.9e9) * 1e6
-    return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_path_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))           # dram bytes per launch from the committed ncu --set full captures
+    return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], traffic=traffic, peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
                 kernels='vq_tc_fwd_kernel (tcgen05 score + exact verify) + infonce_stream_fwd_kernel (forward); '
                         'infonce_stream_bwd_kernel + vq_fused_bwd_stream_kernel (backward)',
                 timing='CUDA-graph replay of the launch sequence over %d rotating buffer sets (> L2); us_fwd_eager = same '
