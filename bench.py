@@ -32,6 +32,7 @@ for p in (ROOT, os.path.join(ROOT, 'vqcpc-bach_b200')):
 
 import torch  # noqa: E402
 
+_OUT = sys.stdout
 METRIC = 'vqcpc_encoder_training_samples_per_sec'
 UNIT = 'samples/s'
 KL = KR = 8
@@ -115,7 +116,7 @@ def run_reference(args):
                 data='synthetic', config=dict(workload=workload_name(args.batch), note='CPU port of the reference step; B=16 sample'),
                 cpu_baseline=dict(value=val, unit=UNIT, **info),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU leg
@@ -380,7 +381,16 @@ def run_ours(args):
         line['cpu_baseline'] = dict(value=cpu_val, unit=UNIT, **cpu_info)
     if qi is not None:
         line['roofline_quantizer_infonce'] = qi
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+def _quiet_stdout():
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr; returns a file object on the real
+    stdout for the one JSON line the driver parses."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, 'w')
 
 
 def main():
@@ -395,13 +405,15 @@ def main():
     ap.add_argument('--no-path-roofline', action='store_true')
     ap.add_argument('--path-only', action='store_true', help='only the stand-alone quantizer + InfoNCE path measurement')
     args = ap.parse_args()
+    global _OUT
+    _OUT = _quiet_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit('bench.py --impl ours needs a CUDA device (no CPU fallback on the product path)')
         if args.path_only:
-            print(json.dumps(bench_quantizer_infonce(args.batch)))
+            print(json.dumps(bench_quantizer_infonce(args.batch)), file=_OUT, flush=True)
             return
         run_ours(args)
 
