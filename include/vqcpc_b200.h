@@ -73,6 +73,9 @@ int vqcpc_colsum_split(const void* x_hi, const void* x_lo, int ld, float* out, i
 /* nn.SELU of the MLP upscaler (upscalers/mlp_upscaler.py:21-26). */
 int vqcpc_selu_fwd(const float* x, float* out, int64_t n, void* stream);
 int vqcpc_selu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* nn.Dropout (mlp_upscaler.py:23) with an explicit keep mask (one byte per element, drawn by the caller so that
+ * forward, backward and tests share it): out = keep ? x * scale : 0, scale = 1 / (1 - p). */
+int vqcpc_mask_scale(const float* x, const unsigned char* keep, float scale, float* out, int64_t n, void* stream);
 /* out[0] = scale * sum(x[0..n)) in a fixed order (deterministic). */
 int vqcpc_reduce_sum(const float* x, int64_t n, float* out, float scale, void* stream);
 

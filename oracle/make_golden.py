@@ -32,17 +32,22 @@ def import_reference():
     from VQCPCB.vqcpc_encoder_trainer import VQCPCEncoderTrainer
     from VQCPCB.data_processor.bach_cpc_data_processor import BachCPCDataProcessor
     from VQCPCB.downscalers.relative_transformer_downscaler import RelativeTransformerDownscaler
+    from VQCPCB.downscalers.lstm_downscaler import LstmDownscaler
     from VQCPCB.quantizer.vector_quantizer import ProductVectorQuantizer
     from VQCPCB.upscalers.mlp_upscaler import MlpUpscaler
     return dict(Encoder=Encoder, Trainer=VQCPCEncoderTrainer, DP=BachCPCDataProcessor,
-                Down=RelativeTransformerDownscaler, VQ=ProductVectorQuantizer, Up=MlpUpscaler)
+                Down=RelativeTransformerDownscaler, LstmDown=LstmDownscaler, VQ=ProductVectorQuantizer, Up=MlpUpscaler)
 
 
 def build_reference(R, cfg, prm, model_dir='/tmp/vqcpc_golden'):
     dp = R['DP'](cfg.embedding_size, cfg.ticks_per_block, cfg.num_voices, list(cfg.vocab),
                  cfg.num_voices * cfg.ticks_per_block)
-    down = R['Down'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
-                     cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
+    if cfg.get('downscaler', 'transformer') == 'lstm':
+        down = R['LstmDown'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
+                             cfg.lstm_hidden, cfg.lstm_layers, 0.0, cfg.lstm_bidirectional)
+    else:
+        down = R['Down'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
+                         cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
     vq = R['VQ'](cfg.codebook_size, cfg.codebook_dim, cfg.commitment_cost, cfg.num_codebooks, False, False,
                  cfg.squared_l2_norm)
     up = R['Up'](cfg.codebook_dim, cfg.z_dim, cfg.up_hidden, 0.0) if cfg.upscaler else None
@@ -98,6 +103,11 @@ CASES = {
                               squared_l2_norm=False), B=4),
     # bidirectional c-net (encoder_random_16C.py style) incl. the reference's backward-negative indexing (quirk Q1)
     'cfg1_bidir': dict(cfg=dict(codebook_size=16, KL=2, KR=2, bidirectional=True), B=6),
+    # GRU block downscaler (encoder_random_config.py shape: bidirectional 2-layer GRU pair, K = 32, 6 + 6 blocks)
+    'lstm': dict(cfg=dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=512, lstm_layers=2,
+                          lstm_bidirectional=True, codebook_size=32, codebook_scale=0.05, KL=6, KR=6), B=4),
+    'lstm_uni': dict(cfg=dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=96, lstm_layers=1,
+                              lstm_bidirectional=False, codebook_size=16, codebook_scale=0.05, KL=2, KR=2), B=3),
 }
 
 
@@ -187,8 +197,12 @@ def quantizer_cases(R):
 def main():
     R = import_reference()
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
-    torch.save(quantizer_cases(R), os.path.join(ROOT, 'tests', 'golden', 'quantizer.pt'))
+    only = sys.argv[1:]                      # optional: regenerate just the named cases
+    if not only:
+        torch.save(quantizer_cases(R), os.path.join(ROOT, 'tests', 'golden', 'quantizer.pt'))
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         gold = run_case(R, name, spec)
         path = os.path.join(ROOT, 'tests', 'golden', f'{name}.pt')
         torch.save(gold, path)

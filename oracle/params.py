@@ -35,35 +35,49 @@ def param_shapes(cfg):
     out = {}
     for v in range(V):
         out[f'data_processor.embeddings.{v}.weight'] = ((cfg.vocab[v] + 1, E), ('normal', 1.0))
-    out['downscaler.target_channel_embeddings'] = ((1, 1, V, pe), ('normal', 1.0))
-    out['downscaler.events_positioning_embeddings'] = ((1, 1, S // V, pe), ('normal', 1.0))
-    out['downscaler.input_linear.weight'] = ((d - 2 * pe, E), ('uniform', 1 / math.sqrt(E)))
-    out['downscaler.input_linear.bias'] = ((d - 2 * pe,), ('uniform', 1 / math.sqrt(E)))
-    out['downscaler.output_linear.weight'] = ((cfg.codebook_dim, d), ('uniform', 1 / math.sqrt(d)))
-    out['downscaler.output_linear.bias'] = ((cfg.codebook_dim,), ('uniform', 1 / math.sqrt(d)))
-    L = S
-    for s, (factor, nl) in enumerate(zip(cfg.downscale_factors, cfg.list_of_num_layers)):
-        for l in range(nl):
-            p = f'downscaler.transformers.{s}.layers.{l}.'
-            out[p + 'self_attn.in_proj_weight'] = ((3 * d, d), ('uniform', math.sqrt(6.0 / (4 * d))))
-            out[p + 'self_attn.in_proj_bias'] = ((3 * d,), ('uniform', 0.02))
-            out[p + 'self_attn.out_proj.weight'] = ((d, d), ('uniform', 1 / math.sqrt(d)))
-            out[p + 'self_attn.out_proj.bias'] = ((d,), ('uniform', 0.02))
-            out[p + 'self_attn.attn_bias.e1'] = ((H * L, hd), ('normal', 1.0))
-            out[p + 'self_attn.attn_bias.e2'] = ((H * L, hd), ('normal', 1.0))
-            out[p + 'linear1.weight'] = ((F, d), ('uniform', 1 / math.sqrt(d)))
-            out[p + 'linear1.bias'] = ((F,), ('uniform', 1 / math.sqrt(d)))
-            out[p + 'linear2.weight'] = ((d, F), ('uniform', 1 / math.sqrt(F)))
-            out[p + 'linear2.bias'] = ((d,), ('uniform', 1 / math.sqrt(F)))
-            out[p + 'norm1.weight'] = ((d,), ('normal1', 0.1))
-            out[p + 'norm1.bias'] = ((d,), ('normal', 0.1))
-            out[p + 'norm2.weight'] = ((d,), ('normal1', 0.1))
-            out[p + 'norm2.bias'] = ((d,), ('normal', 0.1))
-        L //= factor
+    if cfg.get('downscaler', 'transformer') == 'lstm':
+        Hl = cfg.lstm_hidden
+        bl = 1 / math.sqrt(Hl)
+        for g in (['g_enc_fwd', 'g_enc_bwd'] if cfg.lstm_bidirectional else ['g_enc_fwd']):
+            for l in range(cfg.lstm_layers):
+                inp = E if l == 0 else Hl
+                out[f'downscaler.{g}.weight_ih_l{l}'] = ((3 * Hl, inp), ('uniform', bl))
+                out[f'downscaler.{g}.weight_hh_l{l}'] = ((3 * Hl, Hl), ('uniform', bl))
+                out[f'downscaler.{g}.bias_ih_l{l}'] = ((3 * Hl,), ('uniform', bl))
+                out[f'downscaler.{g}.bias_hh_l{l}'] = ((3 * Hl,), ('uniform', bl))
+        fin = Hl * (2 if cfg.lstm_bidirectional else 1)
+        out['downscaler.output_linear.weight'] = ((cfg.codebook_dim, fin), ('uniform', 1 / math.sqrt(fin)))
+        out['downscaler.output_linear.bias'] = ((cfg.codebook_dim,), ('uniform', 1 / math.sqrt(fin)))
+    else:
+        out['downscaler.target_channel_embeddings'] = ((1, 1, V, pe), ('normal', 1.0))
+        out['downscaler.events_positioning_embeddings'] = ((1, 1, S // V, pe), ('normal', 1.0))
+        out['downscaler.input_linear.weight'] = ((d - 2 * pe, E), ('uniform', 1 / math.sqrt(E)))
+        out['downscaler.input_linear.bias'] = ((d - 2 * pe,), ('uniform', 1 / math.sqrt(E)))
+        out['downscaler.output_linear.weight'] = ((cfg.codebook_dim, d), ('uniform', 1 / math.sqrt(d)))
+        out['downscaler.output_linear.bias'] = ((cfg.codebook_dim,), ('uniform', 1 / math.sqrt(d)))
+        L = S
+        for s, (factor, nl) in enumerate(zip(cfg.downscale_factors, cfg.list_of_num_layers)):
+            for l in range(nl):
+                p = f'downscaler.transformers.{s}.layers.{l}.'
+                out[p + 'self_attn.in_proj_weight'] = ((3 * d, d), ('uniform', math.sqrt(6.0 / (4 * d))))
+                out[p + 'self_attn.in_proj_bias'] = ((3 * d,), ('uniform', 0.02))
+                out[p + 'self_attn.out_proj.weight'] = ((d, d), ('uniform', 1 / math.sqrt(d)))
+                out[p + 'self_attn.out_proj.bias'] = ((d,), ('uniform', 0.02))
+                out[p + 'self_attn.attn_bias.e1'] = ((H * L, hd), ('normal', 1.0))
+                out[p + 'self_attn.attn_bias.e2'] = ((H * L, hd), ('normal', 1.0))
+                out[p + 'linear1.weight'] = ((F, d), ('uniform', 1 / math.sqrt(d)))
+                out[p + 'linear1.bias'] = ((F,), ('uniform', 1 / math.sqrt(d)))
+                out[p + 'linear2.weight'] = ((d, F), ('uniform', 1 / math.sqrt(F)))
+                out[p + 'linear2.bias'] = ((d,), ('uniform', 1 / math.sqrt(F)))
+                out[p + 'norm1.weight'] = ((d,), ('normal1', 0.1))
+                out[p + 'norm1.bias'] = ((d,), ('normal', 0.1))
+                out[p + 'norm2.weight'] = ((d,), ('normal1', 0.1))
+                out[p + 'norm2.bias'] = ((d,), ('normal', 0.1))
+            L //= factor
     if cfg.codebook_size is not None:
         for i in range(cfg.num_codebooks):
             out[f'quantizer.embeddings.{i}'] = ((cfg.codebook_size, cfg.codebook_dim // cfg.num_codebooks),
-                                                ('normal', 1.0))
+                                                ('normal', cfg.get('codebook_scale', 1.0)))
     zd = cfg.codebook_dim
     if cfg.upscaler:
         out['upscaler.mlp.0.weight'] = ((cfg.up_hidden, cfg.codebook_dim), ('uniform', 1 / math.sqrt(cfg.codebook_dim)))

@@ -42,6 +42,8 @@ def default_cfg(**over):
         upscaler=True, up_hidden=512, z_dim=32,
         c_hidden=512, c_layers=2, c_dim=32,
         KL=2, KR=2, N=15, quantization_weighting=0.5, bidirectional=False,
+        downscaler='transformer',                 # or 'lstm' (LstmDownscaler: per-block GRUs, downscale_factors = [16])
+        lstm_hidden=512, lstm_layers=2, lstm_bidirectional=True,
     )
     c.update(over)
     return c
@@ -205,7 +207,10 @@ def encoder_forward(x, prm, cfg, trace=None):
     emb = embed(tok, tables)                                  # (b, nb, 16, E)
     b, nb = emb.shape[:2]
     emb = emb.reshape(b, nb * S, -1)                          # utils.py:52-63 flatten
-    z = downscaler_forward(emb, prm, cfg, trace=trace)
+    if cfg.get('downscaler', 'transformer') == 'lstm':
+        z = lstm_downscaler_forward(emb, prm, cfg)
+    else:
+        z = downscaler_forward(emb, prm, cfg, trace=trace)
     if trace is not None:
         trace['z'] = z
     if cfg.codebook_size is None:                             # NoQuantization vector_quantizer.py:15-24
@@ -221,16 +226,14 @@ def encoder_forward(x, prm, cfg, trace=None):
 # --------------------------------------------------------------------------------------------
 # CPC heads
 # --------------------------------------------------------------------------------------------
-def gru_c(y_left, prm, cfg, pre='c_module.'):
-    """VQCPCB/vqcpc_helper.py:54-76: multi-layer GRU (batch_first, h0=0), last time step, Linear.
-    Gate order (r, z, n) and n = tanh(W_in x + b_in + r*(W_hn h + b_hn)) per torch.nn.GRU."""
-    x = y_left
+def gru_stack(x, prm, pre, layers, hidden):
+    """torch.nn.GRU(batch_first=True, h0 = 0) as explicit math: gate order (r, z, n),
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) n + z h.  x (B, T, in) -> (B, T, hidden)."""
     B, T, _ = x.shape
-    Hh = cfg.c_hidden
-    for l in range(cfg.c_layers):
-        wi, wh = prm[f'{pre}g_ar_fwd.weight_ih_l{l}'], prm[f'{pre}g_ar_fwd.weight_hh_l{l}']
-        bi, bh = prm[f'{pre}g_ar_fwd.bias_ih_l{l}'], prm[f'{pre}g_ar_fwd.bias_hh_l{l}']
-        h = x.new_zeros(B, Hh)
+    for l in range(layers):
+        wi, wh = prm[f'{pre}weight_ih_l{l}'], prm[f'{pre}weight_hh_l{l}']
+        bi, bh = prm[f'{pre}bias_ih_l{l}'], prm[f'{pre}bias_hh_l{l}']
+        h = x.new_zeros(B, hidden)
         outs = []
         for t in range(T):
             gi = F.linear(x[:, t], wi, bi)
@@ -243,7 +246,29 @@ def gru_c(y_left, prm, cfg, pre='c_module.'):
             h = (1 - zg) * n + zg * h
             outs.append(h)
         x = torch.stack(outs, 1)
+    return x
+
+
+def gru_c(y_left, prm, cfg, pre='c_module.'):
+    """VQCPCB/vqcpc_helper.py:54-76: multi-layer GRU (batch_first, h0=0), last time step, Linear."""
+    x = gru_stack(y_left, prm, pre + 'g_ar_fwd.', cfg.c_layers, cfg.c_hidden)
     return F.linear(x[:, -1], prm[pre + 'output_linear.weight'], prm[pre + 'output_linear.bias'])
+
+
+def lstm_downscaler_forward(emb, prm, cfg, pre='downscaler.'):
+    """VQCPCB/downscalers/lstm_downscaler.py:57-94: the sequence is cut into blocks of downscale_factors[0] tokens; each
+    block goes through a multi-layer GRU (and, if bidirectional, a SECOND GRU on the time-flipped block); the last
+    states are concatenated and projected by output_linear.  emb (b, nb * S, E) -> (b, nb, D)."""
+    b, ntok, E = emb.shape
+    S = cfg.num_voices * cfg.ticks_per_block
+    nb = ntok // S
+    x = emb.reshape(b * nb, S, E)
+    last = gru_stack(x, prm, pre + 'g_enc_fwd.', cfg.lstm_layers, cfg.lstm_hidden)[:, -1]
+    if cfg.lstm_bidirectional:
+        last_b = gru_stack(x.flip(dims=[1]), prm, pre + 'g_enc_bwd.', cfg.lstm_layers, cfg.lstm_hidden)[:, -1]
+        last = torch.cat([last, last_b], dim=-1)
+    z = F.linear(last, prm[pre + 'output_linear.weight'], prm[pre + 'output_linear.bias'])
+    return z.view(b, nb, -1)
 
 
 def fks(c, zs, W):

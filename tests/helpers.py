@@ -14,8 +14,13 @@ def build_product_encoder(cfg, model_dir='/tmp/vqcpc_b200_test'):
     from VQCPCB.encoder import Encoder
     S = cfg.num_voices * cfg.ticks_per_block
     dp = BachCPCDataProcessor(cfg.embedding_size, cfg.ticks_per_block, cfg.num_voices, list(cfg.vocab), S)
-    down = RelativeTransformerDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
-                                         cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
+    if cfg.get('downscaler', 'transformer') == 'lstm':
+        from VQCPCB.downscalers.lstm_downscaler import LstmDownscaler
+        down = LstmDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
+                              cfg.lstm_hidden, cfg.lstm_layers, 0.0, cfg.lstm_bidirectional)
+    else:
+        down = RelativeTransformerDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
+                                             cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
     vq = ProductVectorQuantizer(cfg.codebook_size, cfg.codebook_dim, cfg.commitment_cost, cfg.num_codebooks, False, False,
                                 cfg.squared_l2_norm)
     up = MlpUpscaler(cfg.codebook_dim, cfg.z_dim, cfg.up_hidden, 0.0) if cfg.upscaler else None

@@ -64,7 +64,9 @@ def test_state_dict_keys_match_reference_checkpoints():
     """Strict load of the oracle's parameter dict, whose keys were pinned by a strict load into the live reference."""
     from oracle import params as P, vqcpc_oracle as O
     from tests.helpers import build_product_trainer, load_params_into, product_named_params
-    for over in (dict(), dict(codebook_dim=32, upscaler=False, KL=2, KR=2)):
+    for over in (dict(), dict(codebook_dim=32, upscaler=False, KL=2, KR=2),
+                 dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=64, lstm_bidirectional=True),
+                 dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=64, lstm_layers=1, lstm_bidirectional=False)):
         cfg = O.default_cfg(**over)
         tr = build_product_trainer(cfg, device='cpu')
         prm = P.make_params(cfg, 0)
@@ -98,6 +100,27 @@ def test_getters_and_config_build_the_model():
     b = next(iter(train))
     assert b['x_left'].shape == (3, 32, 4) and b['negative_samples'].shape == (3, 15, 8, 4, 4)
     assert b['x_left'].dtype == torch.int64 and not b['x_left'].is_cuda
+
+
+def test_lstm_config_builds_the_reference_shaped_model():
+    """configs/encoder_vqcpc_lstm.py (the shape of the reference's encoder_random_config.py: GRU block downscaler,
+    dropout 0.1) goes through the same factories."""
+    import importlib.util
+    from VQCPCB.getters import get_dataloader_generator, get_encoder, get_encoder_trainer
+    from VQCPCB.downscalers.lstm_downscaler import LstmDownscaler
+    path = os.path.join(ROOT, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'encoder_vqcpc_lstm.py')
+    spec = importlib.util.spec_from_file_location('cfgmod_lstm', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    config = mod.config
+    gen = get_dataloader_generator(config['dataset'], config['training_method'], config['dataloader_generator_kwargs'])
+    enc = get_encoder('/tmp/x', gen, config)
+    tr = get_encoder_trainer('/tmp/x', gen, config['training_method'], enc, config['auxiliary_networks_kwargs'])
+    assert isinstance(enc.downscaler, LstmDownscaler) and enc.downscaler.g_enc_bwd is not None
+    assert enc.downscaler.downscale_factors == [16] and enc.upscaler.dropout == 0.1
+    keys = set(enc.downscaler.state_dict())
+    assert {'g_enc_fwd.weight_ih_l0', 'g_enc_bwd.weight_hh_l1', 'output_linear.weight'} <= keys
+    assert tuple(enc.downscaler.output_linear.weight.shape) == (3, 1024)
 
 
 def test_preprocess_layout_matches_oracle():

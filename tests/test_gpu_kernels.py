@@ -306,3 +306,32 @@ def test_attention_kept_rows_and_split_io(L, keep, P):
     dqkv, dsp = ops.attn_bwd(qkv, e1, e2, probs, go, b1, b2, P, L, H, hd, 0.125, keep=keep, want_split=True)
     assert rel_err(dqkv, ref_dqkv) < 1e-6 and rel_err(b1, a1) < 1e-5 and rel_err(b2, a2) < 1e-5
     assert torch.equal(dsp[0], dqkv.to(torch.bfloat16)) and rel_err(_unsplit(dsp), dqkv) < 1e-5
+
+
+def test_upscaler_dropout_replays_mask():
+    """MlpUpscaler in training mode with dropout (mlp_upscaler.py:21-35: Linear -> Dropout -> SELU -> Linear): with the
+    keep mask given, output and gradients match the same computation in fp64 torch; the default draw keeps ~1 - p."""
+    from VQCPCB import ops
+    from VQCPCB.upscalers.mlp_upscaler import MlpUpscaler
+    torch.manual_seed(11)
+    ops.set_gemm_mode('fp32')
+    up = MlpUpscaler(3, 32, 512, 0.3).cuda().train()
+    x = torch.randn(777, 3, device='cuda', requires_grad=True)
+    keep = ops.draw_keep_mask((777, 512), 0.3, 'cuda')
+    assert abs(keep.float().mean().item() - 0.7) < 0.01
+    y = up(x, keep_mask=keep)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xd = x.detach().double().requires_grad_(True)
+    w0, b0, w3, b3 = (t.detach().double().requires_grad_(True) for t in (up.mlp[0].weight, up.mlp[0].bias, up.mlp[3].weight, up.mlp[3].bias))
+    h = F.linear(xd, w0, b0) * keep.double() / 0.7
+    yr = F.linear(F.selu(h), w3, b3)
+    yr.backward(g.double())
+    assert rel_err(y, yr) < 1e-5
+    assert rel_err(x.grad, xd.grad) < 1e-5
+    for a, b in ((up.mlp[0].weight, w0), (up.mlp[0].bias, b0), (up.mlp[3].weight, w3), (up.mlp[3].bias, b3)):
+        assert rel_err(a.grad, b.grad) < 1e-5
+    # eval mode: dropout is the identity (and the fused table path takes over inside the Encoder)
+    up.eval()
+    assert rel_err(up(x.detach()), F.linear(F.selu(F.linear(x.detach().double(), w0.detach(), b0.detach())), w3.detach(), b3.detach())) < 1e-5
+    ops.set_gemm_mode('bf16x3')

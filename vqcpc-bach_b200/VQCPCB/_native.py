@@ -27,6 +27,7 @@ SIGNATURES = {
     'vqcpc_colsum_split': [_P, _P, _I, _P, _L, _I, _P],
     'vqcpc_selu_fwd': [_P, _P, _L, _P],
     'vqcpc_selu_bwd': [_P, _P, _P, _L, _P],
+    'vqcpc_mask_scale': [_P, _P, _F, _P, _L, _P],
     'vqcpc_split_bf16': [_P, _I, _P, _P, _I, _L, _I, _P],
     'vqcpc_reduce_sum': [_P, _L, _P, _F, _P],
     'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],

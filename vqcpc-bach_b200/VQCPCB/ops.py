@@ -385,6 +385,34 @@ class SeluFn(torch.autograd.Function):
         return dx
 
 
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout(p) in training mode with an explicit keep mask (uint8): y = x * keep / (1 - p)  (mlp_upscaler.py:23).
+    The mask is drawn by the caller (``draw_keep_mask``) so tests can replay the exact draw through a reference implementation."""
+
+    @staticmethod
+    def forward(ctx, x, keep, p):
+        x = _f32c(x)
+        out = torch.empty_like(x)
+        scale = 1.0 / (1.0 - p)
+        _native.call('vqcpc_mask_scale', _p(x), _p(keep), scale, _p(out), x.numel(), _stream())
+        ctx.save_for_backward(keep)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (keep,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(dy)
+        _native.call('vqcpc_mask_scale', _p(dy), _p(keep), ctx.scale, _p(dx), dy.numel(), _stream())
+        return dx, None, None
+
+
+def draw_keep_mask(shape, p, device):
+    """Bernoulli(1 - p) keep mask as uint8 from torch's CUDA generator (reproducible with torch.manual_seed)."""
+    return (torch.rand(shape, device=device) >= p).to(torch.uint8)
+
+
 class QuantizeFn(torch.autograd.Function):
     """quantizer/vector_quantizer.py:104-157 — search (or given indices), gather, loss, straight-through output."""
 

@@ -12,10 +12,14 @@ class MlpUpscaler(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(input_dim, hidden_size, bias=True), nn.Dropout(p=dropout), nn.SELU(),
                                  nn.Linear(hidden_size, output_dim, bias=True))
 
-    def forward(self, inputs):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError('dropout > 0 is not implemented on the fused path yet (use dropout=0.0 or .eval())')
+    def forward(self, inputs, keep_mask=None):
+        """keep_mask (uint8, shape of the hidden layer) replays a given dropout draw (tests); by default a fresh one is
+        drawn from torch's CUDA generator when training with dropout > 0."""
         h = ops.LinearFn.apply(inputs, self.mlp[0].weight, self.mlp[0].bias)
+        if self.training and self.dropout > 0:
+            if keep_mask is None:
+                keep_mask = ops.draw_keep_mask(h.shape, self.dropout, h.device)
+            h = ops.DropoutFn.apply(h, keep_mask, self.dropout)
         h = ops.SeluFn.apply(h)
         return ops.LinearFn.apply(h, self.mlp[3].weight, self.mlp[3].bias)
 

@@ -337,6 +337,16 @@ __global__ void selu_bwd_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // ----------------------------------------------------------------------------------------------
+// inverted dropout with an explicit keep mask (nn.Dropout, mlp_upscaler.py:23): out = x * keep * scale, scale = 1/(1-p).
+// The mask is an input (one byte per element) so forward and backward see the same draw and tests can replay it.
+// ----------------------------------------------------------------------------------------------
+__global__ void mask_scale_kernel(const float* __restrict__ x, const unsigned char* __restrict__ keep, float scale,
+                                  float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = keep[i] ? x[i] * scale : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------
 // fp32 -> (bf16 hi, bf16 lo) split for the BF16x3 tensor-core GEMM:  x ~= hi + lo  (16 significand bits)
 // ----------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi,
@@ -560,6 +570,14 @@ VQ_API int vqcpc_selu_bwd(const float* x, const float* dy, float* dx, int64_t n,
   if (n == 0) return VQ_OK;
   selu_bwd_kernel<<<grid_for(n, 256), 256, 0, vq_stream(stream)>>>(x, dy, dx, n);
   VQ_CUDA_LAUNCH_CHECK("selu_bwd_kernel");
+  return VQ_OK;
+}
+
+// nn.Dropout with an explicit keep mask (u8, one per element): out = keep ? x * scale : 0
+VQ_API int vqcpc_mask_scale(const float* x, const unsigned char* keep, float scale, float* out, int64_t n, void* stream) {
+  if (n == 0) return VQ_OK;
+  mask_scale_kernel<<<grid_for(n, 256), 256, 0, vq_stream(stream)>>>(x, keep, scale, out, n);
+  VQ_CUDA_LAUNCH_CHECK("mask_scale_kernel");
   return VQ_OK;
 }
 
