@@ -254,3 +254,39 @@ def test_fused_bottleneck_matches_unfused():
     assert abs(s0['loss'].item() - s1['loss'].item()) < 1e-6 * abs(s0['loss'].item())
     assert rel_err(g1, g0) < 2e-5, rel_err(g1, g0)
     ops.set_gemm_mode('bf16x3')
+
+
+def test_lstm_config_trains_with_dropout():
+    """configs/encoder_vqcpc_lstm.py as shipped (dropout 0.1 in the GRUs, the upscaler and the context network): a few
+    optimizer steps through the public factories run, stay finite and reduce the contrastive loss on a repeated batch
+    (at the config's lr; at 10x that the commitment term of this model runs away, with or without dropout - the reference
+    behaves the same)."""
+    import importlib.util
+    from VQCPCB import ops
+    from VQCPCB.getters import get_dataloader_generator, get_encoder, get_encoder_trainer
+    ops.set_gemm_mode('bf16x3')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'encoder_vqcpc_lstm.py')
+    spec = importlib.util.spec_from_file_location('cfg_lstm_train', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    config = mod.config
+    torch.manual_seed(0)
+    gen = get_dataloader_generator(config['dataset'], config['training_method'], config['dataloader_generator_kwargs'])
+    enc = get_encoder('/tmp/vqcpc_lstm_test', gen, config)
+    tr = get_encoder_trainer('/tmp/vqcpc_lstm_test', gen, config['training_method'], enc, config['auxiliary_networks_kwargs'])
+    tr.to('cuda')
+    tr.init_optimizers(config['lr'], False)
+    tr.train()
+    assert enc.upscaler.dropout == 0.1 and not enc._fusable(False)      # per-vector path with dropout while training
+    train, _, _ = gen.dataloaders(batch_size=16)
+    batch = next(iter(train))
+    losses = [tr.step(batch, True, False)['loss_contrastive'].item() for _ in range(80)]
+    assert all(torch.isfinite(torch.tensor(losses)))
+    first, last = sum(losses[:10]) / 10, sum(losses[-10:]) / 10
+    assert last < first - 0.05, (first, last)
+    tr.eval()
+    assert enc._fusable(False)                                          # evaluation: fused table path
+    with torch.no_grad():
+        zq, idx, ql = enc(batch['x_left'])
+    assert zq.shape == (16, 6, 32) and idx.shape == (16, 6, 1)
