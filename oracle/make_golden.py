@@ -33,10 +33,11 @@ def import_reference():
     from VQCPCB.data_processor.bach_cpc_data_processor import BachCPCDataProcessor
     from VQCPCB.downscalers.relative_transformer_downscaler import RelativeTransformerDownscaler
     from VQCPCB.downscalers.lstm_downscaler import LstmDownscaler
+    from VQCPCB.downscalers.relative_transformer_downscaler_linear import RelativeTransformerDownscalerLinear
     from VQCPCB.quantizer.vector_quantizer import ProductVectorQuantizer
     from VQCPCB.upscalers.mlp_upscaler import MlpUpscaler
     return dict(Encoder=Encoder, Trainer=VQCPCEncoderTrainer, DP=BachCPCDataProcessor,
-                Down=RelativeTransformerDownscaler, LstmDown=LstmDownscaler, VQ=ProductVectorQuantizer, Up=MlpUpscaler)
+                Down=RelativeTransformerDownscaler, LstmDown=LstmDownscaler, DownLin=RelativeTransformerDownscalerLinear, VQ=ProductVectorQuantizer, Up=MlpUpscaler)
 
 
 def build_reference(R, cfg, prm, model_dir='/tmp/vqcpc_golden'):
@@ -45,6 +46,9 @@ def build_reference(R, cfg, prm, model_dir='/tmp/vqcpc_golden'):
     if cfg.get('downscaler', 'transformer') == 'lstm':
         down = R['LstmDown'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
                              cfg.lstm_hidden, cfg.lstm_layers, 0.0, cfg.lstm_bidirectional)
+    elif cfg.get('downscaler', 'transformer') == 'transformer_linear':
+        down = R['DownLin'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
+                            cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
     else:
         down = R['Down'](cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
                          cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
@@ -106,6 +110,8 @@ CASES = {
     # GRU block downscaler (encoder_random_config.py shape: bidirectional 2-layer GRU pair, K = 32, 6 + 6 blocks)
     'lstm': dict(cfg=dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=512, lstm_layers=2,
                           lstm_bidirectional=True, codebook_size=32, codebook_scale=0.05, KL=6, KR=6), B=4),
+    # aggregation by Linear(factor * d -> d) instead of subsampling (encoder_random_transfolin_config.py shape)
+    'translin': dict(cfg=dict(downscaler='transformer_linear', codebook_size=16, KL=2, KR=2), B=4),
     'lstm_uni': dict(cfg=dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=96, lstm_layers=1,
                               lstm_bidirectional=False, codebook_size=16, codebook_scale=0.05, KL=2, KR=2), B=3),
 }

@@ -73,6 +73,9 @@ def param_shapes(cfg):
                 out[p + 'norm1.bias'] = ((d,), ('normal', 0.1))
                 out[p + 'norm2.weight'] = ((d,), ('normal1', 0.1))
                 out[p + 'norm2.bias'] = ((d,), ('normal', 0.1))
+            if cfg.get('downscaler', 'transformer') == 'transformer_linear':
+                out[f'downscaler.linear_aggs.{s}.weight'] = ((d, d * factor), ('uniform', 1 / math.sqrt(d * factor)))
+                out[f'downscaler.linear_aggs.{s}.bias'] = ((d,), ('uniform', 1 / math.sqrt(d * factor)))
             L //= factor
     if cfg.codebook_size is not None:
         for i in range(cfg.num_codebooks):

@@ -157,7 +157,13 @@ def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None):
             h = encoder_layer(h, prm, f'{pre}transformers.{s}.layers.{l}.', cfg.n_head)
             if trace is not None:
                 trace[f'x_{s}_{l}'] = h
-        h = h[:, ::factor]
+        if cfg.get('downscaler', 'transformer') == 'transformer_linear':
+            # relative_transformer_downscaler_linear.py:129-133: concat `factor` consecutive tokens, Linear(factor*d -> d)
+            n, Lc, dm = h.shape
+            h = F.linear(h.reshape(n, Lc // factor, factor * dm), prm[f'{pre}linear_aggs.{s}.weight'],
+                         prm[f'{pre}linear_aggs.{s}.bias'])
+        else:
+            h = h[:, ::factor]
     assert h.shape[1] == 1                                                                    # :128
     z = F.linear(h[:, 0], prm[pre + 'output_linear.weight'], prm[pre + 'output_linear.bias'])  # :132
     return z.view(b, nb, -1)

@@ -18,6 +18,11 @@ def build_product_encoder(cfg, model_dir='/tmp/vqcpc_b200_test'):
         from VQCPCB.downscalers.lstm_downscaler import LstmDownscaler
         down = LstmDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
                               cfg.lstm_hidden, cfg.lstm_layers, 0.0, cfg.lstm_bidirectional)
+    elif cfg.get('downscaler', 'transformer') == 'transformer_linear':
+        from VQCPCB.downscalers.relative_transformer_downscaler_linear import RelativeTransformerDownscalerLinear
+        down = RelativeTransformerDownscalerLinear(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices,
+                                                   list(cfg.downscale_factors), cfg.d_model, cfg.n_head,
+                                                   list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
     else:
         down = RelativeTransformerDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
                                              cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)

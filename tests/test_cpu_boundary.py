@@ -65,6 +65,7 @@ def test_state_dict_keys_match_reference_checkpoints():
     from oracle import params as P, vqcpc_oracle as O
     from tests.helpers import build_product_trainer, load_params_into, product_named_params
     for over in (dict(), dict(codebook_dim=32, upscaler=False, KL=2, KR=2),
+                 dict(downscaler='transformer_linear'),
                  dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=64, lstm_bidirectional=True),
                  dict(downscaler='lstm', downscale_factors=[16], lstm_hidden=64, lstm_layers=1, lstm_bidirectional=False)):
         cfg = O.default_cfg(**over)

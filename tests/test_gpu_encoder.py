@@ -18,7 +18,7 @@ from oracle import vqcpc_oracle as O
 from tests.helpers import build_product_encoder, build_product_trainer, load_params_into, product_named_params, rel_err
 
 pytestmark = pytest.mark.gpu
-CASES = ['cfg1', 'cfg2_small', 'noup_d32', 'cfg1_bidir', 'lstm', 'lstm_uni']
+CASES = ['cfg1', 'cfg2_small', 'noup_d32', 'cfg1_bidir', 'lstm', 'lstm_uni', 'translin']
 MODES = ['fp32', 'bf16x3']
 
 

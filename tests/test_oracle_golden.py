@@ -8,7 +8,7 @@ import torch
 from oracle import params as P
 from oracle import vqcpc_oracle as O
 
-CASES = ['cfg1', 'cfg2_small', 'noup_d32', 'cfg1_bidir', 'lstm', 'lstm_uni']
+CASES = ['cfg1', 'cfg2_small', 'noup_d32', 'cfg1_bidir', 'lstm', 'lstm_uni', 'translin']
 
 
 def _load(golden_dir, name):

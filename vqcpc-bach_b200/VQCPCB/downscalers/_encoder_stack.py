@@ -8,7 +8,9 @@ transformer/transformer_custom.py:268-291 and multihead_attention_custom.py:154-
                 o   = softmax(q~ (k + E)^T) v   per (block, head)                   attn kernel
                 y1  = o Wo^T + bo + x ; x1 = LN1(y1)                                GEMM(+residual) + LN kernel
                 hm  = relu(x1 W1^T + b1) ; y2 = hm W2^T + b2 + x1 ; x2 = LN2(y2)    GEMM(relu) + GEMM(+residual) + LN
-    after each stack keep every ``factor``-th token; z = x W_out^T + b_out.
+    after each stack keep every ``factor``-th token (or, for the ``...DownscalerLinear`` variant, concatenate ``factor``
+    consecutive tokens and apply ``linear_aggs[s]``: Linear(factor * d -> d),
+    relative_transformer_downscaler_linear.py:84-86,129-133); z = x W_out^T + b_out.
 
 Rows are blocks-major (row = block * L + token) - blocks never interact, so this equals the reference's time-first
 layout.  Backward replays the saved activations in reverse; parameter gradients are written by the kernels straight
@@ -39,7 +41,8 @@ def _subsample_bwd(dout, P, L, factor, d):
 class EncoderStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb2d, meta, *params):
-        S, V, pe, d, H, factors, layers_per_stack, out_dim = meta
+        S, V, pe, d, H, factors, layers_per_stack, out_dim = meta[:8]
+        linear_agg = len(meta) > 8 and bool(meta[8])
         hd = d // H
         emb2d = ops._f32c(emb2d)
         M0, E = emb2d.shape
@@ -48,7 +51,9 @@ class EncoderStackFn(torch.autograd.Function):
         dev = emb2d.device
         prm = [p.detach() for p in params]
         w_in, b_in, chan, evt, w_out, b_out = prm[:6]
-        layer_params = prm[6:]
+        n_layers_total = sum(layers_per_stack)
+        layer_params = prm[6:6 + 14 * n_layers_total]
+        agg_params = prm[6 + 14 * n_layers_total:]          # (weight, bias) per stack, DownscalerLinear only
         train = any(ctx.needs_input_grad)      # (grad mode is off inside Function.forward; this is the reliable signal)
 
         h = torch.empty(M0, d, dtype=torch.float32, device=dev)
@@ -59,7 +64,8 @@ class EncoderStackFn(torch.autograd.Function):
         tc = ops.tensor_core_mode()
         x, x_sp, L, li = h, None, S, 0
         q_scale = float(hd) ** -0.5
-        for factor, nl in zip(factors, layers_per_stack):
+        agg_in = []
+        for si, (factor, nl) in enumerate(zip(factors, layers_per_stack)):
             for layer_in_stack in range(nl):
                 lp = dict(zip(_LAYER_KEYS, layer_params[li * 14:(li + 1) * 14]))
                 li += 1
@@ -67,7 +73,7 @@ class EncoderStackFn(torch.autograd.Function):
                 # (relative_transformer_downscaler.py:124), and a token's post-attention path (out-proj, LN, FFN, LN)
                 # is row-wise, so that layer runs it on the surviving rows only.  K/V (hence the in-proj and the
                 # attention itself) still see all L tokens.  Saves ~31 % of the encoder FLOPs with identical results.
-                last = (layer_in_stack == nl - 1) and factor > 1
+                last = (layer_in_stack == nl - 1) and factor > 1 and not linear_agg
                 keep = factor if last else 1
                 if tc:
                     # tensor-core path: every GEMM operand travels as a bf16 (hi, lo) pair written by its PRODUCER
@@ -103,7 +109,14 @@ class EncoderStackFn(torch.autograd.Function):
                 if train:
                     saved.append((x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, L, last))
                 x = x2
-            if nl == 0 or factor == 1:
+            if linear_agg:
+                # rows are blocks-major, so ``factor`` consecutive tokens of a block are ``factor`` consecutive rows: the
+                # reference's reshape/permute/reshape is a free view here
+                xv = x.view(P * (L // factor), factor * d)
+                if train:
+                    agg_in.append(xv)
+                x, x_sp = ops.linear_fwd(xv, agg_params[2 * si], agg_params[2 * si + 1]), None
+            elif nl == 0 or factor == 1:
                 x = _subsample(x, P, L, factor, d) if factor > 1 else x
             L = L // factor
         assert L == 1, 'the product of downscale_factors must equal the block length'
@@ -113,22 +126,27 @@ class EncoderStackFn(torch.autograd.Function):
         ctx.params = params
         ctx.tc = tc
         ctx.saved = saved
+        ctx.agg_in = agg_in
         ctx.emb2d = emb2d if train else None
         ctx.x_last = x if train else None
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        S, V, pe, d, H, factors, layers_per_stack, out_dim = ctx.meta
+        S, V, pe, d, H, factors, layers_per_stack, out_dim = ctx.meta[:8]
+        linear_agg = len(ctx.meta) > 8 and bool(ctx.meta[8])
         hd = d // H
         params = ctx.params
         prm = [p.detach() for p in params]
         w_in, b_in, chan, evt, w_out, b_out = prm[:6]
-        layer_params = prm[6:]
+        n_layers_total = sum(layers_per_stack)
+        layer_params = prm[6:6 + 14 * n_layers_total]
+        agg_params = prm[6 + 14 * n_layers_total:]
         # frozen parameters get a scratch accumulator that is simply dropped
         grads = [ops._grad_buf(p) if p.requires_grad else torch.zeros_like(p) for p in params]
         g_in = grads[:6]
-        g_layers = grads[6:]
+        g_layers = grads[6:6 + 14 * n_layers_total]
+        g_agg = grads[6 + 14 * n_layers_total:]
         dz = ops._f32c(dz)
         P = dz.shape[0]
         q_scale = float(hd) ** -0.5
@@ -136,9 +154,12 @@ class EncoderStackFn(torch.autograd.Function):
         dx = ops.linear_bwd(ctx.x_last, w_out, dz, g_in[4], g_in[5])           # (P, d): grad wrt last kept token
         L = 1
         li = len(ctx.saved)
-        for factor, nl in reversed(list(zip(factors, layers_per_stack))):
+        for si, (factor, nl) in reversed(list(enumerate(zip(factors, layers_per_stack)))):
             Lf = L * factor
-            if nl == 0 and factor > 1:
+            if linear_agg:
+                dx = ops.linear_bwd(ctx.agg_in[si], agg_params[2 * si], dx, g_agg[2 * si], g_agg[2 * si + 1]).view(P * Lf, d)
+                ctx.agg_in[si] = None
+            elif nl == 0 and factor > 1:
                 dx = _subsample_bwd(dx, P, Lf, factor, d)
             L = Lf
             for _ in range(nl):
@@ -147,6 +168,7 @@ class EncoderStackFn(torch.autograd.Function):
                 gp = dict(zip(_LAYER_KEYS, g_layers[li * 14:(li + 1) * 14]))
                 x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls, last = ctx.saved[li]
                 assert Ls == L
+                assert not (last and linear_agg)
                 keep = factor if last else 1
                 Mk = P * (L // keep)
                 # (for a stack's last layer everything down to the out-proj lives on the surviving rows only)
@@ -196,6 +218,7 @@ class EncoderStackFn(torch.autograd.Function):
         need_demb = ctx.needs_input_grad[0]
         demb = ops.linear_bwd(ctx.emb2d, w_in, dh_lin, g_in[0], g_in[1], need_dx=need_demb)
         ctx.saved = None
+        ctx.agg_in = None
         ctx.emb2d = None
         ctx.x_last = None
         # parameter gradients were accumulated in place -> autograd gets None for them

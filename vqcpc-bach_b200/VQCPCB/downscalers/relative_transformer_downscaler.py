@@ -15,6 +15,7 @@ class RelativeTransformerDownscaler(Downscaler):
     """(batch, num_tokens, embedding_dim) -> (batch, num_tokens // prod(downscale_factors), output_dim)."""
 
     POS_EMB = 8
+    LINEAR_AGG = False       # True in RelativeTransformerDownscalerLinear: stacks end in Linear(factor * d -> d)
 
     def __init__(self, input_dim, output_dim, num_channels, downscale_factors, d_model, n_head, list_of_num_layers,
                  dim_feedforward, dropout):
@@ -63,6 +64,6 @@ class RelativeTransformerDownscaler(Downscaler):
                                       '(the parity-checked setting) or call .eval()')
         nb = seq_len // self.sequence_length
         meta = (self.sequence_length, self.num_channels, self.POS_EMB, self.d_model, self.n_head,
-                tuple(self.downscale_factors), tuple(self.list_of_num_layers), self.output_dim)
+                tuple(self.downscale_factors), tuple(self.list_of_num_layers), self.output_dim, self.LINEAR_AGG)
         z = EncoderStackFn.apply(embedded_seq.reshape(batch * seq_len, dim), meta, *self._flat_params())
         return z.view(batch, nb, self.output_dim)

@@ -9,6 +9,7 @@ from .data_processor.bach_data_processor import BachDataProcessor
 from .dataloaders.synthetic_cpc_dataloader import SyntheticCPCDataloaderGenerator
 from .downscalers.lstm_downscaler import LstmDownscaler
 from .downscalers.relative_transformer_downscaler import RelativeTransformerDownscaler
+from .downscalers.relative_transformer_downscaler_linear import RelativeTransformerDownscalerLinear
 from .encoder import Encoder
 from .quantizer.vector_quantizer import ProductVectorQuantizer, NoQuantization
 from .upscalers.mlp_upscaler import MlpUpscaler
@@ -44,12 +45,17 @@ def get_downscaler(downscaler_type, downscaler_kwargs):
             input_dim=kw['input_dim'], output_dim=kw['output_dim'], downscale_factors=kw['downscale_factors'],
             num_channels=kw['num_channels'], d_model=kw['d_model'], n_head=kw['n_head'],
             list_of_num_layers=kw['list_of_num_layers'], dim_feedforward=kw['dim_feedforward'], dropout=kw['dropout'])
+    if downscaler_type == 'relative_transformer_downscaler_linear':
+        return RelativeTransformerDownscalerLinear(
+            input_dim=kw['input_dim'], output_dim=kw['output_dim'], downscale_factors=kw['downscale_factors'],
+            num_channels=kw['num_channels'], d_model=kw['d_model'], n_head=kw['n_head'],
+            list_of_num_layers=kw['list_of_num_layers'], dim_feedforward=kw['dim_feedforward'], dropout=kw['dropout'])
     if downscaler_type == 'lstm_downscaler':
         return LstmDownscaler(
             input_dim=kw['input_dim'], output_dim=kw['output_dim'], num_channels=kw['num_channels'],
             downscale_factors=kw['downscale_factors'], hidden_size=kw['hidden_size'], num_layers=kw['num_layers'],
             dropout=kw['dropout'], bidirectional=kw['bidirectional'])
-    if downscaler_type in ('relative_transformer_downscaler_linear', 'mlp_downscaler'):
+    if downscaler_type == 'mlp_downscaler':
         raise NotImplementedError(f'downscaler_type={downscaler_type!r} {_NEXT}')
     raise NotImplementedError
 
