@@ -76,6 +76,11 @@ int vqcpc_selu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* 
 /* nn.Dropout (mlp_upscaler.py:23) with an explicit keep mask (one byte per element, drawn by the caller so that
  * forward, backward and tests share it): out = keep ? x * scale : 0, scale = 1 / (1 - p). */
 int vqcpc_mask_scale(const float* x, const unsigned char* keep, float scale, float* out, int64_t n, void* stream);
+/* The dropout sites of the encoder layer (transformer_custom.py:278-290: dropout1 / dropout2 before the residual add,
+ * `dropout` after the activation) and their backward: out = (keep ? x * scale : 0) (+ residual, may be NULL), written as
+ * fp32 (`out`) and / or as the bf16 split (out_hi, out_lo) the next GEMM consumes; n % 4 == 0. */
+int vqcpc_mask_scale_add(const float* x, const unsigned char* keep, float scale, const float* residual, float* out,
+                         void* out_hi, void* out_lo, int64_t n, void* stream);
 /* out[0] = scale * sum(x[0..n)) in a fixed order (deterministic). */
 int vqcpc_reduce_sum(const float* x, int64_t n, float* out, float scale, void* stream);
 
@@ -116,6 +121,16 @@ int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* ou
 int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
                    float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
                    int head_dim, float q_scale, int keep, void* stream);
+
+/* Same with dropout on the attention weights (F.dropout at multihead_attention_custom.py:339): drop_keep (P, H, L, L) uint8
+ * keep mask or NULL, drop_scale = 1 / (1 - p).  `probs` always holds the softmax output; the mask acts on the P.V product
+ * (forward) and on dA / dV (backward). */
+int vqcpc_attn_fwd_ex(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo, float* probs,
+                      int64_t P, int L, int H, int head_dim, int keep, const unsigned char* drop_keep, float drop_scale,
+                      void* stream);
+int vqcpc_attn_bwd_ex(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
+                      float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
+                      int head_dim, float q_scale, int keep, const unsigned char* drop_keep, float drop_scale, void* stream);
 
 /* ---- vector quantizer (quantizer/vector_quantizer.py:85-159) --------------------------------------------------
  * x (n, D); books: host array of ncb device pointers, each (Kc, D/ncb); idx (n, ncb) int64. */

@@ -103,7 +103,7 @@ def rel_bias(q_scaled, e1, e2):
     return torch.where(lower, b1, b2)
 
 
-def mha_self(x, prm, pre, H, return_probs=False):
+def mha_self(x, prm, pre, H, return_probs=False, attn_keep=None):
     """VQCPCB/transformer/multihead_attention_custom.py:154-353 (self-attention branch :168-171).
 
     x (P, L, d).  q is scaled by hd**-0.5 *after* the in-proj bias and *before* the relative bias (:247)."""
@@ -117,7 +117,9 @@ def mha_self(x, prm, pre, H, return_probs=False):
     v = v.view(P, L, H, hd).transpose(1, 2)
     s = torch.matmul(q, k.transpose(-1, -2))         # :314
     s = s + rel_bias(q, prm[pre + 'attn_bias.e1'], prm[pre + 'attn_bias.e2'])   # :331-333
-    a = torch.softmax(s, dim=-1)                     # :338 (dropout p=0 in the oracle)
+    a = torch.softmax(s, dim=-1)                     # :338
+    if attn_keep is not None:                        # :339 F.dropout on the weights, replayed from an explicit mask
+        a = a * attn_keep                            # (keep / (1 - p), shape (P, H, L, L))
     o = torch.matmul(a, v).transpose(1, 2).reshape(P, L, d)    # :343-345
     out = F.linear(o, prm[pre + 'out_proj.weight'], prm[pre + 'out_proj.bias'])  # :346
     if return_probs:
@@ -125,18 +127,28 @@ def mha_self(x, prm, pre, H, return_probs=False):
     return out
 
 
-def encoder_layer(x, prm, pre, H):
-    """VQCPCB/transformer/transformer_custom.py:268-291 (post-LN, ReLU FFN, eps=1e-5)."""
+def encoder_layer(x, prm, pre, H, drop=None):
+    """VQCPCB/transformer/transformer_custom.py:268-291 (post-LN, ReLU FFN, eps=1e-5).
+
+    drop: None (p = 0) or a dict of multiplicative dropout factors keep / (1 - p) replaying a given draw:
+    'attn' (P, H, L, L) on the attention weights, 'drop1' / 'drop2' (P, L, d) on the two residual branches (:278, :287),
+    'ffn' (P, L, F) after the activation (:283)."""
     d = x.shape[-1]
-    a = mha_self(x, prm, pre + 'self_attn.', H)
+    a = mha_self(x, prm, pre + 'self_attn.', H, attn_keep=None if drop is None else drop['attn'])
+    if drop is not None:
+        a = a * drop['drop1']
     x = F.layer_norm(x + a, (d,), prm[pre + 'norm1.weight'], prm[pre + 'norm1.bias'], 1e-5)
-    f = F.linear(torch.relu(F.linear(x, prm[pre + 'linear1.weight'], prm[pre + 'linear1.bias'])),
-                 prm[pre + 'linear2.weight'], prm[pre + 'linear2.bias'])
+    hid = torch.relu(F.linear(x, prm[pre + 'linear1.weight'], prm[pre + 'linear1.bias']))
+    if drop is not None:
+        hid = hid * drop['ffn']
+    f = F.linear(hid, prm[pre + 'linear2.weight'], prm[pre + 'linear2.bias'])
+    if drop is not None:
+        f = f * drop['drop2']
     x = F.layer_norm(x + f, (d,), prm[pre + 'norm2.weight'], prm[pre + 'norm2.bias'], 1e-5)
     return x
 
 
-def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None):
+def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None, drops=None):
     """VQCPCB/downscalers/relative_transformer_downscaler.py:93-133.
 
     emb (b, n_tok, E) -> z (b, n_tok / prod(factors), D)."""
@@ -154,7 +166,8 @@ def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None):
         trace['h0'] = h
     for s, (factor, nl) in enumerate(zip(cfg.downscale_factors, cfg.list_of_num_layers)):   # :122-124
         for l in range(nl):
-            h = encoder_layer(h, prm, f'{pre}transformers.{s}.layers.{l}.', cfg.n_head)
+            h = encoder_layer(h, prm, f'{pre}transformers.{s}.layers.{l}.', cfg.n_head,
+                              drop=None if drops is None else drops[len([1 for ss in range(s) for _ in range(cfg.list_of_num_layers[ss])]) + l])
             if trace is not None:
                 trace[f'x_{s}_{l}'] = h
         if cfg.get('downscaler', 'transformer') == 'transformer_linear':

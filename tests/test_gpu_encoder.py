@@ -290,3 +290,82 @@ def test_lstm_config_trains_with_dropout():
     with torch.no_grad():
         zq, idx, ql = enc(batch['x_left'])
     assert zq.shape == (16, 6, 32) and idx.shape == (16, 6, 1)
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('linear', [False, True])
+def test_transformer_dropout_replay_vs_oracle(mode, linear):
+    """Training-mode dropout in the fused encoder (attention weights, dropout1 / dropout2, FFN dropout - the reference's
+    four sites per layer): the keep masks the kernels used are recorded and replayed through the fp64 oracle, so output
+    AND gradients are checked exactly, including the dead-row-eliminated last layers (their masks live on kept rows)."""
+    from VQCPCB import ops
+    ops.set_gemm_mode(mode)
+    p = 0.25
+    cfg = O.default_cfg(codebook_size=16, KL=2, KR=2, downscaler='transformer_linear' if linear else 'transformer')
+    prm = P.make_params(cfg, 3)
+    tr = build_product_trainer(cfg)
+    load_params_into(tr, prm)
+    down = tr.encoder.downscaler
+    down.dropout = p
+    down.train()
+    S = 16
+    nb, b = 3, 2
+    g = torch.Generator().manual_seed(5)
+    emb = torch.randn(b, nb * S, cfg.embedding_size, generator=g)
+    rec = {}
+
+    def hook(site, shape, pp, device):
+        m = (torch.rand(shape, generator=g) >= pp).to(torch.uint8)
+        rec[site] = m
+        return m.to(device)
+
+    ops.DROPOUT_MASK_HOOK = hook
+    try:
+        x = emb.cuda().requires_grad_(True)
+        z = down(x)
+        gz = torch.randn(z.shape, generator=g)
+        named = dict(down.named_parameters())
+        for q in named.values():
+            q.grad = None
+        z.backward(gz.cuda())
+        torch.cuda.synchronize()
+    finally:
+        ops.DROPOUT_MASK_HOOK = None
+    # replay through the oracle in fp64: expand the compact (kept-row) masks of each stack's last layer to all rows
+    Pn, d, H, Fh = b * nb, cfg.d_model, cfg.n_head, cfg.dim_feedforward
+    drops, li, L = [], 0, S
+    for factor, nl in zip(cfg.downscale_factors, cfg.list_of_num_layers):
+        for l in range(nl):
+            last = (l == nl - 1) and factor > 1 and not linear
+            keep = factor if last else 1
+
+            def full(site, width):
+                m = rec[f'{site}{li}'].double().view(Pn, L // keep, width) / (1 - p)
+                if keep == 1:
+                    return m
+                out = torch.ones(Pn, L, width, dtype=torch.float64)
+                out[:, ::keep] = m
+                return out
+            drops.append(dict(attn=rec[f'attn{li}'].double() / (1 - p), drop1=full('drop1_', d), ffn=full('ffn', Fh),
+                              drop2=full('drop2_', d)))
+            li += 1
+        L //= factor
+    prm64 = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+    e64 = emb.double().requires_grad_(True)
+    z64 = O.downscaler_forward(e64, prm64, cfg, drops=drops)
+    z64.backward(gz.double())
+    tol = 2e-5 if mode == 'fp32' else 1e-4
+    assert rel_err(z, z64) < tol, rel_err(z, z64)
+    # bf16x3: 16-bit significands on every GEMM operand; the worst parameter here (a bias gradient summed from the split
+    # hi + lo halves of a small batch) sits at 6e-3, the same floor as the dropout-free training-step test
+    gtol = 1e-3 if mode == 'fp32' else 1e-2
+    assert rel_err(x.grad, e64.grad) < gtol, rel_err(x.grad, e64.grad)
+    worst = (0.0, '')
+    for k, q in named.items():
+        r = prm64['downscaler.' + k].grad
+        if r is None or r.norm() < 1e-9:
+            continue
+        worst = max(worst, (rel_err(q.grad, r), k))
+    print(f'[dropout/{mode}/linear={linear}] z rel {rel_err(z, z64):.2e} worst grad rel {worst[0]:.2e} ({worst[1]})')
+    assert worst[0] < gtol, worst
+    ops.set_gemm_mode('bf16x3')

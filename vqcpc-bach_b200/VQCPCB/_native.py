@@ -28,6 +28,7 @@ SIGNATURES = {
     'vqcpc_selu_fwd': [_P, _P, _L, _P],
     'vqcpc_selu_bwd': [_P, _P, _P, _L, _P],
     'vqcpc_mask_scale': [_P, _P, _F, _P, _L, _P],
+    'vqcpc_mask_scale_add': [_P, _P, _F, _P, _P, _P, _P, _L, _P],
     'vqcpc_split_bf16': [_P, _I, _P, _P, _I, _L, _I, _P],
     'vqcpc_reduce_sum': [_P, _L, _P, _F, _P],
     'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],
@@ -36,6 +37,8 @@ SIGNATURES = {
     'vqcpc_gemm_set_tile_config': [_I],
     'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
+    'vqcpc_attn_fwd_ex': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _F, _P],
+    'vqcpc_attn_bwd_ex': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P, _F, _P],
     'vqcpc_vq_search': [_P, _L, _I, _P, _I, _I, _P, _P],
     'vqcpc_vq_gather': [_P, _L, _I, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],
     'vqcpc_vq_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _P, _P, _P],

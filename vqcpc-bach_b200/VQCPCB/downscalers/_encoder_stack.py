@@ -14,8 +14,13 @@ transformer/transformer_custom.py:268-291 and multihead_attention_custom.py:154-
 
 Rows are blocks-major (row = block * L + token) - blocks never interact, so this equals the reference's time-first
 layout.  Backward replays the saved activations in reverse; parameter gradients are written by the kernels straight
-into ``param.grad`` (accumulating), which the trainer aliases to its flat gradient buffer.  Dropout: p = 0 only (the
-parity-checked setting); p > 0 raises until the Philox-dropout epilogues land.
+into ``param.grad`` (accumulating), which the trainer aliases to its flat gradient buffer.
+
+Dropout (training with p > 0; the reference's four sites per layer: on the attention weights, ``dropout1`` / ``dropout2``
+before the residual adds, ``dropout`` after the activation) uses explicit uint8 keep masks drawn per site: the attention
+kernels take the mask directly, the three GEMM-side sites run ``vqcpc_mask_scale_add`` on the GEMM output (which also
+adds the residual / writes the bf16 split the next GEMM reads), and backward applies the same masks to the incoming
+gradients.  With p = 0 (the parity-checked headline setting) nothing changes: residual / ReLU stay in the GEMM epilogues.
 """
 import torch
 
@@ -43,6 +48,9 @@ class EncoderStackFn(torch.autograd.Function):
     def forward(ctx, emb2d, meta, *params):
         S, V, pe, d, H, factors, layers_per_stack, out_dim = meta[:8]
         linear_agg = len(meta) > 8 and bool(meta[8])
+        drop_p = float(meta[9]) if len(meta) > 9 else 0.0
+        dp = drop_p > 0.0
+        ds = 1.0 / (1.0 - drop_p) if dp else 1.0
         hd = d // H
         emb2d = ops._f32c(emb2d)
         M0, E = emb2d.shape
@@ -83,31 +91,59 @@ class EncoderStackFn(torch.autograd.Function):
                         x_sp = ops.split_bf16(x)
                     qkv = ops.gemm(None, lp['wqkv'], P * L, 3 * d, d, bias=lp['bqkv'], scale_cols=(q_scale, d),
                                    b_is_weight=True, a_split=x_sp)
-                    _, o_sp, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep,
-                                                  want_fp32=False, want_split=True)
-                    x_k = _subsample(x, P, L, factor, d) if last else x
                     Mk = P * (L // keep)
-                    y1 = ops.gemm(None, lp['wo'], Mk, d, d, bias=lp['bo'], residual=x_k, b_is_weight=True, a_split=o_sp)
-                    x1, x1_sp, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'], want_split=True)
                     Fh = lp['w1'].shape[0]
-                    _, hm_sp = ops.gemm(None, lp['w1'], Mk, Fh, d, bias=lp['b1'], relu=True, b_is_weight=True, a_split=x1_sp,
-                                        want_c=False, out_split=True)
-                    y2 = ops.gemm(None, lp['w2'], Mk, d, Fh, bias=lp['b2'], residual=x1, b_is_weight=True, a_split=hm_sp)
+                    masks = None
+                    if dp:
+                        masks = tuple(ops.dropout_mask(f'{site}{li - 1}', shp, drop_p, dev) for site, shp in
+                                      (('attn', (P, H, L, L)), ('drop1_', (Mk, d)), ('ffn', (Mk, Fh)), ('drop2_', (Mk, d))))
+                    _, o_sp, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep,
+                                                  want_fp32=False, want_split=True, drop=(masks[0], ds) if dp else None)
+                    x_k = _subsample(x, P, L, factor, d) if last else x
+                    if dp:
+                        y1p = ops.gemm(None, lp['wo'], Mk, d, d, bias=lp['bo'], b_is_weight=True, a_split=o_sp)
+                        y1, _ = ops.mask_scale_add(y1p, masks[1], ds, residual=x_k)
+                    else:
+                        y1 = ops.gemm(None, lp['wo'], Mk, d, d, bias=lp['bo'], residual=x_k, b_is_weight=True, a_split=o_sp)
+                    x1, x1_sp, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'], want_split=True)
+                    if dp:
+                        hmp = ops.gemm(None, lp['w1'], Mk, Fh, d, bias=lp['b1'], relu=True, b_is_weight=True, a_split=x1_sp)
+                        _, hm_sp = ops.mask_scale_add(hmp, masks[2], ds, want_fp32=False, want_split=True)
+                        del hmp
+                        y2p = ops.gemm(None, lp['w2'], Mk, d, Fh, bias=lp['b2'], b_is_weight=True, a_split=hm_sp)
+                        y2, _ = ops.mask_scale_add(y2p, masks[3], ds, residual=x1)
+                    else:
+                        _, hm_sp = ops.gemm(None, lp['w1'], Mk, Fh, d, bias=lp['b1'], relu=True, b_is_weight=True, a_split=x1_sp,
+                                            want_c=False, out_split=True)
+                        y2 = ops.gemm(None, lp['w2'], Mk, d, Fh, bias=lp['b2'], residual=x1, b_is_weight=True, a_split=hm_sp)
                     x2, x2_sp, mean2, rstd2 = ops.layernorm_fwd(y2, lp['g2'], lp['be2'], want_split=True)
                     if train:
-                        saved.append((x_sp, qkv, probs, o_sp, y1, mean1, rstd1, x1_sp, hm_sp, y2, mean2, rstd2, L, last))
+                        saved.append((x_sp, qkv, probs, o_sp, y1, mean1, rstd1, x1_sp, hm_sp, y2, mean2, rstd2, L, last, masks))
                     x, x_sp = x2, x2_sp
                     continue
                 qkv = ops.linear_fwd(x, lp['wqkv'], lp['bqkv'], scale_cols=(q_scale, d))
-                o_k, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep)
+                Mk = P * (L // keep)
+                masks = None
+                if dp:
+                    masks = tuple(ops.dropout_mask(f'{site}{li - 1}', shp, drop_p, dev) for site, shp in
+                                  (('attn', (P, H, L, L)), ('drop1_', (Mk, d)), ('ffn', (Mk, lp['w1'].shape[0])), ('drop2_', (Mk, d))))
+                o_k, probs = ops.attn_fwd(qkv, lp['e1'], lp['e2'], P, L, H, hd, need_probs=train, keep=keep,
+                                          drop=(masks[0], ds) if dp else None)
                 x_k = _subsample(x, P, L, factor, d) if last else x
-                y1 = ops.linear_fwd(o_k, lp['wo'], lp['bo'], residual=x_k)
+                if dp:
+                    y1, _ = ops.mask_scale_add(ops.linear_fwd(o_k, lp['wo'], lp['bo']), masks[1], ds, residual=x_k)
+                else:
+                    y1 = ops.linear_fwd(o_k, lp['wo'], lp['bo'], residual=x_k)
                 x1, mean1, rstd1 = ops.layernorm_fwd(y1, lp['g1'], lp['be1'])
                 hm = ops.linear_fwd(x1, lp['w1'], lp['b1'], relu=True)
-                y2 = ops.linear_fwd(hm, lp['w2'], lp['b2'], residual=x1)
+                if dp:
+                    hm, _ = ops.mask_scale_add(hm, masks[2], ds)
+                    y2, _ = ops.mask_scale_add(ops.linear_fwd(hm, lp['w2'], lp['b2']), masks[3], ds, residual=x1)
+                else:
+                    y2 = ops.linear_fwd(hm, lp['w2'], lp['b2'], residual=x1)
                 x2, mean2, rstd2 = ops.layernorm_fwd(y2, lp['g2'], lp['be2'])
                 if train:
-                    saved.append((x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, L, last))
+                    saved.append((x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, L, last, masks))
                 x = x2
             if linear_agg:
                 # rows are blocks-major, so ``factor`` consecutive tokens of a block are ``factor`` consecutive rows: the
@@ -135,6 +171,8 @@ class EncoderStackFn(torch.autograd.Function):
     def backward(ctx, dz):
         S, V, pe, d, H, factors, layers_per_stack, out_dim = ctx.meta[:8]
         linear_agg = len(ctx.meta) > 8 and bool(ctx.meta[8])
+        drop_p = float(ctx.meta[9]) if len(ctx.meta) > 9 else 0.0
+        ds = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
         hd = d // H
         params = ctx.params
         prm = [p.detach() for p in params]
@@ -166,7 +204,8 @@ class EncoderStackFn(torch.autograd.Function):
                 li -= 1
                 lp = dict(zip(_LAYER_KEYS, layer_params[li * 14:(li + 1) * 14]))
                 gp = dict(zip(_LAYER_KEYS, g_layers[li * 14:(li + 1) * 14]))
-                x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls, last = ctx.saved[li]
+                x, qkv, probs, o_k, y1, mean1, rstd1, x1, hm, y2, mean2, rstd2, Ls, last, masks = ctx.saved[li]
+                adrop = (masks[0], ds) if masks is not None else None
                 assert Ls == L
                 assert not (last and linear_agg)
                 keep = factor if last else 1
@@ -176,18 +215,33 @@ class EncoderStackFn(torch.autograd.Function):
                     # x, o_k, x1, hm are bf16 (hi, lo) pairs saved by the forward; gradients that feed GEMMs are produced
                     # pre-split by the LayerNorm-backward / attention-backward kernels and the GEMM epilogues.
                     Fh = lp['w1'].shape[0]
-                    dy2, dy2_sp = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'], want_split=True)
-                    # FFN2: dhm = (dy2 W2) * (hm > 0) -> only its split is needed (dgrad + wgrad of FFN1)
-                    _, dhm_sp = ops.linear_bwd(None, lp['w2'], dy2, gp['w2'], gp['b2'], relu_mask=hm[0], x_split=hm,
-                                               dy_split=dy2_sp, dx_want_c=False, dx_out_split=True, shape=(Mk, Fh))
+                    if masks is not None:
+                        # dropout2: the FFN branch sees the masked gradient, the residual path the plain one
+                        dy2 = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'])
+                        _, dy2_sp = ops.mask_scale_add(dy2, masks[3], ds, want_fp32=False, want_split=True)
+                        dy2_for_bias = None                    # bias gradient from the masked split
+                    else:
+                        dy2, dy2_sp = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'], want_split=True)
+                        dy2_for_bias = dy2
+                    # FFN2: dhm = (dy2 W2) * (hm > 0) -> only its split is needed (dgrad + wgrad of FFN1); with dropout
+                    # the saved hm is the dropped activation (zero where dropped) and the kept entries carry 1 / (1 - p)
+                    _, dhm_sp = ops.linear_bwd(None, lp['w2'], dy2_for_bias, gp['w2'], gp['b2'], relu_mask=hm[0], x_split=hm,
+                                               dy_split=dy2_sp, dx_want_c=False, dx_out_split=True, shape=(Mk, Fh),
+                                               dx_scale=ds if masks is not None else None)
                     # FFN1: dx1 = dhm W1 + dy2
                     dx1 = ops.linear_bwd(None, lp['w1'], None, gp['w1'], gp['b1'], dx_residual=dy2, x_split=x1,
                                          dy_split=dhm_sp, shape=(Mk, d))
                     del dhm_sp
-                    dy1, dy1_sp = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'], want_split=True)
-                    do = ops.linear_bwd(None, lp['wo'], dy1, gp['wo'], gp['bo'], x_split=o_k, dy_split=dy1_sp, shape=(Mk, d))
+                    if masks is not None:
+                        dy1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'])
+                        _, dy1_sp = ops.mask_scale_add(dy1, masks[1], ds, want_fp32=False, want_split=True)
+                        dy1_for_bias = None
+                    else:
+                        dy1, dy1_sp = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'], want_split=True)
+                        dy1_for_bias = dy1
+                    do = ops.linear_bwd(None, lp['wo'], dy1_for_bias, gp['wo'], gp['bo'], x_split=o_k, dy_split=dy1_sp, shape=(Mk, d))
                     _, dqkv_sp = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale,
-                                              keep=keep, want_fp32=False, want_split=True)
+                                              keep=keep, want_fp32=False, want_split=True, drop=adrop)
                     if last:
                         dy1 = _subsample_bwd(dy1, P, L, factor, d)
                     dx = ops.linear_bwd(None, lp['wqkv'], None, gp['wqkv'], gp['bqkv'], dx_residual=dy1, x_split=x,
@@ -196,15 +250,18 @@ class EncoderStackFn(torch.autograd.Function):
                     continue
                 # LN2 -> dy2 (flows to the FFN branch and, as the residual, to x1)
                 dy2 = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'])
-                # FFN2: dhm = (dy2 W2) * (hm > 0)
-                dhm = ops.linear_bwd(hm, lp['w2'], dy2, gp['w2'], gp['b2'], relu_mask=hm)
+                dy2m = ops.mask_scale_add(dy2, masks[3], ds)[0] if masks is not None else dy2
+                # FFN2: dhm = (dy2 W2) * (hm > 0)   (with dropout: hm is the dropped activation, kept entries carry 1/(1-p))
+                dhm = ops.linear_bwd(hm, lp['w2'], dy2m, gp['w2'], gp['b2'], relu_mask=hm, dx_scale=ds if masks is not None else None)
                 # FFN1: dx1 = dhm W1 + dy2
                 dx1 = ops.linear_bwd(x1, lp['w1'], dhm, gp['w1'], gp['b1'], dx_residual=dy2)
                 del dhm
                 dy1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'])
+                dy1m = ops.mask_scale_add(dy1, masks[1], ds)[0] if masks is not None else dy1
                 # out-proj (its dgrad is the gradient of the kept query rows' attention output)
-                do = ops.linear_bwd(o_k, lp['wo'], dy1, gp['wo'], gp['bo'])
-                dqkv = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale, keep=keep)
+                do = ops.linear_bwd(o_k, lp['wo'], dy1m, gp['wo'], gp['bo'])
+                dqkv = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale, keep=keep,
+                                    drop=adrop)
                 if last:                       # residual path: scatter back to all L rows (zeros for the dropped rows)
                     dy1 = _subsample_bwd(dy1, P, L, factor, d)
                 # in-proj: dx = dqkv Wqkv + dy1 (residual path)

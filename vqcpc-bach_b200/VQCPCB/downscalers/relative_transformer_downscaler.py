@@ -59,11 +59,9 @@ class RelativeTransformerDownscaler(Downscaler):
     def forward(self, embedded_seq):
         batch, seq_len, dim = embedded_seq.shape
         assert seq_len % self.sequence_length == 0
-        if self.training and self.dropout > 0:
-            raise NotImplementedError('dropout > 0 is not implemented in the fused encoder yet: train with dropout=0.0 '
-                                      '(the parity-checked setting) or call .eval()')
         nb = seq_len // self.sequence_length
         meta = (self.sequence_length, self.num_channels, self.POS_EMB, self.d_model, self.n_head,
-                tuple(self.downscale_factors), tuple(self.list_of_num_layers), self.output_dim, self.LINEAR_AGG)
+                tuple(self.downscale_factors), tuple(self.list_of_num_layers), self.output_dim, self.LINEAR_AGG,
+                float(self.dropout) if self.training else 0.0)
         z = EncoderStackFn.apply(embedded_seq.reshape(batch * seq_len, dim), meta, *self._flat_params())
         return z.view(batch, nb, self.output_dim)

@@ -203,16 +203,17 @@ def linear_fwd(x2d, w, b, relu=False, residual=None, scale_cols=None, out=None):
 
 
 def linear_bwd(x2d, w, dy, dw, db, need_dx=True, dx_residual=None, relu_mask=None, dx_out=None, x_split=None,
-               dy_split=None, dx_want_c=True, dx_out_split=False, shape=None):
+               dy_split=None, dx_want_c=True, dx_out_split=False, shape=None, dx_scale=None):
     """Gradients of y = x @ w.T + b.  dw/db are ACCUMULATED in place (flat-gradient-buffer views).
-    dx = dy @ w (+ dx_residual) (* relu_mask > 0).  x / dy may be given pre-split (x_split / dy_split, with
+    dx = dx_scale * dy @ w (+ dx_residual) (* relu_mask > 0).  x / dy may be given pre-split (x_split / dy_split, with
     shape=(M, K)); db then comes from the split (hi + lo) unless an fp32 dy is also given."""
     M, K = shape if shape is not None else x2d.shape
     N = w.shape[0]
     dx = None
     if need_dx:
         dx = gemm(dy if dy_split is None else None, w, M, K, N, True, False, out=dx_out, residual=dx_residual,
-                  relu_mask=relu_mask, b_is_weight=True, a_split=dy_split, want_c=dx_want_c, out_split=dx_out_split)
+                  relu_mask=relu_mask, b_is_weight=True, a_split=dy_split, want_c=dx_want_c, out_split=dx_out_split,
+                  scale_cols=None if dx_scale is None else (float(dx_scale), K))
     if dw is not None:
         tiles = ((N + 127) // 128) * ((K + 127) // 128)
         gemm(dy if dy_split is None else None, x2d if x_split is None else None, N, K, M, False, False, out=dw.view(N, K),
@@ -280,27 +281,49 @@ def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta, want_split=False):
     return dy
 
 
-def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, want_split=False):
-    """-> (out fp32 | None, probs) or (out | None, (hi, lo), probs) when want_split; rows = P * L / keep."""
+def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, want_split=False, drop=None):
+    """-> (out fp32 | None, probs) or (out | None, (hi, lo), probs) when want_split; rows = P * L / keep.
+    drop = (keep_mask uint8 (P, H, L, L), scale): dropout on the attention weights."""
     Mo = P * (L // keep)
     out = torch.empty(Mo, H * hd, dtype=torch.float32, device=qkv.device) if want_fp32 else None
     sp = _split_buffers(Mo, H * hd, qkv.device) if want_split else (None, None)
     probs = torch.empty(P, H, L, L, dtype=torch.float32, device=qkv.device) if need_probs else None
-    _native.call('vqcpc_attn_fwd', _p(qkv), _p(e1), _p(e2), _p(out), _p(sp[0]), _p(sp[1]), _p(probs), P, L, H, hd, int(keep),
-                 _stream())
+    _native.call('vqcpc_attn_fwd_ex', _p(qkv), _p(e1), _p(e2), _p(out), _p(sp[0]), _p(sp[1]), _p(probs), P, L, H, hd, int(keep),
+                 _p(drop[0]) if drop else None, float(drop[1]) if drop else 1.0, _stream())
     if want_split:
         return out, sp, probs
     return out, probs
 
 
-def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False):
+def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False, drop=None):
     dqkv = torch.empty_like(qkv) if want_fp32 else None
     sp = _split_buffers(qkv.shape[0], qkv.shape[1], qkv.device) if want_split else (None, None)
-    _native.call('vqcpc_attn_bwd', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(sp[0]), _p(sp[1]), _p(de1), _p(de2),
-                 P, L, H, hd, float(q_scale), int(keep), _stream())
+    _native.call('vqcpc_attn_bwd_ex', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(sp[0]), _p(sp[1]), _p(de1), _p(de2),
+                 P, L, H, hd, float(q_scale), int(keep), _p(drop[0]) if drop else None, float(drop[1]) if drop else 1.0, _stream())
     if want_split:
         return dqkv, sp
     return dqkv
+
+
+def mask_scale_add(x, keep, scale, residual=None, want_fp32=True, want_split=False):
+    """(keep ? x * scale : 0) (+ residual) -> (fp32 | None, (hi, lo) | None): the dropout sites of the encoder layer."""
+    x = _f32c(x)
+    out = torch.empty_like(x) if want_fp32 else None
+    sp = _split_buffers(x.shape[0], x.shape[1], x.device) if want_split else (None, None)
+    _native.call('vqcpc_mask_scale_add', _p(x), _p(keep), float(scale), _p(residual), _p(out), _p(sp[0]), _p(sp[1]), x.numel(),
+                 _stream())
+    return out, (sp if want_split else None)
+
+
+# Tests install a callable (site, shape, p, device) -> uint8 keep mask here to record / replay the dropout draws of the
+# fused encoder; None = draw from torch's CUDA generator.
+DROPOUT_MASK_HOOK = None
+
+
+def dropout_mask(site, shape, p, device):
+    if DROPOUT_MASK_HOOK is not None:
+        return DROPOUT_MASK_HOOK(site, tuple(shape), p, device)
+    return draw_keep_mask(shape, p, device)
 
 
 def reduce_sum(x, scale=1.0):

@@ -77,7 +77,8 @@ template <int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
                 float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                float* __restrict__ probs, int64_t M, int H, int64_t ntiles, int keep) {
+                float* __restrict__ probs, int64_t M, int H, int64_t ntiles, int keep,
+                const unsigned char* __restrict__ drop_keep, float drop_scale) {
   extern __shared__ __align__(16) float smem[];
   float* e1s = smem;
   float* e2s = e1s + L * TS;
@@ -140,14 +141,15 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       float a = s[jj] * inv;
+      int c = jh * 8 + jj;
+      if (kept && gr < M && c / L == g) {
+        const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
+        if (probs != nullptr) probs[pi] = a;                 // the softmax output; dropout (F.dropout on the weights,
+        if (drop_keep != nullptr) a = drop_keep[pi] ? a * drop_scale : 0.f;   // multihead_attention_custom.py:339) acts on PV only
+      }
       float o = __shfl_xor_sync(0xffffffffu, a, 1);
       a_all[jj] = jh == 0 ? a : o;     // selects, not dynamic register indexing
       a_all[8 + jj] = jh == 0 ? o : a;
-      int c = jh * 8 + jj;
-      if (probs != nullptr && kept && gr < M && c / L == g) {
-        int64_t p = gr / L;
-        probs[((p * H + h) * L + i) * L + (c % L)] = a;
-      }
     }
     // O[r][jh*32 .. +32) = sum_c A[r][c] v[c][...]
     float4 o4[8];
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
                 const float* __restrict__ probs, const float* __restrict__ dout, float* __restrict__ dqkv,
                 __nv_bfloat16* __restrict__ dqkv_hi, __nv_bfloat16* __restrict__ dqkv_lo,
-                float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale, int keep) {
+                float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale, int keep,
+                const unsigned char* __restrict__ drop_keep, float drop_scale) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PER_WARP = 4 * TR * TS + 4 * TR * PS;
   float* e1s = smem;                     // [16][TS], rows >= L are zero
@@ -278,8 +281,9 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
     load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
     if (keep == 1) load_tile(gs, dout + h * HD, row0, M, d, lane);
     else load_tile_compact(gs, dout + h * HD, row0, M, d, lane, L, keep);     // dO exists for the kept query rows only
-    // probabilities of this lane's 2x4 patch
-    float a[2][4];
+    // probabilities of this lane's 2x4 patch (and, with dropout, the factor m = keep * scale of each: the forward used
+    // A' = A * m in O = A' V, so dV = A'^T dO and dA = (dO V^T) * m, while the softmax backward uses A itself)
+    float a[2][4], mk[2][4];
 #pragma unroll
     for (int ri = 0; ri < 2; ++ri) {
       const int r = r2 + ri;
@@ -289,11 +293,16 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c = c4 + ci;
-        float v = 0.f;
-        if (rowok && c / L == r / L) v = probs[(((gr / L) * H + h) * L + i) * L + (c % L)];
+        float v = 0.f, m = 1.f;
+        if (rowok && c / L == r / L) {
+          const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
+          v = probs[pi];
+          if (drop_keep != nullptr) m = drop_keep[pi] ? drop_scale : 0.f;
+        }
         a[ri][ci] = v;
+        mk[ri][ci] = m;
       }
-      st4(As + r * PS + c4, make_float4(a[ri][0], a[ri][1], a[ri][2], a[ri][3]));
+      st4(As + r * PS + c4, make_float4(a[ri][0] * mk[ri][0], a[ri][1] * mk[ri][1], a[ri][2] * mk[ri][2], a[ri][3] * mk[ri][3]));
     }
     __syncwarp();
 
@@ -315,6 +324,8 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
     }
 #pragma unroll
     for (int ri = 0; ri < 2; ++ri) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) da[ri][ci] *= mk[ri][ci];
       float rd = a[ri][0] * da[ri][0] + a[ri][1] * da[ri][1] + a[ri][2] * da[ri][2] + a[ri][3] * da[ri][3];
       rd += __shfl_xor_sync(0xffffffffu, rd, 1);
       rd += __shfl_xor_sync(0xffffffffu, rd, 2);
@@ -413,7 +424,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 
 template <int L>
 int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-               float* probs, int64_t M, int H, int keep, cudaStream_t st) {
+               float* probs, int64_t M, int H, int keep, const unsigned char* drop_keep, float drop_scale, cudaStream_t st) {
   constexpr int WARPS = 8;
   int64_t ntiles = vq_cdiv(M, TR);
   size_t smem = (size_t)(2 * L * TS + WARPS * 3 * TR * TS) * sizeof(float);
@@ -423,7 +434,7 @@ int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, _
     done = true;
   }
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 4);
-  attn_fwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, out_hi, out_lo, probs, M, H, ntiles, keep);
+  attn_fwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, out_hi, out_lo, probs, M, H, ntiles, keep, drop_keep, drop_scale);
   VQ_CUDA_LAUNCH_CHECK("attn_fwd_kernel");
   return VQ_OK;
 }
@@ -431,7 +442,7 @@ int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, _
 template <int L>
 int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* dout, float* dqkv,
                __nv_bfloat16* dqkv_hi, __nv_bfloat16* dqkv_lo, float* de1, float* de2, int64_t M, int H, float q_scale, int keep,
-               cudaStream_t st) {
+               const unsigned char* drop_keep, float drop_scale, cudaStream_t st) {
   constexpr int WARPS = 4;
   int64_t ntiles = vq_cdiv(M, TR);
   size_t smem = (size_t)(2 * TR * TS + WARPS * (4 * TR * TS + 4 * TR * PS)) * sizeof(float);
@@ -442,7 +453,7 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
     done = true;
   }
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 2);
-  attn_bwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep);
+  attn_bwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep, drop_keep, drop_scale);
   VQ_CUDA_LAUNCH_CHECK("attn_bwd_kernel");
   return VQ_OK;
 }
@@ -453,8 +464,11 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
 // out (fp32) and/or (out_hi, out_lo) (bf16 split, operand of the out-proj GEMM): (P*L/keep, H*64) — only the query rows
 // with token % keep == 0 are computed and stored, compacted (keep = 1: all rows; keep = downscale factor in the last
 // layer of a stack = exact dead-row elimination); probs: (P, H, L, L) saved for backward (kept rows only; may be NULL).
-VQ_API int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
-                          float* probs, int64_t P, int L, int H, int head_dim, int keep, void* stream) {
+// drop_keep (P, H, L, L) uint8 or NULL: dropout on the attention weights (F.dropout, multihead_attention_custom.py:339) with
+// an explicit keep mask, drop_scale = 1 / (1 - p); `probs` always receives the softmax output itself.
+VQ_API int vqcpc_attn_fwd_ex(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                             float* probs, int64_t P, int L, int H, int head_dim, int keep, const unsigned char* drop_keep,
+                             float drop_scale, void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_fwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_fwd: bad head count %d", H);
   VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_fwd: keep=%d must divide L=%d", keep, L);
@@ -465,22 +479,28 @@ VQ_API int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, fl
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   switch (L) {
-    case 16: return launch_fwd<16>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
-    case 8: return launch_fwd<8>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
-    case 4: return launch_fwd<4>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
-    case 2: return launch_fwd<2>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
-    case 1: return launch_fwd<1>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, st);
+    case 16: return launch_fwd<16>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, drop_keep, drop_scale, st);
+    case 8: return launch_fwd<8>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, drop_keep, drop_scale, st);
+    case 4: return launch_fwd<4>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, drop_keep, drop_scale, st);
+    case 2: return launch_fwd<2>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, drop_keep, drop_scale, st);
+    case 1: return launch_fwd<1>(qkv, e1, e2, out, oh, ol, probs, M, H, keep, drop_keep, drop_scale, st);
     default: VQ_CHECK_ARG(false, "attn_fwd: block length L must be 1, 2, 4, 8 or 16 (got %d)", L);
   }
   return VQ_OK;
 }
 
+VQ_API int vqcpc_attn_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                          float* probs, int64_t P, int L, int H, int head_dim, int keep, void* stream) {
+  return vqcpc_attn_fwd_ex(qkv, e1, e2, out, out_hi, out_lo, probs, P, L, H, head_dim, keep, nullptr, 1.f, stream);
+}
+
 // d_out: (P*L/keep, H*64) gradient of the kept query rows (see vqcpc_attn_fwd).  d_qkv (fp32, P*L x 3*H*64) and/or its
 // bf16 split (d_qkv_hi, d_qkv_lo) are overwritten (q third = gradient wrt the UNscaled projection: q_scale * dq~);
 // d_e1 / d_e2 (H*L, 64) are ACCUMULATED.
-VQ_API int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
-                          float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
-                          int head_dim, float q_scale, int keep, void* stream) {
+VQ_API int vqcpc_attn_bwd_ex(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
+                             float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
+                             int head_dim, float q_scale, int keep, const unsigned char* drop_keep, float drop_scale,
+                             void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_bwd: bad head count %d", H);
   VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_bwd: keep=%d must divide L=%d", keep, L);
@@ -491,12 +511,19 @@ VQ_API int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, co
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d_qkv_hi);
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d_qkv_lo);
   switch (L) {
-    case 16: return launch_bwd<16>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
-    case 8: return launch_bwd<8>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
-    case 4: return launch_bwd<4>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
-    case 2: return launch_bwd<2>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
-    case 1: return launch_bwd<1>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, st);
+    case 16: return launch_bwd<16>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, drop_keep, drop_scale, st);
+    case 8: return launch_bwd<8>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, drop_keep, drop_scale, st);
+    case 4: return launch_bwd<4>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, drop_keep, drop_scale, st);
+    case 2: return launch_bwd<2>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, drop_keep, drop_scale, st);
+    case 1: return launch_bwd<1>(qkv, e1, e2, probs, d_out, d_qkv, oh, ol, d_e1, d_e2, M, H, q_scale, keep, drop_keep, drop_scale, st);
     default: VQ_CHECK_ARG(false, "attn_bwd: block length L must be 1, 2, 4, 8 or 16 (got %d)", L);
   }
   return VQ_OK;
+}
+
+VQ_API int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
+                          float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
+                          int head_dim, float q_scale, int keep, void* stream) {
+  return vqcpc_attn_bwd_ex(qkv, e1, e2, probs, d_out, d_qkv, d_qkv_hi, d_qkv_lo, d_e1, d_e2, P, L, H, head_dim, q_scale, keep,
+                           nullptr, 1.f, stream);
 }

@@ -346,6 +346,33 @@ __global__ void mask_scale_kernel(const float* __restrict__ x, const unsigned ch
     out[i] = keep[i] ? x[i] * scale : 0.f;
 }
 
+// out = (keep ? x * scale : 0) + residual, four elements per thread; fp32 and / or bf16-split outputs (the dropout sites
+// of the encoder layer, transformer_custom.py:278-290: dropout1 / dropout2 before the residual add, `dropout` after the
+// activation, and the same mask applied to the incoming gradient in backward)
+__global__ void mask_scale_add_kernel(const float* __restrict__ x, const unsigned char* __restrict__ keep, float scale,
+                                      const float* __restrict__ residual, float* __restrict__ out,
+                                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(x + i * 4);
+    const uchar4 k = *reinterpret_cast<const uchar4*>(keep + i * 4);
+    v.x = k.x ? v.x * scale : 0.f; v.y = k.y ? v.y * scale : 0.f; v.z = k.z ? v.z * scale : 0.f; v.w = k.w ? v.w * scale : 0.f;
+    if (residual) {
+      const float4 r = ld4(residual + i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (out) st4(out + i * 4, v);
+    if (out_hi) {
+      __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+      __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                    l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+      __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(out_hi + i * 4);
+      __nv_bfloat162* lp = reinterpret_cast<__nv_bfloat162*>(out_lo + i * 4);
+      hp[0] = __nv_bfloat162(h0, h1); hp[1] = __nv_bfloat162(h2, h3);
+      lp[0] = __nv_bfloat162(l0, l1); lp[1] = __nv_bfloat162(l2, l3);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // fp32 -> (bf16 hi, bf16 lo) split for the BF16x3 tensor-core GEMM:  x ~= hi + lo  (16 significand bits)
 // ----------------------------------------------------------------------------------------------
@@ -578,6 +605,19 @@ VQ_API int vqcpc_mask_scale(const float* x, const unsigned char* keep, float sca
   if (n == 0) return VQ_OK;
   mask_scale_kernel<<<grid_for(n, 256), 256, 0, vq_stream(stream)>>>(x, keep, scale, out, n);
   VQ_CUDA_LAUNCH_CHECK("mask_scale_kernel");
+  return VQ_OK;
+}
+
+// dropout site of the encoder layer: out = (keep ? x * scale : 0) (+ residual); contiguous (n elements, n % 4 == 0);
+// fp32 `out` and / or the bf16 split (out_hi, out_lo) may be requested
+VQ_API int vqcpc_mask_scale_add(const float* x, const unsigned char* keep, float scale, const float* residual, float* out,
+                                void* out_hi, void* out_lo, int64_t n, void* stream) {
+  VQ_CHECK_ARG(n % 4 == 0, "mask_scale_add: n must be a multiple of 4 (got %lld)", (long long)n);
+  VQ_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "mask_scale_add: out_hi and out_lo go together");
+  if (n == 0) return VQ_OK;
+  mask_scale_add_kernel<<<grid_for(n / 4, 256), 256, 0, vq_stream(stream)>>>(
+      x, keep, scale, residual, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), n / 4);
+  VQ_CUDA_LAUNCH_CHECK("mask_scale_add_kernel");
   return VQ_OK;
 }
 
