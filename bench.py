@@ -337,6 +337,29 @@ def run_ours(args):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    # ---- second line: the same step with the reference's training dropout (0.1 in the encoder layers and the upscaler)
+    drop_line = None
+    if world == 1 and not args.no_dropout_line:
+        enc = tr.encoder
+        enc.downscaler.dropout = 0.1
+        if enc.upscaler is not None:
+            enc.upscaler.dropout = 0.1
+        tr.step(dev_batches[0], True, False)
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for i in range(2):
+            tr.step(dev_batches[i % n_batches], True, False)
+        e5.record()
+        barrier()
+        ms3 = e4.elapsed_time(e5)
+        drop_line = dict(dropout=0.1, value=B * 2 / (ms3 / 1000.0), unit=UNIT, ms_per_step=ms3 / 2, steps=2,
+                         note='explicit keep masks (one byte per element) at the four sites of every encoder layer + the '
+                              'upscaler; per-vector upscaler instead of the code table')
+        enc.downscaler.dropout = 0.0
+        if enc.upscaler is not None:
+            enc.upscaler.dropout = 0.0
+
     qi = None
     if rank == 0 and world == 1 and not args.no_path_roofline:
         del dev_batches
@@ -379,6 +402,8 @@ def run_ours(args):
         line['roofline'] = roof
     if cpu_val is not None:
         line['cpu_baseline'] = dict(value=cpu_val, unit=UNIT, **cpu_info)
+    if drop_line is not None:
+        line['with_dropout'] = drop_line
     if qi is not None:
         line['roofline_quantizer_infonce'] = qi
     print(json.dumps(line), file=_OUT, flush=True)
@@ -403,6 +428,7 @@ def main():
     ap.add_argument('--mode', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-path-roofline', action='store_true')
+    ap.add_argument('--no-dropout-line', action='store_true')
     ap.add_argument('--path-only', action='store_true', help='only the stand-alone quantizer + InfoNCE path measurement')
     args = ap.parse_args()
     global _OUT
