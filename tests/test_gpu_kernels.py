@@ -335,3 +335,68 @@ def test_upscaler_dropout_replays_mask():
     up.eval()
     assert rel_err(up(x.detach()), F.linear(F.selu(F.linear(x.detach().double(), w0.detach(), b0.detach())), w3.detach(), b3.detach())) < 1e-5
     ops.set_gemm_mode('bf16x3')
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('B,T,inp,H,nl', [(37, 8, 32, 512, 2), (5, 16, 32, 96, 1), (300, 1, 32, 64, 2), (4096, 8, 32, 512, 2)])
+def test_native_gru_matches_torch_gru(B, T, inp, H, nl, mode):
+    """ops.GRUFn (native GEMMs + gate kernels) against torch.nn.GRU in fp64 on the CPU - the module the reference uses for
+    the context network (vqcpc_helper.py:59) and the block downscaler (lstm_downscaler.py:31): outputs, input gradient and
+    every parameter gradient."""
+    from VQCPCB import ops
+    ops.set_gemm_mode(mode)
+    torch.manual_seed(B + T)
+    gru = torch.nn.GRU(inp, H, nl, bias=True, batch_first=True, dropout=0.0).cuda()
+    x = torch.randn(B, T, inp, device='cuda', requires_grad=True)
+    y = ops.gru_forward(gru, x, True)
+    g = torch.randn_like(y)
+    for q in gru.parameters():
+        q.grad = None
+    y.backward(g)
+    ref = torch.nn.GRU(inp, H, nl, bias=True, batch_first=True).double()
+    ref.load_state_dict({k: v.detach().double().cpu() for k, v in gru.state_dict().items()})
+    xr = x.detach().double().cpu().requires_grad_(True)
+    yr, _ = ref(xr)
+    yr.backward(g.double().cpu())
+    tol = 2e-5 if mode == 'fp32' else 2e-4
+    assert rel_err(y, yr) < tol, rel_err(y, yr)
+    assert rel_err(x.grad, xr.grad) < 10 * tol, rel_err(x.grad, xr.grad)
+    for (k, a), (_, b) in zip(gru.named_parameters(), ref.named_parameters()):
+        assert rel_err(a.grad, b.grad) < 10 * tol, (k, rel_err(a.grad, b.grad))
+    ops.set_gemm_mode('bf16x3')
+
+
+def test_native_gru_dropout_replay():
+    """Inter-layer dropout of the GRU (nn.GRU's ``dropout``): explicit keep mask on the first layer's outputs, checked
+    against two stacked single-layer torch GRUs with the same mask in fp64."""
+    from VQCPCB import ops
+    ops.set_gemm_mode('fp32')
+    torch.manual_seed(2)
+    B, T, inp, H, p = 21, 8, 32, 128, 0.3
+    gru = torch.nn.GRU(inp, H, 2, bias=True, batch_first=True, dropout=p).cuda()
+    x = torch.randn(B, T, inp, device='cuda', requires_grad=True)
+    rec = {}
+
+    def hook(site, shape, pp, device):
+        rec[site] = (torch.rand(shape, device=device) >= pp).to(torch.uint8)
+        return rec[site]
+    ops.DROPOUT_MASK_HOOK = hook
+    try:
+        y = ops.gru_forward(gru, x, True)
+        g = torch.randn_like(y)
+        y.backward(g)
+    finally:
+        ops.DROPOUT_MASK_HOOK = None
+    sd = {k: v.detach().double().cpu() for k, v in gru.state_dict().items()}
+    l0 = torch.nn.GRU(inp, H, 1, batch_first=True).double()
+    l1 = torch.nn.GRU(H, H, 1, batch_first=True).double()
+    l0.load_state_dict({k: sd[k] for k in sd if k.endswith('l0')})
+    l1.load_state_dict({k.replace('l1', 'l0'): sd[k] for k in sd if k.endswith('l1')})
+    xr = x.detach().double().cpu().requires_grad_(True)
+    h0, _ = l0(xr)
+    h0 = h0 * rec['gru0'].view(B, T, H).double().cpu() / (1 - p)
+    yr, _ = l1(h0)
+    yr.backward(g.double().cpu())
+    assert rel_err(y, yr) < 2e-5 and rel_err(x.grad, xr.grad) < 2e-4
+    assert rel_err(gru.weight_hh_l0.grad, l0.weight_hh_l0.grad) < 2e-4
+    ops.set_gemm_mode('bf16x3')

@@ -4,8 +4,9 @@ Each block of ``downscale_factors[0]`` tokens is summarised by the last state of
 ``bidirectional``, of a SECOND independent GRU run on the time-flipped block; the concatenated states go through
 ``output_linear``.  State-dict keys are the reference's (``g_enc_fwd.*``, ``g_enc_bwd.*``, ``output_linear.*``).
 
-The recurrences run through ``nn.GRU`` (cuDNN, TF32 off) like the context network (hand-written
-persistent-RNN kernels are the next step); the projection uses the native GEMM.  Dropout between GRU layers is cuDNN's.
+The ``nn.GRU`` modules are parameter containers only: the recurrences run on the native GEMMs + GRU gate kernels
+(``ops.GRUFn``: one input-projection GEMM per layer, one recurrent GEMM + one point-wise kernel per time step), the
+projection on the native GEMM; inter-layer dropout uses explicit keep masks like the rest of the encoder.
 """
 import math
 
@@ -43,8 +44,8 @@ class LstmDownscaler(Downscaler):
         seq_len, input_size = x.shape[-2:]
         batch_dims = x.shape[:-2]
         x = x.reshape(math.prod(batch_dims), seq_len, input_size)
-        last = self.g_enc_fwd(x)[0][:, -1]
+        last = ops.gru_forward(self.g_enc_fwd, x, self.training)[:, -1]
         if self.g_enc_bwd is not None:
-            last = torch.cat([last, self.g_enc_bwd(x.flip(dims=[1]))[0][:, -1]], dim=-1)
+            last = torch.cat([last, ops.gru_forward(self.g_enc_bwd, x.flip(dims=[1]), self.training)[:, -1]], dim=-1)
         z = ops.LinearFn.apply(last, self.output_linear.weight, self.output_linear.bias)
         return z.view(*batch_dims, -1)

@@ -436,6 +436,113 @@ def draw_keep_mask(shape, p, device):
     return (torch.rand(shape, device=device) >= p).to(torch.uint8)
 
 
+class GRUFn(torch.autograd.Function):
+    """Multi-layer GRU, batch_first, zero initial state (torch.nn.GRU semantics; CModule vqcpc_helper.py:54-76 and
+    LstmDownscaler lstm_downscaler.py:31-48) on the native GEMMs + the point-wise gate kernels:
+
+        per layer:  GI = X W_ih^T + b_ih (one GEMM over all (b, t) rows);  per step  GH = h_{t-1} W_hh^T + b_hh (GEMM),
+                    gate kernel -> h_t written into out[:, t] (the next step's GEMM reads it there, row stride T * H)
+        backward :  per step gate kernel + dh_{t-1} = dh_t z + dGH_t W_hh and dW_hh += dGH_t^T h_{t-1} (two GEMMs);
+                    per layer dW_ih, db_ih, db_hh, dX from the stacked dGI / dGH
+
+    meta = (num_layers, hidden, p, masks): inter-layer dropout (nn.GRU's ``dropout``) with explicit keep masks
+    ((B * T, hidden) uint8 per layer boundary, or None).  params = (w_ih, w_hh, b_ih, b_hh) per layer; their gradients
+    are accumulated in place (flat-buffer views) like every other native op."""
+
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        nl, H, p, masks = meta
+        x = _f32c(x)
+        B, T, _ = x.shape
+        prm = [q.detach() for q in params]
+        train = any(ctx.needs_input_grad)
+        dev = x.device
+        saved = []
+        inp = x.reshape(B * T, -1)
+        out = None
+        for l in range(nl):
+            wih, whh, bih, bhh = prm[4 * l:4 * l + 4]
+            gi = linear_fwd(inp, wih, bih)
+            out = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+            gates = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev) if train else None
+            ghn = torch.empty(B * T, H, dtype=torch.float32, device=dev) if train else None
+            gh0 = bhh.expand(B, 3 * H).contiguous()              # h_{-1} = 0: GH = b_hh
+            gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
+            for t in range(T):
+                hp = out[:, t - 1, :] if t > 0 else None
+                if t > 0:
+                    gemm(hp, whh, B, 3 * H, H, out=gh, bias=bhh, b_is_weight=True)
+                _native.call('vqcpc_gru_gate_fwd', _p(gi), _p(gh if t > 0 else gh0), _p(hp), T * H, _p(out), _p(gates), _p(ghn),
+                             B, T, H, t, _stream())
+            layer_in = inp
+            inp = out.view(B * T, H)
+            mask = None
+            if l < nl - 1 and p > 0 and masks is not None:
+                mask = masks[l]
+                dropped = torch.empty_like(inp)
+                _native.call('vqcpc_mask_scale', _p(inp), _p(mask), 1.0 / (1.0 - p), _p(dropped), inp.numel(), _stream())
+                inp = dropped
+            if train:
+                saved.append((layer_in, out, gates, ghn, mask))
+        ctx.meta = (nl, H, p, B, T)
+        ctx.params = params
+        ctx.saved = saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        nl, H, p, B, T = ctx.meta
+        params = ctx.params
+        prm = [q.detach() for q in params]
+        grads = [_grad_buf(q) if q.requires_grad else torch.zeros_like(q) for q in params]
+        dout = _f32c(dout)
+        dev = dout.device
+        dx = None
+        for l in reversed(range(nl)):
+            wih, whh, bih, bhh = prm[4 * l:4 * l + 4]
+            g_wih, g_whh, g_bih, g_bhh = grads[4 * l:4 * l + 4]
+            layer_in, out, gates, ghn, mask = ctx.saved[l]
+            if mask is not None:                                 # dropout sat on this layer's output
+                dm = torch.empty_like(dout)
+                _native.call('vqcpc_mask_scale', _p(dout), _p(mask), 1.0 / (1.0 - p), _p(dm), dout.numel(), _stream())
+                dout = dm
+            dgi = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev)
+            dgh = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev)
+            dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
+            dgh3 = dgh.view(B, T, 3 * H)
+            for t in range(T - 1, -1, -1):
+                hp = out[:, t - 1, :] if t > 0 else None
+                _native.call('vqcpc_gru_gate_bwd', _p(gates), _p(ghn), _p(hp), T * H, _p(dh), _p(dout), _p(dgi), _p(dgh),
+                             B, T, H, t, _stream())
+                if t > 0:
+                    # dh_{t-1} = dh_t z + dGH_t W_hh ;  dW_hh += dGH_t^T h_{t-1}
+                    dh = linear_bwd(hp, whh, dgh3[:, t, :], g_whh, None, dx_residual=dh)
+            colsum(dgh, g_bhh)
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            dx = linear_bwd(layer_in, wih, dgi, g_wih, g_bih, need_dx=need_dx)
+            ctx.saved[l] = None
+            if l > 0:
+                dout = dx.view(B, T, H)
+        ctx.saved = None
+        dx_in = dx.view(B, T, -1) if ctx.needs_input_grad[0] else None
+        return (dx_in, None) + (None,) * len(params)
+
+
+def gru_forward(gru, x, training):
+    """Run a torch.nn.GRU *parameter container* (batch_first, unidirectional) through GRUFn."""
+    assert gru.batch_first and not gru.bidirectional and gru.bias
+    nl, H, p = gru.num_layers, gru.hidden_size, float(gru.dropout) if training else 0.0
+    B, T, _ = x.shape
+    masks = None
+    if p > 0 and nl > 1:
+        masks = [dropout_mask(f'gru{l}', (B * T, H), p, x.device) for l in range(nl - 1)]
+    params = []
+    for l in range(nl):
+        params += [getattr(gru, f'weight_ih_l{l}'), getattr(gru, f'weight_hh_l{l}'), getattr(gru, f'bias_ih_l{l}'),
+                   getattr(gru, f'bias_hh_l{l}')]
+    return GRUFn.apply(x, (nl, H, p, masks), *params)
+
+
 class QuantizeFn(torch.autograd.Function):
     """quantizer/vector_quantizer.py:104-157 — search (or given indices), gather, loss, straight-through output."""
 

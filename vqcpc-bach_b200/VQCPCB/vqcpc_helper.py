@@ -29,8 +29,8 @@ def quantization_loss(loss_quantization_left, loss_quantization_negative, loss_q
 class CModule(nn.Module):
     """Autoregressive context: multi-layer GRU over the left codes, last step, Linear (vqcpc_helper.py:54-76).
 
-    The recurrence runs through ``nn.GRU`` (cuDNN) for now: it is 0.1 % of the step FLOPs and listed as the first
-    'next' row of SURVEY.md §8f; the output projection uses the native GEMM."""
+    ``g_ar_fwd`` is an ``nn.GRU`` used as the parameter container (same state_dict keys as the reference); the
+    recurrence itself runs on the native GEMMs + GRU gate kernels (``ops.GRUFn``), not on cuDNN."""
 
     def __init__(self, input_dim, hidden_size, output_dim, num_layers, dropout):
         super().__init__()
@@ -39,7 +39,8 @@ class CModule(nn.Module):
         self.output_linear = nn.Linear(hidden_size, output_dim)
 
     def forward(self, zs, h):
-        c, _ = self.g_ar_fwd(zs, h)
+        assert h is None, 'the context network always starts from a zero state (vqcpc_encoder_trainer.py:237)'
+        c = ops.gru_forward(self.g_ar_fwd, zs, self.training)
         return ops.LinearFn.apply(c[:, -1], self.output_linear.weight, self.output_linear.bias)
 
 
