@@ -365,6 +365,11 @@ def run_ours(args):
         del dev_batches
         torch.cuda.empty_cache()
         qi = bench_quantizer_infonce(B)
+    if world > 1:
+        try:
+            torch.distributed.destroy_process_group()
+        except Exception:
+            pass
     if rank != 0:
         return
     pk = peaks()
