@@ -1,7 +1,7 @@
 """vqcpc_b200: B200-native VQ-CPC encoder-training hot path behind the reference's ``VQCPCB`` class surface."""
 import torch as _torch
 
-# The only library kernels left on the path are cuDNN's GRU (CModule).  cuDNN RNNs default to TF32 tensor-core math,
-# which costs ~1e-3 relative error in the context vector and every gradient that flows through it; the parity bar is
-# 1e-4, so keep the recurrence in fp32.  (Our own GEMMs never use TF32: fp32 FMA or the bf16x3 split.)
+# The GRUs run on the native kernels (ops.GRUFn); their nn.GRU modules are parameter containers only.  Should a caller
+# ever invoke one directly, keep cuDNN away from TF32: it costs ~1e-3 relative error in the context vector and the parity
+# bar is 1e-4.  (Our own GEMMs never use TF32: fp32 FMA or the bf16x3 split.)
 _torch.backends.cudnn.allow_tf32 = False
