@@ -180,14 +180,16 @@ int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos, const 
  * The products GI = X W_ih^T + b_ih (all steps at once) and GH = h_{t-1} W_hh^T + b_hh (per step) are vqcpc_gemm_* calls;
  * these are the point-wise stages of step t, gate order (r, z, n), batch-first layouts: gi (B*T, 3H) rows b*T + t,
  * gh (B, 3H), h_prev (B, H) with row stride hprev_ld (NULL = zero state), out (B, T, H) written at [:, t],
- * gates (B*T, 3H) and ghn (B*T, H) saved for backward (both NULL for inference). */
-int vqcpc_gru_gate_fwd(const float* gi, const float* gh, const float* h_prev, int64_t hprev_ld, float* out, float* gates,
-                       float* ghn, int B, int T, int H, int t, void* stream);
+ * gates (B*T, 3H) and ghn (B*T, H) saved for backward (both NULL for inference); out_hi / out_lo: optional bf16 split
+ * of h_t (same layout as out), which the next step's tensor-core GEMM reads directly. */
+int vqcpc_gru_gate_fwd(const float* gi, const float* gh, const float* h_prev, int64_t hprev_ld, float* out, void* out_hi,
+                       void* out_lo, float* gates, float* ghn, int B, int T, int H, int t, void* stream);
 /* dh (B, H): recurrent part of the gradient wrt h_t on entry (the upstream d_out[:, t], (B, T, H) or NULL, is added here),
  * overwritten with (dh + d_out_t) * z (the caller adds dGH_t W_hh to obtain the gradient wrt h_{t-1}); d_gi / d_gh
- * (B*T, 3H) receive the gradients of GI_t / GH_t at rows b*T + t. */
+ * (B*T, 3H) receive the gradients of GI_t / GH_t at rows b*T + t; d_gh may be given as fp32 and / or as its bf16 split. */
 int vqcpc_gru_gate_bwd(const float* gates, const float* ghn, const float* h_prev, int64_t hprev_ld, float* dh,
-                       const float* d_out, float* d_gi, float* d_gh, int B, int T, int H, int t, void* stream);
+                       const float* d_out, float* d_gi, float* d_gh, void* d_gh_hi, void* d_gh_lo, int B, int T, int H,
+                       int t, void* stream);
 
 /* ---- optimizer tail (clip_grad_norm_(…, 5) + Adam: vqcpc_encoder_trainer.py:92, :313-314) ----------------------
  * out[0] = ||grad_scale * g||_2^2 (device scalar, deterministic). */

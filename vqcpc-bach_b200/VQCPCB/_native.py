@@ -48,8 +48,8 @@ SIGNATURES = {
     'vqcpc_infonce_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_set_algo': [_I],
     'vqcpc_infonce_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-    'vqcpc_gru_gate_fwd': [_P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P],
-    'vqcpc_gru_gate_bwd': [_P, _P, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'vqcpc_gru_gate_fwd': [_P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'vqcpc_gru_gate_bwd': [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     'vqcpc_grad_sumsq': [_P, _L, _F, _P, _P],
     'vqcpc_clip_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _I, _P],
 }

@@ -458,12 +458,19 @@ class GRUFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad)
         dev = x.device
         saved = []
-        inp = x.reshape(B * T, -1)
+        inp, inp_sp = x.reshape(B * T, -1), None
         out = None
+        tc = tensor_core_mode() and _tc_ok(B, 3 * H, H, None, None, True, True)
         for l in range(nl):
             wih, whh, bih, bhh = prm[4 * l:4 * l + 4]
-            gi = linear_fwd(inp, wih, bih)
+            if inp_sp is not None:
+                gi = gemm(None, wih, B * T, 3 * H, inp.shape[1], bias=bih, b_is_weight=True, a_split=inp_sp)
+            else:
+                gi = linear_fwd(inp, wih, bih)
             out = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+            # tensor-core mode: the gate kernel also writes the bf16 split of h_t, read by the next step's GEMM (row stride
+            # T * H), by the next layer's input projection and by the weight-gradient GEMMs of backward
+            osp = (torch.empty(B, T, H, dtype=torch.bfloat16, device=dev), torch.empty(B, T, H, dtype=torch.bfloat16, device=dev)) if tc else None
             gates = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev) if train else None
             ghn = torch.empty(B * T, H, dtype=torch.float32, device=dev) if train else None
             gh0 = bhh.expand(B, 3 * H).contiguous()              # h_{-1} = 0: GH = b_hh
@@ -471,27 +478,31 @@ class GRUFn(torch.autograd.Function):
             for t in range(T):
                 hp = out[:, t - 1, :] if t > 0 else None
                 if t > 0:
-                    gemm(hp, whh, B, 3 * H, H, out=gh, bias=bhh, b_is_weight=True)
-                _native.call('vqcpc_gru_gate_fwd', _p(gi), _p(gh if t > 0 else gh0), _p(hp), T * H, _p(out), _p(gates), _p(ghn),
-                             B, T, H, t, _stream())
-            layer_in = inp
+                    if tc:
+                        gemm(None, whh, B, 3 * H, H, out=gh, bias=bhh, b_is_weight=True, a_split=(osp[0][:, t - 1, :], osp[1][:, t - 1, :]))
+                    else:
+                        gemm(hp, whh, B, 3 * H, H, out=gh, bias=bhh, b_is_weight=True)
+                _native.call('vqcpc_gru_gate_fwd', _p(gi), _p(gh if t > 0 else gh0), _p(hp), T * H, _p(out),
+                             _p(osp[0]) if tc else None, _p(osp[1]) if tc else None, _p(gates), _p(ghn), B, T, H, t, _stream())
+            layer_in, layer_in_sp = inp, inp_sp
             inp = out.view(B * T, H)
+            inp_sp = (osp[0].view(B * T, H), osp[1].view(B * T, H)) if tc else None
             mask = None
             if l < nl - 1 and p > 0 and masks is not None:
                 mask = masks[l]
                 dropped = torch.empty_like(inp)
                 _native.call('vqcpc_mask_scale', _p(inp), _p(mask), 1.0 / (1.0 - p), _p(dropped), inp.numel(), _stream())
-                inp = dropped
+                inp, inp_sp = dropped, None
             if train:
-                saved.append((layer_in, out, gates, ghn, mask))
-        ctx.meta = (nl, H, p, B, T)
+                saved.append((layer_in, layer_in_sp, out, osp, gates, ghn, mask))
+        ctx.meta = (nl, H, p, B, T, tc)
         ctx.params = params
         ctx.saved = saved
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        nl, H, p, B, T = ctx.meta
+        nl, H, p, B, T, tc = ctx.meta
         params = ctx.params
         prm = [q.detach() for q in params]
         grads = [_grad_buf(q) if q.requires_grad else torch.zeros_like(q) for q in params]
@@ -501,25 +512,38 @@ class GRUFn(torch.autograd.Function):
         for l in reversed(range(nl)):
             wih, whh, bih, bhh = prm[4 * l:4 * l + 4]
             g_wih, g_whh, g_bih, g_bhh = grads[4 * l:4 * l + 4]
-            layer_in, out, gates, ghn, mask = ctx.saved[l]
+            layer_in, layer_in_sp, out, osp, gates, ghn, mask = ctx.saved[l]
             if mask is not None:                                 # dropout sat on this layer's output
                 dm = torch.empty_like(dout)
                 _native.call('vqcpc_mask_scale', _p(dout), _p(mask), 1.0 / (1.0 - p), _p(dm), dout.numel(), _stream())
                 dout = dm
             dgi = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev)
-            dgh = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev)
             dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
-            dgh3 = dgh.view(B, T, 3 * H)
+            if tc:
+                dgh = None
+                dsp = (torch.empty(B, T, 3 * H, dtype=torch.bfloat16, device=dev), torch.empty(B, T, 3 * H, dtype=torch.bfloat16, device=dev))
+            else:
+                dgh = torch.empty(B * T, 3 * H, dtype=torch.float32, device=dev)
+                dgh3 = dgh.view(B, T, 3 * H)
             for t in range(T - 1, -1, -1):
                 hp = out[:, t - 1, :] if t > 0 else None
                 _native.call('vqcpc_gru_gate_bwd', _p(gates), _p(ghn), _p(hp), T * H, _p(dh), _p(dout), _p(dgi), _p(dgh),
-                             B, T, H, t, _stream())
+                             _p(dsp[0]) if tc else None, _p(dsp[1]) if tc else None, B, T, H, t, _stream())
                 if t > 0:
                     # dh_{t-1} = dh_t z + dGH_t W_hh ;  dW_hh += dGH_t^T h_{t-1}
-                    dh = linear_bwd(hp, whh, dgh3[:, t, :], g_whh, None, dx_residual=dh)
-            colsum(dgh, g_bhh)
+                    if tc:
+                        dh = linear_bwd(None, whh, None, g_whh, None, dx_residual=dh, shape=(B, H),
+                                        x_split=(osp[0][:, t - 1, :], osp[1][:, t - 1, :]),
+                                        dy_split=(dsp[0][:, t, :], dsp[1][:, t, :]))
+                    else:
+                        dh = linear_bwd(hp, whh, dgh3[:, t, :], g_whh, None, dx_residual=dh)
+            if tc:
+                _native.call('vqcpc_colsum_split', _p(dsp[0]), _p(dsp[1]), 3 * H, _p(g_bhh), B * T, 3 * H, _stream())
+            else:
+                colsum(dgh, g_bhh)
             need_dx = l > 0 or ctx.needs_input_grad[0]
-            dx = linear_bwd(layer_in, wih, dgi, g_wih, g_bih, need_dx=need_dx)
+            dx = linear_bwd(layer_in if layer_in_sp is None else None, wih, dgi, g_wih, g_bih, need_dx=need_dx,
+                            x_split=layer_in_sp, shape=tuple(layer_in.shape))
             ctx.saved[l] = None
             if l > 0:
                 dout = dx.view(B, T, H)
