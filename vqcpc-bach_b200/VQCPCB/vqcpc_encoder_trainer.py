@@ -60,8 +60,10 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         self.scheduler = None
         self.flat = None
         self.max_grad_norm = 5.0
-        # micro-batching: at most this many 16-token blocks per forward/backward pass
-        self.max_blocks_per_pass = int(os.environ.get('VQCPC_MAX_BLOCKS_PER_PASS', 17408))
+        # micro-batching: at most this many 16-token blocks per forward/backward pass (256 samples of the headline config,
+        # ~30 GB of saved activations; measured on B200: 17408 -> 2951, 34816 -> 3084, 69632 -> 3083, 139264 -> 3049
+        # samples/s - larger passes amortise the launch-bound GRU steps, the largest run into the power cap)
+        self.max_blocks_per_pass = int(os.environ.get('VQCPC_MAX_BLOCKS_PER_PASS', 34816))
         self.is_main_process = vq_dist.rank() == 0
         self.last_grad_norm_sq = None
         self.distributed = True     # False: ignore an initialised process group (single-process reference runs)
