@@ -270,19 +270,33 @@ colsum_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xh,
   int64_t r0 = blockIdx.y * rows_per_cta;
   int64_t r1 = min(M, r0 + rows_per_cta);
   float4 a = make_float4(0, 0, 0, 0);
+  auto load_row = [&](int64_t r) -> float4 {
+    float4 v;
+    if (SPLIT) {
+      uint2 h = *reinterpret_cast<const uint2*>(xh + r * ld + col);
+      uint2 l = *reinterpret_cast<const uint2*>(xl + r * ld + col);
+      v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+      v.y = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
+      v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+      v.w = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
+    } else {
+      v = ld4(x + r * ld + col);
+    }
+    return v;
+  };
   if (col < N) {
-    for (int64_t r = r0 + w; r < r1; r += 8) {
-      float4 v;
-      if (SPLIT) {
-        uint2 h = *reinterpret_cast<const uint2*>(xh + r * ld + col);
-        uint2 l = *reinterpret_cast<const uint2*>(xl + r * ld + col);
-        v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-        v.y = __uint_as_float(h.x & 0xFFFF0000u) + __uint_as_float(l.x & 0xFFFF0000u);
-        v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-        v.w = __uint_as_float(h.y & 0xFFFF0000u) + __uint_as_float(l.y & 0xFFFF0000u);
-      } else {
-        v = ld4(x + r * ld + col);
-      }
+    // eight independent row loads in flight per warp (a warp-wide row segment is 512 B): with ~32 warps per SM that is
+    // well above the ~45 KB per SM an HBM-bound stream needs; the plain loop had one load in flight per warp
+    int64_t r = r0 + w;
+    for (; r + 56 < r1; r += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = load_row(r + 8 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    }
+    for (; r < r1; r += 8) {
+      const float4 v = load_row(r);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
   }
