@@ -163,3 +163,32 @@ def test_vq_fused_bwd_matches_autograd(D, n, Kc, squared):
     assert rel(dz, dz_ref) < 1e-5, rel(dz, dz_ref)
     assert rel(dT, dT_ref) < 1e-5, rel(dT, dT_ref)
     assert rel(dE, Er.grad) < 1e-4, rel(dE, Er.grad)
+
+
+def test_vq_tc_randomized_sweep():
+    """Property sweep: 24 random problems (vector / codebook scales over six orders of magnitude, clustered and
+    data-drawn codebooks, shifted means, D = 3 and 4, ragged n) - the tensor-core search and the direct scan must agree on
+    every index and the usage histogram every time."""
+    g = torch.Generator(device='cuda')
+    g.manual_seed(2024)
+    bad = []
+    for trial in range(24):
+        D = 3 if trial % 3 else 4
+        Kc = [512, 300, 1024, 64][trial % 4]
+        n = 100000 + 37 * trial
+        zs = 10.0 ** ((trial % 7) - 3)
+        es = 10.0 ** (((trial * 5) % 7) - 3)
+        z = torch.randn(n, D, device='cuda', generator=g) * zs + (0.5 * zs if trial % 2 else 0.0)
+        if trial % 5 == 0:
+            E = z[torch.randperm(n, device='cuda', generator=g)[:Kc]].contiguous()            # data-dependent init
+        elif trial % 5 == 1:
+            centers = torch.randn(8, D, device='cuda', generator=g) * es
+            E = (centers[torch.randint(0, 8, (Kc,), device='cuda', generator=g)] +
+                 1e-3 * es * torch.randn(Kc, D, device='cuda', generator=g)).contiguous()      # tight clusters: many near-ties
+        else:
+            E = (torch.randn(Kc, D, device='cuda', generator=g) * es).contiguous()
+        T = torch.randn(Kc, 32, device='cuda', generator=g)
+        r1, r2 = run_fused(z, E, T, 1), run_fused(z, E, T, 2)
+        if not (torch.equal(r1['idx'], r2['idx']) and torch.equal(r1['counts'], r2['counts']) and torch.equal(r1['y'], r2['y'])):
+            bad.append((trial, D, Kc, zs, es, int((r1['idx'] != r2['idx']).sum())))
+    assert not bad, bad
