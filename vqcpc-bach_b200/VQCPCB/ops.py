@@ -433,7 +433,7 @@ class DropoutFn(torch.autograd.Function):
 
 def draw_keep_mask(shape, p, device):
     """Bernoulli(1 - p) keep mask as uint8 from torch's CUDA generator (reproducible with torch.manual_seed)."""
-    return (torch.rand(shape, device=device) >= p).to(torch.uint8)
+    return torch.empty(shape, dtype=torch.uint8, device=device).bernoulli_(1.0 - p)     # one kernel, one byte per element
 
 
 class GRUFn(torch.autograd.Function):
