@@ -122,6 +122,10 @@ int vqcpc_attn_bwd(const float* qkv, const float* e1, const float* e2, const flo
                    float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P, int L, int H,
                    int head_dim, float q_scale, int keep, void* stream);
 
+/* Attention kernel choice (process-wide): 0 = tensor cores (mma.sync 3xTF32, ~2^-20 per product; default), 1 = CUDA cores
+ * (plain fp32 FMA; what the Python side selects in the exact 'fp32' GEMM mode). */
+int vqcpc_attn_set_fwd_algo(int algo);
+int vqcpc_attn_set_bwd_algo(int algo);
 /* Same with dropout on the attention weights (F.dropout at multihead_attention_custom.py:339): drop_keep (P, H, L, L) uint8
  * keep mask or NULL, drop_scale = 1 / (1 - p).  `probs` always holds the softmax output; the mask acts on the P.V product
  * (forward) and on dA / dV (backward). */

@@ -37,6 +37,8 @@ SIGNATURES = {
     'vqcpc_gemm_set_tile_config': [_I],
     'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
+    'vqcpc_attn_set_fwd_algo': [_I],
+    'vqcpc_attn_set_bwd_algo': [_I],
     'vqcpc_attn_fwd_ex': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _F, _P],
     'vqcpc_attn_bwd_ex': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P, _F, _P],
     'vqcpc_vq_search': [_P, _L, _I, _P, _I, _I, _P, _P],

@@ -281,9 +281,26 @@ def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta, want_split=False):
     return dy
 
 
-def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, want_split=False, drop=None):
+_ATTN_ALGO = {'fwd': None, 'bwd': None}          # kernels currently selected in the library (None = not set yet)
+
+
+def _select_attn_kernel(which, algo=None):
+    """Attention kernels: tensor cores (mma.sync 3xTF32, ~2^-20 per product) in the tensor-core GEMM modes, the CUDA-core
+    fp32 kernels in the exact 'fp32' mode (whose parity tests hold every gradient to the fp32 noise floor).
+    VQCPC_ATTN_FWD_ALGO / VQCPC_ATTN_BWD_ALGO = 0|1 override (tuning hooks); ``algo`` overrides both (tests)."""
+    if algo is None:
+        env = os.environ.get('VQCPC_ATTN_%s_ALGO' % which.upper())
+        algo = int(env) if env else (1 if _GEMM_MODE == 'fp32' else 0)
+    if _ATTN_ALGO[which] != algo:
+        _native.call('vqcpc_attn_set_%s_algo' % which, int(algo))
+        _ATTN_ALGO[which] = int(algo)
+
+
+def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, want_split=False, drop=None, algo=None):
     """-> (out fp32 | None, probs) or (out | None, (hi, lo), probs) when want_split; rows = P * L / keep.
-    drop = (keep_mask uint8 (P, H, L, L), scale): dropout on the attention weights."""
+    drop = (keep_mask uint8 (P, H, L, L), scale): dropout on the attention weights.
+    algo: None = by GEMM mode (see _select_attn_kernel), 0 = tensor cores, 1 = CUDA cores."""
+    _select_attn_kernel('fwd', algo)
     Mo = P * (L // keep)
     out = torch.empty(Mo, H * hd, dtype=torch.float32, device=qkv.device) if want_fp32 else None
     sp = _split_buffers(Mo, H * hd, qkv.device) if want_split else (None, None)
@@ -295,7 +312,9 @@ def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, 
     return out, probs
 
 
-def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False, drop=None):
+def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False, drop=None,
+             algo=None):
+    _select_attn_kernel('bwd', algo)
     dqkv = torch.empty_like(qkv) if want_fp32 else None
     sp = _split_buffers(qkv.shape[0], qkv.shape[1], qkv.device) if want_split else (None, None)
     _native.call('vqcpc_attn_bwd_ex', _p(qkv), _p(e1), _p(e2), _p(probs), _p(dout), _p(dqkv), _p(sp[0]), _p(sp[1]), _p(de1), _p(de2),

@@ -177,6 +177,206 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Forward on the tensor cores: mma.sync.m16n8k8 TF32 with the 3xTF32 error compensation (x = big + small, both TF32;
+// D += a_small b_big + a_big b_small + a_big b_big: ~2^-20 relative to |a||b| per product, 16x coarser than fp32 FMA;
+// the exact-fp32 GEMM mode therefore keeps the CUDA-core kernel).  The CUDA-core kernel above is
+// bound by shared-memory bandwidth (17 LDS.128 per 8 dot products of the fused q.(k + E) form, ncu: l1tex 84 %); here
+// the skewed bias is separated into two small matrix products over the relative tables,
+//     S = Q K^T,   R1 = Q E1^T,   R2 = Q E2^T   (16 x 16, 16 x L, 16 x L),   S[i][j] += (j <= i ? R1[i][L-1-(i-j)] : R2[i][j-i])
+// fragments are read with conflict-free LDS.32 (row stride 68 floats), the Q fragment of a k-step is split once and
+// reused by all three products, and P V is a fourth product after the softmax.  ~8x less shared-memory traffic per tile.
+constexpr int PSM = 20;   // padded stride of the 16 x 16 scratch matrices
+
+// x = big + small with big = x rounded to TF32 (10 explicit mantissa bits, nearest, ties away: one integer add + mask on
+// the bit pattern; inf stays inf) and small = x - big (exact in fp32).  The tensor core ignores the low 13 mantissa bits of
+// a .tf32 operand, so small is used as is: |x - big - tf32(small)| <= 2^-21 |x|.  (cvt.rna.tf32.f32 is emulated with ~5
+// integer instructions on sm_100; at 336 conversions per tile it was 60 % of the kernel's instructions.)
+__device__ __forceinline__ void tf32_split(float x, uint32_t& big, uint32_t& small) {
+  big = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  small = __float_as_uint(x - __uint_as_float(big));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A B with A given as (big, small) fragments and B as fp32 values split here
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], float b0f, float b1f) {
+  uint32_t b0b, b0s, b1b, b1s;
+  tf32_split(b0f, b0b, b0s);
+  tf32_split(b1f, b1b, b1s);
+  mma_tf32(c, as, b0b, b1b);
+  mma_tf32(c, ab, b0s, b1s);
+  mma_tf32(c, ab, b0b, b1b);
+}
+
+template <int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
+                    float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                    float* __restrict__ probs, int64_t M, int H, int64_t ntiles, int keep,
+                    const unsigned char* __restrict__ drop_keep, float drop_scale) {
+  constexpr int NTR = (L + 7) / 8;                 // n-tiles of the relative-table products
+  extern __shared__ __align__(16) float smem[];
+  float* e1s = smem;                               // [16][TS], rows >= L zero
+  float* e2s = e1s + TR * TS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = e2s + TR * TS + warp * (3 * TR * TS);
+  float* ks = qs + TR * TS;
+  float* vs = ks + TR * TS;
+  float* r1s = qs;                                 // after the three Q products the q tile is scratch:
+  float* r2s = qs + TR * PSM;                      //   R1, R2 (16 x 16) and the probabilities P (16 x 16)
+  float* ps = qs + 2 * TR * PSM;
+  const int h = blockIdx.y;
+  const int d = H * HD;
+  for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
+    int r = i / 16, c = (i % 16) * 4;
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if (r < L) {
+      a = ld4(e1 + ((size_t)h * L + r) * HD + c);
+      b = ld4(e2 + ((size_t)h * L + r) * HD + c);
+    }
+    st4(e1s + r * TS + c, a);
+    st4(e2s + r * TS + c, b);
+  }
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
+  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
+    const int64_t row0 = tile * TR;
+    __syncwarp();
+    load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
+    load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
+    load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
+    __syncwarp();
+    float sc[2][4], ra[NTR][4], rb[NTR][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) sc[n][x] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NTR; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) { ra[n][x] = 0.f; rb[n][x] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      // Q as the A fragment of this k-step, split once and shared by the three products
+      uint32_t qb[4], qsm[4];
+      tf32_split(qs[g * TS + kk * 8 + t], qb[0], qsm[0]);
+      tf32_split(qs[(g + 8) * TS + kk * 8 + t], qb[1], qsm[1]);
+      tf32_split(qs[g * TS + kk * 8 + t + 4], qb[2], qsm[2]);
+      tf32_split(qs[(g + 8) * TS + kk * 8 + t + 4], qb[3], qsm[3]);
+#pragma unroll
+      for (int n = 0; n < 2; ++n)                   // S = Q K^T : B[k][n] = K[n][k]
+        mma_3x(sc[n], qb, qsm, ks[(n * 8 + g) * TS + kk * 8 + t], ks[(n * 8 + g) * TS + kk * 8 + t + 4]);
+#pragma unroll
+      for (int n = 0; n < NTR; ++n) {               // R1 = Q E1^T, R2 = Q E2^T
+        mma_3x(ra[n], qb, qsm, e1s[(n * 8 + g) * TS + kk * 8 + t], e1s[(n * 8 + g) * TS + kk * 8 + t + 4]);
+        mma_3x(rb[n], qb, qsm, e2s[(n * 8 + g) * TS + kk * 8 + t], e2s[(n * 8 + g) * TS + kk * 8 + t + 4]);
+      }
+    }
+    __syncwarp();                                   // every lane is done with the q tile: it becomes scratch
+    // ---- R1 / R2 to scratch (C layout: rows g, g + 8; cols n*8 + 2t, +1)
+#pragma unroll
+    for (int n = 0; n < NTR; ++n) {
+      r1s[g * PSM + n * 8 + 2 * t] = ra[n][0]; r1s[g * PSM + n * 8 + 2 * t + 1] = ra[n][1];
+      r1s[(g + 8) * PSM + n * 8 + 2 * t] = ra[n][2]; r1s[(g + 8) * PSM + n * 8 + 2 * t + 1] = ra[n][3];
+      r2s[g * PSM + n * 8 + 2 * t] = rb[n][0]; r2s[g * PSM + n * 8 + 2 * t + 1] = rb[n][1];
+      r2s[(g + 8) * PSM + n * 8 + 2 * t] = rb[n][2]; r2s[(g + 8) * PSM + n * 8 + 2 * t + 1] = rb[n][3];
+    }
+    __syncwarp();
+    // ---- bias + block mask + softmax; this lane holds rows g and g + 8, columns n*8 + 2t + {0, 1}
+    float pv[2][4];                                 // [n][c0 c1 (row g), c2 c3 (row g + 8)]
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int r = g + (x >> 1) * 8, c = n * 8 + 2 * t + (x & 1);
+        const int i = r % L, j = c % L;
+        float v = -INFINITY;
+        if (r / L == c / L) v = sc[n][x] + ((j <= i) ? r1s[r * PSM + (L - 1 - (i - j))] : r2s[r * PSM + (j - i)]);
+        pv[n][x] = v;
+        mx[x >> 1] = fmaxf(mx[x >> 1], v);
+      }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+    }
+    float sm[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        pv[n][x] = expf(pv[n][x] - mx[x >> 1]);     // exp(-inf) = 0 outside the block
+        sm[x >> 1] += pv[n][x];
+      }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], 1);
+      sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], 2);
+      sm[rr] = 1.f / sm[rr];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int r = g + (x >> 1) * 8, c = n * 8 + 2 * t + (x & 1);
+        float a = pv[n][x] * sm[x >> 1];
+        const int64_t gr = row0 + r;
+        const int i = r % L;
+        if (gr < M && (i % keep) == 0 && r / L == c / L) {
+          const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
+          if (probs != nullptr) probs[pi] = a;
+          if (drop_keep != nullptr) a = drop_keep[pi] ? a * drop_scale : 0.f;
+        }
+        ps[r * PSM + c] = a;
+      }
+    __syncwarp();
+    // ---- O = P V  (16 x 64): A fragments from the P scratch, B[k][n] = V[k][n]
+    float oc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) oc[n][x] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t pb[4], psm_[4];
+      tf32_split(ps[g * PSM + kk * 8 + t], pb[0], psm_[0]);
+      tf32_split(ps[(g + 8) * PSM + kk * 8 + t], pb[1], psm_[1]);
+      tf32_split(ps[g * PSM + kk * 8 + t + 4], pb[2], psm_[2]);
+      tf32_split(ps[(g + 8) * PSM + kk * 8 + t + 4], pb[3], psm_[3]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+        mma_3x(oc[n], pb, psm_, vs[(kk * 8 + t) * TS + n * 8 + g], vs[(kk * 8 + t + 4) * TS + n * 8 + g]);
+    }
+    // ---- store rows g and g + 8 (kept query rows only), two consecutive features per fragment half
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = g + rr * 8;
+      const int64_t gr = row0 + r;
+      const int i = r % L;
+      if (gr < M && (i % keep) == 0) {
+        const int64_t orow = (gr / L) * (L / keep) + i / keep;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const int64_t off = orow * d + h * HD + n * 8 + 2 * t;
+          const float v0 = oc[n][rr * 2], v1 = oc[n][rr * 2 + 1];
+          if (out) *reinterpret_cast<float2*>(out + off) = make_float2(v0, v1);
+          if (out_hi) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            *reinterpret_cast<__nv_bfloat162*>(out_hi + off) = __nv_bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162*>(out_lo + off) =
+                __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward: reads the saved probabilities A (nothing is recomputed).
 //   dA = dO V^T ; dS = A * (dA - rowsum(A*dA)) ; dQ~ = dS K + T1 e1 + T2 e2 ; dK = dS^T Q~ ; dV = A^T dO ;
 //   dE1 = T1^T Q~ ; dE2 = T2^T Q~ ; dq = q_scale * dq~
@@ -422,23 +622,318 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Backward on the tensor cores (mma.sync.m16n8k8 3xTF32, see the forward): the same seven products as above, as 384 MMAs
+// per (tile, head) instead of ~4100 FMAs + ~400 LDS.128 per lane.
+//   (1) dA = dO V^T            features are the contraction index
+//   (2) dS = A * (dA - rowsum(A * dA)) on the accumulator fragment; A', dS, T1, T2 (16 x 16) go to shared memory
+//   (3) dQ~ = dS K + T1 e1 + T2 e2          (4) dK = dS^T Q~      (5) dV = A'^T dO      (6) dE1 += T1^T Q~, dE2 += T2^T Q~
+// Index permutations keep every shared-memory access a 128-bit one:
+//   * where the 64 features are contracted (1), the k-step kk = 2j + s pairs logical columns (t, t + 4) with the physical
+//     features 16j + 4t + 2s, + 1 in BOTH operands, so one LDS.128 feeds two k-steps;
+//   * where the features are the output columns (3)-(6), column g of n-tile n is the physical feature 8g + n, so the B
+//     fragments of all eight n-tiles are two LDS.128 and a lane ends up with 16 consecutive output features per row
+//     (64-byte global stores).
+// (4) and (6) share the split Q~ fragments.  The relative tables' gradients stay in registers for the whole kernel.
+__device__ __forceinline__ void mma_3x_pre(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t b0b,
+                                           uint32_t b0s, uint32_t b1b, uint32_t b1s) {
+  mma_tf32(c, as, b0b, b1b);
+  mma_tf32(c, ab, b0s, b1s);
+  mma_tf32(c, ab, b0b, b1b);
+}
+
+// B fragments of one k-step for all eight n-tiles in the "features are output columns" layout: rows k0 + t and k0 + t + 4
+// of a [16][TS] tile, physical features 8g .. 8g + 7; bb/bs[n] = split of row k0 + t, cb/cs[n] = split of row k0 + t + 4.
+__device__ __forceinline__ void load_bfrag_n(const float* __restrict__ Y, int k0, int g, int t, uint32_t (&bb)[8], uint32_t (&bs)[8],
+                                             uint32_t (&cb)[8], uint32_t (&cs)[8]) {
+  const float4 x0 = ld4(Y + (k0 + t) * TS + 8 * g), x1 = ld4(Y + (k0 + t) * TS + 8 * g + 4);
+  const float4 y0 = ld4(Y + (k0 + t + 4) * TS + 8 * g), y1 = ld4(Y + (k0 + t + 4) * TS + 8 * g + 4);
+  const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    tf32_split(xv[n], bb[n], bs[n]);
+    tf32_split(yv[n], cb[n], cs[n]);
+  }
+}
+
+// A fragment (split) of a row-major [16][PSM] matrix, k-step kk
+__device__ __forceinline__ void load_afrag(const float* __restrict__ X, int kk, int g, int t, uint32_t (&ab)[4], uint32_t (&as)[4]) {
+  tf32_split(X[g * PSM + kk * 8 + t], ab[0], as[0]);
+  tf32_split(X[(g + 8) * PSM + kk * 8 + t], ab[1], as[1]);
+  tf32_split(X[g * PSM + kk * 8 + t + 4], ab[2], as[2]);
+  tf32_split(X[(g + 8) * PSM + kk * 8 + t + 4], ab[3], as[3]);
+}
+// A fragment of the TRANSPOSE of a row-major [16][PSM] matrix: A[m][k] = X[k][m]
+__device__ __forceinline__ void load_afrag_t(const float* __restrict__ X, int kk, int g, int t, uint32_t (&ab)[4], uint32_t (&as)[4]) {
+  tf32_split(X[(kk * 8 + t) * PSM + g], ab[0], as[0]);
+  tf32_split(X[(kk * 8 + t) * PSM + g + 8], ab[1], as[1]);
+  tf32_split(X[(kk * 8 + t + 4) * PSM + g], ab[2], as[2]);
+  tf32_split(X[(kk * 8 + t + 4) * PSM + g + 8], ab[3], as[3]);
+}
+
+// store a 16 x 64 accumulator in the permuted layout: this lane holds, for rows g and g + 8, the 16 consecutive features
+// 16t .. 16t + 15 (feature 16t + n = acc[n][0 | 2], feature 16t + 8 + n = acc[n][1 | 3])
+__device__ __forceinline__ void store_acc_n(const float (&acc)[8][4], float scale, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_hi,
+                                            __nv_bfloat16* __restrict__ dst_lo, int64_t row0, int64_t M, int64_t ld, int64_t col0, int g, int t) {
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int64_t gr = row0 + g + rr * 8;
+    if (gr < M) {
+      const int64_t off = gr * ld + col0 + 16 * t;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                // q = 0, 1: features 16t + 4q ..; q = 2, 3: features 16t + 8 + 4(q-2) ..
+        const int x = rr * 2 + (q >> 1), n0 = (q & 1) * 4;
+        const float4 v = make_float4(acc[n0][x] * scale, acc[n0 + 1][x] * scale, acc[n0 + 2][x] * scale, acc[n0 + 3][x] * scale);
+        if (dst) st4(dst + off + 4 * q, v);
+        if (dst_hi) store_split4(dst_hi + off + 4 * q, dst_lo + off + 4 * q, v);
+      }
+    }
+  }
+}
+
+template <int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
+                    const float* __restrict__ probs, const float* __restrict__ dout, float* __restrict__ dqkv,
+                    __nv_bfloat16* __restrict__ dqkv_hi, __nv_bfloat16* __restrict__ dqkv_lo,
+                    float* __restrict__ de1, float* __restrict__ de2, int64_t M, int H, int64_t ntiles, float q_scale, int keep,
+                    const unsigned char* __restrict__ drop_keep, float drop_scale) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int PER_WARP = 4 * TR * TS + 4 * TR * PSM;
+  float* e1s = smem;                     // [16][TS], rows >= L are zero
+  float* e2s = e1s + TR * TS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = e2s + TR * TS + warp * PER_WARP;
+  float* ks = qs + TR * TS;
+  float* vs = ks + TR * TS;
+  float* gs = vs + TR * TS;              // dO tile
+  float* As = gs + TR * TS;              // A' = probabilities * dropout factor, [16][PSM], zero outside the block
+  float* Ds = As + TR * PSM;             // dS
+  float* T1 = Ds + TR * PSM;             // dS skewed onto the causal table index
+  float* T2 = T1 + TR * PSM;             // ... anticausal
+  const int h = blockIdx.y;
+  const int d = H * HD;
+  for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
+    int r = i / 16, c = (i % 16) * 4;
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if (r < L) {
+      a = ld4(e1 + ((size_t)h * L + r) * HD + c);
+      b = ld4(e2 + ((size_t)h * L + r) * HD + c);
+    }
+    st4(e1s + r * TS + c, a);
+    st4(e2s + r * TS + c, b);
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;                     // mma fragment coordinates
+  const int sr = lane >> 1, sh = lane & 1;                   // skew step: row sr, table indices sh*8..+7
+  float acc_e1[8][4], acc_e2[8][4];                          // dE1 / dE2: rows (table index) g, g + 8; permuted features
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { acc_e1[n][x] = 0.f; acc_e2[n][x] = 0.f; }
+
+  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
+    const int64_t row0 = tile * TR;
+    __syncwarp();
+    load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
+    load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
+    load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
+    if (keep == 1) load_tile(gs, dout + h * HD, row0, M, d, lane);
+    else load_tile_compact(gs, dout + h * HD, row0, M, d, lane, L, keep);     // dO exists for the kept query rows only
+    // probabilities of this lane's accumulator entries (rows g, g + 8; key columns n*8 + 2t, + 1) and, with dropout, the
+    // factor m = keep * scale of each: the forward used A' = A * m in O = A' V, so dV = A'^T dO and dA = (dO V^T) * m,
+    // while the softmax backward uses A itself
+    float a[2][4], mk[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int r = g + (x >> 1) * 8, c = n * 8 + 2 * t + (x & 1);
+        const int64_t gr = row0 + r;
+        const int i = r % L;
+        float v = 0.f, m = 1.f;
+        if (gr < M && (i % keep) == 0 && c / L == r / L) {
+          const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
+          v = probs[pi];
+          if (drop_keep != nullptr) m = drop_keep[pi] ? drop_scale : 0.f;
+        }
+        a[n][x] = v;
+        mk[n][x] = m;
+      }
+    __syncwarp();
+
+    // ---- (1) dA = dO V^T
+    float da[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) da[n][x] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 x0 = ld4(gs + g * TS + 16 * j + 4 * t), x1 = ld4(gs + (g + 8) * TS + 16 * j + 4 * t);
+      const float4 v0 = ld4(vs + g * TS + 16 * j + 4 * t), v1 = ld4(vs + (g + 8) * TS + 16 * j + 4 * t);
+      uint32_t ab[4], as[4];
+      // k-step 2j: physical features 16j + 4t + {0, 1}
+      tf32_split(x0.x, ab[0], as[0]); tf32_split(x1.x, ab[1], as[1]); tf32_split(x0.y, ab[2], as[2]); tf32_split(x1.y, ab[3], as[3]);
+      mma_3x(da[0], ab, as, v0.x, v0.y);
+      mma_3x(da[1], ab, as, v1.x, v1.y);
+      // k-step 2j + 1: physical features 16j + 4t + {2, 3}
+      tf32_split(x0.z, ab[0], as[0]); tf32_split(x1.z, ab[1], as[1]); tf32_split(x0.w, ab[2], as[2]); tf32_split(x1.w, ab[3], as[3]);
+      mma_3x(da[0], ab, as, v0.z, v0.w);
+      mma_3x(da[1], ab, as, v1.z, v1.w);
+    }
+    // ---- (2) dS = A * (dA * m - rowsum(A * dA * m)); A' and dS to shared memory
+    float rd[2] = {0.f, 0.f};
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        da[n][x] *= mk[n][x];
+        rd[x >> 1] = fmaf(a[n][x], da[n][x], rd[x >> 1]);
+      }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      rd[rr] += __shfl_xor_sync(0xffffffffu, rd[rr], 1);
+      rd[rr] += __shfl_xor_sync(0xffffffffu, rd[rr], 2);
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int o = (g + rr * 8) * PSM + n * 8 + 2 * t;
+        *reinterpret_cast<float2*>(Ds + o) = make_float2(a[n][rr * 2] * (da[n][rr * 2] - rd[rr]), a[n][rr * 2 + 1] * (da[n][rr * 2 + 1] - rd[rr]));
+        *reinterpret_cast<float2*>(As + o) = make_float2(a[n][rr * 2] * mk[n][rr * 2], a[n][rr * 2 + 1] * mk[n][rr * 2 + 1]);
+      }
+    __syncwarp();
+    // ---- skew dS onto the relative-table index
+    {
+      const int i = sr % L, gb = (sr / L) * L;
+      float t1[8], t2[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const int idx = sh * 8 + x;
+        const int j1 = i - (L - 1 - idx);            // e1 row idx <-> key j = i - (L-1-idx) <= i
+        const int j2 = i + idx;                      // e2 row idx (>= 1) <-> key j = i + idx > i
+        t1[x] = (idx < L && j1 >= 0) ? Ds[sr * PSM + gb + j1] : 0.f;
+        t2[x] = (idx >= 1 && idx < L && j2 < L) ? Ds[sr * PSM + gb + j2] : 0.f;
+      }
+      st4(T1 + sr * PSM + sh * 8, make_float4(t1[0], t1[1], t1[2], t1[3]));
+      st4(T1 + sr * PSM + sh * 8 + 4, make_float4(t1[4], t1[5], t1[6], t1[7]));
+      st4(T2 + sr * PSM + sh * 8, make_float4(t2[0], t2[1], t2[2], t2[3]));
+      st4(T2 + sr * PSM + sh * 8 + 4, make_float4(t2[4], t2[5], t2[6], t2[7]));
+    }
+    __syncwarp();
+
+    float acc[8][4];
+    uint32_t bb[8], bs[8], cb[8], cs[8], ab[4], as[4];
+    // ---- (3) dQ~ = dS K + T1 e1 + T2 e2
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int which = 0; which < 3; ++which) {
+        if (which > 0 && kk * 8 >= L) continue;      // table rows >= L are zero
+        load_afrag(which == 0 ? Ds : (which == 1 ? T1 : T2), kk, g, t, ab, as);
+        load_bfrag_n(which == 0 ? ks : (which == 1 ? e1s : e2s), kk * 8, g, t, bb, bs, cb, cs);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+      }
+    }
+    store_acc_n(acc, q_scale, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, h * HD, g, t);
+    // ---- (4) dK = dS^T Q~ and (6) dE1 += T1^T Q~, dE2 += T2^T Q~ on the same Q~ fragments
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      load_bfrag_n(qs, kk * 8, g, t, bb, bs, cb, cs);
+      load_afrag_t(Ds, kk, g, t, ab, as);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+      if (L > 1) {
+        load_afrag_t(T1, kk, g, t, ab, as);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) mma_3x_pre(acc_e1[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+        load_afrag_t(T2, kk, g, t, ab, as);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) mma_3x_pre(acc_e2[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+      }
+    }
+    store_acc_n(acc, 1.f, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, d + h * HD, g, t);
+    // ---- (5) dV = A'^T dO
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      load_bfrag_n(gs, kk * 8, g, t, bb, bs, cb, cs);
+      load_afrag_t(As, kk, g, t, ab, as);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+    }
+    store_acc_n(acc, 1.f, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, 2 * d + h * HD, g, t);
+  }
+
+  // reduce the table gradients over the CTA's warps, then one atomic per element per CTA
+  __syncthreads();
+  float* red = e2s + TR * TS;           // reuse the per-warp staging area: [WARPS][2][16][64]
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = g + rr * 8, x = rr * 2 + (q >> 1), n0 = (q & 1) * 4;
+      st4(red + ((warp * 2 + 0) * TR + idx) * HD + 16 * t + 4 * q, make_float4(acc_e1[n0][x], acc_e1[n0 + 1][x], acc_e1[n0 + 2][x], acc_e1[n0 + 3][x]));
+      st4(red + ((warp * 2 + 1) * TR + idx) * HD + 16 * t + 4 * q, make_float4(acc_e2[n0][x], acc_e2[n0 + 1][x], acc_e2[n0 + 2][x], acc_e2[n0 + 3][x]));
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * L * HD; e += blockDim.x) {
+    const int which = e / (L * HD), rem = e % (L * HD);       // rem = idx * 64 + col, idx < L
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[(w * 2 + which) * TR * HD + rem];
+    float* dst = (which == 0 ? de1 : de2) + (size_t)h * L * HD + rem;
+    atomicAdd(dst, s);
+  }
+}
+
+int g_attn_fwd_algo = 0;       // 0 = tensor-core (mma.sync 3xTF32) forward, 1 = CUDA-core forward (exact-fp32 mode / tuning hook)
+int g_attn_bwd_algo = 0;       // same for the backward kernel
+
 template <int L>
 int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
                float* probs, int64_t M, int H, int keep, const unsigned char* drop_keep, float drop_scale, cudaStream_t st) {
   constexpr int WARPS = 8;
   int64_t ntiles = vq_cdiv(M, TR);
+  int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 4);
+  if (g_attn_fwd_algo == 0) {
+    size_t smem = (size_t)(2 * TR * TS + WARPS * 3 * TR * TS) * sizeof(float);
+    static_assert(3 * TR * PSM <= TR * TS, "R1, R2 and P must fit in the q tile");
+    static bool done_mma = false;
+    if (!done_mma) {
+      VQ_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_mma_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done_mma = true;
+    }
+    attn_fwd_mma_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, out_hi, out_lo, probs, M, H, ntiles, keep, drop_keep, drop_scale);
+    VQ_CUDA_LAUNCH_CHECK("attn_fwd_mma_kernel");
+    return VQ_OK;
+  }
   size_t smem = (size_t)(2 * L * TS + WARPS * 3 * TR * TS) * sizeof(float);
   static bool done = false;
   if (!done) {
     VQ_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 4);
   attn_fwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, out, out_hi, out_lo, probs, M, H, ntiles, keep, drop_keep, drop_scale);
   VQ_CUDA_LAUNCH_CHECK("attn_fwd_kernel");
   return VQ_OK;
 }
-
 template <int L>
 int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* dout, float* dqkv,
                __nv_bfloat16* dqkv_hi, __nv_bfloat16* dqkv_lo, float* de1, float* de2, int64_t M, int H, float q_scale, int keep,
@@ -453,6 +948,17 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
     done = true;
   }
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 2);
+  if (g_attn_bwd_algo == 0) {
+    static_assert(PSM == PS, "both backward kernels use the same staging layout");
+    static bool done_mma = false;
+    if (!done_mma) {
+      VQ_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_mma_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done_mma = true;
+    }
+    attn_bwd_mma_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep, drop_keep, drop_scale);
+    VQ_CUDA_LAUNCH_CHECK("attn_bwd_mma_kernel");
+    return VQ_OK;
+  }
   attn_bwd_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep, drop_keep, drop_scale);
   VQ_CUDA_LAUNCH_CHECK("attn_bwd_kernel");
   return VQ_OK;
@@ -464,6 +970,16 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
 // out (fp32) and/or (out_hi, out_lo) (bf16 split, operand of the out-proj GEMM): (P*L/keep, H*64) — only the query rows
 // with token % keep == 0 are computed and stored, compacted (keep = 1: all rows; keep = downscale factor in the last
 // layer of a stack = exact dead-row elimination); probs: (P, H, L, L) saved for backward (kept rows only; may be NULL).
+/* kernel choice, forward / backward: 0 = tensor cores (mma.sync 3xTF32, default), 1 = CUDA cores (exact fp32) */
+VQ_API int vqcpc_attn_set_fwd_algo(int algo) {
+  g_attn_fwd_algo = algo == 1 ? 1 : 0;
+  return VQ_OK;
+}
+VQ_API int vqcpc_attn_set_bwd_algo(int algo) {
+  g_attn_bwd_algo = algo == 1 ? 1 : 0;
+  return VQ_OK;
+}
+
 // drop_keep (P, H, L, L) uint8 or NULL: dropout on the attention weights (F.dropout, multihead_attention_custom.py:339) with
 // an explicit keep mask, drop_scale = 1 / (1 - p); `probs` always receives the softmax output itself.
 VQ_API int vqcpc_attn_fwd_ex(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
