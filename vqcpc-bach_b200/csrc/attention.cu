@@ -53,16 +53,17 @@ __device__ __forceinline__ void load_tile_compact(float* s, const float* __restr
   }
 }
 
+// fp32 x4 -> bf16 (hi, lo) x4 with x ~= hi + lo, two values per conversion instruction (cvt.rn.bf16x2.f32)
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);                     // .x (low half) = x, .y = y
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float4 v) {
-  __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                h3 = __float2bfloat16_rn(v.w);
-  __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
   uint2 hv, lv;
-  hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lv.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lv.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  split_pair(v.x, v.y, hv.x, lv.x);
+  split_pair(v.z, v.w, hv.y, lv.y);
   *reinterpret_cast<uint2*>(hi) = hv;
   *reinterpret_cast<uint2*>(lo) = lv;
 }
@@ -210,6 +211,80 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ab)[4], c
   mma_tf32(c, ab, b0b, b1b);
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without reading
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// asynchronous versions of load_tile / load_tile_compact (same layout, rows >= M or dropped rows are zero)
+__device__ __forceinline__ void load_tile_async(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 2 + (lane >> 4), c = (lane & 15) * 4;
+    const int64_t gr = row0 + r;
+    const bool ok = gr < M;
+    cp_async16(s + r * TS + c, ok ? g + gr * ld + c : g, ok);
+  }
+}
+__device__ __forceinline__ void load_tile_compact_async(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld,
+                                                        int lane, int L, int keep) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 2 + (lane >> 4), c = (lane & 15) * 4;
+    const int64_t gr = row0 + r;
+    const int i = (int)(gr % L);
+    const bool ok = gr < M && (i % keep) == 0;
+    cp_async16(s + r * TS + c, ok ? g + ((gr / L) * (L / keep) + i / keep) * ld + c : g, ok);
+  }
+}
+
+// B fragments of one k-step for all eight n-tiles in the "features are output columns" layout: column g of n-tile n is the
+// physical feature 8g + n, so rows ra / rb (the k indices t and t + 4 of the step) of a [16][TS] tile give all eight
+// n-tiles with two LDS.128 each; bb/bs[n] = split of row ra, cb/cs[n] = split of row rb.
+__device__ __forceinline__ void load_bfrag_n(const float* __restrict__ Y, int ra, int rb, int g, uint32_t (&bb)[8], uint32_t (&bs)[8],
+                                             uint32_t (&cb)[8], uint32_t (&cs)[8]) {
+  const float4 x0 = ld4(Y + ra * TS + 8 * g), x1 = ld4(Y + ra * TS + 8 * g + 4);
+  const float4 y0 = ld4(Y + rb * TS + 8 * g), y1 = ld4(Y + rb * TS + 8 * g + 4);
+  const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    tf32_split(xv[n], bb[n], bs[n]);
+    tf32_split(yv[n], cb[n], cs[n]);
+  }
+}
+// same for a tile stored already split (Yb = big parts, Ys = small parts, as TF32 bit patterns)
+__device__ __forceinline__ void load_bfrag_n_pre(const float* __restrict__ Yb, const float* __restrict__ Ys, int ra, int rb, int g,
+                                                 uint32_t (&bb)[8], uint32_t (&bs)[8], uint32_t (&cb)[8], uint32_t (&cs)[8]) {
+  const uint4 x0 = *reinterpret_cast<const uint4*>(Yb + ra * TS + 8 * g), x1 = *reinterpret_cast<const uint4*>(Yb + ra * TS + 8 * g + 4);
+  const uint4 y0 = *reinterpret_cast<const uint4*>(Yb + rb * TS + 8 * g), y1 = *reinterpret_cast<const uint4*>(Yb + rb * TS + 8 * g + 4);
+  const uint4 u0 = *reinterpret_cast<const uint4*>(Ys + ra * TS + 8 * g), u1 = *reinterpret_cast<const uint4*>(Ys + ra * TS + 8 * g + 4);
+  const uint4 w0 = *reinterpret_cast<const uint4*>(Ys + rb * TS + 8 * g), w1 = *reinterpret_cast<const uint4*>(Ys + rb * TS + 8 * g + 4);
+  bb[0] = x0.x; bb[1] = x0.y; bb[2] = x0.z; bb[3] = x0.w; bb[4] = x1.x; bb[5] = x1.y; bb[6] = x1.z; bb[7] = x1.w;
+  cb[0] = y0.x; cb[1] = y0.y; cb[2] = y0.z; cb[3] = y0.w; cb[4] = y1.x; cb[5] = y1.y; cb[6] = y1.z; cb[7] = y1.w;
+  bs[0] = u0.x; bs[1] = u0.y; bs[2] = u0.z; bs[3] = u0.w; bs[4] = u1.x; bs[5] = u1.y; bs[6] = u1.z; bs[7] = u1.w;
+  cs[0] = w0.x; cs[1] = w0.y; cs[2] = w0.z; cs[3] = w0.w; cs[4] = w1.x; cs[5] = w1.y; cs[6] = w1.z; cs[7] = w1.w;
+}
+__device__ __forceinline__ void mma_3x_pre(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t b0b,
+                                           uint32_t b0s, uint32_t b1b, uint32_t b1s) {
+  mma_tf32(c, as, b0b, b1b);
+  mma_tf32(c, ab, b0s, b1s);
+  mma_tf32(c, ab, b0b, b1b);
+}
+
+// Index permutations keep every shared-memory access a 128-bit one:
+//   * where the 64 features are contracted (S, R1, R2), the k-step kk = 2j + s pairs the logical columns (t, t + 4) with
+//     the physical features 16j + 4t + 2s, + 1 in BOTH operands, so one LDS.128 feeds two k-steps;
+//   * in P V the two k-steps contract the keys (n*8 + 2t, n*8 + 2t + 1), which are exactly the accumulator entries of S this
+//     lane already holds: the probabilities never leave the registers;
+//   * the output columns of P V are permuted (column g of n-tile n = feature 8g + n): all eight B fragments of a k-step are
+//     two LDS.128 and a lane ends up with 16 consecutive output features per row (64-byte global stores).
+// The next tile's k and q are fetched with cp.async as soon as the scores are final (they overlap softmax, P V and the
+// stores), v right after P V.
 template <int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
@@ -224,11 +299,17 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   float* qs = e2s + TR * TS + warp * (3 * TR * TS);
   float* ks = qs + TR * TS;
   float* vs = ks + TR * TS;
-  float* r1s = qs;                                 // after the three Q products the q tile is scratch:
-  float* r2s = qs + TR * PSM;                      //   R1, R2 (16 x 16) and the probabilities P (16 x 16)
-  float* ps = qs + 2 * TR * PSM;
+  float* r1s = qs;                                 // after the three Q products the q tile is scratch for R1, R2 (16 x 16):
+  float* r2s = qs + TR * PSM;                      //   q . e1 / q . e2 before the skew
   const int h = blockIdx.y;
   const int d = H * HD;
+  const int64_t tile0 = (int64_t)blockIdx.x * WARPS + warp, tstride = (int64_t)gridDim.x * WARPS;
+  if (tile0 < ntiles) {
+    load_tile_async(qs, qkv + h * HD, tile0 * TR, M, 3 * d, lane);
+    load_tile_async(ks, qkv + d + h * HD, tile0 * TR, M, 3 * d, lane);
+    load_tile_async(vs, qkv + 2 * d + h * HD, tile0 * TR, M, 3 * d, lane);
+  }
+  cp_async_commit();
   for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
     int r = i / 16, c = (i % 16) * 4;
     float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -241,12 +322,11 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   }
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
-  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
+  for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
     const int64_t row0 = tile * TR;
-    __syncwarp();
-    load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
-    load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
-    load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
+    const int64_t nrow0 = (tile + tstride) * TR;
+    const bool has_next = tile + tstride < ntiles;
+    cp_async_wait_all();
     __syncwarp();
     float sc[2][4], ra[NTR][4], rb[NTR][4];
 #pragma unroll
@@ -258,30 +338,45 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
 #pragma unroll
       for (int x = 0; x < 4; ++x) { ra[n][x] = 0.f; rb[n][x] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      // Q as the A fragment of this k-step, split once and shared by the three products
+    for (int j = 0; j < 4; ++j) {
+      const float4 q0 = ld4(qs + g * TS + 16 * j + 4 * t), q1 = ld4(qs + (g + 8) * TS + 16 * j + 4 * t);
+      float4 kf[2], ef1[NTR], ef2[NTR];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) kf[n] = ld4(ks + (n * 8 + g) * TS + 16 * j + 4 * t);
+#pragma unroll
+      for (int n = 0; n < NTR; ++n) {
+        ef1[n] = ld4(e1s + (n * 8 + g) * TS + 16 * j + 4 * t);
+        ef2[n] = ld4(e2s + (n * 8 + g) * TS + 16 * j + 4 * t);
+      }
       uint32_t qb[4], qsm[4];
-      tf32_split(qs[g * TS + kk * 8 + t], qb[0], qsm[0]);
-      tf32_split(qs[(g + 8) * TS + kk * 8 + t], qb[1], qsm[1]);
-      tf32_split(qs[g * TS + kk * 8 + t + 4], qb[2], qsm[2]);
-      tf32_split(qs[(g + 8) * TS + kk * 8 + t + 4], qb[3], qsm[3]);
+      // k-step 2j: physical features 16j + 4t + {0, 1}
+      tf32_split(q0.x, qb[0], qsm[0]); tf32_split(q1.x, qb[1], qsm[1]); tf32_split(q0.y, qb[2], qsm[2]); tf32_split(q1.y, qb[3], qsm[3]);
 #pragma unroll
-      for (int n = 0; n < 2; ++n)                   // S = Q K^T : B[k][n] = K[n][k]
-        mma_3x(sc[n], qb, qsm, ks[(n * 8 + g) * TS + kk * 8 + t], ks[(n * 8 + g) * TS + kk * 8 + t + 4]);
+      for (int n = 0; n < 2; ++n) mma_3x(sc[n], qb, qsm, kf[n].x, kf[n].y);
 #pragma unroll
-      for (int n = 0; n < NTR; ++n) {               // R1 = Q E1^T, R2 = Q E2^T
-        mma_3x(ra[n], qb, qsm, e1s[(n * 8 + g) * TS + kk * 8 + t], e1s[(n * 8 + g) * TS + kk * 8 + t + 4]);
-        mma_3x(rb[n], qb, qsm, e2s[(n * 8 + g) * TS + kk * 8 + t], e2s[(n * 8 + g) * TS + kk * 8 + t + 4]);
+      for (int n = 0; n < NTR; ++n) {
+        mma_3x(ra[n], qb, qsm, ef1[n].x, ef1[n].y);
+        mma_3x(rb[n], qb, qsm, ef2[n].x, ef2[n].y);
+      }
+      // k-step 2j + 1: physical features 16j + 4t + {2, 3}
+      tf32_split(q0.z, qb[0], qsm[0]); tf32_split(q1.z, qb[1], qsm[1]); tf32_split(q0.w, qb[2], qsm[2]); tf32_split(q1.w, qb[3], qsm[3]);
+#pragma unroll
+      for (int n = 0; n < 2; ++n) mma_3x(sc[n], qb, qsm, kf[n].z, kf[n].w);
+#pragma unroll
+      for (int n = 0; n < NTR; ++n) {
+        mma_3x(ra[n], qb, qsm, ef1[n].z, ef1[n].w);
+        mma_3x(rb[n], qb, qsm, ef2[n].z, ef2[n].w);
       }
     }
-    __syncwarp();                                   // every lane is done with the q tile: it becomes scratch
+    __syncwarp();                                   // every lane is done with q and k: prefetch the next tile's k
+    if (has_next) load_tile_async(ks, qkv + d + h * HD, nrow0, M, 3 * d, lane);
     // ---- R1 / R2 to scratch (C layout: rows g, g + 8; cols n*8 + 2t, +1)
 #pragma unroll
     for (int n = 0; n < NTR; ++n) {
-      r1s[g * PSM + n * 8 + 2 * t] = ra[n][0]; r1s[g * PSM + n * 8 + 2 * t + 1] = ra[n][1];
-      r1s[(g + 8) * PSM + n * 8 + 2 * t] = ra[n][2]; r1s[(g + 8) * PSM + n * 8 + 2 * t + 1] = ra[n][3];
-      r2s[g * PSM + n * 8 + 2 * t] = rb[n][0]; r2s[g * PSM + n * 8 + 2 * t + 1] = rb[n][1];
-      r2s[(g + 8) * PSM + n * 8 + 2 * t] = rb[n][2]; r2s[(g + 8) * PSM + n * 8 + 2 * t + 1] = rb[n][3];
+      *reinterpret_cast<float2*>(r1s + g * PSM + n * 8 + 2 * t) = make_float2(ra[n][0], ra[n][1]);
+      *reinterpret_cast<float2*>(r1s + (g + 8) * PSM + n * 8 + 2 * t) = make_float2(ra[n][2], ra[n][3]);
+      *reinterpret_cast<float2*>(r2s + g * PSM + n * 8 + 2 * t) = make_float2(rb[n][0], rb[n][1]);
+      *reinterpret_cast<float2*>(r2s + (g + 8) * PSM + n * 8 + 2 * t) = make_float2(rb[n][2], rb[n][3]);
     }
     __syncwarp();
     // ---- bias + block mask + softmax; this lane holds rows g and g + 8, columns n*8 + 2t + {0, 1}
@@ -298,6 +393,9 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         pv[n][x] = v;
         mx[x >> 1] = fmaxf(mx[x >> 1], v);
       }
+    __syncwarp();                                   // the scratch (= q tile) is free: prefetch the next tile's q
+    if (has_next) load_tile_async(qs, qkv + h * HD, nrow0, M, 3 * d, lane);
+    cp_async_commit();
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
@@ -317,7 +415,6 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], 2);
       sm[rr] = 1.f / sm[rr];
     }
-    __syncwarp();
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
@@ -331,10 +428,9 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
           if (probs != nullptr) probs[pi] = a;
           if (drop_keep != nullptr) a = drop_keep[pi] ? a * drop_scale : 0.f;
         }
-        ps[r * PSM + c] = a;
+        pv[n][x] = a;
       }
-    __syncwarp();
-    // ---- O = P V  (16 x 64): A fragments from the P scratch, B[k][n] = V[k][n]
+    // ---- O = P V (16 x 64), keys contracted in the order this lane's S entries have them
     float oc[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -342,34 +438,32 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       for (int x = 0; x < 4; ++x) oc[n][x] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      uint32_t pb[4], psm_[4];
-      tf32_split(ps[g * PSM + kk * 8 + t], pb[0], psm_[0]);
-      tf32_split(ps[(g + 8) * PSM + kk * 8 + t], pb[1], psm_[1]);
-      tf32_split(ps[g * PSM + kk * 8 + t + 4], pb[2], psm_[2]);
-      tf32_split(ps[(g + 8) * PSM + kk * 8 + t + 4], pb[3], psm_[3]);
+      uint32_t pb[4], psm_[4], bb[8], bs[8], cb[8], cs[8];
+      tf32_split(pv[kk][0], pb[0], psm_[0]);        // (row g,     key kk*8 + 2t)
+      tf32_split(pv[kk][2], pb[1], psm_[1]);        // (row g + 8, key kk*8 + 2t)
+      tf32_split(pv[kk][1], pb[2], psm_[2]);        // (row g,     key kk*8 + 2t + 1)
+      tf32_split(pv[kk][3], pb[3], psm_[3]);        // (row g + 8, key kk*8 + 2t + 1)
+      load_bfrag_n(vs, kk * 8 + 2 * t, kk * 8 + 2 * t + 1, g, bb, bs, cb, cs);
 #pragma unroll
-      for (int n = 0; n < 8; ++n)
-        mma_3x(oc[n], pb, psm_, vs[(kk * 8 + t) * TS + n * 8 + g], vs[(kk * 8 + t + 4) * TS + n * 8 + g]);
+      for (int n = 0; n < 8; ++n) mma_3x_pre(oc[n], pb, psm_, bb[n], bs[n], cb[n], cs[n]);
     }
-    // ---- store rows g and g + 8 (kept query rows only), two consecutive features per fragment half
+    __syncwarp();                                   // v is free: prefetch the next tile's
+    if (has_next) load_tile_async(vs, qkv + 2 * d + h * HD, nrow0, M, 3 * d, lane);
+    cp_async_commit();
+    // ---- store rows g and g + 8 (kept query rows only): features 16t .. 16t + 15 (16t + n = oc[n][0|2], 16t + 8 + n = oc[n][1|3])
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int r = g + rr * 8;
       const int64_t gr = row0 + r;
       const int i = r % L;
       if (gr < M && (i % keep) == 0) {
-        const int64_t orow = (gr / L) * (L / keep) + i / keep;
+        const int64_t off = ((gr / L) * (L / keep) + i / keep) * d + h * HD + 16 * t;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const int64_t off = orow * d + h * HD + n * 8 + 2 * t;
-          const float v0 = oc[n][rr * 2], v1 = oc[n][rr * 2 + 1];
-          if (out) *reinterpret_cast<float2*>(out + off) = make_float2(v0, v1);
-          if (out_hi) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            *reinterpret_cast<__nv_bfloat162*>(out_hi + off) = __nv_bfloat162(h0, h1);
-            *reinterpret_cast<__nv_bfloat162*>(out_lo + off) =
-                __nv_bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int x = rr * 2 + (q >> 1), n0 = (q & 1) * 4;
+          const float4 v = make_float4(oc[n0][x], oc[n0 + 1][x], oc[n0 + 2][x], oc[n0 + 3][x]);
+          if (out) st4(out + off + 4 * q, v);
+          if (out_hi) store_split4(out_hi + off + 4 * q, out_lo + off + 4 * q, v);
         }
       }
     }
@@ -635,28 +729,6 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 //     fragments of all eight n-tiles are two LDS.128 and a lane ends up with 16 consecutive output features per row
 //     (64-byte global stores).
 // (4) and (6) share the split Q~ fragments.  The relative tables' gradients stay in registers for the whole kernel.
-__device__ __forceinline__ void mma_3x_pre(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t b0b,
-                                           uint32_t b0s, uint32_t b1b, uint32_t b1s) {
-  mma_tf32(c, as, b0b, b1b);
-  mma_tf32(c, ab, b0s, b1s);
-  mma_tf32(c, ab, b0b, b1b);
-}
-
-// B fragments of one k-step for all eight n-tiles in the "features are output columns" layout: rows k0 + t and k0 + t + 4
-// of a [16][TS] tile, physical features 8g .. 8g + 7; bb/bs[n] = split of row k0 + t, cb/cs[n] = split of row k0 + t + 4.
-__device__ __forceinline__ void load_bfrag_n(const float* __restrict__ Y, int k0, int g, int t, uint32_t (&bb)[8], uint32_t (&bs)[8],
-                                             uint32_t (&cb)[8], uint32_t (&cs)[8]) {
-  const float4 x0 = ld4(Y + (k0 + t) * TS + 8 * g), x1 = ld4(Y + (k0 + t) * TS + 8 * g + 4);
-  const float4 y0 = ld4(Y + (k0 + t + 4) * TS + 8 * g), y1 = ld4(Y + (k0 + t + 4) * TS + 8 * g + 4);
-  const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    tf32_split(xv[n], bb[n], bs[n]);
-    tf32_split(yv[n], cb[n], cs[n]);
-  }
-}
-
 // A fragment (split) of a row-major [16][PSM] matrix, k-step kk
 __device__ __forceinline__ void load_afrag(const float* __restrict__ X, int kk, int g, int t, uint32_t (&ab)[4], uint32_t (&as)[4]) {
   tf32_split(X[g * PSM + kk * 8 + t], ab[0], as[0]);
@@ -701,10 +773,13 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
                     const unsigned char* __restrict__ drop_keep, float drop_scale) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PER_WARP = 4 * TR * TS + 4 * TR * PSM;
-  float* e1s = smem;                     // [16][TS], rows >= L are zero
+  float* e1s = smem;                     // [16][TS], rows >= L are zero: TF32 "big" parts of the tables ...
   float* e2s = e1s + TR * TS;
+  float* e1l = e2s + TR * TS;            // ... and their "small" parts (split once per CTA, not once per tile)
+  float* e2l = e1l + TR * TS;
+  float* stage = e2l + TR * TS;          // per-warp staging areas
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* qs = e2s + TR * TS + warp * PER_WARP;
+  float* qs = stage + warp * PER_WARP;
   float* ks = qs + TR * TS;
   float* vs = ks + TR * TS;
   float* gs = vs + TR * TS;              // dO tile
@@ -721,8 +796,17 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       a = ld4(e1 + ((size_t)h * L + r) * HD + c);
       b = ld4(e2 + ((size_t)h * L + r) * HD + c);
     }
-    st4(e1s + r * TS + c, a);
-    st4(e2s + r * TS + c, b);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ab_[4], as_[4], bb_[4], bs_[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      tf32_split(av[x], ab_[x], as_[x]);
+      tf32_split(bv[x], bb_[x], bs_[x]);
+    }
+    *reinterpret_cast<uint4*>(e1s + r * TS + c) = make_uint4(ab_[0], ab_[1], ab_[2], ab_[3]);
+    *reinterpret_cast<uint4*>(e1l + r * TS + c) = make_uint4(as_[0], as_[1], as_[2], as_[3]);
+    *reinterpret_cast<uint4*>(e2s + r * TS + c) = make_uint4(bb_[0], bb_[1], bb_[2], bb_[3]);
+    *reinterpret_cast<uint4*>(e2l + r * TS + c) = make_uint4(bs_[0], bs_[1], bs_[2], bs_[3]);
   }
   __syncthreads();
 
@@ -734,14 +818,24 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
 #pragma unroll
     for (int x = 0; x < 4; ++x) { acc_e1[n][x] = 0.f; acc_e2[n][x] = 0.f; }
 
-  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * WARPS) {
+  const int64_t tile0 = (int64_t)blockIdx.x * WARPS + warp, tstride = (int64_t)gridDim.x * WARPS;
+  auto fetch_g = [&](int64_t r0) {                          // dO exists for the kept query rows only
+    if (keep == 1) load_tile_async(gs, dout + h * HD, r0, M, d, lane);
+    else load_tile_compact_async(gs, dout + h * HD, r0, M, d, lane, L, keep);
+  };
+  if (tile0 < ntiles) {
+    load_tile_async(qs, qkv + h * HD, tile0 * TR, M, 3 * d, lane);
+    load_tile_async(ks, qkv + d + h * HD, tile0 * TR, M, 3 * d, lane);
+    load_tile_async(vs, qkv + 2 * d + h * HD, tile0 * TR, M, 3 * d, lane);
+    fetch_g(tile0 * TR);
+  }
+  cp_async_commit();
+  // The next tile's operands are fetched with cp.async into the same buffers as soon as the current tile's last reader is
+  // done: v and dO after (1) + (5), k after (3), q after (4) + (6).
+  for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
     const int64_t row0 = tile * TR;
-    __syncwarp();
-    load_tile(qs, qkv + h * HD, row0, M, 3 * d, lane);
-    load_tile(ks, qkv + d + h * HD, row0, M, 3 * d, lane);
-    load_tile(vs, qkv + 2 * d + h * HD, row0, M, 3 * d, lane);
-    if (keep == 1) load_tile(gs, dout + h * HD, row0, M, d, lane);
-    else load_tile_compact(gs, dout + h * HD, row0, M, d, lane, L, keep);     // dO exists for the kept query rows only
+    const int64_t nrow0 = (tile + tstride) * TR;
+    const bool has_next = tile + tstride < ntiles;
     // probabilities of this lane's accumulator entries (rows g, g + 8; key columns n*8 + 2t, + 1) and, with dropout, the
     // factor m = keep * scale of each: the forward used A' = A * m in O = A' V, so dV = A'^T dO and dA = (dO V^T) * m,
     // while the softmax backward uses A itself
@@ -762,6 +856,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         a[n][x] = v;
         mk[n][x] = m;
       }
+    cp_async_wait_all();
     __syncwarp();
 
     // ---- (1) dA = dO V^T
@@ -828,31 +923,54 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
 
     float acc[8][4];
     uint32_t bb[8], bs[8], cb[8], cs[8], ab[4], as[4];
+    // ---- (5) dV = A'^T dO
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
+#pragma unroll 1                                  // (rolled: 3 % faster than unrolled, the loop body is instruction-cache bound)
+    for (int kk = 0; kk < 2; ++kk) {
+      load_bfrag_n(gs, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
+      load_afrag_t(As, kk, g, t, ab, as);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
+    }
+    store_acc_n(acc, 1.f, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, 2 * d + h * HD, g, t);
+    __syncwarp();                                   // v and dO are free
+    if (has_next) {
+      load_tile_async(vs, qkv + 2 * d + h * HD, nrow0, M, 3 * d, lane);
+      fetch_g(nrow0);
+    }
+    cp_async_commit();
     // ---- (3) dQ~ = dS K + T1 e1 + T2 e2
 #pragma unroll
     for (int n = 0; n < 8; ++n)
 #pragma unroll
       for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
-#pragma unroll
+#pragma unroll 1                                  // (rolled: 3 % faster than unrolled, the loop body is instruction-cache bound)
     for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
       for (int which = 0; which < 3; ++which) {
         if (which > 0 && kk * 8 >= L) continue;      // table rows >= L are zero
         load_afrag(which == 0 ? Ds : (which == 1 ? T1 : T2), kk, g, t, ab, as);
-        load_bfrag_n(which == 0 ? ks : (which == 1 ? e1s : e2s), kk * 8, g, t, bb, bs, cb, cs);
+        if (which == 0) load_bfrag_n(ks, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
+        else load_bfrag_n_pre(which == 1 ? e1s : e2s, which == 1 ? e1l : e2l, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
 #pragma unroll
         for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
       }
     }
     store_acc_n(acc, q_scale, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, h * HD, g, t);
+    __syncwarp();                                   // k is free
+    if (has_next) load_tile_async(ks, qkv + d + h * HD, nrow0, M, 3 * d, lane);
+    cp_async_commit();
     // ---- (4) dK = dS^T Q~ and (6) dE1 += T1^T Q~, dE2 += T2^T Q~ on the same Q~ fragments
 #pragma unroll
     for (int n = 0; n < 8; ++n)
 #pragma unroll
       for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
-#pragma unroll
+#pragma unroll 1                                  // (rolled: 3 % faster than unrolled, the loop body is instruction-cache bound)
     for (int kk = 0; kk < 2; ++kk) {
-      load_bfrag_n(qs, kk * 8, g, t, bb, bs, cb, cs);
+      load_bfrag_n(qs, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
       load_afrag_t(Ds, kk, g, t, ab, as);
 #pragma unroll
       for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
@@ -866,24 +984,14 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       }
     }
     store_acc_n(acc, 1.f, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, d + h * HD, g, t);
-    // ---- (5) dV = A'^T dO
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-      for (int x = 0; x < 4; ++x) acc[n][x] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      load_bfrag_n(gs, kk * 8, g, t, bb, bs, cb, cs);
-      load_afrag_t(As, kk, g, t, ab, as);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
-    }
-    store_acc_n(acc, 1.f, dqkv, dqkv_hi, dqkv_lo, row0, M, 3 * d, 2 * d + h * HD, g, t);
+    __syncwarp();                                   // q is free
+    if (has_next) load_tile_async(qs, qkv + h * HD, nrow0, M, 3 * d, lane);
+    cp_async_commit();
   }
 
   // reduce the table gradients over the CTA's warps, then one atomic per element per CTA
   __syncthreads();
-  float* red = e2s + TR * TS;           // reuse the per-warp staging area: [WARPS][2][16][64]
+  float* red = stage;                   // reuse the per-warp staging areas: [WARPS][2][16][64]
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -914,7 +1022,7 @@ int launch_fwd(const float* qkv, const float* e1, const float* e2, float* out, _
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 4);
   if (g_attn_fwd_algo == 0) {
     size_t smem = (size_t)(2 * TR * TS + WARPS * 3 * TR * TS) * sizeof(float);
-    static_assert(3 * TR * PSM <= TR * TS, "R1, R2 and P must fit in the q tile");
+    static_assert(2 * TR * PSM <= TR * TS, "R1 and R2 must fit in the q tile");
     static bool done_mma = false;
     if (!done_mma) {
       VQ_CUDA_CALL(cudaFuncSetAttribute(attn_fwd_mma_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -950,12 +1058,13 @@ int launch_bwd(const float* qkv, const float* e1, const float* e2, const float* 
   int64_t gx = std::min<int64_t>(vq_cdiv(ntiles, WARPS), std::max(1, vq_sm_count() * 2 / H) * 2);
   if (g_attn_bwd_algo == 0) {
     static_assert(PSM == PS, "both backward kernels use the same staging layout");
+    const size_t smem_mma = smem + (size_t)(2 * TR * TS) * sizeof(float);      // + the small parts of the split tables
     static bool done_mma = false;
     if (!done_mma) {
-      VQ_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_mma_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VQ_CUDA_CALL(cudaFuncSetAttribute(attn_bwd_mma_kernel<L, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
       done_mma = true;
     }
-    attn_bwd_mma_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep, drop_keep, drop_scale);
+    attn_bwd_mma_kernel<L, WARPS><<<dim3((unsigned)gx, H), WARPS * 32, smem_mma, st>>>(qkv, e1, e2, probs, dout, dqkv, dqkv_hi, dqkv_lo, de1, de2, M, H, ntiles, q_scale, keep, drop_keep, drop_scale);
     VQ_CUDA_LAUNCH_CHECK("attn_bwd_mma_kernel");
     return VQ_OK;
   }
