@@ -63,6 +63,11 @@ int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* beta, f
 int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
                         float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, int64_t M, int d,
                         void* stream);
+/* Same; d_y_colsum (d floats, may be NULL) additionally ACCUMULATES the column sums of d_y = the bias gradient of the
+ * linear layer feeding the LN (out_proj.bias for norm1, linear2.bias for norm2; transformer_custom.py:283-289). */
+int vqcpc_layernorm_bwd_ex(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
+                           float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, float* d_y_colsum,
+                           int64_t M, int d, void* stream);
 /* relative_transformer_downscaler.py:124 `output[::downscaling]` in blocks-major layout: x (P*L, d) -> out (P*L/f, d). */
 int vqcpc_subsample_fwd(const float* x, float* out, int64_t P, int L, int factor, int d, void* stream);
 int vqcpc_subsample_bwd(const float* d_out, float* d_x, int64_t P, int L, int factor, int d, void* stream);

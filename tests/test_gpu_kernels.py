@@ -61,6 +61,13 @@ def test_layernorm_fwd_bwd(M):
     dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
     dy = ops.layernorm_bwd(go, y.detach(), mean, rstd, g.detach(), dg, db)
     assert rel_err(dy, y.grad) < 2e-6 and rel_err(dg, g.grad) < 2e-6 and rel_err(db, b.grad) < 2e-6
+    # fused variant: same outputs (+ bf16 split) and the column sums of dy accumulated into a bias-gradient buffer
+    dg2, db2, cs = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda'), torch.full((d,), 0.25, device='cuda')
+    dy2, sp = ops.layernorm_bwd(go, y.detach(), mean, rstd, g.detach(), dg2, db2, want_split=True, colsum_out=cs)
+    assert torch.equal(dy2, dy) and rel_err(dg2, dg) < 1e-6 and rel_err(db2, db) < 1e-6
+    assert rel_err(sp[0].float() + sp[1].float(), dy) < 1e-4
+    ref_cs = 0.25 + y.grad.sum(0)
+    assert (cs.double() - ref_cs).abs().max().item() < 1e-5 * max(1.0, y.grad.abs().sum(0).max().item())
 
 
 def test_subsample_colsum_selu_reduce():

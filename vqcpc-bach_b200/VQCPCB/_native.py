@@ -21,6 +21,7 @@ SIGNATURES = {
     'vqcpc_posemb_bwd': [_P, _I, _I, _P, _P, _L, _I, _I, _I, _P],
     'vqcpc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     'vqcpc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
+    'vqcpc_layernorm_bwd_ex': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     'vqcpc_subsample_fwd': [_P, _P, _L, _I, _I, _I, _P],
     'vqcpc_subsample_bwd': [_P, _P, _L, _I, _I, _I, _P],
     'vqcpc_colsum': [_P, _I, _P, _L, _I, _P],

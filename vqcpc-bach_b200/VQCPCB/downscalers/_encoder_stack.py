@@ -219,13 +219,15 @@ class EncoderStackFn(torch.autograd.Function):
                         # dropout2: the FFN branch sees the masked gradient, the residual path the plain one
                         dy2 = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'])
                         _, dy2_sp = ops.mask_scale_add(dy2, masks[3], ds, want_fp32=False, want_split=True)
-                        dy2_for_bias = None                    # bias gradient from the masked split
                     else:
-                        dy2, dy2_sp = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'], want_split=True)
-                        dy2_for_bias = dy2
+                        # linear2.bias gradient = column sums of dy2: accumulated by the LayerNorm-backward kernel itself
+                        dy2, dy2_sp = ops.layernorm_bwd(dx, y2, mean2, rstd2, lp['g2'], gp['g2'], gp['be2'], want_split=True,
+                                                        colsum_out=gp['b2'])
+                    # (with dropout the bias gradients come from the masked splits, inside linear_bwd)
                     # FFN2: dhm = (dy2 W2) * (hm > 0) -> only its split is needed (dgrad + wgrad of FFN1); with dropout
                     # the saved hm is the dropped activation (zero where dropped) and the kept entries carry 1 / (1 - p)
-                    _, dhm_sp = ops.linear_bwd(None, lp['w2'], dy2_for_bias, gp['w2'], gp['b2'], relu_mask=hm[0], x_split=hm,
+                    _, dhm_sp = ops.linear_bwd(None, lp['w2'], None, gp['w2'], gp['b2'] if masks is not None else None,
+                                               relu_mask=hm[0], x_split=hm,
                                                dy_split=dy2_sp, dx_want_c=False, dx_out_split=True, shape=(Mk, Fh),
                                                dx_scale=ds if masks is not None else None)
                     # FFN1: dx1 = dhm W1 + dy2
@@ -235,11 +237,11 @@ class EncoderStackFn(torch.autograd.Function):
                     if masks is not None:
                         dy1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'])
                         _, dy1_sp = ops.mask_scale_add(dy1, masks[1], ds, want_fp32=False, want_split=True)
-                        dy1_for_bias = None
                     else:
-                        dy1, dy1_sp = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'], want_split=True)
-                        dy1_for_bias = dy1
-                    do = ops.linear_bwd(None, lp['wo'], dy1_for_bias, gp['wo'], gp['bo'], x_split=o_k, dy_split=dy1_sp, shape=(Mk, d))
+                        dy1, dy1_sp = ops.layernorm_bwd(dx1, y1, mean1, rstd1, lp['g1'], gp['g1'], gp['be1'], want_split=True,
+                                                        colsum_out=gp['bo'])      # out_proj.bias gradient, same way
+                    do = ops.linear_bwd(None, lp['wo'], None, gp['wo'], gp['bo'] if masks is not None else None, x_split=o_k,
+                                        dy_split=dy1_sp, shape=(Mk, d))
                     _, dqkv_sp = ops.attn_bwd(qkv, lp['e1'], lp['e2'], probs, do, gp['e1'], gp['e2'], P, L, H, hd, q_scale,
                                               keep=keep, want_fp32=False, want_split=True, drop=adrop)
                     if last:

@@ -270,12 +270,13 @@ def layernorm_fwd(y, gamma, beta, eps=1e-5, want_fp32=True, want_split=False):
     return out, mean, rstd
 
 
-def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta, want_split=False):
+def layernorm_bwd(dout, y, mean, rstd, gamma, dgamma, dbeta, want_split=False, colsum_out=None):
+    """colsum_out (d,), optional: accumulates the column sums of the returned dy (bias gradient of the layer feeding the LN)."""
     M, d = y.shape
     dy = torch.empty_like(y)
     sp = _split_buffers(M, d, y.device) if want_split else (None, None)
-    _native.call('vqcpc_layernorm_bwd', _p(dout), _p(y), _p(mean), _p(rstd), _p(gamma), _p(dy), _p(sp[0]), _p(sp[1]), _p(dgamma),
-                 _p(dbeta), M, d, _stream())
+    _native.call('vqcpc_layernorm_bwd_ex', _p(dout), _p(y), _p(mean), _p(rstd), _p(gamma), _p(dy), _p(sp[0]), _p(sp[1]), _p(dgamma),
+                 _p(dbeta), _p(colsum_out), M, d, _stream())
     if want_split:
         return dy, sp
     return dy

@@ -163,23 +163,24 @@ layernorm_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamm
   }
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(256)
+template <int VPL, bool COLSUM>
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dy,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M,
-                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
+                     __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, float* __restrict__ dy_colsum) {
   const int d = 128 * VPL;
   __shared__ float red[2][8][128 * VPL];   // [dgamma|dbeta][warp][col]   (VPL=4: 32 KB)
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float4 g[VPL], ag[VPL], ab[VPL];
+  float4 g[VPL], ag[VPL], ab[VPL], ad[COLSUM ? VPL : 1];   // ad: column sums of dy (the bias gradient of the layer feeding the LN)
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    g[i] = ld4(gamma + (i * 32 + lane) * 4);
+    if (!COLSUM) g[i] = ld4(gamma + (i * 32 + lane) * 4);
     ag[i] = make_float4(0, 0, 0, 0);
     ab[i] = make_float4(0, 0, 0, 0);
+    if (COLSUM) ad[i] = make_float4(0, 0, 0, 0);
   }
   for (int64_t r = warp; r < M; r += nwarps) {
     float mu = mean[r], rs = rstd[r];
@@ -192,7 +193,8 @@ layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y
       xh[i] = make_float4((yy.x - mu) * rs, (yy.y - mu) * rs, (yy.z - mu) * rs, (yy.w - mu) * rs);
       ag[i].x += go[i].x * xh[i].x; ag[i].y += go[i].y * xh[i].y; ag[i].z += go[i].z * xh[i].z; ag[i].w += go[i].w * xh[i].w;
       ab[i].x += go[i].x; ab[i].y += go[i].y; ab[i].z += go[i].z; ab[i].w += go[i].w;
-      go[i].x *= g[i].x; go[i].y *= g[i].y; go[i].z *= g[i].z; go[i].w *= g[i].w;
+      const float4 gm = COLSUM ? ld4(gamma + (i * 32 + lane) * 4) : g[i];   // (COLSUM: gamma re-read from L1, 16 registers freed)
+      go[i].x *= gm.x; go[i].y *= gm.y; go[i].z *= gm.z; go[i].w *= gm.w;
       s1 += (go[i].x + go[i].y) + (go[i].z + go[i].w);
       s2 += (go[i].x * xh[i].x + go[i].y * xh[i].y) + (go[i].z * xh[i].z + go[i].w * xh[i].w);
     }
@@ -206,6 +208,7 @@ layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y
       o.w = (go[i].w - c1 - xh[i].w * c2) * rs;
       st4(dy + r * d + (i * 32 + lane) * 4, o);
       if (dy_hi) store_split4(dy_hi + r * d + (i * 32 + lane) * 4, dy_lo + r * d + (i * 32 + lane) * 4, o);
+      if (COLSUM) { ad[i].x += o.x; ad[i].y += o.y; ad[i].z += o.z; ad[i].w += o.w; }
     }
   }
 #pragma unroll
@@ -223,6 +226,18 @@ layernorm_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y
     }
     atomicAdd(dgamma + c, a);
     atomicAdd(dbeta + c, b);
+  }
+  if (COLSUM) {                              // second round through the same scratch
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) st4(&red[0][wib][(i * 32 + lane) * 4], ad[i]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += red[0][w][c];
+      atomicAdd(dy_colsum + c, a);
+    }
   }
 }
 
@@ -532,10 +547,12 @@ VQ_API int vqcpc_layernorm_fwd(const float* y, const float* gamma, const float* 
   return VQ_OK;
 }
 
-// d_y = LN backward wrt its input; d_gamma / d_beta are ACCUMULATED (+=)
-VQ_API int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
-                               float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, int64_t M, int d,
-                               void* stream) {
+// d_y = LN backward wrt its input; d_gamma / d_beta are ACCUMULATED (+=).  d_y_colsum (d floats, may be NULL) additionally
+// accumulates the column sums of d_y: the bias gradient of the linear layer whose output (+ residual) the LN normalises
+// (out_proj.bias for norm1, linear2.bias for norm2; transformer_custom.py:283-289) - saves a separate pass over d_y.
+VQ_API int vqcpc_layernorm_bwd_ex(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
+                                  float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, float* d_y_colsum,
+                                  int64_t M, int d, void* stream) {
   VQ_CHECK_ARG(d == 128 || d == 256 || d == 512, "layernorm_bwd: d_model must be 128/256/512 (got %d)", d);
   VQ_CHECK_ARG((d_y_hi == nullptr) == (d_y_lo == nullptr), "layernorm_bwd: d_y_hi/d_y_lo must be given together");
   if (M == 0) return VQ_OK;
@@ -543,13 +560,29 @@ VQ_API int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* 
   cudaStream_t st = vq_stream(stream);
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d_y_hi);
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d_y_lo);
-  switch (d / 128) {
-    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
-    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
-    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol); break;
+#define VQ_LN_BWD(V, C) layernorm_bwd_kernel<V, C><<<grid, 256, 0, st>>>(d_out, y, mean, rstd, gamma, d_y, d_gamma, d_beta, M, oh, ol, d_y_colsum)
+  if (d_y_colsum) {
+    switch (d / 128) {
+      case 1: VQ_LN_BWD(1, true); break;
+      case 2: VQ_LN_BWD(2, true); break;
+      default: VQ_LN_BWD(4, true); break;
+    }
+  } else {
+    switch (d / 128) {
+      case 1: VQ_LN_BWD(1, false); break;
+      case 2: VQ_LN_BWD(2, false); break;
+      default: VQ_LN_BWD(4, false); break;
+    }
   }
+#undef VQ_LN_BWD
   VQ_CUDA_LAUNCH_CHECK("layernorm_bwd_kernel");
   return VQ_OK;
+}
+
+VQ_API int vqcpc_layernorm_bwd(const float* d_out, const float* y, const float* mean, const float* rstd, const float* gamma,
+                               float* d_y, void* d_y_hi, void* d_y_lo, float* d_gamma, float* d_beta, int64_t M, int d,
+                               void* stream) {
+  return vqcpc_layernorm_bwd_ex(d_out, y, mean, rstd, gamma, d_y, d_y_hi, d_y_lo, d_gamma, d_beta, nullptr, M, d, stream);
 }
 
 // relative_transformer_downscaler.py:124  transfo_input = output[::downscaling]  (blocks-major layout here)
