@@ -132,7 +132,9 @@ def test_attention_fwd_bwd_vs_oracle(L, P):
     assert rel_err(de1, e1d.grad) < 5e-6 and rel_err(de2, e2d.grad) < 5e-6
 
 
-@pytest.mark.parametrize('L,P,keep', [(16, 37, 1), (16, 9, 4), (4, 37, 1), (4, 21, 4), (2, 9, 1)])
+# (the last three cases give every warp several tiles: the cp.async prefetch of the next tile is live)
+@pytest.mark.parametrize('L,P,keep', [(16, 37, 1), (16, 9, 4), (4, 37, 1), (4, 21, 4), (2, 9, 1), (16, 3001, 1), (16, 2501, 4),
+                                      (4, 9001, 4)])
 def test_attention_fwd_both_kernels_agree(L, P, keep):
     """The tensor-core forward (mma.sync 3xTF32, default) and the CUDA-core forward are two evaluations of the same fp32
     math: outputs, the bf16 split and the saved probabilities agree to fp32 round-off, with and without dead-row
@@ -156,7 +158,8 @@ def test_attention_fwd_both_kernels_agree(L, P, keep):
     assert rel_err(res[0][1], res[0][0].double().cpu()) < 1e-4          # the split reproduces the fp32 output to 16 bits
 
 
-@pytest.mark.parametrize('L,P,keep', [(16, 37, 1), (16, 9, 4), (8, 11, 2), (4, 37, 1), (4, 21, 4), (2, 9, 1), (1, 19, 1)])
+@pytest.mark.parametrize('L,P,keep', [(16, 37, 1), (16, 9, 4), (8, 11, 2), (4, 37, 1), (4, 21, 4), (2, 9, 1), (1, 19, 1),
+                                      (16, 3001, 1), (16, 2501, 4), (4, 9001, 4)])
 def test_attention_bwd_both_kernels_agree(L, P, keep):
     """Tensor-core backward (default) vs CUDA-core backward on the same saved probabilities: d_qkv (fp32 and bf16 split),
     dE1 / dE2, with dead-row elimination and with a dropout keep mask."""
@@ -170,16 +173,17 @@ def test_attention_bwd_both_kernels_agree(L, P, keep):
     for drop in (None, ((torch.rand(P, H, L, L, device='cuda') > 0.3).to(torch.uint8), 1.0 / 0.7)):
         _, probs = ops.attn_fwd(qkv, e1, e2, P, L, H, hd, keep=keep, drop=drop, algo=1)
         go = torch.randn(P * (L // keep), d, device='cuda')
-        res = []
-        for algo in (0, 1):
+        res = {}
+        for algo in (0, 1):                    # 0 = tensor cores, 1 = CUDA cores (the reference here)
             de1, de2 = torch.zeros_like(e1), torch.zeros_like(e2)
             dqkv, sp = ops.attn_bwd(qkv, e1, e2, probs, go, de1, de2, P, L, H, hd, 0.125, keep=keep, want_split=True, drop=drop,
                                     algo=algo)
             torch.cuda.synchronize()
-            res.append((dqkv, sp[0].float() + sp[1].float(), de1, de2))
-        for a, b in zip(*res):
-            assert rel_err(a, b) < 3e-6, rel_err(a, b)
-        assert rel_err(res[0][1], res[0][0]) < 1e-4
+            res[algo] = (dqkv, sp[0].float() + sp[1].float(), de1, de2)
+        for algo in (0,):
+            for a, b in zip(res[algo], res[1]):
+                assert rel_err(a, b) < 3e-6, (algo, rel_err(a, b))
+            assert rel_err(res[algo][1], res[algo][0]) < 1e-4
 
 
 def test_quantizer_bit_exact_vs_reference_golden(golden_dir):

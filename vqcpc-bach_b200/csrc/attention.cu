@@ -219,6 +219,8 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N newest groups
 
 // asynchronous versions of load_tile / load_tile_compact (same layout, rows >= M or dropped rows are zero)
 __device__ __forceinline__ void load_tile_async(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld, int lane) {
@@ -304,11 +306,15 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   const int h = blockIdx.y;
   const int d = H * HD;
   const int64_t tile0 = (int64_t)blockIdx.x * WARPS + warp, tstride = (int64_t)gridDim.x * WARPS;
+  // cp.async groups are committed in the order [q + k], [v] per tile, and each is awaited only where its tile is first
+  // read ("all but the newest group"), so the v prefetch issued at the very end of a tile overlaps the next tile's
+  // score products instead of being waited for at its top.
   if (tile0 < ntiles) {
     load_tile_async(qs, qkv + h * HD, tile0 * TR, M, 3 * d, lane);
     load_tile_async(ks, qkv + d + h * HD, tile0 * TR, M, 3 * d, lane);
-    load_tile_async(vs, qkv + 2 * d + h * HD, tile0 * TR, M, 3 * d, lane);
   }
+  cp_async_commit();
+  if (tile0 < ntiles) load_tile_async(vs, qkv + 2 * d + h * HD, tile0 * TR, M, 3 * d, lane);
   cp_async_commit();
   for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
     int r = i / 16, c = (i % 16) * 4;
@@ -326,7 +332,7 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
     const int64_t row0 = tile * TR;
     const int64_t nrow0 = (tile + tstride) * TR;
     const bool has_next = tile + tstride < ntiles;
-    cp_async_wait_all();
+    cp_async_wait_but<1>();                         // q and k of this tile have landed (v may still be in flight)
     __syncwarp();
     float sc[2][4], ra[NTR][4], rb[NTR][4];
 #pragma unroll
@@ -430,6 +436,8 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         }
         pv[n][x] = a;
       }
+    cp_async_wait_but<1>();                         // v of this tile has landed (the next q + k may still be in flight)
+    __syncwarp();
     // ---- O = P V (16 x 64), keys contracted in the order this lane's S entries have them
     float oc[8][4];
 #pragma unroll
@@ -729,6 +737,11 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 //     fragments of all eight n-tiles are two LDS.128 and a lane ends up with 16 consecutive output features per row
 //     (64-byte global stores).
 // (4) and (6) share the split Q~ fragments.  The relative tables' gradients stay in registers for the whole kernel.
+// Measured and rejected (34 816 blocks x 16 tokens, 2.65 ms): a warp-PAIR per tile sharing the staging buffers (128
+// registers, 16 warps / SM instead of 8: 2.78 ms) and fully unrolled k-loops (2.75 ms); awaiting each cp.async group only
+// where its tile is first read instead of at the top of the tile changes nothing either - the kernel is bound by its
+// ~2900 dependent-issue-limited instructions per tile (issue slots 27 % busy, no memory or pipe above 60 %), not by load
+// latency or occupancy.
 // A fragment (split) of a row-major [16][PSM] matrix, k-step kk
 __device__ __forceinline__ void load_afrag(const float* __restrict__ X, int kk, int g, int t, uint32_t (&ab)[4], uint32_t (&as)[4]) {
   tf32_split(X[g * PSM + kk * 8 + t], ab[0], as[0]);
@@ -823,15 +836,19 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
     if (keep == 1) load_tile_async(gs, dout + h * HD, r0, M, d, lane);
     else load_tile_compact_async(gs, dout + h * HD, r0, M, d, lane, L, keep);
   };
+  // The next tile's operands are fetched with cp.async into the same buffers as soon as the current tile's last reader is
+  // done: v and dO after (1) + (5), k after (3), q after (4) + (6).  The groups are committed in that order - [v + dO], [k],
+  // [q] - and each is awaited only where its tile is first read ("all but the two newest groups"), so k and q, which are
+  // released late, have the whole front of the next tile to arrive.
   if (tile0 < ntiles) {
-    load_tile_async(qs, qkv + h * HD, tile0 * TR, M, 3 * d, lane);
-    load_tile_async(ks, qkv + d + h * HD, tile0 * TR, M, 3 * d, lane);
     load_tile_async(vs, qkv + 2 * d + h * HD, tile0 * TR, M, 3 * d, lane);
     fetch_g(tile0 * TR);
   }
   cp_async_commit();
-  // The next tile's operands are fetched with cp.async into the same buffers as soon as the current tile's last reader is
-  // done: v and dO after (1) + (5), k after (3), q after (4) + (6).
+  if (tile0 < ntiles) load_tile_async(ks, qkv + d + h * HD, tile0 * TR, M, 3 * d, lane);
+  cp_async_commit();
+  if (tile0 < ntiles) load_tile_async(qs, qkv + h * HD, tile0 * TR, M, 3 * d, lane);
+  cp_async_commit();
   for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
     const int64_t row0 = tile * TR;
     const int64_t nrow0 = (tile + tstride) * TR;
@@ -856,7 +873,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         a[n][x] = v;
         mk[n][x] = m;
       }
-    cp_async_wait_all();
+    cp_async_wait_but<2>();                         // v and dO of this tile have landed
     __syncwarp();
 
     // ---- (1) dA = dO V^T
@@ -942,6 +959,8 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       fetch_g(nrow0);
     }
     cp_async_commit();
+    cp_async_wait_but<2>();                         // k of this tile has landed
+    __syncwarp();
     // ---- (3) dQ~ = dS K + T1 e1 + T2 e2
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -963,6 +982,8 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
     __syncwarp();                                   // k is free
     if (has_next) load_tile_async(ks, qkv + d + h * HD, nrow0, M, 3 * d, lane);
     cp_async_commit();
+    cp_async_wait_but<2>();                         // q of this tile has landed
+    __syncwarp();
     // ---- (4) dK = dS^T Q~ and (6) dE1 += T1^T Q~, dE2 += T2^T Q~ on the same Q~ fragments
 #pragma unroll
     for (int n = 0; n < 8; ++n)
