@@ -9,8 +9,15 @@
 //
 // Blocks are independent length-L sequences (L = 16, then 4), rows are blocks-major: row = p*L + t.
 // One warp owns a 16-row tile (= 16/L whole blocks) of one head (head_dim 64); attention is masked to the block.
-// Everything is fp32 on CUDA cores (0.8 MFLOP per block-layer against ~100 MFLOP of GEMMs); the kernel is bound by
-// the HBM read of QKV / write of O, so q/k/v/e are staged once in shared memory with float4 accesses.
+// Two implementations of the same math:
+//   * attn_fwd_mma_kernel / attn_bwd_mma_kernel (default): every product on the tensor cores, mma.sync.m16n8k8 TF32 with
+//     3xTF32 error compensation (~2^-20 per product), q/k/v/dO tiles staged in shared memory by cp.async with the next
+//     tile prefetched behind the current one.  Forward: 71 % of the HBM roofline; backward: 48 % (instruction bound).
+//   * attn_fwd_kernel / attn_bwd_kernel: plain fp32 FMAs on the CUDA cores (shared-memory-bandwidth bound, 1.4-2.7x slower),
+//     kept for the exact 'fp32' arithmetic mode whose parity tests hold gradients to the fp32 noise floor, and as the
+//     reference of the A/B tests (tests/test_gpu_kernels.py::test_attention_*_both_kernels_agree).
+// The attention FLOPs are small (0.8 MFLOP per block-layer against ~100 MFLOP of GEMMs); what matters is moving 8.7 KB
+// (forward) / 14.8 KB (backward) per token through HBM once.
 #include "common.cuh"
 
 namespace {
@@ -218,7 +225,6 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N newest groups
 
