@@ -238,15 +238,17 @@ __device__ __forceinline__ void load_tile_async(float* s, const float* __restric
     cp_async16(s + r * TS + c, ok ? g + gr * ld + c : g, ok);
   }
 }
+// (keep is a power of two - it divides L in {1, 2, 4, 8, 16} - so the kernels work with kmask = keep - 1 and
+// kshift = log2(keep): no integer divisions in the tile loops)
 __device__ __forceinline__ void load_tile_compact_async(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld,
-                                                        int lane, int L, int keep) {
+                                                        int lane, int L, int kmask, int kshift) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 2 + (lane >> 4), c = (lane & 15) * 4;
     const int64_t gr = row0 + r;
     const int i = (int)(gr % L);
-    const bool ok = gr < M && (i % keep) == 0;
-    cp_async16(s + r * TS + c, ok ? g + ((gr / L) * (L / keep) + i / keep) * ld + c : g, ok);
+    const bool ok = gr < M && (i & kmask) == 0;
+    cp_async16(s + r * TS + c, ok ? g + ((gr / L) * (L >> kshift) + (i >> kshift)) * ld + c : g, ok);
   }
 }
 
@@ -311,6 +313,7 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   float* r2s = qs + TR * PSM;                      //   q . e1 / q . e2 before the skew
   const int h = blockIdx.y;
   const int d = H * HD;
+  const int kmask = keep - 1, kshift = __ffs(keep) - 1;
   const int64_t tile0 = (int64_t)blockIdx.x * WARPS + warp, tstride = (int64_t)gridDim.x * WARPS;
   // cp.async groups are committed in the order [q + k], [v] per tile, and each is awaited only where its tile is first
   // read ("all but the newest group"), so the v prefetch issued at the very end of a tile overlaps the next tile's
@@ -435,7 +438,7 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         float a = pv[n][x] * sm[x >> 1];
         const int64_t gr = row0 + r;
         const int i = r % L;
-        if (gr < M && (i % keep) == 0 && r / L == c / L) {
+        if (gr < M && (i & kmask) == 0 && r / L == c / L) {
           const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
           if (probs != nullptr) probs[pi] = a;
           if (drop_keep != nullptr) a = drop_keep[pi] ? a * drop_scale : 0.f;
@@ -470,8 +473,8 @@ attn_fwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       const int r = g + rr * 8;
       const int64_t gr = row0 + r;
       const int i = r % L;
-      if (gr < M && (i % keep) == 0) {
-        const int64_t off = ((gr / L) * (L / keep) + i / keep) * d + h * HD + 16 * t;
+      if (gr < M && (i & kmask) == 0) {
+        const int64_t off = ((gr / L) * (L >> kshift) + (i >> kshift)) * d + h * HD + 16 * t;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int x = rr * 2 + (q >> 1), n0 = (q & 1) * 4;
@@ -808,6 +811,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   float* T2 = T1 + TR * PSM;             // ... anticausal
   const int h = blockIdx.y;
   const int d = H * HD;
+  const int kmask = keep - 1, kshift = __ffs(keep) - 1;
   for (int i = threadIdx.x; i < TR * 16; i += blockDim.x) {
     int r = i / 16, c = (i % 16) * 4;
     float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -840,7 +844,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
   const int64_t tile0 = (int64_t)blockIdx.x * WARPS + warp, tstride = (int64_t)gridDim.x * WARPS;
   auto fetch_g = [&](int64_t r0) {                          // dO exists for the kept query rows only
     if (keep == 1) load_tile_async(gs, dout + h * HD, r0, M, d, lane);
-    else load_tile_compact_async(gs, dout + h * HD, r0, M, d, lane, L, keep);
+    else load_tile_compact_async(gs, dout + h * HD, r0, M, d, lane, L, kmask, kshift);
   };
   // The next tile's operands are fetched with cp.async into the same buffers as soon as the current tile's last reader is
   // done: v and dO after (1) + (5), k after (3), q after (4) + (6).  The groups are committed in that order - [v + dO], [k],
@@ -871,7 +875,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         const int64_t gr = row0 + r;
         const int i = r % L;
         float v = 0.f, m = 1.f;
-        if (gr < M && (i % keep) == 0 && c / L == r / L) {
+        if (gr < M && (i & kmask) == 0 && c / L == r / L) {
           const int64_t pi = (((gr / L) * H + h) * L + i) * L + (c % L);
           v = probs[pi];
           if (drop_keep != nullptr) m = drop_keep[pi] ? drop_scale : 0.f;
@@ -1123,7 +1127,7 @@ VQ_API int vqcpc_attn_fwd_ex(const float* qkv, const float* e1, const float* e2,
                              float drop_scale, void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_fwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_fwd: bad head count %d", H);
-  VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_fwd: keep=%d must divide L=%d", keep, L);
+  VQ_CHECK_ARG(keep >= 1 && L % keep == 0 && (keep & (keep - 1)) == 0, "attn_fwd: keep=%d must be a power of two dividing L=%d", keep, L);
   VQ_CHECK_ARG((out || out_hi) && ((out_hi == nullptr) == (out_lo == nullptr)), "attn_fwd: need out and/or (out_hi, out_lo)");
   if (P == 0) return VQ_OK;
   cudaStream_t st = vq_stream(stream);
@@ -1155,7 +1159,7 @@ VQ_API int vqcpc_attn_bwd_ex(const float* qkv, const float* e1, const float* e2,
                              void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(H >= 1 && H <= 64, "attn_bwd: bad head count %d", H);
-  VQ_CHECK_ARG(keep >= 1 && L % keep == 0, "attn_bwd: keep=%d must divide L=%d", keep, L);
+  VQ_CHECK_ARG(keep >= 1 && L % keep == 0 && (keep & (keep - 1)) == 0, "attn_bwd: keep=%d must be a power of two dividing L=%d", keep, L);
   VQ_CHECK_ARG((d_qkv || d_qkv_hi) && ((d_qkv_hi == nullptr) == (d_qkv_lo == nullptr)), "attn_bwd: need d_qkv and/or its split");
   if (P == 0) return VQ_OK;
   cudaStream_t st = vq_stream(stream);
