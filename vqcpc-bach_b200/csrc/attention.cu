@@ -194,6 +194,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 // fragments are read with conflict-free LDS.32 (row stride 68 floats), the Q fragment of a k-step is split once and
 // reused by all three products, and P V is a fourth product after the softmax.  ~8x less shared-memory traffic per tile.
 constexpr int PSM = 20;   // padded stride of the 16 x 16 scratch matrices
+static_assert(8 * 132 <= TR * TS, "a pair-interleaved table fits in a [16][TS] slot");
 
 // x = big + small with big = x rounded to TF32 (10 explicit mantissa bits, nearest, ties away: one integer add + mask on
 // the bit pattern; inf stays inf) and small = x - big (exact in fp32).  The tensor core ignores the low 13 mantissa bits of
@@ -230,12 +231,15 @@ __device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wai
 
 // asynchronous versions of load_tile / load_tile_compact (same layout, rows >= M or dropped rows are zero)
 __device__ __forceinline__ void load_tile_async(float* s, const float* __restrict__ g, int64_t row0, int64_t M, int64_t ld, int lane) {
+  const int r0 = lane >> 4, c = (lane & 15) * 4;
+  const float* p = g + (row0 + r0) * ld + c;       // one 64-bit multiply per tile, then pointer steps
+  float* sp = s + r0 * TS + c;
+  const int64_t left = M - row0 - r0;              // row r0 + 2 it exists while 2 it < left
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int r = it * 2 + (lane >> 4), c = (lane & 15) * 4;
-    const int64_t gr = row0 + r;
-    const bool ok = gr < M;
-    cp_async16(s + r * TS + c, ok ? g + gr * ld + c : g, ok);
+    const bool ok = 2 * it < left;
+    cp_async16(sp + it * 2 * TS, ok ? p : g, ok);
+    p += 2 * ld;
   }
 }
 // (keep is a power of two - it divides L in {1, 2, 4, 8, 16} - so the kernels work with kmask = keep - 1 and
@@ -267,17 +271,23 @@ __device__ __forceinline__ void load_bfrag_n(const float* __restrict__ Y, int ra
     tf32_split(yv[n], cb[n], cs[n]);
   }
 }
-// same for a tile stored already split (Yb = big parts, Ys = small parts, as TF32 bit patterns)
-__device__ __forceinline__ void load_bfrag_n_pre(const float* __restrict__ Yb, const float* __restrict__ Ys, int ra, int rb, int g,
+// Relative tables as B operand, split to TF32 once per CTA and stored pair-interleaved: row pair p = kk * 4 + t holds the
+// table rows (kk*8 + t, kk*8 + t + 4) - the k indices t and t + 4 of k-step kk - as [feature][2], row-pair stride TPS.
+// One LDS.128 then returns (b0, b1) of two n-tiles in adjacent registers, exactly what the MMA wants (loading the two rows
+// separately cost two register moves per MMA); TPS = 132 makes the quarter-warp phases bank-conflict free.
+constexpr int TPS = 132;
+__device__ __forceinline__ int tab_index(int r, int f) { return ((r >> 3) * 4 + (r & 3)) * TPS + 2 * f + ((r >> 2) & 1); }
+__device__ __forceinline__ void load_bfrag_n_tab(const float* __restrict__ Tb, const float* __restrict__ Tl, int kk, int t, int g,
                                                  uint32_t (&bb)[8], uint32_t (&bs)[8], uint32_t (&cb)[8], uint32_t (&cs)[8]) {
-  const uint4 x0 = *reinterpret_cast<const uint4*>(Yb + ra * TS + 8 * g), x1 = *reinterpret_cast<const uint4*>(Yb + ra * TS + 8 * g + 4);
-  const uint4 y0 = *reinterpret_cast<const uint4*>(Yb + rb * TS + 8 * g), y1 = *reinterpret_cast<const uint4*>(Yb + rb * TS + 8 * g + 4);
-  const uint4 u0 = *reinterpret_cast<const uint4*>(Ys + ra * TS + 8 * g), u1 = *reinterpret_cast<const uint4*>(Ys + ra * TS + 8 * g + 4);
-  const uint4 w0 = *reinterpret_cast<const uint4*>(Ys + rb * TS + 8 * g), w1 = *reinterpret_cast<const uint4*>(Ys + rb * TS + 8 * g + 4);
-  bb[0] = x0.x; bb[1] = x0.y; bb[2] = x0.z; bb[3] = x0.w; bb[4] = x1.x; bb[5] = x1.y; bb[6] = x1.z; bb[7] = x1.w;
-  cb[0] = y0.x; cb[1] = y0.y; cb[2] = y0.z; cb[3] = y0.w; cb[4] = y1.x; cb[5] = y1.y; cb[6] = y1.z; cb[7] = y1.w;
-  bs[0] = u0.x; bs[1] = u0.y; bs[2] = u0.z; bs[3] = u0.w; bs[4] = u1.x; bs[5] = u1.y; bs[6] = u1.z; bs[7] = u1.w;
-  cs[0] = w0.x; cs[1] = w0.y; cs[2] = w0.z; cs[3] = w0.w; cs[4] = w1.x; cs[5] = w1.y; cs[6] = w1.z; cs[7] = w1.w;
+  const float* pb = Tb + (kk * 4 + t) * TPS + 16 * g;
+  const float* pl = Tl + (kk * 4 + t) * TPS + 16 * g;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 x = *reinterpret_cast<const uint4*>(pb + 4 * i);
+    const uint4 u = *reinterpret_cast<const uint4*>(pl + 4 * i);
+    bb[2 * i] = x.x; cb[2 * i] = x.y; bb[2 * i + 1] = x.z; cb[2 * i + 1] = x.w;
+    bs[2 * i] = u.x; cs[2 * i] = u.y; bs[2 * i + 1] = u.z; cs[2 * i + 1] = u.w;
+  }
 }
 __device__ __forceinline__ void mma_3x_pre(float (&c)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], uint32_t b0b,
                                            uint32_t b0s, uint32_t b1b, uint32_t b1s) {
@@ -795,7 +805,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
                     const unsigned char* __restrict__ drop_keep, float drop_scale) {
   extern __shared__ __align__(16) float smem[];
   constexpr int PER_WARP = 4 * TR * TS + 4 * TR * PSM;
-  float* e1s = smem;                     // [16][TS], rows >= L are zero: TF32 "big" parts of the tables ...
+  float* e1s = smem;                     // rows >= L are zero: TF32 "big" parts of the tables (pair-interleaved, 8 x TPS) ...
   float* e2s = e1s + TR * TS;
   float* e1l = e2s + TR * TS;            // ... and their "small" parts (split once per CTA, not once per tile)
   float* e2l = e1l + TR * TS;
@@ -826,10 +836,14 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
       tf32_split(av[x], ab_[x], as_[x]);
       tf32_split(bv[x], bb_[x], bs_[x]);
     }
-    *reinterpret_cast<uint4*>(e1s + r * TS + c) = make_uint4(ab_[0], ab_[1], ab_[2], ab_[3]);
-    *reinterpret_cast<uint4*>(e1l + r * TS + c) = make_uint4(as_[0], as_[1], as_[2], as_[3]);
-    *reinterpret_cast<uint4*>(e2s + r * TS + c) = make_uint4(bb_[0], bb_[1], bb_[2], bb_[3]);
-    *reinterpret_cast<uint4*>(e2l + r * TS + c) = make_uint4(bs_[0], bs_[1], bs_[2], bs_[3]);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {                  // pair-interleaved layout, see load_bfrag_n_tab
+      const int o = tab_index(r, c + x);
+      e1s[o] = __uint_as_float(ab_[x]);
+      e1l[o] = __uint_as_float(as_[x]);
+      e2s[o] = __uint_as_float(bb_[x]);
+      e2l[o] = __uint_as_float(bs_[x]);
+    }
   }
   __syncthreads();
 
@@ -983,7 +997,7 @@ attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ e1,
         if (which > 0 && kk * 8 >= L) continue;      // table rows >= L are zero
         load_afrag(which == 0 ? Ds : (which == 1 ? T1 : T2), kk, g, t, ab, as);
         if (which == 0) load_bfrag_n(ks, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
-        else load_bfrag_n_pre(which == 1 ? e1s : e2s, which == 1 ? e1l : e2l, kk * 8 + t, kk * 8 + t + 4, g, bb, bs, cb, cs);
+        else load_bfrag_n_tab(which == 1 ? e1s : e2s, which == 1 ? e1l : e2l, kk, t, g, bb, bs, cb, cs);
 #pragma unroll
         for (int n = 0; n < 8; ++n) mma_3x_pre(acc[n], ab, as, bb[n], bs[n], cb[n], cs[n]);
       }
