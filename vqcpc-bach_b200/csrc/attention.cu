@@ -12,7 +12,7 @@
 // Two implementations of the same math:
 //   * attn_fwd_mma_kernel / attn_bwd_mma_kernel (default): every product on the tensor cores, mma.sync.m16n8k8 TF32 with
 //     3xTF32 error compensation (~2^-20 per product), q/k/v/dO tiles staged in shared memory by cp.async with the next
-//     tile prefetched behind the current one.  Forward: 71 % of the HBM roofline; backward: 48 % (instruction bound).
+//     tile prefetched behind the current one.  Forward: 78 % of the HBM roofline; backward: 55 % (instruction bound).
 //   * attn_fwd_kernel / attn_bwd_kernel: plain fp32 FMAs on the CUDA cores (shared-memory-bandwidth bound, 1.4-2.7x slower),
 //     kept for the exact 'fp32' arithmetic mode whose parity tests hold gradients to the fp32 noise floor, and as the
 //     reference of the A/B tests (tests/test_gpu_kernels.py::test_attention_*_both_kernels_agree).
@@ -756,7 +756,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, con
 //     fragments of all eight n-tiles are two LDS.128 and a lane ends up with 16 consecutive output features per row
 //     (64-byte global stores).
 // (4) and (6) share the split Q~ fragments.  The relative tables' gradients stay in registers for the whole kernel.
-// Measured and rejected (34 816 blocks x 16 tokens, 2.65 ms): a warp-PAIR per tile sharing the staging buffers (128
+// Measured and rejected (34 816 blocks x 16 tokens, on the 2.65 ms version): a warp-PAIR per tile sharing the staging buffers (128
 // registers, 16 warps / SM instead of 8: 2.78 ms) and fully unrolled k-loops (2.75 ms); awaiting each cp.async group only
 // where its tile is first read instead of at the top of the tile changes nothing either - the kernel is bound by its
 // ~2900 dependent-issue-limited instructions per tile (issue slots 27 % busy, no memory or pipe above 60 %), not by load
