@@ -38,6 +38,9 @@ UNIT = 'samples/s'
 KL = KR = 8
 NNEG = 15
 CODEBOOK = 512
+# bounded CPU sample of the reference arm / cpu_baseline: ~10 s of work on the GPU box's host cores (CPU throughput is
+# batch independent: 3.3 / 3.5 samples/s at B = 16 / 32 on 8 cores)
+CPU_SAMPLE_BATCH = 32
 FLOPS_PER_SAMPLE = 103.8e9          # fwd+bwd algorithmic (SURVEY.md §8a FLOP accounting), no recompute / dead-row skipping
 
 
@@ -85,7 +88,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle leg
-def cpu_port_samples_per_sec(B_cpu=16, steps=2, warmup=1):
+def cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=2, warmup=1):
     """The reference trainer step as restated by the oracle, on the host cores, at the benchmark shapes with a
     CPU-sized batch (one fp32 activation at B=4096 would be 18 GB; CPU throughput is ~batch independent)."""
     from oracle import params as P, vqcpc_oracle as O
@@ -110,10 +113,10 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    val, info = cpu_port_samples_per_sec(B_cpu=16, steps=steps, warmup=1)
+    val, info = cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=steps, warmup=1)
     line = dict(metric=METRIC, value=val, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps, warmup=1,
-                ms_per_step=1000.0 * 16 / val, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', config=dict(workload=workload_name(args.batch), note='CPU port of the reference step; B=16 sample'),
+                ms_per_step=1000.0 * CPU_SAMPLE_BATCH / val, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=dict(workload=workload_name(args.batch), note=f'CPU port of the reference step; B={CPU_SAMPLE_BATCH} sample'),
                 cpu_baseline=dict(value=val, unit=UNIT, **info),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), file=_OUT, flush=True)
@@ -396,7 +399,7 @@ def run_ours(args):
                     note=f'algorithmic 2MNK FLOPs; the tensor pipe executes {passes}x that (bf16 split passes)')
     cpu_val, cpu_info = (None, None)
     if world == 1 and not args.no_cpu_baseline:
-        cpu_val, cpu_info = cpu_port_samples_per_sec(B_cpu=16, steps=2, warmup=1)
+        cpu_val, cpu_info = cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=2, warmup=1)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16x3 (bf16 hi/lo split on tcgen05, fp32 accumulate; fp32 elsewhere)' if args.mode == 'bf16x3' else args.mode,
