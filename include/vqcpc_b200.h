@@ -112,7 +112,9 @@ int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K, const 
                          const float* bias, const void* residual, int ldr, int flags, float alpha, int scale_ncols,
                          int passes, int ksplit, void* stream);
 
-/* tuning / test hook: force the tcgen05 tile configuration (0 = 128x128x64, 1 = 128x256x32, -1 = automatic by N). */
+/* tuning / test hook: force the tcgen05 tile configuration: 0 = 128x128x64, 1 = 128x256x32, 2 / 3 = 128x256x32 with the
+ * B tile TMA-multicast over a cluster of 2 / 4 CTAs, 4 = CTA pairs (cta_group::2, 256x256 tiles), 5 = 4 with eight epilogue
+ * warps per CTA (experimental), -1 = automatic per shape. */
 int vqcpc_gemm_set_tile_config(int cfg);
 
 /* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +

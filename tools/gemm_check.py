@@ -1,0 +1,60 @@
+"""Quick A/B of two tcgen05 GEMM tile configurations on the forward shapes of the encoder (bit-identical outputs expected:
+the arithmetic per element is the same) + timing.  python tools/gemm_check.py [--cfg -1 5] [--rows 139264]"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'vqcpc-bach_b200')):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+from VQCPCB import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--cfg', type=int, nargs='+', default=[-1, 5])
+    ap.add_argument('--rows', type=int, default=139264)
+    ap.add_argument('--iters', type=int, default=8)
+    a = ap.parse_args()
+    M = a.rows
+    g = torch.Generator(device='cuda')
+    g.manual_seed(0)
+    cases = [('out  K512 N512  bias+residual', 512, 512, dict(residual=True)),
+             ('qkv  K512 N1536 bias+scale', 1536, 512, dict(scale=True)),
+             ('ffn1 K512 N2048 bias+relu->split', 2048, 512, dict(relu=True, split=True)),
+             ('ffn2 K2048 N512 bias+residual', 512, 2048, dict(residual=True))]
+    for name, N, K, o in cases:
+        x = torch.randn(M, K, device='cuda', generator=g)
+        w = torch.randn(N, K, device='cuda', generator=g) * 0.05
+        b = torch.randn(N, device='cuda', generator=g)
+        res = torch.randn(M, N, device='cuda', generator=g) if o.get('residual') else None
+        xs, ws = ops.split_bf16(x), ops.split_bf16(w)
+        outs, times = {}, {}
+        for cfg in a.cfg:
+            ops.set_tile_config(cfg)
+
+            def run():
+                return ops.gemm(None, None, M, N, K, bias=b, residual=res, relu=bool(o.get('relu')),
+                                scale_cols=(0.125, N // 3) if o.get('scale') else None, a_split=xs, b_split=ws,
+                                want_c=not o.get('split'), out_split=bool(o.get('split')))
+            r = run()
+            torch.cuda.synchronize()
+            outs[cfg] = r[1] if o.get('split') else (r,)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            times[cfg] = e0.elapsed_time(e1) * 1e3 / a.iters
+        ops.set_tile_config(-1)
+        ref = outs[a.cfg[0]]
+        same = all(all(torch.equal(u, v) for u, v in zip(outs[c], ref)) for c in a.cfg[1:])
+        fl = 2.0 * M * N * K * 3
+        print(f'{name}: ' + '  '.join(f'cfg {c}: {times[c]:8.1f} us {fl / times[c] / 1e6:7.1f} tensor-TFLOP/s' for c in a.cfg) +
+              f'  identical={same}', flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -24,7 +24,7 @@ _WSPLIT_CACHE = {}          # id(param storage) -> (version, hi, lo)
 
 
 def set_tile_config(cfg):
-    """Force the tcgen05 tile configuration: 0 = 128x128x64, 1 = 128x256x32, -1 = automatic (by N)."""
+    """Force the tcgen05 tile configuration (see vqcpc_gemm_set_tile_config in include/vqcpc_b200.h): 0 .. 5, -1 = automatic."""
     _native.call('vqcpc_gemm_set_tile_config', int(cfg))
 
 

@@ -360,7 +360,9 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
-  const int cfg = pick_cfg(M, N, b_kmajor != 0);
+  int cfg = pick_cfg(M, N, b_kmajor != 0);
+  const bool epw8 = cfg == 5;                        // configuration 5 = configuration 4 with eight epilogue warps per CTA
+  if (epw8) cfg = 4;
   const int BN = cfg >= 1 ? 256 : 128, BK = (cfg >= 1 && cfg <= 3) ? 32 : 64;
   const int CLh = cfg == 3 ? 4 : (cfg == 2 || cfg == 4 ? 2 : 1);   // B K-major boxes cover BN / CL rows (pair: own half)
   p.m_tiles = (int)vq_cdiv(M, BM);
@@ -395,7 +397,7 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
     if ((rc = tc_make_map(&maps[3], blo, K, N, ldb, 64, BK)) != VQ_OK) return rc;
   }
 
-  if (cfg == 4) return tc_launch_pair(a_kmajor, b_kmajor, passes, maps, p, st);
+  if (cfg == 4) return tc_launch_pair(a_kmajor, b_kmajor, passes, maps, p, st, epw8);
   if (a_kmajor && b_kmajor) return launch_tc<true, true>(cfg, passes, maps, p, st);
   if (a_kmajor && !b_kmajor) return launch_tc<true, false>(cfg, passes, maps, p, st);
   if (!a_kmajor && b_kmajor) return launch_tc<false, true>(cfg, passes, maps, p, st);
@@ -403,9 +405,10 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
 }
 
 // Testing / tuning hook: force a tile configuration (0 = 128x128x64, 1 = 128x256x32, 2 / 3 = 128x256x32 with the B tile
-// multicast over a cluster of 2 / 4 CTAs, 4 = CTA pairs with 256x256x32 tiles, -1 = automatic).
+// multicast over a cluster of 2 / 4 CTAs, 4 = CTA pairs with 256x256x32 tiles, 5 = 4 with eight epilogue warps per CTA
+// (experimental), -1 = automatic).
 VQ_API int vqcpc_gemm_set_tile_config(int cfg) {
-  VQ_CHECK_ARG(cfg >= -1 && cfg <= 4, "gemm_set_tile_config: cfg must be -1 .. 4");
+  VQ_CHECK_ARG(cfg >= -1 && cfg <= 5, "gemm_set_tile_config: cfg must be -1 .. 5");
   g_force_cfg = cfg;
   return VQ_OK;
 }

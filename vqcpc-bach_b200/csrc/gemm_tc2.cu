@@ -54,8 +54,11 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(bool a_kmajor, bool b_kma
          ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);      // M = 256 across the pair, N = 256
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES>
-__global__ void __launch_bounds__(THREADS, 1)
+// EPW = number of epilogue warps per CTA: 4 (warps 2..5, one per TMEM lane quadrant, all 256 columns each) or 8 (warps 2..9:
+// warps w and w + 4 share a lane quadrant and drain 128 columns each - halves the epilogue latency per tile, which is what
+// bounds the K = 512 shapes; experimental, tile configuration 5).
+template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES, int EPW = 4>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
   constexpr int TILE_A_BYTES = BM * BK2 * 2;            // 8 KB  (own 128 rows)
@@ -85,7 +88,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 8);           // 4 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * EPW);     // EPW epilogue warps x 2 CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,7 +210,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
-      epilogue_tile<BN2>(p, taddr, m0, n0, q, lane, first_split);
+      if constexpr (EPW == 8) {
+        if (warp < 6) epilogue_tile<BN2, 0, BN2 / 64>(p, taddr, m0, n0, q, lane, first_split);
+        else epilogue_tile<BN2, BN2 / 64, BN2 / 32>(p, taddr, m0, n0, q, lane, first_split);
+      } else {
+        epilogue_tile<BN2>(p, taddr, m0, n0, q, lane, first_split);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // leader's barrier
@@ -224,12 +232,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   }
 }
 
-template <bool AK, bool BKM, int PASSES, int STAGES>
+template <bool AK, bool BKM, int PASSES, int STAGES, int EPW = 4>
 int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK2 * 2 + HALF_N * BK2 * 2);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
-  auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES>;
+  auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES, EPW>;
   static bool done = false;
   if (!done) {
     VQ_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -240,7 +248,7 @@ int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   const int clusters = std::max(1, std::min(items, vq_sm_count() / 2));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * 2));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(64 + 32 * EPW);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -262,7 +270,14 @@ int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 
 // Tile configuration 4 of vqcpc_gemm_bf16x3_ex: CTA pairs, 256 x 256 x 32 tiles.  `p` carries m_tiles in units of 128
 // rows and n_tiles in units of 256 columns; maps[2..3] (B) must use boxes of 128 rows (K-major) / 64 x 32 (MN-major).
-int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st,
+                         bool eight_epilogue_warps) {
+  if (eight_epilogue_warps && passes == 3) {
+    if (a_kmajor && b_kmajor) return launch_pair<true, true, 3, 3, 8>(maps, p, st);
+    if (a_kmajor && !b_kmajor) return launch_pair<true, false, 3, 3, 8>(maps, p, st);
+    if (!a_kmajor && b_kmajor) return launch_pair<false, true, 3, 3, 8>(maps, p, st);
+    return launch_pair<false, false, 3, 3, 8>(maps, p, st);
+  }
   if (a_kmajor && b_kmajor) return passes == 3 ? launch_pair<true, true, 3, 3>(maps, p, st) : launch_pair<true, true, 1, 6>(maps, p, st);
   if (a_kmajor && !b_kmajor) return passes == 3 ? launch_pair<true, false, 3, 3>(maps, p, st) : launch_pair<true, false, 1, 6>(maps, p, st);
   if (!a_kmajor && b_kmajor) return passes == 3 ? launch_pair<false, true, 3, 3>(maps, p, st) : launch_pair<false, true, 1, 6>(maps, p, st);

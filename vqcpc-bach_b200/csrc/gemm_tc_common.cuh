@@ -173,11 +173,13 @@ struct TcParams {
 
 // Epilogue of one 128 x BN accumulator tile held in TMEM at `taddr` (lane quadrant q of this warp): 32-column chunks,
 // tcgen05.ld -> fused bias / scale / residual / ReLU / mask -> fp32 and / or bf16-split stores (or atomics for split-K).
-template <int BN>
+// CH0 / CH1: range of 32-column chunks this warp drains (all of them by default; the 8-epilogue-warp variant of the pair
+// kernel gives each of the two warps of a lane quadrant one half of the columns).
+template <int BN, int CH0 = 0, int CH1 = BN / 32>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane, bool first_split) {
   const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-for (int ch = 0; ch < BN / 32; ++ch) {
+for (int ch = CH0; ch < CH1; ++ch) {
   uint32_t r[32];
   tmem_ld32(taddr + ch * 32, r);
   tmem_ld_wait();
@@ -304,6 +306,7 @@ for (int ch = 0; ch < BN / 32; ++ch) {
 int tc_get_encode();
 int tc_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows);
 // CTA-pair kernel (gemm_tc2.cu)
-int tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st);
+int tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st,
+                   bool eight_epilogue_warps = false);
 
 }  // namespace vqtc
