@@ -1,5 +1,5 @@
-"""Quick A/B of two tcgen05 GEMM tile configurations on the forward shapes of the encoder (bit-identical outputs expected:
-the arithmetic per element is the same) + timing.  python tools/gemm_check.py [--cfg -1 5] [--rows 139264]"""
+"""Quick A/B of two tcgen05 GEMM tile configurations on the forward shapes of the encoder (identical outputs expected - the
+arithmetic per element is the same; compared through an integer fingerprint) + timing.  python tools/gemm_check.py [--cfg -1 5] [--rows 139264]"""
 import argparse
 import os
 import sys
@@ -40,7 +40,13 @@ def main():
                                 want_c=not o.get('split'), out_split=bool(o.get('split')))
             r = run()
             torch.cuda.synchronize()
-            outs[cfg] = r[1] if o.get('split') else (r,)
+            res_t = r[1] if o.get('split') else (r,)
+            # keep only a fingerprint: holding the outputs would make every timed call cudaMalloc a fresh block
+            outs[cfg] = tuple(int(t.view(torch.int16).to(torch.int64).sum().item()) for t in res_t)
+            del r, res_t
+            for _ in range(3):                       # warm-up: the caching allocator now owns reusable output blocks
+                run()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.iters):
@@ -49,8 +55,7 @@ def main():
             torch.cuda.synchronize()
             times[cfg] = e0.elapsed_time(e1) * 1e3 / a.iters
         ops.set_tile_config(-1)
-        ref = outs[a.cfg[0]]
-        same = all(all(torch.equal(u, v) for u, v in zip(outs[c], ref)) for c in a.cfg[1:])
+        same = all(outs[c] == outs[a.cfg[0]] for c in a.cfg[1:])
         fl = 2.0 * M * N * K * 3
         print(f'{name}: ' + '  '.join(f'cfg {c}: {times[c]:8.1f} us {fl / times[c] / 1e6:7.1f} tensor-TFLOP/s' for c in a.cfg) +
               f'  identical={same}', flush=True)
