@@ -105,3 +105,35 @@ def test_lr_lambda_shape():
     assert abs(O.lr_lambda(0) - 0.1) < 1e-12
     assert abs(O.lr_lambda(10000) - 1.0) < 1e-9
     assert O.lr_lambda(10 ** 7) == 0.1
+
+
+def test_tf32_split_error_bound():
+    """The attention kernels split an fp32 value for the 3xTF32 products with one integer add + mask
+    (csrc/attention.cu::tf32_split): big = x rounded to 10 explicit mantissa bits (nearest, ties away), small = x - big
+    (exact in fp32), of which the tensor core reads the top 10 explicit mantissa bits.  Emulated here bit for bit:
+    |x - big - tf32(small)| <= 2^-21 |x|, and the three-term product a_big b_big + a_big b_small + a_small b_big
+    misses a*b by less than 2^-19.9 |a b| - the figure quoted in DESIGN.md / attention.cu.  (Magnitudes whose small part
+    would be denormal, |x| < 2^-115, are outside the claim: activations never get there.)"""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(200000).astype(np.float32) * 3, np.float32(2.0) ** rng.integers(-60, 60, 2000),
+                        np.array([1.0, -1.0, 1.0009765625, 0.99951171875, 3.4e38, 1e-30], dtype=np.float32)]).astype(np.float32)
+
+    def split(v):
+        bits = v.view(np.uint32)
+        big = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+        small = (v - big).astype(np.float32)
+        assert np.all((big.astype(np.float64) + small.astype(np.float64)) == v.astype(np.float64))   # the subtraction is exact
+        small_tc = (small.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)                     # what the MMA reads
+        return big.astype(np.float64), small_tc.astype(np.float64)
+
+    big, small = split(x)
+    err = np.abs(x.astype(np.float64) - big - small)
+    assert np.all(err <= 2.0 ** -21 * np.abs(x.astype(np.float64)))
+    a, b = x[:100000], x[100000:200000]
+    ab, asm = split(a)
+    bb, bsm = split(b)
+    prod = ab * bb + ab * bsm + asm * bb
+    exact = a.astype(np.float64) * b.astype(np.float64)
+    rel = np.abs(prod - exact) / np.abs(exact)
+    assert rel.max() < 2.0 ** -19.9, rel.max()
