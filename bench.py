@@ -88,11 +88,26 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle leg
-def cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=2, warmup=1):
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every worker; the CPU legs must use the box's cores."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=2, warmup=1, dropout=0.0):
     """The reference trainer step as restated by the oracle, on the host cores, at the benchmark shapes with a
-    CPU-sized batch (one fp32 activation at B=4096 would be 18 GB; CPU throughput is ~batch independent)."""
+    CPU-sized batch (one fp32 activation at B=4096 would be 18 GB; CPU throughput is ~batch independent).
+    dropout > 0: fresh F.dropout draws at the reference's sites (the shipped training setting, p = 0.1)."""
     from oracle import params as P, vqcpc_oracle as O
+    cores = use_all_host_threads()
     cfg = O.default_cfg(codebook_size=CODEBOOK, KL=KL, KR=KR, N=NNEG)
+    if dropout > 0:
+        cfg['dropout'] = float(dropout)
     prm = P.make_params(cfg, 0)
     m = v = None
     t_total = 0.0
@@ -103,22 +118,28 @@ def cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=2, warmup=1):
         dt = time.perf_counter() - t0
         if i >= warmup:
             t_total += dt
-    return B_cpu * steps / t_total, dict(cores=torch.get_num_threads(), kind='port',
+    return B_cpu * steps / t_total, dict(cores=cores, kind='port', dropout=dropout,
                                          sample=f'{steps} steps of B={B_cpu} at the benchmark shapes (seq 256, K={CODEBOOK}, N=15), '
-                                                f'{warmup} warm-up, torch {torch.__version__} CPU fp32, oracle/vqcpc_oracle.trainer_step')
+                                                f'{warmup} warm-up, torch {torch.__version__} CPU fp32 on {cores} threads, '
+                                                f'oracle/vqcpc_oracle.trainer_step')
 
 
 def run_reference(args):
+    """--impl reference: the CPU port of the reference step with all host threads; honours --steps / --warmup (every step
+    is a bounded B=32 sample of the workload, ~2-3 s on 16 cores).  Under torchrun only rank 0 works."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    val, info = cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=steps, warmup=1)
-    line = dict(metric=METRIC, value=val, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps, warmup=1,
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, info = cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=steps, warmup=warmup)
+    line = dict(metric=METRIC, value=val, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=1000.0 * CPU_SAMPLE_BATCH / val, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', config=dict(workload=workload_name(args.batch), note=f'CPU port of the reference step; B={CPU_SAMPLE_BATCH} sample'),
+                data='synthetic', config=dict(workload=workload_name(args.batch), note=f'CPU port of the reference step; B={CPU_SAMPLE_BATCH} sample per step'),
                 cpu_baseline=dict(value=val, unit=UNIT, **info),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    if not args.no_dropout_line:
+        dval, dinfo = cpu_port_samples_per_sec(B_cpu=CPU_SAMPLE_BATCH, steps=min(steps, 3), warmup=1, dropout=0.1)
+        line['with_dropout'] = dict(value=dval, unit=UNIT, **dinfo)
     print(json.dumps(line), file=_OUT, flush=True)
 
 
@@ -302,6 +323,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ops.PROFILE_GEMM = []
+    vq_dist.COLLECTIVE_EVENTS = [] if world > 1 else None
     launches0 = _native.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -319,9 +341,27 @@ def run_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = t.item()
     loss_val = float(st['loss'].item())
+    # per-rank step time (skew) and the collective: min / max over ranks of the same timed region, and the all-reduce of
+    # the flat [grads | stats | counts] buffer bracketed by CUDA events inside the optimizer (vq_dist.COLLECTIVE_EVENTS)
+    skew = None
+    coll = None
+    if world > 1:
+        tmin = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(tmin, op=torch.distributed.ReduceOp.MIN)
+        skew = dict(min_ms_per_step=tmin.item() / args.steps, max_ms_per_step=ms / args.steps)
+        evs = vq_dist.COLLECTIVE_EVENTS or []
+        if evs:
+            torch.cuda.synchronize()
+            per = [a.elapsed_time(b) for a, b in evs]
+            tc_ = torch.tensor([sum(per) / len(per), max(per)], dtype=torch.float64, device='cuda')
+            torch.distributed.all_reduce(tc_, op=torch.distributed.ReduceOp.MAX)
+            coll = dict(allreduce_ms_mean=tc_[0].item(), allreduce_ms_max=tc_[1].item(), calls=len(per),
+                        bytes=int(tr.optimizer.flat.grad_full.numel() * 4),
+                        note='ncclAllReduce of the flat buffer incl. the wait for the slowest rank (max over ranks)')
+    vq_dist.COLLECTIVE_EVENTS = None
 
     # ---- timed: end to end through the public call with HOST buffers + D2H loss read every step
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
     tr.step(host_batches[0], True, False)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -368,7 +408,20 @@ def run_ours(args):
         del dev_batches
         torch.cuda.empty_cache()
         qi = bench_quantizer_infonce(B)
+    replicas = None
     if world > 1:
+        # data-parallel correctness: after all these steps (the first of which re-initialised the codebook from data)
+        # every rank must hold BIT-identical parameters
+        flat = tr.optimizer.flat.data
+        bits = flat.view(torch.int32).long()
+        wts = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.long)
+        chk = torch.stack([(bits * wts).sum(), (bits ^ (wts * 2654435761)).sum()])
+        got = [torch.zeros_like(chk) for _ in range(world)]
+        torch.distributed.all_gather(got, chk)
+        same = all(torch.equal(g, got[0]) for g in got)
+        replicas = dict(identical_parameters=bool(same), checksum=[int(v) for v in got[0].tolist()], ranks=world,
+                        global_usage_sum=int(tr.encoder.quantizer.global_usage.sum().item()))
+        assert same, 'data-parallel replicas diverged: %s' % [g.tolist() for g in got]
         try:
             torch.distributed.destroy_process_group()
         except Exception:
@@ -412,6 +465,12 @@ def run_ours(args):
                 step_tensor_frac=dict(achieved_tflops=value / world * FLOPS_PER_SAMPLE / 1e12, peak=pk['tflops'],
                                       frac=value / world * FLOPS_PER_SAMPLE / 1e12 / pk['tflops'],
                                       note='whole step: samples/s/GPU x 103.8 GFLOP algorithmic / sustained bf16 peak'))
+    if skew is not None:
+        line['rank_skew'] = skew
+    if coll is not None:
+        line['collective'] = coll
+    if replicas is not None:
+        line['replicas'] = replicas
     if roof:
         line['roofline'] = roof
     if cpu_val is not None:

@@ -88,6 +88,9 @@ int vqcpc_mask_scale_add(const float* x, const unsigned char* keep, float scale,
                          void* out_hi, void* out_lo, int64_t n, void* stream);
 /* out[0] = scale * sum(x[0..n)) in a fixed order (deterministic). */
 int vqcpc_reduce_sum(const float* x, int64_t n, float* out, float scale, void* stream);
+/* Code-usage histogram: counts[idx[i]] += 1 for 0 <= idx[i] < bins (int32, ACCUMULATED).  Replaces the torch.unique
+ * monitoring of VQCPCB/vqcpc_encoder_trainer.py:325-331 and feeds the per-code counts of the data-parallel all-reduce. */
+int vqcpc_code_hist(const int64_t* idx, int64_t n, int bins, int* counts, void* stream);
 
 /* ---- GEMMs (F.linear / matmul call sites: multihead_attention_custom.py:171,346; transformer_custom.py:285;
  *      relative_transformer_downscaler.py:104,132; mlp_upscaler.py:21-26; vqcpc_helper.py:69 and their backward) -------

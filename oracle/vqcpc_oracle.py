@@ -118,7 +118,9 @@ def mha_self(x, prm, pre, H, return_probs=False, attn_keep=None):
     s = torch.matmul(q, k.transpose(-1, -2))         # :314
     s = s + rel_bias(q, prm[pre + 'attn_bias.e1'], prm[pre + 'attn_bias.e2'])   # :331-333
     a = torch.softmax(s, dim=-1)                     # :338
-    if attn_keep is not None:                        # :339 F.dropout on the weights, replayed from an explicit mask
+    if isinstance(attn_keep, float):                 # :339 F.dropout on the weights, fresh draw (CPU-baseline timing only)
+        a = F.dropout(a, attn_keep, training=True)
+    elif attn_keep is not None:                      # ... or replayed from an explicit mask
         a = a * attn_keep                            # (keep / (1 - p), shape (P, H, L, L))
     o = torch.matmul(a, v).transpose(1, 2).reshape(P, L, d)    # :343-345
     out = F.linear(o, prm[pre + 'out_proj.weight'], prm[pre + 'out_proj.bias'])  # :346
@@ -134,6 +136,15 @@ def encoder_layer(x, prm, pre, H, drop=None):
     'attn' (P, H, L, L) on the attention weights, 'drop1' / 'drop2' (P, L, d) on the two residual branches (:278, :287),
     'ffn' (P, L, F) after the activation (:283)."""
     d = x.shape[-1]
+    if isinstance(drop, float):
+        # fresh draws at the reference's four sites (the training setting of the shipped configs, p = 0.1).  RNG streams
+        # cannot be compared with anything, so this branch exists for the CPU-baseline TIMING line only.
+        p = drop
+        a = F.dropout(mha_self(x, prm, pre + 'self_attn.', H, attn_keep=p), p, training=True)
+        x = F.layer_norm(x + a, (d,), prm[pre + 'norm1.weight'], prm[pre + 'norm1.bias'], 1e-5)
+        hid = F.dropout(torch.relu(F.linear(x, prm[pre + 'linear1.weight'], prm[pre + 'linear1.bias'])), p, training=True)
+        f = F.dropout(F.linear(hid, prm[pre + 'linear2.weight'], prm[pre + 'linear2.bias']), p, training=True)
+        return F.layer_norm(x + f, (d,), prm[pre + 'norm2.weight'], prm[pre + 'norm2.bias'], 1e-5)
     a = mha_self(x, prm, pre + 'self_attn.', H, attn_keep=None if drop is None else drop['attn'])
     if drop is not None:
         a = a * drop['drop1']
@@ -164,6 +175,9 @@ def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None, drops=None)
     h = torch.cat([h, chan[t % V].expand(b * nb, S, -1), evt[t // V].expand(b * nb, S, -1)], dim=-1)   # :106-112
     if trace is not None:
         trace['h0'] = h
+    p_draw = float(cfg.get('dropout', 0.0))
+    if drops is None and p_draw > 0:
+        drops = [p_draw] * sum(cfg.list_of_num_layers)
     for s, (factor, nl) in enumerate(zip(cfg.downscale_factors, cfg.list_of_num_layers)):   # :122-124
         for l in range(nl):
             h = encoder_layer(h, prm, f'{pre}transformers.{s}.layers.{l}.', cfg.n_head,
@@ -185,8 +199,10 @@ def downscaler_forward(emb, prm, cfg, pre='downscaler.', trace=None, drops=None)
 # --------------------------------------------------------------------------------------------
 # quantizer / upscaler
 # --------------------------------------------------------------------------------------------
-def quantize(z, codebooks, commitment_cost, squared_l2_norm=True):
-    """VQCPCB/quantizer/vector_quantizer.py:85-159 (no batch-norm, no init, no label corruption).
+def quantize(z, codebooks, commitment_cost, squared_l2_norm=True, given_idx=None):
+    """VQCPCB/quantizer/vector_quantizer.py:85-159 (no batch-norm, no init).  Label corruption (:118-132) replaces a
+    random 5 % of the searched indices; RNG streams cannot be matched, so the caller passes the already corrupted
+    indices as ``given_idx`` (n, ncb) and the search is skipped for them.
 
     z (..., D); codebooks: list of (Kc, D/ncb).  Returns (z_sg, idx int64 (..., ncb), loss (...))."""
     shp = z.shape
@@ -194,7 +210,11 @@ def quantize(z, codebooks, commitment_cost, squared_l2_norm=True):
     flat = z.reshape(-1, D)
     ncb = len(codebooks)
     idxs, qs = [], []
-    for comp, E in zip(flat.chunk(ncb, dim=1), codebooks):
+    for ci, (comp, E) in enumerate(zip(flat.chunk(ncb, dim=1), codebooks)):
+        if given_idx is not None:
+            idxs.append(given_idx.reshape(-1, ncb)[:, ci])
+            qs.append(E[idxs[-1]])
+            continue
         dist = torch.sum((comp.unsqueeze(1) - E.unsqueeze(0)) ** 2, dim=2)      # :105-112
         idx = torch.argmin(dist, dim=1)                                         # :115-116 first-min tie rule
         idxs.append(idx)
@@ -212,9 +232,12 @@ def quantize(z, codebooks, commitment_cost, squared_l2_norm=True):
     return z_sg, idx, loss
 
 
-def upscale(zq, prm, pre='upscaler.'):
-    """VQCPCB/upscalers/mlp_upscaler.py:21-35: Linear -> (Dropout p=0) -> SELU -> Linear."""
-    h = F.selu(F.linear(zq, prm[pre + 'mlp.0.weight'], prm[pre + 'mlp.0.bias']))
+def upscale(zq, prm, pre='upscaler.', p=0.0):
+    """VQCPCB/upscalers/mlp_upscaler.py:21-35: Linear -> Dropout(p) -> SELU -> Linear (p > 0: fresh draw, timing only)."""
+    h = F.linear(zq, prm[pre + 'mlp.0.weight'], prm[pre + 'mlp.0.bias'])
+    if p > 0:
+        h = F.dropout(h, p, training=True)
+    h = F.selu(h)
     return F.linear(h, prm[pre + 'mlp.3.weight'], prm[pre + 'mlp.3.bias'])
 
 
@@ -238,14 +261,14 @@ def encoder_forward(x, prm, cfg, trace=None):
         books = [prm[f'quantizer.embeddings.{i}'] for i in range(cfg.num_codebooks)]
         zq, idx, ql = quantize(z, books, cfg.commitment_cost, cfg.squared_l2_norm)
     if cfg.upscaler:
-        zq = upscale(zq, prm)
+        zq = upscale(zq, prm, p=float(cfg.get('dropout', 0.0)))
     return zq, idx, ql
 
 
 # --------------------------------------------------------------------------------------------
 # CPC heads
 # --------------------------------------------------------------------------------------------
-def gru_stack(x, prm, pre, layers, hidden):
+def gru_stack(x, prm, pre, layers, hidden, p=0.0):
     """torch.nn.GRU(batch_first=True, h0 = 0) as explicit math: gate order (r, z, n),
     n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) n + z h.  x (B, T, in) -> (B, T, hidden)."""
     B, T, _ = x.shape
@@ -265,12 +288,14 @@ def gru_stack(x, prm, pre, layers, hidden):
             h = (1 - zg) * n + zg * h
             outs.append(h)
         x = torch.stack(outs, 1)
+        if p > 0 and l < layers - 1:                 # nn.GRU(dropout=p): between layers only (fresh draw, timing only)
+            x = F.dropout(x, p, training=True)
     return x
 
 
 def gru_c(y_left, prm, cfg, pre='c_module.'):
     """VQCPCB/vqcpc_helper.py:54-76: multi-layer GRU (batch_first, h0=0), last time step, Linear."""
-    x = gru_stack(y_left, prm, pre + 'g_ar_fwd.', cfg.c_layers, cfg.c_hidden)
+    x = gru_stack(y_left, prm, pre + 'g_ar_fwd.', cfg.c_layers, cfg.c_hidden, p=float(cfg.get('dropout', 0.0)))
     return F.linear(x[:, -1], prm[pre + 'output_linear.weight'], prm[pre + 'output_linear.bias'])
 
 

@@ -26,8 +26,12 @@ def build_product_encoder(cfg, model_dir='/tmp/vqcpc_b200_test'):
     else:
         down = RelativeTransformerDownscaler(cfg.embedding_size, cfg.codebook_dim, cfg.num_voices, list(cfg.downscale_factors),
                                              cfg.d_model, cfg.n_head, list(cfg.list_of_num_layers), cfg.dim_feedforward, 0.0)
-    vq = ProductVectorQuantizer(cfg.codebook_size, cfg.codebook_dim, cfg.commitment_cost, cfg.num_codebooks, False, False,
-                                cfg.squared_l2_norm)
+    if cfg.codebook_size is None:
+        from VQCPCB.quantizer.vector_quantizer import NoQuantization
+        vq = NoQuantization(cfg.codebook_dim)
+    else:
+        vq = ProductVectorQuantizer(cfg.codebook_size, cfg.codebook_dim, cfg.commitment_cost, cfg.num_codebooks, False, False,
+                                    cfg.squared_l2_norm)
     up = MlpUpscaler(cfg.codebook_dim, cfg.z_dim, cfg.up_hidden, 0.0) if cfg.upscaler else None
     return Encoder(model_dir, dp, down, vq, up)
 

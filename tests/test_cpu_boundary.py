@@ -183,12 +183,41 @@ opt = FusedClipAdam.__new__(FusedClipAdam); opt.flat = flat
 flat.attach_grads(tail=16)
 flat.grad.fill_(float(rank + 1))                        # rank0: 1, rank1: 2
 sums = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1); correct = torch.tensor([4.0, 8.0]) * (rank + 1)
-counts = torch.tensor([1, 0, 2, 0], dtype=torch.int32) * (rank + 1)
-scale = FusedClipAdam.all_reduce(opt, stats=(sums, correct), counts=counts)
+# counts beyond 2^24 (not representable in one fp32) must still sum exactly: they travel as two 12-bit-split halves
+big = 20_000_003
+counts = torch.tensor([[1, 0, 2, big], [7, 4095, 4096, 0]], dtype=torch.int32) * (rank + 1)
+assert FusedClipAdam.tail_elems(5, counts.numel()) <= 21
+flat.attach_grads(tail=21)
+flat.grad.fill_(float(rank + 1))
+scale = FusedClipAdam.all_reduce(opt, stats=(sums, correct), counts=[counts])
 assert scale == 0.5
 assert flat.grad.eq(3.0).all()                          # summed gradients; update applies scale 1/world
 assert torch.allclose(sums, torch.tensor([1.5, 3.0, 4.5])) and torch.allclose(correct, torch.tensor([6.0, 12.0]))
-assert counts.tolist() == [3, 0, 6, 0]
+assert counts.tolist() == [[3, 0, 6, 3 * big], [21, 3 * 4095, 3 * 4096, 0]], counts.tolist()
+# data-dependent codebook initialisation (quirk Q5) under data parallelism: every rank draws from ITS OWN first batch,
+# rank 0's draw must win on all replicas (reference: quantizer/vector_quantizer.py:57-70 has no collective at all)
+from VQCPCB.quantizer.vector_quantizer import ProductVectorQuantizer
+torch.manual_seed(100 + rank)
+vq = ProductVectorQuantizer(8, 4, 0.25, 2, False, True, True)
+data = torch.randn(64, 4)
+vq._initialize(data)
+assert vq.initialize is False
+cb = torch.cat([e.detach().reshape(-1) for e in vq.embeddings])
+got = [torch.zeros_like(cb) for _ in range(2)]
+dist.all_gather(got, cb)
+assert torch.equal(got[0], got[1]), "codebooks differ across ranks after the data-dependent init"
+rows0 = [torch.zeros_like(data) for _ in range(2)]
+dist.all_gather(rows0, data)
+for k, e in enumerate(vq.embeddings):                   # every code is a row of RANK 0's batch
+    src = rows0[0][:, 2 * k:2 * k + 2]
+    assert all((src == r).all(1).any() for r in e.detach())
+vq2 = ProductVectorQuantizer(8, 4, 0.25, 1, False, True, True)
+vq2.sync_init = False                                   # opt-out: single-process use inside a process group
+vq2._initialize(data)
+cb2 = vq2.embeddings[0].detach().reshape(-1)
+got2 = [torch.zeros_like(cb2) for _ in range(2)]
+dist.all_gather(got2, cb2)
+assert not torch.equal(got2[0], got2[1])
 assert vq_dist.shard_seed(1234) == 1234 + rank
 vq_dist.barrier()
 sys.stdout.write(f"rank{rank}ok\n"); sys.stdout.flush()

@@ -32,6 +32,7 @@ SIGNATURES = {
     'vqcpc_mask_scale_add': [_P, _P, _F, _P, _P, _P, _P, _L, _P],
     'vqcpc_split_bf16': [_P, _I, _P, _P, _I, _L, _I, _P],
     'vqcpc_reduce_sum': [_P, _L, _P, _F, _P],
+    'vqcpc_code_hist': [_P, _L, _I, _P, _P],
     'vqcpc_gemm_f32': [_I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P],
     'vqcpc_gemm_bf16x3': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
     'vqcpc_gemm_bf16x3_ex': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],

@@ -3,7 +3,7 @@ schema of its ``encoder_random_transfo_config.py`` with the two keys that file f
 ``c_net_kwargs['bidirectional']`` — filled in, K=512 codes, a 256-token window (8 + 8 blocks) and dropout 0).
 
 Environment overrides (used by bench.py / tests, so one file covers configs[0..2] of BASELINE.json):
-    VQCPC_BATCH, VQCPC_BLOCKS (left == right), VQCPC_CODEBOOK, VQCPC_DATASET
+    VQCPC_BATCH, VQCPC_BLOCKS (left == right), VQCPC_CODEBOOK, VQCPC_DATASET, VQCPC_NUM_BATCHES, VQCPC_EPOCHS
 """
 import os
 from pathlib import Path
@@ -34,8 +34,8 @@ def _encoder():
 
 
 def _training():
-    return dict(lr=1e-4, schedule_lr=False, batch_size=int(os.environ.get('VQCPC_BATCH', 4096)), num_batches=16,
-                num_epochs=20000, quantizer_regularization=dict(corrupt_labels=False))
+    return dict(lr=1e-4, schedule_lr=False, batch_size=int(os.environ.get('VQCPC_BATCH', 4096)),
+                num_batches=int(os.environ.get('VQCPC_NUM_BATCHES', 16)), num_epochs=int(os.environ.get('VQCPC_EPOCHS', 20000)), quantizer_regularization=dict(corrupt_labels=False))
 
 
 config = dict(training_method='vqcpc', dataset=os.environ.get('VQCPC_DATASET', 'synthetic'),

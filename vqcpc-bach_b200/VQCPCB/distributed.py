@@ -41,9 +41,21 @@ def init_from_env(backend=None):
     return dist.get_rank(), dist.get_world_size(), local
 
 
+# bench.py sets this to a list: every all-reduce is then bracketed by CUDA events on the current stream
+COLLECTIVE_EVENTS = None
+
+
 def all_reduce_sum(flat_tensor):
     if world_size() > 1:
-        dist.all_reduce(flat_tensor, op=dist.ReduceOp.SUM)
+        ev = COLLECTIVE_EVENTS
+        if ev is not None and flat_tensor.is_cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dist.all_reduce(flat_tensor, op=dist.ReduceOp.SUM)
+            b.record()
+            ev.append((a, b))
+        else:
+            dist.all_reduce(flat_tensor, op=dist.ReduceOp.SUM)
 
 
 def broadcast_parameters(params, src=0):

@@ -62,7 +62,10 @@ class EncoderStackFn(torch.autograd.Function):
         n_layers_total = sum(layers_per_stack)
         layer_params = prm[6:6 + 14 * n_layers_total]
         agg_params = prm[6 + 14 * n_layers_total:]          # (weight, bias) per stack, DownscalerLinear only
-        train = any(ctx.needs_input_grad)      # (grad mode is off inside Function.forward; this is the reliable signal)
+        # activations are saved only when a backward can follow.  Grad mode is always off inside Function.forward and
+        # ``needs_input_grad`` stays True for parameters under torch.no_grad(), so the CALLER samples
+        # torch.is_grad_enabled() and passes it in meta[10] (eval epochs then keep no probabilities / activations).
+        train = any(ctx.needs_input_grad) and (bool(meta[10]) if len(meta) > 10 else True)
 
         h = torch.empty(M0, d, dtype=torch.float32, device=dev)
         ops.gemm(emb2d, w_in, M0, d - 2 * pe, E, True, True, out=h[:, :d - 2 * pe], bias=b_in, b_is_weight=True)

@@ -62,6 +62,6 @@ class RelativeTransformerDownscaler(Downscaler):
         nb = seq_len // self.sequence_length
         meta = (self.sequence_length, self.num_channels, self.POS_EMB, self.d_model, self.n_head,
                 tuple(self.downscale_factors), tuple(self.list_of_num_layers), self.output_dim, self.LINEAR_AGG,
-                float(self.dropout) if self.training else 0.0)
+                float(self.dropout) if self.training else 0.0, torch.is_grad_enabled())
         z = EncoderStackFn.apply(embedded_seq.reshape(batch * seq_len, dim), meta, *self._flat_params())
         return z.view(batch, nb, self.output_dim)

@@ -13,6 +13,13 @@ from . import ops
 from .utils import dict_pretty_print, flatten
 
 
+def save_state_dict(module, path):
+    """torch.save of a module's state_dict with every tensor CLONED first: once the trainer has re-homed the parameters
+    as views into its flat buffer, saving the views would serialise the whole underlying storage into each of the
+    per-module files (the reference writes compact per-module files, encoder.py:47-57)."""
+    torch.save({k: v.detach().clone() for k, v in module.state_dict().items()}, path)
+
+
 class Encoder(nn.Module):
     def __init__(self, model_dir, data_processor, downscaler, quantizer, upscaler):
         super().__init__()
@@ -28,11 +35,11 @@ class Encoder(nn.Module):
     def save(self, early_stopped):
         d = self._dir(early_stopped)
         os.makedirs(d, exist_ok=True)
-        torch.save(self.data_processor.state_dict(), f'{d}/data_processor')
-        torch.save(self.downscaler.state_dict(), f'{d}/downscaler')
-        torch.save(self.quantizer.state_dict(), f'{d}/quantizer')
+        save_state_dict(self.data_processor, f'{d}/data_processor')
+        save_state_dict(self.downscaler, f'{d}/downscaler')
+        save_state_dict(self.quantizer, f'{d}/quantizer')
         if self.upscaler is not None:
-            torch.save(self.upscaler.state_dict(), f'{d}/upscaler')
+            save_state_dict(self.upscaler, f'{d}/upscaler')
 
     def load(self, early_stopped, device):
         print(f'Loading models {self.__repr__()}')

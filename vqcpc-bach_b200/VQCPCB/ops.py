@@ -78,12 +78,16 @@ def split_bf16(x2d):
 def weight_split(w):
     """Cached bf16 split of a parameter (invalidated by the in-place optimizer update via ``bump_weight_version``)."""
     key = (w.data_ptr(), tuple(w.shape))
+    # two invalidation signals: the global counter (bumped by the fused optimizer / loaders, whose kernels write through
+    # raw pointers that autograd does not see) and the tensor's own in-place version counter (load_state_dict, copy_,
+    # a stock torch optimizer ...), so no in-place update can leave a stale split behind
+    ver = (_WEIGHT_VERSION[0], w._version)
     ent = _WSPLIT_CACHE.get(key)
-    if ent is not None and ent[0] == _WEIGHT_VERSION[0]:
+    if ent is not None and ent[0] == ver:
         return ent[1], ent[2]
     w2 = w.detach().reshape(w.shape[0], -1)
     hi, lo = split_bf16(w2)
-    _WSPLIT_CACHE[key] = (_WEIGHT_VERSION[0], hi, lo)
+    _WSPLIT_CACHE[key] = (ver, hi, lo)
     return hi, lo
 
 
@@ -352,6 +356,15 @@ def reduce_sum(x, scale=1.0):
     return out
 
 
+def code_hist(idx, counts):
+    """counts[idx[i]] += 1 (int32, accumulated) over all elements of the int64 index tensor."""
+    idx = idx.reshape(-1)
+    if not idx.is_contiguous():
+        idx = idx.contiguous()
+    _chk(idx, counts)
+    _native.call('vqcpc_code_hist', _p(idx), idx.numel(), counts.numel(), _p(counts), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ autograd Functions
 def _grad_buf(p):
     """Gradient accumulator of a leaf parameter (allocated zeroed on first use; kernels accumulate in place)."""
@@ -471,11 +484,11 @@ class GRUFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, meta, *params):
-        nl, H, p, masks = meta
+        nl, H, p, masks = meta[:4]
         x = _f32c(x)
         B, T, _ = x.shape
         prm = [q.detach() for q in params]
-        train = any(ctx.needs_input_grad)
+        train = any(ctx.needs_input_grad) and (bool(meta[4]) if len(meta) > 4 else True)   # meta[4]: caller's grad mode
         dev = x.device
         saved = []
         inp, inp_sp = x.reshape(B * T, -1), None
@@ -584,7 +597,7 @@ def gru_forward(gru, x, training):
     for l in range(nl):
         params += [getattr(gru, f'weight_ih_l{l}'), getattr(gru, f'weight_hh_l{l}'), getattr(gru, f'bias_ih_l{l}'),
                    getattr(gru, f'bias_hh_l{l}')]
-    return GRUFn.apply(x, (nl, H, p, masks), *params)
+    return GRUFn.apply(x, (nl, H, p, masks, torch.is_grad_enabled()), *params)
 
 
 class QuantizeFn(torch.autograd.Function):

@@ -80,36 +80,56 @@ class FusedClipAdam(torch.optim.Optimizer):
         # the .grad views must stay alive (kernels accumulate into them): always zero in place
         self.flat.grad_full.zero_()
 
+    @staticmethod
+    def tail_elems(stats_elems, count_elems):
+        """fp32 slots the all-reduce tail needs: statistics as they are, every integer count as two halves."""
+        return stats_elems + 2 * count_elems
+
     @torch.no_grad()
     def all_reduce(self, stats=None, counts=None):
-        """The ONE collective of a step: sum all-reduce of [gradients | counts | stats]; returns the gradient scale
-        (1 / world_size) the update must apply.  ``stats`` tensors are replaced by their cross-rank mean, ``counts``
-        (int32 code-usage histogram) by its cross-rank sum.  No-op (scale 1) in a single process."""
+        """The ONE collective of a step: sum all-reduce of [gradients | stats | counts]; returns the gradient scale
+        (1 / world_size) the update must apply.  ``stats`` (float tensors) are replaced by their cross-rank mean;
+        ``counts`` (integer tensors, e.g. the code-usage histograms) by their cross-rank SUM.  Counts travel through the
+        fp32 buffer as two halves (low 12 bits, rest), so the sums stay exact for any realistic count (each half < 2^24
+        after the reduction) although the collective is a float one.  No-op (scale 1) in a single process."""
         flat = self.flat
         world = vq_dist.world_size() if getattr(self, 'distributed', True) else 1
         if world <= 1:
             return 1.0
         tail = flat.tail
-        items = [(t, 'mean') for t in (stats or [])] + ([(counts, 'sum')] if counts is not None else [])
+        stats = list(stats or [])
+        counts = list(counts or [])
         o = 0
-        for t, _ in items:
+        for t in stats:
             assert o + t.numel() <= tail.numel(), 'all-reduce tail too small'
             tail[o:o + t.numel()].copy_(t.reshape(-1))
             o += t.numel()
+        for t in counts:
+            n = t.numel()
+            assert o + 2 * n <= tail.numel(), 'all-reduce tail too small'
+            v = t.reshape(-1).long()
+            tail[o:o + n].copy_(v & 0xFFF)
+            tail[o + n:o + 2 * n].copy_(v >> 12)
+            o += 2 * n
         vq_dist.all_reduce_sum(flat.grad_full)
         o = 0
-        for t, kind in items:
-            v = tail[o:o + t.numel()].view(t.shape)
-            t.copy_(v / world if kind == 'mean' else v)
+        for t in stats:
+            t.copy_(tail[o:o + t.numel()].view(t.shape) / world)
             o += t.numel()
+        for t in counts:
+            n = t.numel()
+            tot = tail[o:o + n].round().long() + (tail[o + n:o + 2 * n].round().long() << 12)
+            t.copy_(tot.view(t.shape))
+            o += 2 * n
         return 1.0 / world
 
     @torch.no_grad()
-    def step(self, closure=None, max_norm=0.0, stats=None):
-        """Clip by global norm ``max_norm`` (0 = no clip) and apply Adam.  ``stats`` = (sums, correct) device tensors
-        that ride in the tail of the all-reduce buffer (averaged across ranks in place)."""
+    def step(self, closure=None, max_norm=0.0, stats=None, counts=None):
+        """Clip by global norm ``max_norm`` (0 = no clip) and apply Adam.  ``stats`` = (sums, correct) device tensors and
+        ``counts`` = integer code-usage histograms ride in the tail of the all-reduce buffer (stats averaged, counts
+        summed across ranks, both in place)."""
         flat = self.flat
-        grad_scale = self.all_reduce(stats)
+        grad_scale = self.all_reduce(stats, counts)
         g = self.param_groups[0]
         self.step_count += 1
         _native.call('vqcpc_grad_sumsq', _p(flat.grad), flat.numel, grad_scale, _p(self.gnorm_sq), _stream())

@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from .. import ops
+from .. import distributed as vq_dist
 
 
 class VectorQuantizer(nn.Module):
@@ -48,7 +49,13 @@ class ProductVectorQuantizer(VectorQuantizer):
         if use_batch_norm:
             # never enabled in a shipped config; under data parallelism it would need SyncBN
             raise NotImplementedError('use_batch_norm=True is not supported by the B200 quantizer')
-        self.usage_counts = None      # int32 (num_codebooks * codebook_size), accumulated while not None
+        self.usage_counts = None      # int32 (num_codebooks * codebook_size), accumulated by the kernels while not None
+        # data parallel: the data-dependent initialisation draws rows of the RANK-LOCAL first batch, so rank 0's draw is
+        # broadcast to every replica right after it (False: single-process use inside an initialised process group)
+        self.sync_init = True
+        # running GLOBAL code-usage histogram (int64, codebook_size): the trainer adds the cross-rank sum of every training
+        # step's counts, i.e. the vector the per-step all-reduce carries
+        self.global_usage = None
 
     def track_usage(self, enable=True):
         dev = self.embeddings[0].device
@@ -63,6 +70,9 @@ class ProductVectorQuantizer(VectorQuantizer):
         for k, emb in enumerate(self.embeddings):
             perm = torch.randperm(flat_input.shape[0], device=flat_input.device)[:emb.shape[0]]
             emb.data.copy_(flat_input.detach()[perm, k * ds:(k + 1) * ds])
+        if self.sync_init and vq_dist.world_size() > 1:
+            # every rank reaches this point on its first forward (quirk Q5), so the collective is matched
+            vq_dist.broadcast_parameters(list(self.embeddings), src=0)
         self.initialize = False
         ops.bump_weight_version()
 

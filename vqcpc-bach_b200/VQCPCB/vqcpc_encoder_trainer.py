@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops, vqcpc_helper
-from .encoder import EncoderTrainer
+from .encoder import EncoderTrainer, save_state_dict
 from .optim import FlatParams, FusedClipAdam
 from . import distributed as vq_dist
 
@@ -83,6 +83,10 @@ class VQCPCEncoderTrainer(EncoderTrainer):
             params += list(m.parameters())
         if self.distributed and vq_dist.world_size() > 1:
             vq_dist.broadcast_parameters(params)          # replicas must start identical
+        # (the data-dependent codebook initialisation happens later, inside the first forward: the quantizer broadcasts
+        #  rank 0's draw itself - vector_quantizer.py `_initialize`)
+        if hasattr(self.encoder.quantizer, 'sync_init'):
+            self.encoder.quantizer.sync_init = bool(self.distributed)
         self.flat = FlatParams(params)
         self.optimizer = FusedClipAdam(self.flat, lr=lr, extra_tail=self._tail_size())
         self.optimizer.distributed = self.distributed
@@ -95,9 +99,9 @@ class VQCPCEncoderTrainer(EncoderTrainer):
                 self.optimizer, lr_lambda=lambda step: max(min(lo + s1 * step, hi + (step - warmup_steps) * s2), lo))
 
     def _tail_size(self):
-        q = self.encoder.quantizer
-        kc = getattr(q, 'codebook_size', 0) * getattr(q, 'num_codebooks', 0)
-        return kc + 8 + self.dataloader_generator.num_blocks_right
+        """[loss sums (3) | accuracy counts (KR) | code-usage histograms of the positive and the negative blocks]"""
+        kc = getattr(self.encoder.quantizer, 'codebook_size', 0)
+        return FusedClipAdam.tail_elems(3 + self.dataloader_generator.num_blocks_right, 2 * kc) + 4
 
     def to(self, device):
         for m in self._modules_in_order():
@@ -110,11 +114,11 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         d = self._dir(early_stopped)
         os.makedirs(d, exist_ok=True)
         self.encoder.save(early_stopped=early_stopped)
-        torch.save(self.c_module.state_dict(), f'{d}/c_module')
-        torch.save(self.fks_module.state_dict(), f'{d}/fks_module')
+        save_state_dict(self.c_module, f'{d}/c_module')
+        save_state_dict(self.fks_module, f'{d}/fks_module')
         if self.c_module_back is not None:
-            torch.save(self.c_module_back.state_dict(), f'{d}/c_module_back')
-            torch.save(self.fks_module_back.state_dict(), f'{d}/fks_module_back')
+            save_state_dict(self.c_module_back, f'{d}/c_module_back')
+            save_state_dict(self.fks_module_back, f'{d}/fks_module_back')
 
     def load(self, early_stopped, device):
         print(f'Loading models {self.__repr__()}')
@@ -167,8 +171,9 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         correct = torch.zeros(KR, dtype=torch.float32, device=dev)
         q = enc.quantizer
         Kc = getattr(q, 'codebook_size', None)
-        seen_pos = torch.zeros(Kc, dtype=torch.bool, device=dev) if Kc else None
-        seen_neg = torch.zeros(Kc, dtype=torch.bool, device=dev) if Kc else None
+        # code-usage histograms of this step: row 0 = positive blocks (left + right), row 1 = negatives (the reference
+        # counts torch.unique of the same two sets, :325-331).  Under data parallelism they ride in the step's all-reduce.
+        hist = torch.zeros(2, Kc, dtype=torch.int32, device=dev) if Kc else None
 
         bs = self._samples_per_pass(B, KL + KR + N * KR * (2 if bidir else 1))
         for b0 in range(0, B, bs):
@@ -228,20 +233,25 @@ class VQCPCEncoderTrainer(EncoderTrainer):
                 sums += torch.stack([loss.detach(), qloss.detach(), nce.detach()])
                 correct += corr_f.sum(0)
                 if idx_left is not None:
-                    seen_pos[idx_left.reshape(-1)] = True
-                    seen_pos[idx_right.reshape(-1)] = True
-                    seen_neg[idx_neg.reshape(-1)] = True
+                    ops.code_hist(idx_left, hist[0])
+                    ops.code_hist(idx_right, hist[0])
+                    ops.code_hist(idx_neg, hist[1])
             del loss, nce, qloss, z_neg, z_left, z_right, c
 
         if train:
-            self.optimizer.step(max_norm=self.max_grad_norm, stats=(sums, correct))        # :313-314 (+ all-reduce)
+            # :313-314 (+ the one all-reduce: gradients | loss/accuracy sums | code counts)
+            self.optimizer.step(max_norm=self.max_grad_norm, stats=(sums, correct), counts=[hist] if hist is not None else None)
             ops.bump_weight_version()
+            if hist is not None:
+                if q.global_usage is None or q.global_usage.device != hist.device:
+                    q.global_usage = torch.zeros(Kc, dtype=torch.int64, device=dev)
+                q.global_usage += hist.sum(0)
             if self.scheduler is not None:
                 self.scheduler.step()                                                      # :315-316
         out = dict(loss=sums[0], loss_quantize=sums[1], loss_contrastive=sums[2], accuracy=correct / B)
-        if seen_pos is not None:
-            out['num_codewords'] = seen_pos.sum()
-            out['num_codewords_negative'] = seen_neg.sum()
+        if hist is not None:
+            out['num_codewords'] = (hist[0] > 0).sum()
+            out['num_codewords_negative'] = (hist[1] > 0).sum()
         return out
 
     # ------------------------------------------------------------------------------------------ epoch

@@ -443,6 +443,21 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
   }
 }
 
+// Histogram of code indices: counts[idx[i]] += 1 (int32, ACCUMULATED).  Per-CTA privatised in shared memory with native
+// integer atomics (ATOMS.ADD), one global atomic per (CTA, non-empty bin).  Out-of-range values are ignored.
+__global__ void __launch_bounds__(512) code_hist_kernel(const int64_t* __restrict__ idx, int64_t n, int bins, int* __restrict__ counts) {
+  extern __shared__ int hist_s[];
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) hist_s[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = idx[i];
+    if (k >= 0 && k < bins) atomicAdd(&hist_s[(int)k], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x)
+    if (hist_s[i]) atomicAdd(counts + i, hist_s[i]);
+}
+
 inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   int64_t g = vq_cdiv(work_items, threads);
   int64_t cap = (int64_t)vq_sm_count() * per_sm;
@@ -684,5 +699,15 @@ VQ_API int vqcpc_split_bf16(const float* x, int ldx, void* hi, void* lo, int ldo
 VQ_API int vqcpc_reduce_sum(const float* x, int64_t n, float* out, float scale, void* stream) {
   reduce_sum_kernel<<<1, 1024, 0, vq_stream(stream)>>>(x, n, out, scale);
   VQ_CUDA_LAUNCH_CHECK("reduce_sum_kernel");
+  return VQ_OK;
+}
+
+// Code-usage histogram (the per-code counts that ride in the data-parallel all-reduce; replaces torch.unique monitoring,
+// VQCPCB/vqcpc_encoder_trainer.py:325-331): counts[idx[i]] += 1 for 0 <= idx[i] < bins.  counts int32, ACCUMULATED.
+VQ_API int vqcpc_code_hist(const int64_t* idx, int64_t n, int bins, int* counts, void* stream) {
+  VQ_CHECK_ARG(bins >= 1 && bins <= 12288, "vqcpc_code_hist: bins must be in [1, 12288] (got %d)", bins);
+  if (n <= 0) return VQ_OK;
+  code_hist_kernel<<<grid_for(n, 512, 2), 512, bins * sizeof(int), vq_stream(stream)>>>(idx, n, bins, counts);
+  VQ_CUDA_LAUNCH_CHECK("code_hist_kernel");
   return VQ_OK;
 }
