@@ -217,17 +217,62 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
         _native.call('vqcpc_vq_fused_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(d['dy']), p_(d['gl']),
                      p_(d['dz']), p_(d['dT']), p_(d['dE']), st())
 
+    # ---- index-gather form (csrc/idxpath.cu): what the trainer runs in table mode
+    n_left = B * KL
+    for d in sets:
+        d.update(y_left=torch.empty(n_left, zd, device=dev), dy_left=torch.randn(n_left, zd, device=dev, generator=g) * 1e-3,
+                 coef_pos=torch.empty(B, KR, device=dev), coef_neg=torch.empty(B, NNEG, KR, device=dev))
+    parts = _native.load().vqcpc_infonce_idx_parts(B, KR)
+    part = torch.empty(parts, Kc * zd + zd * cd * KR, device=dev)
+    seg_row0 = (ctypes.c_int64 * 3)(0, n_neg, n_neg + n_left)
+    seg_rows = (ctypes.c_int64 * 3)(n_neg, n_left, B * KR)
+    seg_kind = (ctypes.c_int * 3)(2, 1, 2)
+    seg_per_b = (ctypes.c_int * 3)(NNEG * KR, 1, KR)
+
+    def vq_fwd_idx(d):
+        _native.call('vqcpc_vq_fused_fwd_rows', p_(d['z']), P, D, p_(E), p_(T), Kc, zd, 0.25, 1, p_(d['idx']), p_(d['loss']), None,
+                     p_(d['y_left']), n_neg, n_left, p_(d['counts']), st())
+
+    def nce_fwd_idx(d):
+        idx = d['idx']
+        _native.call('vqcpc_infonce_idx_fwd', p_(d['c']), p_(W), p_(T), p_(idx[n_neg + n_left:]), p_(idx), B, NNEG, KR, zd, cd, Kc,
+                     p_(d['u']), p_(d['pos']), p_(d['neg']), p_(d['lse']), p_(d['nll']), p_(d['correct']), st())
+
+    def nce_bwd_idx(d):
+        idx = d['idx']
+        _native.call('vqcpc_infonce_idx_bwd', p_(d['c']), p_(W), p_(T), p_(idx[n_neg + n_left:]), p_(idx), p_(d['u']), p_(d['pos']),
+                     p_(d['neg']), p_(d['lse']), None, 1.0 / B, B, NNEG, KR, zd, cd, Kc, p_(d['dc']), p_(d['coef_pos']),
+                     p_(d['coef_neg']), p_(part), p_(d['dW']), p_(d['dT']), st())
+
+    def scat_idx(d):
+        _native.call('vqcpc_table_scatter_add', p_(d['idx'][n_neg:n_neg + n_left]), n_left, p_(d['dy_left']), zd, Kc, p_(d['dT']), st())
+
+    def vq_bwd_idx(d):
+        pa = (ctypes.c_void_p * 3)(d['coef_neg'].data_ptr(), d['dy_left'].data_ptr(), d['coef_pos'].data_ptr())
+        pb = (ctypes.c_void_p * 3)(d['u'].data_ptr(), 0, d['u'].data_ptr())
+        _native.call('vqcpc_vq_idx_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(d['gl']), 3, seg_row0,
+                     seg_rows, seg_kind, pa, pb, seg_per_b, KR, p_(d['dz']), p_(d['dE']), st())
+
     def fwd(d):
+        vq_fwd_idx(d)
+        nce_fwd_idx(d)
+
+    def bwd(d):
+        nce_bwd_idx(d)
+        scat_idx(d)
+        vq_bwd_idx(d)
+
+    def fwd_pv(d):
         vq_fwd(d)
         nce_fwd(d)
 
-    def bwd(d):
+    def bwd_pv(d):
         nce_bwd(d)
         vq_bwd(d)
 
     def timeit(fn, graph=True):
         """Mean device time of fn over the rotating buffer sets (> L2).  graph=True replays a CUDA graph of the launch
-        sequence so that host launch latency (13 us per ctypes call) does not pad kernels that take 15-50 us."""
+        sequence so that host launch latency (13 us per ctypes call) does not pad kernels that take 5-50 us."""
         for d in sets:
             fn(d)
         torch.cuda.synchronize()
@@ -266,32 +311,48 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
     us_f = timeit(fwd)
     us_b = timeit(bwd)
     us_f_launch = timeit(fwd, graph=False)
-    per_kernel = dict(vq_fused_fwd_us=timeit(vq_fwd), infonce_fwd_us=timeit(nce_fwd), infonce_bwd_us=timeit(nce_bwd),
-                      vq_fused_bwd_us=timeit(vq_bwd))
+    per_kernel = dict(vq_fused_fwd_rows_us=timeit(vq_fwd_idx), infonce_idx_fwd_us=timeit(nce_fwd_idx),
+                      infonce_idx_bwd_us=timeit(nce_bwd_idx), table_scatter_add_us=timeit(scat_idx), vq_idx_bwd_us=timeit(vq_bwd_idx))
+    us_f_pv, us_b_pv = timeit(fwd_pv), timeit(bwd_pv)
+    per_kernel_pv = dict(vq_fused_fwd_us=timeit(vq_fwd), infonce_fwd_us=timeit(nce_fwd), infonce_bwd_us=timeit(nce_bwd),
+                         vq_fused_bwd_us=timeit(vq_bwd))
     pk = peaks()
     vec = KL + KR + NNEG * KR
     bytes_f = B * (vec * (4 * D + 8 + 4 + 4 * zd) + (KR + NNEG * KR) * 4 * zd + 4 * cd + 8 * KR)
     # backward: read dy-producing inputs (y for right+neg, u, scores) and write dy for right+neg; then per vector read
     # dy (4 zd) + idx (8) + z (4 D) + g_loss (4), write dz (4 D)
     bytes_b = B * ((KR + NNEG * KR) * 8 * zd + vec * (4 * zd + 8 + 8 * D + 4))
+    # bytes the index form really moves (indices, z, loss, y of the left blocks, c, u, scores / coefficients, dz)
+    real_f = B * (vec * (4 * D + 8 + 4) + KL * 4 * zd + 4 * cd + (KR + NNEG * KR) * 8 + KR * (4 * zd + 4 * (NNEG + 4)))
+    real_b = B * (KR * (4 * zd + 4 * (NNEG + 2) + 4 * (NNEG + 1)) + (KR + NNEG * KR) * 8 + 8 * cd + KL * (4 * zd + 8) + vec * (8 * D + 8 + 4 + 4))
     search_instr = P * Kc * 11.0                                   # exact direct-form search: 11 fp32 instr per (vector, code)
     alu_us = search_instr / (148 * 128 * 1.9e9) * 1e6
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_path_traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))           # dram bytes per launch from the committed ncu --set full captures
+    for tname in ('r02_path_traffic.json', 'r01_path_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))           # dram bytes per launch from the committed ncu --set full captures
+            traffic['source'] = 'profiles/' + tname
+            break
     return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], traffic=traffic, peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
-                kernels='vq_tc_fwd_kernel (tcgen05 score + exact verify) + infonce_stream_fwd_kernel (forward); '
-                        'infonce_stream_bwd_kernel + vq_fused_bwd_stream_kernel (backward)',
+                kernels='index-gather form: vq_tc_fwd_kernel (tcgen05 score + exact verify; y for the left blocks only) + '
+                        'nce_idx_fwd_kernel (forward); nce_idx_bwd_kernel + reduce_partials_kernel + table_scatter_add_kernel + '
+                        'vq_idx_bwd_kernel (backward)',
                 timing='CUDA-graph replay of the launch sequence over %d rotating buffer sets (> L2); us_fwd_eager = same '
                        'launches issued one by one from Python' % nsets, us_fwd_eager=us_f_launch,
                 batch=B, vectors=P, algorithmic_bytes_fwd=bytes_f, us_fwd=us_f, achieved=bytes_f / us_f / 1e3,
                 frac=bytes_f / us_f / 1e3 / pk['hbm'], algorithmic_bytes_bwd=bytes_b, us_bwd=us_b,
                 achieved_bwd=bytes_b / us_b / 1e3, frac_bwd=bytes_b / us_b / 1e3 / pk['hbm'],
+                moved_bytes_fwd=real_f, moved_bytes_bwd=real_b,
                 fp32_alu_bound_us_exact_search=alu_us, per_kernel_us=per_kernel,
-                note='forward search ranks codes on the tensor cores and re-evaluates the reference arithmetic only on the '
-                     'candidates (bit-identical indices); a direct-form scan of every (vector, code) pair would be ALU bound at '
-                     '%.0f us; HBM bound of the forward path %.0f us' % (alu_us, bytes_f / pk['hbm'] / 1e3))
+                per_vector_path=dict(us_fwd=us_f_pv, us_bwd=us_b_pv, frac=bytes_f / us_f_pv / 1e3 / pk['hbm'],
+                                     frac_bwd=bytes_b / us_b_pv / 1e3 / pk['hbm'], per_kernel_us=per_kernel_pv,
+                                     note='round-1 kernels: upscaled rows materialised (what upscaler dropout / product codebooks still use)'),
+                note='achieved = ALGORITHMIC bytes of the per-vector formulation (SURVEY 8d: 36.7 KB / sample forward) over the '
+                     'measured time; the index form moves only moved_bytes_* (tables live in shared memory), so achieved can '
+                     'exceed what the same time would carry over HBM.  The forward search ranks codes on the tensor cores and '
+                     're-evaluates the reference arithmetic only on the candidates (bit-identical indices); a direct-form scan '
+                     'would be ALU bound at %.0f us; HBM bound of the forward path %.0f us' % (alu_us, bytes_f / pk['hbm'] / 1e3))
 
 
 def run_ours(args):

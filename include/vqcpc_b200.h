@@ -190,6 +190,48 @@ int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos, const 
                       const float* pos, const float* neg, const float* lse, const float* g_dev, float scale, int B, int N,
                       int KR, int zd, int cd, float* d_c, float* d_W, float* d_ypos, float* d_yneg, void* stream);
 
+/* ---- index-gather form of the quantizer -> upscaler -> InfoNCE path (csrc/idxpath.cu) ------------------------------
+ * Table mode (one codebook, no active upscaler dropout): every upscaled vector is a row of T = upscaler(E) (Kc, zd), so
+ * the scores f_k = u_k . y of vqcpc_helper.py:79-98 and the loss of :5-29 are evaluated from the code indices, and the
+ * backward never materialises d y.  Supported: zd == cd == 32, 1 <= N <= 15, 1 <= KR <= 16, Kc <= 698 (T and d T in shared
+ * memory), D in {3, 4}; vqcpc_idxpath_supported() returns 1 for such shapes (callers keep the per-vector entry points
+ * above for everything else). */
+int vqcpc_idxpath_supported(int N, int KR, int zd, int cd, int Kc, int D);
+/* vqcpc_vq_fused_fwd with the upscaled rows y = T[idx] produced only for the rows [y_row0, y_row0 + y_rows) (the left
+ * blocks, which the context GRU reads; y has y_rows rows).  Replaces vector_quantizer.py:104-157 + mlp_upscaler.py:21-35. */
+int vqcpc_vq_fused_fwd_rows(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                            int squared, int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows,
+                            int* counts, void* stream);
+/* c (B, cd); W (zd, cd, KR); T (Kc, zd); idx_pos (B, KR), idx_neg (B, N, KR) int64.  Outputs as vqcpc_infonce_fwd:
+ * u (B, KR, zd), pos (B, KR), neg (B, KR, N), lse, nll = lse - pos (B, KR), correct (B, KR) int32.
+ * vqcpc_helper.py:79-98, :5-29; vqcpc_encoder_trainer.py:240-272. */
+int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
+                          int B, int N, int KR, int zd, int cd, int Kc, float* u, float* pos, float* neg, float* lse,
+                          float* nll, int* correct, void* stream);
+/* rows of the scratch `part` of vqcpc_infonce_idx_bwd: part holds parts * (Kc * zd + zd * cd * KR) floats. */
+int vqcpc_infonce_idx_parts(int B, int KR);
+/* gradient of sum(nll) scaled by scale * g_dev[0] (g_dev device scalar or NULL): d_c (B, cd) overwritten; coef_pos (B, KR)
+ * and coef_neg (B, N, KR) = d loss / d score of every candidate, overwritten (vqcpc_vq_idx_bwd turns them into d z);
+ * d_W (zd, cd, KR) and d_T (Kc, zd) ACCUMULATED (per-CTA partial tables in `part`, summed in a fixed order). */
+int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
+                          const float* u, const float* pos, const float* neg, const float* lse, const float* g_dev,
+                          float scale, int B, int N, int KR, int zd, int cd, int Kc, float* d_c, float* coef_pos,
+                          float* coef_neg, float* part, float* d_W, float* d_T, void* stream);
+/* out[idx[i]] += rows[i] (rows (n, zd), out (Kc, zd) ACCUMULATED) without atomics, deterministic: the gradient of the
+ * table gather y = T[idx] of the left blocks. */
+int vqcpc_table_scatter_add(const int64_t* idx, int64_t n, const float* rows, int zd, int Kc, float* out, void* stream);
+/* backward of the quantizer in index form.  d_x (n, D) overwritten = coef_p * J[idx_p]^T v_p + g_loss_p * dloss/dx, where
+ * the upscaled-side gradient v_p of the vectors of segment s (rows [seg_row0[s], +seg_rows[s]), at most 4 segments, other
+ * vectors get none) is  kind 1: the dense row seg_a[s][(p - row0) * zd ..] (coef = 1)
+ *                       kind 2: coef = seg_a[s][p - row0],  v = seg_b[s][((p - row0) / per_b * KR + (p - row0) % KR) * zd ..]
+ * (per_b = N * KR for the negatives laid out (B, N, KR), KR for the right blocks; seg_b = the u of vqcpc_infonce_idx_fwd).
+ * d_E (Kc, D) ACCUMULATED (may be NULL).  J (Kc, zd, D), g_loss (n) or NULL.  seg_* are HOST arrays. */
+int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,
+                     float beta, int squared, const float* g_loss, int nseg, const int64_t* seg_row0 /*host*/,
+                     const int64_t* seg_rows /*host*/, const int* seg_kind /*host*/, const float* const* seg_a /*host*/,
+                     const float* const* seg_b /*host*/, const int* seg_per_b /*host*/, int KR, float* d_x, float* d_E,
+                     void* stream);
+
 /* ---- GRU (torch.nn.GRU semantics; CModule vqcpc_helper.py:54-76, LstmDownscaler lstm_downscaler.py:31-48) ---------------
  * The products GI = X W_ih^T + b_ih (all steps at once) and GH = h_{t-1} W_hh^T + b_hh (per step) are vqcpc_gemm_* calls;
  * these are the point-wise stages of step t, gate order (r, z, n), batch-first layouts: gi (B*T, 3H) rows b*T + t,

@@ -96,6 +96,21 @@ class Encoder(nn.Module):
                                                   q.usage_counts)
         return y, idx, loss
 
+    def forward_tokens_indexed(self, x_proc, y_row0, y_rows):
+        """Index path (table mode): tokens (1, P, S) -> (y of the rows [y_row0, +y_rows) (y_rows, z_dim), idx (P,) int64,
+        loss (P,), link).  The upscaled vectors of all other rows are never materialised: the trainer scores them from
+        their indices (``FksModule.fused_nce_indexed``) and ``link`` carries what the two autograd nodes share."""
+        q, u = self.quantizer, self.upscaler
+        z = self.downscaler.forward(flatten(self.data_processor.embed(x_proc)))
+        codebook = q.embeddings[0]
+        table, jac = u.code_table_and_jacobian(codebook)
+        link = ops.BottleneckLink()
+        link.table = table
+        y, idx, loss, token = ops.VQIndexFn.apply(z.reshape(-1, q.codebook_dim), codebook, table, jac, q._commitment_cost,
+                                                  q.squared_l2_norm, q.usage_counts, int(y_row0), int(y_rows), link)
+        link.token = token
+        return y, idx, loss, link
+
     def merge_codes(self, codes):
         """Pack the indices of a product quantizer into one integer per position (encoder.py:97-110)."""
         _, _, num_codebooks = codes.shape

@@ -723,3 +723,137 @@ class InfoNCEFn(torch.autograd.Function):
         _native.call('vqcpc_infonce_bwd', _p(c), _p(W), _p(y_pos), _p(y_neg), _p(u), _p(pos), _p(neg), _p(lse), _p(g), 1.0, B, N, KR,
                      zd, cd, _p(dc), _p(dW), _p(dyp), _p(dyn), _stream())
         return dc, dW, dyp, dyn
+
+
+# ------------------------------------------------------------------------------------------------ index-gather path
+def idxpath_supported(N, KR, zd, cd, Kc, D):
+    """True when csrc/idxpath.cu handles these shapes (zd == cd == 32, N <= 15, KR <= 16, Kc <= 698, D in {3, 4})."""
+    return bool(_native.load().vqcpc_idxpath_supported(int(N), int(KR), int(zd), int(cd), int(Kc), int(D)))
+
+
+class BottleneckLink:
+    """Side channel between the two autograd nodes of the index path.
+
+    In table mode the upscaled vectors of the right / negative blocks are never materialised, so the gradient that flows
+    from the InfoNCE node back into the quantizer node is not a tensor of rows either: it is the per-candidate
+    coefficients d loss / d score plus the u vectors (``segments``), which ``VQIndexFn.backward`` turns into d z with the
+    upscaler Jacobian J[idx].  ``token`` is a one-element differentiable output of the quantizer node that the InfoNCE
+    node takes as an input, which makes autograd run the InfoNCE backward first."""
+
+    def __init__(self):
+        self.table = None        # T = upscaler(E) with autograd history to the MLP weights
+        self.token = None
+        self.idx = None          # (P,) int64 codes of every vector of the pass
+        self.segments = []       # filled by InfoNCEIdxFn.backward: (row0, rows, coef, u, per_b, KR)
+
+
+class VQIndexFn(torch.autograd.Function):
+    """Quantizer node of the index path: exact search over all P vectors, loss, and the upscaled rows y = T[idx] of the
+    LEFT blocks only (rows [y_row0, y_row0 + y_rows): the context GRU reads them).  vector_quantizer.py:104-157 +
+    mlp_upscaler.py:21-35.  Backward: d z = coef * J[idx]^T v + commitment term for every vector, d E, and d T from the
+    left rows (the right / negative part of d T comes from InfoNCEIdxFn)."""
+
+    @staticmethod
+    def forward(ctx, z, E, T, J, beta, squared, counts, y_row0, y_rows, link):
+        shp = z.shape
+        D = shp[-1]
+        z2 = _f32c(z).view(-1, D)
+        n = z2.shape[0]
+        Kc, zd = T.shape
+        Ed, Td = _f32c(E.detach()), _f32c(T.detach())
+        idx = torch.empty(n, dtype=torch.int64, device=z.device)
+        loss = torch.empty(n, dtype=torch.float32, device=z.device)
+        y = torch.empty(y_rows, zd, dtype=torch.float32, device=z.device)
+        _native.call('vqcpc_vq_fused_fwd_rows', _p(z2), n, D, _p(Ed), _p(Td), Kc, zd, float(beta), int(squared), _p(idx), _p(loss),
+                     None, _p(y), int(y_row0), int(y_rows), _p(counts), _stream())
+        token = torch.zeros(1, dtype=torch.float32, device=z.device)
+        ctx.save_for_backward(z2, Ed, J, idx)
+        ctx.meta = (shp, beta, squared, Kc, zd, y_row0, y_rows)
+        ctx.link = link
+        link.idx = idx
+        ctx.mark_non_differentiable(idx)
+        return y, idx, loss, token
+
+    @staticmethod
+    def backward(ctx, g_y, _g_idx, g_loss, _g_token):
+        z2, Ed, J, idx = ctx.saved_tensors
+        shp, beta, squared, Kc, zd, y_row0, y_rows = ctx.meta
+        n, D = z2.shape
+        dev = z2.device
+        gl = None if g_loss is None else _f32c(g_loss).reshape(n)
+        dT = torch.zeros(Kc, zd, dtype=torch.float32, device=dev)
+        dE = torch.zeros_like(Ed)
+        segs = list(ctx.link.segments)
+        ctx.link.segments = []
+        keep = []
+        if g_y is not None and y_rows > 0:
+            gy = _f32c(g_y).view(y_rows, zd)
+            if gy.data_ptr() % 16:
+                gy = gy.clone()
+            keep.append(gy)
+            _native.call('vqcpc_table_scatter_add', _p(idx[y_row0:y_row0 + y_rows]), y_rows, _p(gy), zd, Kc, _p(dT), _stream())
+            segs.append((y_row0, y_rows, gy, None, 1, 1))
+        KR = max([s[5] for s in segs if s[3] is not None], default=1)
+        ns = len(segs)
+        row0 = (ctypes.c_int64 * max(ns, 1))(*[s[0] for s in segs])
+        rows = (ctypes.c_int64 * max(ns, 1))(*[s[1] for s in segs])
+        kind = (ctypes.c_int * max(ns, 1))(*[1 if s[3] is None else 2 for s in segs])
+        pa = (ctypes.c_void_p * max(ns, 1))(*[s[2].data_ptr() for s in segs])
+        pb = (ctypes.c_void_p * max(ns, 1))(*[s[3].data_ptr() if s[3] is not None else 0 for s in segs])
+        per_b = (ctypes.c_int * max(ns, 1))(*[s[4] for s in segs])
+        dx = torch.empty_like(z2)
+        _native.call('vqcpc_vq_idx_bwd', _p(z2), n, D, _p(Ed), _p(J), Kc, zd, _p(idx), float(beta), int(squared), _p(gl), ns, row0,
+                     rows, kind, pa, pb, per_b, int(KR), _p(dx), _p(dE), _stream())
+        return dx.view(shp), dE, dT, None, None, None, None, None, None, None
+
+
+class InfoNCEIdxFn(torch.autograd.Function):
+    """Fks scoring + log-sum-exp from code indices (vqcpc_helper.py:79-98, :5-29; vqcpc_encoder_trainer.py:240-272).
+    ``seg_pos`` / ``seg_neg`` = first row of the right blocks (B, KR) / the negatives (B, N, KR) in the pass's flat vector
+    list: the quantizer node needs them to route the score gradients back to z."""
+
+    @staticmethod
+    def forward(ctx, c, W, T, token, idx_pos, idx_neg, link, seg_pos, seg_neg):
+        c, W, Td = _f32c(c), _f32c(W), _f32c(T.detach())
+        B, cd = c.shape
+        zd, cd2, KR = W.shape
+        N = idx_neg.shape[1]
+        Kc = Td.shape[0]
+        assert cd2 == cd and idx_pos.shape == (B, KR) and idx_neg.shape == (B, N, KR)
+        assert idx_pos.is_contiguous() and idx_neg.is_contiguous()
+        dev = c.device
+        u = torch.empty(B, KR, zd, dtype=torch.float32, device=dev)
+        pos = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        neg = torch.empty(B, KR, N, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        correct = torch.empty(B, KR, dtype=torch.int32, device=dev)
+        nll = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        _native.call('vqcpc_infonce_idx_fwd', _p(c), _p(W), _p(Td), _p(idx_pos), _p(idx_neg), B, N, KR, zd, cd, Kc, _p(u), _p(pos),
+                     _p(neg), _p(lse), _p(nll), _p(correct), _stream())
+        total = reduce_sum(nll).reshape(())
+        ctx.save_for_backward(c, W, Td, idx_pos, idx_neg, u, pos, neg, lse)
+        ctx.link, ctx.segs = link, (seg_pos, seg_neg)
+        ctx.mark_non_differentiable(pos, neg, correct)
+        return total, pos, neg, correct
+
+    @staticmethod
+    def backward(ctx, g_total, *_):
+        c, W, Td, idx_pos, idx_neg, u, pos, neg, lse = ctx.saved_tensors
+        B, cd = c.shape
+        zd, _, KR = W.shape
+        N = idx_neg.shape[1]
+        Kc = Td.shape[0]
+        dev = c.device
+        dc = torch.empty_like(c)
+        dW = torch.zeros_like(W)
+        dT = torch.zeros_like(Td)
+        coef_pos = torch.empty(B, KR, dtype=torch.float32, device=dev)
+        coef_neg = torch.empty(B, N, KR, dtype=torch.float32, device=dev)
+        parts = _native.load().vqcpc_infonce_idx_parts(B, KR)
+        part = torch.empty(parts, Kc * zd + zd * cd * KR, dtype=torch.float32, device=dev)
+        g = _f32c(g_total).reshape(1)
+        _native.call('vqcpc_infonce_idx_bwd', _p(c), _p(W), _p(Td), _p(idx_pos), _p(idx_neg), _p(u), _p(pos), _p(neg), _p(lse), _p(g),
+                     1.0, B, N, KR, zd, cd, Kc, _p(dc), _p(coef_pos), _p(coef_neg), _p(part), _p(dW), _p(dT), _stream())
+        seg_pos, seg_neg = ctx.segs
+        ctx.link.segments += [(seg_neg, B * N * KR, coef_neg, u, N * KR, KR), (seg_pos, B * KR, coef_pos, u, KR, KR)]
+        return dc, dW, dT, torch.zeros(1, dtype=torch.float32, device=dev), None, None, None, None, None

@@ -67,6 +67,9 @@ class VQCPCEncoderTrainer(EncoderTrainer):
         self.is_main_process = vq_dist.rank() == 0
         self.last_grad_norm_sq = None
         self.distributed = True     # False: ignore an initialised process group (single-process reference runs)
+        # index-gather quantizer -> InfoNCE path (csrc/idxpath.cu) whenever the bottleneck is in table mode; False (or
+        # VQCPC_INDEX_PATH=0) keeps the per-vector kernels (materialised upscaled rows)
+        self.index_path = os.environ.get('VQCPC_INDEX_PATH', '1') != '0'
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _modules_in_order(self):
@@ -180,7 +183,26 @@ class VQCPCEncoderTrainer(EncoderTrainer):
             sl = slice(b0, b0 + bs)
             neg = neg_all[sl].reshape(bs * N * KR, T, V)
             merged = (not corrupt_labels) and not getattr(q, 'initialize', False)
-            if merged:
+            use_idx = (merged and self.index_path and not bidir and enc._fusable(False)
+                       and ops.idxpath_supported(N, KR, enc.upscaler.output_dim, self.fks_module.W.shape[1], Kc, q.codebook_dim))
+            if use_idx:
+                # table mode: one encoder pass over [negatives | left | right]; only the left blocks get their upscaled
+                # rows (the context GRU reads them), right / negative blocks are scored from their code indices
+                dp = enc.data_processor
+                toks = [dp.preprocess(neg), dp.preprocess(x_left_all[sl]), dp.preprocess(x_right_all[sl])]
+                S_tok = toks[0].shape[-1]
+                n_neg, n_left, n_right = bs * N * KR, bs * KL, bs * KR
+                allt = torch.cat([t.reshape(-1, S_tok) for t in toks], 0).unsqueeze(0)
+                y_left, idx_flat, ql_flat, link = enc.forward_tokens_indexed(allt, n_neg, n_left)
+                zd = y_left.shape[-1]
+                z_left = y_left.view(bs, KL, zd)
+                idx_neg, idx_left, idx_right = idx_flat.split([n_neg, n_left, n_right])
+                ql_neg, ql_left, ql_right = ql_flat.split([n_neg, n_left, n_right])
+                c = self.c_module(z_left, None)                                            # :237
+                nll_sum, pos, negs, corr = self.fks_module.fused_nce_indexed(              # :240-272
+                    c, link, idx_right.view(bs, KR), idx_neg.view(bs, N, KR), n_neg + n_left, 0)
+                z_neg = z_right = None
+            elif merged:
                 # blocks are independent, so the reference's separate Encoder.forward calls (:201, :219, :227, :230) are
                 # one pass over the concatenated blocks (bigger GEMMs, 3-4x fewer launches); results are identical.
                 dp = enc.data_processor
@@ -210,8 +232,9 @@ class VQCPCEncoderTrainer(EncoderTrainer):
                 z_left, idx_left, ql_left = enc(x_left_all[sl], corrupt_labels=False)      # :227
                 z_right, idx_right, ql_right = enc(x_right_all[sl], corrupt_labels=False)  # :230
 
-            c = self.c_module(z_left, None)                                                # :237
-            nll_sum, pos, negs, corr = self.fks_module.fused_nce(c, z_right, z_neg)        # :240-272
+            if not use_idx:
+                c = self.c_module(z_left, None)                                            # :237
+                nll_sum, pos, negs, corr = self.fks_module.fused_nce(c, z_right, z_neg)    # :240-272
             nce = nll_sum / B
             corr_f = corr.float()
             if bidir:

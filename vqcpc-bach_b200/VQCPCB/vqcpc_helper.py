@@ -62,3 +62,8 @@ class FksModule(nn.Module):
         """c (B, c_dim), z_pos (B, k_max, z), z_neg (B, N, k_max, z) ->
         (sum_{b,k} (lse - pos)  [differentiable], pos (B,k), neg (B,k,N), correct (B,k) int32)."""
         return ops.InfoNCEFn.apply(c, self.W, z_pos, z_neg)
+
+    def fused_nce_indexed(self, c, link, idx_pos, idx_neg, seg_pos, seg_neg):
+        """Index form of ``fused_nce`` (table mode): the candidates are given by their code indices idx_pos (B, k_max),
+        idx_neg (B, N, k_max) into ``link.table``; seg_pos / seg_neg = first row of those blocks in the pass's vector list."""
+        return ops.InfoNCEIdxFn.apply(c, self.W, link.table, link.token, idx_pos, idx_neg, link, int(seg_pos), int(seg_neg))

@@ -1,0 +1,649 @@
+// Index-gather form of the quantizer -> upscaler -> InfoNCE path (table mode: no active upscaler dropout, one codebook).
+//
+// Every quantised + upscaled vector of the step is one of only Kc rows of the table T = upscaler(E) (Kc, zd), so the
+// InfoNCE scores of VQCPCB/vqcpc_helper.py:79-98 / :5-29 (f_k = u_k . y, u_k = W_k c) and everything behind them can be
+// computed from the code INDICES instead of from materialised 128-byte rows:
+//
+//   forward   s_n = u_k . T[idx_n]                 (n = 0: the positive, 1..N: the negatives of (b, k))  -> lse, nll, accuracy
+//   backward  coef_n = g (softmax(s)_n - [n = 0]);  du_k = sum_n coef_n T[idx_n];  dc = W_k^T du_k;  dW_k += du_k (x) c
+//             dT[code] += sum_{(b,k,n): idx = code} coef_n u_k                      (gradient of the upscaler table)
+//             dz_p = coef_p J[idx_p]^T u_k  (+ the commitment term)                 (straight-through, vector_quantizer.py:148)
+//
+// Real traffic per sample drops from 36.7 KB (z_up rows written by the quantizer and re-read by the
+// scorer, dy rows written and re-read in backward) to ~3 KB (indices, z, u, scores); the tables (T 64 KB, J 192 KB, W 32 KB)
+// live in shared memory / registers of persistent CTAs.  The tensor pipe is NOT used here on purpose: scoring 16 candidates
+// per row from a shared-memory table is 512 FMAs per row, a dense U.T^T product on tcgen05 would compute all Kc scores per
+// row (32x the work) and TMEM cannot be gathered per lane (tcgen05.ld addresses are warp-uniform).
+//
+// No floating-point shared-memory atomics anywhere (CAS loops on sm_100): scatter-adds are turned into
+//   * owner-computes sweeps (a warp owns a residue class of codes and adds into its rows of a CTA-private table), or
+//   * a counting sort by code inside the CTA (native integer ATOMS) followed by per-code sequential sums,
+// and the cross-CTA reduction goes through per-CTA partial tables summed by a second small kernel (fixed order).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int IZ = 32;          // zd == cd == 32: one lane per feature (every shipped configuration)
+constexpr int TST = 36;         // padded row stride (floats) of the shared-memory table: rows start 4 banks apart
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// stage the (Kc, 32) table with padded rows
+__device__ __forceinline__ void stage_table(float* T_s, const float* __restrict__ T, int Kc) {
+  for (int i = threadIdx.x; i < Kc * 8; i += blockDim.x) {
+    const int r = i >> 3, ch = i & 7;
+    *reinterpret_cast<float4*>(T_s + r * TST + ch * 4) = __ldg(reinterpret_cast<const float4*>(T) + i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------------
+struct NceFwdP {
+  const float *c, *W, *T;
+  const int64_t *idx_pos, *idx_neg;
+  int B, N, KR, Kc, SPI;
+  float *u, *pos, *neg, *lse, *nll;
+  int* correct;
+};
+
+// CTA = KR * SPI warps; warp (s, k) walks the samples b = (blockIdx + i * grid) * SPI + s and always handles step k, so
+// W[:, :, k] stays in its registers for the whole kernel.
+__global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
+  extern __shared__ __align__(16) float sm[];
+  float* T_s = sm;                                   // [Kc][TST]
+  float* u_s = T_s + (size_t)p.Kc * TST;             // [warps][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_table(T_s, p.T, p.Kc);
+  const int k = warp % p.KR, s = warp / p.KR;
+  float Wc[IZ];                                      // Wc[c] = W[z = lane][c][k]
+#pragma unroll
+  for (int c = 0; c < IZ; ++c) Wc[c] = __ldg(p.W + ((size_t)lane * IZ + c) * p.KR + k);
+  __syncthreads();
+  float* us = u_s + warp * IZ;
+  const int n = lane & 15, h = lane >> 4;            // candidate n (0 = positive), feature half h
+  const bool act = n <= p.N;
+  for (int64_t b = (int64_t)blockIdx.x * p.SPI + s; b < p.B; b += (int64_t)gridDim.x * p.SPI) {
+    const int64_t r = b * p.KR + k;
+    const float4* c4 = reinterpret_cast<const float4*>(p.c + b * IZ);
+    int code = 0;
+    if (act) code = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * p.N + (n - 1)) * p.KR + k]);
+    code = min(max(code, 0), p.Kc - 1);
+    float u = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(c4 + j);                // same address on every lane: one broadcast transaction
+      u = fmaf(Wc[4 * j], t.x, u);
+      u = fmaf(Wc[4 * j + 1], t.y, u);
+      u = fmaf(Wc[4 * j + 2], t.z, u);
+      u = fmaf(Wc[4 * j + 3], t.w, u);
+    }
+    us[lane] = u;
+    p.u[r * IZ + lane] = u;
+    __syncwarp();
+    // every lane runs the SAME sequence of 16 FMAs on its half row, so candidates that drew the same code get
+    // bit-identical scores (a negative equal to the positive is never "correct", like the reference)
+    const float4* t4 = reinterpret_cast<const float4*>(T_s + code * TST + h * 16);
+    const float4* u4 = reinterpret_cast<const float4*>(us + h * 16);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = t4[j], q = u4[j];
+      acc = fmaf(a.x, q.x, acc);
+      acc = fmaf(a.y, q.y, acc);
+      acc = fmaf(a.z, q.z, acc);
+      acc = fmaf(a.w, q.w, acc);
+    }
+    const float other = __shfl_xor_sync(FULL, acc, 16);
+    float sc = (h == 0) ? acc + other : other + acc;          // (low half) + (high half) on both lanes
+    if (!act) sc = -INFINITY;
+    float m = sc, nm = (n == 0) ? -INFINITY : sc;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+      nm = fmaxf(nm, __shfl_xor_sync(FULL, nm, o));
+    }
+    float e = act ? expf(sc - m) : 0.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
+    const float lse = m + logf(e);
+    if (lane == 0) {
+      p.pos[r] = sc;
+      p.lse[r] = lse;
+      p.nll[r] = lse - sc;
+      p.correct[r] = sc > nm ? 1 : 0;
+    } else if (lane <= p.N) {
+      p.neg[r * p.N + lane - 1] = sc;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward of the scorer: coefficients, dc, per-CTA partial dW and dT
+// ---------------------------------------------------------------------------------------------------------------------
+struct NceBwdP {
+  const float *c, *W, *T;
+  const int64_t *idx_pos, *idx_neg;
+  const float *u, *pos, *neg, *lse, *g_dev;
+  float scale;
+  int B, N, KR, Kc, SPI;
+  float *dc, *coef_pos, *coef_neg, *part;            // part: [gridDim][Kc * 32 + 32 * 32 * KR]
+  size_t scratch_floats;                             // size of the T_s / scratch region
+};
+
+__global__ void __launch_bounds__(512, 1) nce_idx_bwd_kernel(NceBwdP p) {
+  extern __shared__ __align__(16) float sm[];
+  const int NW = blockDim.x >> 5, R = NW;            // rows (b, k) per iteration == warps
+  float* T_s = sm;                                   // [Kc][TST]; reused as [NW][32][32] scratch at the end
+  float* dT_s = T_s + p.scratch_floats;              // [Kc][32]  CTA-private gradient of the table
+  float* u_s = dT_s + (size_t)p.Kc * IZ;             // [R][32]
+  float* du_s = u_s + R * IZ;                        // [R][32]
+  float* dcp_s = du_s + R * IZ;                      // [R][32]
+  float* coef_s = dcp_s + R * IZ;                    // [R][16]
+  uint32_t* code_s = reinterpret_cast<uint32_t*>(coef_s + R * 16);   // [R][16]: code | owner warp << 16 (0xFFFF....: none)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_table(T_s, p.T, p.Kc);
+  for (int i = threadIdx.x; i < p.Kc * IZ; i += blockDim.x) dT_s[i] = 0.f;
+  const int k = warp % p.KR, s = warp / p.KR;
+  float Wz[IZ], acc[IZ];                             // Wz[z] = W[z][c = lane][k];  acc[z] = dW[z][c = lane][k]
+#pragma unroll
+  for (int z = 0; z < IZ; ++z) {
+    Wz[z] = __ldg(p.W + ((size_t)z * IZ + lane) * p.KR + k);
+    acc[z] = 0.f;
+  }
+  const float gs = p.scale * (p.g_dev ? __ldg(p.g_dev) : 1.f);
+  __syncthreads();
+  const int64_t nit = (p.B + (int64_t)gridDim.x * p.SPI - 1) / ((int64_t)gridDim.x * p.SPI);
+  for (int64_t it = 0; it < nit; ++it) {
+    const int64_t b = (it * gridDim.x + blockIdx.x) * p.SPI + s;
+    const bool valid = b < p.B;
+    const int64_t r = b * p.KR + k;
+    // ---- phase a: this warp's row
+    if (lane < 16) {
+      const int n = lane;
+      uint32_t cw = 0xFFFF0000u;
+      float cf = 0.f;
+      if (valid && n <= p.N) {
+        const float sc = (n == 0) ? __ldg(p.pos + r) : __ldg(p.neg + r * p.N + n - 1);
+        int code = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * p.N + (n - 1)) * p.KR + k]);
+        code = min(max(code, 0), p.Kc - 1);
+        cf = gs * (expf(sc - __ldg(p.lse + r)) - (n == 0 ? 1.f : 0.f));
+        if (n == 0) p.coef_pos[r] = cf; else p.coef_neg[(b * p.N + (n - 1)) * p.KR + k] = cf;
+        cw = (uint32_t)code | ((uint32_t)(code % NW) << 16);
+      }
+      code_s[warp * 16 + n] = cw;
+      coef_s[warp * 16 + n] = cf;
+    }
+    u_s[warp * IZ + lane] = valid ? __ldg(p.u + r * IZ + lane) : 0.f;
+    const float cb = valid ? __ldg(p.c + b * IZ + lane) : 0.f;         // lane = c
+    __syncwarp();
+    float du = 0.f;                                                     // lane = z
+#pragma unroll
+    for (int n4 = 0; n4 < 4; ++n4) {
+      const uint4 cd = *reinterpret_cast<const uint4*>(code_s + warp * 16 + n4 * 4);
+      const float4 cf = *reinterpret_cast<const float4*>(coef_s + warp * 16 + n4 * 4);
+      du = fmaf(cf.x, T_s[(cd.x & 0xFFFFu) * TST + lane], du);
+      du = fmaf(cf.y, T_s[(cd.y & 0xFFFFu) * TST + lane], du);
+      du = fmaf(cf.z, T_s[(cd.z & 0xFFFFu) * TST + lane], du);
+      du = fmaf(cf.w, T_s[(cd.w & 0xFFFFu) * TST + lane], du);
+    }
+    du_s[warp * IZ + lane] = du;
+    __syncwarp();
+    float dck = 0.f;
+#pragma unroll
+    for (int z4 = 0; z4 < 8; ++z4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(du_s + warp * IZ + z4 * 4);
+      dck = fmaf(Wz[4 * z4], d4.x, dck);
+      dck = fmaf(Wz[4 * z4 + 1], d4.y, dck);
+      dck = fmaf(Wz[4 * z4 + 2], d4.z, dck);
+      dck = fmaf(Wz[4 * z4 + 3], d4.w, dck);
+      acc[4 * z4] = fmaf(d4.x, cb, acc[4 * z4]);
+      acc[4 * z4 + 1] = fmaf(d4.y, cb, acc[4 * z4 + 1]);
+      acc[4 * z4 + 2] = fmaf(d4.z, cb, acc[4 * z4 + 2]);
+      acc[4 * z4 + 3] = fmaf(d4.w, cb, acc[4 * z4 + 3]);
+    }
+    dcp_s[warp * IZ + lane] = dck;
+    __syncthreads();
+    // ---- phase b: dc of the sample (fixed order over k), then the owner-computes sweep for dT
+    if (k == 0 && valid) {
+      float t = 0.f;
+      for (int kk = 0; kk < p.KR; ++kk) t += dcp_s[(s * p.KR + kk) * IZ + lane];
+      p.dc[b * IZ + lane] = t;
+    }
+    for (int t0 = 0; t0 < R * 16; t0 += 32) {
+      const uint32_t v = code_s[t0 + lane];
+      uint32_t m = __ballot_sync(FULL, (v >> 16) == (uint32_t)warp);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t vv = __shfl_sync(FULL, v, j);
+        const int t = t0 + j;
+        float* d = dT_s + (vv & 0xFFFFu) * IZ + lane;
+        *d = fmaf(coef_s[t], u_s[(t >> 4) * IZ + lane], *d);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- per-CTA partials: dT as is, dW combined over the warps that share k (fixed order), stored in (z, c, k) order
+  float* part = p.part + (size_t)blockIdx.x * ((size_t)p.Kc * IZ + (size_t)IZ * IZ * p.KR);
+  for (int i = threadIdx.x; i < p.Kc * 8; i += blockDim.x)
+    reinterpret_cast<float4*>(part)[i] = reinterpret_cast<const float4*>(dT_s)[i];
+  float* scr = T_s;                                  // all reads of T_s are behind the loop's last barrier
+#pragma unroll
+  for (int z = 0; z < IZ; ++z) scr[(warp * IZ + z) * IZ + lane] = acc[z];
+  __syncthreads();
+  float* pw = part + (size_t)p.Kc * IZ;
+  for (int i = threadIdx.x; i < IZ * IZ * p.KR; i += blockDim.x) {
+    const int kk = i % p.KR, zc = i / p.KR;
+    float t = 0.f;
+    for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
+    pw[i] = t;
+  }
+}
+
+// out_a[i] += sum_p part[p][i] (i < na);  out_b[i] += sum_p part[p][na + i] (i < nb);  na, nb multiples of 4.
+// 256 threads = 32 float4 columns x 8 groups of partials; fixed summation order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t stride,
+                                                              float* __restrict__ out_a, int na, float* __restrict__ out_b, int nb) {
+  __shared__ float4 red[8][32];
+  const int cx = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int col4 = blockIdx.x * 32 + cx;
+  const int ncol4 = (na + nb) >> 2;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col4 < ncol4) {
+#pragma unroll 4
+    for (int q = pg; q < nparts; q += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)q * stride) + col4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[pg][cx] = a;
+  __syncthreads();
+  if (pg == 0 && col4 < ncol4) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float4 v = red[q][cx];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float4* o = (col4 * 4 < na) ? reinterpret_cast<float4*>(out_a) + col4 : reinterpret_cast<float4*>(out_b) + (col4 - (na >> 2));
+    float4 c = *o;
+    c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w;
+    *o = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// out[idx[i]] += rows[i]  without atomics: CTA j owns the codes [j * cpc, (j + 1) * cpc), every warp scans its slice of
+// the index list and keeps warp-private sums, combined in warp order (deterministic).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) table_scatter_add_kernel(const int64_t* __restrict__ idx, int64_t n, const float* __restrict__ rows,
+                                                                int zd, int Kc, int cpc, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];        // [warps][cpc][zd]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int c0 = blockIdx.x * cpc;
+  for (int i = threadIdx.x; i < NW * cpc * zd; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float* mine = sm + (size_t)warp * cpc * zd;
+  const int64_t per = ((n + NW - 1) / NW + 31) / 32 * 32;
+  const int64_t beg = warp * per, end = min(n, beg + per);
+  for (int64_t i0 = beg; i0 < end; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const int code = i < end ? (int)idx[i] : -1;
+    uint32_t m = __ballot_sync(FULL, code >= c0 && code < c0 + cpc);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int cj = __shfl_sync(FULL, code, j) - c0;
+      for (int f = lane; f < zd; f += 32) mine[cj * zd + f] += __ldg(rows + (i0 + j) * zd + f);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < cpc * zd; e += blockDim.x) {
+    if (c0 + e / zd >= Kc) break;
+    float t = 0.f;
+    for (int w = 0; w < NW; ++w) t += sm[(size_t)w * cpc * zd + e];
+    out[(size_t)c0 * zd + e] += t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward of the quantizer in index form: dz for every vector, dE
+// ---------------------------------------------------------------------------------------------------------------------
+struct IdxSeg {
+  int64_t row0, rows;
+  int kind;                   // 1: dy rows a[(p - row0) * 32 ..];  2: a[p - row0] * b[((p - row0) / per_b * KR + (p - row0) % KR) * 32 ..]
+  const float *a, *b;
+  int per_b, KR;
+};
+struct VqIdxBwdP {
+  const float *x, *E, *J, *gl;
+  const int64_t* idx;
+  int64_t n;
+  int Kc;
+  float beta;
+  int squared, nseg, j_smem;
+  IdxSeg seg[4];
+  float *dx, *dE;
+};
+
+constexpr int VCH = 512;      // vectors per CTA pass == threads
+
+template <int DS>
+__global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
+  constexpr int JROW = IZ * DS;                      // floats of J per code
+  constexpr int JST = JROW + 4;                      // padded stride: consecutive codes start 4 banks apart
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* J_s = reinterpret_cast<float*>(smraw);                                        // [Kc][JST] (if j_smem)
+  float* gdq_s = J_s + (p.j_smem ? (size_t)p.Kc * JST : 0);                              // [VCH][DS]  g_loss * dloss/dq
+  float* coef_s = gdq_s + VCH * DS;                                                      // [VCH]      scale of the source row
+  uint32_t* src_s = reinterpret_cast<uint32_t*>(coef_s + VCH);                           // [VCH]      source row | segment << 30
+  int* hist_s = reinterpret_cast<int*>(src_s + VCH);                                     // [Kc]
+  int* start_s = hist_s + p.Kc;                                                          // [Kc + 1]
+  int* cur_s = start_s + p.Kc + 1;                                                       // [Kc]
+  int* wsum_s = cur_s + p.Kc;                                                            // [32]
+  uint16_t* code_s = reinterpret_cast<uint16_t*>(wsum_s + 32);                           // [VCH]
+  uint16_t* perm_s = code_s + VCH;                                                       // [VCH]
+  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(perm_s + VCH) + 7) & ~(uintptr_t)7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_a = s_u32(bar);
+  if (p.j_smem) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(p.Kc * JROW * 4)) : "memory");
+    __syncthreads();
+    // one bulk copy per code row (JROW * 4 bytes, a multiple of 16) into the padded layout; overlaps the first pass
+    for (int kx = tid; kx < p.Kc; kx += VCH)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(J_s + (size_t)kx * JST)),
+                   "l"(p.J + (size_t)kx * JROW), "r"((uint32_t)(JROW * 4)), "r"(bar_a)
+                   : "memory");
+  }
+  for (int i = tid; i < p.Kc; i += VCH) hist_s[i] = 0;
+  float accE[2][DS];                                 // thread t owns the codes t and t + VCH (Kc <= 2 * VCH)
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int d = 0; d < DS; ++d) accE[a][d] = 0.f;
+  bool j_ready = !p.j_smem;
+  __syncthreads();
+  const int64_t nchunk = (p.n + VCH - 1) / VCH;
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    // ---- phase 1: thread == vector: loss gradients, source row of the upscaled-side gradient, histogram
+    {
+      const int64_t v = ch * VCH + tid;
+      const bool ok = v < p.n;
+      int code = 0xFFFF;
+      uint32_t src = 0xFFFFFFFFu;
+      float cf = 0.f;
+      float g[DS];
+#pragma unroll
+      for (int d = 0; d < DS; ++d) g[d] = 0.f;
+      if (ok) {
+        code = min(max((int)p.idx[v], 0), p.Kc - 1);
+        const float gl = p.gl ? __ldg(p.gl + v) : 0.f;
+        float df[DS];
+        float ssq = 0.f;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+          df[d] = __ldg(p.E + code * DS + d) - __ldg(p.x + v * DS + d);
+          const float t = df[d] + 1e-5f;
+          ssq = fmaf(t, t, ssq);
+        }
+        const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
+#pragma unroll
+        for (int d = 0; d < DS; ++d) g[d] = gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
+        for (int sgi = 0; sgi < p.nseg; ++sgi) {
+          const IdxSeg& sg = p.seg[sgi];
+          if (v >= sg.row0 && v < sg.row0 + sg.rows) {
+            const uint32_t pl = (uint32_t)(v - sg.row0);
+            if (sg.kind == 1) {
+              src = pl | ((uint32_t)sgi << 30);
+              cf = 1.f;
+            } else {
+              src = ((pl / (uint32_t)sg.per_b) * (uint32_t)sg.KR + pl % (uint32_t)sg.KR) | ((uint32_t)sgi << 30);
+              cf = __ldg(sg.a + pl);
+            }
+          }
+        }
+        atomicAdd(&hist_s[code], 1);
+      }
+#pragma unroll
+      for (int d = 0; d < DS; ++d) gdq_s[tid * DS + d] = g[d];
+      coef_s[tid] = cf;
+      src_s[tid] = src;
+      code_s[tid] = (uint16_t)code;
+    }
+    __syncthreads();
+    // ---- phase 2: exclusive scan of the histogram (Kc <= 2 * VCH bins, two per thread)
+    {
+      const int b0 = 2 * tid, b1 = 2 * tid + 1;
+      const int h0 = b0 < p.Kc ? hist_s[b0] : 0, h1 = b1 < p.Kc ? hist_s[b1] : 0;
+      int incl = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) wsum_s[warp] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; ++w) base += wsum_s[w];
+      const int ex = base + incl - (h0 + h1);
+      if (b0 < p.Kc) { start_s[b0] = ex; cur_s[b0] = ex; hist_s[b0] = 0; }
+      if (b1 < p.Kc) { start_s[b1] = ex + h0; cur_s[b1] = ex + h0; hist_s[b1] = 0; }
+    }
+    __syncthreads();
+    // ---- phase 3: scatter the vector slots into code order
+    {
+      const int code = code_s[tid];
+      if (code != 0xFFFF) perm_s[atomicAdd(&cur_s[code], 1)] = (uint16_t)tid;
+    }
+    __syncthreads();
+    // ---- phase 4: thread == code: sequential sum over the code's vectors of this pass (no atomics)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int code = tid + a * VCH;
+      if (code < p.Kc) {
+        const int e = cur_s[code];
+        for (int t = start_s[code]; t < e; ++t) {
+          const int i = perm_s[t];
+#pragma unroll
+          for (int d = 0; d < DS; ++d) accE[a][d] += gdq_s[i * DS + d];
+        }
+      }
+    }
+    // ---- phase J: a quad of lanes per vector: dz = coef * J[code]^T v - beta * g_loss * dloss/dq
+    if (!j_ready) {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+      j_ready = true;
+    }
+    const int ql = tid & 3, qid = tid >> 2;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      const int i = pass * (VCH / 4) + qid;
+      const int64_t v = ch * VCH + i;
+      const uint32_t src = src_s[i];
+      float gz[DS];
+#pragma unroll
+      for (int d = 0; d < DS; ++d) gz[d] = 0.f;
+      if (src != 0xFFFFFFFFu) {
+        const IdxSeg& sg = p.seg[src >> 30];
+        const float* row = (sg.kind == 1 ? sg.a : sg.b) + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(row)), v1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const int code = code_s[i];
+        const float* jr = p.j_smem ? (J_s + (size_t)code * JST + ql * 8 * DS) : (p.J + (size_t)code * JROW + ql * 8 * DS);
+        float jv[8 * DS];
+#pragma unroll
+        for (int q4 = 0; q4 < 2 * DS; ++q4) {
+          const float4 t = *reinterpret_cast<const float4*>(jr + q4 * 4);
+          jv[q4 * 4] = t.x; jv[q4 * 4 + 1] = t.y; jv[q4 * 4 + 2] = t.z; jv[q4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int d = 0; d < DS; ++d) gz[d] = fmaf(vv[t], jv[t * DS + d], gz[d]);
+      }
+      // (all four lanes of a quad take the same branch above; the shuffles below are executed by the whole warp)
+#pragma unroll
+      for (int d = 0; d < DS; ++d) {
+        gz[d] += __shfl_xor_sync(FULL, gz[d], 1);
+        gz[d] += __shfl_xor_sync(FULL, gz[d], 2);
+      }
+      if (v < p.n && ql < DS) {
+        float mine = gz[0];
+#pragma unroll
+        for (int d = 1; d < DS; ++d) mine = (ql == d) ? gz[d] : mine;
+        p.dx[v * DS + ql] = fmaf(coef_s[i], mine, -p.beta * gdq_s[i * DS + ql]);
+      }
+    }
+    __syncthreads();
+  }
+  if (p.dE) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int code = tid + a * VCH;
+      if (code < p.Kc)
+#pragma unroll
+        for (int d = 0; d < DS; ++d)
+          if (accE[a][d] != 0.f) atomicAdd(p.dE + code * DS + d, accE[a][d]);
+    }
+  }
+}
+
+template <int DS>
+size_t vq_idx_bwd_smem(int Kc, bool j_smem) {
+  size_t s = j_smem ? (size_t)Kc * (IZ * DS + 4) * 4 : 0;
+  s += (size_t)VCH * DS * 4 + VCH * 4 + VCH * 4;     // gdq, coef, src
+  s += ((size_t)3 * Kc + 1 + 32) * 4;                // hist, start, cur, wsum
+  s += VCH * 2 * 2;                                  // code, perm
+  s = (s + 7) & ~(size_t)7;
+  return s + 16;
+}
+
+int nce_spi(int KR) { return KR >= 9 ? 1 : 16 / KR; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+static int idx_path_check(const char* who, int N, int KR, int zd, int cd, int Kc) {
+  VQ_CHECK_ARG(zd == IZ && cd == IZ, "%s: the index path is specialised for zd == cd == 32 (got %d, %d)", who, zd, cd);
+  VQ_CHECK_ARG(N >= 1 && N <= 15, "%s: 1 <= N <= 15 negatives supported (got %d)", who, N);
+  VQ_CHECK_ARG(KR >= 1 && KR <= 16, "%s: 1 <= KR <= 16 (got %d)", who, KR);
+  VQ_CHECK_ARG(Kc >= 1 && Kc <= 65535 && (size_t)Kc * (TST + IZ) * 4 <= 190 * 1024, "%s: Kc=%d tables do not fit in shared memory", who, Kc);
+  return VQ_OK;
+}
+
+// 1 if the shapes are handled by the index-path kernels below (callers fall back to the per-vector path otherwise)
+VQ_API int vqcpc_idxpath_supported(int N, int KR, int zd, int cd, int Kc, int D) {
+  return (zd == IZ && cd == IZ && N >= 1 && N <= 15 && KR >= 1 && KR <= 16 && Kc >= 1 && Kc <= 2 * VCH &&
+          (size_t)Kc * (TST + IZ) * 4 <= 190 * 1024 && (D == 3 || D == 4)) ? 1 : 0;
+}
+
+// number of per-CTA partial tables vqcpc_infonce_idx_bwd writes (rows of `part`)
+VQ_API int vqcpc_infonce_idx_parts(int B, int KR) {
+  const int spi = nce_spi(KR);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(vq_sm_count(), vq_cdiv(B, spi)));
+}
+
+VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
+                                 int B, int N, int KR, int zd, int cd, int Kc, float* u, float* pos, float* neg, float* lse,
+                                 float* nll, int* correct, void* stream) {
+  if (int rc = idx_path_check("infonce_idx_fwd", N, KR, zd, cd, Kc)) return rc;
+  if (B == 0) return VQ_OK;
+  NceFwdP p{c, W, T, idx_pos, idx_neg, B, N, KR, Kc, nce_spi(KR), u, pos, neg, lse, nll, correct};
+  const int warps = KR * p.SPI;
+  const size_t smem = ((size_t)Kc * TST + (size_t)warps * IZ) * 4;
+  const int grid = vqcpc_infonce_idx_parts(B, KR);
+  VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nce_idx_fwd_kernel<<<grid, warps * 32, smem, vq_stream(stream)>>>(p);
+  VQ_CUDA_LAUNCH_CHECK("nce_idx_fwd_kernel");
+  return VQ_OK;
+}
+
+VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
+                                 const float* u, const float* pos, const float* neg, const float* lse, const float* g_dev,
+                                 float scale, int B, int N, int KR, int zd, int cd, int Kc, float* d_c, float* coef_pos,
+                                 float* coef_neg, float* part, float* d_W, float* d_T, void* stream) {
+  if (int rc = idx_path_check("infonce_idx_bwd", N, KR, zd, cd, Kc)) return rc;
+  if (B == 0) return VQ_OK;
+  NceBwdP p{};
+  p.c = c; p.W = W; p.T = T; p.idx_pos = idx_pos; p.idx_neg = idx_neg; p.u = u; p.pos = pos; p.neg = neg; p.lse = lse;
+  p.g_dev = g_dev; p.scale = scale; p.B = B; p.N = N; p.KR = KR; p.Kc = Kc; p.SPI = nce_spi(KR);
+  p.dc = d_c; p.coef_pos = coef_pos; p.coef_neg = coef_neg; p.part = part;
+  const int warps = KR * p.SPI;
+  p.scratch_floats = std::max<size_t>((size_t)Kc * TST, (size_t)warps * IZ * IZ);
+  p.scratch_floats = (p.scratch_floats + 3) & ~(size_t)3;
+  const size_t smem = (p.scratch_floats + (size_t)Kc * IZ + (size_t)warps * (3 * IZ + 32)) * 4;
+  VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_bwd: %zu bytes of shared memory needed", smem);
+  const int grid = vqcpc_infonce_idx_parts(B, KR);
+  cudaStream_t st = vq_stream(stream);
+  VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nce_idx_bwd_kernel<<<grid, warps * 32, smem, st>>>(p);
+  VQ_CUDA_LAUNCH_CHECK("nce_idx_bwd_kernel");
+  const int na = Kc * IZ, nb = IZ * IZ * KR;
+  const int ncol4 = (na + nb) / 4;
+  reduce_partials_kernel<<<(ncol4 + 31) / 32, 256, 0, st>>>(part, grid, (size_t)na + nb, d_T, na, d_W, nb);
+  VQ_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
+  return VQ_OK;
+}
+
+VQ_API int vqcpc_table_scatter_add(const int64_t* idx, int64_t n, const float* rows, int zd, int Kc, float* out, void* stream) {
+  VQ_CHECK_ARG(zd >= 1 && Kc >= 1, "table_scatter_add: bad shape zd=%d Kc=%d", zd, Kc);
+  if (n == 0) return VQ_OK;
+  const int grid = std::min(vq_sm_count(), Kc);
+  const int cpc = (Kc + grid - 1) / grid;
+  const size_t smem = (size_t)16 * cpc * zd * 4;
+  VQ_CHECK_ARG(smem <= 200 * 1024, "table_scatter_add: %zu bytes of shared memory needed", smem);
+  VQ_CUDA_CALL(cudaFuncSetAttribute(table_scatter_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  table_scatter_add_kernel<<<(Kc + cpc - 1) / cpc, 512, smem, vq_stream(stream)>>>(idx, n, rows, zd, Kc, cpc, out);
+  VQ_CUDA_LAUNCH_CHECK("table_scatter_add_kernel");
+  return VQ_OK;
+}
+
+VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,
+                            float beta, int squared, const float* g_loss, int nseg, const int64_t* seg_row0, const int64_t* seg_rows,
+                            const int* seg_kind, const float* const* seg_a, const float* const* seg_b, const int* seg_per_b, int KR,
+                            float* d_x, float* d_E, void* stream) {
+  VQ_CHECK_ARG(D == 3 || D == 4, "vq_idx_bwd: D must be 3 or 4 (got %d)", D);
+  VQ_CHECK_ARG(zd == IZ, "vq_idx_bwd: zd must be 32 (got %d)", zd);
+  VQ_CHECK_ARG(Kc >= 1 && Kc <= 2 * VCH, "vq_idx_bwd: Kc <= %d (got %d)", 2 * VCH, Kc);
+  VQ_CHECK_ARG(nseg >= 0 && nseg <= 4, "vq_idx_bwd: at most 4 segments (got %d)", nseg);
+  if (n == 0) return VQ_OK;
+  VqIdxBwdP p{};
+  p.x = x; p.E = E; p.J = J; p.gl = g_loss; p.idx = idx; p.n = n; p.Kc = Kc; p.beta = beta; p.squared = squared; p.nseg = nseg;
+  p.dx = d_x; p.dE = d_E;
+  for (int i = 0; i < nseg; ++i) {
+    VQ_CHECK_ARG(seg_kind[i] == 1 || seg_kind[i] == 2, "vq_idx_bwd: segment kind must be 1 (rows) or 2 (coef * u)");
+    VQ_CHECK_ARG(seg_row0[i] >= 0 && seg_rows[i] >= 0 && seg_row0[i] + seg_rows[i] <= n && seg_rows[i] < (1 << 30),
+                 "vq_idx_bwd: segment %d out of range", i);
+    VQ_CHECK_ARG(seg_kind[i] == 1 || (seg_per_b[i] >= 1 && KR >= 1 && seg_per_b[i] % KR == 0), "vq_idx_bwd: segment %d: bad per_b / KR", i);
+    VQ_CHECK_ARG((((uintptr_t)seg_a[i] | (uintptr_t)(seg_kind[i] == 2 ? seg_b[i] : nullptr)) & 15) == 0, "vq_idx_bwd: segment %d: sources must be 16-byte aligned", i);
+    p.seg[i] = IdxSeg{seg_row0[i], seg_rows[i], seg_kind[i], seg_a[i], seg_kind[i] == 2 ? seg_b[i] : nullptr, seg_kind[i] == 2 ? seg_per_b[i] : 1, KR};
+  }
+  cudaStream_t st = vq_stream(stream);
+  const int64_t nchunk = vq_cdiv(n, VCH);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, vq_sm_count()));
+#define VQ_IB(DSV)                                                                                                            \
+  do {                                                                                                                        \
+    const bool js = (((uintptr_t)J & 15) == 0) && vq_idx_bwd_smem<DSV>(Kc, true) <= 227 * 1024;                               \
+    p.j_smem = js ? 1 : 0;                                                                                                    \
+    const size_t smem = vq_idx_bwd_smem<DSV>(Kc, js);                                                                         \
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_bwd_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    vq_idx_bwd_kernel<DSV><<<grid, VCH, smem, st>>>(p);                                                                       \
+  } while (0)
+  if (D == 3) VQ_IB(3); else VQ_IB(4);
+#undef VQ_IB
+  VQ_CUDA_LAUNCH_CHECK("vq_idx_bwd_kernel");
+  return VQ_OK;
+}

@@ -159,7 +159,7 @@ template <int DS>
 __global__ void __launch_bounds__(256)
 vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, const float* __restrict__ T, int Kc, int zd,
                     int64_t n, float beta, int squared, int64_t* __restrict__ idx, float* __restrict__ loss,
-                    float* __restrict__ zsg, float* __restrict__ y, int* __restrict__ counts) {
+                    float* __restrict__ zsg, float* __restrict__ y, int64_t y_row0, int64_t y_rows, int* __restrict__ counts) {
   extern __shared__ __align__(16) float sm[];
   constexpr int CS = (DS == 3) ? 4 : DS;          // padded code stride (one LDS.128 per code for D = 3)
   float* cb = sm;                                  // [Kc][CS]
@@ -207,11 +207,12 @@ vq_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ E, co
       idx[v] = bi;
       if (counts) atomicAdd(&hist[bi], 1);
     }
-    if (y) {
+    if (y && v0 < y_row0 + y_rows && v0 + 32 > y_row0) {         // y covers the rows [y_row0, y_row0 + y_rows) only
       for (int sft = 0; sft < 32; ++sft) {
         const int b = __shfl_sync(0xffffffffu, bi, sft);
-        if (v0 + sft < n)
-          for (int j = lane; j < zd; j += 32) y[(v0 + sft) * zd + j] = __ldg(T + (size_t)b * zd + j);
+        const int64_t r = v0 + sft;
+        if (r < n && r >= y_row0 && r < y_row0 + y_rows)
+          for (int j = lane; j < zd; j += 32) y[(r - y_row0) * zd + j] = __ldg(T + (size_t)b * zd + j);
       }
     }
   }
@@ -576,7 +577,8 @@ VQ_API int vqcpc_vq_bwd(const float* x, int64_t n, int D, const float* const* bo
 //   algo: 0 = automatic, 1 = direct-form scan on the CUDA cores, 2 = tcgen05 score + exact verification (vq_tc.cu).
 //   Both algorithms return bit-identical indices.  dbg_scores / stats: test hooks of algo 2 (NULL in production).
 static int vq_fused_fwd_direct(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
-                               int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, cudaStream_t st) {
+                               int squared, int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows,
+                               int* counts, cudaStream_t st) {
   const int cs = D == 3 ? 4 : D;
   size_t smem = ((size_t)Kc * cs + Kc) * sizeof(float);
   VQ_CHECK_ARG(smem <= 200 * 1024, "vq_fused_fwd: codebook (%zu B) does not fit in shared memory", smem);
@@ -585,7 +587,7 @@ static int vq_fused_fwd_direct(const float* x, int64_t n, int D, const float* E,
 #define VQ_FL(DSV)                                                                                                          \
   do {                                                                                                                      \
     VQ_CUDA_CALL(cudaFuncSetAttribute(vq_fused_fwd_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    vq_fused_fwd_kernel<DSV><<<grid, 256, smem, st>>>(x, E, T, Kc, zd, n, beta, squared, idx, loss, z_sg, y, counts);       \
+    vq_fused_fwd_kernel<DSV><<<grid, 256, smem, st>>>(x, E, T, Kc, zd, n, beta, squared, idx, loss, z_sg, y, y_row0, y_rows, counts);        \
   } while (0)
   switch (D) {
     case 3: VQ_FL(3); break;
@@ -599,12 +601,14 @@ static int vq_fused_fwd_direct(const float* x, int64_t n, int D, const float* E,
   return VQ_OK;
 }
 
-VQ_API int vqcpc_vq_fused_fwd_ex(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
-                                 int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, int algo,
-                                 float* dbg_scores, int* stats, void* stream) {
+static int vq_fused_fwd_any(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                            int squared, int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows,
+                            int* counts, int algo, float* dbg_scores, int* stats, void* stream) {
   VQ_CHECK_ARG(D == 3 || D == 4 || D == 8 || D == 16 || D == 32, "vq_fused_fwd: D must be 3, 4, 8, 16 or 32 (got %d)", D);
   VQ_CHECK_ARG((T == nullptr) == (y == nullptr), "vq_fused_fwd: T and y go together");
   VQ_CHECK_ARG(algo >= 0 && algo <= 2, "vq_fused_fwd: algo must be 0 (auto), 1 (direct) or 2 (tensor) (got %d)", algo);
+  VQ_CHECK_ARG(y_row0 >= 0 && y_rows >= 0 && y_row0 + y_rows <= n, "vq_fused_fwd: y row range [%lld, +%lld) outside [0, %lld)",
+               (long long)y_row0, (long long)y_rows, (long long)n);
   if (n == 0) return VQ_OK;
   cudaStream_t st = vq_stream(stream);
   if (algo == 0) {
@@ -615,9 +619,24 @@ VQ_API int vqcpc_vq_fused_fwd_ex(const float* x, int64_t n, int D, const float* 
   if (algo == 2) {
     VQ_CHECK_ARG(vq_tc_supported(D, Kc), "vq_fused_fwd: tensor-core search supports D in {3, 4}, Kc <= 2048 (got D=%d Kc=%d)", D, Kc);
     static const int variant = getenv("VQCPC_VQTC_LAYOUT") ? atoi(getenv("VQCPC_VQTC_LAYOUT")) : 0;
-    return vq_tc_fused_fwd(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, counts, dbg_scores, stats, variant, st);
+    return vq_tc_fused_fwd(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, y_row0, y_rows, counts, dbg_scores, stats,
+                           variant, st);
   }
-  return vq_fused_fwd_direct(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, counts, st);
+  return vq_fused_fwd_direct(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, y_row0, y_rows, counts, st);
+}
+
+VQ_API int vqcpc_vq_fused_fwd_ex(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                                 int squared, int64_t* idx, float* loss, float* z_sg, float* y, int* counts, int algo,
+                                 float* dbg_scores, int* stats, void* stream) {
+  return vq_fused_fwd_any(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, 0, n, counts, algo, dbg_scores, stats, stream);
+}
+
+// Index-path form: the upscaled rows y = T[idx] are produced only for the rows [y_row0, y_row0 + y_rows) (y has y_rows rows).
+VQ_API int vqcpc_vq_fused_fwd_rows(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,
+                                   int squared, int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows,
+                                   int* counts, void* stream) {
+  return vq_fused_fwd_any(x, n, D, E, T, Kc, zd, beta, squared, idx, loss, z_sg, y, y_row0, y_rows, counts, 0, nullptr, nullptr,
+                          stream);
 }
 
 VQ_API int vqcpc_vq_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,

@@ -60,6 +60,7 @@ struct VtParams {
   float* loss;
   float* zsg;
   float* y;
+  int64_t y_row0, y_rows;   // y holds T[idx] for the rows [y_row0, y_row0 + y_rows) only, stored from row 0 of y
   int* counts;
   float* dbg;            // optional (n, dbg_ld) dump of the tensor-core scores (tests only)
   int dbg_ld;
@@ -450,8 +451,12 @@ vq_tc_fwd_kernel(VtParams p) {
         p.idx[row] = bi;
         if (p.counts) atomicAdd(&hist[bi], 1);
       }
-      if (p.y) {
+      // y = T[idx] only for the rows of the range (the index path needs the upscaled vector of the LEFT blocks alone: the
+      // context GRU reads them; right / negative blocks are scored from their indices).  Warp-uniform early-out.
+      if (p.y && tile * 128 + q * 32 < p.y_row0 + p.y_rows && tile * 128 + q * 32 + 32 > p.y_row0) {
         const int64_t row0 = tile * 128 + q * 32;
+        const int64_t yend = min(p.n, p.y_row0 + p.y_rows);
+        float* ybase = p.y - p.y_row0 * (int64_t)p.zd;
         const int zd = p.zd;
         if (!t_ready) {
           mbar_wait(BAR(BAR_T), 0);
@@ -465,16 +470,18 @@ vq_tc_fwd_kernel(VtParams p) {
             const int b = __shfl_sync(0xffffffffu, bi, ps * 4 + (lane >> 3));
             v[ps] = *(reinterpret_cast<const float4*>(t_sm + b * 32) + (lane & 7));
           }
-          float4* yp = reinterpret_cast<float4*>(p.y + row0 * 32) + lane;
+          float4* yp = reinterpret_cast<float4*>(ybase + row0 * 32) + lane;
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps)
-            if (row0 + ps * 4 + (lane >> 3) < p.n) yp[ps * 32] = v[ps];
+          for (int ps = 0; ps < 8; ++ps) {
+            const int64_t rr = row0 + ps * 4 + (lane >> 3);
+            if (rr >= p.y_row0 && rr < yend) yp[ps * 32] = v[ps];
+          }
         } else {
           for (int r = 0; r < 32; ++r) {
             const int b = __shfl_sync(0xffffffffu, bi, r);
-            if (row0 + r < p.n)
+            if (row0 + r >= p.y_row0 && row0 + r < yend)
               for (int j = lane; j < zd; j += 32)
-                p.y[(row0 + r) * zd + j] = p.t_smem ? t_sm[(size_t)b * zd + j] : __ldg(p.T + (size_t)b * zd + j);
+                ybase[(row0 + r) * zd + j] = p.t_smem ? t_sm[(size_t)b * zd + j] : __ldg(p.T + (size_t)b * zd + j);
           }
         }
       }
@@ -545,13 +552,13 @@ int vt_launch(VtParams& p, cudaStream_t st) {
 bool vq_tc_supported(int D, int Kc) { return (D == 3 || D == 4) && Kc >= 1 && Kc <= 2048; }
 
 int vq_tc_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta, int squared,
-                    int64_t* idx, float* loss, float* z_sg, float* y, int* counts, float* dbg_scores, int* stats, int variant,
-                    cudaStream_t st) {
+                    int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows, int* counts,
+                    float* dbg_scores, int* stats, int variant, cudaStream_t st) {
   (void)variant;
   VQ_CHECK_ARG(vq_tc_supported(D, Kc), "vq_tc: unsupported D=%d / Kc=%d", D, Kc);
   VtParams p;
   p.x = x; p.E = E; p.T = T; p.n = n; p.Kc = Kc; p.nch = 0; p.zd = zd; p.beta = beta; p.squared = squared;
-  p.idx = idx; p.loss = loss; p.zsg = z_sg; p.y = y; p.counts = counts; p.dbg = dbg_scores; p.dbg_ld = (Kc + 255) / 256 * 256;
+  p.idx = idx; p.loss = loss; p.zsg = z_sg; p.y = y; p.y_row0 = y_row0; p.y_rows = y_rows; p.counts = counts; p.dbg = dbg_scores; p.dbg_ld = (Kc + 255) / 256 * 256;
   p.t_smem = 0; p.x_bulk = 0; p.stats = stats;
   switch (D) {
     case 3: return vt_launch<3>(p, st);
