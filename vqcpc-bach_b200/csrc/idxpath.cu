@@ -19,8 +19,11 @@
 //   * owner-computes sweeps (a warp owns a residue class of codes and adds into its rows of a CTA-private table), or
 //   * a counting sort by code inside the CTA (native integer ATOMS) followed by per-code sequential sums,
 // and the cross-CTA reduction goes through per-CTA partial tables summed by a second small kernel (fixed order).
-#include "common.cuh"
+#include "gemm_tc_common.cuh"
 #include <algorithm>
+#include <cstdlib>
+
+using namespace vqtc;
 
 namespace {
 
@@ -28,7 +31,7 @@ constexpr int IZ = 32;          // zd == cd == 32: one lane per feature (every s
 constexpr int TST = 36;         // padded row stride (floats) of the shared-memory table: rows start 4 banks apart
 constexpr unsigned FULL = 0xffffffffu;
 
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return smem_u32(p); }
 
 // stage the (Kc, 32) table with padded rows
 __device__ __forceinline__ void stage_table(float* T_s, const float* __restrict__ T, int Kc) {
@@ -49,55 +52,75 @@ struct NceFwdP {
   int* correct;
 };
 
-// CTA = KR * SPI warps; warp (s, k) walks the samples b = (blockIdx + i * grid) * SPI + s and always handles step k, so
-// W[:, :, k] stays in its registers for the whole kernel.
-__global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
+// 16 warps per CTA, two CTAs per SM (<= 64 registers, ~112 KB of shared memory: the padded table and W transposed to
+// [k][z][c]).  A warp handles TWO (b, k) rows per step: lanes = features while u = W_k c is formed, then lane (j, n) scores
+// candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.  The index
+// gathers are issued before the u phase (their latency hides behind it).
+__global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
   extern __shared__ __align__(16) float sm[];
   float* T_s = sm;                                   // [Kc][TST]
-  float* u_s = T_s + (size_t)p.Kc * TST;             // [warps][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* W_s = T_s + (size_t)p.Kc * TST;             // [KR][32 z][TST]  W_s[k][z][c] = W[z][c][k]
+  float* u_s = W_s + (size_t)p.KR * IZ * TST;        // [warps][2][32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
   stage_table(T_s, p.T, p.Kc);
-  const int k = warp % p.KR, s = warp / p.KR;
-  float Wc[IZ];                                      // Wc[c] = W[z = lane][c][k]
-#pragma unroll
-  for (int c = 0; c < IZ; ++c) Wc[c] = __ldg(p.W + ((size_t)lane * IZ + c) * p.KR + k);
+  for (int i = threadIdx.x; i < IZ * IZ * p.KR; i += blockDim.x) {
+    const int k = i % p.KR, zc = i / p.KR;           // i = (z * 32 + c) * KR + k
+    W_s[(k * IZ + (zc >> 5)) * TST + (zc & 31)] = __ldg(p.W + i);
+  }
   __syncthreads();
-  float* us = u_s + warp * IZ;
-  const int n = lane & 15, h = lane >> 4;            // candidate n (0 = positive), feature half h
+  float* us = u_s + warp * 2 * IZ;
+  const int n = lane & 15, j = lane >> 4;            // candidate n (0 = positive) of row j of the pair
   const bool act = n <= p.N;
-  for (int64_t b = (int64_t)blockIdx.x * p.SPI + s; b < p.B; b += (int64_t)gridDim.x * p.SPI) {
-    const int64_t r = b * p.KR + k;
-    const float4* c4 = reinterpret_cast<const float4*>(p.c + b * IZ);
+  const int64_t rtot = (int64_t)p.B * p.KR;
+  for (int64_t pi = (int64_t)blockIdx.x * NW + warp; 2 * pi < rtot; pi += (int64_t)gridDim.x * NW) {
+    // ---- gather of this lane's candidate code (row 2 pi + j)
+    const int64_t rj = 2 * pi + j;
+    const bool vj = rj < rtot;
+    const int64_t bj = rj / p.KR;
+    const int kj = (int)(rj - bj * p.KR);
     int code = 0;
-    if (act) code = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * p.N + (n - 1)) * p.KR + k]);
-    code = min(max(code, 0), p.Kc - 1);
-    float u = 0.f;
+    if (act && vj) code = (int)(n == 0 ? p.idx_pos[rj] : p.idx_neg[(bj * p.N + (n - 1)) * p.KR + kj]);
+    // ---- u of both rows, lanes = features
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 t = __ldg(c4 + j);                // same address on every lane: one broadcast transaction
-      u = fmaf(Wc[4 * j], t.x, u);
-      u = fmaf(Wc[4 * j + 1], t.y, u);
-      u = fmaf(Wc[4 * j + 2], t.z, u);
-      u = fmaf(Wc[4 * j + 3], t.w, u);
+    for (int jj = 0; jj < 2; ++jj) {
+      const int64_t r = 2 * pi + jj;
+      float u = 0.f;
+      if (r < rtot) {
+        const int64_t b = r / p.KR;
+        const int k = (int)(r - b * p.KR);
+        const float4* c4 = reinterpret_cast<const float4*>(p.c + b * IZ);
+        const float4* w4 = reinterpret_cast<const float4*>(W_s + (k * IZ + lane) * TST);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(c4 + q);            // same address on every lane: one broadcast transaction
+          const float4 w = w4[q];
+          a0 = fmaf(w.x, t.x, a0);
+          a1 = fmaf(w.y, t.y, a1);
+          a2 = fmaf(w.z, t.z, a2);
+          a3 = fmaf(w.w, t.w, a3);
+        }
+        u = (a0 + a1) + (a2 + a3);
+        p.u[r * IZ + lane] = u;
+      }
+      us[jj * IZ + lane] = u;
     }
-    us[lane] = u;
-    p.u[r * IZ + lane] = u;
     __syncwarp();
-    // every lane runs the SAME sequence of 16 FMAs on its half row, so candidates that drew the same code get
+    // ---- scores: every lane runs the SAME sequence of FMAs on its row, so candidates that drew the same code get
     // bit-identical scores (a negative equal to the positive is never "correct", like the reference)
-    const float4* t4 = reinterpret_cast<const float4*>(T_s + code * TST + h * 16);
-    const float4* u4 = reinterpret_cast<const float4*>(us + h * 16);
-    float acc = 0.f;
+    code = min(max(code, 0), p.Kc - 1);
+    const float4* t4 = reinterpret_cast<const float4*>(T_s + code * TST);
+    const float4* u4 = reinterpret_cast<const float4*>(us + j * IZ);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = t4[j], q = u4[j];
-      acc = fmaf(a.x, q.x, acc);
-      acc = fmaf(a.y, q.y, acc);
-      acc = fmaf(a.z, q.z, acc);
-      acc = fmaf(a.w, q.w, acc);
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = t4[q], v = u4[q];
+      a0 = fmaf(a.x, v.x, a0);
+      a1 = fmaf(a.y, v.y, a1);
+      a2 = fmaf(a.z, v.z, a2);
+      a3 = fmaf(a.w, v.w, a3);
     }
-    const float other = __shfl_xor_sync(FULL, acc, 16);
-    float sc = (h == 0) ? acc + other : other + acc;          // (low half) + (high half) on both lanes
+    float sc = (a0 + a1) + (a2 + a3);
     if (!act) sc = -INFINITY;
     float m = sc, nm = (n == 0) ? -INFINITY : sc;
 #pragma unroll
@@ -109,13 +132,15 @@ __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
     const float lse = m + logf(e);
-    if (lane == 0) {
-      p.pos[r] = sc;
-      p.lse[r] = lse;
-      p.nll[r] = lse - sc;
-      p.correct[r] = sc > nm ? 1 : 0;
-    } else if (lane <= p.N) {
-      p.neg[r * p.N + lane - 1] = sc;
+    if (vj) {
+      if (n == 0) {
+        p.pos[rj] = sc;
+        p.lse[rj] = lse;
+        p.nll[rj] = lse - sc;
+        p.correct[rj] = sc > nm ? 1 : 0;
+      } else if (act) {
+        p.neg[rj * p.N + n - 1] = sc;
+      }
     }
     __syncwarp();
   }
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(512, 1) nce_idx_bwd_kernel(NceBwdP p) {
       p.dc[b * IZ + lane] = t;
     }
     for (int t0 = 0; t0 < R * 16; t0 += 32) {
-      const uint32_t v = code_s[t0 + lane];
+      const uint32_t v = (t0 + lane < R * 16) ? code_s[t0 + lane] : 0xFFFF0000u;
       uint32_t m = __ballot_sync(FULL, (v >> 16) == (uint32_t)warp);
       while (m) {
         const int j = __ffs(m) - 1;
@@ -241,6 +266,275 @@ __global__ void __launch_bounds__(512, 1) nce_idx_bwd_kernel(NceBwdP p) {
     float t = 0.f;
     for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
     pw[i] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Same contract, production version: the table gradient  dT = C^T U  on the tensor cores.
+//
+//   C (rows (b, k) x Kc codes) holds the 1 + N coefficients of every row at its code columns, U stacks the u vectors, so
+//   dT[code][z] = sum_rows C[row][code] u[row][z] is a (Kc x rows) . (rows x 32) product.  One tcgen05.mma (kind::f16,
+//   M = 128 codes, N = 32 features, K = 16 rows) per 128-code tile and operand-split pass, accumulated in TMEM (Kc/128 x 32
+//   columns) over ALL rows of the CTA and read back once at the end: no scatter, no sort, no floating-point atomics.
+//   Operands are bf16 (hi, lo) pairs of coef and u; passes hi.hi + hi.lo + lo.hi, fp32 accumulation (the same 16-bit
+//   significand arithmetic as every tcgen05 GEMM of the encoder; |error| <= 2^-16 |coef| |u| per product).
+//
+// CTA = PW = KR * SPI producer warps + 1 MMA warp.  Producer warp w owns K-slot w: per step it turns ONE row (b, k = w % KR)
+// into its column of the operands - the <= 16 non-zero entries of C^T (2-byte stores into a zero-initialised SWIZZLE_32B
+// K-major tile, duplicates of a code merged first; the entries are zeroed again when the stage is recycled) and column w of
+// U^T - and does the small dense parts on the CUDA cores (du = sum_n coef_n T[idx_n], dc = W_k^T du, dW_k += du (x) c).
+// Stages are handed to the MMA warp through mbarriers (full: PW arrivals; empty: tcgen05.commit), so warps run up to NST
+// steps apart and no CTA-wide barrier sits in the loop.
+constexpr int NST = 3;
+
+struct NceBwdTcP {
+  NceBwdP b;
+  int kpad;                   // Kc rounded up to 128
+  int PW;                     // producer warps
+  int tmem_cols;              // power of two >= kpad / 128 * 32
+  uint32_t stage_region;      // bytes of the operand stages (>= PW * 4 KB: reused as the dW scratch at the end)
+};
+
+// byte offset of element (row r, k) inside a SWIZZLE_32B K-major slab [rows][16 bf16]: 16-byte chunk index ^= bit 2 of r
+__device__ __forceinline__ uint32_t kelem_off(int r, int k) { return (uint32_t)(r * 32 + (((k >> 3) ^ ((r >> 2) & 1)) << 4) + (k & 7) * 2); }
+
+__device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, uint32_t off, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+}
+
+__global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
+  const NceBwdP& p = q.b;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int PW = q.PW, kpad = q.kpad, MT = kpad >> 7;
+  const uint32_t A_BYTES = (uint32_t)kpad * 32, STAGE = 2 * A_BYTES + 2048;       // A_hi | A_lo | B_hi (1 KB) | B_lo (1 KB)
+  uint8_t* stages = smem;                                                           // [NST][STAGE]
+  float* T_s = reinterpret_cast<float*>(stages + q.stage_region);                   // [Kc][TST]
+  float* W_s = T_s + (size_t)p.Kc * TST;                                            // [KR][32 c][TST]  W_s[k][c][z] = W[z][c][k]
+  float* coef_s = W_s + (size_t)p.KR * IZ * TST;                                    // [PW][16]
+  int* code_s = reinterpret_cast<int*>(coef_s + PW * 16);                           // [PW][16]
+  float* du_s = reinterpret_cast<float*>(code_s + PW * 16);                         // [PW][32]
+  float* dcp_s = du_s + PW * IZ;                                                    // [2][PW][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dcp_s + 2 * PW * IZ);                // full[NST], empty[NST], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+  const uint32_t bar0 = smem_u32(bars);
+#define BARF(i) (bar0 + 8u * (uint32_t)(i))
+#define BARE(i) (bar0 + 8u * (uint32_t)(NST + (i)))
+#define BARD (bar0 + 8u * (uint32_t)(2 * NST))
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ------------------------------------------------------------------ set-up
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(BARF(i), PW);
+      mbar_init(BARE(i), 1);
+    }
+    mbar_init(BARD, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(q.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (int)(NST * STAGE / 16); i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+  stage_table(T_s, p.T, p.Kc);
+  for (int i = threadIdx.x; i < IZ * IZ * p.KR; i += blockDim.x) {
+    const int k = i % p.KR, zc = i / p.KR;           // i = (z * 32 + c) * KR + k
+    W_s[(k * IZ + (zc & 31)) * TST + (zc >> 5)] = __ldg(p.W + i);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t nit = (p.B + (int64_t)gridDim.x * p.SPI - 1) / ((int64_t)gridDim.x * p.SPI);
+
+  if (warp == PW) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<32>(true, true);
+      constexpr uint32_t hi_c = (256u >> 4) | (1u << 14) | (6u << 29);      // SBO 256 B, descriptor version 1, SWIZZLE_32B
+      constexpr uint32_t lo_c = 1u << 16;
+      const uint32_t sbase = smem_u32(stages) & 0x3FFFFu;
+      for (int64_t it = 0; it < nit; ++it) {
+        const int st = (int)(it % NST);
+        mbar_wait(BARF(st), (uint32_t)((it / NST) & 1));
+        tcgen05_fence_after();
+        const uint32_t a_hi = sbase + (uint32_t)st * STAGE, a_lo = a_hi + A_BYTES, b_hi = a_lo + A_BYTES, b_lo = b_hi + 1024;
+        const uint64_t dbh = pack_desc(lo_c | (b_hi >> 4), hi_c), dbl = pack_desc(lo_c | (b_lo >> 4), hi_c);
+        for (int m = 0; m < MT; ++m) {
+          const uint64_t dah = pack_desc(lo_c | ((a_hi + (uint32_t)m * 4096) >> 4), hi_c);
+          const uint64_t dal = pack_desc(lo_c | ((a_lo + (uint32_t)m * 4096) >> 4), hi_c);
+          const uint32_t d = tmem_base + (uint32_t)(m * 32);
+          umma_bf16(d, dah, dbh, idesc, it > 0 ? 1u : 0u);
+          umma_bf16(d, dah, dbl, idesc, 1u);
+          umma_bf16(d, dal, dbh, idesc, 1u);
+        }
+        umma_commit(BARE(st));
+      }
+      umma_commit(BARD);
+    }
+    __syncwarp();
+  } else {
+    // ============================== producers ==============================
+    const int k = warp % p.KR, s = warp / p.KR;
+    float acc[IZ];                                   // acc[z] = dW[z][c = lane][k]
+#pragma unroll
+    for (int z = 0; z < IZ; ++z) acc[z] = 0.f;
+    const float gs = p.scale * (p.g_dev ? __ldg(p.g_dev) : 1.f);
+    int old_code[NST];                               // lane n: the code whose entry it may have written into stage i
+#pragma unroll
+    for (int i = 0; i < NST; ++i) old_code[i] = -1;
+    float* cfs = coef_s + warp * 16;
+    int* cds = code_s + warp * 16;
+    float* dus = du_s + warp * IZ;
+    const float4* w4 = reinterpret_cast<const float4*>(W_s + (k * IZ + lane) * TST);
+#pragma unroll 1
+    for (int64_t it = 0; it < nit; ++it) {
+      const int st = (int)(it % NST);
+      const int64_t b = (it * gridDim.x + blockIdx.x) * p.SPI + s;
+      const bool valid = b < p.B;
+      const int64_t r = b * p.KR + k;
+      // ---- global reads of the row (issued before the stage wait)
+      float cf = 0.f;
+      int code = -1 - lane;                          // inactive lanes: distinct keys
+      if (lane < 16 && valid && lane <= p.N) {
+        const int n = lane;
+        const float sc = (n == 0) ? __ldg(p.pos + r) : __ldg(p.neg + r * p.N + n - 1);
+        code = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * p.N + (n - 1)) * p.KR + k]);
+        code = min(max(code, 0), p.Kc - 1);
+        cf = gs * (expf(sc - __ldg(p.lse + r)) - (n == 0 ? 1.f : 0.f));
+        if (n == 0) p.coef_pos[r] = cf; else p.coef_neg[(b * p.N + (n - 1)) * p.KR + k] = cf;
+      }
+      const float uz = valid ? __ldg(p.u + r * IZ + lane) : 0.f;          // lane = z
+      const float cb = valid ? __ldg(p.c + b * IZ + lane) : 0.f;          // lane = c
+      if (lane < 16) {
+        cfs[lane] = cf;
+        cds[lane] = code >= 0 ? code : 0;
+      }
+      __syncwarp();
+      // ---- stage hand-over: wait until the MMAs that read this stage NST steps ago have retired, un-write our old entries
+      uint8_t* sg = stages + (size_t)st * STAGE;
+      if (it >= NST) {
+        mbar_wait(BARE(st), (uint32_t)(((it / NST) - 1) & 1));
+        int oc = old_code[0];
+#pragma unroll
+        for (int i = 1; i < NST; ++i) oc = (st == i) ? old_code[i] : oc;
+        if (oc >= 0) {
+          const uint32_t off = kelem_off(oc, warp);
+          *reinterpret_cast<uint16_t*>(sg + off) = 0;
+          *reinterpret_cast<uint16_t*>(sg + A_BYTES + off) = 0;
+        }
+      }
+      __syncwarp();
+      // ---- column `warp` of C^T: merge the candidates that share a code, one 2-byte store pair per distinct code
+      if (lane < 16) {
+        const uint32_t mm = __match_any_sync(0x0000FFFFu, code);
+        float tot = cf;
+        if (code >= 0 && (mm & (mm - 1)) && (__ffs(mm) - 1 == lane)) {
+          uint32_t rest = mm & ~(1u << lane);
+          while (rest) {
+            const int j = __ffs(rest) - 1;
+            rest &= rest - 1;
+            tot += cfs[j];
+          }
+        }
+        if (code >= 0 && (__ffs(mm) - 1 == lane)) split_store(sg, sg + A_BYTES, kelem_off(code, warp), tot);
+      }
+#pragma unroll
+      for (int i = 0; i < NST; ++i) old_code[i] = (st == i) ? code : old_code[i];
+      // ---- column `warp` of U^T (row = feature = lane); zeros for rows past the batch
+      split_store(sg + 2 * A_BYTES, sg + 2 * A_BYTES + 1024, kelem_off(lane, warp), uz);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BARF(st));
+      // ---- du[z = lane] = sum_n coef_n T[code_n][z]
+      float du = 0.f;
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const int4 cd = *reinterpret_cast<const int4*>(cds + n4 * 4);
+        const float4 c4 = *reinterpret_cast<const float4*>(cfs + n4 * 4);
+        du = fmaf(c4.x, T_s[cd.x * TST + lane], du);
+        du = fmaf(c4.y, T_s[cd.y * TST + lane], du);
+        du = fmaf(c4.z, T_s[cd.z * TST + lane], du);
+        du = fmaf(c4.w, T_s[cd.w * TST + lane], du);
+      }
+      dus[lane] = du;
+      __syncwarp();
+      // ---- dc_k[c = lane] = sum_z W[z][c][k] du[z];  dW[z][c][k] += du[z] c_b[c]
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int z4 = 0; z4 < 8; ++z4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dus + z4 * 4);
+        const float4 w = w4[z4];
+        d0 = fmaf(w.x, d4.x, d0);
+        d1 = fmaf(w.y, d4.y, d1);
+        d2 = fmaf(w.z, d4.z, d2);
+        d3 = fmaf(w.w, d4.w, d3);
+        acc[4 * z4] = fmaf(d4.x, cb, acc[4 * z4]);
+        acc[4 * z4 + 1] = fmaf(d4.y, cb, acc[4 * z4 + 1]);
+        acc[4 * z4 + 2] = fmaf(d4.z, cb, acc[4 * z4 + 2]);
+        acc[4 * z4 + 3] = fmaf(d4.w, cb, acc[4 * z4 + 3]);
+      }
+      const float dck = (d0 + d1) + (d2 + d3);
+      if (p.KR == 1) {
+        if (valid) p.dc[b * IZ + lane] = dck;
+      } else {
+        // the KR warps of sample slot s meet at named barrier 1 + s (fixed summation order over k)
+        float* dcp = dcp_s + ((it & 1) * PW + warp) * IZ;
+        dcp[lane] = dck;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(p.KR * 32) : "memory");
+        if (k == 0 && valid) {
+          float t = 0.f;
+          for (int kk = 0; kk < p.KR; ++kk) t += dcp_s[((it & 1) * PW + s * p.KR + kk) * IZ + lane];
+          p.dc[b * IZ + lane] = t;
+        }
+      }
+      __syncwarp();
+    }
+    // ---- all MMAs retired: TMEM holds dT of this CTA
+    mbar_wait(BARD, 0);
+    tcgen05_fence_after();
+    float* part = p.part + (size_t)blockIdx.x * ((size_t)p.Kc * IZ + (size_t)IZ * IZ * p.KR);
+    if (warp < 4) {
+      for (int m = 0; m < MT; ++m) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * 32), rr);
+        tmem_ld_wait();
+        const int code = m * 128 + warp * 32 + lane;
+        if (code < p.Kc) {
+          float4* o = reinterpret_cast<float4*>(part + (size_t)code * IZ);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        }
+      }
+    }
+    // ---- dW: combine the warps that share k through the (now idle) operand stages
+    float* scr = reinterpret_cast<float*>(stages);
+    asm volatile("bar.sync 9, %0;" ::"r"(PW * 32) : "memory");
+#pragma unroll
+    for (int z = 0; z < IZ; ++z) scr[(warp * IZ + z) * IZ + lane] = acc[z];
+    asm volatile("bar.sync 9, %0;" ::"r"(PW * 32) : "memory");
+    float* pw = part + (size_t)p.Kc * IZ;
+    for (int i = warp * 32 + lane; i < IZ * IZ * p.KR; i += PW * 32) {
+      const int kk = i % p.KR, zc = i / p.KR;
+      float t = 0.f;
+      for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
+      pw[i] = t;
+    }
+  }
+#undef BARF
+#undef BARE
+#undef BARD
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == PW) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(q.tmem_cols) : "memory");
   }
 }
 
@@ -289,15 +583,22 @@ __global__ void __launch_bounds__(512) table_scatter_add_kernel(const int64_t* _
   float* mine = sm + (size_t)warp * cpc * zd;
   const int64_t per = ((n + NW - 1) / NW + 31) / 32 * 32;
   const int64_t beg = warp * per, end = min(n, beg + per);
-  for (int64_t i0 = beg; i0 < end; i0 += 32) {
-    const int64_t i = i0 + lane;
-    const int code = i < end ? (int)idx[i] : -1;
-    uint32_t m = __ballot_sync(FULL, code >= c0 && code < c0 + cpc);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const int cj = __shfl_sync(FULL, code, j) - c0;
-      for (int f = lane; f < zd; f += 32) mine[cj * zd + f] += __ldg(rows + (i0 + j) * zd + f);
+  for (int64_t i0 = beg; i0 < end; i0 += 32 * 8) {
+    int codes[8];                                    // eight independent index loads in flight per lane
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int64_t i = i0 + q * 32 + lane;
+      codes[q] = i < end ? (int)idx[i] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t m = __ballot_sync(FULL, codes[q] >= c0 && codes[q] < c0 + cpc);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int cj = __shfl_sync(FULL, codes[q], j) - c0;
+        for (int f = lane; f < zd; f += 32) mine[cj * zd + f] += __ldg(rows + (i0 + q * 32 + j) * zd + f);
+      }
     }
   }
   __syncthreads();
@@ -331,13 +632,54 @@ struct VqIdxBwdP {
 
 constexpr int VCH = 512;      // vectors per CTA pass == threads
 
+// per-vector inputs of one pass, fetched one pass ahead (their global-load latency hides behind phases 2 .. J)
+template <int DS>
+struct VqVec {
+  int code;
+  uint32_t src;
+  float cf, gl, x[DS];
+};
+
+template <int DS>
+__device__ __forceinline__ VqVec<DS> vq_vec_load(const VqIdxBwdP& p, int64_t v) {
+  VqVec<DS> r;
+  r.code = 0xFFFF;
+  r.src = 0xFFFFFFFFu;
+  r.cf = 0.f;
+  r.gl = 0.f;
+#pragma unroll
+  for (int d = 0; d < DS; ++d) r.x[d] = 0.f;
+  if (v < p.n) {
+    r.code = min(max((int)p.idx[v], 0), p.Kc - 1);
+    r.gl = p.gl ? __ldg(p.gl + v) : 0.f;
+#pragma unroll
+    for (int d = 0; d < DS; ++d) r.x[d] = __ldg(p.x + v * DS + d);
+    for (int sgi = 0; sgi < p.nseg; ++sgi) {
+      const IdxSeg& sg = p.seg[sgi];
+      if (v >= sg.row0 && v < sg.row0 + sg.rows) {
+        const uint32_t pl = (uint32_t)(v - sg.row0);
+        if (sg.kind == 1) {
+          r.src = pl | ((uint32_t)sgi << 30);
+          r.cf = 1.f;
+        } else {
+          r.src = ((pl / (uint32_t)sg.per_b) * (uint32_t)sg.KR + pl % (uint32_t)sg.KR) | ((uint32_t)sgi << 30);
+          r.cf = __ldg(sg.a + pl);
+        }
+      }
+    }
+  }
+  return r;
+}
+
 template <int DS>
 __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
   constexpr int JROW = IZ * DS;                      // floats of J per code
   constexpr int JST = JROW + 4;                      // padded stride: consecutive codes start 4 banks apart
+  constexpr int ES = 4;                              // padded code stride of the shared-memory codebook
   extern __shared__ __align__(16) unsigned char smraw[];
   float* J_s = reinterpret_cast<float*>(smraw);                                        // [Kc][JST] (if j_smem)
-  float* gdq_s = J_s + (p.j_smem ? (size_t)p.Kc * JST : 0);                              // [VCH][DS]  g_loss * dloss/dq
+  float* E_s = J_s + (p.j_smem ? (size_t)p.Kc * JST : 0);                                // [Kc][4]
+  float* gdq_s = E_s + (size_t)p.Kc * ES;                                                // [VCH][DS]  g_loss * dloss/dq
   float* coef_s = gdq_s + VCH * DS;                                                      // [VCH]      scale of the source row
   uint32_t* src_s = reinterpret_cast<uint32_t*>(coef_s + VCH);                           // [VCH]      source row | segment << 30
   int* hist_s = reinterpret_cast<int*>(src_s + VCH);                                     // [Kc]
@@ -364,61 +706,48 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
                    "l"(p.J + (size_t)kx * JROW), "r"((uint32_t)(JROW * 4)), "r"(bar_a)
                    : "memory");
   }
-  for (int i = tid; i < p.Kc; i += VCH) hist_s[i] = 0;
+  for (int i = tid; i < p.Kc; i += VCH) {
+    hist_s[i] = 0;
+#pragma unroll
+    for (int d = 0; d < ES; ++d) E_s[i * ES + d] = d < DS ? __ldg(p.E + i * DS + d) : 0.f;
+  }
   float accE[2][DS];                                 // thread t owns the codes t and t + VCH (Kc <= 2 * VCH)
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int d = 0; d < DS; ++d) accE[a][d] = 0.f;
   bool j_ready = !p.j_smem;
-  __syncthreads();
   const int64_t nchunk = (p.n + VCH - 1) / VCH;
+  VqVec<DS> cur = vq_vec_load<DS>(p, (int64_t)blockIdx.x * VCH + tid);
+  __syncthreads();
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
     // ---- phase 1: thread == vector: loss gradients, source row of the upscaled-side gradient, histogram
     {
-      const int64_t v = ch * VCH + tid;
-      const bool ok = v < p.n;
-      int code = 0xFFFF;
-      uint32_t src = 0xFFFFFFFFu;
-      float cf = 0.f;
       float g[DS];
 #pragma unroll
       for (int d = 0; d < DS; ++d) g[d] = 0.f;
-      if (ok) {
-        code = min(max((int)p.idx[v], 0), p.Kc - 1);
-        const float gl = p.gl ? __ldg(p.gl + v) : 0.f;
+      if (cur.code != 0xFFFF) {
         float df[DS];
         float ssq = 0.f;
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
-          df[d] = __ldg(p.E + code * DS + d) - __ldg(p.x + v * DS + d);
+          df[d] = E_s[cur.code * ES + d] - cur.x[d];
           const float t = df[d] + 1e-5f;
           ssq = fmaf(t, t, ssq);
         }
         const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
 #pragma unroll
-        for (int d = 0; d < DS; ++d) g[d] = gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
-        for (int sgi = 0; sgi < p.nseg; ++sgi) {
-          const IdxSeg& sg = p.seg[sgi];
-          if (v >= sg.row0 && v < sg.row0 + sg.rows) {
-            const uint32_t pl = (uint32_t)(v - sg.row0);
-            if (sg.kind == 1) {
-              src = pl | ((uint32_t)sgi << 30);
-              cf = 1.f;
-            } else {
-              src = ((pl / (uint32_t)sg.per_b) * (uint32_t)sg.KR + pl % (uint32_t)sg.KR) | ((uint32_t)sgi << 30);
-              cf = __ldg(sg.a + pl);
-            }
-          }
-        }
-        atomicAdd(&hist_s[code], 1);
+        for (int d = 0; d < DS; ++d) g[d] = cur.gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
+        atomicAdd(&hist_s[cur.code], 1);
       }
 #pragma unroll
       for (int d = 0; d < DS; ++d) gdq_s[tid * DS + d] = g[d];
-      coef_s[tid] = cf;
-      src_s[tid] = src;
-      code_s[tid] = (uint16_t)code;
+      coef_s[tid] = cur.cf;
+      src_s[tid] = cur.src;
+      code_s[tid] = (uint16_t)cur.code;
     }
+    // next pass's inputs: in flight until the next phase 1
+    cur = vq_vec_load<DS>(p, (ch + gridDim.x) * VCH + tid);
     __syncthreads();
     // ---- phase 2: exclusive scan of the histogram (Kc <= 2 * VCH bins, two per thread)
     {
@@ -444,6 +773,59 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       const int code = code_s[tid];
       if (code != 0xFFFF) perm_s[atomicAdd(&cur_s[code], 1)] = (uint16_t)tid;
     }
+    // ---- phase J (needs phase 1 only): a quad of lanes per vector: dz = coef * J[code]^T v - beta * g_loss * dloss/dq.
+    // All source rows of the four passes are requested first, then consumed.
+    const int ql = tid & 3, qid = tid >> 2;
+    float4 va[4], vb[4];
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const uint32_t src = src_s[pass * (VCH / 4) + qid];
+      va[pass] = vb[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src != 0xFFFFFFFFu) {
+        const IdxSeg& sg = p.seg[src >> 30];
+        const float4* row = reinterpret_cast<const float4*>((sg.kind == 1 ? sg.a : sg.b) + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8);
+        va[pass] = __ldg(row);
+        vb[pass] = __ldg(row + 1);
+      }
+    }
+    if (!j_ready) {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+      j_ready = true;
+    }
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int i = pass * (VCH / 4) + qid;
+      const int64_t v = ch * VCH + i;
+      const float vv[8] = {va[pass].x, va[pass].y, va[pass].z, va[pass].w, vb[pass].x, vb[pass].y, vb[pass].z, vb[pass].w};
+      const int code = min((int)code_s[i], p.Kc - 1);
+      const float* jr = p.j_smem ? (J_s + (size_t)code * JST + ql * 8 * DS) : (p.J + (size_t)code * JROW + ql * 8 * DS);
+      float gz[DS];
+#pragma unroll
+      for (int d = 0; d < DS; ++d) gz[d] = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 2 * DS; ++q4) {
+        const float4 t = *reinterpret_cast<const float4*>(jr + q4 * 4);
+        const float jv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int f = q4 * 4 + e;                  // flat index (feature t, component d) = t * DS + d
+          gz[f % DS] = fmaf(vv[f / DS], jv[e], gz[f % DS]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < DS; ++d) {
+        gz[d] += __shfl_xor_sync(FULL, gz[d], 1);
+        gz[d] += __shfl_xor_sync(FULL, gz[d], 2);
+      }
+      if (v < p.n && ql < DS) {
+        float mine = gz[0];
+#pragma unroll
+        for (int d = 1; d < DS; ++d) mine = (ql == d) ? gz[d] : mine;
+        p.dx[v * DS + ql] = fmaf(coef_s[i], mine, -p.beta * gdq_s[i * DS + ql]);
+      }
+    }
     __syncthreads();
     // ---- phase 4: thread == code: sequential sum over the code's vectors of this pass (no atomics)
 #pragma unroll
@@ -456,53 +838,6 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
 #pragma unroll
           for (int d = 0; d < DS; ++d) accE[a][d] += gdq_s[i * DS + d];
         }
-      }
-    }
-    // ---- phase J: a quad of lanes per vector: dz = coef * J[code]^T v - beta * g_loss * dloss/dq
-    if (!j_ready) {
-      uint32_t done = 0;
-      while (!done)
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
-      j_ready = true;
-    }
-    const int ql = tid & 3, qid = tid >> 2;
-#pragma unroll 1
-    for (int pass = 0; pass < 4; ++pass) {
-      const int i = pass * (VCH / 4) + qid;
-      const int64_t v = ch * VCH + i;
-      const uint32_t src = src_s[i];
-      float gz[DS];
-#pragma unroll
-      for (int d = 0; d < DS; ++d) gz[d] = 0.f;
-      if (src != 0xFFFFFFFFu) {
-        const IdxSeg& sg = p.seg[src >> 30];
-        const float* row = (sg.kind == 1 ? sg.a : sg.b) + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(row)), v1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const int code = code_s[i];
-        const float* jr = p.j_smem ? (J_s + (size_t)code * JST + ql * 8 * DS) : (p.J + (size_t)code * JROW + ql * 8 * DS);
-        float jv[8 * DS];
-#pragma unroll
-        for (int q4 = 0; q4 < 2 * DS; ++q4) {
-          const float4 t = *reinterpret_cast<const float4*>(jr + q4 * 4);
-          jv[q4 * 4] = t.x; jv[q4 * 4 + 1] = t.y; jv[q4 * 4 + 2] = t.z; jv[q4 * 4 + 3] = t.w;
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-#pragma unroll
-          for (int d = 0; d < DS; ++d) gz[d] = fmaf(vv[t], jv[t * DS + d], gz[d]);
-      }
-      // (all four lanes of a quad take the same branch above; the shuffles below are executed by the whole warp)
-#pragma unroll
-      for (int d = 0; d < DS; ++d) {
-        gz[d] += __shfl_xor_sync(FULL, gz[d], 1);
-        gz[d] += __shfl_xor_sync(FULL, gz[d], 2);
-      }
-      if (v < p.n && ql < DS) {
-        float mine = gz[0];
-#pragma unroll
-        for (int d = 1; d < DS; ++d) mine = (ql == d) ? gz[d] : mine;
-        p.dx[v * DS + ql] = fmaf(coef_s[i], mine, -p.beta * gdq_s[i * DS + ql]);
       }
     }
     __syncthreads();
@@ -522,6 +857,7 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
 template <int DS>
 size_t vq_idx_bwd_smem(int Kc, bool j_smem) {
   size_t s = j_smem ? (size_t)Kc * (IZ * DS + 4) * 4 : 0;
+  s += (size_t)Kc * 4 * 4;                           // codebook
   s += (size_t)VCH * DS * 4 + VCH * 4 + VCH * 4;     // gdq, coef, src
   s += ((size_t)3 * Kc + 1 + 32) * 4;                // hist, start, cur, wsum
   s += VCH * 2 * 2;                                  // code, perm
@@ -562,9 +898,12 @@ VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T,
   if (int rc = idx_path_check("infonce_idx_fwd", N, KR, zd, cd, Kc)) return rc;
   if (B == 0) return VQ_OK;
   NceFwdP p{c, W, T, idx_pos, idx_neg, B, N, KR, Kc, nce_spi(KR), u, pos, neg, lse, nll, correct};
-  const int warps = KR * p.SPI;
-  const size_t smem = ((size_t)Kc * TST + (size_t)warps * IZ) * 4;
-  const int grid = vqcpc_infonce_idx_parts(B, KR);
+  const int warps = 16;
+  const size_t smem = ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * 2 * IZ) * 4;
+  VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_fwd: %zu bytes of shared memory needed", smem);
+  const int64_t pairs = ((int64_t)B * KR + 1) / 2;
+  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)vq_sm_count() * per_sm, vq_cdiv(pairs, warps)));
   VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nce_idx_fwd_kernel<<<grid, warps * 32, smem, vq_stream(stream)>>>(p);
   VQ_CUDA_LAUNCH_CHECK("nce_idx_fwd_kernel");
@@ -582,15 +921,34 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   p.g_dev = g_dev; p.scale = scale; p.B = B; p.N = N; p.KR = KR; p.Kc = Kc; p.SPI = nce_spi(KR);
   p.dc = d_c; p.coef_pos = coef_pos; p.coef_neg = coef_neg; p.part = part;
   const int warps = KR * p.SPI;
-  p.scratch_floats = std::max<size_t>((size_t)Kc * TST, (size_t)warps * IZ * IZ);
-  p.scratch_floats = (p.scratch_floats + 3) & ~(size_t)3;
-  const size_t smem = (p.scratch_floats + (size_t)Kc * IZ + (size_t)warps * (3 * IZ + 32)) * 4;
-  VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_bwd: %zu bytes of shared memory needed", smem);
   const int grid = vqcpc_infonce_idx_parts(B, KR);
   cudaStream_t st = vq_stream(stream);
-  VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nce_idx_bwd_kernel<<<grid, warps * 32, smem, st>>>(p);
-  VQ_CUDA_LAUNCH_CHECK("nce_idx_bwd_kernel");
+  // production kernel: dT on the tensor cores (tcgen05, TMEM accumulators); VQCPC_NCE_BWD_ALGO=1 forces the CUDA-core
+  // owner-computes kernel (also the fallback when the operand stages do not fit next to the table)
+  static const int force_simt = getenv("VQCPC_NCE_BWD_ALGO") ? atoi(getenv("VQCPC_NCE_BWD_ALGO")) : 0;
+  NceBwdTcP q{};
+  q.kpad = (Kc + 127) / 128 * 128;
+  q.PW = warps;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < q.kpad / 128 * 32) q.tmem_cols *= 2;
+  q.stage_region = (uint32_t)std::max<size_t>((size_t)NST * (2 * (size_t)q.kpad * 32 + 2048), (size_t)warps * IZ * IZ * 4);
+  q.stage_region = (q.stage_region + 1023u) & ~1023u;
+  const size_t tc_smem = 1024 + (size_t)q.stage_region +
+                         ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * (32 + IZ + 2 * IZ)) * 4 + (2 * NST + 1) * 8 + 16;
+  if (force_simt != 1 && tc_smem <= 227 * 1024 && q.tmem_cols <= 512) {
+    q.b = p;
+    VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    nce_idx_bwd_tc_kernel<<<grid, (warps + 1) * 32, tc_smem, st>>>(q);
+    VQ_CUDA_LAUNCH_CHECK("nce_idx_bwd_tc_kernel");
+  } else {
+    p.scratch_floats = std::max<size_t>((size_t)Kc * TST, (size_t)warps * IZ * IZ);
+    p.scratch_floats = (p.scratch_floats + 3) & ~(size_t)3;
+    const size_t smem = (p.scratch_floats + (size_t)Kc * IZ + (size_t)warps * (3 * IZ + 32)) * 4;
+    VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_bwd: %zu bytes of shared memory needed", smem);
+    VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nce_idx_bwd_kernel<<<grid, warps * 32, smem, st>>>(p);
+    VQ_CUDA_LAUNCH_CHECK("nce_idx_bwd_kernel");
+  }
   const int na = Kc * IZ, nb = IZ * IZ * KR;
   const int ncol4 = (na + nb) / 4;
   reduce_partials_kernel<<<(ncol4 + 31) / 32, 256, 0, st>>>(part, grid, (size_t)na + nb, d_T, na, d_W, nb);
