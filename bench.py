@@ -222,8 +222,7 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
     for d in sets:
         d.update(y_left=torch.empty(n_left, zd, device=dev), dy_left=torch.randn(n_left, zd, device=dev, generator=g) * 1e-3,
                  coef_pos=torch.empty(B, KR, device=dev), coef_neg=torch.empty(B, NNEG, KR, device=dev))
-    parts = _native.load().vqcpc_infonce_idx_parts(B, KR)
-    part = torch.empty(parts, Kc * zd + zd * cd * KR, device=dev)
+    part = torch.empty(_native.load().vqcpc_infonce_idx_scratch(B, KR, Kc), device=dev)
     seg_row0 = (ctypes.c_int64 * 3)(0, n_neg, n_neg + n_left)
     seg_rows = (ctypes.c_int64 * 3)(n_neg, n_left, B * KR)
     seg_kind = (ctypes.c_int * 3)(2, 1, 2)
@@ -244,14 +243,11 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
                      p_(d['neg']), p_(d['lse']), None, 1.0 / B, B, NNEG, KR, zd, cd, Kc, p_(d['dc']), p_(d['coef_pos']),
                      p_(d['coef_neg']), p_(part), p_(d['dW']), p_(d['dT']), st())
 
-    def scat_idx(d):
-        _native.call('vqcpc_table_scatter_add', p_(d['idx'][n_neg:n_neg + n_left]), n_left, p_(d['dy_left']), zd, Kc, p_(d['dT']), st())
-
     def vq_bwd_idx(d):
         pa = (ctypes.c_void_p * 3)(d['coef_neg'].data_ptr(), d['dy_left'].data_ptr(), d['coef_pos'].data_ptr())
         pb = (ctypes.c_void_p * 3)(d['u'].data_ptr(), 0, d['u'].data_ptr())
         _native.call('vqcpc_vq_idx_bwd', p_(d['z']), P, D, p_(E), p_(J), Kc, zd, p_(d['idx']), 0.25, 1, p_(d['gl']), 3, seg_row0,
-                     seg_rows, seg_kind, pa, pb, seg_per_b, KR, p_(d['dz']), p_(d['dE']), st())
+                     seg_rows, seg_kind, pa, pb, seg_per_b, KR, p_(d['dz']), p_(d['dE']), p_(d['dT']), st())
 
     def fwd(d):
         vq_fwd_idx(d)
@@ -259,7 +255,6 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
 
     def bwd(d):
         nce_bwd_idx(d)
-        scat_idx(d)
         vq_bwd_idx(d)
 
     def fwd_pv(d):
@@ -312,7 +307,7 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
     us_b = timeit(bwd)
     us_f_launch = timeit(fwd, graph=False)
     per_kernel = dict(vq_fused_fwd_rows_us=timeit(vq_fwd_idx), infonce_idx_fwd_us=timeit(nce_fwd_idx),
-                      infonce_idx_bwd_us=timeit(nce_bwd_idx), table_scatter_add_us=timeit(scat_idx), vq_idx_bwd_us=timeit(vq_bwd_idx))
+                      infonce_idx_bwd_us=timeit(nce_bwd_idx), vq_idx_bwd_us=timeit(vq_bwd_idx))
     us_f_pv, us_b_pv = timeit(fwd_pv), timeit(bwd_pv)
     per_kernel_pv = dict(vq_fused_fwd_us=timeit(vq_fwd), infonce_fwd_us=timeit(nce_fwd), infonce_bwd_us=timeit(nce_bwd),
                          vq_fused_bwd_us=timeit(vq_bwd))
@@ -336,7 +331,7 @@ def bench_quantizer_infonce(B, iters=60, nsets=5):
             break
     return dict(bound='hbm', unit='GB/s', peak=pk['hbm'], traffic=traffic, peak_source=pk['src'].replace('sustained bf16', 'hbm copy'),
                 kernels='index-gather form: vq_tc_fwd_kernel (tcgen05 score + exact verify; y for the left blocks only) + '
-                        'nce_idx_fwd_kernel (forward); nce_idx_bwd_kernel + reduce_partials_kernel + table_scatter_add_kernel + '
+                        'nce_idx_fwd_kernel (forward); nce_idx_bwd_tc_kernel (tcgen05 dT = C^T U) + reduce_partials_kernel + '
                         'vq_idx_bwd_kernel (backward)',
                 timing='CUDA-graph replay of the launch sequence over %d rotating buffer sets (> L2); us_fwd_eager = same '
                        'launches issued one by one from Python' % nsets, us_fwd_eager=us_f_launch,

@@ -208,11 +208,15 @@ int vqcpc_vq_fused_fwd_rows(const float* x, int64_t n, int D, const float* E, co
 int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
                           int B, int N, int KR, int zd, int cd, int Kc, float* u, float* pos, float* neg, float* lse,
                           float* nll, int* correct, void* stream);
-/* rows of the scratch `part` of vqcpc_infonce_idx_bwd: part holds parts * (Kc * zd + zd * cd * KR) floats. */
+/* per-CTA partial tables vqcpc_infonce_idx_bwd writes, and the floats of scratch it needs in total
+ * (parts * (Kc * zd + zd * cd * KR) for the partial d_T | d_W tables + B * KR * cd per-row d_c contributions). */
 int vqcpc_infonce_idx_parts(int B, int KR);
+int64_t vqcpc_infonce_idx_scratch(int B, int KR, int Kc);
 /* gradient of sum(nll) scaled by scale * g_dev[0] (g_dev device scalar or NULL): d_c (B, cd) overwritten; coef_pos (B, KR)
  * and coef_neg (B, N, KR) = d loss / d score of every candidate, overwritten (vqcpc_vq_idx_bwd turns them into d z);
- * d_W (zd, cd, KR) and d_T (Kc, zd) ACCUMULATED (per-CTA partial tables in `part`, summed in a fixed order). */
+ * d_W (zd, cd, KR) and d_T (Kc, zd) ACCUMULATED (per-CTA partial tables in the scratch `part`, summed in a fixed order by a
+ * second kernel).  d_T = C^T U runs on the tensor cores: tcgen05.mma with the accumulators in TMEM (bf16 hi/lo operand
+ * split, fp32 accumulation); VQCPC_NCE_BWD_ALGO=1 selects the CUDA-core owner-computes kernel instead. */
 int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
                           const float* u, const float* pos, const float* neg, const float* lse, const float* g_dev,
                           float scale, int B, int N, int KR, int zd, int cd, int Kc, float* d_c, float* coef_pos,
@@ -225,12 +229,13 @@ int vqcpc_table_scatter_add(const int64_t* idx, int64_t n, const float* rows, in
  * vectors get none) is  kind 1: the dense row seg_a[s][(p - row0) * zd ..] (coef = 1)
  *                       kind 2: coef = seg_a[s][p - row0],  v = seg_b[s][((p - row0) / per_b * KR + (p - row0) % KR) * zd ..]
  * (per_b = N * KR for the negatives laid out (B, N, KR), KR for the right blocks; seg_b = the u of vqcpc_infonce_idx_fwd).
- * d_E (Kc, D) ACCUMULATED (may be NULL).  J (Kc, zd, D), g_loss (n) or NULL.  seg_* are HOST arrays. */
+ * d_E (Kc, D) ACCUMULATED (may be NULL); d_T (Kc, zd) ACCUMULATED with the kind-1 rows (d_T[idx_p] += row: the gradient
+ * of the table gather of the left blocks) or NULL.  J (Kc, zd, D), g_loss (n) or NULL.  seg_* are HOST arrays. */
 int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,
                      float beta, int squared, const float* g_loss, int nseg, const int64_t* seg_row0 /*host*/,
                      const int64_t* seg_rows /*host*/, const int* seg_kind /*host*/, const float* const* seg_a /*host*/,
                      const float* const* seg_b /*host*/, const int* seg_per_b /*host*/, int KR, float* d_x, float* d_E,
-                     void* stream);
+                     float* d_T, void* stream);
 
 /* ---- GRU (torch.nn.GRU semantics; CModule vqcpc_helper.py:54-76, LstmDownscaler lstm_downscaler.py:31-48) ---------------
  * The products GI = X W_ih^T + b_ih (all steps at once) and GH = h_{t-1} W_hh^T + b_hh (per step) are vqcpc_gemm_* calls;

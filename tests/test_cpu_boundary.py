@@ -16,7 +16,7 @@ def _header_functions():
     src = open(HEADER).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     out = {}
-    for m in re.finditer(r'\b(?:int|const char\*)\s+(vqcpc_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'\b(?:int64_t|int|const char\*)\s+(vqcpc_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ('', 'void') else len([a for a in args.split(',') if a.strip()])
         out[m.group(1)] = n

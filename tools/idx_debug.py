@@ -51,8 +51,7 @@ dW = torch.zeros_like(W)
 dT = torch.zeros_like(T)
 cp = torch.empty(B, KR, device=dev)
 cn = torch.empty(B, N, KR, device=dev)
-parts = _native.load().vqcpc_infonce_idx_parts(B, KR)
-part = torch.empty(parts, Kc * zd + zd * cd * KR, device=dev)
+part = torch.empty(_native.load().vqcpc_infonce_idx_scratch(B, KR, Kc), device=dev)
 step('infonce_idx_bwd', lambda: _native.call('vqcpc_infonce_idx_bwd', p_(c), p_(W), p_(T), p_(idx[n_neg + n_left:]), p_(idx), p_(u), p_(pos), p_(neg),
                                               p_(lse), None, 1.0 / B, B, N, KR, zd, cd, Kc, p_(dc), p_(cp), p_(cn), p_(part), p_(dW), p_(dT), st()))
 # reference for dT / dW / dc in fp64
@@ -80,5 +79,5 @@ per_b = (ctypes.c_int * 3)(N * KR, 1, KR)
 pa = (ctypes.c_void_p * 3)(cn.data_ptr(), dyl.data_ptr(), cp.data_ptr())
 pb = (ctypes.c_void_p * 3)(u.data_ptr(), 0, u.data_ptr())
 step('vq_idx_bwd', lambda: _native.call('vqcpc_vq_idx_bwd', p_(z), P, D, p_(E), p_(J), Kc, zd, p_(idx), 0.25, 1, p_(gl), 3, row0, rows, kind, pa, pb,
-                                         per_b, KR, p_(dz), p_(dE), st()))
+                                         per_b, KR, p_(dz), p_(dE), p_(dT), st()))
 print('all ok')

@@ -53,7 +53,7 @@ SIGNATURES = {
     'vqcpc_infonce_idx_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_idx_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_table_scatter_add': [_P, _L, _P, _I, _I, _P, _P],
-    'vqcpc_vq_idx_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    'vqcpc_vq_idx_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     'vqcpc_infonce_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_set_algo': [_I],
     'vqcpc_infonce_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -63,7 +63,8 @@ SIGNATURES = {
     'vqcpc_clip_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _I, _P],
 }
 _SPECIAL = {'vqcpc_last_error': (_c.c_char_p, []), 'vqcpc_abi_version': (_I, []),
-            'vqcpc_idxpath_supported': (_I, [_I, _I, _I, _I, _I, _I]), 'vqcpc_infonce_idx_parts': (_I, [_I, _I])}
+            'vqcpc_idxpath_supported': (_I, [_I, _I, _I, _I, _I, _I]), 'vqcpc_infonce_idx_parts': (_I, [_I, _I]),
+            'vqcpc_infonce_idx_scratch': (_L, [_I, _I, _I])}
 
 _lib = None
 launch_count = 0   # number of kernel-launching C-ABI calls made through this module (bench.py reports it)

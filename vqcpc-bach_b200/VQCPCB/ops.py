@@ -791,8 +791,7 @@ class VQIndexFn(torch.autograd.Function):
             if gy.data_ptr() % 16:
                 gy = gy.clone()
             keep.append(gy)
-            _native.call('vqcpc_table_scatter_add', _p(idx[y_row0:y_row0 + y_rows]), y_rows, _p(gy), zd, Kc, _p(dT), _stream())
-            segs.append((y_row0, y_rows, gy, None, 1, 1))
+            segs.append((y_row0, y_rows, gy, None, 1, 1))      # (the kernel also scatters these rows into dT)
         KR = max([s[5] for s in segs if s[3] is not None], default=1)
         ns = len(segs)
         row0 = (ctypes.c_int64 * max(ns, 1))(*[s[0] for s in segs])
@@ -803,7 +802,7 @@ class VQIndexFn(torch.autograd.Function):
         per_b = (ctypes.c_int * max(ns, 1))(*[s[4] for s in segs])
         dx = torch.empty_like(z2)
         _native.call('vqcpc_vq_idx_bwd', _p(z2), n, D, _p(Ed), _p(J), Kc, zd, _p(idx), float(beta), int(squared), _p(gl), ns, row0,
-                     rows, kind, pa, pb, per_b, int(KR), _p(dx), _p(dE), _stream())
+                     rows, kind, pa, pb, per_b, int(KR), _p(dx), _p(dE), _p(dT), _stream())
         return dx.view(shp), dE, dT, None, None, None, None, None, None, None
 
 
@@ -849,8 +848,7 @@ class InfoNCEIdxFn(torch.autograd.Function):
         dT = torch.zeros_like(Td)
         coef_pos = torch.empty(B, KR, dtype=torch.float32, device=dev)
         coef_neg = torch.empty(B, N, KR, dtype=torch.float32, device=dev)
-        parts = _native.load().vqcpc_infonce_idx_parts(B, KR)
-        part = torch.empty(parts, Kc * zd + zd * cd * KR, dtype=torch.float32, device=dev)
+        part = torch.empty(_native.load().vqcpc_infonce_idx_scratch(B, KR, Kc), dtype=torch.float32, device=dev)
         g = _f32c(g_total).reshape(1)
         _native.call('vqcpc_infonce_idx_bwd', _p(c), _p(W), _p(Td), _p(idx_pos), _p(idx_neg), _p(u), _p(pos), _p(neg), _p(lse), _p(g),
                      1.0, B, N, KR, zd, cd, Kc, _p(dc), _p(coef_pos), _p(coef_neg), _p(part), _p(dW), _p(dT), _stream())

@@ -33,6 +33,28 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return smem_u32(p); }
 
+// asynchronous staging of the (Kc, 32) table into padded rows: one 128-byte bulk copy per row, completion on `bar`
+// (initialised by the caller with count 1; thread 0 posts the expected byte count).  Needs a 16-byte aligned T.
+__device__ __forceinline__ void stage_table_bulk(float* T_s, const float* __restrict__ T, int Kc, uint32_t bar) {
+  if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)Kc * IZ * 4);
+  __syncthreads();
+  for (int r = threadIdx.x; r < Kc; r += blockDim.x)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(T_s + r * TST)),
+                 "l"(T + (size_t)r * IZ), "r"(128u), "r"(bar)
+                 : "memory");
+}
+
+// W (z, c, k) -> W_s[k][row][col]: row = z, col = c (ZMAJOR: u = W_k c) or row = c, col = z (dc = W_k^T du); padded rows.
+// One (z, c) pair per thread step: KR consecutive floats in, KR scattered stores out.
+template <bool ZMAJOR>
+__device__ __forceinline__ void stage_w(float* W_s, const float* __restrict__ W, int KR) {
+  for (int zc = threadIdx.x; zc < IZ * IZ; zc += blockDim.x) {
+    const int z = zc >> 5, c = zc & 31;
+    const int row = ZMAJOR ? z : c, col = ZMAJOR ? c : z;
+    for (int k = 0; k < KR; ++k) W_s[(k * IZ + row) * TST + col] = __ldg(W + (size_t)zc * KR + k);
+  }
+}
+
 // stage the (Kc, 32) table with padded rows
 __device__ __forceinline__ void stage_table(float* T_s, const float* __restrict__ T, int Kc) {
   for (int i = threadIdx.x; i < Kc * 8; i += blockDim.x) {
@@ -54,61 +76,91 @@ struct NceFwdP {
 
 // 16 warps per CTA, two CTAs per SM (<= 64 registers, ~112 KB of shared memory: the padded table and W transposed to
 // [k][z][c]).  A warp handles TWO (b, k) rows per step: lanes = features while u = W_k c is formed, then lane (j, n) scores
-// candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.  The index
-// gathers are issued before the u phase (their latency hides behind it).
+// candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.  The table
+// arrives by bulk copies that overlap the W staging; the per-row global reads (candidate code, one c element per lane) are
+// fetched one step ahead.
 __global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
   extern __shared__ __align__(16) float sm[];
   float* T_s = sm;                                   // [Kc][TST]
   float* W_s = T_s + (size_t)p.Kc * TST;             // [KR][32 z][TST]  W_s[k][z][c] = W[z][c][k]
-  float* u_s = W_s + (size_t)p.KR * IZ * TST;        // [warps][2][32]
+  float* u_s = W_s + (size_t)p.KR * IZ * TST;        // [warps][2][32]: the c vectors of the pair, then their u vectors
+  uint64_t* bar = reinterpret_cast<uint64_t*>(u_s + (blockDim.x >> 5) * 2 * IZ);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
-  stage_table(T_s, p.T, p.Kc);
-  for (int i = threadIdx.x; i < IZ * IZ * p.KR; i += blockDim.x) {
-    const int k = i % p.KR, zc = i / p.KR;           // i = (z * 32 + c) * KR + k
-    W_s[(k * IZ + (zc >> 5)) * TST + (zc & 31)] = __ldg(p.W + i);
+  const uint32_t bar_a = smem_u32(bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  stage_table_bulk(T_s, p.T, p.Kc, bar_a);
+  stage_w<true>(W_s, p.W, p.KR);
+  __syncthreads();
   float* us = u_s + warp * 2 * IZ;
+  float* cs = us;
   const int n = lane & 15, j = lane >> 4;            // candidate n (0 = positive) of row j of the pair
   const bool act = n <= p.N;
-  const int64_t rtot = (int64_t)p.B * p.KR;
-  for (int64_t pi = (int64_t)blockIdx.x * NW + warp; 2 * pi < rtot; pi += (int64_t)gridDim.x * NW) {
-    // ---- gather of this lane's candidate code (row 2 pi + j)
-    const int64_t rj = 2 * pi + j;
-    const bool vj = rj < rtot;
-    const int64_t bj = rj / p.KR;
-    const int kj = (int)(rj - bj * p.KR);
-    int code = 0;
-    if (act && vj) code = (int)(n == 0 ? p.idx_pos[rj] : p.idx_neg[(bj * p.N + (n - 1)) * p.KR + kj]);
+  const int rtot = p.B * p.KR, KR = p.KR, N = p.N;
+  const int step = gridDim.x * NW;
+  // per-step global reads: this lane's candidate code (row 2 pi + j) and element `lane` of the c vector of both rows
+  auto fetch = [&](int pi, int& code, float& c0, float& c1) {
+    code = 0;
+    c0 = c1 = 0.f;
+    const int r0 = 2 * pi;
+    if (r0 >= rtot) return;
+    const int b0 = r0 / KR, k0 = r0 - b0 * KR;
+    const bool wrap = k0 + 1 == KR;
+    const int b1 = wrap ? b0 + 1 : b0, k1 = wrap ? 0 : k0 + 1;
+    const bool v1 = r0 + 1 < rtot;
+    c0 = __ldg(p.c + b0 * IZ + lane);
+    if (v1) c1 = __ldg(p.c + b1 * IZ + lane);
+    const int rj = r0 + j, bj = j ? b1 : b0, kj = j ? k1 : k0;
+    if (act && (j == 0 || v1)) code = (int)(n == 0 ? p.idx_pos[rj] : p.idx_neg[(bj * N + (n - 1)) * KR + kj]);
+  };
+  int pi = blockIdx.x * NW + warp;
+  int code_n;
+  float c0_n, c1_n;
+  fetch(pi, code_n, c0_n, c1_n);
+  bool t_ready = false;
+  for (; 2 * pi < rtot; pi += step) {
+    const int code_raw = code_n;
+    cs[lane] = c0_n;
+    cs[IZ + lane] = c1_n;
+    fetch(pi + step, code_n, c0_n, c1_n);            // next step's reads are in flight during this step
+    __syncwarp();
+    const int r0 = 2 * pi;
+    const int b0 = r0 / KR, k0 = r0 - b0 * KR;
+    const int k1 = (k0 + 1 == KR) ? 0 : k0 + 1;
+    const bool v1 = r0 + 1 < rtot;
     // ---- u of both rows, lanes = features
+    float uu[2];
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
-      const int64_t r = 2 * pi + jj;
-      float u = 0.f;
-      if (r < rtot) {
-        const int64_t b = r / p.KR;
-        const int k = (int)(r - b * p.KR);
-        const float4* c4 = reinterpret_cast<const float4*>(p.c + b * IZ);
-        const float4* w4 = reinterpret_cast<const float4*>(W_s + (k * IZ + lane) * TST);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float4* c4 = reinterpret_cast<const float4*>(cs + jj * IZ);
+      const float4* w4 = reinterpret_cast<const float4*>(W_s + ((jj ? k1 : k0) * IZ + lane) * TST);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = __ldg(c4 + q);            // same address on every lane: one broadcast transaction
-          const float4 w = w4[q];
-          a0 = fmaf(w.x, t.x, a0);
-          a1 = fmaf(w.y, t.y, a1);
-          a2 = fmaf(w.z, t.z, a2);
-          a3 = fmaf(w.w, t.w, a3);
-        }
-        u = (a0 + a1) + (a2 + a3);
-        p.u[r * IZ + lane] = u;
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = c4[q];
+        const float4 w = w4[q];
+        a0 = fmaf(w.x, t.x, a0);
+        a1 = fmaf(w.y, t.y, a1);
+        a2 = fmaf(w.z, t.z, a2);
+        a3 = fmaf(w.w, t.w, a3);
       }
-      us[jj * IZ + lane] = u;
+      uu[jj] = (a0 + a1) + (a2 + a3);
+      if (jj == 0 || v1) p.u[(r0 + jj) * IZ + lane] = uu[jj];
     }
+    __syncwarp();                                    // the u vectors replace the c vectors in the warp's buffer
+    us[lane] = uu[0];
+    us[IZ + lane] = uu[1];
     __syncwarp();
+    if (!t_ready) {
+      mbar_wait(bar_a, 0);
+      t_ready = true;
+    }
     // ---- scores: every lane runs the SAME sequence of FMAs on its row, so candidates that drew the same code get
     // bit-identical scores (a negative equal to the positive is never "correct", like the reference)
-    code = min(max(code, 0), p.Kc - 1);
+    const int code = min(max(code_raw, 0), p.Kc - 1);
     const float4* t4 = reinterpret_cast<const float4*>(T_s + code * TST);
     const float4* u4 = reinterpret_cast<const float4*>(us + j * IZ);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -132,18 +184,20 @@ __global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
     const float lse = m + logf(e);
-    if (vj) {
+    const int rj = r0 + j;
+    if (j == 0 || v1) {
       if (n == 0) {
         p.pos[rj] = sc;
         p.lse[rj] = lse;
         p.nll[rj] = lse - sc;
         p.correct[rj] = sc > nm ? 1 : 0;
       } else if (act) {
-        p.neg[rj * p.N + n - 1] = sc;
+        p.neg[rj * N + n - 1] = sc;
       }
     }
     __syncwarp();
   }
+  if (!t_ready) mbar_wait(bar_a, 0);                 // never leave with bulk copies in flight
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -156,6 +210,7 @@ struct NceBwdP {
   float scale;
   int B, N, KR, Kc, SPI;
   float *dc, *coef_pos, *coef_neg, *part;            // part: [gridDim][Kc * 32 + 32 * 32 * KR]
+  float* dcp;                                        // [B * KR][32] per-row W_k^T du (tensor-core kernel; summed over k later)
   size_t scratch_floats;                             // size of the T_s / scratch region
 };
 
@@ -317,13 +372,13 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
   float* coef_s = W_s + (size_t)p.KR * IZ * TST;                                    // [PW][16]
   int* code_s = reinterpret_cast<int*>(coef_s + PW * 16);                           // [PW][16]
   float* du_s = reinterpret_cast<float*>(code_s + PW * 16);                         // [PW][32]
-  float* dcp_s = du_s + PW * IZ;                                                    // [2][PW][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dcp_s + 2 * PW * IZ);                // full[NST], empty[NST], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(du_s + PW * IZ);                     // full[NST], empty[NST], done, table
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
   const uint32_t bar0 = smem_u32(bars);
 #define BARF(i) (bar0 + 8u * (uint32_t)(i))
 #define BARE(i) (bar0 + 8u * (uint32_t)(NST + (i)))
 #define BARD (bar0 + 8u * (uint32_t)(2 * NST))
+#define BART (bar0 + 8u * (uint32_t)(2 * NST + 1))
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ------------------------------------------------------------------ set-up
@@ -333,18 +388,17 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       mbar_init(BARE(i), 1);
     }
     mbar_init(BARD, 1);
+    mbar_init(BART, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  stage_table_bulk(T_s, p.T, p.Kc, BART);            // overlaps the zero fill, the W staging and the first operand columns
   if (warp == PW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(q.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < (int)(NST * STAGE / 16); i += blockDim.x) reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
-  stage_table(T_s, p.T, p.Kc);
-  for (int i = threadIdx.x; i < IZ * IZ * p.KR; i += blockDim.x) {
-    const int k = i % p.KR, zc = i / p.KR;           // i = (z * 32 + c) * KR + k
-    W_s[(k * IZ + (zc & 31)) * TST + (zc >> 5)] = __ldg(p.W + i);
-  }
+  stage_w<false>(W_s, p.W, p.KR);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tcgen05_fence_before();
   __syncthreads();
@@ -380,7 +434,7 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
     __syncwarp();
   } else {
     // ============================== producers ==============================
-    const int k = warp % p.KR, s = warp / p.KR;
+    const int k = warp % p.KR, s = warp / p.KR, KR = p.KR, N = p.N;
     float acc[IZ];                                   // acc[z] = dW[z][c = lane][k]
 #pragma unroll
     for (int z = 0; z < IZ; ++z) acc[z] = 0.f;
@@ -392,25 +446,44 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
     int* cds = code_s + warp * 16;
     float* dus = du_s + warp * IZ;
     const float4* w4 = reinterpret_cast<const float4*>(W_s + (k * IZ + lane) * TST);
+    const bool cand = lane < 16 && lane <= N;        // lane n < 16 handles candidate n (0 = the positive)
+    // global reads of one row, fetched one step ahead: score, code, lse (candidate lanes), u[z = lane], c[c = lane]
+    float sc_n = 0.f, lse_n = 0.f, uz_n = 0.f, cb_n = 0.f;
+    int code_n = 0;
+    auto fetch = [&](int64_t it) {
+      const int64_t b64 = (it * gridDim.x + blockIdx.x) * p.SPI + s;
+      sc_n = lse_n = uz_n = cb_n = 0.f;
+      code_n = 0;
+      if (it >= nit || b64 >= p.B) return;
+      const int b = (int)b64, r = b * KR + k;
+      uz_n = __ldg(p.u + r * IZ + lane);
+      cb_n = __ldg(p.c + b * IZ + lane);
+      if (cand) {
+        const int n = lane;
+        sc_n = (n == 0) ? __ldg(p.pos + r) : __ldg(p.neg + r * N + n - 1);
+        code_n = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * N + (n - 1)) * KR + k]);
+        lse_n = __ldg(p.lse + r);
+      }
+    };
+    fetch(0);
+    bool t_ready = false;
 #pragma unroll 1
     for (int64_t it = 0; it < nit; ++it) {
       const int st = (int)(it % NST);
-      const int64_t b = (it * gridDim.x + blockIdx.x) * p.SPI + s;
-      const bool valid = b < p.B;
-      const int64_t r = b * p.KR + k;
-      // ---- global reads of the row (issued before the stage wait)
+      const int64_t b64 = (it * gridDim.x + blockIdx.x) * p.SPI + s;
+      const bool valid = b64 < p.B;
+      const int b = (int)b64, r = b * KR + k;
+      const float sc = sc_n, lse_r = lse_n, uz = uz_n, cb = cb_n;
+      const int code_raw = code_n;
+      fetch(it + 1);                                 // next row's reads are in flight during this step
       float cf = 0.f;
       int code = -1 - lane;                          // inactive lanes: distinct keys
-      if (lane < 16 && valid && lane <= p.N) {
+      if (cand && valid) {
         const int n = lane;
-        const float sc = (n == 0) ? __ldg(p.pos + r) : __ldg(p.neg + r * p.N + n - 1);
-        code = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * p.N + (n - 1)) * p.KR + k]);
-        code = min(max(code, 0), p.Kc - 1);
-        cf = gs * (expf(sc - __ldg(p.lse + r)) - (n == 0 ? 1.f : 0.f));
-        if (n == 0) p.coef_pos[r] = cf; else p.coef_neg[(b * p.N + (n - 1)) * p.KR + k] = cf;
+        code = min(max(code_raw, 0), p.Kc - 1);
+        cf = gs * (expf(sc - lse_r) - (n == 0 ? 1.f : 0.f));
+        if (n == 0) p.coef_pos[r] = cf; else p.coef_neg[(b * N + (n - 1)) * KR + k] = cf;
       }
-      const float uz = valid ? __ldg(p.u + r * IZ + lane) : 0.f;          // lane = z
-      const float cb = valid ? __ldg(p.c + b * IZ + lane) : 0.f;          // lane = c
       if (lane < 16) {
         cfs[lane] = cf;
         cds[lane] = code >= 0 ? code : 0;
@@ -451,20 +524,24 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BARF(st));
+      if (!t_ready) {
+        mbar_wait(BART, 0);
+        t_ready = true;
+      }
       // ---- du[z = lane] = sum_n coef_n T[code_n][z]
-      float du = 0.f;
+      float du0 = 0.f, du1 = 0.f;
 #pragma unroll
       for (int n4 = 0; n4 < 4; ++n4) {
         const int4 cd = *reinterpret_cast<const int4*>(cds + n4 * 4);
         const float4 c4 = *reinterpret_cast<const float4*>(cfs + n4 * 4);
-        du = fmaf(c4.x, T_s[cd.x * TST + lane], du);
-        du = fmaf(c4.y, T_s[cd.y * TST + lane], du);
-        du = fmaf(c4.z, T_s[cd.z * TST + lane], du);
-        du = fmaf(c4.w, T_s[cd.w * TST + lane], du);
+        du0 = fmaf(c4.x, T_s[cd.x * TST + lane], du0);
+        du1 = fmaf(c4.y, T_s[cd.y * TST + lane], du1);
+        du0 = fmaf(c4.z, T_s[cd.z * TST + lane], du0);
+        du1 = fmaf(c4.w, T_s[cd.w * TST + lane], du1);
       }
-      dus[lane] = du;
+      dus[lane] = du0 + du1;
       __syncwarp();
-      // ---- dc_k[c = lane] = sum_z W[z][c][k] du[z];  dW[z][c][k] += du[z] c_b[c]
+      // ---- dc_k[c = lane] = sum_z W[z][c][k] du[z]  (summed over k by the reduction kernel);  dW[z][c][k] += du[z] c_b[c]
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
       for (int z4 = 0; z4 < 8; ++z4) {
@@ -479,22 +556,10 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
         acc[4 * z4 + 2] = fmaf(d4.z, cb, acc[4 * z4 + 2]);
         acc[4 * z4 + 3] = fmaf(d4.w, cb, acc[4 * z4 + 3]);
       }
-      const float dck = (d0 + d1) + (d2 + d3);
-      if (p.KR == 1) {
-        if (valid) p.dc[b * IZ + lane] = dck;
-      } else {
-        // the KR warps of sample slot s meet at named barrier 1 + s (fixed summation order over k)
-        float* dcp = dcp_s + ((it & 1) * PW + warp) * IZ;
-        dcp[lane] = dck;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(p.KR * 32) : "memory");
-        if (k == 0 && valid) {
-          float t = 0.f;
-          for (int kk = 0; kk < p.KR; ++kk) t += dcp_s[((it & 1) * PW + s * p.KR + kk) * IZ + lane];
-          p.dc[b * IZ + lane] = t;
-        }
-      }
+      if (valid) p.dcp[r * IZ + lane] = (d0 + d1) + (d2 + d3);
       __syncwarp();
     }
+    if (!t_ready) mbar_wait(BART, 0);
     // ---- all MMAs retired: TMEM holds dT of this CTA
     mbar_wait(BARD, 0);
     tcgen05_fence_after();
@@ -530,6 +595,7 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
 #undef BARF
 #undef BARE
 #undef BARD
+#undef BART
   tcgen05_fence_before();
   __syncthreads();
   if (warp == PW) {
@@ -539,28 +605,46 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
 }
 
 // out_a[i] += sum_p part[p][i] (i < na);  out_b[i] += sum_p part[p][na + i] (i < nb);  na, nb multiples of 4.
-// 256 threads = 32 float4 columns x 8 groups of partials; fixed summation order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t stride,
-                                                              float* __restrict__ out_a, int na, float* __restrict__ out_b, int nb) {
-  __shared__ float4 red[8][32];
+// Blocks [0, nblk_tab): 512 threads = 32 float4 columns x 16 groups of partials (<= RP_MAX loads per thread, all in flight
+// at once), fixed summation order.  Blocks from nblk_tab on: dc[b][c] = sum_k dcp[(b * KR + k)][c] (one float4 per thread).
+constexpr int RP_MAX = 12;    // partial tables per thread: up to 16 * 12 = 192 CTAs
+__global__ void __launch_bounds__(512) reduce_partials_kernel(const float* __restrict__ part, int nparts, size_t stride,
+                                                              float* __restrict__ out_a, int na, float* __restrict__ out_b, int nb,
+                                                              int nblk_tab, const float* __restrict__ dcp, float* __restrict__ dc,
+                                                              int B, int KR) {
+  if ((int)blockIdx.x >= nblk_tab) {
+    const int i = (blockIdx.x - nblk_tab) * 512 + threadIdx.x;      // (b, c4)
+    if (i < B * 8) {
+      const int b = i >> 3, c4 = i & 7;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < KR; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dcp + ((size_t)b * KR + k) * IZ) + c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      reinterpret_cast<float4*>(dc + (size_t)b * IZ)[c4] = a;
+    }
+    return;
+  }
+  __shared__ float4 red[16][32];
   const int cx = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int col4 = blockIdx.x * 32 + cx;
   const int ncol4 = (na + nb) >> 2;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col4 < ncol4) {
-#pragma unroll 4
-    for (int q = pg; q < nparts; q += 8) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(part + (size_t)q * stride) + col4);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
+  float4 v[RP_MAX];
+#pragma unroll
+  for (int j = 0; j < RP_MAX; ++j) {
+    const int q = pg + 16 * j;
+    v[j] = (col4 < ncol4 && q < nparts) ? __ldg(reinterpret_cast<const float4*>(part + (size_t)q * stride) + col4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  float4 a = v[0];
+#pragma unroll
+  for (int j = 1; j < RP_MAX; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
   red[pg][cx] = a;
   __syncthreads();
   if (pg == 0 && col4 < ncol4) {
 #pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      const float4 v = red[q][cx];
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    for (int q = 1; q < 16; ++q) {
+      const float4 t = red[q][cx];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
     }
     float4* o = (col4 * 4 < na) ? reinterpret_cast<float4*>(out_a) + col4 : reinterpret_cast<float4*>(out_b) + (col4 - (na >> 2));
     float4 c = *o;
@@ -627,7 +711,7 @@ struct VqIdxBwdP {
   float beta;
   int squared, nseg, j_smem;
   IdxSeg seg[4];
-  float *dx, *dE;
+  float *dx, *dE, *dT;
 };
 
 constexpr int VCH = 512;      // vectors per CTA pass == threads
@@ -650,7 +734,7 @@ __device__ __forceinline__ VqVec<DS> vq_vec_load(const VqIdxBwdP& p, int64_t v) 
 #pragma unroll
   for (int d = 0; d < DS; ++d) r.x[d] = 0.f;
   if (v < p.n) {
-    r.code = min(max((int)p.idx[v], 0), p.Kc - 1);
+    r.code = (int)p.idx[v];          // (clamped by the consumer: nothing here may wait for a load)
     r.gl = p.gl ? __ldg(p.gl + v) : 0.f;
 #pragma unroll
     for (int d = 0; d < DS; ++d) r.x[d] = __ldg(p.x + v * DS + d);
@@ -726,25 +810,27 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       float g[DS];
 #pragma unroll
       for (int d = 0; d < DS; ++d) g[d] = 0.f;
-      if (cur.code != 0xFFFF) {
+      const bool have = ch * VCH + tid < p.n;
+      const int code1 = have ? min(max(cur.code, 0), p.Kc - 1) : 0xFFFF;
+      if (have) {
         float df[DS];
         float ssq = 0.f;
 #pragma unroll
         for (int d = 0; d < DS; ++d) {
-          df[d] = E_s[cur.code * ES + d] - cur.x[d];
+          df[d] = E_s[code1 * ES + d] - cur.x[d];
           const float t = df[d] + 1e-5f;
           ssq = fmaf(t, t, ssq);
         }
         const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
 #pragma unroll
         for (int d = 0; d < DS; ++d) g[d] = cur.gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
-        atomicAdd(&hist_s[cur.code], 1);
+        atomicAdd(&hist_s[code1], 1);
       }
 #pragma unroll
       for (int d = 0; d < DS; ++d) gdq_s[tid * DS + d] = g[d];
       coef_s[tid] = cur.cf;
       src_s[tid] = cur.src;
-      code_s[tid] = (uint16_t)cur.code;
+      code_s[tid] = (uint16_t)code1;
     }
     // next pass's inputs: in flight until the next phase 1
     cur = vq_vec_load<DS>(p, (ch + gridDim.x) * VCH + tid);
@@ -786,6 +872,13 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
         const float4* row = reinterpret_cast<const float4*>((sg.kind == 1 ? sg.a : sg.b) + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8);
         va[pass] = __ldg(row);
         vb[pass] = __ldg(row + 1);
+        if (sg.kind == 1 && p.dT) {
+          // gradient of the table gather y = T[idx] of the dense-row (left) blocks: dT[code] += dy, 32 bytes per lane as two
+          // fire-and-forget vector reductions (these rows are ~6 % of the vectors; the L2 atomic units work in the background)
+          float* t = p.dT + (size_t)min((int)code_s[pass * (VCH / 4) + qid], p.Kc - 1) * IZ + ql * 8;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t), "f"(va[pass].x), "f"(va[pass].y), "f"(va[pass].z), "f"(va[pass].w) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t + 4), "f"(vb[pass].x), "f"(vb[pass].y), "f"(vb[pass].z), "f"(vb[pass].w) : "memory");
+        }
       }
     }
     if (!j_ready) {
@@ -886,10 +979,15 @@ VQ_API int vqcpc_idxpath_supported(int N, int KR, int zd, int cd, int Kc, int D)
           (size_t)Kc * (TST + IZ) * 4 <= 190 * 1024 && (D == 3 || D == 4)) ? 1 : 0;
 }
 
-// number of per-CTA partial tables vqcpc_infonce_idx_bwd writes (rows of `part`)
+// number of per-CTA partial tables vqcpc_infonce_idx_bwd writes
 VQ_API int vqcpc_infonce_idx_parts(int B, int KR) {
   const int spi = nce_spi(KR);
   return (int)std::max<int64_t>(1, std::min<int64_t>(vq_sm_count(), vq_cdiv(B, spi)));
+}
+
+// floats of scratch vqcpc_infonce_idx_bwd needs: per-CTA partial tables (dT | dW) followed by the per-row dc contributions
+VQ_API int64_t vqcpc_infonce_idx_scratch(int B, int KR, int Kc) {
+  return (int64_t)vqcpc_infonce_idx_parts(B, KR) * ((int64_t)Kc * IZ + (int64_t)IZ * IZ * KR) + (int64_t)B * KR * IZ;
 }
 
 VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T, const int64_t* idx_pos, const int64_t* idx_neg,
@@ -899,10 +997,12 @@ VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T,
   if (B == 0) return VQ_OK;
   NceFwdP p{c, W, T, idx_pos, idx_neg, B, N, KR, Kc, nce_spi(KR), u, pos, neg, lse, nll, correct};
   const int warps = 16;
-  const size_t smem = ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * 2 * IZ) * 4;
+  const size_t smem = ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * 2 * IZ) * 4 + 16;
   VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_fwd: %zu bytes of shared memory needed", smem);
+  VQ_CHECK_ARG((((uintptr_t)T | (uintptr_t)c) & 15) == 0, "infonce_idx_fwd: T and c must be 16-byte aligned");
+  VQ_CHECK_ARG((int64_t)B * (N + 1) * KR < (1ll << 31), "infonce_idx_fwd: B * (N + 1) * KR must fit in 31 bits");
   const int64_t pairs = ((int64_t)B * KR + 1) / 2;
-  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  const int per_sm = smem <= 113 * 1024 ? 2 : 1;   // (228 KB per SM, 1 KB reserved per CTA)
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)vq_sm_count() * per_sm, vq_cdiv(pairs, warps)));
   VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nce_idx_fwd_kernel<<<grid, warps * 32, smem, vq_stream(stream)>>>(p);
@@ -922,6 +1022,11 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   p.dc = d_c; p.coef_pos = coef_pos; p.coef_neg = coef_neg; p.part = part;
   const int warps = KR * p.SPI;
   const int grid = vqcpc_infonce_idx_parts(B, KR);
+  VQ_CHECK_ARG(grid <= 16 * RP_MAX, "infonce_idx_bwd: %d partial tables exceed the reduction kernel's limit", grid);
+  VQ_CHECK_ARG((int64_t)B * (N + 1) * KR < (1ll << 31) && (int64_t)B * KR * IZ < (1ll << 31), "infonce_idx_bwd: problem too large for 32-bit indexing");
+  VQ_CHECK_ARG((((uintptr_t)T | (uintptr_t)part) & 15) == 0, "infonce_idx_bwd: T and the scratch must be 16-byte aligned");
+  p.dcp = part + (size_t)grid * ((size_t)Kc * IZ + (size_t)IZ * IZ * KR);
+  bool dc_in_reduce = false;
   cudaStream_t st = vq_stream(stream);
   // production kernel: dT on the tensor cores (tcgen05, TMEM accumulators); VQCPC_NCE_BWD_ALGO=1 forces the CUDA-core
   // owner-computes kernel (also the fallback when the operand stages do not fit next to the table)
@@ -934,12 +1039,13 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   q.stage_region = (uint32_t)std::max<size_t>((size_t)NST * (2 * (size_t)q.kpad * 32 + 2048), (size_t)warps * IZ * IZ * 4);
   q.stage_region = (q.stage_region + 1023u) & ~1023u;
   const size_t tc_smem = 1024 + (size_t)q.stage_region +
-                         ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * (32 + IZ + 2 * IZ)) * 4 + (2 * NST + 1) * 8 + 16;
+                         ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * (32 + IZ)) * 4 + (2 * NST + 2) * 8 + 16;
   if (force_simt != 1 && tc_smem <= 227 * 1024 && q.tmem_cols <= 512) {
     q.b = p;
     VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     nce_idx_bwd_tc_kernel<<<grid, (warps + 1) * 32, tc_smem, st>>>(q);
     VQ_CUDA_LAUNCH_CHECK("nce_idx_bwd_tc_kernel");
+    dc_in_reduce = true;
   } else {
     p.scratch_floats = std::max<size_t>((size_t)Kc * TST, (size_t)warps * IZ * IZ);
     p.scratch_floats = (p.scratch_floats + 3) & ~(size_t)3;
@@ -951,7 +1057,8 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   }
   const int na = Kc * IZ, nb = IZ * IZ * KR;
   const int ncol4 = (na + nb) / 4;
-  reduce_partials_kernel<<<(ncol4 + 31) / 32, 256, 0, st>>>(part, grid, (size_t)na + nb, d_T, na, d_W, nb);
+  const int nblk_tab = (ncol4 + 31) / 32, nblk_dc = dc_in_reduce ? (B * 8 + 511) / 512 : 0;
+  reduce_partials_kernel<<<nblk_tab + nblk_dc, 512, 0, st>>>(part, grid, (size_t)na + nb, d_T, na, d_W, nb, nblk_tab, p.dcp, d_c, B, KR);
   VQ_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
   return VQ_OK;
 }
@@ -972,7 +1079,7 @@ VQ_API int vqcpc_table_scatter_add(const int64_t* idx, int64_t n, const float* r
 VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, const float* J, int Kc, int zd, const int64_t* idx,
                             float beta, int squared, const float* g_loss, int nseg, const int64_t* seg_row0, const int64_t* seg_rows,
                             const int* seg_kind, const float* const* seg_a, const float* const* seg_b, const int* seg_per_b, int KR,
-                            float* d_x, float* d_E, void* stream) {
+                            float* d_x, float* d_E, float* d_T, void* stream) {
   VQ_CHECK_ARG(D == 3 || D == 4, "vq_idx_bwd: D must be 3 or 4 (got %d)", D);
   VQ_CHECK_ARG(zd == IZ, "vq_idx_bwd: zd must be 32 (got %d)", zd);
   VQ_CHECK_ARG(Kc >= 1 && Kc <= 2 * VCH, "vq_idx_bwd: Kc <= %d (got %d)", 2 * VCH, Kc);
@@ -980,7 +1087,8 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
   if (n == 0) return VQ_OK;
   VqIdxBwdP p{};
   p.x = x; p.E = E; p.J = J; p.gl = g_loss; p.idx = idx; p.n = n; p.Kc = Kc; p.beta = beta; p.squared = squared; p.nseg = nseg;
-  p.dx = d_x; p.dE = d_E;
+  p.dx = d_x; p.dE = d_E; p.dT = d_T;
+  VQ_CHECK_ARG(d_T == nullptr || ((uintptr_t)d_T & 15) == 0, "vq_idx_bwd: d_T must be 16-byte aligned");
   for (int i = 0; i < nseg; ++i) {
     VQ_CHECK_ARG(seg_kind[i] == 1 || seg_kind[i] == 2, "vq_idx_bwd: segment kind must be 1 (rows) or 2 (coef * u)");
     VQ_CHECK_ARG(seg_row0[i] >= 0 && seg_rows[i] >= 0 && seg_row0[i] + seg_rows[i] <= n && seg_rows[i] < (1 << 30),
