@@ -74,82 +74,83 @@ struct NceFwdP {
   int* correct;
 };
 
-// 16 warps per CTA, two CTAs per SM (<= 64 registers, ~112 KB of shared memory: the padded table and W transposed to
-// [k][z][c]).  A warp handles TWO (b, k) rows per step: lanes = features while u = W_k c is formed, then lane (j, n) scores
-// candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.  The table
-// arrives by bulk copies that overlap the W staging; the per-row global reads (candidate code, one c element per lane) are
-// fetched one step ahead.
-__global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
+// CTA = KR * SPI warps, one per SM; warp (s, k) always handles step k, so W[:, :, k] stays in its registers (no shared-memory
+// traffic for W) and walks the samples two at a time: lanes = features while the two u = W_k c are formed, then lane (j, n)
+// scores candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.
+// The table is ONE bulk copy in its global layout; bank conflicts of the row gathers are avoided by visiting the eight
+// 16-byte chunks of a row in the order q ^ (code & 7) (same order for equal codes: equal codes -> bit-equal scores, so a
+// negative that drew the positive's code is never "correct", like the reference).  Per-row global reads (candidate code,
+// one element of c per lane) are fetched one step ahead.
+__global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
   extern __shared__ __align__(16) float sm[];
-  float* T_s = sm;                                   // [Kc][TST]
-  float* W_s = T_s + (size_t)p.Kc * TST;             // [KR][32 z][TST]  W_s[k][z][c] = W[z][c][k]
-  float* u_s = W_s + (size_t)p.KR * IZ * TST;        // [warps][2][32]: the c vectors of the pair, then their u vectors
+  float* T_s = sm;                                   // [Kc][32]
+  float* u_s = T_s + (size_t)p.Kc * IZ;              // [warps][2][32]: the c vectors of the two rows, then their u vectors
   uint64_t* bar = reinterpret_cast<uint64_t*>(u_s + (blockDim.x >> 5) * 2 * IZ);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)p.Kc * IZ * 4;
+    mbar_expect_tx(bar_a, bytes);
+    for (uint32_t o = 0; o < bytes; o += 16384) {
+      const uint32_t nb = min(16384u, bytes - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(T_s) + o),
+                   "l"(reinterpret_cast<const char*>(p.T) + o), "r"(nb), "r"(bar_a)
+                   : "memory");
+    }
   }
-  __syncthreads();
-  stage_table_bulk(T_s, p.T, p.Kc, bar_a);
-  stage_w<true>(W_s, p.W, p.KR);
-  __syncthreads();
+  const int KR = p.KR, N = p.N, SPI = p.SPI;
+  const int k = warp % KR, s = warp / KR;
+  float Wc[IZ];                                      // Wc[c] = W[z = lane][c][k]
+#pragma unroll
+  for (int c = 0; c < IZ; ++c) Wc[c] = __ldg(p.W + ((size_t)lane * IZ + c) * KR + k);
+  __syncthreads();                                   // (mbarrier initialised before anybody waits on it)
   float* us = u_s + warp * 2 * IZ;
-  float* cs = us;
-  const int n = lane & 15, j = lane >> 4;            // candidate n (0 = positive) of row j of the pair
-  const bool act = n <= p.N;
-  const int rtot = p.B * p.KR, KR = p.KR, N = p.N;
-  const int step = gridDim.x * NW;
-  // per-step global reads: this lane's candidate code (row 2 pi + j) and element `lane` of the c vector of both rows
-  auto fetch = [&](int pi, int& code, float& c0, float& c1) {
+  const int n = lane & 15, j = lane >> 4;            // candidate n (0 = positive) of row j of the step
+  const bool act = n <= N;
+  const int B = p.B, bstep = gridDim.x * SPI;
+  // step i of this warp: samples b0 = base + 2 i bstep and b1 = b0 + bstep
+  auto fetch = [&](int b0, int& code, float& c0, float& c1) {
     code = 0;
     c0 = c1 = 0.f;
-    const int r0 = 2 * pi;
-    if (r0 >= rtot) return;
-    const int b0 = r0 / KR, k0 = r0 - b0 * KR;
-    const bool wrap = k0 + 1 == KR;
-    const int b1 = wrap ? b0 + 1 : b0, k1 = wrap ? 0 : k0 + 1;
-    const bool v1 = r0 + 1 < rtot;
-    c0 = __ldg(p.c + b0 * IZ + lane);
-    if (v1) c1 = __ldg(p.c + b1 * IZ + lane);
-    const int rj = r0 + j, bj = j ? b1 : b0, kj = j ? k1 : k0;
-    if (act && (j == 0 || v1)) code = (int)(n == 0 ? p.idx_pos[rj] : p.idx_neg[(bj * N + (n - 1)) * KR + kj]);
+    const int b1 = b0 + bstep;
+    if (b0 < B) c0 = __ldg(p.c + b0 * IZ + lane);
+    if (b1 < B) c1 = __ldg(p.c + b1 * IZ + lane);
+    const int bj = j ? b1 : b0;
+    if (act && bj < B) code = (int)(n == 0 ? p.idx_pos[bj * KR + k] : p.idx_neg[(bj * N + (n - 1)) * KR + k]);
   };
-  int pi = blockIdx.x * NW + warp;
+  int b0 = blockIdx.x * SPI + s;
   int code_n;
   float c0_n, c1_n;
-  fetch(pi, code_n, c0_n, c1_n);
+  fetch(b0, code_n, c0_n, c1_n);
   bool t_ready = false;
-  for (; 2 * pi < rtot; pi += step) {
-    const int code_raw = code_n;
-    cs[lane] = c0_n;
-    cs[IZ + lane] = c1_n;
-    fetch(pi + step, code_n, c0_n, c1_n);            // next step's reads are in flight during this step
+  for (; b0 < B; b0 += 2 * bstep) {
+    const int code = min(max(code_n, 0), p.Kc - 1);
+    us[lane] = c0_n;
+    us[IZ + lane] = c1_n;
+    fetch(b0 + 2 * bstep, code_n, c0_n, c1_n);       // next step's reads are in flight during this step
     __syncwarp();
-    const int r0 = 2 * pi;
-    const int b0 = r0 / KR, k0 = r0 - b0 * KR;
-    const int k1 = (k0 + 1 == KR) ? 0 : k0 + 1;
-    const bool v1 = r0 + 1 < rtot;
+    const int b1 = b0 + bstep;
+    const bool v1 = b1 < B;
     // ---- u of both rows, lanes = features
     float uu[2];
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
-      const float4* c4 = reinterpret_cast<const float4*>(cs + jj * IZ);
-      const float4* w4 = reinterpret_cast<const float4*>(W_s + ((jj ? k1 : k0) * IZ + lane) * TST);
+      const float4* c4 = reinterpret_cast<const float4*>(us + jj * IZ);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 t = c4[q];
-        const float4 w = w4[q];
-        a0 = fmaf(w.x, t.x, a0);
-        a1 = fmaf(w.y, t.y, a1);
-        a2 = fmaf(w.z, t.z, a2);
-        a3 = fmaf(w.w, t.w, a3);
+        const float4 t = c4[q];                      // broadcast
+        a0 = fmaf(Wc[4 * q], t.x, a0);
+        a1 = fmaf(Wc[4 * q + 1], t.y, a1);
+        a2 = fmaf(Wc[4 * q + 2], t.z, a2);
+        a3 = fmaf(Wc[4 * q + 3], t.w, a3);
       }
       uu[jj] = (a0 + a1) + (a2 + a3);
-      if (jj == 0 || v1) p.u[(r0 + jj) * IZ + lane] = uu[jj];
     }
+    p.u[(b0 * KR + k) * IZ + lane] = uu[0];
+    if (v1) p.u[(b1 * KR + k) * IZ + lane] = uu[1];
     __syncwarp();                                    // the u vectors replace the c vectors in the warp's buffer
     us[lane] = uu[0];
     us[IZ + lane] = uu[1];
@@ -158,15 +159,14 @@ __global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
       mbar_wait(bar_a, 0);
       t_ready = true;
     }
-    // ---- scores: every lane runs the SAME sequence of FMAs on its row, so candidates that drew the same code get
-    // bit-identical scores (a negative equal to the positive is never "correct", like the reference)
-    const int code = min(max(code_raw, 0), p.Kc - 1);
-    const float4* t4 = reinterpret_cast<const float4*>(T_s + code * TST);
+    // ---- scores
+    const float4* t4 = reinterpret_cast<const float4*>(T_s + code * IZ);
     const float4* u4 = reinterpret_cast<const float4*>(us + j * IZ);
+    const int sw = code & 7;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 a = t4[q], v = u4[q];
+      const float4 a = t4[q ^ sw], v = u4[q ^ sw];
       a0 = fmaf(a.x, v.x, a0);
       a1 = fmaf(a.y, v.y, a1);
       a2 = fmaf(a.z, v.z, a2);
@@ -184,8 +184,9 @@ __global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
     const float lse = m + logf(e);
-    const int rj = r0 + j;
-    if (j == 0 || v1) {
+    const int bj = j ? b1 : b0;
+    if (bj < B) {
+      const int rj = bj * KR + k;
       if (n == 0) {
         p.pos[rj] = sc;
         p.lse[rj] = lse;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(512, 2) nce_idx_fwd_kernel(NceFwdP p) {
     }
     __syncwarp();
   }
-  if (!t_ready) mbar_wait(bar_a, 0);                 // never leave with bulk copies in flight
+  if (!t_ready) mbar_wait(bar_a, 0);                 // never leave with a bulk copy in flight
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -585,12 +586,12 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
     for (int z = 0; z < IZ; ++z) scr[(warp * IZ + z) * IZ + lane] = acc[z];
     asm volatile("bar.sync 9, %0;" ::"r"(PW * 32) : "memory");
     float* pw = part + (size_t)p.Kc * IZ;
-    for (int i = warp * 32 + lane; i < IZ * IZ * p.KR; i += PW * 32) {
-      const int kk = i % p.KR, zc = i / p.KR;
-      float t = 0.f;
-      for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
-      pw[i] = t;
-    }
+    for (int zc = warp * 32 + lane; zc < IZ * IZ; zc += PW * 32)
+      for (int kk = 0; kk < p.KR; ++kk) {
+        float t = 0.f;
+        for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
+        pw[zc * p.KR + kk] = t;
+      }
   }
 #undef BARF
 #undef BARE
@@ -710,6 +711,7 @@ struct VqIdxBwdP {
   int Kc;
   float beta;
   int squared, nseg, j_smem;
+  uint32_t kind1_mask;        // bit s: segment s holds dense rows (kind 1)
   IdxSeg seg[4];
   float *dx, *dE, *dT;
 };
@@ -738,10 +740,12 @@ __device__ __forceinline__ VqVec<DS> vq_vec_load(const VqIdxBwdP& p, int64_t v) 
     r.gl = p.gl ? __ldg(p.gl + v) : 0.f;
 #pragma unroll
     for (int d = 0; d < DS; ++d) r.x[d] = __ldg(p.x + v * DS + d);
-    for (int sgi = 0; sgi < p.nseg; ++sgi) {
+    const uint32_t v32 = (uint32_t)v;                  // (n < 2^31, checked by the host side)
+#pragma unroll
+    for (int sgi = 0; sgi < 4; ++sgi) {                // static indices: the segment descriptors stay in the constant bank
       const IdxSeg& sg = p.seg[sgi];
-      if (v >= sg.row0 && v < sg.row0 + sg.rows) {
-        const uint32_t pl = (uint32_t)(v - sg.row0);
+      const uint32_t pl = v32 - (uint32_t)sg.row0;
+      if (sgi < p.nseg && pl < (uint32_t)sg.rows) {
         if (sg.kind == 1) {
           r.src = pl | ((uint32_t)sgi << 30);
           r.cf = 1.f;
@@ -773,8 +777,10 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
   uint16_t* code_s = reinterpret_cast<uint16_t*>(wsum_s + 32);                           // [VCH]
   uint16_t* perm_s = code_s + VCH;                                                       // [VCH]
   uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(perm_s + VCH) + 7) & ~(uintptr_t)7);
+  const float** segbase_s = reinterpret_cast<const float**>(bar + 1);                    // [4] source matrix of each segment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_a = s_u32(bar);
+  if (tid < 4) segbase_s[tid] = tid < p.nseg ? (p.seg[tid].kind == 1 ? p.seg[tid].a : p.seg[tid].b) : nullptr;
   if (p.j_smem) {
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
@@ -868,11 +874,10 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       const uint32_t src = src_s[pass * (VCH / 4) + qid];
       va[pass] = vb[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (src != 0xFFFFFFFFu) {
-        const IdxSeg& sg = p.seg[src >> 30];
-        const float4* row = reinterpret_cast<const float4*>((sg.kind == 1 ? sg.a : sg.b) + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8);
+        const float4* row = reinterpret_cast<const float4*>(segbase_s[src >> 30] + (size_t)(src & 0x3FFFFFFFu) * IZ + ql * 8);
         va[pass] = __ldg(row);
         vb[pass] = __ldg(row + 1);
-        if (sg.kind == 1 && p.dT) {
+        if (p.dT && ((p.kind1_mask >> (src >> 30)) & 1u)) {
           // gradient of the table gather y = T[idx] of the dense-row (left) blocks: dT[code] += dy, 32 bytes per lane as two
           // fire-and-forget vector reductions (these rows are ~6 % of the vectors; the L2 atomic units work in the background)
           float* t = p.dT + (size_t)min((int)code_s[pass * (VCH / 4) + qid], p.Kc - 1) * IZ + ql * 8;
@@ -955,7 +960,7 @@ size_t vq_idx_bwd_smem(int Kc, bool j_smem) {
   s += ((size_t)3 * Kc + 1 + 32) * 4;                // hist, start, cur, wsum
   s += VCH * 2 * 2;                                  // code, perm
   s = (s + 7) & ~(size_t)7;
-  return s + 16;
+  return s + 8 + 4 * 8 + 8;                          // mbarrier, segment bases, alignment slack
 }
 
 int nce_spi(int KR) { return KR >= 9 ? 1 : 16 / KR; }
@@ -996,14 +1001,12 @@ VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T,
   if (int rc = idx_path_check("infonce_idx_fwd", N, KR, zd, cd, Kc)) return rc;
   if (B == 0) return VQ_OK;
   NceFwdP p{c, W, T, idx_pos, idx_neg, B, N, KR, Kc, nce_spi(KR), u, pos, neg, lse, nll, correct};
-  const int warps = 16;
-  const size_t smem = ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * 2 * IZ) * 4 + 16;
+  const int warps = KR * p.SPI;
+  const size_t smem = ((size_t)Kc * IZ + (size_t)warps * 2 * IZ) * 4 + 16;
   VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_fwd: %zu bytes of shared memory needed", smem);
   VQ_CHECK_ARG((((uintptr_t)T | (uintptr_t)c) & 15) == 0, "infonce_idx_fwd: T and c must be 16-byte aligned");
-  VQ_CHECK_ARG((int64_t)B * (N + 1) * KR < (1ll << 31), "infonce_idx_fwd: B * (N + 1) * KR must fit in 31 bits");
-  const int64_t pairs = ((int64_t)B * KR + 1) / 2;
-  const int per_sm = smem <= 113 * 1024 ? 2 : 1;   // (228 KB per SM, 1 KB reserved per CTA)
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)vq_sm_count() * per_sm, vq_cdiv(pairs, warps)));
+  VQ_CHECK_ARG((int64_t)B * (N + 1) * KR < (1ll << 31) && (int64_t)B * KR * IZ < (1ll << 31), "infonce_idx_fwd: problem too large for 32-bit indexing");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)vq_sm_count(), vq_cdiv(B, 2 * p.SPI)));
   VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nce_idx_fwd_kernel<<<grid, warps * 32, smem, vq_stream(stream)>>>(p);
   VQ_CUDA_LAUNCH_CHECK("nce_idx_fwd_kernel");
@@ -1084,6 +1087,7 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
   VQ_CHECK_ARG(zd == IZ, "vq_idx_bwd: zd must be 32 (got %d)", zd);
   VQ_CHECK_ARG(Kc >= 1 && Kc <= 2 * VCH, "vq_idx_bwd: Kc <= %d (got %d)", 2 * VCH, Kc);
   VQ_CHECK_ARG(nseg >= 0 && nseg <= 4, "vq_idx_bwd: at most 4 segments (got %d)", nseg);
+  VQ_CHECK_ARG(n < (1ll << 31), "vq_idx_bwd: n must fit in 31 bits");
   if (n == 0) return VQ_OK;
   VqIdxBwdP p{};
   p.x = x; p.E = E; p.J = J; p.gl = g_loss; p.idx = idx; p.n = n; p.Kc = Kc; p.beta = beta; p.squared = squared; p.nseg = nseg;
@@ -1096,6 +1100,7 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
     VQ_CHECK_ARG(seg_kind[i] == 1 || (seg_per_b[i] >= 1 && KR >= 1 && seg_per_b[i] % KR == 0), "vq_idx_bwd: segment %d: bad per_b / KR", i);
     VQ_CHECK_ARG((((uintptr_t)seg_a[i] | (uintptr_t)(seg_kind[i] == 2 ? seg_b[i] : nullptr)) & 15) == 0, "vq_idx_bwd: segment %d: sources must be 16-byte aligned", i);
     p.seg[i] = IdxSeg{seg_row0[i], seg_rows[i], seg_kind[i], seg_a[i], seg_kind[i] == 2 ? seg_b[i] : nullptr, seg_kind[i] == 2 ? seg_per_b[i] : 1, KR};
+    if (seg_kind[i] == 1) p.kind1_mask |= 1u << i;
   }
   cudaStream_t st = vq_stream(stream);
   const int64_t nchunk = vq_cdiv(n, VCH);
