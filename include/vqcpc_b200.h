@@ -197,6 +197,8 @@ int vqcpc_infonce_bwd(const float* c, const float* W, const float* y_pos, const 
  * memory), D in {3, 4}; vqcpc_idxpath_supported() returns 1 for such shapes (callers keep the per-vector entry points
  * above for everything else). */
 int vqcpc_idxpath_supported(int N, int KR, int zd, int cd, int Kc, int D);
+/* debugging aid: clock64 phase timers of block 0 of the last vqcpc_infonce_idx_fwd launch (16 values, host buffer). */
+int vqcpc_idx_debug_read(long long* out16 /*host*/);
 /* vqcpc_vq_fused_fwd with the upscaled rows y = T[idx] produced only for the rows [y_row0, y_row0 + y_rows) (the left
  * blocks, which the context GRU reads; y has y_rows rows).  Replaces vector_quantizer.py:104-157 + mlp_upscaler.py:21-35. */
 int vqcpc_vq_fused_fwd_rows(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta,

@@ -46,6 +46,9 @@ nll = torch.empty(B, KR, device=dev)
 corr = torch.empty(B, KR, dtype=torch.int32, device=dev)
 step('infonce_idx_fwd', lambda: _native.call('vqcpc_infonce_idx_fwd', p_(c), p_(W), p_(T), p_(idx[n_neg + n_left:]), p_(idx), B, N, KR, zd, cd, Kc,
                                               p_(u), p_(pos), p_(neg), p_(lse), p_(nll), p_(corr), st()))
+dbg = (ctypes.c_longlong * 16)()
+_native.call('vqcpc_idx_debug_read', dbg)
+print('fwd dbg [setup, table wait, loop, steps, top, u, score, softmax+out]:', list(dbg)[:8], flush=True)
 dc = torch.zeros(B, cd, device=dev)
 dW = torch.zeros_like(W)
 dT = torch.zeros_like(T)
@@ -54,6 +57,8 @@ cn = torch.empty(B, N, KR, device=dev)
 part = torch.empty(_native.load().vqcpc_infonce_idx_scratch(B, KR, Kc), device=dev)
 step('infonce_idx_bwd', lambda: _native.call('vqcpc_infonce_idx_bwd', p_(c), p_(W), p_(T), p_(idx[n_neg + n_left:]), p_(idx), p_(u), p_(pos), p_(neg),
                                               p_(lse), None, 1.0 / B, B, N, KR, zd, cd, Kc, p_(dc), p_(cp), p_(cn), p_(part), p_(dW), p_(dT), st()))
+_native.call('vqcpc_idx_debug_read', dbg)
+print('bwd dbg [setup, loop, end, coef, wait-empty, build, du, dc/dW]:', list(dbg)[8:16], flush=True)
 # reference for dT / dW / dc in fp64
 i_neg = idx[:n_neg].view(B, N, KR)
 i_pos = idx[n_neg + n_left:].view(B, KR)

@@ -304,13 +304,16 @@ int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 //                         2 = 128x256x32 with the B tile multicast over a cluster of 2 CTAs along M, 3 = cluster of 4,
 //                         4 = CTA pairs (tcgen05.mma.cta_group::2), 256x256x32 tiles, 6 / 12 stages (gemm_tc2.cu)
 int g_force_cfg = -1;
-inline int pick_cfg(int M, int N, bool b_kmajor) {
+inline int pick_cfg(int M, int N, int K, bool b_kmajor) {
   if (g_force_cfg >= 0) return (N < 256 && g_force_cfg > 0) ? 0 : g_force_cfg;
   if (N < 256) return 0;
   if (M < 2 * BM) return 1;
-  // measured on the encoder shapes (profiles/r01_gemm_bench_*.txt): the CTA-pair kernel wins when B is K-major
-  // (forward GEMMs), the multicast kernel when B is MN-major (data / weight gradients)
-  return b_kmajor ? 4 : 2;
+  // measured on the encoder shapes (profiles/r01_gemm_bench_*.txt, profiles/r02_gemm_check_cfgs.txt): the CTA-pair kernel
+  // wins when B is K-major (forward GEMMs), the multicast kernel when B is MN-major (data / weight gradients).  With a
+  // short K and only two N tiles (out-proj forward, 512 x 512) the epilogue is the bottleneck of the pair kernel: its
+  // eight-epilogue-warp variant measured 860 vs 777 tensor-TFLOP/s there (and loses on every wider / deeper shape).
+  if (b_kmajor) return (N <= 512 && K <= 1024) ? 5 : 4;
+  return 2;
 }
 
 template <bool AK, bool BKM>
@@ -360,7 +363,7 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
-  int cfg = pick_cfg(M, N, b_kmajor != 0);
+  int cfg = pick_cfg(M, N, K, b_kmajor != 0);
   const bool epw8 = cfg == 5;                        // configuration 5 = configuration 4 with eight epilogue warps per CTA
   if (epw8) cfg = 4;
   const int BN = cfg >= 1 ? 256 : 128, BK = (cfg >= 1 && cfg <= 3) ? 32 : 64;

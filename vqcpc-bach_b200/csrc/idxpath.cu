@@ -55,6 +55,19 @@ __device__ __forceinline__ void stage_w(float* W_s, const float* __restrict__ W,
   }
 }
 
+// global loads that stay where they are written (asm volatile): used for software prefetching, where ptxas would otherwise
+// sink the loads towards their first use to shorten live ranges
+__device__ __forceinline__ float ldg_now(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ long long ldg_now(const int64_t* p) {
+  long long v;
+  asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
 // stage the (Kc, 32) table with padded rows
 __device__ __forceinline__ void stage_table(float* T_s, const float* __restrict__ T, int Kc) {
   for (int i = threadIdx.x; i < Kc * 8; i += blockDim.x) {
@@ -74,18 +87,22 @@ struct NceFwdP {
   int* correct;
 };
 
+__device__ long long g_idx_dbg[16];
+
 // CTA = KR * SPI warps, one per SM; warp (s, k) always handles step k, so W[:, :, k] stays in its registers (no shared-memory
 // traffic for W) and walks the samples two at a time: lanes = features while the two u = W_k c are formed, then lane (j, n)
 // scores candidate n of row j with one 32-term dot product, so the log-sum-exp shuffles serve both rows at once.
-// The table is ONE bulk copy in its global layout; bank conflicts of the row gathers are avoided by visiting the eight
-// 16-byte chunks of a row in the order q ^ (code & 7) (same order for equal codes: equal codes -> bit-equal scores, so a
-// negative that drew the positive's code is never "correct", like the reference).  Per-row global reads (candidate code,
-// one element of c per lane) are fetched one step ahead.
+// The table is ONE bulk copy in its global layout; the row gathers are bank-conflict free by construction: lane l visits the
+// eight 16-byte chunks of its row in the order (q + l) & 7, so the eight lanes of a quarter warp always touch eight different
+// bank groups.  The summation order therefore depends on the lane; a negative that drew the positive's code takes the
+// positive's score (one shuffle), which keeps such a candidate bit-equal and never "correct", like the reference.
+// Per-row global reads (candidate code, one element of c per lane) are fetched one step ahead.
 __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
   extern __shared__ __align__(16) float sm[];
   float* T_s = sm;                                   // [Kc][32]
   float* u_s = T_s + (size_t)p.Kc * IZ;              // [warps][2][32]: the c vectors of the two rows, then their u vectors
-  uint64_t* bar = reinterpret_cast<uint64_t*>(u_s + (blockDim.x >> 5) * 2 * IZ);
+  float* W_s = u_s + (blockDim.x >> 5) * 2 * IZ;     // [KR][32 z][TST] staging of W (coalesced global reads) on its way to registers
+  uint64_t* bar = reinterpret_cast<uint64_t*>(W_s + (size_t)p.KR * IZ * TST);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
@@ -100,12 +117,19 @@ __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
                    : "memory");
     }
   }
+  const long long t_begin = clock64();
+  const bool dbg = blockIdx.x == 0 && threadIdx.x == 0;
+  long long t_u = 0, t_sc = 0, t_sm = 0, t_top = 0;
   const int KR = p.KR, N = p.N, SPI = p.SPI;
   const int k = warp % KR, s = warp / KR;
+  stage_w<true>(W_s, p.W, KR);
+  __syncthreads();                                   // (also: mbarrier initialised before anybody waits on it)
   float Wc[IZ];                                      // Wc[c] = W[z = lane][c][k]
 #pragma unroll
-  for (int c = 0; c < IZ; ++c) Wc[c] = __ldg(p.W + ((size_t)lane * IZ + c) * KR + k);
-  __syncthreads();                                   // (mbarrier initialised before anybody waits on it)
+  for (int q = 0; q < 8; ++q) {
+    const float4 w = *reinterpret_cast<const float4*>(W_s + (k * IZ + lane) * TST + 4 * q);
+    Wc[4 * q] = w.x; Wc[4 * q + 1] = w.y; Wc[4 * q + 2] = w.z; Wc[4 * q + 3] = w.w;
+  }
   float* us = u_s + warp * 2 * IZ;
   const int n = lane & 15, j = lane >> 4;            // candidate n (0 = positive) of row j of the step
   const bool act = n <= N;
@@ -115,22 +139,28 @@ __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
     code = 0;
     c0 = c1 = 0.f;
     const int b1 = b0 + bstep;
-    if (b0 < B) c0 = __ldg(p.c + b0 * IZ + lane);
-    if (b1 < B) c1 = __ldg(p.c + b1 * IZ + lane);
+    if (b0 < B) c0 = ldg_now(p.c + b0 * IZ + lane);
+    if (b1 < B) c1 = ldg_now(p.c + b1 * IZ + lane);
     const int bj = j ? b1 : b0;
-    if (act && bj < B) code = (int)(n == 0 ? p.idx_pos[bj * KR + k] : p.idx_neg[(bj * N + (n - 1)) * KR + k]);
+    if (act && bj < B) code = (int)ldg_now(n == 0 ? p.idx_pos + bj * KR + k : p.idx_neg + (bj * N + (n - 1)) * KR + k);
   };
   int b0 = blockIdx.x * SPI + s;
   int code_n;
   float c0_n, c1_n;
   fetch(b0, code_n, c0_n, c1_n);
   bool t_ready = false;
+  const long long t_setup = clock64();
+  long long t_wait = 0;
+  int nsteps = 0;
   for (; b0 < B; b0 += 2 * bstep) {
+    long long t0 = clock64();
+    ++nsteps;
     const int code = min(max(code_n, 0), p.Kc - 1);
     us[lane] = c0_n;
     us[IZ + lane] = c1_n;
     fetch(b0 + 2 * bstep, code_n, c0_n, c1_n);       // next step's reads are in flight during this step
     __syncwarp();
+    { const long long t1 = clock64(); t_top += t1 - t0; t0 = t1; }
     const int b1 = b0 + bstep;
     const bool v1 = b1 < B;
     // ---- u of both rows, lanes = features
@@ -155,25 +185,32 @@ __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
     us[lane] = uu[0];
     us[IZ + lane] = uu[1];
     __syncwarp();
+    { const long long t1 = clock64(); t_u += t1 - t0; t0 = t1; }
     if (!t_ready) {
       mbar_wait(bar_a, 0);
       t_ready = true;
+      const long long t1 = clock64(); t_wait = t1 - t0; t0 = t1;
     }
     // ---- scores
     const float4* t4 = reinterpret_cast<const float4*>(T_s + code * IZ);
     const float4* u4 = reinterpret_cast<const float4*>(us + j * IZ);
-    const int sw = code & 7;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 a = t4[q ^ sw], v = u4[q ^ sw];
+      const float4 a = t4[(q + lane) & 7], v = u4[(q + lane) & 7];
       a0 = fmaf(a.x, v.x, a0);
       a1 = fmaf(a.y, v.y, a1);
       a2 = fmaf(a.z, v.z, a2);
       a3 = fmaf(a.w, v.w, a3);
     }
     float sc = (a0 + a1) + (a2 + a3);
+    {
+      const int code0 = __shfl_sync(FULL, code, lane & 16);          // the positive of this lane's row
+      const float sc0 = __shfl_sync(FULL, sc, lane & 16);
+      if (code == code0) sc = sc0;
+    }
     if (!act) sc = -INFINITY;
+    { const long long t1 = clock64(); t_sc += t1 - t0; t0 = t1; }
     float m = sc, nm = (n == 0) ? -INFINITY : sc;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
@@ -197,8 +234,14 @@ __global__ void __launch_bounds__(512, 1) nce_idx_fwd_kernel(NceFwdP p) {
       }
     }
     __syncwarp();
+    { const long long t1 = clock64(); t_sm += t1 - t0; t0 = t1; }
   }
   if (!t_ready) mbar_wait(bar_a, 0);                 // never leave with a bulk copy in flight
+  if (dbg) {
+    const long long t_end = clock64();
+    g_idx_dbg[0] = t_setup - t_begin; g_idx_dbg[1] = t_wait; g_idx_dbg[2] = t_end - t_setup; g_idx_dbg[3] = nsteps;
+    g_idx_dbg[4] = t_top; g_idx_dbg[5] = t_u; g_idx_dbg[6] = t_sc; g_idx_dbg[7] = t_sm;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -381,6 +424,7 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
 #define BARD (bar0 + 8u * (uint32_t)(2 * NST))
 #define BART (bar0 + 8u * (uint32_t)(2 * NST + 1))
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_begin = clock64();
 
   // ------------------------------------------------------------------ set-up
   if (threadIdx.x == 0) {
@@ -406,6 +450,8 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int64_t nit = (p.B + (int64_t)gridDim.x * p.SPI - 1) / ((int64_t)gridDim.x * p.SPI);
+  const long long t_setup_end = clock64();
+  long long tp_coef = 0, tp_wait = 0, tp_build = 0, tp_du = 0, tp_dc = 0;
 
   if (warp == PW) {
     // ============================== MMA issuer ==============================
@@ -457,19 +503,20 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       code_n = 0;
       if (it >= nit || b64 >= p.B) return;
       const int b = (int)b64, r = b * KR + k;
-      uz_n = __ldg(p.u + r * IZ + lane);
-      cb_n = __ldg(p.c + b * IZ + lane);
+      uz_n = ldg_now(p.u + r * IZ + lane);
+      cb_n = ldg_now(p.c + b * IZ + lane);
       if (cand) {
         const int n = lane;
-        sc_n = (n == 0) ? __ldg(p.pos + r) : __ldg(p.neg + r * N + n - 1);
-        code_n = (int)(n == 0 ? p.idx_pos[r] : p.idx_neg[(b * N + (n - 1)) * KR + k]);
-        lse_n = __ldg(p.lse + r);
+        sc_n = ldg_now((n == 0) ? p.pos + r : p.neg + r * N + n - 1);
+        code_n = (int)ldg_now(n == 0 ? p.idx_pos + r : p.idx_neg + (b * N + (n - 1)) * KR + k);
+        lse_n = ldg_now(p.lse + r);
       }
     };
     fetch(0);
     bool t_ready = false;
 #pragma unroll 1
     for (int64_t it = 0; it < nit; ++it) {
+      long long tq = clock64();
       const int st = (int)(it % NST);
       const int64_t b64 = (it * gridDim.x + blockIdx.x) * p.SPI + s;
       const bool valid = b64 < p.B;
@@ -490,10 +537,12 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
         cds[lane] = code >= 0 ? code : 0;
       }
       __syncwarp();
+      { const long long t1 = clock64(); tp_coef += t1 - tq; tq = t1; }
       // ---- stage hand-over: wait until the MMAs that read this stage NST steps ago have retired, un-write our old entries
       uint8_t* sg = stages + (size_t)st * STAGE;
       if (it >= NST) {
         mbar_wait(BARE(st), (uint32_t)(((it / NST) - 1) & 1));
+        { const long long t1 = clock64(); tp_wait += t1 - tq; tq = t1; }
         int oc = old_code[0];
 #pragma unroll
         for (int i = 1; i < NST; ++i) oc = (st == i) ? old_code[i] : oc;
@@ -525,6 +574,7 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BARF(st));
+      { const long long t1 = clock64(); tp_build += t1 - tq; tq = t1; }
       if (!t_ready) {
         mbar_wait(BART, 0);
         t_ready = true;
@@ -542,6 +592,7 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       }
       dus[lane] = du0 + du1;
       __syncwarp();
+      { const long long t1 = clock64(); tp_du += t1 - tq; tq = t1; }
       // ---- dc_k[c = lane] = sum_z W[z][c][k] du[z]  (summed over k by the reduction kernel);  dW[z][c][k] += du[z] c_b[c]
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
@@ -559,18 +610,22 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       }
       if (valid) p.dcp[r * IZ + lane] = (d0 + d1) + (d2 + d3);
       __syncwarp();
+      { const long long t1 = clock64(); tp_dc += t1 - tq; tq = t1; }
     }
     if (!t_ready) mbar_wait(BART, 0);
+    const long long t_loop_end = clock64();
     // ---- all MMAs retired: TMEM holds dT of this CTA
     mbar_wait(BARD, 0);
     tcgen05_fence_after();
     float* part = p.part + (size_t)blockIdx.x * ((size_t)p.Kc * IZ + (size_t)IZ * IZ * p.KR);
-    if (warp < 4) {
-      for (int m = 0; m < MT; ++m) {
+    {
+      // warp w reads lane quadrant w & 3 of the code tiles w >> 2, w >> 2 + PW / 4, ...
+      for (int m = warp >> 2; m < MT; m += max(1, PW >> 2)) {
+        if ((warp >> 2) >= max(1, PW >> 2)) break;
         uint32_t rr[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * 32), rr);
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(m * 32), rr);
         tmem_ld_wait();
-        const int code = m * 128 + warp * 32 + lane;
+        const int code = m * 128 + (warp & 3) * 32 + lane;
         if (code < p.Kc) {
           float4* o = reinterpret_cast<float4*>(part + (size_t)code * IZ);
 #pragma unroll
@@ -592,6 +647,10 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
         for (int ss = 0; ss < p.SPI; ++ss) t += scr[(ss * p.KR + kk) * IZ * IZ + zc];
         pw[zc * p.KR + kk] = t;
       }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      g_idx_dbg[8] = t_setup_end - t_begin; g_idx_dbg[9] = t_loop_end - t_setup_end; g_idx_dbg[10] = clock64() - t_loop_end;
+      g_idx_dbg[11] = tp_coef; g_idx_dbg[12] = tp_wait; g_idx_dbg[13] = tp_build; g_idx_dbg[14] = tp_du; g_idx_dbg[15] = tp_dc;
+    }
   }
 #undef BARF
 #undef BARE
@@ -736,10 +795,10 @@ __device__ __forceinline__ VqVec<DS> vq_vec_load(const VqIdxBwdP& p, int64_t v) 
 #pragma unroll
   for (int d = 0; d < DS; ++d) r.x[d] = 0.f;
   if (v < p.n) {
-    r.code = (int)p.idx[v];          // (clamped by the consumer: nothing here may wait for a load)
-    r.gl = p.gl ? __ldg(p.gl + v) : 0.f;
+    r.code = (int)ldg_now(p.idx + v);          // (clamped by the consumer: nothing here may wait for a load)
+    r.gl = p.gl ? ldg_now(p.gl + v) : 0.f;
 #pragma unroll
-    for (int d = 0; d < DS; ++d) r.x[d] = __ldg(p.x + v * DS + d);
+    for (int d = 0; d < DS; ++d) r.x[d] = ldg_now(p.x + v * DS + d);
     const uint32_t v32 = (uint32_t)v;                  // (n < 2^31, checked by the host side)
 #pragma unroll
     for (int sgi = 0; sgi < 4; ++sgi) {                // static indices: the segment descriptors stay in the constant bank
@@ -751,7 +810,7 @@ __device__ __forceinline__ VqVec<DS> vq_vec_load(const VqIdxBwdP& p, int64_t v) 
           r.cf = 1.f;
         } else {
           r.src = ((pl / (uint32_t)sg.per_b) * (uint32_t)sg.KR + pl % (uint32_t)sg.KR) | ((uint32_t)sgi << 30);
-          r.cf = __ldg(sg.a + pl);
+          r.cf = ldg_now(sg.a + pl);
         }
       }
     }
@@ -978,6 +1037,12 @@ static int idx_path_check(const char* who, int N, int KR, int zd, int cd, int Kc
   return VQ_OK;
 }
 
+// debugging aid: the clock64 phase timers the forward kernel's block 0 / thread 0 recorded at its last launch
+VQ_API int vqcpc_idx_debug_read(long long* out16 /*host*/) {
+  VQ_CUDA_CALL(cudaMemcpyFromSymbol(out16, g_idx_dbg, sizeof(long long) * 16));
+  return VQ_OK;
+}
+
 // 1 if the shapes are handled by the index-path kernels below (callers fall back to the per-vector path otherwise)
 VQ_API int vqcpc_idxpath_supported(int N, int KR, int zd, int cd, int Kc, int D) {
   return (zd == IZ && cd == IZ && N >= 1 && N <= 15 && KR >= 1 && KR <= 16 && Kc >= 1 && Kc <= 2 * VCH &&
@@ -1002,7 +1067,7 @@ VQ_API int vqcpc_infonce_idx_fwd(const float* c, const float* W, const float* T,
   if (B == 0) return VQ_OK;
   NceFwdP p{c, W, T, idx_pos, idx_neg, B, N, KR, Kc, nce_spi(KR), u, pos, neg, lse, nll, correct};
   const int warps = KR * p.SPI;
-  const size_t smem = ((size_t)Kc * IZ + (size_t)warps * 2 * IZ) * 4 + 16;
+  const size_t smem = ((size_t)Kc * IZ + (size_t)warps * 2 * IZ + (size_t)KR * IZ * TST) * 4 + 16;
   VQ_CHECK_ARG(smem <= 227 * 1024, "infonce_idx_fwd: %zu bytes of shared memory needed", smem);
   VQ_CHECK_ARG((((uintptr_t)T | (uintptr_t)c) & 15) == 0, "infonce_idx_fwd: T and c must be 16-byte aligned");
   VQ_CHECK_ARG((int64_t)B * (N + 1) * KR < (1ll << 31) && (int64_t)B * KR * IZ < (1ll << 31), "infonce_idx_fwd: problem too large for 32-bit indexing");
