@@ -415,3 +415,24 @@ def trainer_step(batch, prm, cfg, m=None, v=None, step=1, lr=1e-4):
     newp, m, v = adam_step({k: p.detach() for k, p in prm.items()}, clipped, m, v, step, lr)
     out = {k: (t.detach() if torch.is_tensor(t) else t) for k, t in out.items()}
     return out, grads, gnorm, newp, m, v
+
+
+# --------------------------------------------------------------------------------------------
+# EMA codebook (extension; NO reference counterpart: "parity unpinned")
+# --------------------------------------------------------------------------------------------
+def ema_codebook_update(N, m, z, idx, decay, eps=1e-5):
+    """CPU restatement of the optional EMA codebook update of the product (quantizer.ema_update), the standard VQ-VAE
+    rule (van den Oord et al. 2017, appendix A; Sonnet ``VectorQuantizerEMA``).  The reference repository has no EMA
+    update at all (its codebook is a gradient-trained ParameterList, vector_quantizer.py:44-48, :72-83), so this function
+    pins nothing against the reference - it only pins the CUDA path against an independent statement of the same rule.
+
+    N (K,) cluster sizes, m (K, D) cluster sums, z (n, D) encoder outputs of the step, idx (n,) their codes.
+    Returns (N', m', E')."""
+    K, D = m.shape
+    n = torch.bincount(idx.reshape(-1), minlength=K).to(m.dtype)
+    s = torch.zeros_like(m).index_add_(0, idx.reshape(-1), z.reshape(-1, D).to(m.dtype))
+    N2 = decay * N + (1 - decay) * n
+    m2 = decay * m + (1 - decay) * s
+    tot = N2.sum()
+    Ns = (N2 + eps) / (tot + K * eps) * tot
+    return N2, m2, m2 / Ns.unsqueeze(1)

@@ -258,3 +258,46 @@ def test_index_parity_at_pass_scale(mode):
     T_or = O.upscale(E, prm)
     assert rel_err(zq.view(-1, 32).cpu()[same], T_or[idx32[same]]) < 1e-5
     ops.set_gemm_mode('bf16x3')
+
+
+def test_ema_codebook_option_matches_cpu_restatement():
+    """Optional EMA codebook (north_star extension; the reference has none -> parity unpinned): three trainer steps with
+    ema_decay = 0.9 against the CPU restatement of the rule fed with the product's own z / indices; and the default
+    (ema_decay=None) stays the reference's gradient codebook."""
+    from VQCPCB import ops
+    ops.set_gemm_mode('fp32')
+    cfg = O.default_cfg(codebook_size=64, KL=2, KR=2)
+    prm = P.make_params(cfg, 0)
+    tr = build_product_trainer(cfg)
+    load_params_into(tr, prm)
+    q = tr.encoder.quantizer
+    q.ema_decay = 0.9
+    tr.init_optimizers(1e-4, False)
+    tr.train()
+    E0 = q.embeddings[0].detach().clone()
+    N = torch.ones(64, dtype=torch.float64)
+    m = E0.double().cpu()
+    seen = []
+    orig = q.ema_accumulate
+
+    def spy(flat_z, idx):
+        seen.append((flat_z.detach().reshape(-1, 3).double().cpu(), idx.reshape(-1).cpu()))
+        return orig(flat_z, idx)
+
+    q.ema_accumulate = spy
+    for s in range(3):
+        seen.clear()
+        st = tr.step(P.make_batch(cfg, 6, seed=40 + s), True, False)
+        assert torch.isfinite(st['loss'])
+        z = torch.cat([a for a, _ in seen])
+        ix = torch.cat([b for _, b in seen])
+        assert z.shape[0] == 6 * (cfg.KL + cfg.KR + cfg.N * cfg.KR)
+        N, m, E = O.ema_codebook_update(N, m, z, ix, 0.9, q.ema_eps)
+        assert rel_err(q.embeddings[0], E) < 1e-5, (s, rel_err(q.embeddings[0], E))
+        assert rel_err(q._ema_N, N) < 1e-6
+    assert not torch.equal(E0, q.embeddings[0].detach())
+    assert int(q._ema_cnt.sum()) == 0                       # cleared after the update
+    # default: gradient codebook, no EMA state
+    tr2 = build_product_trainer(cfg)
+    assert tr2.encoder.quantizer.ema_decay is None and tr2.encoder.quantizer._ema_N is None
+    ops.set_gemm_mode('bf16x3')

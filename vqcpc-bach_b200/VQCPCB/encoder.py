@@ -94,6 +94,7 @@ class Encoder(nn.Module):
         table, jac = u.code_table_and_jacobian(codebook)
         y, idx, loss = ops.FusedVQUpscaleFn.apply(z, codebook, table, jac, q._commitment_cost, q.squared_l2_norm,
                                                   q.usage_counts)
+        q.ema_accumulate(z, idx)
         return y, idx, loss
 
     def forward_tokens_indexed(self, x_proc, y_row0, y_rows):
@@ -109,6 +110,7 @@ class Encoder(nn.Module):
         y, idx, loss, token = ops.VQIndexFn.apply(z.reshape(-1, q.codebook_dim), codebook, table, jac, q._commitment_cost,
                                                   q.squared_l2_norm, q.usage_counts, int(y_row0), int(y_rows), link)
         link.token = token
+        q.ema_accumulate(z, idx)
         return y, idx, loss, link
 
     def merge_codes(self, codes):

@@ -365,6 +365,15 @@ def code_hist(idx, counts):
     _native.call('vqcpc_code_hist', _p(idx), idx.numel(), counts.numel(), _p(counts), _stream())
 
 
+def table_scatter_add(idx, rows, out):
+    """out[idx[i]] += rows[i] (rows (n, w) fp32, out (K, w) accumulated): deterministic, no atomics."""
+    idx = idx.reshape(-1)
+    idx = idx if idx.is_contiguous() else idx.contiguous()
+    rows = _f32c(rows)
+    _chk(idx, rows, out)
+    _native.call('vqcpc_table_scatter_add', _p(idx), idx.numel(), _p(rows), rows.shape[1], out.shape[0], _p(out), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ autograd Functions
 def _grad_buf(p):
     """Gradient accumulator of a leaf parameter (allocated zeroed on first use; kernels accumulate in place)."""

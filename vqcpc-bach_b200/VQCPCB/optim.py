@@ -86,7 +86,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         return stats_elems + 2 * count_elems
 
     @torch.no_grad()
-    def all_reduce(self, stats=None, counts=None):
+    def all_reduce(self, stats=None, counts=None, sums=None):
         """The ONE collective of a step: sum all-reduce of [gradients | stats | counts]; returns the gradient scale
         (1 / world_size) the update must apply.  ``stats`` (float tensors) are replaced by their cross-rank mean;
         ``counts`` (integer tensors, e.g. the code-usage histograms) by their cross-rank SUM.  Counts travel through the
@@ -99,7 +99,12 @@ class FusedClipAdam(torch.optim.Optimizer):
         tail = flat.tail
         stats = list(stats or [])
         counts = list(counts or [])
+        sums = [t for t in (sums or []) if t is not None]           # float tensors replaced by their cross-rank SUM
         o = 0
+        for t in sums:
+            assert o + t.numel() <= tail.numel(), 'all-reduce tail too small'
+            tail[o:o + t.numel()].copy_(t.reshape(-1))
+            o += t.numel()
         for t in stats:
             assert o + t.numel() <= tail.numel(), 'all-reduce tail too small'
             tail[o:o + t.numel()].copy_(t.reshape(-1))
@@ -113,6 +118,9 @@ class FusedClipAdam(torch.optim.Optimizer):
             o += 2 * n
         vq_dist.all_reduce_sum(flat.grad_full)
         o = 0
+        for t in sums:
+            t.copy_(tail[o:o + t.numel()].view(t.shape))
+            o += t.numel()
         for t in stats:
             t.copy_(tail[o:o + t.numel()].view(t.shape) / world)
             o += t.numel()
@@ -124,12 +132,12 @@ class FusedClipAdam(torch.optim.Optimizer):
         return 1.0 / world
 
     @torch.no_grad()
-    def step(self, closure=None, max_norm=0.0, stats=None, counts=None):
+    def step(self, closure=None, max_norm=0.0, stats=None, counts=None, sums=None):
         """Clip by global norm ``max_norm`` (0 = no clip) and apply Adam.  ``stats`` = (sums, correct) device tensors and
         ``counts`` = integer code-usage histograms ride in the tail of the all-reduce buffer (stats averaged, counts
         summed across ranks, both in place)."""
         flat = self.flat
-        grad_scale = self.all_reduce(stats, counts)
+        grad_scale = self.all_reduce(stats, counts, sums)
         g = self.param_groups[0]
         self.step_count += 1
         _native.call('vqcpc_grad_sumsq', _p(flat.grad), flat.numel, grad_scale, _p(self.gnorm_sq), _stream())

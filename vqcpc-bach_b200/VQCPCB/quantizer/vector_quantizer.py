@@ -34,7 +34,7 @@ class NoQuantization(VectorQuantizer):
 
 class ProductVectorQuantizer(VectorQuantizer):
     def __init__(self, codebook_size, codebook_dim, commitment_cost, num_codebooks, use_batch_norm, initialize,
-                 squared_l2_norm):
+                 squared_l2_norm, ema_decay=None, ema_eps=1e-5):
         super().__init__()
         assert codebook_dim % num_codebooks == 0
         self.num_codebooks = num_codebooks
@@ -53,6 +53,19 @@ class ProductVectorQuantizer(VectorQuantizer):
         # data parallel: the data-dependent initialisation draws rows of the RANK-LOCAL first batch, so rank 0's draw is
         # broadcast to every replica right after it (False: single-process use inside an initialised process group)
         self.sync_init = True
+        # OPTIONAL exponential-moving-average codebook (BASELINE.json north_star; the reference has NO such update - its
+        # codebook is trained by Adam through q_latent_loss, vector_quantizer.py:72-83 - so this branch has no reference
+        # counterpart: "parity unpinned", checked only against an independent CPU restatement of the same rule in the tests).
+        # ema_decay=None (default) keeps the reference's gradient codebook.  With a decay g in (0, 1) the trainer calls
+        # ``ema_update`` once per optimizer step:  N <- g N + (1 - g) n,  m <- g m + (1 - g) sum_{idx = k} z,
+        # E = m / ((N + eps) / (sum N + K eps) * sum N)   (Laplace-smoothed cluster sizes), where the per-step counts n and
+        # sums ride in the step's single all-reduce under data parallelism; the codebook then receives no gradient step.
+        self.ema_decay = ema_decay
+        self.ema_eps = ema_eps
+        self._ema_N = None            # (Kc,) fp32 cluster sizes
+        self._ema_m = None            # (Kc, D) fp32 cluster sums
+        self._ema_cnt = None          # (Kc,) int32 counts of the current step (all passes)
+        self._ema_sum = None          # (Kc, D) fp32 sums of the current step
         # running GLOBAL code-usage histogram (int64, codebook_size): the trainer adds the cross-rank sum of every training
         # step's counts, i.e. the vector the per-step all-reduce carries
         self.global_usage = None
@@ -60,6 +73,50 @@ class ProductVectorQuantizer(VectorQuantizer):
     def track_usage(self, enable=True):
         dev = self.embeddings[0].device
         self.usage_counts = torch.zeros(self.num_codebooks * self.codebook_size, dtype=torch.int32, device=dev) if enable else None
+
+    # ---- EMA codebook (optional extension, see __init__) -------------------------------------------------------------
+    def _ema_buffers(self):
+        E = self.embeddings[0]
+        if self._ema_N is None or self._ema_N.device != E.device:
+            assert self.num_codebooks == 1, 'the EMA codebook supports a single codebook'
+            self._ema_N = torch.ones(self.codebook_size, dtype=torch.float32, device=E.device)
+            self._ema_m = E.detach().clone().float()
+            self._ema_cnt = torch.zeros(self.codebook_size, dtype=torch.int32, device=E.device)
+            self._ema_sum = torch.zeros(self.codebook_size, self.codebook_dim, dtype=torch.float32, device=E.device)
+
+    def ema_accumulate(self, flat_z, idx):
+        """Add this pass's per-code counts and sums of z (training mode only)."""
+        if self.ema_decay is None or not self.training:
+            return
+        self._ema_buffers()
+        with torch.no_grad():
+            z = flat_z.detach().reshape(-1, self.codebook_dim)
+            z = z if z.is_contiguous() else z.contiguous()
+            ix = idx.reshape(-1)
+            ops.code_hist(ix, self._ema_cnt)
+            ops.table_scatter_add(ix, z, self._ema_sum)
+
+    def ema_step_tensors(self):
+        """(float sums, int counts) of the current step for the data-parallel all-reduce, or (None, None)."""
+        if self.ema_decay is None or self._ema_cnt is None:
+            return None, None
+        return self._ema_sum, self._ema_cnt
+
+    @torch.no_grad()
+    def ema_update(self):
+        """Apply the EMA update from the (already cross-rank summed) counts / sums of the step and clear them."""
+        if self.ema_decay is None or self._ema_cnt is None:
+            return
+        g, eps, K = float(self.ema_decay), float(self.ema_eps), self.codebook_size
+        n = self._ema_cnt.float()
+        self._ema_N.mul_(g).add_(n, alpha=1.0 - g)
+        self._ema_m.mul_(g).add_(self._ema_sum, alpha=1.0 - g)
+        tot = self._ema_N.sum()
+        Ns = (self._ema_N + eps) / (tot + K * eps) * tot
+        self.embeddings[0].data.copy_(self._ema_m / Ns.unsqueeze(1))
+        self._ema_cnt.zero_()
+        self._ema_sum.zero_()
+        ops.bump_weight_version()
 
     def _initialize(self, flat_input):
         """Data-dependent init: random rows of the first batch become the codebook (vector_quantizer.py:57-70)."""
@@ -74,6 +131,9 @@ class ProductVectorQuantizer(VectorQuantizer):
             # every rank reaches this point on its first forward (quirk Q5), so the collective is matched
             vq_dist.broadcast_parameters(list(self.embeddings), src=0)
         self.initialize = False
+        if self.ema_decay is not None:
+            self._ema_N = None                 # cluster statistics restart from the freshly drawn codes
+            self._ema_buffers()
         ops.bump_weight_version()
 
     def forward(self, inputs, corrupt_labels=False, **kwargs):
@@ -91,4 +151,5 @@ class ProductVectorQuantizer(VectorQuantizer):
                 given = torch.where(keep, idx, rnd)
         zsg, idx, loss = ops.QuantizeFn.apply(flat, given, self._commitment_cost, self.squared_l2_norm, self.usage_counts,
                                               *self.embeddings)
+        self.ema_accumulate(flat, idx)
         return zsg.view(shp), idx.view(*shp[:-1], self.num_codebooks), loss.view(shp[:-1])

@@ -103,8 +103,10 @@ class VQCPCEncoderTrainer(EncoderTrainer):
 
     def _tail_size(self):
         """[loss sums (3) | accuracy counts (KR) | code-usage histograms of the positive and the negative blocks]"""
-        kc = getattr(self.encoder.quantizer, 'codebook_size', 0)
-        return FusedClipAdam.tail_elems(3 + self.dataloader_generator.num_blocks_right, 2 * kc) + 4
+        q = self.encoder.quantizer
+        kc = getattr(q, 'codebook_size', 0)
+        ema = kc * (1 + q.codebook_dim) if getattr(q, 'ema_decay', None) is not None else 0     # EMA sums + counts
+        return FusedClipAdam.tail_elems(3 + self.dataloader_generator.num_blocks_right + ema, 2 * kc + ema) + 4
 
     def to(self, device):
         for m in self._modules_in_order():
@@ -263,7 +265,15 @@ class VQCPCEncoderTrainer(EncoderTrainer):
 
         if train:
             # :313-314 (+ the one all-reduce: gradients | loss/accuracy sums | code counts)
-            self.optimizer.step(max_norm=self.max_grad_norm, stats=(sums, correct), counts=[hist] if hist is not None else None)
+            ema_sum, ema_cnt = q.ema_step_tensors() if hasattr(q, 'ema_step_tensors') else (None, None)
+            if ema_cnt is not None:
+                for e in q.embeddings:                  # EMA codebook: no gradient step on the codes
+                    if e.grad is not None:
+                        e.grad.zero_()
+            counts = ([hist] if hist is not None else []) + ([ema_cnt] if ema_cnt is not None else [])
+            self.optimizer.step(max_norm=self.max_grad_norm, stats=(sums, correct), counts=counts or None, sums=[ema_sum])
+            if ema_cnt is not None:
+                q.ema_update()
             ops.bump_weight_version()
             if hist is not None:
                 if q.global_usage is None or q.global_usage.device != hist.device:
