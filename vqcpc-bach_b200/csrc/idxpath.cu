@@ -867,9 +867,13 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
     for (int d = 0; d < DS; ++d) accE[a][d] = 0.f;
   bool j_ready = !p.j_smem;
   const int64_t nchunk = (p.n + VCH - 1) / VCH;
+  const long long tb0 = clock64();
+  long long tb_p1 = 0, tb_scan = 0, tb_sc = 0, tb_ld = 0, tb_j = 0, tb_p4 = 0;
   VqVec<DS> cur = vq_vec_load<DS>(p, (int64_t)blockIdx.x * VCH + tid);
   __syncthreads();
+  const long long tb1 = clock64();
   for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    long long tq = clock64();
     // ---- phase 1: thread == vector: loss gradients, source row of the upscaled-side gradient, histogram
     {
       float g[DS];
@@ -900,6 +904,7 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
     // next pass's inputs: in flight until the next phase 1
     cur = vq_vec_load<DS>(p, (ch + gridDim.x) * VCH + tid);
     __syncthreads();
+    { const long long t1 = clock64(); tb_p1 += t1 - tq; tq = t1; }
     // ---- phase 2: exclusive scan of the histogram (Kc <= 2 * VCH bins, two per thread)
     {
       const int b0 = 2 * tid, b1 = 2 * tid + 1;
@@ -919,11 +924,13 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       if (b1 < p.Kc) { start_s[b1] = ex + h0; cur_s[b1] = ex + h0; hist_s[b1] = 0; }
     }
     __syncthreads();
+    { const long long t1 = clock64(); tb_scan += t1 - tq; tq = t1; }
     // ---- phase 3: scatter the vector slots into code order
     {
       const int code = code_s[tid];
       if (code != 0xFFFF) perm_s[atomicAdd(&cur_s[code], 1)] = (uint16_t)tid;
     }
+    { const long long t1 = clock64(); tb_sc += t1 - tq; tq = t1; }
     // ---- phase J (needs phase 1 only): a quad of lanes per vector: dz = coef * J[code]^T v - beta * g_loss * dloss/dq.
     // All source rows of the four passes are requested first, then consumed.
     const int ql = tid & 3, qid = tid >> 2;
@@ -951,6 +958,7 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
       j_ready = true;
     }
+    { const long long t1 = clock64(); tb_ld += t1 - tq; tq = t1; }
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
       const int i = pass * (VCH / 4) + qid;
@@ -984,6 +992,7 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       }
     }
     __syncthreads();
+    { const long long t1 = clock64(); tb_j += t1 - tq; tq = t1; }
     // ---- phase 4: thread == code: sequential sum over the code's vectors of this pass (no atomics)
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -998,6 +1007,7 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
       }
     }
     __syncthreads();
+    { const long long t1 = clock64(); tb_p4 += t1 - tq; tq = t1; }
   }
   if (p.dE) {
 #pragma unroll
@@ -1008,6 +1018,10 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
         for (int d = 0; d < DS; ++d)
           if (accE[a][d] != 0.f) atomicAdd(p.dE + code * DS + d, accE[a][d]);
     }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    g_idx_dbg[0] = tb1 - tb0; g_idx_dbg[1] = clock64() - tb1; g_idx_dbg[2] = tb_p1; g_idx_dbg[3] = tb_scan; g_idx_dbg[4] = tb_sc;
+    g_idx_dbg[5] = tb_ld; g_idx_dbg[6] = tb_j; g_idx_dbg[7] = tb_p4;
   }
 }
 

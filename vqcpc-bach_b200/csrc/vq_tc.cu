@@ -374,22 +374,24 @@ vq_tc_fwd_kernel(VtParams p) {
             TICK(acc_w);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CH);
+            // software pipeline over the eight 32-column chunks of the stage: the TMEM load of chunk j + 1 is in flight
+            // while chunk j is reduced (tcgen05.wait::ld waits for everything outstanding, so the wait sits after the
+            // reduction of the previous chunk)
+            uint32_t rb[2][32];
+            tmem_ld32(taddr, rb[0]);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < CH / 64; ++j) {
-              uint32_t r0[32], r1[32];
-              tmem_ld32(taddr + j * 64, r0);
-              tmem_ld32(taddr + j * 64 + 32, r1);
-              tmem_ld_wait();
+            for (int j = 0; j < CH / 32; ++j) {
+              uint32_t* r0 = rb[j & 1];
+              if (j + 1 < CH / 32) tmem_ld32(taddr + (j + 1) * 32, rb[(j + 1) & 1]);
               if (DBG && p.dbg && ok) {
-                float* drow = p.dbg + (size_t)row * p.dbg_ld + c * CH + j * 64;
+                float* drow = p.dbg + (size_t)row * p.dbg_ld + c * CH + j * 32;
 #pragma unroll
-                for (int t = 0; t < 32; ++t) { drow[t] = __uint_as_float(r0[t]); drow[32 + t] = __uint_as_float(r1[t]); }
+                for (int t = 0; t < 32; ++t) drow[t] = __uint_as_float(r0[t]);
               }
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                gm[h * NG + j * 8 + t] = max8(r0 + t * 8);
-                gm[h * NG + j * 8 + 4 + t] = max8(r1 + t * 8);
-              }
+              for (int t = 0; t < 4; ++t) gm[h * NG + j * 4 + t] = max8(r0 + t * 8);
+              if (j + 1 < CH / 32) tmem_ld_wait();
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -400,18 +402,26 @@ vq_tc_fwd_kernel(VtParams p) {
             for (int t = 0; t < NG; ++t) gm[h * NG + t] = -INFINITY;
           }
         }
-        float cmax = gm[0];
+        // maximum of the 64 group maxima as a tree (depth 4 instead of a 32-long dependent chain)
+        float tm[22];
 #pragma unroll
-        for (int t = 1; t + 1 < 2 * NG; t += 2) cmax = fmax3(cmax, gm[t], gm[t + 1]);
-        cmax = fmaxf(cmax, gm[2 * NG - 1]);
+        for (int t = 0; t < 21; ++t) tm[t] = fmax3(gm[3 * t], gm[3 * t + 1], gm[3 * t + 2]);
+        tm[21] = gm[63];
+        float tn[8];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) tn[t] = fmax3(tm[3 * t], tm[3 * t + 1], tm[3 * t + 2]);
+        tn[7] = tm[21];
+        const float cmax = fmax3(fmax3(tn[0], tn[1], tn[2]), fmax3(tn[3], tn[4], tn[5]), fmaxf(tn[6], tn[7]));
         runmax = fmaxf(runmax, cmax);
         const float thr = runmax - margin;
-        uint32_t mlo = 0, mhi = 0;
+        // candidate masks: four independent accumulators per half instead of one 32-long LOP3 chain
+        uint32_t ml[4] = {0, 0, 0, 0}, mh[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int t = 0; t < NG; ++t) {
-          mlo = mask_ge(mlo, gm[t], thr, 1u << t);
-          mhi = mask_ge(mhi, gm[NG + t], thr, 1u << t);
+          ml[t & 3] = mask_ge(ml[t & 3], gm[t], thr, 1u << t);
+          mh[t & 3] = mask_ge(mh[t & 3], gm[NG + t], thr, 1u << t);
         }
+        uint32_t mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]), mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]);
         if (scan_all || !(cmax == cmax)) { mlo = mhi = 0xFFFFFFFFu; ++n_full; }      // NaN / inf / overflow: scan all
         if (!ok) mlo = mhi = 0u;
         TICK(acc_m);
