@@ -411,8 +411,8 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
   const int PW = q.PW, kpad = q.kpad, MT = kpad >> 7;
   const uint32_t A_BYTES = (uint32_t)kpad * 32, STAGE = 2 * A_BYTES + 2048;       // A_hi | A_lo | B_hi (1 KB) | B_lo (1 KB)
   uint8_t* stages = smem;                                                           // [NST][STAGE]
-  float* T_s = reinterpret_cast<float*>(stages + q.stage_region);                   // [Kc][TST]
-  float* W_s = T_s + (size_t)p.Kc * TST;                                            // [KR][32 c][TST]  W_s[k][c][z] = W[z][c][k]
+  float* T_s = reinterpret_cast<float*>(stages + q.stage_region);                   // [Kc][32] (read lane = feature: no padding needed)
+  float* W_s = T_s + (size_t)p.Kc * IZ;                                             // [KR][32 c][TST]  W_s[k][c][z] = W[z][c][k]
   float* coef_s = W_s + (size_t)p.KR * IZ * TST;                                    // [PW][16]
   int* code_s = reinterpret_cast<int*>(coef_s + PW * 16);                           // [PW][16]
   float* du_s = reinterpret_cast<float*>(code_s + PW * 16);                         // [PW][32]
@@ -437,7 +437,16 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  stage_table_bulk(T_s, p.T, p.Kc, BART);            // overlaps the zero fill, the W staging and the first operand columns
+  if (threadIdx.x == 0) {                            // the table in its global layout: a few large bulk copies, overlapping
+    const uint32_t bytes = (uint32_t)p.Kc * IZ * 4;  // the zero fill, the W staging and the first operand columns
+    mbar_expect_tx(BART, bytes);
+    for (uint32_t o = 0; o < bytes; o += 16384) {
+      const uint32_t nb = min(16384u, bytes - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(T_s) + o),
+                   "l"(reinterpret_cast<const char*>(p.T) + o), "r"(nb), "r"(BART)
+                   : "memory");
+    }
+  }
   if (warp == PW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(q.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -585,10 +594,10 @@ __global__ void __launch_bounds__(544, 1) nce_idx_bwd_tc_kernel(NceBwdTcP q) {
       for (int n4 = 0; n4 < 4; ++n4) {
         const int4 cd = *reinterpret_cast<const int4*>(cds + n4 * 4);
         const float4 c4 = *reinterpret_cast<const float4*>(cfs + n4 * 4);
-        du0 = fmaf(c4.x, T_s[cd.x * TST + lane], du0);
-        du1 = fmaf(c4.y, T_s[cd.y * TST + lane], du1);
-        du0 = fmaf(c4.z, T_s[cd.z * TST + lane], du0);
-        du1 = fmaf(c4.w, T_s[cd.w * TST + lane], du1);
+        du0 = fmaf(c4.x, T_s[cd.x * IZ + lane], du0);
+        du1 = fmaf(c4.y, T_s[cd.y * IZ + lane], du1);
+        du0 = fmaf(c4.z, T_s[cd.z * IZ + lane], du0);
+        du1 = fmaf(c4.w, T_s[cd.w * IZ + lane], du1);
       }
       dus[lane] = du0 + du1;
       __syncwarp();
@@ -762,7 +771,9 @@ struct IdxSeg {
   int kind;                   // 1: dy rows a[(p - row0) * 32 ..];  2: a[p - row0] * b[((p - row0) / per_b * KR + (p - row0) % KR) * 32 ..]
   const float *a, *b;
   int per_b, KR;
+  unsigned long long m_per_b, m_kr;   // ceil(2^40 / d): x / d == (x * m) >> 40 for x < 2^30, d < 1024 (two instructions)
 };
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, unsigned long long m) { return (uint32_t)(((unsigned long long)x * m) >> 40); }
 struct VqIdxBwdP {
   const float *x, *E, *J, *gl;
   const int64_t* idx;
@@ -1025,6 +1036,284 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Production split of the quantizer backward (the single kernel above is kept as VQCPC_VQ_BWD_ALGO=1 / fallback):
+//   vq_idx_dz_kernel : pure stream, a quad of lanes per vector, no shared-memory staging and no CTA barrier after set-up:
+//                      dz = coef * J[code]^T v - beta * g_loss * dloss/dq, plus the vector reductions of the dense rows into dT.
+//                      Everything a vector needs from global memory (code, z, g_loss, coefficient, source row) is fetched one
+//                      iteration ahead.
+//   vq_idx_de_kernel : dE[code] += g_loss * dloss/dq by a counting sort of a large slab of vectors per CTA (8 per thread) and
+//                      per-code sequential sums - small shared-memory footprint, so the slab is big enough (4096 vectors
+//                      over <= 1024 codes) for the sort to pay.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DS, bool JS>      // JS: J staged in shared memory (compile-time, so that its reads are LDS, not generic loads)
+__global__ void __launch_bounds__(512, 1) vq_idx_dz_kernel(VqIdxBwdP p) {
+  constexpr int JROW = IZ * DS, JST = JROW + 4, ES = 4;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* J_s = reinterpret_cast<float*>(smraw);                                        // [Kc][JST] (if j_smem)
+  float* E_s = J_s + (JS ? (size_t)p.Kc * JST : 0);                                      // [Kc][4]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(E_s + (size_t)p.Kc * ES);
+  IdxSeg* seg_s = reinterpret_cast<IdxSeg*>(bar + 1);                                    // [4] shared-memory copy (dynamic index)
+  const int tid = threadIdx.x;
+  const uint32_t bar_a = s_u32(bar);
+  if (tid < 4) seg_s[tid] = p.seg[tid];
+  if (JS) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(p.Kc * JROW * 4)) : "memory");
+    __syncthreads();
+    for (int kx = tid; kx < p.Kc; kx += blockDim.x)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(J_s + (size_t)kx * JST)),
+                   "l"(p.J + (size_t)kx * JROW), "r"((uint32_t)(JROW * 4)), "r"(bar_a)
+                   : "memory");
+  }
+  for (int i = tid; i < p.Kc; i += blockDim.x) {
+#pragma unroll
+    for (int d = 0; d < ES; ++d) E_s[i * ES + d] = d < DS ? __ldg(p.E + i * DS + d) : 0.f;
+  }
+  __syncthreads();
+  const int ql = tid & 3;
+  const int64_t nquads = (int64_t)gridDim.x * (blockDim.x >> 2);
+  int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 2) + (tid >> 2);
+  // one-ahead fetch: code, g_loss, z, coefficient, 32 bytes of the source row (this lane's 8 features)
+  int code_n = 0;
+  uint32_t seg_n = 4;                                 // 4 = no source row
+  float gl_n = 0.f, cf_n = 0.f, x_n[DS];
+  float4 va_n = make_float4(0.f, 0.f, 0.f, 0.f), vb_n = va_n;
+  auto fetch = [&](int64_t vv) {
+    seg_n = 4;
+    cf_n = gl_n = 0.f;
+    code_n = 0;
+    va_n = vb_n = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < DS; ++d) x_n[d] = 0.f;
+    if (vv >= p.n) return;
+    code_n = (int)ldg_now(p.idx + vv);
+    gl_n = p.gl ? ldg_now(p.gl + vv) : 0.f;
+#pragma unroll
+    for (int d = 0; d < DS; ++d) x_n[d] = ldg_now(p.x + vv * DS + d);
+    const uint32_t v32 = (uint32_t)vv;
+    // which segment (at most one) holds this vector: a short compare chain on constant-bank operands ...
+    uint32_t sgi = 4, pl = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t d = v32 - (uint32_t)p.seg[t].row0;
+      if (t < p.nseg && d < (uint32_t)p.seg[t].rows) { sgi = t; pl = d; }
+    }
+    // ... then ONE copy of the source-row code, its descriptor read from shared memory
+    if (sgi < 4) {
+      const IdxSeg& sg = seg_s[sgi];
+      uint32_t row = pl;
+      cf_n = 1.f;
+      const float* base = sg.a;
+      if (sg.kind != 1) {
+        const uint32_t bq = fast_div(pl, sg.m_per_b), kq = fast_div(pl, sg.m_kr);
+        row = bq * (uint32_t)sg.KR + (pl - kq * (uint32_t)sg.KR);
+        cf_n = ldg_now(sg.a + pl);
+        base = sg.b;
+      }
+      seg_n = sgi;
+      const float* src = base + row * IZ + ql * 8;
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va_n.x), "=f"(va_n.y), "=f"(va_n.z), "=f"(va_n.w) : "l"(src));
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb_n.x), "=f"(vb_n.y), "=f"(vb_n.z), "=f"(vb_n.w) : "l"(src + 4));
+    }
+  };
+  fetch(v);
+  if (JS) {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+  }
+  const int qw = (tid >> 2) & 7;                      // whole warps stay in the loop together (shuffles below):
+  for (; v - qw < p.n; v += nquads) {                 // v - qw is the first vector of the warp, the same on all 32 lanes
+    const bool ok = v < p.n;
+    const int code = min(max(code_n, 0), p.Kc - 1);
+    const uint32_t sgi = seg_n;
+    const float gl = gl_n, cf = cf_n;
+    float x[DS];
+#pragma unroll
+    for (int d = 0; d < DS; ++d) x[d] = x_n[d];
+    const float vv8[8] = {va_n.x, va_n.y, va_n.z, va_n.w, vb_n.x, vb_n.y, vb_n.z, vb_n.w};
+    fetch(v + nquads);
+    // loss-side gradient of this vector (all four lanes of the quad compute it: cheaper than a shuffle)
+    float g[DS];
+    {
+      float df[DS];
+      float ssq = 0.f;
+#pragma unroll
+      for (int d = 0; d < DS; ++d) {
+        df[d] = E_s[code * ES + d] - x[d];
+        const float t = df[d] + 1e-5f;
+        ssq = fmaf(t, t, ssq);
+      }
+      const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
+#pragma unroll
+      for (int d = 0; d < DS; ++d) g[d] = gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
+    }
+    float gz[DS];
+#pragma unroll
+    for (int d = 0; d < DS; ++d) gz[d] = 0.f;
+    if (sgi < 4) {
+#pragma unroll
+      for (int q4 = 0; q4 < 2 * DS; ++q4) {
+        const float4 t = JS ? *reinterpret_cast<const float4*>(J_s + code * JST + ql * 8 * DS + q4 * 4)
+                            : __ldg(reinterpret_cast<const float4*>(p.J + (size_t)code * JROW + ql * 8 * DS + q4 * 4));
+        const float jv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int f = q4 * 4 + e;                  // flat index (feature t, component d) = t * DS + d
+          gz[f % DS] = fmaf(vv8[f / DS], jv[e], gz[f % DS]);
+        }
+      }
+      if (ok && p.dT && ((p.kind1_mask >> sgi) & 1u)) {
+        float* t = p.dT + (size_t)code * IZ + ql * 8;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t), "f"(vv8[0]), "f"(vv8[1]), "f"(vv8[2]), "f"(vv8[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t + 4), "f"(vv8[4]), "f"(vv8[5]), "f"(vv8[6]), "f"(vv8[7]) : "memory");
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DS; ++d) {
+      gz[d] += __shfl_xor_sync(FULL, gz[d], 1);
+      gz[d] += __shfl_xor_sync(FULL, gz[d], 2);
+    }
+    if (ok && ql < DS) {
+      float mine = gz[0], gm = g[0];
+#pragma unroll
+      for (int d = 1; d < DS; ++d) {
+        mine = (ql == d) ? gz[d] : mine;
+        gm = (ql == d) ? g[d] : gm;
+      }
+      p.dx[v * DS + ql] = fmaf(cf, mine, -p.beta * gm);
+    }
+  }
+}
+
+constexpr int DE_T = 512, DE_V = 8, DE_CH = DE_T * DE_V;     // dE kernel: threads, vectors per thread, slab
+template <int DS>
+__global__ void __launch_bounds__(DE_T, 2) vq_idx_de_kernel(VqIdxBwdP p) {
+  constexpr int ES = 4;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* E_s = reinterpret_cast<float*>(smraw);                                          // [Kc][4]
+  float* gdq_s = E_s + (size_t)p.Kc * ES;                                                // [DE_CH][DS]
+  int* hist_s = reinterpret_cast<int*>(gdq_s + DE_CH * DS);                              // [Kc]
+  int* start_s = hist_s + p.Kc;                                                          // [Kc]
+  int* cur_s = start_s + p.Kc;                                                           // [Kc]
+  int* wsum_s = cur_s + p.Kc;                                                            // [32]
+  uint16_t* code_s = reinterpret_cast<uint16_t*>(wsum_s + 32);                           // [DE_CH]
+  uint16_t* perm_s = code_s + DE_CH;                                                     // [DE_CH]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < p.Kc; i += DE_T) {
+    hist_s[i] = 0;
+#pragma unroll
+    for (int d = 0; d < ES; ++d) E_s[i * ES + d] = d < DS ? __ldg(p.E + i * DS + d) : 0.f;
+  }
+  float accE[2][DS];                                 // thread t owns the codes t and t + DE_T
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int d = 0; d < DS; ++d) accE[a][d] = 0.f;
+  __syncthreads();
+  const int64_t nchunk = (p.n + DE_CH - 1) / DE_CH;
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+    // ---- all global reads of the slab first (8 vectors per thread, coalesced), then the loss gradients
+    int codes[DE_V];
+    float gl[DE_V], x[DE_V][DS];
+#pragma unroll
+    for (int j = 0; j < DE_V; ++j) {
+      const int64_t v = ch * DE_CH + j * DE_T + tid;
+      codes[j] = -1;
+      gl[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < DS; ++d) x[j][d] = 0.f;
+      if (v < p.n) {
+        codes[j] = (int)ldg_now(p.idx + v);
+        gl[j] = p.gl ? ldg_now(p.gl + v) : 0.f;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) x[j][d] = ldg_now(p.x + v * DS + d);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DE_V; ++j) {
+      const int i = j * DE_T + tid;
+      int code = 0xFFFF;
+      float g[DS];
+#pragma unroll
+      for (int d = 0; d < DS; ++d) g[d] = 0.f;
+      if (ch * DE_CH + i < p.n) {
+        code = min(max(codes[j], 0), p.Kc - 1);
+        float df[DS];
+        float ssq = 0.f;
+#pragma unroll
+        for (int d = 0; d < DS; ++d) {
+          df[d] = E_s[code * ES + d] - x[j][d];
+          const float t = df[d] + 1e-5f;
+          ssq = fmaf(t, t, ssq);
+        }
+        const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
+#pragma unroll
+        for (int d = 0; d < DS; ++d) g[d] = gl[j] * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
+        atomicAdd(&hist_s[code], 1);
+      }
+#pragma unroll
+      for (int d = 0; d < DS; ++d) gdq_s[i * DS + d] = g[d];
+      code_s[i] = (uint16_t)code;
+    }
+    __syncthreads();
+    // ---- exclusive scan of the histogram (Kc <= 2 * DE_T bins, two per thread)
+    {
+      const int b0 = 2 * tid, b1 = 2 * tid + 1;
+      const int h0 = b0 < p.Kc ? hist_s[b0] : 0, h1 = b1 < p.Kc ? hist_s[b1] : 0;
+      int incl = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) wsum_s[warp] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; ++w) base += wsum_s[w];
+      const int ex = base + incl - (h0 + h1);
+      if (b0 < p.Kc) { start_s[b0] = ex; cur_s[b0] = ex; hist_s[b0] = 0; }
+      if (b1 < p.Kc) { start_s[b1] = ex + h0; cur_s[b1] = ex + h0; hist_s[b1] = 0; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < DE_V; ++j) {
+      const int i = j * DE_T + tid;
+      const int code = code_s[i];
+      if (code != 0xFFFF) perm_s[atomicAdd(&cur_s[code], 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+    // ---- thread == code: sequential sum over the code's vectors of the slab (no atomics)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int code = tid + a * DE_T;
+      if (code < p.Kc) {
+        const int e = cur_s[code];
+        for (int t = start_s[code]; t < e; ++t) {
+          const int i = perm_s[t];
+#pragma unroll
+          for (int d = 0; d < DS; ++d) accE[a][d] += gdq_s[i * DS + d];
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int code = tid + a * DE_T;
+    if (code < p.Kc)
+#pragma unroll
+      for (int d = 0; d < DS; ++d)
+        if (accE[a][d] != 0.f) atomicAdd(p.dE + code * DS + d, accE[a][d]);
+  }
+}
+
 template <int DS>
 size_t vq_idx_bwd_smem(int Kc, bool j_smem) {
   size_t s = j_smem ? (size_t)Kc * (IZ * DS + 4) * 4 : 0;
@@ -1121,7 +1410,7 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   q.stage_region = (uint32_t)std::max<size_t>((size_t)NST * (2 * (size_t)q.kpad * 32 + 2048), (size_t)warps * IZ * IZ * 4);
   q.stage_region = (q.stage_region + 1023u) & ~1023u;
   const size_t tc_smem = 1024 + (size_t)q.stage_region +
-                         ((size_t)Kc * TST + (size_t)KR * IZ * TST + (size_t)warps * (32 + IZ)) * 4 + (2 * NST + 2) * 8 + 16;
+                         ((size_t)Kc * IZ + (size_t)KR * IZ * TST + (size_t)warps * (32 + IZ)) * 4 + (2 * NST + 2) * 8 + 16;
   if (force_simt != 1 && tc_smem <= 227 * 1024 && q.tmem_cols <= 512) {
     q.b = p;
     VQ_CUDA_CALL(cudaFuncSetAttribute(nce_idx_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
@@ -1178,10 +1467,43 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
                  "vq_idx_bwd: segment %d out of range", i);
     VQ_CHECK_ARG(seg_kind[i] == 1 || (seg_per_b[i] >= 1 && KR >= 1 && seg_per_b[i] % KR == 0), "vq_idx_bwd: segment %d: bad per_b / KR", i);
     VQ_CHECK_ARG((((uintptr_t)seg_a[i] | (uintptr_t)(seg_kind[i] == 2 ? seg_b[i] : nullptr)) & 15) == 0, "vq_idx_bwd: segment %d: sources must be 16-byte aligned", i);
-    p.seg[i] = IdxSeg{seg_row0[i], seg_rows[i], seg_kind[i], seg_a[i], seg_kind[i] == 2 ? seg_b[i] : nullptr, seg_kind[i] == 2 ? seg_per_b[i] : 1, KR};
+    const int pb = seg_kind[i] == 2 ? seg_per_b[i] : 1;
+    VQ_CHECK_ARG(pb < 1024 && KR < 1024, "vq_idx_bwd: per_b / KR too large");
+    p.seg[i] = IdxSeg{seg_row0[i], seg_rows[i], seg_kind[i], seg_a[i], seg_kind[i] == 2 ? seg_b[i] : nullptr, pb, KR,
+                      ((1ull << 40) + pb - 1) / pb, ((1ull << 40) + KR - 1) / KR};
     if (seg_kind[i] == 1) p.kind1_mask |= 1u << i;
   }
   cudaStream_t st = vq_stream(stream);
+  static const int algo = getenv("VQCPC_VQ_BWD_ALGO") ? atoi(getenv("VQCPC_VQ_BWD_ALGO")) : 0;    // 1: the single-kernel version
+  if (algo != 1) {
+    // production: streaming dz kernel + counting-sort dE kernel
+#define VQ_IB2(DSV)                                                                                                           \
+  do {                                                                                                                        \
+    const size_t js_bytes = (size_t)Kc * (IZ * DSV + 4) * 4, tail = (size_t)Kc * 16 + 8 + 4 * sizeof(IdxSeg) + 8;                            \
+    const bool js = (((uintptr_t)J & 15) == 0) && js_bytes + tail <= 227 * 1024;                                              \
+    p.j_smem = js ? 1 : 0;                                                                                                    \
+    const size_t smem = (js ? js_bytes : 0) + tail;                                                                           \
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 128), vq_sm_count()));                            \
+    if (js) {                                                                                                                 \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      vq_idx_dz_kernel<DSV, true><<<grid, 512, smem, st>>>(p);                                                                \
+    } else {                                                                                                                  \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      vq_idx_dz_kernel<DSV, false><<<grid, 512, smem, st>>>(p);                                                               \
+    }                                                                                                                         \
+    VQ_CUDA_LAUNCH_CHECK("vq_idx_dz_kernel");                                                                                 \
+    if (d_E) {                                                                                                                \
+      const size_t smem2 = (size_t)Kc * 16 + (size_t)DE_CH * DSV * 4 + ((size_t)3 * Kc + 32) * 4 + (size_t)DE_CH * 4 + 16;    \
+      const int grid2 = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, DE_CH), 2 * (int64_t)vq_sm_count()));          \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_de_kernel<DSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));     \
+      vq_idx_de_kernel<DSV><<<grid2, DE_T, smem2, st>>>(p);                                                                   \
+      VQ_CUDA_LAUNCH_CHECK("vq_idx_de_kernel");                                                                               \
+    }                                                                                                                         \
+  } while (0)
+    if (D == 3) VQ_IB2(3); else VQ_IB2(4);
+#undef VQ_IB2
+    return VQ_OK;
+  }
   const int64_t nchunk = vq_cdiv(n, VCH);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nchunk, vq_sm_count()));
 #define VQ_IB(DSV)                                                                                                            \

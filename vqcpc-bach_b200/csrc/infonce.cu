@@ -317,6 +317,7 @@ infonce_stream_fwd_kernel(NceParams p) {
     float4 wv[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(p.W) + threadIdx.x + j * NCE_THREADS);
+    __syncwarp();                                      // (lane 0 of each team initialised barriers: reconverge first - synccheck)
     __syncthreads();                                   // barriers initialised
     if (tt == 0)
       for (int i = 0; i < p.nst - 1; ++i) issue(i);
@@ -482,6 +483,7 @@ infonce_stream_bwd_kernel(NceBwdParams p) {
     float4 wv[PER];
 #pragma unroll
     for (int j = 0; j < PER; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(p.W) + threadIdx.x + j * NCE_THREADS);
+    __syncwarp();                                      // (lane 0 of each team initialised barriers: reconverge first - synccheck)
     __syncthreads();                                   // barriers initialised
     if (tt == 0)
       for (int i = 0; i < p.nst - 1; ++i) issue(i);
