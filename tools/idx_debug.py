@@ -86,5 +86,5 @@ pb = (ctypes.c_void_p * 3)(u.data_ptr(), 0, u.data_ptr())
 step('vq_idx_bwd', lambda: _native.call('vqcpc_vq_idx_bwd', p_(z), P, D, p_(E), p_(J), Kc, zd, p_(idx), 0.25, 1, p_(gl), 3, row0, rows, kind, pa, pb,
                                          per_b, KR, p_(dz), p_(dE), p_(dT), st()))
 _native.call('vqcpc_idx_debug_read', dbg)
-print('vq_idx_bwd dbg [setup, loop+end, phase1, scan, scatter, row loads, J, phase4]:', list(dbg)[:8], flush=True)
+print('vq_idx_dz dbg [setup, J wait, loop]:', list(dbg)[:3], flush=True)
 print('all ok')

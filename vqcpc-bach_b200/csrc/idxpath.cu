@@ -33,17 +33,6 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return smem_u32(p); }
 
-// asynchronous staging of the (Kc, 32) table into padded rows: one 128-byte bulk copy per row, completion on `bar`
-// (initialised by the caller with count 1; thread 0 posts the expected byte count).  Needs a 16-byte aligned T.
-__device__ __forceinline__ void stage_table_bulk(float* T_s, const float* __restrict__ T, int Kc, uint32_t bar) {
-  if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)Kc * IZ * 4);
-  __syncthreads();
-  for (int r = threadIdx.x; r < Kc; r += blockDim.x)
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(T_s + r * TST)),
-                 "l"(T + (size_t)r * IZ), "r"(128u), "r"(bar)
-                 : "memory");
-}
-
 // W (z, c, k) -> W_s[k][row][col]: row = z, col = c (ZMAJOR: u = W_k c) or row = c, col = z (dc = W_k^T du); padded rows.
 // One (z, c) pair per thread step: KR consecutive floats in, KR scattered stores out.
 template <bool ZMAJOR>
@@ -1046,15 +1035,28 @@ __global__ void __launch_bounds__(VCH, 1) vq_idx_bwd_kernel(VqIdxBwdP p) {
 //                      per-code sequential sums - small shared-memory footprint, so the slab is big enough (4096 vectors
 //                      over <= 1024 codes) for the sort to pay.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int DS, bool JS>      // JS: J staged in shared memory (compile-time, so that its reads are LDS, not generic loads)
-__global__ void __launch_bounds__(512, 1) vq_idx_dz_kernel(VqIdxBwdP p) {
+template <int DS, int NV4>
+struct DzIn {                                        // everything one vector needs from global memory
+  int code;
+  uint32_t seg;                                      // 4 = no source row
+  float gl, cf, x[DS];
+  float4 vr[NV4];
+};
+
+template <int DS, bool JS, int LPV>      // JS: J staged in shared memory (compile-time, so that its reads are LDS, not generic
+__global__ void __launch_bounds__(512, 1) vq_idx_dz_kernel(VqIdxBwdP p) {   // loads); LPV: lanes per vector (2 or 4)
   constexpr int JROW = IZ * DS, JST = JROW + 4, ES = 4;
+  constexpr int FP = IZ / LPV;                       // features per lane
+  constexpr int NV4 = FP / 4;                        // float4 loads of the source row per lane
+  constexpr int NJ4 = FP * DS / 4;                   // float4 loads of J per lane
+  constexpr int VPW = 32 / LPV;                      // vectors per warp and iteration
   extern __shared__ __align__(16) unsigned char smraw[];
-  float* J_s = reinterpret_cast<float*>(smraw);                                        // [Kc][JST] (if j_smem)
+  float* J_s = reinterpret_cast<float*>(smraw);                                        // [Kc][JST] (if JS)
   float* E_s = J_s + (JS ? (size_t)p.Kc * JST : 0);                                      // [Kc][4]
   uint64_t* bar = reinterpret_cast<uint64_t*>(E_s + (size_t)p.Kc * ES);
   IdxSeg* seg_s = reinterpret_cast<IdxSeg*>(bar + 1);                                    // [4] shared-memory copy (dynamic index)
   const int tid = threadIdx.x;
+  const long long tz0 = clock64();
   const uint32_t bar_a = s_u32(bar);
   if (tid < 4) seg_s[tid] = p.seg[tid];
   if (JS) {
@@ -1076,26 +1078,24 @@ __global__ void __launch_bounds__(512, 1) vq_idx_dz_kernel(VqIdxBwdP p) {
     for (int d = 0; d < ES; ++d) E_s[i * ES + d] = d < DS ? __ldg(p.E + i * DS + d) : 0.f;
   }
   __syncthreads();
-  const int ql = tid & 3;
-  const int64_t nquads = (int64_t)gridDim.x * (blockDim.x >> 2);
-  int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 2) + (tid >> 2);
-  // one-ahead fetch: code, g_loss, z, coefficient, 32 bytes of the source row (this lane's 8 features)
-  int code_n = 0;
-  uint32_t seg_n = 4;                                 // 4 = no source row
-  float gl_n = 0.f, cf_n = 0.f, x_n[DS];
-  float4 va_n = make_float4(0.f, 0.f, 0.f, 0.f), vb_n = va_n;
-  auto fetch = [&](int64_t vv) {
-    seg_n = 4;
-    cf_n = gl_n = 0.f;
-    code_n = 0;
-    va_n = vb_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int ql = tid & (LPV - 1);
+  const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / LPV);
+  int64_t v = (int64_t)blockIdx.x * (blockDim.x / LPV) + (tid / LPV);
+  // The loop is unrolled by two with two register sets: a set is refilled right after it has been consumed and used again
+  // two iterations later, so every global read has two iterations (> the DRAM latency) to land.
+  auto fetch = [&](DzIn<DS, NV4>& in, int64_t vv) {
+    in.seg = 4;
+    in.cf = in.gl = 0.f;
+    in.code = 0;
 #pragma unroll
-    for (int d = 0; d < DS; ++d) x_n[d] = 0.f;
+    for (int q = 0; q < NV4; ++q) in.vr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < DS; ++d) in.x[d] = 0.f;
     if (vv >= p.n) return;
-    code_n = (int)ldg_now(p.idx + vv);
-    gl_n = p.gl ? ldg_now(p.gl + vv) : 0.f;
+    in.code = (int)ldg_now(p.idx + vv);
+    in.gl = p.gl ? ldg_now(p.gl + vv) : 0.f;
 #pragma unroll
-    for (int d = 0; d < DS; ++d) x_n[d] = ldg_now(p.x + vv * DS + d);
+    for (int d = 0; d < DS; ++d) in.x[d] = ldg_now(p.x + vv * DS + d);
     const uint32_t v32 = (uint32_t)vv;
     // which segment (at most one) holds this vector: a short compare chain on constant-bank operands ...
     uint32_t sgi = 4, pl = 0;
@@ -1108,88 +1108,97 @@ __global__ void __launch_bounds__(512, 1) vq_idx_dz_kernel(VqIdxBwdP p) {
     if (sgi < 4) {
       const IdxSeg& sg = seg_s[sgi];
       uint32_t row = pl;
-      cf_n = 1.f;
+      in.cf = 1.f;
       const float* base = sg.a;
       if (sg.kind != 1) {
         const uint32_t bq = fast_div(pl, sg.m_per_b), kq = fast_div(pl, sg.m_kr);
         row = bq * (uint32_t)sg.KR + (pl - kq * (uint32_t)sg.KR);
-        cf_n = ldg_now(sg.a + pl);
+        in.cf = ldg_now(sg.a + pl);
         base = sg.b;
       }
-      seg_n = sgi;
-      const float* src = base + row * IZ + ql * 8;
-      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va_n.x), "=f"(va_n.y), "=f"(va_n.z), "=f"(va_n.w) : "l"(src));
-      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb_n.x), "=f"(vb_n.y), "=f"(vb_n.z), "=f"(vb_n.w) : "l"(src + 4));
+      in.seg = sgi;
+      const float* src = base + row * IZ + ql * FP;
+#pragma unroll
+      for (int q = 0; q < NV4; ++q)
+        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(in.vr[q].x), "=f"(in.vr[q].y), "=f"(in.vr[q].z), "=f"(in.vr[q].w) : "l"(src + 4 * q));
     }
   };
-  fetch(v);
-  if (JS) {
-    uint32_t done = 0;
-    while (!done)
-      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
-  }
-  const int qw = (tid >> 2) & 7;                      // whole warps stay in the loop together (shuffles below):
-  for (; v - qw < p.n; v += nquads) {                 // v - qw is the first vector of the warp, the same on all 32 lanes
-    const bool ok = v < p.n;
-    const int code = min(max(code_n, 0), p.Kc - 1);
-    const uint32_t sgi = seg_n;
-    const float gl = gl_n, cf = cf_n;
-    float x[DS];
+  auto process = [&](const DzIn<DS, NV4>& in, int64_t vv) {
+    const bool ok = vv < p.n;
+    const int code = min(max(in.code, 0), p.Kc - 1);
+    const uint32_t sgi = in.seg;
+    float vf[FP];
 #pragma unroll
-    for (int d = 0; d < DS; ++d) x[d] = x_n[d];
-    const float vv8[8] = {va_n.x, va_n.y, va_n.z, va_n.w, vb_n.x, vb_n.y, vb_n.z, vb_n.w};
-    fetch(v + nquads);
-    // loss-side gradient of this vector (all four lanes of the quad compute it: cheaper than a shuffle)
+    for (int q = 0; q < NV4; ++q) { vf[4 * q] = in.vr[q].x; vf[4 * q + 1] = in.vr[q].y; vf[4 * q + 2] = in.vr[q].z; vf[4 * q + 3] = in.vr[q].w; }
+    // loss-side gradient of this vector (every lane of the group computes it: cheaper than a shuffle)
     float g[DS];
     {
       float df[DS];
       float ssq = 0.f;
 #pragma unroll
       for (int d = 0; d < DS; ++d) {
-        df[d] = E_s[code * ES + d] - x[d];
+        df[d] = E_s[code * ES + d] - in.x[d];
         const float t = df[d] + 1e-5f;
         ssq = fmaf(t, t, ssq);
       }
       const float inv = p.squared ? 0.f : 1.f / sqrtf(ssq);
 #pragma unroll
-      for (int d = 0; d < DS; ++d) g[d] = gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
+      for (int d = 0; d < DS; ++d) g[d] = in.gl * (p.squared ? 2.f * df[d] : (df[d] + 1e-5f) * inv);
     }
     float gz[DS];
 #pragma unroll
     for (int d = 0; d < DS; ++d) gz[d] = 0.f;
     if (sgi < 4) {
 #pragma unroll
-      for (int q4 = 0; q4 < 2 * DS; ++q4) {
-        const float4 t = JS ? *reinterpret_cast<const float4*>(J_s + code * JST + ql * 8 * DS + q4 * 4)
-                            : __ldg(reinterpret_cast<const float4*>(p.J + (size_t)code * JROW + ql * 8 * DS + q4 * 4));
+      for (int q4 = 0; q4 < NJ4; ++q4) {
+        const float4 t = JS ? *reinterpret_cast<const float4*>(J_s + code * JST + ql * FP * DS + q4 * 4)
+                            : __ldg(reinterpret_cast<const float4*>(p.J + (size_t)code * JROW + ql * FP * DS + q4 * 4));
         const float jv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int f = q4 * 4 + e;                  // flat index (feature t, component d) = t * DS + d
-          gz[f % DS] = fmaf(vv8[f / DS], jv[e], gz[f % DS]);
+          gz[f % DS] = fmaf(vf[f / DS], jv[e], gz[f % DS]);
         }
       }
       if (ok && p.dT && ((p.kind1_mask >> sgi) & 1u)) {
-        float* t = p.dT + (size_t)code * IZ + ql * 8;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t), "f"(vv8[0]), "f"(vv8[1]), "f"(vv8[2]), "f"(vv8[3]) : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t + 4), "f"(vv8[4]), "f"(vv8[5]), "f"(vv8[6]), "f"(vv8[7]) : "memory");
+        float* t = p.dT + (size_t)code * IZ + ql * FP;
+#pragma unroll
+        for (int q = 0; q < NV4; ++q)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t + 4 * q), "f"(vf[4 * q]), "f"(vf[4 * q + 1]), "f"(vf[4 * q + 2]), "f"(vf[4 * q + 3]) : "memory");
       }
     }
 #pragma unroll
     for (int d = 0; d < DS; ++d) {
-      gz[d] += __shfl_xor_sync(FULL, gz[d], 1);
-      gz[d] += __shfl_xor_sync(FULL, gz[d], 2);
-    }
-    if (ok && ql < DS) {
-      float mine = gz[0], gm = g[0];
 #pragma unroll
-      for (int d = 1; d < DS; ++d) {
-        mine = (ql == d) ? gz[d] : mine;
-        gm = (ql == d) ? g[d] : gm;
-      }
-      p.dx[v * DS + ql] = fmaf(cf, mine, -p.beta * gm);
+      for (int o = 1; o < LPV; o <<= 1) gz[d] += __shfl_xor_sync(FULL, gz[d], o);
     }
+    if (ok) {
+#pragma unroll
+      for (int d = 0; d < DS; ++d)
+        if ((d & (LPV - 1)) == ql) p.dx[vv * DS + d] = fmaf(in.cf, gz[d], -p.beta * g[d]);
+    }
+  };
+  DzIn<DS, NV4> s0, s1;
+  fetch(s0, v);
+  fetch(s1, v + ngroups);
+  const long long tz1 = clock64();
+  if (JS) {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
   }
+  const long long tz2 = clock64();
+  const int qw = (tid / LPV) & (VPW - 1);             // whole warps stay in the loop together (shuffles inside process):
+  while (v - qw < p.n) {                              // v - qw is the first vector of the warp, the same on all 32 lanes
+    process(s0, v);
+    fetch(s0, v + 2 * ngroups);
+    v += ngroups;
+    if (!(v - qw < p.n)) break;
+    process(s1, v);
+    fetch(s1, v + 2 * ngroups);
+    v += ngroups;
+  }
+  if (blockIdx.x == 0 && tid == 0) { g_idx_dbg[0] = tz1 - tz0; g_idx_dbg[1] = tz2 - tz1; g_idx_dbg[2] = clock64() - tz2; }
 }
 
 constexpr int DE_T = 512, DE_V = 8, DE_CH = DE_T * DE_V;     // dE kernel: threads, vectors per thread, slab
@@ -1475,6 +1484,7 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
   }
   cudaStream_t st = vq_stream(stream);
   static const int algo = getenv("VQCPC_VQ_BWD_ALGO") ? atoi(getenv("VQCPC_VQ_BWD_ALGO")) : 0;    // 1: the single-kernel version
+  static const int lpv = getenv("VQCPC_VQ_BWD_LPV") ? atoi(getenv("VQCPC_VQ_BWD_LPV")) : 2;       // lanes per vector of the dz kernel
   if (algo != 1) {
     // production: streaming dz kernel + counting-sort dE kernel
 #define VQ_IB2(DSV)                                                                                                           \
@@ -1484,12 +1494,15 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
     p.j_smem = js ? 1 : 0;                                                                                                    \
     const size_t smem = (js ? js_bytes : 0) + tail;                                                                           \
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(vq_cdiv(n, 128), vq_sm_count()));                            \
-    if (js) {                                                                                                                 \
-      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      vq_idx_dz_kernel<DSV, true><<<grid, 512, smem, st>>>(p);                                                                \
+    if (js && lpv == 2) {                                                                                                     \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      vq_idx_dz_kernel<DSV, true, 2><<<grid, 512, smem, st>>>(p);                                                             \
+    } else if (js) {                                                                                                          \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      vq_idx_dz_kernel<DSV, true, 4><<<grid, 512, smem, st>>>(p);                                                             \
     } else {                                                                                                                  \
-      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      vq_idx_dz_kernel<DSV, false><<<grid, 512, smem, st>>>(p);                                                               \
+      VQ_CUDA_CALL(cudaFuncSetAttribute(vq_idx_dz_kernel<DSV, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      vq_idx_dz_kernel<DSV, false, 4><<<grid, 512, smem, st>>>(p);                                                            \
     }                                                                                                                         \
     VQ_CUDA_LAUNCH_CHECK("vq_idx_dz_kernel");                                                                                 \
     if (d_E) {                                                                                                                \
