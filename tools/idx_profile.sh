@@ -4,7 +4,7 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-KERNELS=${*:-"vq_tc_fwd_kernel nce_idx_fwd_kernel nce_idx_bwd_tc_kernel reduce_partials_kernel table_scatter_add_kernel vq_idx_bwd_kernel"}
+KERNELS=${*:-"vq_tc_fwd_kernel nce_idx_fwd_kernel nce_idx_bwd_tc_kernel reduce_partials_kernel vq_idx_dz_kernel vq_idx_de_kernel"}
 for k in $KERNELS; do
   rep=gpurun_out/r02_$k
   timeout 300 ncu --set full --import-source on --clock-control none -k regex:$k -c 1 -f -o $rep \
