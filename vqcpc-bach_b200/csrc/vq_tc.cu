@@ -38,13 +38,16 @@ using namespace vqtc;
 
 namespace {
 
-constexpr int VT_SETS = 2;                 // epilogue warpgroups; tile i of a CTA belongs to set i % VT_SETS (three sets
-                                          // were measured slower: ptxas caps a 512-thread kernel at 128 registers -> spills)
-constexpr int VT_THREADS = 128 * (1 + VT_SETS);    // warpgroup 0: producer / MMA; warpgroups 1..: the epilogue sets
+// Two thread layouts (template parameter SETS; tile i of a CTA belongs to epilogue set i % SETS):
+//   SETS = 2: 384 threads = producer warpgroup (4 warps, setmaxnreg 56) + 2 epilogue warpgroups (setmaxnreg 224)
+//   SETS = 3: 416 threads = ONE producer warp + 3 epilogue sets of 4 warps, no setmaxnreg (ptxas budget 65536 / 416 -> 152
+//             registers for everybody; a 512-thread variant with a full producer warpgroup is capped at 128 and spills)
+constexpr int VT_MAXSETS = 3;
+__host__ __device__ constexpr int vt_threads(int sets) { return sets == 2 ? 384 : 32 + 128 * sets; }
 constexpr int NABUF = 3;                  // A-operand buffers (see the reuse argument in the producer loop)
 constexpr int CH = 256;               // codes per MMA / accumulator stage (two stages = all 512 TMEM columns)
-constexpr int GROUP = 8;              // codes per group maximum
-constexpr int NG = CH / GROUP;        // group maxima per chunk
+// codes per group maximum: 8 with two epilogue sets (64 group maxima in registers), 16 with three (32: the 128-register
+// budget of that layout; each candidate group then costs 16 exact distances instead of 8)
 constexpr int ZS = 4;                 // depth of the z-tile ring in shared memory
 constexpr int VT_PROF = 8;            // clock64 stamps per CTA in the stats buffer (after the 2 counters)
 
@@ -74,6 +77,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+template <int G>
+__device__ __forceinline__ float maxg(const uint32_t* r);
+__device__ __forceinline__ float max8(const uint32_t* r);
+template <>
+__device__ __forceinline__ float maxg<8>(const uint32_t* r) { return max8(r); }
+template <>
+__device__ __forceinline__ float maxg<16>(const uint32_t* r) {
+  float m = fmaxf(max8(r), max8(r + 8));
+  return m;
 }
 __device__ __forceinline__ float max8(const uint32_t* r) {
   float m = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
@@ -141,14 +154,18 @@ __device__ __forceinline__ void write_krow(uint8_t* base, uint32_t slab_bytes, i
 // DIFFERENT groups (addresses 128 B apart without the padding: the same four banks) spread over all bank groups
 __device__ __forceinline__ int cb_off(int k, int cs) { return k * cs + ((k >> 3) << 2); }
 
-// mbarrier indices
-enum { BAR_FULL = 0 /*[set][stage]*/, BAR_EMPTY = 2 * VT_SETS /*[set][stage]*/, BAR_ZFULL = 4 * VT_SETS /*[ZS]*/,
-       BAR_ZEMPTY = 4 * VT_SETS + ZS /*[ZS]*/, BAR_T = 4 * VT_SETS + 2 * ZS, BAR_COUNT = 4 * VT_SETS + 2 * ZS + 1 };
+// mbarrier indices (sized for the largest layout)
+enum { BAR_FULL = 0 /*[set][stage]*/, BAR_EMPTY = 2 * VT_MAXSETS /*[set][stage]*/, BAR_ZFULL = 4 * VT_MAXSETS /*[ZS]*/,
+       BAR_ZEMPTY = 4 * VT_MAXSETS + ZS /*[ZS]*/, BAR_T = 4 * VT_MAXSETS + 2 * ZS, BAR_COUNT = 4 * VT_MAXSETS + 2 * ZS + 1 };
 
 // DBG: instantiation with the score dump and the clock / counter instrumentation (tests, tools/vq_bench.py --prof)
-template <int DS, bool DBG>
-__global__ void __launch_bounds__(VT_THREADS, 1)
+template <int DS, bool DBG, int SETS>
+__global__ void __launch_bounds__(vt_threads(SETS), 1)
 vq_tc_fwd_kernel(VtParams p) {
+  constexpr int VT_SETS = SETS, VT_THREADS = vt_threads(SETS);
+  constexpr int GROUP = SETS == 2 ? 8 : 16, NG = CH / GROUP;
+  constexpr uint32_t GMASK = NG == 32 ? 0xFFFFFFFFu : ((1u << NG) - 1u);
+  constexpr int NPW = SETS == 2 ? 4 : 1;                       // producer warps
   constexpr int KTOT = 3 * DS + 3, KB = (KTOT + 15) / 16;
   constexpr int CS = (DS == 3) ? 4 : DS;                       // padded fp32 code stride in smem
   constexpr uint32_t A_SLAB = 128 * 32, A_BUF = KB * A_SLAB;
@@ -183,7 +200,7 @@ vq_tc_fwd_kernel(VtParams p) {
     }
     for (int i = 0; i < ZS; ++i) {
       mbar_init(BAR(BAR_ZFULL + i), 1);
-      mbar_init(BAR(BAR_ZEMPTY + i), 8);          // the four producer warps + the four warps of the set that owns the tile
+      mbar_init(BAR(BAR_ZEMPTY + i), NPW + 4);    // the producer warps + the four warps of the set that owns the tile
     }
     mbar_init(BAR(BAR_T), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -239,9 +256,9 @@ vq_tc_fwd_kernel(VtParams p) {
   const uint32_t tmem_base = *tmem_slot;
   if (prof && threadIdx.x == 0) prof[0] = (int)(clock64() - t_start);
 
-  if (warp < 4) {
-    // ============================== warpgroup 0: z-tile fetch, operand producer, MMA issuer ==============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp < NPW) {
+    // ============================== producer warps: z-tile fetch, operand producer, MMA issuer ==============================
+    if (SETS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     const uint32_t idesc = make_idesc<CH>(true, true);
     constexpr uint32_t hi_c = (256u >> 4) | (1u << 14) | (6u << 29);      // SBO 256 B, descriptor version 1, SWIZZLE_32B
     constexpr uint32_t lo_c = 1u << 16;                                   // LBO (unused for swizzled K-major)
@@ -270,23 +287,26 @@ vq_tc_fwd_kernel(VtParams p) {
       for (int i = 0; i < ZS - 1; ++i) fetch(i);
     uint32_t eph = 0;                              // bit (set*2 + stage): parity of BAR_EMPTY[set][stage]
     int last0 = -1, last1 = -1;                    // which epilogue set read accumulator stage 0 / 1 last
-    const int rl = warp * 32 + lane;               // the operand row this thread builds
     for (int it = 0; it < my_tiles; ++it) {
       if (warp == 0) fetch(it + ZS - 1);
       const int slot = it % ZS, set = it % VT_SETS;
       mbar_wait(BAR(BAR_ZFULL + slot), (it / ZS) & 1);
-      const int64_t row = (blockIdx.x + (int64_t)it * gridDim.x) * 128 + rl;
       // A(it) goes to buffer it % 3, last read by the MMAs of tile it-3: warp 0 saw them retire (accumulator waits) while
-      // issuing tile it-2, i.e. before it arrived at the warpgroup barrier of tile it-1, which this thread has passed
+      // issuing tile it-2, i.e. before it arrived at the producer barrier of tile it-1, which this thread has passed
       uint8_t* abuf = a_smem + (it % NABUF) * A_BUF;
-      float zr[DS];
+#pragma unroll 1
+      for (int rr = 0; rr < 4 / NPW; ++rr) {       // the operand rows this thread builds (one with four producer warps, four with one)
+        const int rl = (warp + rr * NPW) * 32 + lane;
+        const int64_t row = (blockIdx.x + (int64_t)it * gridDim.x) * 128 + rl;
+        float zr[DS];
 #pragma unroll
-      for (int d = 0; d < DS; ++d) zr[d] = (row < p.n) ? z_sm[(slot * 128 + rl) * DS + d] : 0.f;
-      write_krow<DS, true>(abuf, A_SLAB, rl, zr, 0.f);
+        for (int d = 0; d < DS; ++d) zr[d] = (row < p.n) ? z_sm[(slot * 128 + rl) * DS + d] : 0.f;
+        write_krow<DS, true>(abuf, A_SLAB, rl, zr, 0.f);
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(BAR_ZEMPTY + slot));
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (NPW == 4) asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0 && lane == 0) {
         const uint32_t a_addr = a_base + (uint32_t)(it % NABUF) * A_BUF;
         for (int c = 0; c < p.nch; ++c) {
@@ -315,10 +335,10 @@ vq_tc_fwd_kernel(VtParams p) {
     // ============================== score reduction + exact verification ==============================
     // set s (warpgroup 1 + s) owns the tiles s, s + VT_SETS, ... of this CTA; thread == vector.
     // Register budget: 128 x 56 (producers) + 256 x 224 (two sets) <= 64 K
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int set = (warp >> 2) - 1;
-    const int q = warp & 3;                        // TMEM lane quadrant
-    const bool stamp = DBG && prof && warp == 4 && lane == 0;
+    if (SETS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int set = (warp - NPW) >> 2;
+    const int q = warp & 3;                        // TMEM lane quadrant (hardware: warp id % 4); each set covers all four
+    const bool stamp = DBG && prof && warp == NPW && lane == 0;
     const float nmax = red[DS];
     float emax[DS];
 #pragma unroll
@@ -377,20 +397,22 @@ vq_tc_fwd_kernel(VtParams p) {
             // software pipeline over the eight 32-column chunks of the stage: the TMEM load of chunk j + 1 is in flight
             // while chunk j is reduced (tcgen05.wait::ld waits for everything outstanding, so the wait sits after the
             // reduction of the previous chunk)
-            uint32_t rb[2][32];
+            constexpr int NB = SETS == 2 ? 2 : 1;       // (the three-set layout has no registers for a second buffer)
+            uint32_t rb[NB][32];
             tmem_ld32(taddr, rb[0]);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < CH / 32; ++j) {
-              uint32_t* r0 = rb[j & 1];
-              if (j + 1 < CH / 32) tmem_ld32(taddr + (j + 1) * 32, rb[(j + 1) & 1]);
+              uint32_t* r0 = rb[j % NB];
+              if (NB == 2 && j + 1 < CH / 32) tmem_ld32(taddr + (j + 1) * 32, rb[(j + 1) % NB]);
               if (DBG && p.dbg && ok) {
                 float* drow = p.dbg + (size_t)row * p.dbg_ld + c * CH + j * 32;
 #pragma unroll
                 for (int t = 0; t < 32; ++t) drow[t] = __uint_as_float(r0[t]);
               }
 #pragma unroll
-              for (int t = 0; t < 4; ++t) gm[h * NG + j * 4 + t] = max8(r0 + t * 8);
+              for (int t = 0; t < 32 / GROUP; ++t) gm[h * NG + j * (32 / GROUP) + t] = maxg<GROUP>(r0 + t * GROUP);
+              if (NB == 1 && j + 1 < CH / 32) tmem_ld32(taddr + (j + 1) * 32, rb[0]);
               if (j + 1 < CH / 32) tmem_ld_wait();
             }
             tcgen05_fence_before();
@@ -402,16 +424,18 @@ vq_tc_fwd_kernel(VtParams p) {
             for (int t = 0; t < NG; ++t) gm[h * NG + t] = -INFINITY;
           }
         }
-        // maximum of the 64 group maxima as a tree (depth 4 instead of a 32-long dependent chain)
-        float tm[22];
+        // maximum of the group maxima: four independent 3-input chains instead of one long dependent chain
+        float cm[4] = {gm[0], gm[1], gm[2], gm[3]};
 #pragma unroll
-        for (int t = 0; t < 21; ++t) tm[t] = fmax3(gm[3 * t], gm[3 * t + 1], gm[3 * t + 2]);
-        tm[21] = gm[63];
-        float tn[8];
+        for (int t = 4; t + 7 < 2 * NG; t += 8) {
+          cm[0] = fmax3(cm[0], gm[t], gm[t + 1]);
+          cm[1] = fmax3(cm[1], gm[t + 2], gm[t + 3]);
+          cm[2] = fmax3(cm[2], gm[t + 4], gm[t + 5]);
+          cm[3] = fmax3(cm[3], gm[t + 6], gm[t + 7]);
+        }
+        float cmax = fmax3(cm[0], cm[1], fmaxf(cm[2], cm[3]));
 #pragma unroll
-        for (int t = 0; t < 7; ++t) tn[t] = fmax3(tm[3 * t], tm[3 * t + 1], tm[3 * t + 2]);
-        tn[7] = tm[21];
-        const float cmax = fmax3(fmax3(tn[0], tn[1], tn[2]), fmax3(tn[3], tn[4], tn[5]), fmaxf(tn[6], tn[7]));
+        for (int t = 4 + (2 * NG - 4) / 8 * 8; t < 2 * NG; ++t) cmax = fmaxf(cmax, gm[t]);
         runmax = fmaxf(runmax, cmax);
         const float thr = runmax - margin;
         // candidate masks: four independent accumulators per half instead of one 32-long LOP3 chain
@@ -422,31 +446,33 @@ vq_tc_fwd_kernel(VtParams p) {
           mh[t & 3] = mask_ge(mh[t & 3], gm[NG + t], thr, 1u << t);
         }
         uint32_t mlo = (ml[0] | ml[1]) | (ml[2] | ml[3]), mhi = (mh[0] | mh[1]) | (mh[2] | mh[3]);
-        if (scan_all || !(cmax == cmax)) { mlo = mhi = 0xFFFFFFFFu; ++n_full; }      // NaN / inf / overflow: scan all
+        if (scan_all || !(cmax == cmax)) { mlo = mhi = GMASK; ++n_full; }            // NaN / inf / overflow: scan all
         if (!ok) mlo = mhi = 0u;
         TICK(acc_m);
         // ascending code order + strict '<' = lowest index on ties
         while (mlo | mhi) {
           int t;
           if (mlo) { t = __ffs(mlo) - 1; mlo &= mlo - 1; }
-          else { t = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+          else { t = NG + __ffs(mhi) - 1; mhi &= mhi - 1; }
           ++n_exact;
           const int k0 = c0 * CH + t * GROUP;
           // all eight codes of the group: loads first, eight independent distance chains, then a tournament that keeps
           // the lower index on ties (padding codes hold +inf coordinates, so their distance is +inf / NaN and never wins)
-          const float* cg = cb + cb_off(k0, CS);
-          float dd[GROUP];
+#pragma unroll 1
+          for (int sub = 0; sub < GROUP; sub += 8) {       // eight codes at a time (ascending: strict '<' keeps the lowest index)
+            float dd[8];
 #pragma unroll
-          for (int j = 0; j < GROUP; ++j) dd[j] = dist_fixed<DS>(xr, cg + j * CS);
-          int ki[GROUP];
+            for (int j = 0; j < 8; ++j) dd[j] = dist_fixed<DS>(xr, cb + cb_off(k0 + sub + j, CS));
+            int ki[8];
 #pragma unroll
-          for (int j = 0; j < GROUP; ++j) ki[j] = k0 + j;
+            for (int j = 0; j < 8; ++j) ki[j] = k0 + sub + j;
 #pragma unroll
-          for (int w = 1; w < GROUP; w <<= 1)
+            for (int w = 1; w < 8; w <<= 1)
 #pragma unroll
-            for (int j = 0; j + w < GROUP; j += 2 * w)
-              if (dd[j + w] < dd[j]) { dd[j] = dd[j + w]; ki[j] = ki[j + w]; }
-          if (dd[0] < best) { best = dd[0]; bi = ki[0]; }      // ascending groups + strict '<' = lowest index on ties
+              for (int j = 0; j + w < 8; j += 2 * w)
+                if (dd[j + w] < dd[j]) { dd[j] = dd[j + w]; ki[j] = ki[j + w]; }
+            if (dd[0] < best) { best = dd[0]; bi = ki[0]; }
+          }
         }
       }
       TICK(acc_v);
@@ -533,7 +559,7 @@ size_t vt_smem_bytes(int Kc, int kpad, int zd, bool t_smem) {
 }
 
 template <int DS>
-int vt_launch(VtParams& p, cudaStream_t st) {
+int vt_launch(VtParams& p, int sets, cudaStream_t st) {
   const int64_t ntiles = (p.n + 127) / 128;
   const bool t_ok = p.T && p.zd >= 1 && ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && (((size_t)p.Kc * p.zd * 4) % 16 == 0);
   const int kpad = (p.Kc + CH - 1) / CH * CH;
@@ -547,11 +573,14 @@ int vt_launch(VtParams& p, cudaStream_t st) {
   smem = std::max<size_t>(smem, 120 * 1024);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)vq_sm_count()));
   if (p.dbg || p.stats) {
-    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_tc_fwd_kernel<DS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_tc_fwd_kernel<DS, true><<<grid, VT_THREADS, smem, st>>>(p);
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_tc_fwd_kernel<DS, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_tc_fwd_kernel<DS, true, 2><<<grid, vt_threads(2), smem, st>>>(p);
+  } else if (sets == 3) {
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_tc_fwd_kernel<DS, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_tc_fwd_kernel<DS, false, 3><<<grid, vt_threads(3), smem, st>>>(p);
   } else {
-    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_tc_fwd_kernel<DS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_tc_fwd_kernel<DS, false><<<grid, VT_THREADS, smem, st>>>(p);
+    VQ_CUDA_CALL(cudaFuncSetAttribute(vq_tc_fwd_kernel<DS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vq_tc_fwd_kernel<DS, false, 2><<<grid, vt_threads(2), smem, st>>>(p);
   }
   VQ_CUDA_LAUNCH_CHECK("vq_tc_fwd_kernel");
   return VQ_OK;
@@ -564,14 +593,14 @@ bool vq_tc_supported(int D, int Kc) { return (D == 3 || D == 4) && Kc >= 1 && Kc
 int vq_tc_fused_fwd(const float* x, int64_t n, int D, const float* E, const float* T, int Kc, int zd, float beta, int squared,
                     int64_t* idx, float* loss, float* z_sg, float* y, int64_t y_row0, int64_t y_rows, int* counts,
                     float* dbg_scores, int* stats, int variant, cudaStream_t st) {
-  (void)variant;
+  const int sets = variant == 3 ? 3 : 2;              // VQCPC_VQTC_LAYOUT=3: three epilogue sets behind a single producer warp
   VQ_CHECK_ARG(vq_tc_supported(D, Kc), "vq_tc: unsupported D=%d / Kc=%d", D, Kc);
   VtParams p;
   p.x = x; p.E = E; p.T = T; p.n = n; p.Kc = Kc; p.nch = 0; p.zd = zd; p.beta = beta; p.squared = squared;
   p.idx = idx; p.loss = loss; p.zsg = z_sg; p.y = y; p.y_row0 = y_row0; p.y_rows = y_rows; p.counts = counts; p.dbg = dbg_scores; p.dbg_ld = (Kc + 255) / 256 * 256;
   p.t_smem = 0; p.x_bulk = 0; p.stats = stats;
   switch (D) {
-    case 3: return vt_launch<3>(p, st);
-    default: return vt_launch<4>(p, st);
+    case 3: return vt_launch<3>(p, sets, st);
+    default: return vt_launch<4>(p, sets, st);
   }
 }
