@@ -223,6 +223,11 @@ int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T, const 
                           const float* u, const float* pos, const float* neg, const float* lse, const float* g_dev,
                           float scale, int B, int N, int KR, int zd, int cd, int Kc, float* d_c, float* coef_pos,
                           float* coef_neg, float* part, float* d_W, float* d_T, void* stream);
+/* test / tuning hooks: kernel choice of the two backward entry points.  infonce_idx: 0 = tcgen05 d T (default), 1 = CUDA-core
+ * owner-computes kernel;  vq_idx: 0 = streaming d z + counting-sort d E kernels (default), 1 = single kernel;  -1 = follow
+ * the environment (VQCPC_NCE_BWD_ALGO / VQCPC_VQ_BWD_ALGO). */
+int vqcpc_infonce_idx_set_bwd_algo(int algo);
+int vqcpc_vq_idx_set_bwd_algo(int algo);
 /* out[idx[i]] += rows[i] (rows (n, zd), out (Kc, zd) ACCUMULATED) without atomics, deterministic: the gradient of the
  * table gather y = T[idx] of the left blocks. */
 int vqcpc_table_scatter_add(const int64_t* idx, int64_t n, const float* rows, int zd, int Kc, float* out, void* stream);

@@ -46,11 +46,16 @@ def _reference(z, E, T, J, c, W, idx, B, N, KR, KL, beta, squared, w_q, w_left):
                 dz=z.grad, dE=E.grad, dT=T.grad, dc=c.grad, dW=W.grad, correct=(pos > neg.max(2)[0]).detach())
 
 
+@pytest.mark.parametrize('algos', [(0, 0), (1, 1)])
 @pytest.mark.parametrize('B,N,KR,KL,Kc,D,squared', [(5, 15, 8, 8, 512, 3, 1), (37, 15, 2, 2, 64, 3, 1), (9, 7, 6, 6, 300, 3, 0),
                                                      (3, 15, 3, 2, 16, 4, 1), (130, 15, 8, 8, 512, 3, 1), (1, 1, 1, 1, 8, 3, 1),
                                                      (6, 15, 16, 3, 600, 3, 1)])
-def test_idxpath_small_kernels_vs_fp64_autograd(B, N, KR, KL, Kc, D, squared):
-    from VQCPCB import ops
+def test_idxpath_small_kernels_vs_fp64_autograd(B, N, KR, KL, Kc, D, squared, algos):
+    """algos = (infonce backward, quantizer backward) kernel choice: (0, 0) production (tcgen05 dT; streaming dz + dE kernels),
+    (1, 1) the CUDA-core / single-kernel variants kept as fallbacks."""
+    from VQCPCB import _native, ops
+    _native.call('vqcpc_infonce_idx_set_bwd_algo', algos[0])
+    _native.call('vqcpc_vq_idx_set_bwd_algo', algos[1])
     dev = 'cuda'
     g = torch.Generator().manual_seed(B * 131 + KR)
     zd = cd = 32
@@ -99,6 +104,8 @@ def test_idxpath_small_kernels_vs_fp64_autograd(B, N, KR, KL, Kc, D, squared):
     assert torch.equal(correct.cpu().bool()[clear], ref['correct'][clear])
     for b in range(1, B, 2):
         assert int(correct[b, 0]) == 0
+    _native.call('vqcpc_infonce_idx_set_bwd_algo', -1)
+    _native.call('vqcpc_vq_idx_set_bwd_algo', -1)
     for name, got, tol in (('dc', cc.grad, 2e-5), ('dW', Wc.grad, 2e-5), ('dT', Tc.grad, 2e-5), ('dE', Ec.grad, 2e-5),
                            ('dz', zc.grad, 2e-5)):
         e = rel_err(got, ref[name])

@@ -55,6 +55,8 @@ SIGNATURES = {
     'vqcpc_table_scatter_add': [_P, _L, _P, _I, _I, _P, _P],
     'vqcpc_vq_idx_bwd': [_P, _L, _I, _P, _P, _I, _I, _P, _F, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     'vqcpc_idx_debug_read': [_P],
+    'vqcpc_infonce_idx_set_bwd_algo': [_I],
+    'vqcpc_vq_idx_set_bwd_algo': [_I],
     'vqcpc_infonce_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     'vqcpc_infonce_set_algo': [_I],
     'vqcpc_infonce_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],

@@ -1341,6 +1341,22 @@ int nce_spi(int KR) { return KR >= 9 ? 1 : 16 / KR; }
 // ---------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------------
+// kernel selection (test / tuning hooks; -1 = take the environment variable, else the default 0)
+static int g_nce_bwd_algo = -1;     // 0: tcgen05 dT (production), 1: CUDA-core owner-computes kernel
+static int g_vq_bwd_algo = -1;      // 0: streaming dz + counting-sort dE kernels (production), 1: single kernel
+static int env_or(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+VQ_API int vqcpc_infonce_idx_set_bwd_algo(int algo) {
+  VQ_CHECK_ARG(algo >= -1 && algo <= 1, "infonce_idx_set_bwd_algo: algo must be -1, 0 or 1");
+  g_nce_bwd_algo = algo;
+  return VQ_OK;
+}
+VQ_API int vqcpc_vq_idx_set_bwd_algo(int algo) {
+  VQ_CHECK_ARG(algo >= -1 && algo <= 1, "vq_idx_set_bwd_algo: algo must be -1, 0 or 1");
+  g_vq_bwd_algo = algo;
+  return VQ_OK;
+}
+
 static int idx_path_check(const char* who, int N, int KR, int zd, int cd, int Kc) {
   VQ_CHECK_ARG(zd == IZ && cd == IZ, "%s: the index path is specialised for zd == cd == 32 (got %d, %d)", who, zd, cd);
   VQ_CHECK_ARG(N >= 1 && N <= 15, "%s: 1 <= N <= 15 negatives supported (got %d)", who, N);
@@ -1410,7 +1426,7 @@ VQ_API int vqcpc_infonce_idx_bwd(const float* c, const float* W, const float* T,
   cudaStream_t st = vq_stream(stream);
   // production kernel: dT on the tensor cores (tcgen05, TMEM accumulators); VQCPC_NCE_BWD_ALGO=1 forces the CUDA-core
   // owner-computes kernel (also the fallback when the operand stages do not fit next to the table)
-  static const int force_simt = getenv("VQCPC_NCE_BWD_ALGO") ? atoi(getenv("VQCPC_NCE_BWD_ALGO")) : 0;
+  const int force_simt = g_nce_bwd_algo >= 0 ? g_nce_bwd_algo : env_or("VQCPC_NCE_BWD_ALGO", 0);
   NceBwdTcP q{};
   q.kpad = (Kc + 127) / 128 * 128;
   q.PW = warps;
@@ -1483,7 +1499,7 @@ VQ_API int vqcpc_vq_idx_bwd(const float* x, int64_t n, int D, const float* E, co
     if (seg_kind[i] == 1) p.kind1_mask |= 1u << i;
   }
   cudaStream_t st = vq_stream(stream);
-  static const int algo = getenv("VQCPC_VQ_BWD_ALGO") ? atoi(getenv("VQCPC_VQ_BWD_ALGO")) : 0;    // 1: the single-kernel version
+  const int algo = g_vq_bwd_algo >= 0 ? g_vq_bwd_algo : env_or("VQCPC_VQ_BWD_ALGO", 0);          // 1: the single-kernel version
   static const int lpv = getenv("VQCPC_VQ_BWD_LPV") ? atoi(getenv("VQCPC_VQ_BWD_LPV")) : 2;       // lanes per vector of the dz kernel
   if (algo != 1) {
     // production: streaming dz kernel + counting-sort dE kernel
