@@ -120,6 +120,18 @@ int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K, const 
  * warps per CTA (experimental), -1 = automatic per shape. */
 int vqcpc_gemm_set_tile_config(int cfg);
 
+/* which epilogue variant of the tcgen05 GEMM the library was built with (-DVQ_EPI_KIND): 0 = quad (mma-fragment TMEM loads +
+ * one shuffle exchange, 8 cache lines per warp access; default), 1 = staged through shared memory, 2 = thread-per-row.
+ * Results are bit-identical; the variants exist for A/B measurements (tools/gemm_check.py --libs). */
+int vqcpc_gemm_epilogue_kind(void);
+
+/* profiling hook: device buffer of 12 uint64 that the CTA-pair GEMM kernel adds phase timers to (NULL = off); layout in
+ * csrc/gemm_tc.cu */
+int vqcpc_gemm_set_debug(void* buf);
+
+/* profiling hook: timing experiments inside the GEMM epilogue (0 = off; non-zero values skip work and give INVALID results) */
+int vqcpc_gemm_set_experiment(int e);
+
 /* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +
  *      subsampled_relative_attention.py:30-122) ---------------------------------------------------------------------
  * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64).  Only the query rows with token % keep == 0 are

@@ -3,11 +3,13 @@
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 SRC="$ROOT/vqcpc-bach_b200/csrc"
-OUT="$ROOT/vqcpc-bach_b200/libvqcpc_b200.so"
-OBJ="$ROOT/build/obj"
+# A/B builds: VQ_EPI_KIND=k VQ_TAG=_epik tools/build.sh -> libvqcpc_b200_epik.so with its own object directory
+TAG=${VQ_TAG:-}
+OUT="$ROOT/vqcpc-bach_b200/libvqcpc_b200$TAG.so"
+OBJ="$ROOT/build/obj$TAG"
 mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -I$ROOT/include -I$SRC"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -I$ROOT/include -I$SRC ${VQ_EPI_KIND:+-DVQ_EPI_KIND=$VQ_EPI_KIND}"
 pids=()
 objs=()
 for f in "$SRC"/*.cu; do

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvqcpc_b200.so')
+# VQCPC_LIB_TAG selects an A/B build of the same sources (tools/build.sh with VQ_TAG=...); the product uses the untagged library
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvqcpc_b200%s.so' % os.environ.get('VQCPC_LIB_TAG', ''))
 
 _c = ctypes
 _P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
@@ -37,6 +38,8 @@ SIGNATURES = {
     'vqcpc_gemm_bf16x3': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
     'vqcpc_gemm_bf16x3_ex': [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _P],
     'vqcpc_gemm_set_tile_config': [_I],
+    'vqcpc_gemm_set_debug': [_P],
+    'vqcpc_gemm_set_experiment': [_I],
     'vqcpc_attn_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     'vqcpc_attn_set_fwd_algo': [_I],
@@ -65,7 +68,7 @@ SIGNATURES = {
     'vqcpc_grad_sumsq': [_P, _L, _F, _P, _P],
     'vqcpc_clip_adam': [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _I, _P],
 }
-_SPECIAL = {'vqcpc_last_error': (_c.c_char_p, []), 'vqcpc_abi_version': (_I, []),
+_SPECIAL = {'vqcpc_last_error': (_c.c_char_p, []), 'vqcpc_abi_version': (_I, []), 'vqcpc_gemm_epilogue_kind': (_I, []),
             'vqcpc_idxpath_supported': (_I, [_I, _I, _I, _I, _I, _I]), 'vqcpc_infonce_idx_parts': (_I, [_I, _I]),
             'vqcpc_infonce_idx_scratch': (_L, [_I, _I, _I])}
 

@@ -36,7 +36,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;     // 4 transpose buffers, one per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -197,7 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(p, taddr, m0, n0, q, lane, first_split);
+      uint8_t* stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
+      epilogue_dispatch<BN>(p, taddr, m0, n0, q, lane, first_split, stg);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -260,7 +262,7 @@ namespace {
 template <bool AK, bool BKM, int PASSES, int BN, int BK, int STAGES, int CL>
 int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK * 2 + BN * BK * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
   auto kern = gemm_tc_kernel<AK, BKM, PASSES, BN, BK, STAGES, CL>;
   static bool done = false;
@@ -304,16 +306,19 @@ int launch_cfg(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 //                         2 = 128x256x32 with the B tile multicast over a cluster of 2 CTAs along M, 3 = cluster of 4,
 //                         4 = CTA pairs (tcgen05.mma.cta_group::2), 256x256x32 tiles, 6 / 12 stages (gemm_tc2.cu)
 int g_force_cfg = -1;
-inline int pick_cfg(int M, int N, int K, bool b_kmajor) {
+unsigned long long* g_dbg = nullptr;
+int g_exp = 0;
+int g_wgrad_cfg = 2;
+inline int pick_cfg(int M, int N, int K, bool a_kmajor, bool b_kmajor) {
   if (g_force_cfg >= 0) return (N < 256 && g_force_cfg > 0) ? 0 : g_force_cfg;
   if (N < 256) return 0;
   if (M < 2 * BM) return 1;
-  // measured on the encoder shapes (profiles/r01_gemm_bench_*.txt, profiles/r02_gemm_check_cfgs.txt): the CTA-pair kernel
-  // wins when B is K-major (forward GEMMs), the multicast kernel when B is MN-major (data / weight gradients).  With a
-  // short K and only two N tiles (out-proj forward, 512 x 512) the epilogue is the bottleneck of the pair kernel: its
-  // eight-epilogue-warp variant measured 860 vs 777 tensor-TFLOP/s there (and loses on every wider / deeper shape).
-  if (b_kmajor) return (N <= 512 && K <= 1024) ? 5 : 4;
-  return 2;
+  // measured on the encoder shapes (profiles/r02_gemm_check_epi*.txt): with the remote mbarrier arrives relaxed and the
+  // epilogue's side inputs pipelined, the CTA-pair kernel (4 epilogue warps) wins on every forward and data-gradient shape
+  // (B K-major or MN-major); round 1 preferred the multicast kernel for MN-major B and the eight-epilogue-warp pair variant
+  // for out-proj.  Weight gradients (A and B MN-major, split-K): see g_wgrad_cfg.
+  if (!a_kmajor) return g_wgrad_cfg;
+  return 4;
 }
 
 template <bool AK, bool BKM>
@@ -363,7 +368,9 @@ VQ_API int vqcpc_gemm_bf16x3_ex(int a_kmajor, int b_kmajor, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ldo = ldo;
   p.ep.bias = bias; p.ep.residual = residual; p.ep.ldr = ldr; p.ep.flags = flags; p.ep.alpha = alpha; p.ep.scale_ncols = scale_ncols;
-  int cfg = pick_cfg(M, N, K, b_kmajor != 0);
+  p.dbg = g_dbg;
+  p.exp = g_exp;
+  int cfg = pick_cfg(M, N, K, a_kmajor != 0, b_kmajor != 0);
   const bool epw8 = cfg == 5;                        // configuration 5 = configuration 4 with eight epilogue warps per CTA
   if (epw8) cfg = 4;
   const int BN = cfg >= 1 ? 256 : 128, BK = (cfg >= 1 && cfg <= 3) ? 32 : 64;
@@ -415,6 +422,24 @@ VQ_API int vqcpc_gemm_set_tile_config(int cfg) {
   g_force_cfg = cfg;
   return VQ_OK;
 }
+
+// Profiling hook: device buffer of 12 uint64 the CTA-pair kernel adds its phase timers to (NULL = off): [0] cycles the MMA
+// threads spent in their tile loops, [1] of them waiting for a free accumulator stage (epilogue-bound), [2] waiting for
+// operands (TMA-bound); [4 + q] cycles the epilogue warps of lane quadrant q waited for an accumulator, [8 + q] spent draining.
+VQ_API int vqcpc_gemm_set_debug(void* buf) {
+  g_dbg = reinterpret_cast<unsigned long long*>(buf);
+  return VQ_OK;
+}
+
+// Timing experiments inside the epilogue (0 = off; anything else produces INVALID results - profiling tools only).
+VQ_API int vqcpc_gemm_set_experiment(int e) {
+  g_exp = e & 0xff;
+  vqtc::g_no_static_epilogue = (e >> 8) & 1;      // bit 8: keep results valid but use the run-time-flag epilogue everywhere
+  return VQ_OK;
+}
+
+// Which epilogue variant this library was built with (VQ_EPI_KIND): 0 = quad, 1 = staged, 2 = thread-per-row.
+VQ_API int vqcpc_gemm_epilogue_kind(void) { return VQ_EPI_KIND; }
 
 VQ_API int vqcpc_gemm_bf16x3(int a_kmajor, int b_kmajor, int M, int N, int K, const void* A_hi, const void* A_lo, int lda,
                              const void* B_hi, const void* B_lo, int ldb, float* C, int ldc, const float* bias,

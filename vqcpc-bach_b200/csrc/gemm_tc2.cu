@@ -28,7 +28,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_r
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // .relaxed: a release arrive on a remote barrier costs MEMBAR.ALL.GPU + ERRBAR each time (ncu round 2: 14 % of the pair
+  // kernel's stall samples - one per k-block on the peer producer, one per tile and epilogue warp), and neither hand-off
+  // publishes generic-proxy data: TMA bytes are tracked by the barrier's tx count, TMEM reads are complete at
+  // tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on the mbarrier of the LEADER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
@@ -54,11 +58,17 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(bool a_kmajor, bool b_kma
          ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);      // M = 256 across the pair, N = 256
 }
 
-// EPW = number of epilogue warps per CTA: 4 (warps 2..5, one per TMEM lane quadrant, all 256 columns each) or 8 (warps 2..9:
-// warps w and w + 4 share a lane quadrant and drain 128 columns each - halves the epilogue latency per tile, which is what
-// bounds the K = 512 shapes; experimental, tile configuration 5).
-template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES, int EPW = 4>
-__global__ void __launch_bounds__(64 + 32 * EPW, 1)
+// EPW = number of epilogue warps per CTA:
+//   4: 192 threads, warps 2..5, one per TMEM lane quadrant (= scheduler partition), all 256 columns each.
+//   8: 384 threads = warpgroup 0 (warp 0 producer, warp 1 MMA issuer, two idle warps; setmaxnreg 56) + warpgroups 1, 2
+//      (warps 4..11, setmaxnreg 224): warps w and w + 4 share a lane quadrant - and therefore a scheduler partition - and drain
+//      128 columns each.  ncu on the K = 512 shapes shows the 4-warp epilogue issuing one instruction every ~7 cycles (one warp
+//      per scheduler, dependent chains, ~350 instructions per 32 x 32 chunk) and needing 1.5 - 2x the tile's MMA time; a second
+//      warp per scheduler hides those latencies.  Round 1 tried 8 warps in a 320-thread block: ten warps put three on two of the
+//      partitions, which caps every thread at 168 registers - hence the warpgroup layout with setmaxnreg.
+// SCFG: static epilogue configuration (see epilogue_tile_quad), -1 = run-time flags.
+template <bool A_KMAJOR, bool B_KMAJOR, int PASSES, int STAGES, int EPW = 4, int SCFG = -1>
+__global__ void __launch_bounds__(EPW == 8 ? 384 : 192, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
   constexpr int TILE_A_BYTES = BM * BK2 * 2;            // 8 KB  (own 128 rows)
@@ -68,7 +78,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (TILE_A_BYTES + TILE_B_BYTES);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;     // EPW transpose buffers, one per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPW * EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -76,6 +87,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NUM_ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EPI_WARP0 = EPW == 8 ? 4 : 2;           // first epilogue warp
   const int crank = (int)cluster_ctarank();             // 0 = leader
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int m_groups = (p.m_tiles + 1) / 2;             // pairs of 128-row tiles
@@ -104,6 +116,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
+    if constexpr (EPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
@@ -152,6 +165,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
+    if constexpr (EPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0 && crank == 0) {
       constexpr uint32_t idesc = make_idesc_pair(A_KMAJOR, B_KMAJOR);
       constexpr uint32_t A_STEP = A_KMAJOR ? (UMMA_K * 2) : (UMMA_K * 128);
@@ -161,15 +175,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t smem_base_u32 = smem_u32(smem) & 0x3FFFFu;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      long long t_tempty = 0, t_full = 0, t_all = clock64();
       for (int item = cluster_id; item < total_items; item += num_clusters) {
         const int ks = item / (m_groups * p.n_tiles);
         const int kb0 = ks * p.kblocks_per_split;
         const int kb1 = min(p.kblocks_total, kb0 + p.kblocks_per_split);
+        long long t0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        if (p.dbg) t_tempty += clock64() - t0;
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN2);
         for (int kb = kb0; kb < kb1; ++kb) {
+          t0 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (p.dbg) t_full += clock64() - t0;
           tcgen05_fence_after();
           const uint32_t a_hi = smem_base_u32 + (uint32_t)(stage * STAGE_BYTES), b_hi = a_hi + TILE_A_BYTES;
           const uint32_t a_lo = b_hi + TILE_B_BYTES, b_lo = a_lo + TILE_A_BYTES;
@@ -196,31 +215,50 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         umma_commit_pair(smem_u32(&tfull_bar[acc]), 3);          // both halves of the accumulator are complete
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
       }
+      if (p.dbg) {   // [0] MMA-thread cycles in the tile loop, [1] of them waiting for a free accumulator, [2] for operands
+        atomicAdd(p.dbg + 0, (unsigned long long)(clock64() - t_all));
+        atomicAdd(p.dbg + 1, (unsigned long long)t_tempty);
+        atomicAdd(p.dbg + 2, (unsigned long long)t_full);
+      }
     }
-  } else {
-    // =============================== epilogue (warps 2..5, both CTAs, own 128 rows) ===============================
+  } else if (warp >= EPI_WARP0) {
+    // =============================== epilogue (both CTAs, own 128 rows) ===============================
+    if constexpr (EPW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long t_wait = 0, t_epi = 0;
     for (int item = cluster_id; item < total_items; item += num_clusters) {
       const int ks = item / (m_groups * p.n_tiles);
       const int rem = item % (m_groups * p.n_tiles);
       const int m0 = ((rem / p.n_tiles) * 2 + crank) * BM, n0 = (rem % p.n_tiles) * BN2;
       const bool first_split = (ks == 0);
+      const long long t0 = p.dbg ? clock64() : 0;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      const long long t1 = p.dbg ? clock64() : 0;
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2);
+      uint8_t* stg = epi_stage + (warp - EPI_WARP0) * EPI_STAGE_BYTES;
       if constexpr (EPW == 8) {
-        if (warp < 6) epilogue_tile<BN2, 0, BN2 / 64>(p, taddr, m0, n0, q, lane, first_split);
-        else epilogue_tile<BN2, BN2 / 64, BN2 / 32>(p, taddr, m0, n0, q, lane, first_split);
+        if (warp < 8) epilogue_dispatch<BN2, 0, BN2 / 64>(p, taddr, m0, n0, q, lane, first_split, stg);
+        else epilogue_dispatch<BN2, BN2 / 64, BN2 / 32>(p, taddr, m0, n0, q, lane, first_split, stg);
       } else {
-        epilogue_tile<BN2>(p, taddr, m0, n0, q, lane, first_split);
+        epilogue_dispatch<BN2, 0, BN2 / 32, SCFG>(p, taddr, m0, n0, q, lane, first_split, stg);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // leader's barrier
       if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1u; }
+      if (p.dbg) { t_wait += t1 - t0; t_epi += clock64() - t1; }
     }
+    if (p.dbg && lane == 0) {   // [4 + q] epilogue-warp cycles waiting for an accumulator, [8 + q] draining it (per lane quadrant)
+      atomicAdd(p.dbg + 4 + q, (unsigned long long)t_wait);
+      atomicAdd(p.dbg + 8 + q, (unsigned long long)t_epi);
+    }
+  }
+
+  else {
+    if constexpr (EPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // idle warps 2, 3 of warpgroup 0
   }
 
   tcgen05_fence_before();
@@ -232,12 +270,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   }
 }
 
-template <bool AK, bool BKM, int PASSES, int STAGES, int EPW = 4>
+template <bool AK, bool BKM, int PASSES, int STAGES, int EPW = 4, int SCFG = -1>
 int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * BK2 * 2 + HALF_N * BK2 * 2);
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  constexpr int SMEM = STAGES * STAGE_BYTES + EPW * EPI_STAGE_BYTES + 1024 + 256;
   static_assert(SMEM <= 227 * 1024, "tile configuration exceeds shared memory");
-  auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES, EPW>;
+  auto kern = gemm_tc2_kernel<AK, BKM, PASSES, STAGES, EPW, SCFG>;
   static bool done = false;
   if (!done) {
     VQ_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -248,7 +286,7 @@ int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   const int clusters = std::max(1, std::min(items, vq_sm_count() / 2));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * 2));
-  cfg.blockDim = dim3(64 + 32 * EPW);
+  cfg.blockDim = dim3(EPW == 8 ? 384 : 192);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -268,6 +306,8 @@ int launch_pair(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 
 }  // namespace
 
+namespace vqtc { int g_no_static_epilogue = 0; }
+
 // Tile configuration 4 of vqcpc_gemm_bf16x3_ex: CTA pairs, 256 x 256 x 32 tiles.  `p` carries m_tiles in units of 128
 // rows and n_tiles in units of 256 columns; maps[2..3] (B) must use boxes of 128 rows (K-major) / 64 x 32 (MN-major).
 int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st,
@@ -277,6 +317,29 @@ int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorM
     if (a_kmajor && !b_kmajor) return launch_pair<true, false, 3, 3, 8>(maps, p, st);
     if (!a_kmajor && b_kmajor) return launch_pair<false, true, 3, 3, 8>(maps, p, st);
     return launch_pair<false, false, 3, 3, 8>(maps, p, st);
+  }
+  // static epilogue configurations of the encoder's forward / data-gradient GEMMs (everything else: run-time flags)
+  if (passes == 3 && a_kmajor && p.ksplit == 1 && !g_no_static_epilogue) {
+    const int fl = p.ep.flags;
+    const bool aligned = (!p.C || (((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0))) &&
+                         (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                        ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                         (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                         (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                          (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+    if (aligned && (p.N % 32) == 0) {
+      const int scfg = fl | (p.C ? SCFG_C : 0) | (p.out_hi ? SCFG_SPLIT : 0);
+      if (b_kmajor) {
+        if (scfg == (EPI_BIAS | EPI_SCALE_COLS | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_SCALE_COLS | SCFG_C>(maps, p, st);
+        if (scfg == (EPI_BIAS | EPI_RESIDUAL | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_RESIDUAL | SCFG_C>(maps, p, st);
+        if (scfg == (EPI_BIAS | EPI_RELU | SCFG_SPLIT)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_RELU | SCFG_SPLIT>(maps, p, st);
+        if (scfg == (EPI_BIAS | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | SCFG_C>(maps, p, st);
+      } else {
+        if (scfg == (EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT)) return launch_pair<true, false, 3, 3, 4, EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT>(maps, p, st);
+        if (scfg == SCFG_C) return launch_pair<true, false, 3, 3, 4, SCFG_C>(maps, p, st);
+        if (scfg == (EPI_RESIDUAL | SCFG_C)) return launch_pair<true, false, 3, 3, 4, EPI_RESIDUAL | SCFG_C>(maps, p, st);
+      }
+    }
   }
   if (a_kmajor && b_kmajor) return passes == 3 ? launch_pair<true, true, 3, 3>(maps, p, st) : launch_pair<true, true, 1, 6>(maps, p, st);
   if (a_kmajor && !b_kmajor) return passes == 3 ? launch_pair<true, false, 3, 3>(maps, p, st) : launch_pair<true, false, 1, 6>(maps, p, st);

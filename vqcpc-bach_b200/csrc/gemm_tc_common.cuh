@@ -111,6 +111,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 32 columns in the mma-accumulator layout: thread t holds, for each 8-column group g = 0..3,
+// r[4g + 0..1] = (lane t/4, columns 8g + 2(t%4) + {0,1}) and r[4g + 2..3] = the same columns of lane t/4 + 8
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// fp32 pair -> packed bf16 (hi, lo) words with x ~= hi + lo: one cvt.rn.bf16x2.f32 per two values (same rounding as the
+// element-wise __float2bfloat16_rn, half the conversion instructions and no byte permutes)
+__device__ __forceinline__ void split_pair_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);                     // .x (low half) = x, .y = y
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __uint_as_float(hi << 16), y - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format: version=1 at bit 46, layout type at bits 61..63; SWIZZLE_128B = 2).
@@ -169,39 +188,82 @@ struct TcParams {
   int ldo;
   EpilogueParams ep;
   int m_tiles, n_tiles, ksplit, kblocks_per_split, kblocks_total;
+  int exp;                        // timing experiments (vqcpc_gemm_set_experiment; results invalid when non-zero)
+  unsigned long long* dbg;        // optional phase timers (vqcpc_gemm_set_debug): cycles summed over CTAs, see gemm_tc2.cu
 };
 
 // Epilogue of one 128 x BN accumulator tile held in TMEM at `taddr` (lane quadrant q of this warp): 32-column chunks,
 // tcgen05.ld -> fused bias / scale / residual / ReLU / mask -> fp32 and / or bf16-split stores (or atomics for split-K).
 // CH0 / CH1: range of 32-column chunks this warp drains (all of them by default; the 8-epilogue-warp variant of the pair
 // kernel gives each of the two warps of a lane quadrant one half of the columns).
+// Thread = row.  Round 2: the side inputs are software-pipelined - the tile's bias values are staged once per tile in the
+// warp's shared-memory buffer (`wbuf`, before the accumulator is waited for) and the residual / mask rows of chunk c + 1
+// are requested before chunk c is processed; round 1 issued them after each tcgen05.ld and exposed one L2 latency per
+// chunk, which is what held the K = 512 shapes with a residual at 780 tensor-TFLOP/s against 1200 without one.
 template <int BN, int CH0 = 0, int CH1 = BN / 32>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane, bool first_split) {
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane, bool first_split,
+                                              uint8_t* wbuf) {
+  static_assert(((CH1 - CH0) & 1) == 0, "chunk range must be even (the loop is unrolled by two)");
   const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-for (int ch = CH0; ch < CH1; ++ch) {
-  uint32_t r[32];
-  tmem_ld32(taddr + ch * 32, r);
-  tmem_ld_wait();
-  const int col0 = n0 + ch * 32;
-  if (row < p.M && col0 < p.N) {
+  const int fl = p.ep.flags;
+  const bool row_ok = row < p.M;
+  const bool aligned = (!p.C || (((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0))) &&
+                       (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                       (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                       (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                        (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+  const bool fast = aligned && !(fl & EPI_ATOMIC);
+  const bool use_bias = first_split && (fl & EPI_BIAS);
+  const bool use_res = first_split && (fl & EPI_RESIDUAL);
+  const bool mask_bf16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
+  const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
+  float* bias_s = reinterpret_cast<float*>(wbuf);
+
+  if (fast && use_bias) {
+    // the bias values of this warp's chunks: (CH1 - CH0) * 32 floats, 8 per lane where needed
+    __syncwarp();
+    for (int j = lane * 4; j < (CH1 - CH0) * 32; j += 128) {
+      const int col = n0 + CH0 * 32 + j;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
+      *reinterpret_cast<float4*>(bias_s + j) = b;
+    }
+    __syncwarp();
+  }
+  // residual / fp32 mask: 8 x float4 of this thread's row; bf16 mask: 4 x uint4 in s[0..3]
+  auto load_side = [&](int col0, float4 (&s)[8]) {
+    if (!row_ok || !fast || col0 + 32 > p.N) return;
+    if (use_res || mask_f32) {
+      const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) s[q4] = __ldg(rp + q4);
+    } else if (mask_bf16) {
+      const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0);
+#pragma unroll
+      for (int q8 = 0; q8 < 4; ++q8) s[q8] = __ldg(mp + q8);
+    }
+  };
+  long long t_ld = 0;
+  auto chunk = [&](int ch, float4 (&side)[8], float4 (&side_next)[8]) {
+    uint32_t r[32];
+    const long long tl0 = p.dbg ? clock64() : 0;
+    tmem_ld32(taddr + ch * 32, r);
+    const int col0 = n0 + ch * 32;
+    if (ch + 1 < CH1) load_side(col0 + 32, side_next);
+    tmem_ld_wait();
+    if (p.dbg) t_ld += clock64() - tl0;
+    if (!(row_ok && col0 < p.N)) return;
     float* dst = p.C ? p.C + (size_t)row * p.ldc + col0 : nullptr;
-    const int fl = p.ep.flags;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                         (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
-                                        ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
-                         (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
-                         (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
-                          (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
-    if (col0 + 32 <= p.N && aligned && !(fl & EPI_ATOMIC)) {
+    if (col0 + 32 <= p.N && fast) {
       // ---- fast path: 32 contiguous columns of one row per thread, all accesses 16-byte vectors
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (first_split && (fl & EPI_BIAS)) {
+      if (use_bias) {
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
-          float4 b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col0) + q4);
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + (ch - CH0) * 32 + q4 * 4);
           v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
         }
       }
@@ -209,11 +271,10 @@ for (int ch = CH0; ch < CH1; ++ch) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.ep.scale_ncols) ? v[j] * p.ep.alpha : v[j];
       }
-      if (first_split && (fl & EPI_RESIDUAL)) {
-        const float4* rp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+      if (use_res) {
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
-          float4 b = __ldg(rp + q4);
+          const float4 b = side[q4];
           v[q4 * 4] += b.x; v[q4 * 4 + 1] += b.y; v[q4 * 4 + 2] += b.z; v[q4 * 4 + 3] += b.w;
         }
       }
@@ -221,32 +282,27 @@ for (int ch = CH0; ch < CH1; ++ch) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (fl & EPI_RELU_MASK) {
-        if (fl & EPI_MASK_BF16) {
-          const uint4* mp = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0);
+      if (mask_bf16) {
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            uint4 mv = __ldg(mp + q8);
-            const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+        for (int q8 = 0; q8 < 4; ++q8) {
+          const float4 mv = side[q8];
+          const uint32_t w[4] = {__float_as_uint(mv.x), __float_as_uint(mv.y), __float_as_uint(mv.z), __float_as_uint(mv.w)};
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-              uint32_t lo16 = w[h] & 0xFFFFu, hi16 = w[h] >> 16;
-              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2] = 0.f;
-              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2 + 1] = 0.f;
-            }
+          for (int h = 0; h < 4; ++h) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            uint32_t lo16 = w[h] & 0xFFFFu, hi16 = w[h] >> 16;
+            if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2] = 0.f;
+            if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[q8 * 8 + h * 2 + 1] = 0.f;
           }
-        } else {
-          const float4* mp = reinterpret_cast<const float4*>(p.ep.residual + (size_t)row * p.ep.ldr + col0);
+        }
+      } else if (mask_f32) {
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            float4 b = __ldg(mp + q4);
-            if (!(b.x > 0.f)) v[q4 * 4] = 0.f;
-            if (!(b.y > 0.f)) v[q4 * 4 + 1] = 0.f;
-            if (!(b.z > 0.f)) v[q4 * 4 + 2] = 0.f;
-            if (!(b.w > 0.f)) v[q4 * 4 + 3] = 0.f;
-          }
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 b = side[q4];
+          if (!(b.x > 0.f)) v[q4 * 4] = 0.f;
+          if (!(b.y > 0.f)) v[q4 * 4 + 1] = 0.f;
+          if (!(b.z > 0.f)) v[q4 * 4 + 2] = 0.f;
+          if (!(b.w > 0.f)) v[q4 * 4 + 3] = 0.f;
         }
       }
       if (dst) {
@@ -264,13 +320,7 @@ for (int ch = CH0; ch < CH1; ++ch) {
       if (p.out_hi) {
         uint32_t hw[16], lw[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-          __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-          __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-          hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
+        for (int j = 0; j < 16; ++j) split_pair_bf16(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
         uint4* hp = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldo + col0);
         uint4* lp = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldo + col0);
 #pragma unroll
@@ -298,14 +348,365 @@ for (int ch = CH0; ch < CH1; ++ch) {
         }
       }
     }
+  };
+
+  float4 sa[8], sb[8];
+  load_side(n0 + CH0 * 32, sa);
+#pragma unroll 1
+  for (int ch = CH0; ch < CH1; ch += 2) {
+    chunk(ch, sa, sb);
+    chunk(ch + 1, sb, sa);
+  }
+  if (p.dbg && lane == 0 && q == 0) atomicAdd(p.dbg + 3, (unsigned long long)t_ld);   // quadrant 0: tcgen05.ld issue -> data
+}
+
+// Quad epilogue (round 2, the default): same contract and bit-identical results as `epilogue_tile`, with 4x fewer cache
+// lines per load / store instruction.  Why: with thread = row every 16-byte access of a warp touches 32 different lines, and
+// the L1/LSU pipe spends one cycle per line - 256 cycles per 32 x 32 chunk and matrix, 8 k (fp32 or split output) to 16 k
+// (plus an fp32 residual) cycles per 128 x 256 tile against 12.3 k cycles of MMA at K = 512.  Measured (gemm_check, stores
+// removed): the K = 512 shapes run at 1160 - 1660 tensor-TFLOP/s without their stores and 815 - 1100 with them.  Staging
+// through shared memory (`epilogue_tile_staged`) is no way out: the MMA operand reads and the TMA writes already take
+// ~106 of the 128 B/clk of shared-memory bandwidth.  Here the accumulator is read in the 16x256b (mma fragment) layout - a
+// quad of lanes holds 8 consecutive columns of a row - and ONE shuffle exchange between neighbouring lanes gives every
+// lane 4 consecutive columns: a quad then covers 64 contiguous bytes of a row and a warp instruction 8 rows (8 lines).
+//   lane = 4 rq + j,  b = j & 1, c = j >> 1;  after the exchange the lane holds, for h, s, k in {0, 1},
+//   row 16 h + 8 s + rq,  columns 8 (2 k + b) + 4 c + {0 .. 3}   of the chunk.
+// Split-K atomics, accumulate and unaligned operands take an element-wise path in the same fragment layout.
+// SCFG >= 0: the epilogue is known when the kernel is compiled (SCFG_* bits: the EPI_* flags, which outputs exist; the
+// host launches such a kernel only for aligned operands, N % 32 == 0 and no split-K) - the code below then folds into a
+// straight line.  With run-time flags every (h, s, k) block carries ~10 branches, and one warp per scheduler pays the full
+// branch latency for each: measured 2.7 k cycles per chunk with the stores removed.
+constexpr int SCFG_C = 0x100, SCFG_SPLIT = 0x200;
+template <int BN, int CH0 = 0, int CH1 = BN / 32, int SCFG = -1>
+__device__ __forceinline__ void epilogue_tile_quad(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane,
+                                                   bool first_split_rt, uint8_t* wbuf) {
+  static_assert(((CH1 - CH0) & 1) == 0, "chunk range must be even (the loop is unrolled by two)");
+  constexpr bool ST = SCFG >= 0;
+  const int fl = ST ? (SCFG & 0xff) : p.ep.flags;
+  const bool first_split = ST ? true : first_split_rt;
+  const bool has_c = ST ? ((SCFG & SCFG_C) != 0) : (p.C != nullptr);
+  const bool has_split = ST ? ((SCFG & SCFG_SPLIT) != 0) : (p.out_hi != nullptr);
+  const bool aligned = ST ? true : (!p.C || (((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0))) &&
+                       (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                       (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                       (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                        (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+  const bool fast = aligned && !(fl & (EPI_ATOMIC | EPI_ACCUMULATE));
+  const bool use_bias = fast && first_split && (fl & EPI_BIAS);
+  const bool use_res = first_split && (fl & EPI_RESIDUAL);
+  const bool mask_bf16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
+  const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
+  const int rq = lane >> 2, j = lane & 3, b = j & 1, c = j >> 1;
+  const int row0 = m0 + q * 32 + rq;                 // + 16 h + 8 s
+  const int cofs = 8 * b + 4 * c;                    // + 16 k
+  float* bias_s = reinterpret_cast<float*>(wbuf);
+
+  if (use_bias) {
+    __syncwarp();
+    for (int i = lane * 4; i < (CH1 - CH0) * 32; i += 128) {
+      const int col = n0 + CH0 * 32 + i;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col + 4 <= p.N) bv = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
+      *reinterpret_cast<float4*>(bias_s + i) = bv;
+    }
+    __syncwarp();
+  }
+  // side inputs of one chunk in the post-exchange layout: index (2 h + s) * 2 + k; bf16 masks use .x / .y
+  auto load_side = [&](int col0, float4 (&sd)[8]) {
+    if (!ST && (col0 + 32 > p.N || !fast)) return;
+    if (use_res || mask_f32) {
+#pragma unroll
+      for (int hs = 0; hs < 4; ++hs) {
+        const int row = row0 + 8 * hs;
+        if (row < p.M) {
+          const float* rp = p.ep.residual + (size_t)row * p.ep.ldr + col0 + cofs;
+          sd[hs * 2] = __ldg(reinterpret_cast<const float4*>(rp));
+          sd[hs * 2 + 1] = __ldg(reinterpret_cast<const float4*>(rp + 16));
+        }
+      }
+    } else if (mask_bf16) {
+#pragma unroll
+      for (int hs = 0; hs < 4; ++hs) {
+        const int row = row0 + 8 * hs;
+        if (row < p.M) {
+          const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.ep.residual) + (size_t)row * p.ep.ldr + col0 + cofs;
+          const uint2 m0v = __ldg(reinterpret_cast<const uint2*>(mp)), m1v = __ldg(reinterpret_cast<const uint2*>(mp + 16));
+          sd[hs * 2].x = __uint_as_float(m0v.x); sd[hs * 2].y = __uint_as_float(m0v.y);
+          sd[hs * 2 + 1].x = __uint_as_float(m1v.x); sd[hs * 2 + 1].y = __uint_as_float(m1v.y);
+        }
+      }
+    }
+  };
+  long long t_ld = 0;
+  auto chunk = [&](int ch, float4 (&side)[8], float4 (&side_next)[8]) {
+    uint32_t a[2][16];
+    const long long tl0 = p.dbg ? clock64() : 0;
+    tmem_ld_16x256b_x4(taddr + ch * 32, a[0]);
+    tmem_ld_16x256b_x4(taddr + (16u << 16) + ch * 32, a[1]);
+    const int col0 = n0 + ch * 32;
+    if (ch + 1 < CH1) load_side(col0 + 32, side_next);
+    tmem_ld_wait();
+    if (p.dbg) t_ld += clock64() - tl0;
+    if (col0 >= p.N) return;
+    if (!ST && (col0 + 32 > p.N || !fast)) {
+      // ---- chunk partial in N, split-K atomics, accumulate, unaligned operands: element-wise from the fragment layout
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = row0 + 16 * h + 8 * ((i >> 1) & 1), col = col0 + 8 * (i >> 2) + 2 * j + (i & 1);
+          if (row < p.M && col < p.N) {
+            float v = epilogue_apply(__uint_as_float(a[h][i]), row, col, p.ep, first_split);
+            if (p.C) {
+              float* dst = p.C + (size_t)row * p.ldc + col;
+              if (fl & EPI_ATOMIC) atomicAdd(dst, v);
+              else if (fl & EPI_ACCUMULATE) { v += *dst; *dst = v; }
+              else *dst = v;
+            }
+            if (p.out_hi) {
+              const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+              p.out_hi[(size_t)row * p.ldo + col] = hv;
+              p.out_lo[(size_t)row * p.ldo + col] = __float2bfloat16_rn(v - __bfloat162float(hv));
+            }
+          }
+        }
+      return;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          // even / odd 8-column group of this pair of groups: the lane keeps group 2 k + b and trades the other one
+          const uint32_t e0 = a[h][8 * k + 2 * s], e1 = a[h][8 * k + 2 * s + 1];
+          const uint32_t o0 = a[h][8 * k + 4 + 2 * s], o1 = a[h][8 * k + 4 + 2 * s + 1];
+          const uint32_t g0 = __shfl_xor_sync(0xffffffffu, b ? e0 : o0, 1);
+          const uint32_t g1 = __shfl_xor_sync(0xffffffffu, b ? e1 : o1, 1);
+          float v0 = __uint_as_float(b ? g0 : e0), v1 = __uint_as_float(b ? g1 : e1);
+          float v2 = __uint_as_float(b ? o0 : g0), v3 = __uint_as_float(b ? o1 : g1);
+          const int row = row0 + 16 * h + 8 * s;
+          const bool row_ok = row < p.M;                 // (stores are predicated: no branch in the block)
+          const int col = col0 + cofs + 16 * k;
+          const float4 sdv = side[(2 * h + s) * 2 + k];
+          if (use_bias) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + (ch - CH0) * 32 + cofs + 16 * k);
+            v0 += bv.x; v1 += bv.y; v2 += bv.z; v3 += bv.w;
+          }
+          if (fl & EPI_SCALE_COLS) {
+            v0 = (col < p.ep.scale_ncols) ? v0 * p.ep.alpha : v0;
+            v1 = (col + 1 < p.ep.scale_ncols) ? v1 * p.ep.alpha : v1;
+            v2 = (col + 2 < p.ep.scale_ncols) ? v2 * p.ep.alpha : v2;
+            v3 = (col + 3 < p.ep.scale_ncols) ? v3 * p.ep.alpha : v3;
+          }
+          if (use_res) { v0 += sdv.x; v1 += sdv.y; v2 += sdv.z; v3 += sdv.w; }
+          if (fl & EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+          if (mask_f32) {
+            if (!(sdv.x > 0.f)) v0 = 0.f;
+            if (!(sdv.y > 0.f)) v1 = 0.f;
+            if (!(sdv.z > 0.f)) v2 = 0.f;
+            if (!(sdv.w > 0.f)) v3 = 0.f;
+          } else if (mask_bf16) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t w0 = __float_as_uint(sdv.x), w1 = __float_as_uint(sdv.y);
+            if (!((w0 & 0x8000u) == 0 && (w0 & 0x7FFFu) != 0)) v0 = 0.f;
+            if (!((w0 & 0x80000000u) == 0 && (w0 & 0x7FFF0000u) != 0)) v1 = 0.f;
+            if (!((w1 & 0x8000u) == 0 && (w1 & 0x7FFFu) != 0)) v2 = 0.f;
+            if (!((w1 & 0x80000000u) == 0 && (w1 & 0x7FFF0000u) != 0)) v3 = 0.f;
+          }
+          if (has_c && row_ok) st4(p.C + (size_t)row * p.ldc + col, make_float4(v0, v1, v2, v3));
+          if (has_split) {
+            uint2 hw, lw;
+            split_pair_bf16(v0, v1, hw.x, lw.x);
+            split_pair_bf16(v2, v3, hw.y, lw.y);
+            if (row_ok) {
+              *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ldo + col) = hw;
+              *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ldo + col) = lw;
+            }
+          }
+        }
+  };
+
+  float4 sa[8], sb[8];
+  load_side(n0 + CH0 * 32, sa);
+#pragma unroll 1
+  for (int ch = CH0; ch < CH1; ch += 2) {
+    chunk(ch, sa, sb);
+    chunk(ch + 1, sb, sa);
+  }
+  if (p.dbg && lane == 0 && q == 0) atomicAdd(p.dbg + 3, (unsigned long long)t_ld);   // quadrant 0: tcgen05.ld issue -> data
+}
+
+// Epilogue variant, chosen when the library is built (-DVQ_EPI_KIND=k; one variant per kernel keeps its register allocation
+// clean - all three inlined behind a run-time switch cost 255 registers and spills): 0 = quad (default; the only one with
+// compile-time epilogue configurations), 1 = staged through shared memory, 2 = thread-per-row.  Results are bit-identical; tools/gemm_check.py --libs compares builds.
+#ifndef VQ_EPI_KIND
+#define VQ_EPI_KIND 0
+#endif
+
+template <int BN, int CH0 = 0, int CH1 = BN / 32, int SCFG = -1>
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane,
+                                                  bool first_split, uint8_t* wbuf);
+
+// Bytes of shared memory each epilogue warp owns as its transpose buffer (32 rows x 128 bytes).
+constexpr int EPI_STAGE_BYTES = 4096;
+
+// Staged epilogue (the default): same contract and bit-identical results as `epilogue_tile`, but every global access of a
+// warp covers whole 128-byte lines.  A 32-column chunk goes TMEM -> registers (thread = row) -> the warp's swizzled
+// shared-memory buffer -> registers again with 8 lanes per row (lane = 4 consecutive columns, 4 rows per instruction).
+// The thread-per-row form issues 16-byte accesses to 32 different lines per instruction and serialises one global-load
+// latency (bias / residual / mask) behind every tcgen05.ld: ncu on the K = 512 shapes showed 4 epilogue warps needing about
+// twice the tile's MMA time (tensor pipe 48-51 % active).  Here the next chunk's tcgen05.ld and its residual / mask / bias
+// loads are in flight while the current chunk is written out.  Chunks that are partial in N and the atomic / accumulate
+// modes take the element-wise path of `epilogue_tile`.
+template <int BN, int CH0 = 0, int CH1 = BN / 32>
+__device__ __forceinline__ void epilogue_tile_staged(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane,
+                                                     bool first_split, uint8_t* stage) {
+  const int fl = p.ep.flags;
+  const bool aligned = (!p.C || (((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 3) == 0))) &&
+                       (!p.out_hi || (((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 15) == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(p.out_lo) & 15) == 0))) &&
+                       (!(fl & EPI_BIAS) || ((reinterpret_cast<uintptr_t>(p.ep.bias) & 15) == 0)) &&
+                       (!(fl & (EPI_RESIDUAL | EPI_RELU_MASK)) ||
+                        (((p.ep.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.ep.residual) & 15) == 0)));
+  const bool fast = aligned && !(fl & (EPI_ATOMIC | EPI_ACCUMULATE)) && ((n0 & 3) == 0);
+  const bool use_bias = first_split && (fl & EPI_BIAS);
+  const bool use_res = first_split && (fl & EPI_RESIDUAL);
+  const bool mask_bf16 = (fl & EPI_RELU_MASK) && (fl & EPI_MASK_BF16);
+  const bool mask_f32 = (fl & EPI_RELU_MASK) && !(fl & EPI_MASK_BF16);
+  const int sr = lane >> 3, cg = lane & 7;          // transposed phase: sub-row and 16-byte column group of this lane
+  const int row_t = m0 + q * 32 + sr;               // + 4 i
+  const int row_own = m0 + q * 32 + lane;           // thread-per-row phase
+
+  // side inputs of one chunk for the transposed phase: aux[i] = residual / fp32 mask (float4) or bf16 mask (x, y words)
+  float4 aux[8], aux_n[8];
+  float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), bia_n = bia;
+  auto load_side = [&](int col0, float4 (&a)[8], float4& b) {
+    const int col = col0 + cg * 4;
+    if (use_bias) b = __ldg(reinterpret_cast<const float4*>(p.ep.bias + col));
+    if (use_res || mask_f32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (row_t + 4 * i < p.M) a[i] = __ldg(reinterpret_cast<const float4*>(p.ep.residual + (size_t)(row_t + 4 * i) * p.ep.ldr + col));
+    } else if (mask_bf16) {
+      const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.ep.residual);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (row_t + 4 * i < p.M) {
+          const uint2 mv = __ldg(reinterpret_cast<const uint2*>(mp + (size_t)(row_t + 4 * i) * p.ep.ldr + col));
+          a[i].x = __uint_as_float(mv.x);
+          a[i].y = __uint_as_float(mv.y);
+        }
+    }
+  };
+
+  uint32_t r[32];
+  tmem_ld32(taddr + CH0 * 32, r);
+  if (fast && n0 + CH0 * 32 + 32 <= p.N) load_side(n0 + CH0 * 32, aux, bia);
+#pragma unroll 1
+  for (int ch = CH0; ch < CH1; ++ch) {
+    const int col0 = n0 + ch * 32;
+    tmem_ld_wait();
+    if (col0 >= p.N) break;
+    const bool full = fast && (col0 + 32 <= p.N);
+    if (full) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    } else if (row_own < p.M) {
+      // ---- partial chunk / split-K / accumulate: element-wise
+      float* dst = p.C ? p.C + (size_t)row_own * p.ldc + col0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < p.N) {
+          float v = epilogue_apply(__uint_as_float(r[j]), row_own, col0 + j, p.ep, first_split);
+          if (dst) {
+            if (fl & EPI_ATOMIC) atomicAdd(dst + j, v);
+            else if (fl & EPI_ACCUMULATE) { v += dst[j]; dst[j] = v; }
+            else dst[j] = v;
+          }
+          if (p.out_hi) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            p.out_hi[(size_t)row_own * p.ldo + col0 + j] = h;
+            p.out_lo[(size_t)row_own * p.ldo + col0 + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+          }
+        }
+      }
+    }
+    // the accumulator registers are dead: fetch the next chunk while this one is written out
+    const bool more = ch + 1 < CH1 && col0 + 32 < p.N;
+    if (more) tmem_ld32(taddr + (ch + 1) * 32, r);
+    if (!full) continue;
+    __syncwarp();
+    const bool next_full = more && (col0 + 64 <= p.N);
+    if (next_full) load_side(col0 + 32, aux_n, bia_n);
+    const int col = col0 + cg * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = 4 * i + sr;
+      const float4 t = *reinterpret_cast<const float4*>(stage + rr * 128 + ((cg ^ (rr & 7)) << 4));
+      const int row = row_t + 4 * i;
+      if (row < p.M) {
+        float v0 = t.x, v1 = t.y, v2 = t.z, v3 = t.w;
+        if (use_bias) { v0 += bia.x; v1 += bia.y; v2 += bia.z; v3 += bia.w; }
+        if (fl & EPI_SCALE_COLS) {
+          v0 = (col < p.ep.scale_ncols) ? v0 * p.ep.alpha : v0;
+          v1 = (col + 1 < p.ep.scale_ncols) ? v1 * p.ep.alpha : v1;
+          v2 = (col + 2 < p.ep.scale_ncols) ? v2 * p.ep.alpha : v2;
+          v3 = (col + 3 < p.ep.scale_ncols) ? v3 * p.ep.alpha : v3;
+        }
+        if (use_res) { v0 += aux[i].x; v1 += aux[i].y; v2 += aux[i].z; v3 += aux[i].w; }
+        if (fl & EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        if (mask_f32) {
+          if (!(aux[i].x > 0.f)) v0 = 0.f;
+          if (!(aux[i].y > 0.f)) v1 = 0.f;
+          if (!(aux[i].z > 0.f)) v2 = 0.f;
+          if (!(aux[i].w > 0.f)) v3 = 0.f;
+        } else if (mask_bf16) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t w0 = __float_as_uint(aux[i].x), w1 = __float_as_uint(aux[i].y);
+          if (!((w0 & 0x8000u) == 0 && (w0 & 0x7FFFu) != 0)) v0 = 0.f;
+          if (!((w0 & 0x80000000u) == 0 && (w0 & 0x7FFF0000u) != 0)) v1 = 0.f;
+          if (!((w1 & 0x8000u) == 0 && (w1 & 0x7FFFu) != 0)) v2 = 0.f;
+          if (!((w1 & 0x80000000u) == 0 && (w1 & 0x7FFF0000u) != 0)) v3 = 0.f;
+        }
+        if (p.C) st4(p.C + (size_t)row * p.ldc + col, make_float4(v0, v1, v2, v3));
+        if (p.out_hi) {
+          uint2 hw, lw;
+          split_pair_bf16(v0, v1, hw.x, lw.x);
+          split_pair_bf16(v2, v3, hw.y, lw.y);
+          *reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.ldo + col) = hw;
+          *reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.ldo + col) = lw;
+        }
+      }
+    }
+    __syncwarp();                                   // the buffer is rewritten by the next chunk
+    if (next_full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aux[i] = aux_n[i];
+      bia = bia_n;
+    }
   }
 }
+
+template <int BN, int CH0, int CH1, int SCFG>
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t taddr, int m0, int n0, int q, int lane,
+                                                  bool first_split, uint8_t* wbuf) {
+#if VQ_EPI_KIND == 0
+  epilogue_tile_quad<BN, CH0, CH1, SCFG>(p, taddr, m0, n0, q, lane, first_split, wbuf);
+#elif VQ_EPI_KIND == 1
+  epilogue_tile_staged<BN, CH0, CH1>(p, taddr, m0, n0, q, lane, first_split, wbuf);
+#else
+  epilogue_tile<BN, CH0, CH1>(p, taddr, m0, n0, q, lane, first_split, wbuf);
+#endif
 }
 
 // host helpers shared by both kernels (defined in gemm_tc.cu)
 int tc_get_encode();
 int tc_make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows);
 // CTA-pair kernel (gemm_tc2.cu)
+extern int g_no_static_epilogue;      // test hook: 1 = always the run-time-flag epilogue
 int tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorMap* maps, const TcParams& p, cudaStream_t st,
                    bool eight_epilogue_warps = false);
 
