@@ -132,6 +132,25 @@ int vqcpc_gemm_set_debug(void* buf);
 /* profiling hook: timing experiments inside the GEMM epilogue (0 = off; non-zero values skip work and give INVALID results) */
 int vqcpc_gemm_set_experiment(int e);
 
+/* ---- full-sequence relative self-attention, L <= 1024 (student / teacher / auxiliary-decoder transformers:
+ *      teachers/teacher_relative.py:33-47, auxiliary_decoders/auxiliary_decoder_relative.py:58-74; same layer math as the
+ *      per-block kernels below: multihead_attention_custom.py:274-345 + subsampled_relative_attention.py:30-122) --------
+ * qkv (P*L, 3*H*64) with the q third pre-scaled, e1 / e2 (H*L, 64); out (P*L, H*64) fp32 and / or bf16 split;
+ * probs (P, H, L, L) or NULL.  Backward: d_qkv (and / or its split) overwritten, q third = q_scale * dq~; d_e1 / d_e2
+ * ACCUMULATED; ds_scratch = (P, H, L, L) floats of caller-owned scratch. */
+int vqcpc_attn_long_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                        float* probs, int64_t P, int L, int H, int head_dim, void* stream);
+int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e2, const float* probs, const float* d_out,
+                        float* ds_scratch, float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P,
+                        int L, int H, int head_dim, float q_scale, void* stream);
+
+/* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159
+ *      distilled_categorical_crossentropy) --------------------------------------------------------------------------
+ * logits (rows, C; ld).  Exactly one of target_idx (int64 class per row) / target_logits (rows, C; ldt: the teacher's
+ * logits, target distribution = their softmax).  loss (rows) and / or d_logits (rows, C; ldd) = scale * dloss/dlogits. */
+int vqcpc_softmax_ce(const float* logits, int ld, const int64_t* target_idx, const float* target_logits, int ldt, float* loss,
+                     float* d_logits, int ldd, float scale, int64_t rows, int C, void* stream);
+
 /* ---- per-block relative self-attention (multihead_attention_custom.py:274-345 +
  *      subsampled_relative_attention.py:30-122) ---------------------------------------------------------------------
  * qkv (P*L, 3*H*64), q third pre-scaled by hd^-0.5; e1, e2 (H*L, 64).  Only the query rows with token % keep == 0 are

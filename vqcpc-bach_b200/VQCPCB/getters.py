@@ -1,12 +1,14 @@
 """String-keyed factories for the encoder-training path (mirror of VQCPCB/getters.py:24-218, :431-516).
 
-Only the branches reachable from ``main_encoder.py -t`` with ``training_method='vqcpc'`` are built; the student /
-decoder / prior branches raise NotImplementedError with a pointer to SURVEY.md §8f.  Config keys that several shipped
+Built: the branches reachable from ``main_encoder.py -t`` with ``training_method='vqcpc'`` and ``'student'`` (teacher +
+auxiliary decoder, getters.py:221-262, :444-482); the decoder / prior branches raise NotImplementedError with a pointer to
+SURVEY.md §8f.  Config keys that several shipped
 configs omit (``c_net_kwargs['bidirectional']``, ``schedule_lr``) get the reference's de-facto defaults.
 """
 from .data_processor.bach_cpc_data_processor import BachCPCDataProcessor
 from .data_processor.bach_data_processor import BachDataProcessor
 from .dataloaders.synthetic_cpc_dataloader import SyntheticCPCDataloaderGenerator
+from .dataloaders.synthetic_dataloader import SyntheticDataloaderGenerator
 from .downscalers.lstm_downscaler import LstmDownscaler
 from .downscalers.relative_transformer_downscaler import RelativeTransformerDownscaler
 from .downscalers.relative_transformer_downscaler_linear import RelativeTransformerDownscalerLinear
@@ -22,6 +24,12 @@ def get_dataloader_generator(dataset, training_method, dataloader_generator_kwar
     """'bach' needs the music21 chorale corpus (absent offline); 'synthetic' is the in-scope producer with the same
     batch-dict contract."""
     kw = dataloader_generator_kwargs
+    if training_method.lower() == 'student':
+        if dataset.lower() in ('synthetic', 'bach_synthetic'):
+            return SyntheticDataloaderGenerator(sequences_size=kw['sequences_size'], vocab_size=kw.get('vocab_size', 64),
+                                                seed=kw.get('seed', 1234))
+        raise NotImplementedError('dataset="bach" needs music21 and the chorale corpus, which are not available here; '
+                                  'use dataset="synthetic" (same batch contract: tensor_dict["x"] (batch, events, channels))')
     if training_method.lower() != 'vqcpc':
         raise NotImplementedError(f'training_method={training_method!r} {_NEXT}')
     if dataset.lower() in ('synthetic', 'bach_synthetic'):
@@ -89,7 +97,7 @@ def get_data_processor(dataloader_generator, data_processor_type, data_processor
 
 def get_encoder(model_dir, dataloader_generator, config):
     method = config['training_method'].lower()
-    if method != 'vqcpc':
+    if method not in ('vqcpc', 'student'):
         raise NotImplementedError(f'training_method={method!r} {_NEXT}')
     qk = config['quantizer_kwargs']
     dk = config['downscaler_kwargs']
@@ -110,7 +118,7 @@ def get_encoder(model_dir, dataloader_generator, config):
     else:
         raise NotImplementedError(f"quantizer_type={config['quantizer_type']!r}")
     upscaler = None
-    if config['upscaler_type'] is not None:
+    if config.get('upscaler_type') is not None:
         uk = config['upscaler_kwargs']
         uk['input_dim'] = qk['codebook_dim']
         upscaler = get_upscaler(config['upscaler_type'], uk)
@@ -123,4 +131,47 @@ def get_encoder_trainer(model_dir, dataloader_generator, training_method, encode
         return VQCPCEncoderTrainer(model_dir=model_dir, dataloader_generator=dataloader_generator, encoder=encoder,
                                    c_net_kwargs=auxiliary_networks_kwargs['c_net_kwargs'],
                                    quantization_weighting=auxiliary_networks_kwargs['quantization_weighting'])
+    if training_method.lower() == 'student':
+        import numpy as np
+        from .student_encoder_trainer import StudentEncoderTrainer
+        # runtime-injected keys (getters.py:446-468)
+        tk = auxiliary_networks_kwargs['teacher_kwargs']
+        tk['num_tokens_per_channel'] = encoder.data_processor.num_tokens_per_channel
+        tk['num_tokens'] = encoder.data_processor.num_tokens
+        teacher = get_teacher(auxiliary_networks_kwargs['teacher_type'], tk, dataloader_generator)
+        ak = auxiliary_networks_kwargs['auxiliary_decoder_kwargs']
+        ak['num_tokens_per_channel'] = encoder.data_processor.num_tokens_per_channel
+        ak['codebook_dim'] = encoder.quantizer.codebook_dim
+        ak['upscale_factors'] = list(reversed(encoder.downscaler.downscale_factors))
+        ak['num_tokens_bottleneck'] = encoder.data_processor.num_tokens // int(np.prod(encoder.downscaler.downscale_factors))
+        auxiliary_decoder = get_auxiliary_decoder(auxiliary_networks_kwargs['auxiliary_decoder_type'], ak)
+        return StudentEncoderTrainer(model_dir=model_dir, dataloader_generator=dataloader_generator, encoder=encoder,
+                                     teacher=teacher, auxiliary_decoder=auxiliary_decoder,
+                                     quantization_weighting=auxiliary_networks_kwargs['quantization_weighting'],
+                                     num_events_masked=auxiliary_networks_kwargs['num_events_masked'])
     raise NotImplementedError(f'training_method={training_method!r} {_NEXT}')
+
+
+def get_teacher(teacher_type, teacher_kwargs, dataloader_generator):
+    """getters.py:221-241 (only the relative teacher is shipped with a config)."""
+    from .teachers.teacher_relative import TeacherRelative
+    if teacher_type != 'relative':
+        raise NotImplementedError(f'teacher_type={teacher_type!r} {_NEXT}')
+    dpc = teacher_kwargs['data_processor_config']
+    data_processor = get_data_processor(dataloader_generator, dpc['data_processor_type'], dpc['data_processor_kwargs'])
+    return TeacherRelative(num_layers=teacher_kwargs['num_layers'], num_tokens_per_channel=teacher_kwargs['num_tokens_per_channel'],
+                           d_model=teacher_kwargs['d_model'], positional_embedding_size=teacher_kwargs['positional_embedding_size'],
+                           dim_feedforward=teacher_kwargs['dim_feedforward'], n_head=teacher_kwargs['n_head'],
+                           dropout=teacher_kwargs['dropout'], num_tokens=teacher_kwargs['num_tokens'], data_processor=data_processor)
+
+
+def get_auxiliary_decoder(auxiliary_decoder_type, auxiliary_decoder_kwargs):
+    """getters.py:244-272 (relative variant)."""
+    from .auxiliary_decoders.auxiliary_decoder_relative import AuxiliaryDecoderRelative
+    if auxiliary_decoder_type != 'relative':
+        raise NotImplementedError(f'auxiliary_decoder_type={auxiliary_decoder_type!r} {_NEXT}')
+    k = auxiliary_decoder_kwargs
+    return AuxiliaryDecoderRelative(num_tokens_per_channel=k['num_tokens_per_channel'], codebook_dim=k['codebook_dim'],
+                                    upscale_factors=k['upscale_factors'], n_head=k['n_head'], dim_feedforward=k['dim_feedforward'],
+                                    list_of_num_layers=k['list_of_num_layers'], d_model=k['d_model'],
+                                    num_tokens_bottleneck=k['num_tokens_bottleneck'], dropout=k['dropout'])

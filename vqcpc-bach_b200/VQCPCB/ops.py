@@ -305,6 +305,14 @@ def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, 
     """-> (out fp32 | None, probs) or (out | None, (hi, lo), probs) when want_split; rows = P * L / keep.
     drop = (keep_mask uint8 (P, H, L, L), scale): dropout on the attention weights.
     algo: None = by GEMM mode (see _select_attn_kernel), 0 = tensor cores, 1 = CUDA cores."""
+    if L > 16:
+        # whole-sequence attention (teacher / auxiliary decoder of the student trainer): csrc/attn_long.cu
+        assert keep == 1 and drop is None, 'full-sequence attention has no dead-row elimination / attention dropout'
+        out = torch.empty(P * L, H * hd, dtype=torch.float32, device=qkv.device) if want_fp32 else None
+        sp = _split_buffers(P * L, H * hd, qkv.device) if want_split else (None, None)
+        probs = torch.empty(P, H, L, L, dtype=torch.float32, device=qkv.device) if need_probs else None
+        _native.call('vqcpc_attn_long_fwd', _p(qkv), _p(e1), _p(e2), _p(out), _p(sp[0]), _p(sp[1]), _p(probs), P, L, H, hd, _stream())
+        return (out, sp, probs) if want_split else (out, probs)
     _select_attn_kernel('fwd', algo)
     Mo = P * (L // keep)
     out = torch.empty(Mo, H * hd, dtype=torch.float32, device=qkv.device) if want_fp32 else None
@@ -319,6 +327,14 @@ def attn_fwd(qkv, e1, e2, P, L, H, hd, need_probs=True, keep=1, want_fp32=True, 
 
 def attn_bwd(qkv, e1, e2, probs, dout, de1, de2, P, L, H, hd, q_scale, keep=1, want_fp32=True, want_split=False, drop=None,
              algo=None):
+    if L > 16:
+        assert keep == 1 and drop is None
+        dqkv = torch.empty_like(qkv) if want_fp32 else None
+        sp = _split_buffers(qkv.shape[0], qkv.shape[1], qkv.device) if want_split else (None, None)
+        ds = torch.empty_like(probs)
+        _native.call('vqcpc_attn_long_bwd', _p(qkv), _p(e1), _p(e2), _p(probs), _p(_f32c(dout)), _p(ds), _p(dqkv), _p(sp[0]), _p(sp[1]),
+                     _p(de1), _p(de2), P, L, H, hd, float(q_scale), _stream())
+        return (dqkv, sp) if want_split else dqkv
     _select_attn_kernel('bwd', algo)
     dqkv = torch.empty_like(qkv) if want_fp32 else None
     sp = _split_buffers(qkv.shape[0], qkv.shape[1], qkv.device) if want_split else (None, None)
@@ -348,6 +364,19 @@ def dropout_mask(site, shape, p, device):
     if DROPOUT_MASK_HOOK is not None:
         return DROPOUT_MASK_HOOK(site, tuple(shape), p, device)
     return draw_keep_mask(shape, p, device)
+
+
+def softmax_ce(logits, target_idx=None, target_logits=None, scale=1.0, want_grad=True):
+    """Row-wise softmax cross-entropy (hard int64 targets or distilled = a teacher's logits) -> (loss (rows,), scale * dloss/dlogits)."""
+    logits = _f32c(logits)
+    rows, C = logits.shape
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    if target_logits is not None:
+        target_logits = _f32c(target_logits)
+    _native.call('vqcpc_softmax_ce', _p(logits), C, _p(target_idx), _p(target_logits), C, _p(loss), _p(dl), C, float(scale), rows, C,
+                 _stream())
+    return loss, dl
 
 
 def reduce_sum(x, scale=1.0):

@@ -439,13 +439,13 @@ __device__ __forceinline__ void epilogue_tile_quad(const TcParams& p, uint32_t t
     }
   };
   long long t_ld = 0;
-  auto chunk = [&](int ch, float4 (&side)[8], float4 (&side_next)[8]) {
+  auto chunk = [&](int ch, float4 (&side)[8], float4 (&side_next)[8], int dist) {
     uint32_t a[2][16];
     const long long tl0 = p.dbg ? clock64() : 0;
     tmem_ld_16x256b_x4(taddr + ch * 32, a[0]);
     tmem_ld_16x256b_x4(taddr + (16u << 16) + ch * 32, a[1]);
     const int col0 = n0 + ch * 32;
-    if (ch + 1 < CH1) load_side(col0 + 32, side_next);
+    if (ch + dist < CH1) load_side(col0 + 32 * dist, side_next);
     tmem_ld_wait();
     if (p.dbg) t_ld += clock64() - tl0;
     if (col0 >= p.N) return;
@@ -528,12 +528,23 @@ __device__ __forceinline__ void epilogue_tile_quad(const TcParams& p, uint32_t t
         }
   };
 
-  float4 sa[8], sb[8];
-  load_side(n0 + CH0 * 32, sa);
+  constexpr bool DEEP = ST && ((SCFG & (EPI_RESIDUAL | EPI_RELU_MASK)) != 0) && (CH1 - CH0 >= 3);
+  if constexpr (DEEP) {
+    // side inputs requested TWO chunks ahead (three register sets, chunk loop fully unrolled): one chunk of lead does not
+    // cover the load latency once the rest of the chunk is a straight line of ~230 instructions
+    float4 sd[3][8];
+    load_side(n0 + CH0 * 32, sd[0]);
+    load_side(n0 + CH0 * 32 + 32, sd[1]);
+#pragma unroll
+    for (int ch = CH0; ch < CH1; ++ch) chunk(ch, sd[(ch - CH0) % 3], sd[(ch - CH0 + 2) % 3], 2);
+  } else {
+    float4 sa[8], sb[8];
+    load_side(n0 + CH0 * 32, sa);
 #pragma unroll 1
-  for (int ch = CH0; ch < CH1; ch += 2) {
-    chunk(ch, sa, sb);
-    chunk(ch + 1, sb, sa);
+    for (int ch = CH0; ch < CH1; ch += 2) {
+      chunk(ch, sa, sb, 1);
+      chunk(ch + 1, sb, sa, 1);
+    }
   }
   if (p.dbg && lane == 0 && q == 0) atomicAdd(p.dbg + 3, (unsigned long long)t_ld);   // quadrant 0: tcgen05.ld issue -> data
 }
