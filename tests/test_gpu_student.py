@@ -192,3 +192,21 @@ def test_student_getters_and_epoch_smoke(tmp_path):
     for f in ('data_processor', 'downscaler', 'quantizer', 'decoder', 'teacher'):
         assert os.path.exists(tmp_path / 'overfitted' / f)
     tr.load(early_stopped=False, device='cuda')
+
+
+def test_main_encoder_student_config(tmp_path):
+    """`main_encoder.py -t -c configs/encoder_student.py` end to end as a subprocess at the shipped widths (d = 512, 8 heads, 384
+    tokens per window, codebook 32) with one layer per stack: one epoch of two batches + validation, checkpoints written."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VQCPC_BATCH='4', VQCPC_NUM_BATCHES='2', VQCPC_EPOCHS='1', VQCPC_STUDENT_LAYERS='1')
+    cfg_path = os.path.join(root, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'encoder_student.py')
+    r = subprocess.run([sys.executable, os.path.join(root, 'main_encoder.py'), '-t', '-c', cfg_path], cwd=str(tmp_path), env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + '\n' + r.stderr[-3000:]
+    assert '======= Epoch 0 =======' in r.stdout and 'Loss_teacher' in r.stdout
+    models = os.listdir(tmp_path / 'models')
+    assert len(models) == 1 and models[0].startswith('encoder_student_')
+    for f in ('data_processor', 'downscaler', 'quantizer', 'decoder', 'teacher'):
+        assert (tmp_path / 'models' / models[0] / 'overfitted' / f).exists()

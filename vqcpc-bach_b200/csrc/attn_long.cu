@@ -19,6 +19,8 @@ namespace {
 constexpr int HD = 64;
 constexpr int R = 8;            // query rows (or key columns) per CTA
 constexpr int THREADS = 256;
+constexpr int KT = 32;           // keys per shared-memory tile
+constexpr int PADW = HD + 4;     // padded row (floats): 16-byte reads of 8 consecutive rows hit all 32 banks once
 
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
@@ -60,20 +62,48 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
     qs[t] = (i < rows) ? base[(int64_t)(i0 + i) * ld + h * HD + d] : 0.f;
   }
   __syncthreads();
-  // scores: thread -> (row i, key j), consecutive threads take consecutive keys
-  for (int t = threadIdx.x; t < rows * L; t += THREADS) {
-    const int i = t / L, j = t % L;
-    const float4* kj = reinterpret_cast<const float4*>(base + (int64_t)j * ld + (H + h) * HD);
-    const float4* rr = reinterpret_cast<const float4*>(rel_row(e1h, e2h, L, i0 + i, j));
-    const float4* qi = reinterpret_cast<const float4*>(qs + i * HD);
-    float a0 = 0.f, a1 = 0.f;          // q.k and q.r accumulated separately, like the reference (bmm + einsum)
-#pragma unroll 4
-    for (int c = 0; c < HD / 4; ++c) {
-      const float4 q4 = qi[c], k4 = __ldg(kj + c), r4 = __ldg(rr + c);
-      a0 += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-      a1 += q4.x * r4.x + q4.y * r4.y + q4.z * r4.z + q4.w * r4.w;
+  // scores, 32 keys at a time: the key tile and the two slabs of relative rows it pairs with (39 consecutive rows of e1 for
+  // j <= i, of e2 for j > i: row = base + (jj - ii), jj = key in tile, ii = query in CTA) are staged in shared memory with
+  // coalesced loads; thread -> (query ii, key jj) then reads padded rows without bank conflicts
+  {
+    float* ks = sc + (size_t)R * L;                 // [KT][PADW]
+    float* s1 = ks + KT * PADW;                     // [KT + R - 1][PADW]  e1 slab
+    float* s2 = s1 + (KT + R - 1) * PADW;           // [KT + R - 1][PADW]  e2 slab
+    const int ii = threadIdx.x >> 5, jj = threadIdx.x & 31;
+    for (int j0 = 0; j0 < L; j0 += KT) {
+      const bool need1 = j0 <= i0 + R - 1, need2 = j0 + KT - 1 > i0;
+      const int b1 = (L - 1 - i0 + j0) - (R - 1), b2 = (j0 - i0) - (R - 1);      // table row of slab row 0
+      __syncthreads();
+      for (int t = threadIdx.x; t < KT * (HD / 4); t += THREADS) {
+        const int r = t / (HD / 4), c = t % (HD / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + r < L) v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(j0 + r) * ld + (H + h) * HD) + c);
+        *reinterpret_cast<float4*>(ks + r * PADW + c * 4) = v;
+      }
+      for (int t = threadIdx.x; t < (KT + R - 1) * (HD / 4); t += THREADS) {
+        const int r = t / (HD / 4), c = t % (HD / 4);
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
+        if (need1 && b1 + r >= 0 && b1 + r < L) v1 = __ldg(reinterpret_cast<const float4*>(e1h + (size_t)(b1 + r) * HD) + c);
+        if (need2 && b2 + r >= 1 && b2 + r < L) v2 = __ldg(reinterpret_cast<const float4*>(e2h + (size_t)(b2 + r) * HD) + c);
+        *reinterpret_cast<float4*>(s1 + r * PADW + c * 4) = v1;
+        *reinterpret_cast<float4*>(s2 + r * PADW + c * 4) = v2;
+      }
+      __syncthreads();
+      const int j = j0 + jj;
+      if (ii < rows && j < L) {
+        const float4* kj = reinterpret_cast<const float4*>(ks + jj * PADW);
+        const float4* rr = reinterpret_cast<const float4*>(((j <= i0 + ii) ? s1 : s2) + (jj - ii + R - 1) * PADW);
+        const float4* qi = reinterpret_cast<const float4*>(qs + ii * HD);
+        float a0 = 0.f, a1 = 0.f;          // q.k and q.r accumulated separately, like the reference (bmm + einsum)
+#pragma unroll
+        for (int c = 0; c < HD / 4; ++c) {
+          const float4 q4 = qi[c], k4 = kj[c], r4 = rr[c];
+          a0 += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+          a1 += q4.x * r4.x + q4.y * r4.y + q4.z * r4.z + q4.w * r4.w;
+        }
+        sc[ii * L + j] = a0 + a1;
+      }
     }
-    sc[i * L + j] = a0 + a1;
   }
   __syncthreads();
   // softmax: one warp per row
@@ -139,17 +169,31 @@ attn_long_bwd_q_kernel(const float* __restrict__ qkv, const float* __restrict__ 
     dos[t] = (i < rows) ? d_out[(size_t)(p * L + i0 + i) * (H * HD) + h * HD + d] : 0.f;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < rows * L; t += THREADS) {
-    const int i = t / L, j = t % L;
-    const float4* vj = reinterpret_cast<const float4*>(base + (int64_t)j * ld + (2 * H + h) * HD);
-    const float4* di = reinterpret_cast<const float4*>(dos + i * HD);
-    float a = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < HD / 4; ++c) {
-      const float4 d4 = di[c], v4 = __ldg(vj + c);
-      a += d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
+  {  // dP = dO v^T, 32 keys at a time through a padded shared-memory tile of v (coalesced loads, conflict-free reads)
+    float* vs = sc + (size_t)R * L;                 // [KT][PADW]
+    const int ii = threadIdx.x >> 5, jj = threadIdx.x & 31;
+    for (int j0 = 0; j0 < L; j0 += KT) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < KT * (HD / 4); t += THREADS) {
+        const int r = t / (HD / 4), c = t % (HD / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + r < L) v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(j0 + r) * ld + (2 * H + h) * HD) + c);
+        *reinterpret_cast<float4*>(vs + r * PADW + c * 4) = v;
+      }
+      __syncthreads();
+      const int j = j0 + jj;
+      if (ii < rows && j < L) {
+        const float4* vj = reinterpret_cast<const float4*>(vs + jj * PADW);
+        const float4* di = reinterpret_cast<const float4*>(dos + ii * HD);
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD / 4; ++c) {
+          const float4 d4 = di[c], v4 = vj[c];
+          a += d4.x * v4.x + d4.y * v4.y + d4.z * v4.z + d4.w * v4.w;
+        }
+        sc[ii * L + j] = a;
+      }
     }
-    sc[i * L + j] = a;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -228,31 +272,50 @@ attn_long_bwd_kv_kernel(const float* __restrict__ qkv, const float* __restrict__
 }
 
 // Backward, relative tables: row r of e1 pairs with the diagonal i - j = L-1-r, row r >= 1 of e2 with j - i = r (row 0 of e2
-// is never read by the forward).  grid (L, H, 2); 256 threads = 4 groups of 64 features splitting the (sequence, position)
-// range; the result is ACCUMULATED into d_e (the parameter's gradient buffer).
+// is never read by the forward).  A CTA owns ER = 8 consecutive table rows: for a query i they pair with 8 CONSECUTIVE keys, so
+// one 32-byte piece of the dS row and one q~ row feed 8 accumulators.  grid (ceil(L / 8), H, 2); 256 threads = 4 groups of 64
+// features splitting the queries; the result is ACCUMULATED into d_e (the parameter's gradient buffer).
+constexpr int ER = 8;
 __global__ void __launch_bounds__(THREADS)
 attn_long_bwd_e_kernel(const float* __restrict__ qkv, const float* __restrict__ ds, float* __restrict__ d_e1,
                        float* __restrict__ d_e2, int64_t P, int L, int H) {
-  __shared__ float red[4][HD];
-  const int r = blockIdx.x, h = blockIdx.y, which = blockIdx.z;
+  __shared__ float red[4][ER][HD];
+  const int r0 = blockIdx.x * ER, h = blockIdx.y, which = blockIdx.z;
   const int ld = 3 * H * HD;
-  if (which == 1 && r == 0) return;
-  const int delta = which == 0 ? (L - 1 - r) : r;            // |i - j|
-  const int n = L - delta;                                    // pairs on the diagonal
   const int g = threadIdx.x >> 6, d = threadIdx.x & 63;
-  float acc = 0.f;
-  for (int64_t t = g; t < P * n; t += 4) {
-    const int64_t p = t / n;
-    const int u = (int)(t % n);
-    const int i = which == 0 ? u + delta : u, j = which == 0 ? u : u + delta;
-    const float w = __ldg(ds + ((p * H + h) * (int64_t)L + i) * L + j);
-    acc += w * __ldg(qkv + (p * L + i) * (int64_t)ld + h * HD + d);
+  float acc[ER];
+#pragma unroll
+  for (int t = 0; t < ER; ++t) acc[t] = 0.f;
+  // key paired with (query i, table row r0 + t): e1: j = i - (L-1) + r0 + t;  e2: j = i + r0 + t
+  const int joff = which == 0 ? r0 - (L - 1) : r0;
+  for (int64_t p = 0; p < P; ++p) {
+    const float* dsp = ds + (p * H + h) * (int64_t)L * L;
+    const float* qp = qkv + p * L * (int64_t)ld + h * HD + d;
+    // queries for which at least one of the 8 keys exists
+    const int i_lo = max(0, -joff - (ER - 1)), i_hi = min(L - 1, L - 1 - joff);
+    for (int i = i_lo + g; i <= i_hi; i += 4) {
+      const float q = __ldg(qp + (int64_t)i * ld);
+      const float* row = dsp + (int64_t)i * L;
+      const int jb = i + joff;
+#pragma unroll
+      for (int t = 0; t < ER; ++t) {
+        const int j = jb + t;
+        if (j >= 0 && j < L) acc[t] += __ldg(row + j) * q;
+      }
+    }
   }
-  red[g][d] = acc;
+#pragma unroll
+  for (int t = 0; t < ER; ++t) red[g][t][d] = acc[t];
   __syncthreads();
   if (g == 0) {
-    float* dst = (which == 0 ? d_e1 : d_e2) + ((size_t)h * L + r) * HD + d;
-    *dst += red[0][d] + red[1][d] + red[2][d] + red[3][d];
+#pragma unroll
+    for (int t = 0; t < ER; ++t) {
+      const int r = r0 + t;
+      if (r < L && !(which == 1 && r == 0)) {
+        float* dst = (which == 0 ? d_e1 : d_e2) + ((size_t)h * L + r) * HD + d;
+        *dst += red[0][t][d] + red[1][t][d] + red[2][t][d] + red[3][t][d];
+      }
+    }
   }
 }
 
@@ -309,7 +372,13 @@ VQ_API int vqcpc_attn_long_fwd(const float* qkv, const float* e1, const float* e
   VQ_CHECK_ARG((out || out_hi) && ((out_hi == nullptr) == (out_lo == nullptr)), "attn_long_fwd: need out and/or (out_hi, out_lo)");
   if (P == 0) return VQ_OK;
   VQ_CHECK_ARG(P <= 65535, "attn_long_fwd: at most 65535 sequences per call (got %lld)", (long long)P);
-  const size_t smem = (size_t)(R * HD + R * L) * sizeof(float);
+  const size_t smem = (size_t)(R * HD + R * L + (KT + 2 * (KT + R - 1)) * PADW) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    VQ_CUDA_CALL(cudaFuncSetAttribute(attn_long_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((R * HD + R * 1024 + (KT + 2 * (KT + R - 1)) * PADW) * sizeof(float))));
+    attr_done = true;
+  }
   dim3 grid((unsigned)vq_cdiv(L, R), (unsigned)H, (unsigned)P);
   attn_long_fwd_kernel<<<grid, THREADS, smem, vq_stream(stream)>>>(qkv, e1, e2, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
                                                                     reinterpret_cast<__nv_bfloat16*>(out_lo), probs, L, H);
@@ -331,7 +400,7 @@ VQ_API int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(d_qkv_hi);
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(d_qkv_lo);
   dim3 grid((unsigned)vq_cdiv(L, R), (unsigned)H, (unsigned)P);
-  attn_long_bwd_q_kernel<<<grid, THREADS, (size_t)(R * HD + R * L) * sizeof(float), st>>>(qkv, e1, e2, probs, d_out, ds_scratch,
+  attn_long_bwd_q_kernel<<<grid, THREADS, (size_t)(R * HD + R * L + KT * PADW) * sizeof(float), st>>>(qkv, e1, e2, probs, d_out, ds_scratch,
                                                                                           d_qkv, oh, ol, L, H, q_scale);
   VQ_CUDA_LAUNCH_CHECK("attn_long_bwd_q_kernel");
   const size_t smem_kv = (size_t)2 * L * R * sizeof(float);
@@ -342,7 +411,7 @@ VQ_API int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e
   }
   attn_long_bwd_kv_kernel<<<grid, THREADS, smem_kv, st>>>(qkv, probs, ds_scratch, d_out, d_qkv, oh, ol, L, H);
   VQ_CUDA_LAUNCH_CHECK("attn_long_bwd_kv_kernel");
-  attn_long_bwd_e_kernel<<<dim3((unsigned)L, (unsigned)H, 2), THREADS, 0, st>>>(qkv, ds_scratch, d_e1, d_e2, P, L, H);
+  attn_long_bwd_e_kernel<<<dim3((unsigned)vq_cdiv(L, ER), (unsigned)H, 2), THREADS, 0, st>>>(qkv, ds_scratch, d_e1, d_e2, P, L, H);
   VQ_CUDA_LAUNCH_CHECK("attn_long_bwd_e_kernel");
   return VQ_OK;
 }

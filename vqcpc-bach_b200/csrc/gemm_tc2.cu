@@ -334,10 +334,13 @@ int vqtc::tc_launch_pair(int a_kmajor, int b_kmajor, int passes, const CUtensorM
         if (scfg == (EPI_BIAS | EPI_RESIDUAL | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_RESIDUAL | SCFG_C>(maps, p, st);
         if (scfg == (EPI_BIAS | EPI_RELU | SCFG_SPLIT)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_RELU | SCFG_SPLIT>(maps, p, st);
         if (scfg == (EPI_BIAS | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | SCFG_C>(maps, p, st);
+        if (scfg == (EPI_BIAS | EPI_RELU | SCFG_C)) return launch_pair<true, true, 3, 3, 4, EPI_BIAS | EPI_RELU | SCFG_C>(maps, p, st);      // dropout: FFN1
       } else {
         if (scfg == (EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT)) return launch_pair<true, false, 3, 3, 4, EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT>(maps, p, st);
         if (scfg == SCFG_C) return launch_pair<true, false, 3, 3, 4, SCFG_C>(maps, p, st);
         if (scfg == (EPI_RESIDUAL | SCFG_C)) return launch_pair<true, false, 3, 3, 4, EPI_RESIDUAL | SCFG_C>(maps, p, st);
+        if (scfg == (EPI_SCALE_COLS | EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT))                                                         // dropout: FFN2 dgrad
+          return launch_pair<true, false, 3, 3, 4, EPI_SCALE_COLS | EPI_RELU_MASK | EPI_MASK_BF16 | SCFG_SPLIT>(maps, p, st);
       }
     }
   }
