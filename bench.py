@@ -496,12 +496,12 @@ def run_ours(args):
     if tc:
         ach = tc_flops / (tc_ms / 1000.0) / 1e12
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r02_gemm_traffic.json')
         if os.path.exists(tpath):                      # committed ncu capture: DRAM bytes per GEMM launch, same shape mix
             tj = json.load(open(tpath))
             traffic = dict(dram_bytes_per_launch=tj['dram_read_bytes_per_launch'] + tj['dram_write_bytes_per_launch'],
-                           source='profiles/r01_gemm_traffic.json (ncu, %d launches)' % tj['launches'])
-        roof = dict(bound='tensor', kernel='gemm_tc_kernel (tcgen05 bf16x3)' if passes == 3 else 'gemm_tc_kernel (tcgen05 bf16)',
+                           source='profiles/r02_gemm_traffic.json (ncu, %d launches)' % tj['launches'])
+        roof = dict(bound='tensor', kernel='gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16x3)' if passes == 3 else 'gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16)',
                     achieved=ach, peak=pk['tflops'], unit='TFLOP/s', frac=ach / pk['tflops'], traffic=traffic,
                     peak_source=pk['src'], launches=len(tc), avg_launch_ms=tc_ms / len(tc),
                     share_of_step=tc_ms / ms, tensor_pipe_tflops=ach * passes,
