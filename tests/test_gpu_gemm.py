@@ -164,3 +164,64 @@ def test_gemm_presplit_operands_split_outputs_and_bf16_mask(mode):
     w_ref = g.double().t() @ c.double()
     assert ((acc.double() - w_ref).norm() / w_ref.norm()).item() < 3e-5
     ops.set_gemm_mode('bf16x3')
+
+
+@pytest.mark.parametrize('M', [300, 4096 + 77])
+def test_gemm_static_epilogue_configurations_equal_runtime_flags(M):
+    """The CTA-pair kernel is instantiated per compile-time epilogue configuration for the encoder's forward / data-gradient
+    GEMMs (csrc/gemm_tc2.cu); `vqcpc_gemm_set_experiment(256)` forces the run-time-flag kernel instead.  Both must give
+    bit-identical results on every configuration (incl. a partial last row tile), and match the fp64 reference."""
+    from VQCPCB import ops, _native
+    ops.set_gemm_mode('bf16x3')
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(3)
+    d, F = 512, 1024
+    x = torch.randn(M, d, generator=gen, device='cuda')
+    h = torch.randn(M, F, generator=gen, device='cuda')
+    w_qkv = torch.randn(3 * d, d, generator=gen, device='cuda') * 0.05
+    w1 = torch.randn(F, d, generator=gen, device='cuda') * 0.05           # (out F, in d)
+    w2 = torch.randn(d, F, generator=gen, device='cuda') * 0.05           # (out d, in F)
+    b3, bF, bd = (torch.randn(n, generator=gen, device='cuda') for n in (3 * d, F, d))
+    res = torch.randn(M, d, generator=gen, device='cuda')
+    resF = torch.randn(M, F, generator=gen, device='cuda')
+    mask = torch.randn(M, F, generator=gen, device='cuda').to(torch.bfloat16)
+    xs, hs = ops.split_bf16(x), ops.split_bf16(h)
+
+    def dd(t):
+        return t.double()
+    cases = {
+        'qkv bias+scale': (lambda: ops.gemm(None, w_qkv, M, 3 * d, d, bias=b3, scale_cols=(0.125, d), b_is_weight=True, a_split=xs),
+                           lambda: torch.cat([(dd(x) @ dd(w_qkv).t() + dd(b3))[:, :d] * 0.125, (dd(x) @ dd(w_qkv).t() + dd(b3))[:, d:]], 1)),
+        'out bias+residual': (lambda: ops.gemm(None, w2, M, d, F, bias=bd, residual=res, b_is_weight=True, a_split=hs),
+                              lambda: dd(h) @ dd(w2).t() + dd(bd) + dd(res)),
+        'ffn1 bias+relu->split': (lambda: ops.gemm(None, w1, M, F, d, bias=bF, relu=True, b_is_weight=True, a_split=xs, want_c=False, out_split=True),
+                                  lambda: torch.relu(dd(x) @ dd(w1).t() + dd(bF))),
+        'bias only': (lambda: ops.gemm(None, w1, M, F, d, bias=bF, b_is_weight=True, a_split=xs),
+                      lambda: dd(x) @ dd(w1).t() + dd(bF)),
+        'bias+relu': (lambda: ops.gemm(None, w1, M, F, d, bias=bF, relu=True, b_is_weight=True, a_split=xs),
+                      lambda: torch.relu(dd(x) @ dd(w1).t() + dd(bF))),
+        'dgrad bf16 mask->split': (lambda: ops.gemm(None, w2, M, F, d, True, False, relu_mask=mask, b_is_weight=True, a_split=xs, want_c=False, out_split=True),
+                                   lambda: (dd(x) @ dd(w2)) * (mask.double() > 0)),
+        'dgrad plain': (lambda: ops.gemm(None, w2, M, F, d, True, False, b_is_weight=True, a_split=xs),
+                        lambda: dd(x) @ dd(w2)),
+        'dgrad residual': (lambda: ops.gemm(None, w2, M, F, d, True, False, residual=resF, b_is_weight=True, a_split=xs),
+                           lambda: dd(x) @ dd(w2) + dd(resF)),
+        'dgrad scale+bf16 mask->split': (lambda: ops.gemm(None, w2, M, F, d, True, False, relu_mask=mask, scale_cols=(1.25, F), b_is_weight=True,
+                                                          a_split=xs, want_c=False, out_split=True),
+                                         lambda: (dd(x) @ dd(w2)) * 1.25 * (mask.double() > 0)),
+    }
+    try:
+        for name, (run, ref) in cases.items():
+            outs = []
+            for force_generic in (0, 1):
+                _native.call('vqcpc_gemm_set_experiment', 256 * force_generic)
+                r = run()
+                torch.cuda.synchronize()
+                outs.append(r[1] if isinstance(r, tuple) else (r,))
+            for a, b in zip(*outs):
+                assert torch.equal(a, b), name
+            val = outs[0][0].double() + (outs[0][1].double() if len(outs[0]) == 2 else 0)
+            rr = ref()
+            assert ((val - rr).norm() / rr.norm()).item() < 3e-5, name
+    finally:
+        _native.call('vqcpc_gemm_set_experiment', 0)

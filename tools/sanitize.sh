@@ -11,7 +11,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 SEL=${SANITIZE_SELECT:-"test_layernorm_fwd_bwd or test_attention_fwd_bwd_vs_oracle or test_attention_kept_rows_and_split_io or test_quantizer_bit_exact_vs_reference_golden or test_infonce_fwd_bwd_vs_oracle or test_clip_adam_matches_oracle or test_embed_fwd_bwd or test_posemb_fill_and_bwd or test_subsample_colsum_selu_reduce or (test_native_gru_matches_torch_gru and 5-16) or (test_vq_tc_scores_and_indices_small and 3-16-1000) or (test_vq_fused_bwd_matches_autograd and 3-5000) or test_gemm_epilogues or test_gemm_presplit_operands_split_outputs_and_bf16_mask or (idxpath and small)"}
 FILES=""
-for f in tests/test_gpu_kernels.py tests/test_gpu_vq_tc.py tests/test_gpu_gemm.py tests/test_gpu_idxpath.py; do [[ -f $f ]] && FILES="$FILES $f"; done
+for f in tests/test_gpu_kernels.py tests/test_gpu_vq_tc.py tests/test_gpu_gemm.py tests/test_gpu_idxpath.py tests/test_gpu_student.py; do [[ -f $f ]] && FILES="$FILES $f"; done
 TOOLS=${SANITIZE_TOOLS:-"memcheck racecheck synccheck"}
 PER_TOOL_TIMEOUT=${SANITIZE_TIMEOUT:-420}
 : > gpurun_out/sanitize_summary.txt
