@@ -144,6 +144,17 @@ int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e2, cons
                         float* ds_scratch, float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P,
                         int L, int H, int head_dim, float q_scale, void* stream);
 
+/* ---- general relative attention, forward only (decoder inference: decoders/decoder.py:431-543, :552-722;
+ *      transformer_custom.py:355-384 decoder layer; multihead_attention_custom.py:168-353 incl. the encoder-decoder branch;
+ *      subsampled_relative_attention.py:30-122 with seq_len_tgt != seq_len_src) -------------------------------------------
+ * q (P*Lq, ldq) head h at columns [64h, 64h+64) of the pointer, pre-scaled; k, v (P*Lk, ldkv) likewise; e1 / e2 (H*Lk, 64);
+ * map1 / map2 (Lq, Lk) int32: >= 0 -> bias term q~[m / Lk] . e[h, m % Lk], -1 -> 0, -2 -> -100 (the reference's pad / view
+ * skewing replayed on flat indices, VQCPCB/transformer/relative_maps.py); mask (Lq, Lk) additive (-inf = hidden) or NULL;
+ * out (P*Lq, H*64); probs (P, H, Lq, Lk) or NULL. */
+int vqcpc_attn_map_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, const float* e1, const float* e2,
+                       const int* map1, const int* map2, const float* mask, float* out, float* probs, int64_t P, int Lq, int Lk,
+                       int H, int head_dim, void* stream);
+
 /* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159
  *      distilled_categorical_crossentropy) --------------------------------------------------------------------------
  * logits (rows, C; ld).  Exactly one of target_idx (int64 class per row) / target_logits (rows, C; ldt: the teacher's

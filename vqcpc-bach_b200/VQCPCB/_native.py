@@ -44,6 +44,7 @@ SIGNATURES = {
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     'vqcpc_attn_long_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     'vqcpc_attn_long_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
+    'vqcpc_attn_map_fwd': [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_softmax_ce': [_P, _I, _P, _P, _I, _P, _P, _I, _F, _L, _I, _P],
     'vqcpc_attn_set_fwd_algo': [_I],
     'vqcpc_attn_set_bwd_algo': [_I],
