@@ -155,6 +155,34 @@ int vqcpc_attn_map_fwd(const float* q, int ldq, const float* k, const float* v, 
                        const int* map1, const int* map2, const float* mask, float* out, float* probs, int64_t P, int Lq, int Lk,
                        int H, int head_dim, void* stream);
 
+/* ---- incremental (key / value cached) generation step (decoders/decoder.py:607-644: the reference recomputes the whole
+ *      teacher-forced forward per token and samples on the host; csrc/decode.cu explains why the cache is exact) -------------
+ * Every entry point reads the current target position from DEVICE memory (`pos`, one int32) so that the launch sequence of
+ * one event is position independent and can be replayed as a CUDA graph. */
+/* feat (B, E + 2 pe) = [ embedding of token pos-1 | channel embedding | event embedding ] of position pos-1 (decoder.py:442-457
+ * shifted right by one, :476-482); zeros at pos == 0.  tables: the per-channel embedding tables concatenated by rows,
+ * table_off (C) int32 device = first row of each channel. */
+int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* tables, const int* table_off, const float* chan,
+                          const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe, void* stream);
+/* nn.Linear on M <= 16 rows in exact fp32: out = [row0 if *pos == 0 else] relu?( (x W^T + bias) * scale on the first
+ * scale_cols columns ) + residual.  W (N, K) row-major; bias / residual / row0 may be NULL. */
+int vqcpc_linear_small(const float* x, int ldx, const float* W, const float* bias, const float* residual, int ldr, float* out,
+                       int ldo, int M, int N, int K, int relu, float scale, int scale_cols, const float* row0, const int* pos,
+                       void* stream);
+/* one query row per (sequence, head) at position *pos (multihead_attention_custom.py:274-345 restricted to that row): q (P, ldq)
+ * pre-scaled; k_new / v_new (P, ldn) appended to the cache at row *pos when non-NULL; kcache / vcache (P * Lmax rows, ldc);
+ * e1 / e2 (H * Lk, 64) with map1 / map2 (Lq, Lk) int32 as in vqcpc_attn_map_fwd (row *pos is used); mask (Lq, Lk) additive or
+ * NULL; causal != 0: keys 0 .. *pos, else all Lk keys; out (P, ldo). */
+int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const float* v_new, int ldn, float* kcache, float* vcache,
+                      int ldc, int Lmax, const float* e1, const float* e2, const int* map1, const int* map2, const float* mask,
+                      int Lk, const int* pos, int causal, float* out, int ldo, int64_t P, int H, int head_dim, void* stream);
+/* tokens[b, *pos] = one draw per row of logits (B, V; ld): logits / temperature, top-k and top-p filtering (utils.py:100-128),
+ * softmax, then numpy.random.choice's inverse-CDF draw (decoder.py:636-644) with the caller's uniform u[*pos * u_stride + b]
+ * (double, [0, 1)); greedy != 0: argmax. */
+int vqcpc_sample_step(const float* logits, int ld, int V, float temperature, int top_k, float top_p, const double* u, int u_stride,
+                      int64_t* tokens, int T, const int* pos, int greedy, int B, void* stream);
+int vqcpc_decode_advance(int* pos, int delta, void* stream);
+
 /* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159
  *      distilled_categorical_crossentropy) --------------------------------------------------------------------------
  * logits (rows, C; ld).  Exactly one of target_idx (int64 class per row) / target_logits (rows, C; ldt: the teacher's

@@ -7,6 +7,7 @@ live reference by ``oracle/make_golden_decoder.py`` -> ``tests/golden/decoder.pt
 formulation the product uses (VQCPCB/transformer/relative_maps.py)."""
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -131,3 +132,29 @@ def decoder_forward(source, target, prm, cfg):
     logits = [F.linear(y[:, :, c], prm[f'pre_softmaxes.{c}.weight'], prm[f'pre_softmaxes.{c}.bias']) for c in range(C)]
     loss = sum(F.cross_entropy(logits[c].reshape(B * Ev, -1), target[:, :, c].reshape(-1), reduction='none') for c in range(C)).mean()
     return loss, logits
+
+
+def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float('inf')):
+    """VQCPCB/utils.py:100-128 on one row of logits (returns a filtered copy)."""
+    logits = logits.clone()
+    top_k = min(top_k, logits.size(-1))
+    if top_k > 0:
+        logits[logits < torch.topk(logits, top_k)[0][..., -1, None]] = filter_value
+    if top_p > 0.0:
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+        cumulative = torch.cumsum(torch.softmax(sorted_logits, dim=-1), dim=-1)
+        remove = cumulative > top_p
+        remove[..., 1:] = remove[..., :-1].clone()
+        remove[..., 0] = False
+        logits[sorted_indices[remove]] = filter_value
+    return logits
+
+
+def sample_rows(logits, temperature, top_k, top_p, rng):
+    """decoder.py:619-644 for one token position: logits (B, V) -> B tokens, one ``rng.choice`` (numpy RandomState) per row in
+    batch order - each consumes exactly one ``random_sample()`` of the stream."""
+    out = []
+    for row in logits.float() / temperature:
+        p = torch.softmax(top_k_top_p_filtering(row, top_k=top_k, top_p=top_p), dim=-1).numpy()
+        out.append(int(rng.choice(np.arange(p.shape[0]), p=p)))
+    return out

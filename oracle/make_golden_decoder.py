@@ -84,6 +84,24 @@ def main():
         print(name, 'loss ref', fp['loss'].item(), 'oracle', loss_o.item(), 'max logit err', err)
         out[name] = dict(cfg=c, B=spec['B'], shapes=shapes, source=source, target=target, loss=fp['loss'].item(),
                          logits=[w.clone() for w in fp['weights_per_category']])
+    # the sampling step of generate (decoder.py:619-644): the reference's own top_k_top_p_filtering + np.random.choice
+    import numpy as np
+    from VQCPCB.utils import top_k_top_p_filtering
+    g = torch.Generator().manual_seed(5)
+    samp = []
+    for V, temperature, top_k, top_p in [(23, 1.0, 0, 1.0), (64, 0.9, 0, 0.8), (130, 1.2, 10, 0.0), (57, 1.0, 5, 0.95), (9, 0.7, 0, 0.3)]:
+        logits = torch.randn(48, V, generator=g) * 2.5
+        logits[::7, 3] = logits[::7, 5]                              # some exact ties
+        np.random.seed(1000 + V)
+        toks = []
+        for row in logits / temperature:
+            fl = top_k_top_p_filtering(row.clone(), top_k=top_k, top_p=top_p)
+            p = torch.softmax(fl, dim=-1).numpy()
+            toks.append(int(np.random.choice(np.arange(V), p=p)))
+        samp.append(dict(V=V, temperature=temperature, top_k=top_k, top_p=top_p, logits=logits, seed=1000 + V,
+                         tokens=torch.tensor(toks)))
+        print('sampler', V, temperature, top_k, top_p, toks[:12])
+    out['sampler'] = samp
     path = os.path.join(ROOT, 'tests', 'golden', 'decoder.pt')
     torch.save(out, path)
     print('wrote', path, os.path.getsize(path))

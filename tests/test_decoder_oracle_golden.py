@@ -40,3 +40,30 @@ def test_relative_index_maps_equal_literal_skewing(T, S):
             rel = (q[bh] @ e.view(H, S, hd)[h].t()).reshape(-1)
             out[bh] += torch.where(mm >= 0, rel[mm.clamp(min=0).long()], torch.where(mm == -2, -100.0, 0.0).double())
     assert (out - ref).abs().max().item() < 1e-12
+
+
+def test_sampler_oracle_matches_reference_golden():
+    """oracle sample_rows (top-k / top-p restatement + RandomState.choice) against tokens drawn by the reference's own
+    top_k_top_p_filtering + np.random.choice on the same logits and seed."""
+    import numpy as np
+    for rec in torch.load(GOLD)['sampler']:
+        rng = np.random.RandomState(rec['seed'])
+        toks = D.sample_rows(rec['logits'], rec['temperature'], rec['top_k'], rec['top_p'], rng)
+        assert toks == rec['tokens'].tolist()
+        # numpy's choice consumes exactly one uniform per call: the stream the GPU sampler is fed with
+        u = np.random.RandomState(rec['seed']).random_sample(len(toks))
+        rng2 = np.random.RandomState(rec['seed'])
+        for k in range(3):
+            rng2.choice(np.arange(rec['V']), p=np.full(rec['V'], 1.0 / rec['V']))
+        assert rng2.random_sample() == np.random.RandomState(rec['seed']).random_sample(4)[3] and u.shape[0] == len(toks)
+
+
+@pytest.mark.parametrize('T,S', [(1024, 64), (1024, 1024), (96, 6), (64, 64)])
+def test_relative_bias_rows_only_read_their_own_query(T, S):
+    """The property the key / value cached generation rests on (asserted inside relative_index_maps as well)."""
+    from VQCPCB.transformer.relative_maps import relative_index_maps
+    m1, m2 = relative_index_maps(T, S)
+    rows = torch.arange(T).view(T, 1)
+    for m in (m1, m2):
+        v = m >= 0
+        assert bool((m[v] // S == rows.expand(T, S)[v]).all())

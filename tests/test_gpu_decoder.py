@@ -111,3 +111,108 @@ def test_decoder_greedy_generation_is_consistent_with_forward():
     xs = dec.generate_from_codes(rec['source'].cuda(), temperature=1.0, top_p=0.9, top_k=8, generator=g)
     for c, v in enumerate(rec['cfg']['vocab']):
         assert int(xs[:, :, c].max()) < v and int(xs[:, :, c].min()) >= 0
+
+
+def _pp(t):
+    import ctypes
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 512, 512), (3, 1536, 512), (8, 512, 1024), (16, 23, 48), (5, 130, 512)])
+def test_linear_small_vs_fp64(M, N, K):
+    """vqcpc_linear_small (bias, q-third scaling, ReLU, residual, start-row substitution) against fp64."""
+    from VQCPCB import _native, ops
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    row0 = torch.randn(N, generator=g).cuda()
+    out = torch.empty(M, N, device='cuda')
+    for relu, scale_cols, use_res, p0 in [(0, 0, False, 5), (1, 0, True, 5), (0, N // 3, True, 3), (0, 0, False, 0)]:
+        pos = torch.tensor([p0], dtype=torch.int32, device='cuda')
+        _native.call('vqcpc_linear_small', _pp(x), K, _pp(w), _pp(b), _pp(res) if use_res else None, N, _pp(out), N, M, N, K, relu,
+                     0.125, scale_cols, _pp(row0), _pp(pos), ops._stream())
+        ref = x.double() @ w.double().t() + b.double()
+        ref[:, :scale_cols] *= 0.125
+        if relu:
+            ref = ref.clamp(min=0)
+        if use_res:
+            ref = ref + res.double()
+        if p0 == 0:
+            ref = row0.double().expand(M, N)
+        assert rel_err(out, ref) < 2e-6
+
+
+def test_sample_step_vs_reference_golden():
+    """vqcpc_sample_step fed with numpy's uniform stream draws the tokens the reference's top_k_top_p_filtering +
+    np.random.choice drew (tests/golden/decoder.pt 'sampler', made by the live reference)."""
+    import numpy as np
+    from VQCPCB import _native, ops
+    for rec in torch.load(GOLD)['sampler']:
+        lg = rec['logits'].cuda().contiguous()
+        n, V = lg.shape
+        u = torch.from_numpy(np.random.RandomState(rec['seed']).random_sample(n)).cuda()
+        # rows are independent "sequences" of one step each: position 0, batch = n, u indexed [0 * n + b]
+        tokens = torch.full((n, 1), -1, dtype=torch.int64, device='cuda')
+        pos = torch.zeros(1, dtype=torch.int32, device='cuda')
+        _native.call('vqcpc_sample_step', _pp(lg), V, V, rec['temperature'], rec['top_k'], rec['top_p'], _pp(u), n, _pp(tokens), 1,
+                     _pp(pos), 0, n, ops._stream())
+        got = tokens.view(-1).cpu()
+        bad = (got != rec['tokens']).nonzero().view(-1).tolist()
+        assert not bad, (rec['V'], rec['top_k'], rec['top_p'], bad, got[bad], rec['tokens'][bad])
+        _native.call('vqcpc_sample_step', _pp(lg), V, V, 1.0, 0, 0.0, None, n, _pp(tokens), 1, _pp(pos), 1, n, ops._stream())
+        assert torch.equal(tokens.view(-1).cpu(), rec['logits'].argmax(dim=-1))
+
+
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full'])
+def test_cached_generation_equals_full_recompute(case):
+    """The incremental path (key / value cache, CUDA graph per event, device sampling) against the reference's schedule (full
+    forward per token) in exact-fp32 mode: greedy tokens identical; sampled tokens identical to the oracle sampler applied to the
+    full-recompute logits with the same numpy uniform stream; graph replay == eager launches."""
+    import numpy as np
+    from VQCPCB import ops
+    rec = torch.load(GOLD)[case]
+    prm = D.make_decoder_params(rec['shapes'], seed=0)
+    ops.set_gemm_mode('fp32')
+    try:
+        dec = _build(rec['cfg'])
+        dec.load_state_dict({k: v.cuda() for k, v in prm.items()}, strict=True)
+        ops.bump_weight_version()
+        src = rec['source'].cuda()
+        full = dec.generate_from_codes(src, greedy=True, kv_cache=False)
+        cached = dec.generate_from_codes(src, greedy=True, kv_cache=True)
+        eager = dec.generate_from_codes(src, greedy=True, kv_cache=True, use_graph=False)
+        assert torch.equal(full, cached) and torch.equal(cached, eager)
+        # sampling: replay the reference loop with the oracle sampler on the product's full-forward logits
+        B, Ev, C = full.shape
+        T = Ev * C
+        seed = 4242
+        u = np.random.RandomState(seed).random_sample((T, B))
+        got = dec.generate_from_codes(src, temperature=0.9, top_k=12, top_p=0.9, uniforms=torch.from_numpy(u))
+        rng = np.random.RandomState(seed)
+        x = torch.zeros(B, Ev, C, dtype=torch.int64, device='cuda')
+        for e in range(Ev):
+            for c in range(C):
+                lg = dec.forward(src, x)['weights_per_category'][c][:, e, :].cpu()
+                x[:, e, c] = torch.tensor(D.sample_rows(lg, 0.9, 12, 0.9, rng), device='cuda')
+        assert torch.equal(got, x)
+        # excluded symbols are never drawn
+        ex = dec.generate_from_codes(src, temperature=1.5, uniforms=torch.from_numpy(u), exclude={0: [0, 1, 2, 3]})
+        assert int(ex[:, :, 0].min()) >= 4
+    finally:
+        ops.set_gemm_mode('bf16x3')
+
+
+def test_cached_generation_teacher_forced_logits():
+    """One cached step at every position reproduces the teacher-forced logits of Decoder.forward (rows of the golden target)."""
+    from VQCPCB import ops
+    rec = torch.load(GOLD)['c_full']
+    prm = D.make_decoder_params(rec['shapes'], seed=0)
+    dec = _build(rec['cfg'])
+    dec.load_state_dict({k: v.cuda() for k, v in prm.items()}, strict=True)
+    ops.bump_weight_version()
+    x = dec.generate_from_codes(rec['source'].cuda(), greedy=True)
+    logits = dec.forward(rec['source'].cuda(), x)['weights_per_category']
+    for c, w in enumerate(logits):
+        assert torch.equal(w.argmax(dim=-1), x[:, :, c])

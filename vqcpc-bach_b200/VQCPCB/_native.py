@@ -45,6 +45,11 @@ SIGNATURES = {
     'vqcpc_attn_long_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     'vqcpc_attn_long_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
     'vqcpc_attn_map_fwd': [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    'vqcpc_decode_features': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'vqcpc_linear_small': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P],
+    'vqcpc_attn_decode': [_P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P],
+    'vqcpc_sample_step': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P],
+    'vqcpc_decode_advance': [_P, _I, _P],
     'vqcpc_softmax_ce': [_P, _I, _P, _P, _I, _P, _P, _I, _F, _L, _I, _P],
     'vqcpc_attn_set_fwd_algo': [_I],
     'vqcpc_attn_set_bwd_algo': [_I],

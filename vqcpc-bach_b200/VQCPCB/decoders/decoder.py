@@ -5,7 +5,7 @@ SURVEY.md §8f row 3, BASELINE config 5).
 Built: ``transformer_type='relative'`` with ``encoder_attention_type`` in {anticausal, causal, full} and ``cross_attention_type``
 in {anticausal, full} (every shipped ``decoder_relative_*`` configuration except the 'diagonal' aligned layer), forward = teacher
 forced logits + cross-entropy, and autoregressive generation that recomputes the forward for every token exactly like the
-reference (no KV cache: the reference's cross-attention bias makes entry (i, j) depend on other query rows - see
+reference does (kept as the parity check), and - the default - INCREMENTALLY over cached keys / values (csrc/decode.cu; see
 ``transformer/relative_maps.py``), with top-k / top-p filtering and sampling on the device.  Training of the decoder is out of
 scope (forward-only kernels); parameter names are the reference's state_dict keys so its checkpoints load.
 
@@ -198,6 +198,29 @@ class Decoder(nn.Module):
         return ops.layernorm_fwd(y, lyr.norm3.weight, lyr.norm3.bias)[0]
 
     @torch.no_grad()
+    def _encode_memory(self, source):
+        """Code embedding (:440) + the encoder stack over the code sequence (:498-505, :509).  -> (memory (B*S, d), S)."""
+        B = source.size(0)
+        dev = self.sos.device
+        d = self.d_model
+        if isinstance(self.source_embeddings, nn.Embedding):
+            src = torch.nn.functional.embedding(source.to(dev).long(), self.source_embeddings.weight).reshape(-1, d)   # :440
+        else:
+            src = ops.linear_fwd(ops._f32c(source.to(dev)).reshape(-1, source.shape[-1]), self.source_embeddings.weight,
+                                 self.source_embeddings.bias)
+        S = src.shape[0] // B
+        if self.encoder_attention_type == 'full':
+            source_mask = None
+        elif self.encoder_attention_type == 'causal':
+            source_mask = _causal_mask(S, dev)
+        else:
+            source_mask = _anticausal_mask(S, dev)
+        x = src.contiguous()
+        for lyr in self.transformer.encoder.layers:
+            x = self._enc_layer(lyr, x, B, S, source_mask)
+        return x, S
+
+    @torch.no_grad()
     def forward(self, source, target):
         """source: code indices (batch, S) (or (batch, S, codebook_dim) without quantization); target: tokens (batch, num_events,
         num_channels).  Returns the reference's dict: loss, weights_per_category (list of (batch, num_events, vocab_c)),
@@ -205,12 +228,7 @@ class Decoder(nn.Module):
         B = source.size(0)
         dev = self.sos.device
         d, C = self.d_model, self.num_channels
-        if isinstance(self.source_embeddings, nn.Embedding):
-            src = torch.nn.functional.embedding(source.to(dev).long(), self.source_embeddings.weight).reshape(-1, d)   # :440
-        else:
-            src = ops.linear_fwd(ops._f32c(source.to(dev)).reshape(-1, source.shape[-1]), self.source_embeddings.weight,
-                                 self.source_embeddings.bias)
-        S = src.shape[0] // B
+        memory, S = self._encode_memory(source)
         target = self.data_processor.preprocess(target)
         tgt = flatten(self.data_processor.embed(target))                                                 # (B, T, E)   :442-444
         T = tgt.size(1)
@@ -220,17 +238,7 @@ class Decoder(nn.Module):
         tgt = ops.linear_fwd(tgt.contiguous(), self.linear_target.weight, self.linear_target.bias).view(B, T, d)   # :469
         tgt = torch.cat([self.sos.expand(B, 1, d), tgt[:, :-1]], dim=1).reshape(B * T, d).contiguous()   # shift by one   :476-482
         memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None  # :487-496
-        if self.encoder_attention_type == 'full':
-            source_mask = None
-        elif self.encoder_attention_type == 'causal':
-            source_mask = _causal_mask(S, dev)
-        else:
-            source_mask = _anticausal_mask(S, dev)
         target_mask = _causal_mask(T, dev)                                                               # :507
-        x = src.contiguous()
-        for lyr in self.transformer.encoder.layers:
-            x = self._enc_layer(lyr, x, B, S, source_mask)
-        memory = x
         y = tgt
         for lyr in self.transformer.decoder.layers:
             y = self._dec_layer(lyr, y, memory, B, T, S, target_mask, memory_mask)
@@ -248,17 +256,32 @@ class Decoder(nn.Module):
         return torch.zeros(1, num_events, self.num_channels, dtype=torch.int64, device=self.sos.device)   # :724-727
 
     @torch.no_grad()
-    def generate_from_codes(self, encoding_indices, temperature=1.0, top_k=0, top_p=1.0, generator=None, greedy=False):
-        """The token loop of ``generate`` (decoder.py:607-644): for every (event, channel) a full forward, the logits of that
-        position divided by the temperature, top-k / top-p filtering, one sample per batch element (``torch.multinomial`` on the
-        device; the reference draws with numpy on the host).  ``greedy`` takes the argmax instead (tests).  Returns tokens
-        (batch, num_events, num_channels)."""
+    def generate_from_codes(self, encoding_indices, temperature=1.0, top_k=0, top_p=1.0, generator=None, greedy=False,
+                            kv_cache=True, uniforms=None, use_graph=True, exclude=None):
+        """The token loop of ``generate`` (decoder.py:607-644).  Returns tokens (batch, num_events, num_channels).
+
+        kv_cache=True (default): incremental decoding - one new row per layer and token over cached keys / values, replayed as a
+        CUDA graph per event, sampling on the device (csrc/decode.cu; exact because the decoder is causal and the relative bias of
+        row i only involves q_i).  ``uniforms`` (num_tokens, batch) float64 in [0, 1): the draws, consumed in the order the
+        reference calls ``np.random.choice`` (token by token, batch index inner); default: drawn from ``generator``.
+        ``exclude``: {channel: [token ids]} never sampled (the reference's ``exclude_meta_symbols``, :624-629).
+
+        kv_cache=False: the reference's schedule - a full teacher-forced forward for every token (kept as the parity check of
+        the cached path), filtering with ``top_k_top_p_filtering`` and ``torch.multinomial`` on the device."""
         self.eval()
+        if kv_cache:
+            B = encoding_indices.size(0)
+            outs = [self._generate_cached(encoding_indices[b0:b0 + 16], temperature, top_k, top_p, generator, greedy,
+                                          None if uniforms is None else uniforms[:, b0:b0 + 16], use_graph, exclude)
+                    for b0 in range(0, B, 16)]
+            return torch.cat(outs, dim=0)
         B = encoding_indices.size(0)
         x = self.init_generation(self.data_processor.num_events).repeat(B, 1, 1)
         for event_index in range(self.data_processor.num_events):
             for channel_index in range(self.num_channels):
                 logits = self.forward(encoding_indices, x)['weights_per_category'][channel_index][:, event_index, :] / temperature
+                if exclude and channel_index in exclude:
+                    logits[:, list(exclude[channel_index])] = -float('inf')
                 if greedy:
                     new = logits.argmax(dim=-1)
                 else:
@@ -266,6 +289,109 @@ class Decoder(nn.Module):
                     new = torch.multinomial(torch.softmax(filtered, dim=-1), 1, generator=generator).squeeze(1)
                 x[:, event_index, channel_index] = new
         return x
+
+    def _generate_cached(self, codes, temperature, top_k, top_p, generator, greedy, uniforms, use_graph, exclude):
+        """<= 16 sequences through the incremental path; see csrc/decode.cu for the launch sequence of one token step."""
+        dev = self.sos.device
+        B, d, H, C = codes.size(0), self.d_model, self.n_head, self.num_channels
+        hd = d // H
+        scale = float(hd) ** -0.5
+        T, up = self.num_tokens_target, self.total_upscaling
+        Ev = T // C
+        memory, S = self._encode_memory(codes)
+        layers = list(self.transformer.decoder.layers)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # keys / values of the memory for every decoder layer (multihead_attention_custom.py:173-196), computed once
+        cross_kv = [ops.linear_fwd(memory, l.multihead_attn.in_proj_weight[d:], l.multihead_attn.in_proj_bias[d:]).contiguous()
+                    for l in layers]
+        kc = [torch.zeros(B * T, d, **f32) for _ in layers]
+        vc = [torch.zeros(B * T, d, **f32) for _ in layers]
+        sm1, sm2 = device_maps(T, T, dev)
+        cm1, cm2 = device_maps(T, S, dev)
+        memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None
+        tables = torch.cat([e.weight.detach() for e in self.data_processor.embeddings], dim=0).contiguous()
+        rows = [e.weight.shape[0] for e in self.data_processor.embeddings]
+        table_off = torch.tensor([sum(rows[:c]) for c in range(C)], dtype=torch.int32, device=dev)
+        E = tables.shape[1]
+        pe = self.target_channel_embeddings.shape[-1]
+        F = E + 2 * pe
+        chan = self.target_channel_embeddings.detach().reshape(C, pe).contiguous()
+        evt = self.target_events_positioning_embeddings.detach().reshape(-1, pe).contiguous()
+        ff = layers[0].linear1.weight.shape[0]
+        Vmax = max(self.num_tokens_per_channel)
+        tokens = torch.zeros(B, T, dtype=torch.int64, device=dev)
+        pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        feat, x, x1, x2, y, att, qc = (torch.empty(B, n, **f32) for n in (F, d, d, d, d, d, d))
+        qkv, hmid, logits = torch.empty(B, 3 * d, **f32), torch.empty(B, ff, **f32), torch.empty(B, Vmax, **f32)
+        mean, rstd = torch.empty(B, **f32), torch.empty(B, **f32)
+        if uniforms is None:
+            uniforms = torch.rand(T, B, dtype=torch.float64, device=dev, generator=generator)
+        u = torch.as_tensor(uniforms, dtype=torch.float64).to(dev).contiguous()
+        assert u.shape == (T, B)
+        head_bias = []
+        for c, ps in enumerate(self.pre_softmaxes):
+            bvec = ps.bias.detach().clone()
+            if exclude and c in exclude:
+                bvec[list(exclude[c])] = -float('inf')
+            head_bias.append(bvec)
+        sos = self.sos.detach().reshape(d).contiguous()
+        keep = [memory, cross_kv, kc, vc, tables, table_off, chan, evt, u, head_bias, sos]    # noqa: F841  (alive during replay)
+        call = _native.call
+
+        def lin(xin, ldx, w, b, res, out, ldo, N, K, relu=0, sc=1.0, sc_cols=0, row0=None):
+            call('vqcpc_linear_small', _p(xin), ldx, _p(w), _p(b), _p(res), d, _p(out), ldo, B, N, K, relu, sc, sc_cols, _p(row0),
+                 _p(pos), ops._stream())
+
+        def ln(src, norm, dst):
+            call('vqcpc_layernorm_fwd', _p(src), _p(norm.weight), _p(norm.bias), _p(dst), None, None, _p(mean), _p(rstd), B, d,
+                 float(norm.eps), ops._stream())
+
+        def step(c):
+            st = ops._stream()
+            call('vqcpc_decode_features', _p(tokens), _p(pos), _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), B, T, C, up, E,
+                 pe, st)
+            lin(feat, F, self.linear_target.weight, self.linear_target.bias, None, x, d, d, F, row0=sos)
+            for li, l in enumerate(layers):
+                a = l.self_attn
+                lin(x, d, a.in_proj_weight, a.in_proj_bias, None, qkv, 3 * d, 3 * d, d, sc=scale, sc_cols=d)
+                call('vqcpc_attn_decode', _p(qkv), 3 * d, _p(qkv[:, d:]), _p(qkv[:, 2 * d:]), 3 * d, _p(kc[li]), _p(vc[li]), d, T,
+                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
+                lin(att, d, a.out_proj.weight, a.out_proj.bias, x, y, d, d, d)
+                ln(y, l.norm1, x1)
+                a = l.multihead_attn
+                lin(x1, d, a.in_proj_weight[:d], a.in_proj_bias[:d], None, qc, d, d, d, sc=scale, sc_cols=d)
+                call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(cross_kv[li]), _p(cross_kv[li][:, d:]), 2 * d, S,
+                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd,
+                     st)
+                lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
+                ln(y, l.norm2, x2)
+                lin(x2, d, l.linear1.weight, l.linear1.bias, None, hmid, ff, ff, d, relu=1)
+                lin(hmid, ff, l.linear2.weight, l.linear2.bias, x2, y, d, d, ff)
+                ln(y, l.norm3, x)
+            V = self.num_tokens_per_channel[c]
+            lin(x, d, self.pre_softmaxes[c].weight, head_bias[c], None, logits, Vmax, V, d)
+            call('vqcpc_sample_step', _p(logits), Vmax, V, float(temperature), int(top_k), float(top_p), _p(u), B, _p(tokens), T,
+                 _p(pos), int(bool(greedy)), B, st)
+            call('vqcpc_decode_advance', _p(pos), 1, st)
+
+        def event():
+            for c in range(C):
+                step(c)
+
+        event()                                              # event 0 eagerly (also the warm-up the capture needs)
+        if Ev > 1:
+            if use_graph:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    event()
+                for _ in range(1, Ev):
+                    graph.replay()
+            else:
+                for _ in range(1, Ev):
+                    event()
+        self.last_generation_launches = Ev * C * (5 + 11 * len(layers))
+        return tokens.view(B, Ev, C)
 
     @torch.no_grad()
     def generate(self, temperature, batch_size=1, top_k=0, top_p=1., seed_set=None, **kwargs):

@@ -37,6 +37,11 @@ def relative_index_maps(T, S):
         masks_up = torch.repeat_interleave(masks_up, ratio, dim=0)
     r1 = r1.masked_fill(masks_up, ZERO)                                        # :119
     r2 = r2.masked_fill(masks_down, ZERO)                                      # :120
+    # every surviving entry of row i is a product of query row i itself (the -100 padding only ever lands in the zeroed parts):
+    # the incremental decoder (csrc/decode.cu) relies on it - row i of a layer never reads another row's query
+    rows = torch.arange(T).view(T, 1)
+    for r in (r1, r2):
+        assert bool(((r < 0) | (r // S == rows)).all()), 'relative bias row reads a foreign query row'
     return r1.to(torch.int32).contiguous(), r2.to(torch.int32).contiguous()
 
 
