@@ -169,6 +169,11 @@ int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* ta
 int vqcpc_linear_small(const float* x, int ldx, const float* W, const float* bias, const float* residual, int ldr, float* out,
                        int ldo, int M, int N, int K, int relu, float scale, int scale_cols, const float* row0, const int* pos,
                        void* stream);
+/* the same with nn.LayerNorm(K) applied to the input rows while they are staged (post-LN blocks, transformer_custom.py:283-289:
+ * x holds the pre-norm sum); ln_out (M, K) != NULL additionally receives the normalised rows (residual of a later linear). */
+int vqcpc_ln_linear_small(const float* x, int ldx, const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out,
+                          const float* W, const float* bias, const float* residual, int ldr, float* out, int ldo, int M, int N, int K,
+                          int relu, float scale, int scale_cols, void* stream);
 /* one query row per (sequence, head) at position *pos (multihead_attention_custom.py:274-345 restricted to that row): q (P, ldq)
  * pre-scaled; k_new / v_new (P, ldn) appended to the cache at row *pos when non-NULL; kcache / vcache (P * Lmax rows, ldc);
  * e1 / e2 (H * Lk, 64) with map1 / map2 (Lq, Lk) int32 as in vqcpc_attn_map_fwd (row *pos is used); mask (Lq, Lk) additive or
@@ -176,11 +181,19 @@ int vqcpc_linear_small(const float* x, int ldx, const float* W, const float* bia
 int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const float* v_new, int ldn, float* kcache, float* vcache,
                       int ldc, int Lmax, const float* e1, const float* e2, const int* map1, const int* map2, const float* mask,
                       int Lk, const int* pos, int causal, float* out, int ldo, int64_t P, int H, int head_dim, void* stream);
+/* keys are split over a thread-block cluster of ns CTAs per (sequence, head): 0 = automatic (default), 1, 2, 4, 8. */
+int vqcpc_attn_decode_set_split(int ns);
 /* tokens[b, *pos] = one draw per row of logits (B, V; ld): logits / temperature, top-k and top-p filtering (utils.py:100-128),
  * softmax, then numpy.random.choice's inverse-CDF draw (decoder.py:636-644) with the caller's uniform u[*pos * u_stride + b]
  * (double, [0, 1)); greedy != 0: argmax. */
 int vqcpc_sample_step(const float* logits, int ld, int V, float temperature, int top_k, float top_p, const double* u, int u_stride,
                       int64_t* tokens, int T, const int* pos, int greedy, int B, void* stream);
+/* vqcpc_sample_step + vqcpc_decode_features of the NEXT position (from the token just drawn) + *pos += 1, in one launch;
+ * done: one zero-initialised int32 (arrival counter of the B CTAs, left at zero). */
+int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float temperature, int top_k, float top_p, const double* u,
+                              int u_stride, int64_t* tokens, int T, int* pos, int greedy, int B, const float* tables,
+                              const int* table_off, const float* chan, const float* evt, float* feat, int C, int total_upscaling,
+                              int E, int pe, int* done, void* stream);
 int vqcpc_decode_advance(int* pos, int delta, void* stream);
 
 /* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159

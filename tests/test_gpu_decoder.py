@@ -216,3 +216,19 @@ def test_cached_generation_teacher_forced_logits():
     logits = dec.forward(rec['source'].cuda(), x)['weights_per_category']
     for c, w in enumerate(logits):
         assert torch.equal(w.argmax(dim=-1), x[:, :, c])
+
+
+def test_ln_linear_small_vs_fp64():
+    """vqcpc_ln_linear_small: LayerNorm on load + linear, normalised rows written once."""
+    from VQCPCB import _native, ops
+    g = torch.Generator().manual_seed(9)
+    for M, N, K in [(1, 512, 512), (7, 1536, 512), (16, 64, 512)]:
+        x = (torch.randn(M, K, generator=g) * 3 + 1).cuda()
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b, gam, bet = (torch.randn(n, generator=g).cuda() for n in (N, K, K))
+        out, lno = torch.empty(M, N, device='cuda'), torch.empty(M, K, device='cuda')
+        _native.call('vqcpc_ln_linear_small', _pp(x), K, _pp(gam), _pp(bet), 1e-5, _pp(lno), _pp(w), _pp(b), None, N, _pp(out), N, M, N, K,
+                     1, 1.0, 0, ops._stream())
+        ln = torch.nn.functional.layer_norm(x.double(), (K,), gam.double(), bet.double(), 1e-5)
+        assert rel_err(lno, ln) < 2e-6
+        assert rel_err(out, (ln @ w.double().t() + b.double()).clamp(min=0)) < 3e-6

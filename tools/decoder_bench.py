@@ -105,13 +105,17 @@ def main():
         xg[:, e, c] = lg.argmax(dim=-1)
         same += int((xg[:, e, c] == cached[:, e, c]).sum())
     torch.cuda.synchronize()
-    ms_full_token = (time.perf_counter() - t0) * 1e3 / n_cmp
+    ms_full_token = (time.perf_counter() - t0) * 1e3 / max(1, n_cmp)
     # teacher-forced logits vs the CPU oracle on the same window (also the CPU baseline timing)
     ocfg = dict(CFG, total_upscaling=16)
     xc, cc = cached[:1].cpu(), codes[:1].cpu()
     torch.set_num_threads(os.cpu_count())
     cpu_s = []
-    for _ in range(max(1, a.cpu_forwards)):
+    if a.cpu_forwards <= 0:
+        print(json.dumps(dict(value=B * T / ms_cached * 1e3, ms_per_window=ms_cached, us_per_token_step=ms_cached / T * 1e3,
+                              ms_per_window_no_graph=ms_eager)))
+        return
+    for _ in range(a.cpu_forwards):
         t0 = time.perf_counter()
         with torch.no_grad():
             _, lo = D.decoder_forward(cc, xc, prm, ocfg)
@@ -127,7 +131,7 @@ def main():
                ms_per_window=ms_cached, us_per_token_step=ms_cached / T * 1e3, ms_per_window_no_graph=ms_eager,
                kernel_launches_per_window=dec.last_generation_launches, host_calls_per_window=launches_host,
                full_recompute=dict(ms_per_forward=ms_fwd, ms_per_token_measured=ms_full_token,
-                                   tokens_per_sec=B / ms_full_token * 1e3, tokens_timed=n_cmp),
+                                   tokens_per_sec=B / max(ms_full_token, 1e-9) * 1e3, tokens_timed=n_cmp),
                cpu_baseline=dict(kind='port', cores=torch.get_num_threads(), s_per_forward=cpu_fwd,
                                  value=1.0 / cpu_fwd, unit='tokens/s',
                                  sample=f'{len(cpu_s)} full forwards at batch 1 (the reference runs one per generated token)'),

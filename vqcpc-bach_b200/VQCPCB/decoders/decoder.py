@@ -291,107 +291,28 @@ class Decoder(nn.Module):
         return x
 
     def _generate_cached(self, codes, temperature, top_k, top_p, generator, greedy, uniforms, use_graph, exclude):
-        """<= 16 sequences through the incremental path; see csrc/decode.cu for the launch sequence of one token step."""
+        """<= 16 sequences through the incremental path.  The buffers, the launch sequence and its CUDA graph live in a
+        ``_DecodeSession`` cached per (batch, sampling settings): a later call only refreshes the memory keys / values and the
+        uniforms and replays."""
         dev = self.sos.device
-        B, d, H, C = codes.size(0), self.d_model, self.n_head, self.num_channels
-        hd = d // H
-        scale = float(hd) ** -0.5
-        T, up = self.num_tokens_target, self.total_upscaling
-        Ev = T // C
-        memory, S = self._encode_memory(codes)
-        layers = list(self.transformer.decoder.layers)
-        f32 = dict(dtype=torch.float32, device=dev)
-        # keys / values of the memory for every decoder layer (multihead_attention_custom.py:173-196), computed once
-        cross_kv = [ops.linear_fwd(memory, l.multihead_attn.in_proj_weight[d:], l.multihead_attn.in_proj_bias[d:]).contiguous()
-                    for l in layers]
-        kc = [torch.zeros(B * T, d, **f32) for _ in layers]
-        vc = [torch.zeros(B * T, d, **f32) for _ in layers]
-        sm1, sm2 = device_maps(T, T, dev)
-        cm1, cm2 = device_maps(T, S, dev)
-        memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None
-        tables = torch.cat([e.weight.detach() for e in self.data_processor.embeddings], dim=0).contiguous()
-        rows = [e.weight.shape[0] for e in self.data_processor.embeddings]
-        table_off = torch.tensor([sum(rows[:c]) for c in range(C)], dtype=torch.int32, device=dev)
-        E = tables.shape[1]
-        pe = self.target_channel_embeddings.shape[-1]
-        F = E + 2 * pe
-        chan = self.target_channel_embeddings.detach().reshape(C, pe).contiguous()
-        evt = self.target_events_positioning_embeddings.detach().reshape(-1, pe).contiguous()
-        ff = layers[0].linear1.weight.shape[0]
-        Vmax = max(self.num_tokens_per_channel)
-        tokens = torch.zeros(B, T, dtype=torch.int64, device=dev)
-        pos = torch.zeros(1, dtype=torch.int32, device=dev)
-        feat, x, x1, x2, y, att, qc = (torch.empty(B, n, **f32) for n in (F, d, d, d, d, d, d))
-        qkv, hmid, logits = torch.empty(B, 3 * d, **f32), torch.empty(B, ff, **f32), torch.empty(B, Vmax, **f32)
-        mean, rstd = torch.empty(B, **f32), torch.empty(B, **f32)
+        B, T = codes.size(0), self.num_tokens_target
+        ex_key = None if not exclude else tuple(sorted((c, tuple(sorted(v))) for c, v in exclude.items()))
+        key = (B, float(temperature), int(top_k), float(top_p), bool(greedy), ex_key, bool(use_graph), self.sos.data_ptr(),
+               ops.weight_version())
+        cache = self.__dict__.setdefault('_decode_sessions', {})
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.clear()
+            cache[key] = _DecodeSession(self, B, temperature, top_k, top_p, greedy, exclude, use_graph)
         if uniforms is None:
             uniforms = torch.rand(T, B, dtype=torch.float64, device=dev, generator=generator)
-        u = torch.as_tensor(uniforms, dtype=torch.float64).to(dev).contiguous()
+        u = torch.as_tensor(uniforms, dtype=torch.float64).to(dev)
         assert u.shape == (T, B)
-        head_bias = []
-        for c, ps in enumerate(self.pre_softmaxes):
-            bvec = ps.bias.detach().clone()
-            if exclude and c in exclude:
-                bvec[list(exclude[c])] = -float('inf')
-            head_bias.append(bvec)
-        sos = self.sos.detach().reshape(d).contiguous()
-        keep = [memory, cross_kv, kc, vc, tables, table_off, chan, evt, u, head_bias, sos]    # noqa: F841  (alive during replay)
-        call = _native.call
+        sess = cache[key]
+        tokens = sess.run(codes, u)
+        self.last_generation_launches = sess.launches_per_window
+        return tokens
 
-        def lin(xin, ldx, w, b, res, out, ldo, N, K, relu=0, sc=1.0, sc_cols=0, row0=None):
-            call('vqcpc_linear_small', _p(xin), ldx, _p(w), _p(b), _p(res), d, _p(out), ldo, B, N, K, relu, sc, sc_cols, _p(row0),
-                 _p(pos), ops._stream())
-
-        def ln(src, norm, dst):
-            call('vqcpc_layernorm_fwd', _p(src), _p(norm.weight), _p(norm.bias), _p(dst), None, None, _p(mean), _p(rstd), B, d,
-                 float(norm.eps), ops._stream())
-
-        def step(c):
-            st = ops._stream()
-            call('vqcpc_decode_features', _p(tokens), _p(pos), _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), B, T, C, up, E,
-                 pe, st)
-            lin(feat, F, self.linear_target.weight, self.linear_target.bias, None, x, d, d, F, row0=sos)
-            for li, l in enumerate(layers):
-                a = l.self_attn
-                lin(x, d, a.in_proj_weight, a.in_proj_bias, None, qkv, 3 * d, 3 * d, d, sc=scale, sc_cols=d)
-                call('vqcpc_attn_decode', _p(qkv), 3 * d, _p(qkv[:, d:]), _p(qkv[:, 2 * d:]), 3 * d, _p(kc[li]), _p(vc[li]), d, T,
-                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
-                lin(att, d, a.out_proj.weight, a.out_proj.bias, x, y, d, d, d)
-                ln(y, l.norm1, x1)
-                a = l.multihead_attn
-                lin(x1, d, a.in_proj_weight[:d], a.in_proj_bias[:d], None, qc, d, d, d, sc=scale, sc_cols=d)
-                call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(cross_kv[li]), _p(cross_kv[li][:, d:]), 2 * d, S,
-                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd,
-                     st)
-                lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
-                ln(y, l.norm2, x2)
-                lin(x2, d, l.linear1.weight, l.linear1.bias, None, hmid, ff, ff, d, relu=1)
-                lin(hmid, ff, l.linear2.weight, l.linear2.bias, x2, y, d, d, ff)
-                ln(y, l.norm3, x)
-            V = self.num_tokens_per_channel[c]
-            lin(x, d, self.pre_softmaxes[c].weight, head_bias[c], None, logits, Vmax, V, d)
-            call('vqcpc_sample_step', _p(logits), Vmax, V, float(temperature), int(top_k), float(top_p), _p(u), B, _p(tokens), T,
-                 _p(pos), int(bool(greedy)), B, st)
-            call('vqcpc_decode_advance', _p(pos), 1, st)
-
-        def event():
-            for c in range(C):
-                step(c)
-
-        event()                                              # event 0 eagerly (also the warm-up the capture needs)
-        if Ev > 1:
-            if use_graph:
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    event()
-                for _ in range(1, Ev):
-                    graph.replay()
-            else:
-                for _ in range(1, Ev):
-                    event()
-        self.last_generation_launches = Ev * C * (5 + 11 * len(layers))
-        return tokens.view(B, Ev, C)
 
     @torch.no_grad()
     def generate(self, temperature, batch_size=1, top_k=0, top_p=1., seed_set=None, **kwargs):
@@ -409,3 +330,124 @@ class Decoder(nn.Module):
         _, recoding, _ = self.encoder(torch.cat([tensor_dict['x'].to(x.device).long(), x], dim=0))
         recoding = None if recoding is None else self.encoder.merge_codes(recoding)
         return x_original, x, recoding
+
+
+class _DecodeSession:
+    """Static buffers + launch sequence (+ CUDA graph of one event) of the incremental decoder for a fixed batch and fixed
+    sampling settings; see csrc/decode.cu for the step.  Holds raw pointers into the decoder's parameters: the session key
+    carries ``ops.weight_version()`` and a parameter address, so re-loaded / moved weights build a fresh session."""
+
+    def __init__(self, dec, B, temperature, top_k, top_p, greedy, exclude, use_graph):
+        self.dec, self.B, self.use_graph = dec, B, use_graph
+        dev = dec.sos.device
+        d, H, C = dec.d_model, dec.n_head, dec.num_channels
+        hd = d // H
+        scale = float(hd) ** -0.5
+        T, up = dec.num_tokens_target, dec.total_upscaling
+        S = dec.seq_len_src
+        self.T, self.C, self.Ev, self.S = T, C, T // C, S
+        layers = list(dec.transformer.decoder.layers)
+        self.layers = layers
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.cross_kv = [torch.empty(B * S, 2 * d, **f32) for _ in layers]
+        kc = [torch.zeros(B * T, d, **f32) for _ in layers]
+        vc = [torch.zeros(B * T, d, **f32) for _ in layers]
+        sm1, sm2 = device_maps(T, T, dev)
+        cm1, cm2 = device_maps(T, S, dev)
+        memory_mask = _anticausal_mask(S, dev, T) if dec.cross_attention_type == 'anticausal' else None
+        tables = torch.cat([e.weight.detach() for e in dec.data_processor.embeddings], dim=0).contiguous()
+        rows = [e.weight.shape[0] for e in dec.data_processor.embeddings]
+        table_off = torch.tensor([sum(rows[:c]) for c in range(C)], dtype=torch.int32, device=dev)
+        E = tables.shape[1]
+        pe = dec.target_channel_embeddings.shape[-1]
+        F = E + 2 * pe
+        chan = dec.target_channel_embeddings.detach().reshape(C, pe).contiguous()
+        evt = dec.target_events_positioning_embeddings.detach().reshape(-1, pe).contiguous()
+        ff = layers[0].linear1.weight.shape[0]
+        Vmax = max(dec.num_tokens_per_channel)
+        self.tokens = tokens = torch.zeros(B, T, dtype=torch.int64, device=dev)
+        self.pos = pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.u = u = torch.zeros(T, B, dtype=torch.float64, device=dev)
+        feat, x, x1, x2, y, att, qc = (torch.zeros(B, n, **f32) for n in (F, d, d, d, d, d, d))
+        qkv, hmid, logits = torch.empty(B, 3 * d, **f32), torch.empty(B, ff, **f32), torch.empty(B, Vmax, **f32)
+        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        head_bias = []
+        for c, ps in enumerate(dec.pre_softmaxes):
+            bvec = ps.bias.detach().clone()
+            if exclude and c in exclude:
+                bvec[list(exclude[c])] = -float('inf')
+            head_bias.append(bvec)
+        sos = dec.sos.detach().reshape(d).contiguous()
+        self._keep = [kc, vc, sm1, sm2, cm1, cm2, memory_mask, tables, table_off, chan, evt, head_bias, sos, feat, x, x1, x2, y,
+                      att, qc, qkv, hmid, logits, done]
+        call = _native.call
+
+        def lin(xin, ldx, w, b, res, out, ldo, N, K, relu=0, sc=1.0, sc_cols=0, row0=None):
+            call('vqcpc_linear_small', _p(xin), ldx, _p(w), _p(b), _p(res), d, _p(out), ldo, B, N, K, relu, sc, sc_cols, _p(row0),
+                 _p(pos), ops._stream())
+
+        def ln_lin(xin, norm, ln_out, w, b, out, ldo, N, relu=0, sc=1.0, sc_cols=0):
+            """out = linear(LayerNorm(xin)); the normalised rows also go to ln_out (the residual of a later linear)."""
+            call('vqcpc_ln_linear_small', _p(xin), d, _p(norm.weight), _p(norm.bias), float(norm.eps), _p(ln_out), _p(w), _p(b), None, d,
+                 _p(out), ldo, B, N, d, relu, sc, sc_cols, ops._stream())
+
+        def step(c):
+            st = ops._stream()
+            lin(feat, F, dec.linear_target.weight, dec.linear_target.bias, None, x, d, d, F, row0=sos)
+            for li, l in enumerate(layers):
+                a = l.self_attn
+                if li == 0:
+                    lin(x, d, a.in_proj_weight, a.in_proj_bias, None, qkv, 3 * d, 3 * d, d, sc=scale, sc_cols=d)
+                else:                                        # x = norm3 of the previous layer, applied while staging
+                    ln_lin(y, layers[li - 1].norm3, x, a.in_proj_weight, a.in_proj_bias, qkv, 3 * d, 3 * d, sc=scale, sc_cols=d)
+                call('vqcpc_attn_decode', _p(qkv), 3 * d, _p(qkv[:, d:]), _p(qkv[:, 2 * d:]), 3 * d, _p(kc[li]), _p(vc[li]), d, T,
+                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
+                lin(att, d, a.out_proj.weight, a.out_proj.bias, x, y, d, d, d)
+                a = l.multihead_attn
+                ln_lin(y, l.norm1, x1, a.in_proj_weight[:d], a.in_proj_bias[:d], qc, d, d, sc=scale, sc_cols=d)
+                ckv = self.cross_kv[li]
+                call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(ckv), _p(ckv[:, d:]), 2 * d, S, _p(a.attn_bias.e1),
+                     _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd, st)
+                lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
+                ln_lin(y, l.norm2, x2, l.linear1.weight, l.linear1.bias, hmid, ff, ff, relu=1)
+                lin(hmid, ff, l.linear2.weight, l.linear2.bias, x2, y, d, d, ff)
+            V = dec.num_tokens_per_channel[c]
+            ln_lin(y, layers[-1].norm3, None, dec.pre_softmaxes[c].weight, head_bias[c], logits, Vmax, V)
+            # draw the token, write the feature row of the next position, advance the position
+            call('vqcpc_decode_sample_embed', _p(logits), Vmax, V, float(temperature), int(top_k), float(top_p), _p(u), B, _p(tokens), T,
+                 _p(pos), int(bool(greedy)), B, _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), C, up, E, pe, _p(done), st)
+
+        def event():
+            for c in range(C):
+                step(c)
+
+        self.event = event
+        self.graph = None
+        self.launches_per_window = T * (3 + 8 * len(layers))
+
+    def run(self, codes, u):
+        dec, d = self.dec, self.dec.d_model
+        memory, S = dec._encode_memory(codes)
+        assert S == self.S
+        for ckv, l in zip(self.cross_kv, self.layers):      # keys / values of the memory (multihead_attention_custom.py:173-196)
+            a = l.multihead_attn
+            ops.linear_fwd(memory, a.in_proj_weight[d:], a.in_proj_bias[d:], out=ckv)
+        self.u.copy_(u)
+        self.tokens.zero_()
+        self.pos.zero_()
+        self.event()                                         # event 0 eagerly (also the warm-up a capture needs)
+        if self.Ev > 1:
+            if self.use_graph:
+                if self.graph is None:
+                    torch.cuda.synchronize()
+                    pos0 = self.pos.clone()
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph):
+                        self.event()
+                    self.pos.copy_(pos0)                      # capture does not execute
+                for _ in range(1, self.Ev):
+                    self.graph.replay()
+            else:
+                for _ in range(1, self.Ev):
+                    self.event()
+        return self.tokens.view(self.B, self.Ev, self.C).clone()

@@ -94,6 +94,10 @@ def weight_split(w):
 _WEIGHT_VERSION = [0]
 
 
+def weight_version():
+    return _WEIGHT_VERSION[0]
+
+
 def bump_weight_version():
     """Call after parameters change (optimizer step / load_state_dict) so cached bf16 splits are rebuilt."""
     _WEIGHT_VERSION[0] += 1
