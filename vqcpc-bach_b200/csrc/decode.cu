@@ -48,74 +48,240 @@ __global__ void decode_features_kernel(const int64_t* __restrict__ tokens, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// out[b, n] = epilogue( sum_k x[b, k] W[n, k] + bias[n] ),  b < M <= 16.  One warp per output column, x staged in shared
-// memory, W rows streamed with 16-byte loads.  Epilogue order = the layer code's: bias, scale of the first `scale_cols` columns
-// (the q third of the in-projection, multihead_attention_custom.py:247), ReLU, residual.  row0 != NULL and *pos == 0: the whole
-// row is replaced by row0 (the start-of-sequence vector, decoder.py:476-482).
+// out[b, n] = epilogue( sum_k x^[b, k] W[n, k] + bias[n] ),  b < M <= 16.  One warp per output column: the W row lives in
+// registers (KV float4 per lane), the M input rows are read straight through L1 (they are a few KB and every warp reads all of
+// them), RB rows in flight.  No shared memory, no block barrier: the kernel is one dependent chain of
+//   W / LayerNorm parameters (independent of the producer) -> rows -> warp reductions -> store,
+// which is what bounds a launch at these sizes.
+// LN: x^ = nn.LayerNorm(K)(x) computed per warp in registers (post-LN blocks, transformer_custom.py:283-289: the producer wrote
+// the pre-norm sum; biased variance, eps inside the square root, two passes like layernorm_fwd_kernel); warp 0 of CTA 0 also
+// stores the normalised rows (ln_out), the residual input of a later linear.
+// Epilogue order = the layer code's: bias, scale of the first `scale_cols` columns (the q third of the in-projection,
+// multihead_attention_custom.py:247), ReLU, residual.  row0 != NULL and *pos == 0: the whole row is replaced by row0 (the
+// start-of-sequence vector, decoder.py:476-482).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MT>
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+template <int KV, int RB, bool LN>
 __global__ void __launch_bounds__(128)
 linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
                     const float* __restrict__ residual, int ldr, float* __restrict__ out, int ldo, int M, int N, int K, int relu,
                     float scale, int scale_cols, const float* __restrict__ row0, const int* __restrict__ pos,
                     const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
                     float* __restrict__ ln_out) {
-  extern __shared__ __align__(16) float xs[];      // [MT][K]
-  for (int t = threadIdx.x; t < MT * (K / 4); t += blockDim.x) {
-    const int b = t / (K / 4), c = t % (K / 4);
-    reinterpret_cast<float4*>(xs)[t] = b < M ? *reinterpret_cast<const float4*>(x + (size_t)b * ldx + c * 4) : make_float4(0, 0, 0, 0);
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (ln_gamma) {
-    // nn.LayerNorm over the K input columns applied while staging (transformer_custom.py:283-289 post-LN: the producer wrote
-    // the pre-norm sum); biased variance, eps inside the square root, two passes like layernorm_fwd_kernel.  CTA 0 also
-    // stores the normalised rows: they are the residual input of a later linear.
-    for (int b = warp; b < M; b += 4) {
-      float* row = xs + b * K;
-      float sum = 0.f;
-      for (int c = lane; c < K; c += 32) sum += row[c];
-      const float mu = warp_sum(sum) / K;
-      float q = 0.f;
-      for (int c = lane; c < K; c += 32) {
-        const float a = row[c] - mu;
-        q += a * a;
+  const int n = blockIdx.x * 4 + warp;
+  if (n >= N) return;
+  const int K4 = K >> 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[KV], g[LN ? KV : 1], be[LN ? KV : 1];
+#pragma unroll
+  for (int i = 0; i < KV; ++i) {
+    const int c = i * 32 + lane;
+    w[i] = c < K4 ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + c) : zero4;
+    if (LN) {
+      g[i] = c < K4 ? __ldg(reinterpret_cast<const float4*>(ln_gamma) + c) : zero4;
+      be[i] = c < K4 ? __ldg(reinterpret_cast<const float4*>(ln_beta) + c) : zero4;
+    }
+  }
+  const float bn = bias ? __ldg(bias + n) : 0.f;
+  const bool use_row0 = row0 != nullptr && *pos == 0;
+  const bool writer = LN && ln_out != nullptr && blockIdx.x == 0 && warp == 0;
+  const float invK = 1.f / (float)K;
+  for (int b0 = 0; b0 < M; b0 += RB) {
+    float4 xr[RB][KV];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int c = i * 32 + lane;
+        xr[r][i] = (b0 + r < M && c < K4) ? *(reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * ldx) + c) : zero4;
       }
-      const float rs = 1.0f / sqrtf(warp_sum(q) / K + ln_eps);
-      for (int c = lane; c < K; c += 32) {
-        const float o = (row[c] - mu) * rs * ln_gamma[c] + ln_beta[c];
-        row[c] = o;
-        if (ln_out && blockIdx.x == 0) ln_out[(size_t)b * K + c] = o;
+    float acc[RB];
+    if (LN) {
+      float mu[RB], rs[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) t += (xr[r][i].x + xr[r][i].y) + (xr[r][i].z + xr[r][i].w);
+        mu[r] = t;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) mu[r] = warp_sum(mu[r]) * invK;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          if (i * 32 + lane < K4) {
+            const float a0 = xr[r][i].x - mu[r], a1 = xr[r][i].y - mu[r], a2 = xr[r][i].z - mu[r], a3 = xr[r][i].w - mu[r];
+            t += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          }
+        }
+        rs[r] = t;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) rs[r] = 1.0f / sqrtf(warp_sum(rs[r]) * invK + ln_eps);
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          float4 o;
+          o.x = (xr[r][i].x - mu[r]) * rs[r] * g[i].x + be[i].x;
+          o.y = (xr[r][i].y - mu[r]) * rs[r] * g[i].y + be[i].y;
+          o.z = (xr[r][i].z - mu[r]) * rs[r] * g[i].z + be[i].z;
+          o.w = (xr[r][i].w - mu[r]) * rs[r] * g[i].w + be[i].w;
+          xr[r][i] = o;
+          const int c = i * 32 + lane;
+          if (writer && b0 + r < M && c < K4) *(reinterpret_cast<float4*>(ln_out + (size_t)(b0 + r) * K) + c) = o;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) t += dot4(w[i], xr[r][i]);
+      acc[r] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = warp_sum(acc[r]);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int b = b0 + r;
+      if (lane == r && b < M) {
+        float v = acc[r] + bn;
+        if (n < scale_cols) v *= scale;
+        if (relu) v = fmaxf(v, 0.f);
+        if (residual) v += residual[(size_t)b * ldr + n];
+        if (use_row0) v = row0[n];
+        out[(size_t)b * ldo + n] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same product for 3 <= M <= 16 rows: the M input rows are staged in shared memory by M bulk (TMA) copies that one thread
+// issues at kernel entry - ONE round of memory latency for the whole input, overlapped with every warp's W-row load - instead
+// of one round per group of rows.  LN: warp w normalises rows w, w + 4, .. in place once per CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ls_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (it > (1u << 26)) { printf("vqcpc linear_small: mbarrier wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+
+template <int KV, int MT, bool LN>
+__global__ void __launch_bounds__(128)
+linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                     const float* __restrict__ residual, int ldr, float* __restrict__ out, int ldo, int M, int N, int K, int relu,
+                     float scale, int scale_cols, const float* __restrict__ row0, const int* __restrict__ pos,
+                     const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
+                     float* __restrict__ ln_out) {
+  extern __shared__ __align__(128) unsigned char ls_smem[];   // [0, 8) mbarrier, [16, 16 + M * K * 4) rows
+  float* xs = reinterpret_cast<float*>(ls_smem + 16);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ls_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(M * K * 4)) : "memory");
+    for (int b = 0; b < M; ++b)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(xs + (size_t)b * K)), "l"(x + (size_t)b * ldx), "r"((uint32_t)(K * 4)), "r"(bar)
+                   : "memory");
+  }
+  const int n = blockIdx.x * 4 + warp;
+  const bool active = n < N;
+  const int K4 = K >> 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[KV];
+#pragma unroll
+  for (int i = 0; i < KV; ++i) {
+    const int c = i * 32 + lane;
+    w[i] = (active && c < K4) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + c) : zero4;
+  }
+  float4 g[LN ? KV : 1], be[LN ? KV : 1];                          // requested before the wait, like the W row
+  if (LN) {
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      const int c = i * 32 + lane;
+      g[i] = c < K4 ? __ldg(reinterpret_cast<const float4*>(ln_gamma) + c) : zero4;
+      be[i] = c < K4 ? __ldg(reinterpret_cast<const float4*>(ln_beta) + c) : zero4;
+    }
+  }
+  const float bn = (active && bias) ? __ldg(bias + n) : 0.f;
+  const float resv = (active && residual && lane < M) ? residual[(size_t)lane * ldr + n] : 0.f;
+  const bool use_row0 = row0 != nullptr && *pos == 0;
+  __syncthreads();                                 // the barrier initialisation is visible to the waiting threads
+  ls_mbar_wait(bar, 0);
+  if (LN) {
+    const float invK = 1.f / (float)K;
+    for (int b = warp; b < M; b += 4) {
+      float4* row = reinterpret_cast<float4*>(xs + (size_t)b * K);
+      float4 v[KV];
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int c = i * 32 + lane;
+        v[i] = c < K4 ? row[c] : zero4;
+        t += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      const float mu = warp_sum(t) * invK;
+      t = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i)
+        if (i * 32 + lane < K4) {
+          const float a0 = v[i].x - mu, a1 = v[i].y - mu, a2 = v[i].z - mu, a3 = v[i].w - mu;
+          t += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+      const float rs = 1.0f / sqrtf(warp_sum(t) * invK + ln_eps);
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const int c = i * 32 + lane;
+        if (c < K4) {
+          float4 o;
+          o.x = (v[i].x - mu) * rs * g[i].x + be[i].x;
+          o.y = (v[i].y - mu) * rs * g[i].y + be[i].y;
+          o.z = (v[i].z - mu) * rs * g[i].z + be[i].z;
+          o.w = (v[i].w - mu) * rs * g[i].w + be[i].w;
+          row[c] = o;
+          if (ln_out && blockIdx.x == 0) *(reinterpret_cast<float4*>(ln_out + (size_t)b * K) + c) = o;
+        }
       }
     }
     __syncthreads();
   }
-  const int n = blockIdx.x * 4 + warp;
-  if (n >= N) return;                              // (after the last block-wide barrier)
-  const bool use_row0 = row0 != nullptr && *pos == 0;
+  if (!active) return;
   float acc[MT];
 #pragma unroll
   for (int b = 0; b < MT; ++b) acc[b] = 0.f;
-  const float4* w4 = reinterpret_cast<const float4*>(W + (size_t)n * K);
-#pragma unroll 4
-  for (int c = lane; c < K / 4; c += 32) {
-    const float4 w = __ldg(w4 + c);
 #pragma unroll
-    for (int b = 0; b < MT; ++b) {
-      const float4 v = reinterpret_cast<const float4*>(xs + b * K)[c];
-      acc[b] += w.x * v.x + w.y * v.y + w.z * v.z + w.w * v.w;
+  for (int i = 0; i < KV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < K4) {
+#pragma unroll
+      for (int b = 0; b < MT; ++b)
+        if (b < M) acc[b] += dot4(w[i], reinterpret_cast<const float4*>(xs + (size_t)b * K)[c]);
     }
   }
 #pragma unroll
   for (int b = 0; b < MT; ++b) acc[b] = warp_sum(acc[b]);
-  const float bn = bias ? bias[n] : 0.f;
 #pragma unroll
   for (int b = 0; b < MT; ++b) {
     if (lane == b && b < M) {
       float v = acc[b] + bn;
       if (n < scale_cols) v *= scale;
       if (relu) v = fmaxf(v, 0.f);
-      if (residual) v += residual[(size_t)b * ldr + n];
+      if (residual) v += resv;
       if (use_row0) v = row0[n];
       out[(size_t)b * ldo + n] = v;
     }
@@ -133,22 +299,23 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
 constexpr int AD_THREADS = 128;
 constexpr int AD_MAX_SPLIT = 8;
 
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-
-__global__ void __launch_bounds__(AD_THREADS)
+template <bool PREFETCH_V>   // true: latency-optimised (few CTAs in flight, 255 registers); false: 3 CTAs per SM for full grids
+__global__ void __launch_bounds__(AD_THREADS, PREFETCH_V ? 1 : 3)
 attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k_new, const float* __restrict__ v_new, int ldn,
                    float* kcache, float* vcache, int ldc, int Lmax, const float* __restrict__ e1, const float* __restrict__ e2,
                    const int* __restrict__ map1, const int* __restrict__ map2, const float* __restrict__ mask, int Lk,
                    const int* __restrict__ pos, int causal, float* __restrict__ out, int ldo, int chunk_max) {
-  extern __shared__ __align__(16) float sm[];      // [64] q, [2][64] partial outputs, [8] reductions, [66] result, [chunk] scores
+  extern __shared__ __align__(16) float sm[];      // [64] q, [8][64] partial outputs, [8] reductions, [72] result, [8][72] gather, [chunk] scores
   float* qs = sm;
-  float* part = qs + HD;
-  float* red = part + 2 * HD;
-  float* result = red + 8;                         // [0..63] sum_j e^(s_j - m) v_j, [64] m, [65] z   (read by CTA 0 of the cluster)
-  float* sc = result + 72;
+  float* part = qs + HD;                           // [8][64]
+  float* red = part + 8 * HD;
+  float* result = red + 8;                         // [0..63] sum_j e^(s_j - m) v_j, [64] m, [65] z
+  float* gather = result + 72;                     // [8][72]: the results of all CTAs of the cluster (used in CTA 0)
+  float* sc = gather + AD_MAX_SPLIT * 72;
   uint32_t crank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   const int h = blockIdx.x, tid = threadIdx.x, i = *pos;
   const int64_t p = blockIdx.y;
   const int n = causal ? min(i + 1, Lk) : Lk;
@@ -159,51 +326,68 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   float* vc = vcache + (size_t)p * Lmax * ldc + h * HD;
   const float* kn = k_new ? k_new + (size_t)p * ldn + h * HD : nullptr;
   const float* vn = v_new ? v_new + (size_t)p * ldn + h * HD : nullptr;
-  if (tid < HD) {
-    qs[tid] = q[(size_t)p * ldq + h * HD + tid];
-    if (kn && crank == 0) {                        // the appended row is read from k_new / v_new below, never from the cache
-      kc[(size_t)i * ldc + tid] = kn[tid];
-      vc[(size_t)i * ldc + tid] = vn[tid];
-    }
-  }
-  __syncthreads();
-  // scores: 16 lanes per key, one float4 each, 8 keys per pass, two passes in flight
-  const int sub = tid & 15, grp = tid >> 4;
-  const float4 q4 = reinterpret_cast<const float4*>(qs)[sub];
+  // Everything that only depends on the position is requested BEFORE the query is staged: the map / mask entries and the key row
+  // of this thread's first key, and the value rows of the first accumulation pass.  With one key per thread (chunk <= 128) the
+  // kernel is then three rounds of memory latency: position -> {q, maps, keys, values} -> relative-table rows.
   const float* e1h = e1 ? e1 + (size_t)h * Lk * HD : nullptr;
   const float* e2h = e2 ? e2 + (size_t)h * Lk * HD : nullptr;
   const int* m1row = map1 ? map1 + (size_t)i * Lk : nullptr;
   const int* m2row = map2 ? map2 + (size_t)i * Lk : nullptr;
   const float* mrow = mask ? mask + (size_t)i * Lk : nullptr;
-  for (int j0 = j_lo; j0 < j_hi; j0 += 16) {
-    float s[2], add[2];
+  int j = j_lo + tid;
+  int m1 = -1, m2 = -1;
+  float add = 0.f;
+  float4 kreg[HD / 4];
+  if (j < j_hi) {
+    m1 = m1row ? m1row[j] : -1;
+    m2 = m2row ? m2row[j] : -1;
+    add = mrow ? mrow[j] : 0.f;
+    const float4* kr = reinterpret_cast<const float4*>((kn && j == i) ? kn : kc + (size_t)j * ldc);
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const int j = j0 + w * 8 + grp;
-      s[w] = 0.f;
-      add[w] = 0.f;
-      if (j < j_hi) {
-        const float* krow = (kn && j == i) ? kn : kc + (size_t)j * ldc;
-        s[w] = dot4(q4, *reinterpret_cast<const float4*>(krow + sub * 4));
-        if (m1row) {
-          const int m = m1row[j];
-          if (m >= 0) s[w] += dot4(q4, __ldg(reinterpret_cast<const float4*>(e1h + (size_t)(m % Lk) * HD) + sub));
-          else if (m == -2) add[w] += -100.f;
-        }
-        if (m2row) {
-          const int m = m2row[j];
-          if (m >= 0) s[w] += dot4(q4, __ldg(reinterpret_cast<const float4*>(e2h + (size_t)(m % Lk) * HD) + sub));
-          else if (m == -2) add[w] += -100.f;
-        }
-        if (mrow) add[w] += mrow[j];
-      }
+    for (int c = 0; c < HD / 4; ++c) kreg[c] = kr[c];
+  }
+  const int sub = tid & 15, grp = tid >> 4;
+  float4 vv[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int jj = t * 8 + grp, ja = j_lo + jj;
+    const float* vrow = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
+    if (PREFETCH_V) vv[t] = jj < cnt ? *reinterpret_cast<const float4*>(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid < HD) {
+    qs[tid] = q[(size_t)p * ldq + h * HD + tid];
+    if (kn && crank == 0) {                        // the appended row is read from k_new / v_new, never from the cache
+      kc[(size_t)i * ldc + tid] = kn[tid];
+      vc[(size_t)i * ldc + tid] = vn[tid];
     }
+  }
+  __syncthreads();
+  // scores: ONE KEY PER THREAD - its 16 + 16 + 16 float4 loads (key row, e1 row, e2 row) are independent of each other (the rows
+  // are whole 128-byte lines, nothing is over-fetched)
+  const float4* q4 = reinterpret_cast<const float4*>(qs);
+  while (j < j_hi) {
+    const float4* r1 = m1 >= 0 ? reinterpret_cast<const float4*>(e1h + (size_t)(m1 % Lk) * HD) : nullptr;
+    const float4* r2 = m2 >= 0 ? reinterpret_cast<const float4*>(e2h + (size_t)(m2 % Lk) * HD) : nullptr;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int c = 0; c < HD / 4; ++c) s0 += dot4(q4[c], kreg[c]);
+    if (r1) {
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s[w] += __shfl_xor_sync(0xffffffffu, s[w], o);
-      const int j = j0 + w * 8 + grp;
-      if (sub == 0 && j < j_hi) sc[j - j_lo] = s[w] + add[w];
+      for (int c = 0; c < HD / 4; ++c) s1 += dot4(q4[c], __ldg(r1 + c));
+    } else if (m1 == -2) add += -100.f;
+    if (r2) {
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c) s2 += dot4(q4[c], __ldg(r2 + c));
+    } else if (m2 == -2) add += -100.f;
+    sc[j - j_lo] = (s0 + s1 + s2) + add;
+    j += AD_THREADS;
+    if (j < j_hi) {
+      m1 = m1row ? m1row[j] : -1;
+      m2 = m2row ? m2row[j] : -1;
+      add = mrow ? mrow[j] : 0.f;
+      const float4* kr = reinterpret_cast<const float4*>((kn && j == i) ? kn : kc + (size_t)j * ldc);
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c) kreg[c] = kr[c];
     }
   }
   __syncthreads();
@@ -224,25 +408,37 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   z = warp_sum(z);
   if (lane == 0) red[4 + warp] = z;
   __syncthreads();
-  // o[d] = sum_j e_j v[j, d]: two key phases x 64 dims, two independent accumulators each
-  const int d = tid & 63, ph = tid >> 6;
-  float o0 = 0.f, o1 = 0.f;
-  int j = ph;
-  for (; j + 2 < cnt; j += 4) {
-    const int ja = j_lo + j, jb = ja + 2;
-    const float* va = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
-    const float* vb = (vn && jb == i) ? vn : vc + (size_t)jb * ldc;
-    o0 += sc[j] * va[d];
-    o1 += sc[j + 2] * vb[d];
+  // o[d] = sum_j e_j v[j, d]: 16 lanes x float4 per value row, 8 rows per pass, 8 passes in flight (the first 64 rows were
+  // requested at kernel entry)
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < cnt; j0 += 64) {
+    float pw[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int jj = j0 + t * 8 + grp, ja = j_lo + jj;
+      const bool ok = jj < cnt;
+      if (!PREFETCH_V || j0 > 0) {
+        const float* vrow = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
+        vv[t] = ok ? *reinterpret_cast<const float4*>(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      pw[t] = ok ? sc[jj] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      o.x += pw[t] * vv[t].x;
+      o.y += pw[t] * vv[t].y;
+      o.z += pw[t] * vv[t].z;
+      o.w += pw[t] * vv[t].w;
+    }
   }
-  for (; j < cnt; j += 2) {
-    const int ja = j_lo + j;
-    const float* va = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
-    o0 += sc[j] * va[d];
-  }
-  part[ph * HD + d] = o0 + o1;
+  reinterpret_cast<float4*>(part)[grp * 16 + sub] = o;          // part[8][64]
   __syncthreads();
-  if (tid < HD) result[tid] = part[tid] + part[HD + tid];
+  if (tid < HD) {
+    float t = 0.f;
+#pragma unroll
+    for (int gph = 0; gph < 8; ++gph) t += part[gph * HD + tid];
+    result[tid] = t;
+  }
   if (tid == 0) {
     result[64] = mx;
     result[65] = red[4] + red[5] + red[6] + red[7];
@@ -252,33 +448,29 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     if (tid < HD) out[(size_t)p * ldo + h * HD + tid] = result[tid] / result[65];
     return;
   }
+  // every CTA pushes its 66 numbers into CTA 0's shared memory (remote stores, nobody waits on a remote load), one cluster
+  // barrier, CTA 0 merges locally.  The arrive at kernel entry + this wait guarantee CTA 0 is running before it is written to.
+  __syncthreads();
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tid < 66) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(gather + crank * 72 + tid)), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(result[tid]) : "memory");
+  }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (crank == 0 && tid < HD) {
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(result);
-    float mr[AD_MAX_SPLIT], M = -INFINITY;
-    for (uint32_t r = 0; r < csize; ++r) {
-      uint32_t ra;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(base + 4u * 64u), "r"(r));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(mr[r]) : "r"(ra));
-      M = fmaxf(M, mr[r]);
-    }
+    float M = -INFINITY;
+    for (uint32_t r = 0; r < csize; ++r) M = fmaxf(M, gather[r * 72 + 64]);
     float Z = 0.f, O = 0.f;
     for (uint32_t r = 0; r < csize; ++r) {
-      if (mr[r] == -INFINITY) continue;
-      uint32_t ra, rz;
-      float zr, orr;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rz) : "r"(base + 4u * 65u), "r"(r));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(zr) : "r"(rz));
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(base + 4u * (uint32_t)tid), "r"(r));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(orr) : "r"(ra));
-      const float w = __expf(mr[r] - M);
-      Z += zr * w;
-      O += orr * w;
+      const float mr = gather[r * 72 + 64];
+      if (mr == -INFINITY) continue;
+      const float w = __expf(mr - M);
+      Z += gather[r * 72 + 65] * w;
+      O += gather[r * 72 + tid] * w;
     }
     out[(size_t)p * ldo + h * HD + tid] = O / Z;
   }
-  // peers must not exit (and release their shared memory) before CTA 0 has read it
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -310,46 +502,77 @@ __device__ int sample_row(const float* __restrict__ lg, int V, float temperature
     order[r] = c;
   }
   __syncthreads();
-  if (tid == 0) {
-    int result;
-    if (greedy) {
-      result = order[0];
-    } else {
-      const int k = min(top_k, V);
-      if (k > 0) {                                           // utils.py:112-115: logits < k-th largest removed (ties stay)
-        const float kth = srt[k - 1];
-        for (int r = k; r < V; ++r)
-          if (srt[r] < kth) srt[r] = -INFINITY;
+  // the exponentials and their sums are evaluated by the whole block (fixed-shape tree sums: deterministic); only the
+  // order-dependent scans (top-p cumulative sum, cdf) run on one thread, over precomputed values
+  __shared__ float s_red[8];
+  const int warp = tid >> 5, lane = tid & 31;
+  if (!greedy) {
+    const int k = min(top_k, V);
+    if (k > 0) {                                             // utils.py:112-115: logits < k-th largest removed (ties stay)
+      const float kth = srt[k - 1];
+      __syncthreads();
+      for (int r = k + tid; r < V; r += 256)
+        if (srt[r] < kth) srt[r] = -INFINITY;
+      __syncthreads();
+    }
+    const float mx = srt[0];
+    float* ex = reinterpret_cast<float*>(cdf);               // [V] scratch (the cdf is built later, by thread 0 only)
+    if (top_p > 0.f) {                                       // utils.py:117-127
+      float zp = 0.f;
+      for (int r = tid; r < V; r += 256) {
+        const float e = expf(srt[r] - mx);
+        ex[r] = e;
+        zp += e;
       }
-      if (top_p > 0.f) {                                     // utils.py:117-127
-        const float mx = srt[0];
-        float z = 0.f;
-        for (int r = 0; r < V; ++r) z += expf(srt[r] - mx);
+      zp = warp_sum(zp);
+      if (lane == 0) s_red[warp] = zp;
+      __syncthreads();
+      float zt = 0.f;
+      for (int wi = 0; wi < 8; ++wi) zt += s_red[wi];
+      for (int r = tid; r < V; r += 256) ex[r] = ex[r] / zt;
+      __syncthreads();
+      if (tid == 0) {
         float cum = 0.f;
         bool prev_above = false;
         for (int r = 0; r < V; ++r) {
-          cum += expf(srt[r] - mx) / z;
+          cum += ex[r];
           const bool above = cum > top_p;
           if (prev_above) srt[r] = -INFINITY;                // shifted right by one: the first token above the threshold stays
           prev_above = above;
         }
       }
-      // softmax of the filtered logits in ORIGINAL index order, double cdf like numpy
-      const float mx = srt[0];
-      for (int r = 0; r < V; ++r) x[order[r]] = srt[r];
-      float z = 0.f;
-      for (int c = 0; c < V; ++c) z += expf(x[c] - mx);
-      double run = 0.0;
+      __syncthreads();
+    }
+    // softmax of the filtered logits in ORIGINAL index order
+    for (int r = tid; r < V; r += 256) x[order[r]] = srt[r];
+    __syncthreads();
+    float zp = 0.f;
+    for (int c = tid; c < V; c += 256) {
+      const float e = expf(x[c] - mx);
+      x[c] = e;
+      zp += e;
+    }
+    zp = warp_sum(zp);
+    if (lane == 0) s_red[warp] = zp;
+    __syncthreads();
+    float zt = 0.f;
+    for (int wi = 0; wi < 8; ++wi) zt += s_red[wi];
+    for (int c = tid; c < V; c += 256) x[c] = x[c] / zt;     // float32 probabilities, as torch.softmax hands them to numpy
+    __syncthreads();
+    if (tid == 0) {
+      double run = 0.0;                                      // double cdf like numpy
       for (int c = 0; c < V; ++c) {
-        run += (double)(expf(x[c] - mx) / z);
+        run += (double)x[c];
         cdf[c] = run;
       }
-      const double uu = uniform * run;                       // cdf /= cdf[-1]  <=>  compare with u * cdf[-1]
-      result = V - 1;
-      for (int c = 0; c < V; ++c)
-        if (cdf[c] > uu) { result = c; break; }
+      s_result = V - 1;
     }
-    s_result = result;
+    __syncthreads();
+    const double uu = uniform * cdf[V - 1];                  // cdf /= cdf[-1]  <=>  compare with u * cdf[-1]
+    for (int c = tid; c < V; c += 256)                       // first index with cdf > u (the cdf is non-decreasing: one winner)
+      if (cdf[c] > uu && (c == 0 || !(cdf[c - 1] > uu))) s_result = c;
+  } else if (tid == 0) {
+    s_result = order[0];
   }
   __syncthreads();
   return s_result;
@@ -411,33 +634,73 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
                                int ldo, int M, int N, int K, int relu, float scale, int scale_cols, const float* row0, const int* pos,
                                const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out, void* stream) {
   VQ_CHECK_ARG(M >= 1 && M <= 16, "linear_small: 1 <= M <= 16 rows per call (got %d)", M);
-  VQ_CHECK_ARG(N >= 1 && K >= 4 && (K % 4) == 0 && (ldx % 4) == 0 && K <= 8192, "linear_small: bad shape N=%d K=%d ldx=%d", N, K, ldx);
+  VQ_CHECK_ARG(N >= 1 && K >= 4 && (K % 4) == 0 && (ldx % 4) == 0 && K <= 2048, "linear_small: bad shape N=%d K=%d ldx=%d (K <= 2048)", N, K, ldx);
   VQ_CHECK_ARG(row0 == nullptr || pos != nullptr, "linear_small: row0 needs the position pointer");
   VQ_CHECK_ARG((ln_gamma == nullptr) == (ln_beta == nullptr) && (ln_out == nullptr || ln_gamma != nullptr), "linear_small: LayerNorm arguments");
-  const int MT = M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : M <= 8 ? 8 : 16;
-  const size_t smem = (size_t)MT * K * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    VQ_CUDA_CALL(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VQ_CUDA_CALL(cudaFuncSetAttribute(linear_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VQ_CUDA_CALL(cudaFuncSetAttribute(linear_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VQ_CUDA_CALL(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VQ_CUDA_CALL(cudaFuncSetAttribute(linear_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
-  VQ_CHECK_ARG(smem <= 200 * 1024, "linear_small: M x K does not fit shared memory");
+  VQ_CHECK_ARG(ln_gamma == nullptr || K <= 1024, "linear_small: LayerNorm on load needs K <= 1024");
   const unsigned grid = (unsigned)vq_cdiv(N, 4);
   cudaStream_t st = vq_stream(stream);
-#define VQ_LS(MTV)                                                                                                                 \
-  linear_small_kernel<MTV><<<grid, 128, smem, st>>>(x, ldx, W, bias, residual, ldr, out, ldo, M, N, K, relu, scale, scale_cols, row0, \
-                                                    pos, ln_gamma, ln_beta, ln_eps, ln_out)
-  switch (MT) {
-    case 1: VQ_LS(1); break;
-    case 2: VQ_LS(2); break;
-    case 4: VQ_LS(4); break;
-    case 8: VQ_LS(8); break;
-    default: VQ_LS(16); break;
+  const bool ln = ln_gamma != nullptr;
+  if (M >= 3 && K <= 1024) {
+    const size_t smem = 16 + (size_t)M * K * sizeof(float);
+    static bool attr_done = false;
+#define VQ_ST_ATTR(KVV, MTV, LNV) \
+  VQ_CUDA_CALL(cudaFuncSetAttribute(linear_staged_kernel<KVV, MTV, LNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 + 16 * 1024 * 4))
+    if (!attr_done) {
+      VQ_ST_ATTR(8, 16, true);
+      VQ_ST_ATTR(8, 16, false);
+      attr_done = true;
+    }
+#undef VQ_ST_ATTR
+#define VQ_ST(KVV, MTV, LNV)                                                                                                            \
+  linear_staged_kernel<KVV, MTV, LNV><<<grid, 128, smem, st>>>(x, ldx, W, bias, residual, ldr, out, ldo, M, N, K, relu, scale, scale_cols, \
+                                                               row0, pos, ln_gamma, ln_beta, ln_eps, ln_out)
+#define VQ_ST_M(KVV, LNV)                    \
+  do {                                       \
+    if (M <= 4) VQ_ST(KVV, 4, LNV);          \
+    else if (M <= 8) VQ_ST(KVV, 8, LNV);     \
+    else VQ_ST(KVV, 16, LNV);                \
+  } while (0)
+#define VQ_ST_K(KVV)                         \
+  do {                                       \
+    if (ln) VQ_ST_M(KVV, true);              \
+    else VQ_ST_M(KVV, false);                \
+  } while (0)
+    if (K <= 128) VQ_ST_K(1);
+    else if (K <= 512) VQ_ST_K(4);
+    else VQ_ST_K(8);
+#undef VQ_ST_K
+#undef VQ_ST_M
+#undef VQ_ST
+    VQ_CUDA_LAUNCH_CHECK("linear_staged_kernel");
+    return VQ_OK;
   }
+  const int rb = M == 1 ? 1 : (M == 2 || K > 512) ? 2 : 4;          // rows in flight per warp (register budget: K / 128 float4 each)
+#define VQ_LS(KVV, RBV, LNV)                                                                                                          \
+  linear_small_kernel<KVV, RBV, LNV><<<grid, 128, 0, st>>>(x, ldx, W, bias, residual, ldr, out, ldo, M, N, K, relu, scale, scale_cols, \
+                                                           row0, pos, ln_gamma, ln_beta, ln_eps, ln_out)
+#define VQ_LS_R(KVV, LNV)                    \
+  do {                                       \
+    if (rb == 1) VQ_LS(KVV, 1, LNV);         \
+    else if (rb == 2) VQ_LS(KVV, 2, LNV);    \
+    else VQ_LS(KVV, 4, LNV);                 \
+  } while (0)
+#define VQ_LS_K(KVV)                         \
+  do {                                       \
+    if (ln) VQ_LS_R(KVV, true);              \
+    else VQ_LS_R(KVV, false);                \
+  } while (0)
+  if (K <= 128) VQ_LS_K(1);
+  else if (K <= 512) VQ_LS_K(4);
+  else if (K <= 1024) {
+    if (ln) { if (rb == 1) VQ_LS(8, 1, true); else VQ_LS(8, 2, true); }
+    else { if (rb == 1) VQ_LS(8, 1, false); else VQ_LS(8, 2, false); }
+  } else {
+    if (rb == 1) VQ_LS(16, 1, false);
+    else VQ_LS(16, 2, false);
+  }
+#undef VQ_LS_R
+#undef VQ_LS_K
 #undef VQ_LS
   VQ_CUDA_LAUNCH_CHECK("linear_small_kernel");
   return VQ_OK;
@@ -473,14 +736,14 @@ VQ_API int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const 
   VQ_CHECK_ARG((map1 == nullptr) == (e1 == nullptr) && (map2 == nullptr) == (e2 == nullptr), "attn_decode: a map needs its table");
   VQ_CHECK_ARG((k_new == nullptr) == (v_new == nullptr) && (ldc % 4) == 0 && (k_new == nullptr || (ldn % 4) == 0), "attn_decode: bad cache arguments");
   VQ_CHECK_ARG(pos != nullptr, "attn_decode: position pointer missing");
-  // split the keys over a cluster so that about 2 CTAs per SM are in flight, at least 64 keys per CTA
+  // split the keys over a cluster so that a CTA (one key per thread) scores its chunk in one round of memory latency
   int ns = g_attn_decode_split;
   if (ns == 0) {
     ns = 1;
-    while (ns < AD_MAX_SPLIT && (int64_t)H * P * ns < 2 * vq_sm_count() && Lk / (2 * ns) >= 32) ns *= 2;
+    while (ns < AD_MAX_SPLIT && Lk > ns * AD_THREADS) ns *= 2;
   }
   const int chunk_max = (int)((vq_cdiv(Lk, ns) + 7) & ~7);
-  const size_t smem = ((size_t)chunk_max + 3 * HD + 8 + 72) * sizeof(float);
+  const size_t smem = ((size_t)chunk_max + 9 * HD + 8 + 72 + AD_MAX_SPLIT * 72) * sizeof(float);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)H, (unsigned)P, (unsigned)ns);
   cfg.blockDim = dim3(AD_THREADS);
@@ -493,8 +756,12 @@ VQ_API int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const 
   attr[0].val.clusterDim.z = (unsigned)ns;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, attn_decode_kernel, q, ldq, k_new, v_new, ldn, kcache, vcache, ldc, Lmax, e1, e2, map1, map2,
-                                  mask, Lk, pos, causal, out, ldo, chunk_max));
+  if ((int64_t)H * P * ns <= 2 * vq_sm_count())
+    VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, attn_decode_kernel<true>, q, ldq, k_new, v_new, ldn, kcache, vcache, ldc, Lmax, e1, e2, map1,
+                                    map2, mask, Lk, pos, causal, out, ldo, chunk_max));
+  else
+    VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, attn_decode_kernel<false>, q, ldq, k_new, v_new, ldn, kcache, vcache, ldc, Lmax, e1, e2, map1,
+                                    map2, mask, Lk, pos, causal, out, ldo, chunk_max));
   return VQ_OK;
 }
 
