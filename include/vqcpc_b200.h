@@ -195,6 +195,9 @@ int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float temperat
                               const int* table_off, const float* chan, const float* evt, float* feat, int C, int total_upscaling,
                               int E, int pe, int* done, void* stream);
 int vqcpc_decode_advance(int* pos, int delta, void* stream);
+/* programmatic dependent launch between the kernels of the generation step (default on): each kernel requests its static
+ * parameters (weight rows, biases, LayerNorm parameters) while its predecessor is still running. */
+int vqcpc_decode_set_pdl(int on);
 
 /* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159
  *      distilled_categorical_crossentropy) --------------------------------------------------------------------------

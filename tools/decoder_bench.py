@@ -69,9 +69,12 @@ def main():
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--full-tokens', type=int, default=32)
     ap.add_argument('--cpu-forwards', type=int, default=2)
+    ap.add_argument('--pdl', type=int, default=-1, help='programmatic dependent launch between the step kernels: 0 / 1 (A/B), -1 = the product heuristic')
     a = ap.parse_args()
     from VQCPCB import ops, _native
     from oracle import decoder_oracle as D
+    if a.pdl >= 0:
+        os.environ['VQCPC_DECODE_PDL'] = str(a.pdl)
     dec, S = build(CFG)
     shapes = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
     prm = D.make_decoder_params(shapes, seed=0)
@@ -129,7 +132,7 @@ def main():
     cpu_fwd = min(cpu_s)
     out = dict(metric='decoder_generation_tokens_per_sec', value=B * T / ms_cached * 1e3, unit='tokens/s', batch=B, tokens_per_sequence=T,
                ms_per_window=ms_cached, us_per_token_step=ms_cached / T * 1e3, ms_per_window_no_graph=ms_eager,
-               kernel_launches_per_window=dec.last_generation_launches, host_calls_per_window=launches_host,
+               kernel_launches_per_window=dec.last_generation_launches, pdl=a.pdl, host_calls_per_window=launches_host,
                full_recompute=dict(ms_per_forward=ms_fwd, ms_per_token_measured=ms_full_token,
                                    tokens_per_sec=B / max(ms_full_token, 1e-9) * 1e3, tokens_timed=n_cmp),
                cpu_baseline=dict(kind='port', cores=torch.get_num_threads(), s_per_forward=cpu_fwd,

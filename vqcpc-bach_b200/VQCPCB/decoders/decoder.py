@@ -427,6 +427,10 @@ class _DecodeSession:
 
     def run(self, codes, u):
         dec, d = self.dec, self.dec.d_model
+        # programmatic dependent launch pays when the step is latency bound (measured on B200: batch 1 +6 %, batch 16 -25 %:
+        # the early-scheduled successors take SM slots from the attention waves); VQCPC_DECODE_PDL=0/1 overrides
+        pdl = os.environ.get('VQCPC_DECODE_PDL')
+        _native.call('vqcpc_decode_set_pdl', int(pdl) if pdl is not None else int(self.B <= 4))
         memory, S = dec._encode_memory(codes)
         assert S == self.S
         for ckv, l in zip(self.cross_kv, self.layers):      # keys / values of the memory (multihead_attention_custom.py:173-196)

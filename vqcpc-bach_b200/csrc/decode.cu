@@ -25,6 +25,13 @@ namespace {
 
 constexpr int HD = 64;
 
+// Programmatic dependent launch: every kernel of the step lets its successor be scheduled at once (launch_dependents at entry)
+// and only touches data a predecessor may have written after griddepcontrol.wait (= the predecessor grid has completed and its
+// writes are visible).  What a kernel requests BEFORE the wait must be static for the whole generation: weight rows, biases,
+// LayerNorm parameters - never the position, the activations or the caches.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // features of the row that enters the decoder at position i = *pos: the embedding of token i-1 with the channel / event
 // positional embeddings of position i-1 (decoder.py:442-457, then shifted right by one :476-482).  Row 0 is the start symbol
@@ -34,6 +41,8 @@ __global__ void decode_features_kernel(const int64_t* __restrict__ tokens, const
                                        const float* __restrict__ tables, const int* __restrict__ table_off,
                                        const float* __restrict__ chan, const float* __restrict__ evt, float* __restrict__ feat,
                                        int T, int C, int up, int E, int pe) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, i = *pos, F = E + 2 * pe;
   float* f = feat + (size_t)b * F;
   if (i <= 0 || i >= T + 1) {
@@ -69,6 +78,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
                     float scale, int scale_cols, const float* __restrict__ row0, const int* __restrict__ pos,
                     const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
                     float* __restrict__ ln_out) {
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 4 + warp;
   if (n >= N) return;
@@ -85,6 +95,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
     }
   }
   const float bn = bias ? __ldg(bias + n) : 0.f;
+  pdl_wait();                                      // above: static parameters only
   const bool use_row0 = row0 != nullptr && *pos == 0;
   const bool writer = LN && ln_out != nullptr && blockIdx.x == 0 && warp == 0;
   const float invK = 1.f / (float)K;
@@ -190,14 +201,10 @@ linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restri
   float* xs = reinterpret_cast<float*>(ls_smem + 16);
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ls_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(M * K * 4)) : "memory");
-    for (int b = 0; b < M; ++b)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"((uint32_t)__cvta_generic_to_shared(xs + (size_t)b * K)), "l"(x + (size_t)b * ldx), "r"((uint32_t)(K * 4)), "r"(bar)
-                   : "memory");
   }
   const int n = blockIdx.x * 4 + warp;
   const bool active = n < N;
@@ -219,6 +226,14 @@ linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restri
     }
   }
   const float bn = (active && bias) ? __ldg(bias + n) : 0.f;
+  pdl_wait();                                      // above: static parameters only; the rows are the predecessor's output
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(M * K * 4)) : "memory");
+    for (int b = 0; b < M; ++b)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(xs + (size_t)b * K)), "l"(x + (size_t)b * ldx), "r"((uint32_t)(K * 4)), "r"(bar)
+                   : "memory");
+  }
   const float resv = (active && residual && lane < M) ? residual[(size_t)lane * ldr + n] : 0.f;
   const bool use_row0 = row0 != nullptr && *pos == 0;
   __syncthreads();                                 // the barrier initialisation is visible to the waiting threads
@@ -315,7 +330,9 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   uint32_t crank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  pdl_launch_dependents();
   if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  pdl_wait();
   const int h = blockIdx.x, tid = threadIdx.x, i = *pos;
   const int64_t p = blockIdx.y;
   const int n = causal ? min(i + 1, Lk) : Lk;
@@ -583,6 +600,8 @@ sample_step_kernel(const float* __restrict__ logits, int ld, int V, float temper
                    const double* __restrict__ u, int u_stride, int64_t* __restrict__ tokens, int T, const int* __restrict__ pos,
                    int greedy, int B) {
   extern __shared__ __align__(16) float smf[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, i = *pos;
   if (i < 0 || i >= T) return;
   const int tok = sample_row(logits + (size_t)b * ld, V, temperature, top_k, top_p, greedy ? 0.0 : u[(size_t)i * u_stride + b], greedy, smf);
@@ -598,6 +617,8 @@ sample_embed_advance_kernel(const float* __restrict__ logits, int ld, int V, flo
                             const float* __restrict__ tables, const int* __restrict__ table_off, const float* __restrict__ chan,
                             const float* __restrict__ evt, float* __restrict__ feat, int C, int up, int E, int pe, int* done) {
   extern __shared__ __align__(16) float smf[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, i = *reinterpret_cast<volatile int*>(pos);
   if (i >= 0 && i < T) {
     const int tok = sample_row(logits + (size_t)b * ld, V, temperature, top_k, top_p, greedy ? 0.0 : u[(size_t)i * u_stride + b], greedy, smf);
@@ -617,16 +638,54 @@ sample_embed_advance_kernel(const float* __restrict__ logits, int ld, int V, flo
   }
 }
 
-__global__ void decode_advance_kernel(int* pos, int delta) { *pos += delta; }
+__global__ void decode_advance_kernel(int* pos, int delta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *pos += delta;
+}
+
+static int g_decode_pdl = 1;
+
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute (and an optional cluster along z)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_z, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster_z > 0) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = cluster_z;
+    ++na;
+  }
+  if (g_decode_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace
+
+VQ_API int vqcpc_decode_set_pdl(int on) {
+  g_decode_pdl = on != 0;
+  return VQ_OK;
+}
 
 VQ_API int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* tables, const int* table_off, const float* chan,
                                  const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe,
                                  void* stream) {
   VQ_CHECK_ARG(B >= 1 && T >= 1 && C >= 1 && total_upscaling % C == 0 && E >= 1 && pe >= 0, "decode_features: bad shape");
-  decode_features_kernel<<<B, 64, 0, vq_stream(stream)>>>(tokens, pos, tables, table_off, chan, evt, feat, T, C, total_upscaling, E, pe);
-  VQ_CUDA_LAUNCH_CHECK("decode_features_kernel");
+  VQ_CUDA_CALL(launch_step(decode_features_kernel, dim3(B), dim3(64), 0, vq_stream(stream), 0, tokens, pos, tables, table_off, chan, evt,
+                           feat, T, C, total_upscaling, E, pe));
   return VQ_OK;
 }
 
@@ -653,8 +712,8 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
     }
 #undef VQ_ST_ATTR
 #define VQ_ST(KVV, MTV, LNV)                                                                                                            \
-  linear_staged_kernel<KVV, MTV, LNV><<<grid, 128, smem, st>>>(x, ldx, W, bias, residual, ldr, out, ldo, M, N, K, relu, scale, scale_cols, \
-                                                               row0, pos, ln_gamma, ln_beta, ln_eps, ln_out)
+  VQ_CUDA_CALL(launch_step(linear_staged_kernel<KVV, MTV, LNV>, dim3(grid), dim3(128), smem, st, 0, x, ldx, W, bias, residual, ldr, out, ldo, \
+                           M, N, K, relu, scale, scale_cols, row0, pos, ln_gamma, ln_beta, ln_eps, ln_out))
 #define VQ_ST_M(KVV, LNV)                    \
   do {                                       \
     if (M <= 4) VQ_ST(KVV, 4, LNV);          \
@@ -672,13 +731,12 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
 #undef VQ_ST_K
 #undef VQ_ST_M
 #undef VQ_ST
-    VQ_CUDA_LAUNCH_CHECK("linear_staged_kernel");
     return VQ_OK;
   }
   const int rb = M == 1 ? 1 : (M == 2 || K > 512) ? 2 : 4;          // rows in flight per warp (register budget: K / 128 float4 each)
 #define VQ_LS(KVV, RBV, LNV)                                                                                                          \
-  linear_small_kernel<KVV, RBV, LNV><<<grid, 128, 0, st>>>(x, ldx, W, bias, residual, ldr, out, ldo, M, N, K, relu, scale, scale_cols, \
-                                                           row0, pos, ln_gamma, ln_beta, ln_eps, ln_out)
+  VQ_CUDA_CALL(launch_step(linear_small_kernel<KVV, RBV, LNV>, dim3(grid), dim3(128), 0, st, 0, x, ldx, W, bias, residual, ldr, out, ldo, M, \
+                           N, K, relu, scale, scale_cols, row0, pos, ln_gamma, ln_beta, ln_eps, ln_out))
 #define VQ_LS_R(KVV, LNV)                    \
   do {                                       \
     if (rb == 1) VQ_LS(KVV, 1, LNV);         \
@@ -702,7 +760,6 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
 #undef VQ_LS_R
 #undef VQ_LS_K
 #undef VQ_LS
-  VQ_CUDA_LAUNCH_CHECK("linear_small_kernel");
   return VQ_OK;
 }
 
@@ -744,24 +801,13 @@ VQ_API int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const 
   }
   const int chunk_max = (int)((vq_cdiv(Lk, ns) + 7) & ~7);
   const size_t smem = ((size_t)chunk_max + 9 * HD + 8 + 72 + AD_MAX_SPLIT * 72) * sizeof(float);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)H, (unsigned)P, (unsigned)ns);
-  cfg.blockDim = dim3(AD_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = vq_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = (unsigned)ns;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  const dim3 grid((unsigned)H, (unsigned)P, (unsigned)ns);
   if ((int64_t)H * P * ns <= 2 * vq_sm_count())
-    VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, attn_decode_kernel<true>, q, ldq, k_new, v_new, ldn, kcache, vcache, ldc, Lmax, e1, e2, map1,
-                                    map2, mask, Lk, pos, causal, out, ldo, chunk_max));
+    VQ_CUDA_CALL(launch_step(attn_decode_kernel<true>, grid, dim3(AD_THREADS), smem, vq_stream(stream), (unsigned)ns, q, ldq, k_new, v_new,
+                             ldn, kcache, vcache, ldc, Lmax, e1, e2, map1, map2, mask, Lk, pos, causal, out, ldo, chunk_max));
   else
-    VQ_CUDA_CALL(cudaLaunchKernelEx(&cfg, attn_decode_kernel<false>, q, ldq, k_new, v_new, ldn, kcache, vcache, ldc, Lmax, e1, e2, map1,
-                                    map2, mask, Lk, pos, causal, out, ldo, chunk_max));
+    VQ_CUDA_CALL(launch_step(attn_decode_kernel<false>, grid, dim3(AD_THREADS), smem, vq_stream(stream), (unsigned)ns, q, ldq, k_new, v_new,
+                             ldn, kcache, vcache, ldc, Lmax, e1, e2, map1, map2, mask, Lk, pos, causal, out, ldo, chunk_max));
   return VQ_OK;
 }
 
@@ -776,9 +822,8 @@ VQ_API int vqcpc_sample_step(const float* logits, int ld, int V, float temperatu
     VQ_CUDA_CALL(cudaFuncSetAttribute(sample_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_done = true;
   }
-  sample_step_kernel<<<B, 256, smem, vq_stream(stream)>>>(logits, ld, V, temperature, top_k, top_p, u, u_stride, tokens, T, pos,
-                                                          greedy, B);
-  VQ_CUDA_LAUNCH_CHECK("sample_step_kernel");
+  VQ_CUDA_CALL(launch_step(sample_step_kernel, dim3(B), dim3(256), smem, vq_stream(stream), 0, logits, ld, V, temperature, top_k, top_p, u,
+                           u_stride, tokens, T, pos, greedy, B));
   return VQ_OK;
 }
 
@@ -796,16 +841,14 @@ VQ_API int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float t
     VQ_CUDA_CALL(cudaFuncSetAttribute(sample_embed_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_done = true;
   }
-  sample_embed_advance_kernel<<<B, 256, smem, vq_stream(stream)>>>(logits, ld, V, temperature, top_k, top_p, u, u_stride, tokens, T, pos,
-                                                                   greedy, tables, table_off, chan, evt, feat, C, total_upscaling, E,
-                                                                   pe, done);
-  VQ_CUDA_LAUNCH_CHECK("sample_embed_advance_kernel");
+  VQ_CUDA_CALL(launch_step(sample_embed_advance_kernel, dim3(B), dim3(256), smem, vq_stream(stream), 0, logits, ld, V, temperature, top_k,
+                           top_p, u, u_stride, tokens, T, pos, greedy, tables, table_off, chan, evt, feat, C, total_upscaling, E, pe,
+                           done));
   return VQ_OK;
 }
 
 VQ_API int vqcpc_decode_advance(int* pos, int delta, void* stream) {
   VQ_CHECK_ARG(pos != nullptr, "decode_advance: position pointer missing");
-  decode_advance_kernel<<<1, 1, 0, vq_stream(stream)>>>(pos, delta);
-  VQ_CUDA_LAUNCH_CHECK("decode_advance_kernel");
+  VQ_CUDA_CALL(launch_step(decode_advance_kernel, dim3(1), dim3(1), 0, vq_stream(stream), 0, pos, delta));
   return VQ_OK;
 }
