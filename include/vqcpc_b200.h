@@ -199,6 +199,17 @@ int vqcpc_decode_advance(int* pos, int delta, void* stream);
  * parameters (weight rows, biases, LayerNorm parameters) while its predecessor is still running. */
 int vqcpc_decode_set_pdl(int on);
 
+/* ---- CPC batch assembly from a chorale tensor dataset resident in HBM (datasets/chorale_dataset.py:542-595 data_loaders over
+ *      the cached tensor_dataset; dataloaders/bach_cpc_dataloader.py:110-252) -------------------------------------------------
+ * data (n_rows, V, ticks) int32 (elem_bytes 4: the reference's cache) or int64 (8); rows: sampled row ids (int64, device).
+ * out (n, n_ev, V) int64 = data[rows[r], :, t0 : t0 + n_ev] with the voice dimension last (:227-233, :242-245). */
+int vqcpc_cpc_window_gather(const void* data, int elem_bytes, int64_t n_rows, int V, int ticks, const int64_t* rows, int64_t n, int t0,
+                            int n_ev, int64_t* out, void* stream);
+/* _build_negatives_sameSeq (:162-184): out (B, KA + KB - 1, nk, evb, V): for every k < nk all KA blocks of part A (ticks from a0),
+ * then the KB blocks of part B (ticks from b0) except block k (the reference loops k over num_blocks_right for both directions). */
+int vqcpc_cpc_same_seq_negatives(const void* data, int elem_bytes, int64_t n_rows, int V, int ticks, const int64_t* rows, int64_t B,
+                                 int a0, int KA, int b0, int KB, int nk, int evb, int64_t* out, void* stream);
+
 /* ---- softmax cross-entropy rows (utils.py:24-49 categorical_crossentropy via nn.CrossEntropyLoss; utils.py:131-159
  *      distilled_categorical_crossentropy) --------------------------------------------------------------------------
  * logits (rows, C; ld).  Exactly one of target_idx (int64 class per row) / target_logits (rows, C; ldt: the teacher's

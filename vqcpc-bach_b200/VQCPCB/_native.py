@@ -54,6 +54,8 @@ SIGNATURES = {
     'vqcpc_decode_sample_embed': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'vqcpc_sample_step': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P],
     'vqcpc_decode_advance': [_P, _I, _P],
+    'vqcpc_cpc_window_gather': [_P, _I, _L, _I, _I, _P, _L, _I, _I, _P, _P],
+    'vqcpc_cpc_same_seq_negatives': [_P, _I, _L, _I, _I, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P],
     'vqcpc_softmax_ce': [_P, _I, _P, _P, _I, _P, _P, _I, _F, _L, _I, _P],
     'vqcpc_attn_set_fwd_algo': [_I],
     'vqcpc_attn_set_bwd_algo': [_I],

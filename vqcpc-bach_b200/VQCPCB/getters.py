@@ -39,9 +39,12 @@ def get_dataloader_generator(dataset, training_method, dataloader_generator_kwar
             num_negative_samples=kw['num_negative_samples'], sequences_size=kw.get('sequences_size', 1),
             vocab_size=kw.get('vocab_size', 64), seed=kw.get('seed', 1234))
     if dataset.lower() == 'bach':
-        raise NotImplementedError('dataset="bach" needs music21 and the chorale corpus, which are not available here; '
-                                  'use dataset="synthetic" (same batch contract) or plug a generator exposing '
-                                  'dataloaders()/num_blocks_right/dataset_positive')
+        # the reference's cached tensor_dataset files (written by its music21 ETL) under database_root / VQCPC_DATA_ROOT
+        from .dataloaders.bach_cpc_dataloader import BachCPCDataloaderGenerator
+        return BachCPCDataloaderGenerator(
+            num_tokens_per_block=kw['num_tokens_per_block'], num_blocks_left=kw['num_blocks_left'],
+            num_blocks_right=kw['num_blocks_right'], negative_sampling_method=kw['negative_sampling_method'],
+            num_negative_samples=kw['num_negative_samples'], database_root=kw.get('database_root'))
     raise NotImplementedError('If you want to use your own datasets, you need to implement a datasets, '
                               'data_processor and dataloader')
 
