@@ -194,6 +194,12 @@ int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float temperat
                               int u_stride, int64_t* tokens, int T, int* pos, int greedy, int B, const float* tables,
                               const int* table_off, const float* chan, const float* evt, float* feat, int C, int total_upscaling,
                               int E, int pe, int* done, void* stream);
+/* aligned ('diagonal') decoder layer, transformer_custom.py:389-479: its cross term is an MLP of the aligned memory event
+ * (Linear, ELU, Linear - :428-432), i.e. a per-position constant add (B, T, d) during generation:
+ * out (B, d) = LayerNorm(y) + add[:, *pos, :] (:447-449 norm1, :472 residual). */
+int vqcpc_decode_ln_add(const float* y, const float* gamma, const float* beta, float eps, const float* add, int T, const int* pos,
+                        float* out, int B, int d, void* stream);
+int vqcpc_elu_fwd(const float* x, float* out, int64_t n, void* stream);
 int vqcpc_decode_advance(int* pos, int delta, void* stream);
 /* programmatic dependent launch between the kernels of the generation step (default on): each kernel requests its static
  * parameters (weight rows, biases, LayerNorm parameters) while its predecessor is still running. */

@@ -94,6 +94,19 @@ def _ffn(x, prm, pre):
                     prm[pre + 'linear2.bias'])
 
 
+def aligned_cross(memory, prm, pre, T, Cd, Ce):
+    """transformer_custom.py:456-471 (TransformerAlignedDecoderLayerCustom): an MLP of the memory event a target position is
+    aligned with replaces the cross-attention.  memory (B, S, d) -> (B, T, d)."""
+    B, S, d = memory.shape
+    Em = S // Ce
+    m = memory.reshape(B, Em, Ce * d)
+    h = F.elu(F.linear(m, prm[pre + 'cross_attn.0.weight'], prm[pre + 'cross_attn.0.bias']))
+    o = F.linear(h, prm[pre + 'cross_attn.2.weight'], prm[pre + 'cross_attn.2.bias'])      # (B, Em, d * Cd)
+    o = o.reshape(B, Em, d, Cd).permute(0, 1, 3, 2)                                        # (B, Em, Cd, d)
+    rep = (T // Cd) // Em
+    return o.repeat_interleave(rep, dim=1).reshape(B, T, d)
+
+
 def causal_mask(n, dtype=torch.float32):
     i = torch.arange(n)
     return torch.where(i.view(1, n) <= i.view(n, 1), 0.0, float('-inf')).to(dtype)
@@ -126,7 +139,10 @@ def decoder_forward(source, target, prm, cfg):
     for l in range(cfg['num_decoder_layers']):
         p = f'transformer.decoder.layers.{l}.'
         y = _ln(y + mha(y, None, prm, p + 'self_attn.', H, causal_mask(T, dt)), prm, p + 'norm1.')
-        y = _ln(y + mha(y, x, prm, p + 'multihead_attn.', H, memory_mask), prm, p + 'norm2.')
+        if cfg['cross_attention_type'] == 'diagonal':
+            y = _ln(y + aligned_cross(x, prm, p, T, C, cfg.get('num_channels_encoder', 1)), prm, p + 'norm2.')
+        else:
+            y = _ln(y + mha(y, x, prm, p + 'multihead_attn.', H, memory_mask), prm, p + 'norm2.')
         y = _ln(y + _ffn(y, prm, p), prm, p + 'norm3.')
     y = y.reshape(B, Ev, C, -1)
     logits = [F.linear(y[:, :, c], prm[f'pre_softmaxes.{c}.weight'], prm[f'pre_softmaxes.{c}.bias']) for c in range(C)]

@@ -27,6 +27,10 @@ CASES = {
     'c_full': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=2, num_decoder_layers=1, num_events=32,
                             vocab=[9, 30, 17, 12], codebook_size=32, encoder_attention_type='causal', cross_attention_type='full'),
                    B=2),
+    # the 'diagonal' aligned decoder layer (decoder_relative_AC_D_C_*: 6 of the 10 shipped relative configurations)
+    'ac_diag': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=2, num_decoder_layers=2, num_events=16,
+                             vocab=[20, 21, 22, 23], codebook_size=16, encoder_attention_type='anticausal',
+                             cross_attention_type='diagonal'), B=3),
 }
 
 

@@ -69,12 +69,14 @@ def main():
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--full-tokens', type=int, default=32)
     ap.add_argument('--cpu-forwards', type=int, default=2)
+    ap.add_argument('--cross', default='anticausal', choices=['anticausal', 'full', 'diagonal'])
     ap.add_argument('--pdl', type=int, default=-1, help='programmatic dependent launch between the step kernels: 0 / 1 (A/B), -1 = the product heuristic')
     a = ap.parse_args()
     from VQCPCB import ops, _native
     from oracle import decoder_oracle as D
     if a.pdl >= 0:
         os.environ['VQCPC_DECODE_PDL'] = str(a.pdl)
+    CFG['cross_attention_type'] = a.cross
     dec, S = build(CFG)
     shapes = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
     prm = D.make_decoder_params(shapes, seed=0)
@@ -139,7 +141,7 @@ def main():
                                  value=1.0 / cpu_fwd, unit='tokens/s',
                                  sample=f'{len(cpu_s)} full forwards at batch 1 (the reference runs one per generated token)'),
                parity=dict(greedy_tokens_equal=same, greedy_tokens_compared=n_cmp * B, logits_rel_err_vs_oracle=errs),
-               config=dict(workload='decoder_relative AC/AC/C generation, 1024 tokens (256 events x 4 voices) from 64 codes, d=512, '
+               config=dict(cross_attention_type=a.cross, workload='decoder_relative generation, 1024 tokens (256 events x 4 voices) from 64 codes, d=512, '
                                     '8 heads, 3+3 layers, FFN 1024, top-p 0.9', data='synthetic codes, random-init weights'))
     print(json.dumps(out))
 

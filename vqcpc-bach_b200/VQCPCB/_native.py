@@ -50,6 +50,8 @@ SIGNATURES = {
     'vqcpc_attn_decode': [_P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P],
     'vqcpc_attn_decode_set_split': [_I],
     'vqcpc_decode_set_pdl': [_I],
+    'vqcpc_decode_ln_add': [_P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P],
+    'vqcpc_elu_fwd': [_P, _P, _L, _P],
     'vqcpc_ln_linear_small': [_P, _I, _P, _P, _F, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     'vqcpc_decode_sample_embed': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'vqcpc_sample_step': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P],

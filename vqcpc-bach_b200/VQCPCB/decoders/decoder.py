@@ -3,7 +3,8 @@
 SURVEY.md §8f row 3, BASELINE config 5).
 
 Built: ``transformer_type='relative'`` with ``encoder_attention_type`` in {anticausal, causal, full} and ``cross_attention_type``
-in {anticausal, full} (every shipped ``decoder_relative_*`` configuration except the 'diagonal' aligned layer), forward = teacher
+in {anticausal, full, diagonal} (every shipped ``decoder_relative_*`` configuration; 'diagonal' = the aligned layer whose
+cross term is an MLP of the aligned memory event, transformer_custom.py:389-479), forward = teacher
 forced logits + cross-entropy, and autoregressive generation that recomputes the forward for every token exactly like the
 reference does (kept as the parity check), and - the default - INCREMENTALLY over cached keys / values (csrc/decode.cu; see
 ``transformer/relative_maps.py``), with top-k / top-p filtering and sampling on the device.  Training of the decoder is out of
@@ -44,10 +45,16 @@ class _Attn(nn.Module):
         self.attn_bias = ab
 
 
-def _layer(d_model, nhead, dim_feedforward, seq_len_self, seq_len_src_cross=None):
+def _layer(d_model, nhead, dim_feedforward, seq_len_self, seq_len_src_cross=None, aligned=None):
+    """aligned = (num_channels_encoder, num_channels_decoder): the 'diagonal' layer (transformer_custom.py:389-479) whose cross
+    term is ``cross_attn = Sequential(Linear(Ce * d, 2 d), ELU, Linear(2 d, d * Cd))`` of the aligned memory event (:428-432)."""
     m = nn.Module()
     m.self_attn = _Attn(d_model, nhead, seq_len_self)
-    if seq_len_src_cross is not None:
+    if aligned is not None:
+        ce, cd = aligned
+        m.cross_attn = nn.Sequential(_Linear(ce * d_model, 2 * d_model), nn.ELU(), _Linear(2 * d_model, d_model * cd))
+        m.norm3 = nn.LayerNorm(d_model)
+    elif seq_len_src_cross is not None:
         m.multihead_attn = _Attn(d_model, nhead, seq_len_src_cross)
         m.norm3 = nn.LayerNorm(d_model)
     m.linear1 = _Linear(d_model, dim_feedforward)
@@ -98,9 +105,9 @@ class Decoder(nn.Module):
         if transformer_type != 'relative':
             raise NotImplementedError("only transformer_type='relative' is built on the B200 path")
         assert encoder_attention_type in ('anticausal', 'causal', 'full')
-        if cross_attention_type not in ('anticausal', 'full'):
-            raise NotImplementedError(f'cross_attention_type={cross_attention_type!r} (causal is unimplemented in the reference as '
-                                      'well, decoder.py:489-493; the diagonal aligned layer is not built)')
+        if cross_attention_type not in ('anticausal', 'full', 'diagonal'):
+            raise NotImplementedError(f'cross_attention_type={cross_attention_type!r} (unimplemented in the reference as well, '
+                                      'decoder.py:489-493)')
         self.transformer_type = transformer_type
         self.encoder_attention_type = encoder_attention_type
         self.cross_attention_type = cross_attention_type
@@ -128,7 +135,10 @@ class Decoder(nn.Module):
         tr.encoder = nn.Module()
         tr.encoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, S) for _ in range(num_encoder_layers)])
         tr.decoder = nn.Module()
-        tr.decoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, T, S) for _ in range(num_decoder_layers)])
+        self.num_channels_encoder, self.num_channels_decoder = num_channels_encoder, num_channels_decoder
+        aligned = (num_channels_encoder, num_channels_decoder) if cross_attention_type == 'diagonal' else None
+        tr.decoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, T, S, aligned=aligned)
+                                           for _ in range(num_decoder_layers)])
         self.transformer = tr
         self.linear_target = _Linear(data_processor.embedding_size + positional_embedding_size * 2, d_model)
         self.sos = nn.Parameter(torch.randn((1, 1, d_model)))
@@ -185,13 +195,29 @@ class Decoder(nn.Module):
         y = ops.linear_fwd(hmid, lyr.linear2.weight, lyr.linear2.bias, residual=x)
         return ops.layernorm_fwd(y, lyr.norm2.weight, lyr.norm2.bias)[0]
 
+    def _aligned_cross(self, lyr, memory, B, T, S):
+        """transformer_custom.py:451-471: (B*S, d) memory -> (B, T, d) cross term of the aligned layer: the MLP output of memory
+        event em, viewed (d, Cd), feeds channel c of every target event aligned with em."""
+        d, ce, cd = self.d_model, self.num_channels_encoder, self.num_channels_decoder
+        em = S // ce
+        l0, l2 = lyr.cross_attn[0], lyr.cross_attn[2]
+        h = ops.linear_fwd(memory.reshape(B * em, ce * d), l0.weight, l0.bias)
+        _native.call('vqcpc_elu_fwd', _p(h), _p(h), h.numel(), ops._stream())
+        o = ops.linear_fwd(h, l2.weight, l2.bias).view(B, em, d, cd).permute(0, 1, 3, 2)          # (B, em, Cd, d)
+        rep = (T // cd) // em
+        return o.unsqueeze(2).expand(B, em, rep, cd, d).reshape(B * T, d).contiguous()
+
     def _dec_layer(self, lyr, x, memory, B, T, S, tgt_mask, memory_mask):
-        """transformer_custom.py:355-384: self-attention, encoder-decoder attention, feed-forward, three post-LNs."""
+        """transformer_custom.py:355-384: self-attention, encoder-decoder attention (or the aligned MLP term, :389-479),
+        feed-forward, three post-LNs."""
         o = self._attention(lyr.self_attn, x, None, B, T, T, tgt_mask)
         y = ops.linear_fwd(o, lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias, residual=x)
         x = ops.layernorm_fwd(y, lyr.norm1.weight, lyr.norm1.bias)[0]
-        o = self._attention(lyr.multihead_attn, x, memory, B, T, S, memory_mask)
-        y = ops.linear_fwd(o, lyr.multihead_attn.out_proj.weight, lyr.multihead_attn.out_proj.bias, residual=x)
+        if self.cross_attention_type == 'diagonal':
+            y = x + self._aligned_cross(lyr, memory, B, T, S)
+        else:
+            o = self._attention(lyr.multihead_attn, x, memory, B, T, S, memory_mask)
+            y = ops.linear_fwd(o, lyr.multihead_attn.out_proj.weight, lyr.multihead_attn.out_proj.bias, residual=x)
         x = ops.layernorm_fwd(y, lyr.norm2.weight, lyr.norm2.bias)[0]
         hmid = ops.linear_fwd(x, lyr.linear1.weight, lyr.linear1.bias, relu=True)
         y = ops.linear_fwd(hmid, lyr.linear2.weight, lyr.linear2.bias, residual=x)
@@ -349,11 +375,13 @@ class _DecodeSession:
         layers = list(dec.transformer.decoder.layers)
         self.layers = layers
         f32 = dict(dtype=torch.float32, device=dev)
-        self.cross_kv = [torch.empty(B * S, 2 * d, **f32) for _ in layers]
+        self.aligned = dec.cross_attention_type == 'diagonal'
+        self.cross_kv = [] if self.aligned else [torch.empty(B * S, 2 * d, **f32) for _ in layers]
+        self.cross_add = [torch.empty(B * T, d, **f32) for _ in layers] if self.aligned else []
         kc = [torch.zeros(B * T, d, **f32) for _ in layers]
         vc = [torch.zeros(B * T, d, **f32) for _ in layers]
         sm1, sm2 = device_maps(T, T, dev)
-        cm1, cm2 = device_maps(T, S, dev)
+        cm1, cm2 = (None, None) if self.aligned else device_maps(T, S, dev)
         memory_mask = _anticausal_mask(S, dev, T) if dec.cross_attention_type == 'anticausal' else None
         tables = torch.cat([e.weight.detach() for e in dec.data_processor.embeddings], dim=0).contiguous()
         rows = [e.weight.shape[0] for e in dec.data_processor.embeddings]
@@ -403,13 +431,19 @@ class _DecodeSession:
                 call('vqcpc_attn_decode', _p(qkv), 3 * d, _p(qkv[:, d:]), _p(qkv[:, 2 * d:]), 3 * d, _p(kc[li]), _p(vc[li]), d, T,
                      _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
                 lin(att, d, a.out_proj.weight, a.out_proj.bias, x, y, d, d, d)
-                a = l.multihead_attn
-                ln_lin(y, l.norm1, x1, a.in_proj_weight[:d], a.in_proj_bias[:d], qc, d, d, sc=scale, sc_cols=d)
-                ckv = self.cross_kv[li]
-                call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(ckv), _p(ckv[:, d:]), 2 * d, S, _p(a.attn_bias.e1),
-                     _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd, st)
-                lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
-                ln_lin(y, l.norm2, x2, l.linear1.weight, l.linear1.bias, hmid, ff, ff, relu=1)
+                if self.aligned:                             # y2 = norm1(y) + the aligned memory term of this position
+                    call('vqcpc_decode_ln_add', _p(y), _p(l.norm1.weight), _p(l.norm1.bias), float(l.norm1.eps),
+                         _p(self.cross_add[li]), T, _p(pos), _p(x1), B, d, st)
+                    y_mid = x1
+                else:
+                    a = l.multihead_attn
+                    ln_lin(y, l.norm1, x1, a.in_proj_weight[:d], a.in_proj_bias[:d], qc, d, d, sc=scale, sc_cols=d)
+                    ckv = self.cross_kv[li]
+                    call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(ckv), _p(ckv[:, d:]), 2 * d, S, _p(a.attn_bias.e1),
+                         _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd, st)
+                    lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
+                    y_mid = y
+                ln_lin(y_mid, l.norm2, x2, l.linear1.weight, l.linear1.bias, hmid, ff, ff, relu=1)
                 lin(hmid, ff, l.linear2.weight, l.linear2.bias, x2, y, d, d, ff)
             V = dec.num_tokens_per_channel[c]
             ln_lin(y, layers[-1].norm3, None, dec.pre_softmaxes[c].weight, head_bias[c], logits, Vmax, V)
@@ -423,7 +457,7 @@ class _DecodeSession:
 
         self.event = event
         self.graph = None
-        self.launches_per_window = T * (3 + 8 * len(layers))
+        self.launches_per_window = T * (3 + (6 if self.aligned else 8) * len(layers))
 
     def run(self, codes, u):
         dec, d = self.dec, self.dec.d_model
@@ -436,6 +470,8 @@ class _DecodeSession:
         for ckv, l in zip(self.cross_kv, self.layers):      # keys / values of the memory (multihead_attention_custom.py:173-196)
             a = l.multihead_attn
             ops.linear_fwd(memory, a.in_proj_weight[d:], a.in_proj_bias[d:], out=ckv)
+        for add, l in zip(self.cross_add, self.layers):     # aligned layers: the memory term of every target position
+            add.copy_(dec._aligned_cross(l, memory, self.B, self.T, S))
         self.u.copy_(u)
         self.tokens.zero_()
         self.pos.zero_()

@@ -31,6 +31,12 @@ constexpr int HD = 64;
 // LayerNorm parameters - never the position, the activations or the caches.  Without the launch attribute both are no-ops.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Under programmatic launch a kernel is resident while its predecessors still write: anything they write (activations, caches,
+// the position) is NOT read-only for the lifetime of this kernel, so it must never be fetched through the non-coherent path
+// (which `const __restrict__` lets the compiler pick) nor be served from a stale L1 line -> L2-coherent loads (ld.global.cg).
+__device__ __forceinline__ float4 ld_dyn4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_dyn(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_pos(const int* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // features of the row that enters the decoder at position i = *pos: the embedding of token i-1 with the channel / event
@@ -43,14 +49,14 @@ __global__ void decode_features_kernel(const int64_t* __restrict__ tokens, const
                                        int T, int C, int up, int E, int pe) {
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x, i = *pos, F = E + 2 * pe;
+  const int b = blockIdx.x, i = ld_pos(pos), F = E + 2 * pe;
   float* f = feat + (size_t)b * F;
   if (i <= 0 || i >= T + 1) {
     for (int c = threadIdx.x; c < F; c += blockDim.x) f[c] = 0.f;
     return;
   }
   const int t = i - 1, ch = t % C, ev = (t % up) / C;
-  const int64_t tok = tokens[(size_t)b * T + t];
+  const int64_t tok = __ldcg(tokens + (size_t)b * T + t);
   const float* row = tables + ((size_t)table_off[ch] + tok) * E;
   for (int c = threadIdx.x; c < F; c += blockDim.x)
     f[c] = c < E ? row[c] : (c < E + pe ? chan[ch * pe + (c - E)] : evt[ev * pe + (c - E - pe)]);
@@ -96,7 +102,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
   }
   const float bn = bias ? __ldg(bias + n) : 0.f;
   pdl_wait();                                      // above: static parameters only
-  const bool use_row0 = row0 != nullptr && *pos == 0;
+  const bool use_row0 = row0 != nullptr && ld_pos(pos) == 0;
   const bool writer = LN && ln_out != nullptr && blockIdx.x == 0 && warp == 0;
   const float invK = 1.f / (float)K;
   for (int b0 = 0; b0 < M; b0 += RB) {
@@ -106,7 +112,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
 #pragma unroll
       for (int i = 0; i < KV; ++i) {
         const int c = i * 32 + lane;
-        xr[r][i] = (b0 + r < M && c < K4) ? *(reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * ldx) + c) : zero4;
+        xr[r][i] = (b0 + r < M && c < K4) ? ld_dyn4(x + (size_t)(b0 + r) * ldx + 4 * c) : zero4;
       }
     float acc[RB];
     if (LN) {
@@ -164,7 +170,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
         float v = acc[r] + bn;
         if (n < scale_cols) v *= scale;
         if (relu) v = fmaxf(v, 0.f);
-        if (residual) v += residual[(size_t)b * ldr + n];
+        if (residual) v += ld_dyn(residual + (size_t)b * ldr + n);
         if (use_row0) v = row0[n];
         out[(size_t)b * ldo + n] = v;
       }
@@ -234,8 +240,8 @@ linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restri
                    ::"r"((uint32_t)__cvta_generic_to_shared(xs + (size_t)b * K)), "l"(x + (size_t)b * ldx), "r"((uint32_t)(K * 4)), "r"(bar)
                    : "memory");
   }
-  const float resv = (active && residual && lane < M) ? residual[(size_t)lane * ldr + n] : 0.f;
-  const bool use_row0 = row0 != nullptr && *pos == 0;
+  const float resv = (active && residual && lane < M) ? ld_dyn(residual + (size_t)lane * ldr + n) : 0.f;
+  const bool use_row0 = row0 != nullptr && ld_pos(pos) == 0;
   __syncthreads();                                 // the barrier initialisation is visible to the waiting threads
   ls_mbar_wait(bar, 0);
   if (LN) {
@@ -333,7 +339,7 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   pdl_launch_dependents();
   if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   pdl_wait();
-  const int h = blockIdx.x, tid = threadIdx.x, i = *pos;
+  const int h = blockIdx.x, tid = threadIdx.x, i = ld_pos(pos);
   const int64_t p = blockIdx.y;
   const int n = causal ? min(i + 1, Lk) : Lk;
   int chunk = (((n + (int)csize - 1) / (int)csize) + 7) & ~7;
@@ -361,7 +367,7 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     add = mrow ? mrow[j] : 0.f;
     const float4* kr = reinterpret_cast<const float4*>((kn && j == i) ? kn : kc + (size_t)j * ldc);
 #pragma unroll
-    for (int c = 0; c < HD / 4; ++c) kreg[c] = kr[c];
+    for (int c = 0; c < HD / 4; ++c) kreg[c] = __ldcg(kr + c);
   }
   const int sub = tid & 15, grp = tid >> 4;
   float4 vv[8];
@@ -369,13 +375,13 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   for (int t = 0; t < 8; ++t) {
     const int jj = t * 8 + grp, ja = j_lo + jj;
     const float* vrow = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
-    if (PREFETCH_V) vv[t] = jj < cnt ? *reinterpret_cast<const float4*>(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PREFETCH_V) vv[t] = jj < cnt ? ld_dyn4(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid < HD) {
-    qs[tid] = q[(size_t)p * ldq + h * HD + tid];
+    qs[tid] = ld_dyn(q + (size_t)p * ldq + h * HD + tid);
     if (kn && crank == 0) {                        // the appended row is read from k_new / v_new, never from the cache
-      kc[(size_t)i * ldc + tid] = kn[tid];
-      vc[(size_t)i * ldc + tid] = vn[tid];
+      kc[(size_t)i * ldc + tid] = ld_dyn(kn + tid);
+      vc[(size_t)i * ldc + tid] = ld_dyn(vn + tid);
     }
   }
   __syncthreads();
@@ -404,7 +410,7 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
       add = mrow ? mrow[j] : 0.f;
       const float4* kr = reinterpret_cast<const float4*>((kn && j == i) ? kn : kc + (size_t)j * ldc);
 #pragma unroll
-      for (int c = 0; c < HD / 4; ++c) kreg[c] = kr[c];
+      for (int c = 0; c < HD / 4; ++c) kreg[c] = __ldcg(kr + c);
     }
   }
   __syncthreads();
@@ -436,7 +442,7 @@ attn_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict
       const bool ok = jj < cnt;
       if (!PREFETCH_V || j0 > 0) {
         const float* vrow = (vn && ja == i) ? vn : vc + (size_t)ja * ldc;
-        vv[t] = ok ? *reinterpret_cast<const float4*>(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vv[t] = ok ? ld_dyn4(vrow + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       pw[t] = ok ? sc[jj] : 0.f;
     }
@@ -505,7 +511,7 @@ __device__ int sample_row(const float* __restrict__ lg, int V, float temperature
   double* cdf = reinterpret_cast<double*>(smf + 3 * V + (V & 1));
   __shared__ int s_result;
   const int tid = threadIdx.x;
-  for (int c = tid; c < V; c += 256) x[c] = lg[c] / temperature;
+  for (int c = tid; c < V; c += 256) x[c] = ld_dyn(lg + c) / temperature;
   __syncthreads();
   // rank = position in the descending order (ties: lower index first)
   for (int c = tid; c < V; c += 256) {
@@ -602,7 +608,7 @@ sample_step_kernel(const float* __restrict__ logits, int ld, int V, float temper
   extern __shared__ __align__(16) float smf[];
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x, i = *pos;
+  const int b = blockIdx.x, i = ld_pos(pos);
   if (i < 0 || i >= T) return;
   const int tok = sample_row(logits + (size_t)b * ld, V, temperature, top_k, top_p, greedy ? 0.0 : u[(size_t)i * u_stride + b], greedy, smf);
   if (threadIdx.x == 0) tokens[(size_t)b * T + i] = tok;
@@ -635,6 +641,54 @@ sample_embed_advance_kernel(const float* __restrict__ logits, int ld, int V, flo
       *done = 0;
       *pos = i + 1;
     }
+  }
+}
+
+// out[b, :] = nn.LayerNorm(d)(y[b, :]) + add[b, *pos, :]: the norm1 of an ALIGNED decoder layer followed by the residual of its
+// "cross-attention", which is an MLP of the aligned memory event and therefore a per-position constant of the whole generation
+// (transformer_custom.py:448-472), precomputed once per window as add (B, T, d).  One CTA per row.
+__global__ void __launch_bounds__(128)
+decode_ln_add_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     const float* __restrict__ add, int T, const int* __restrict__ pos, float* __restrict__ out, int d) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i = min(max(ld_pos(pos), 0), T - 1);
+  const float* row = y + (size_t)b * d;
+  const float* arow = add + ((size_t)b * T + i) * d;
+  float v[8], a[8];                                // d <= 1024
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = k * 128 + tid;
+    v[k] = c < d ? ld_dyn(row + c) : 0.f;
+    a[k] = c < d ? ld_dyn(arow + c) : 0.f;
+    t += v[k];
+  }
+  t = warp_sum(t);
+  if (lane == 0) red[warp] = t;
+  __syncthreads();
+  const float mu = (red[0] + red[1] + red[2] + red[3]) / d;
+  t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k * 128 + tid < d) t += (v[k] - mu) * (v[k] - mu);
+  t = warp_sum(t);
+  if (lane == 0) red[4 + warp] = t;
+  __syncthreads();
+  const float rs = 1.0f / sqrtf((red[4] + red[5] + red[6] + red[7]) / d + eps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = k * 128 + tid;
+    if (c < d) out[(size_t)b * d + c] = (v[k] - mu) * rs * gamma[c] + beta[c] + a[k];
+  }
+}
+
+__global__ void elu_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[t];
+    out[t] = v > 0.f ? v : expm1f(v);              // nn.ELU(alpha = 1)
   }
 }
 
@@ -844,6 +898,22 @@ VQ_API int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float t
   VQ_CUDA_CALL(launch_step(sample_embed_advance_kernel, dim3(B), dim3(256), smem, vq_stream(stream), 0, logits, ld, V, temperature, top_k,
                            top_p, u, u_stride, tokens, T, pos, greedy, tables, table_off, chan, evt, feat, C, total_upscaling, E, pe,
                            done));
+  return VQ_OK;
+}
+
+VQ_API int vqcpc_decode_ln_add(const float* y, const float* gamma, const float* beta, float eps, const float* add, int T, const int* pos,
+                               float* out, int B, int d, void* stream) {
+  VQ_CHECK_ARG(B >= 1 && d >= 1 && d <= 1024 && T >= 1 && pos != nullptr, "decode_ln_add: bad arguments B=%d d=%d", B, d);
+  VQ_CUDA_CALL(launch_step(decode_ln_add_kernel, dim3(B), dim3(128), 0, vq_stream(stream), 0, y, gamma, beta, eps, add, T, pos, out, d));
+  return VQ_OK;
+}
+
+// nn.ELU() of the aligned decoder layer's memory MLP (transformer_custom.py:428-432)
+VQ_API int vqcpc_elu_fwd(const float* x, float* out, int64_t n, void* stream) {
+  if (n == 0) return VQ_OK;
+  const int64_t want = vq_cdiv(n, 256 * 4), cap = (int64_t)vq_sm_count() * 8;
+  elu_kernel<<<(unsigned)(want > cap ? cap : want), 256, 0, vq_stream(stream)>>>(x, out, n);
+  VQ_CUDA_LAUNCH_CHECK("elu_kernel");
   return VQ_OK;
 }
 
