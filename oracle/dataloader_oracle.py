@@ -55,6 +55,12 @@ def cpc_batches(positive, negative, cfg, batch_size, shuffle_train=True, shuffle
     return [agg(*a) for a in zip(pos, neg, nbk)]
 
 
+def window_batches(tensors, batch_size, shuffle_train=True, shuffle_val=False):
+    """bach_dataloader.py:22-33: {'x': (B, ticks, V)} streams."""
+    return [({'x': t[0].transpose(1, 2)} for t in dl)
+            for dl in data_loaders(tensors, batch_size, shuffle_train=shuffle_train, shuffle_val=shuffle_val)]
+
+
 def synthetic_chorale_tensors(n, ticks, seed, vocab=(50, 47, 45, 52)):
     """A stand-in for the cached dataset: (score (n, 4, ticks) int32, metadata (n, 4, ticks, 1) int32) like :166-178."""
     g = torch.Generator().manual_seed(seed)

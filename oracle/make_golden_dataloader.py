@@ -89,6 +89,27 @@ def main():
                 assert all(torch.equal(g[k], w[k]) for k in w), name
         print(name, {k: tuple(v.shape) for k, v in rec['train'][0].items()}, 'oracle == reference')
         out[name] = rec
+    # whole-window loader of the student / decoder trainers (bach_dataloader.py)
+    from VQCPCB.dataloaders.bach_dataloader import BachDataloaderGenerator
+    tens = O.synthetic_chorale_tensors(150, 24, 21)
+    gen = BachDataloaderGenerator.__new__(BachDataloaderGenerator)
+    ds = ChoraleBeatsDataset.__new__(ChoraleBeatsDataset)
+    ds.cache_dir = os.path.join(tmp, 'windows')
+    os.makedirs(ds.cache_dir)
+    torch.save(torch.utils.data.TensorDataset(*tens), f'{ds.cache_dir}/tensor_dataset')
+    gen.dataset = ds
+    torch.manual_seed(21)
+    train, val, _ = gen.dataloaders(batch_size=6)
+    rec = dict(batch_size=6, seed=21, positive=tens[0], train=[], val=[])
+    it = iter(train)
+    for _ in range(3):
+        rec['train'].append({k: v.clone() for k, v in next(it).items()})
+    rec['val'].append({k: v.clone() for k, v in next(iter(val)).items()})
+    torch.manual_seed(21)
+    tr_o, va_o, _ = O.window_batches(tens, 6)
+    assert all(torch.equal(next(tr_o)['x'], w['x']) for w in rec['train']) and torch.equal(next(va_o)['x'], rec['val'][0]['x'])
+    print('windows', tuple(rec['train'][0]['x'].shape), 'oracle == reference')
+    out['windows'] = rec
     path = os.path.join(ROOT, 'tests', 'golden', 'dataloader.pt')
     torch.save(out, path)
     print('wrote', path, os.path.getsize(path))

@@ -64,3 +64,13 @@ def test_cached_dataset_layout_and_errors(tmp_path):
     assert torch.equal(ds.score_tensor(), score)
     assert ds.split_ranges() == ((0, 85), (85, 95), (95, 101))
     assert [len(d) for d in ds.index2note_dicts] == [int(score[:, v].max()) + 1 for v in range(4)]
+
+
+def test_window_loader_oracle_matches_reference_golden():
+    rec = torch.load(GOLD)['windows']
+    tens = (rec['positive'], torch.zeros(rec['positive'].shape + (1,), dtype=torch.int32))
+    torch.manual_seed(rec['seed'])
+    train, val, _ = O.window_batches(tens, rec['batch_size'])
+    for w in rec['train']:
+        assert torch.equal(next(train)['x'], w['x'])
+    assert torch.equal(next(val)['x'], rec['val'][0]['x'])

@@ -84,3 +84,19 @@ def test_trainer_steps_on_device_resident_batches(tmp_path):
     trainer.train()
     st = trainer.step(next(train), True, False)
     assert torch.isfinite(st['loss']).item()
+
+
+def test_window_loader_equals_reference_golden(tmp_path):
+    """BachDataloaderGenerator (student trainer / Decoder.generate producer): tensor_dict['x'] from the device gather."""
+    from VQCPCB import getters
+    rec = torch.load(GOLD)['windows']
+    tens = (rec['positive'], torch.zeros(rec['positive'].shape + (1,), dtype=torch.int32))
+    _write_cache(tmp_path, rec['positive'].shape[2] // 4, tens)
+    gen = getters.get_dataloader_generator('bach', 'student', dict(sequences_size=rec['positive'].shape[2] // 4,
+                                                                   database_root=str(tmp_path)))
+    torch.manual_seed(rec['seed'])
+    train, val, _ = gen.dataloaders(batch_size=rec['batch_size'])
+    for w in rec['train']:
+        g = next(train)['x']
+        assert g.is_cuda and torch.equal(g.cpu(), w['x'].long())
+    assert torch.equal(next(val)['x'].cpu(), rec['val'][0]['x'].long())

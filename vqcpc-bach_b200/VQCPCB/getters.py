@@ -28,8 +28,11 @@ def get_dataloader_generator(dataset, training_method, dataloader_generator_kwar
         if dataset.lower() in ('synthetic', 'bach_synthetic'):
             return SyntheticDataloaderGenerator(sequences_size=kw['sequences_size'], vocab_size=kw.get('vocab_size', 64),
                                                 seed=kw.get('seed', 1234))
-        raise NotImplementedError('dataset="bach" needs music21 and the chorale corpus, which are not available here; '
-                                  'use dataset="synthetic" (same batch contract: tensor_dict["x"] (batch, events, channels))')
+        if dataset.lower() == 'bach':                        # the reference's cached tensor_dataset (see bach_cpc_dataloader.py)
+            from .dataloaders.bach_dataloader import BachDataloaderGenerator
+            return BachDataloaderGenerator(sequences_size=kw['sequences_size'], database_root=kw.get('database_root'))
+        raise NotImplementedError(f'dataset={dataset!r}: use "bach" (cached tensor_dataset) or "synthetic" '
+                                  '(same batch contract: tensor_dict["x"] (batch, events, channels))')
     if training_method.lower() != 'vqcpc':
         raise NotImplementedError(f'training_method={training_method!r} {_NEXT}')
     if dataset.lower() in ('synthetic', 'bach_synthetic'):
