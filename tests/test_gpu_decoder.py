@@ -258,3 +258,26 @@ def test_cached_generation_launch_modes(case, monkeypatch):
                     assert torch.equal(dec.generate_from_codes(src, greedy=True), full), (case, B, pdl)
     finally:
         ops.set_gemm_mode('bf16x3')
+
+
+@pytest.mark.parametrize('decoder_type', ['transformer_relative', 'transformer_relative_diagonal'])
+def test_main_decoder_generates_end_to_end(decoder_type, tmp_path):
+    """`main_decoder.py -c configs/decoder_relative.py` as a subprocess (the reference's inference entry point, main_decoder.py:
+    16-160): real Encoder built by the getters (codes from its quantizer, `merge_codes`), decoder from `get_decoder`, a window from
+    the loader, `Decoder.generate` on the cached path, re-encoding of [original; generated]."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VQCPC_BLOCKS='2', VQCPC_CODEBOOK='16', VQCPC_DECODER_BEATS='4', VQCPC_DECODER_TYPE=decoder_type,
+               VQCPC_DATASET='synthetic')
+    cfg = os.path.join(root, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'decoder_relative.py')
+    r = subprocess.run([sys.executable, os.path.join(root, 'main_decoder.py'), '-c', cfg, '--num_examples', '1', '--batch_size', '2'],
+                       cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert 'tokens/s' in r.stdout
+    models = os.listdir(tmp_path / 'models')
+    assert len(models) == 1 and models[0].startswith('decoder_relative_')
+    rec = torch.load(tmp_path / 'models' / models[0] / 'generation_0.pt')
+    assert rec['original'].shape == (2, 16, 4) and rec['generated'].shape == (2, 16, 4)
+    assert int(rec['generated'].min()) >= 0 and int(rec['generated'].max()) < 64
+    assert rec['recoding'].shape == (3, 4) and int(rec['recoding'].max()) < 16          # [original; 2 generated] x 4 codes

@@ -21,12 +21,16 @@ class BachDataloaderGenerator:
         score = self.dataset.score_tensor()
         loaders, offs = self.dataset.index_loaders(batch_size, shuffle_train=shuffle_train, shuffle_val=shuffle_val)
 
-        def stream(loader, off):
-            for idx in loader:
+        # the reference returns generator EXPRESSIONS (bach_dataloader.py:26-33), which call iter(dataloader) when they are
+        # created: the three loaders draw their base seeds here, in order, before any batch is requested
+        iterators = [iter(l) for l in loaders]
+
+        def stream(it, off):
+            for idx in it:
                 rows = (idx + off).to(score.device, non_blocking=True)
                 yield {'x': BachCPCDataloaderGenerator._window(score, rows, 0, score.shape[2])}
 
-        return [stream(l, o) for l, o in zip(loaders, offs)]
+        return [stream(it, o) for it, o in zip(iterators, offs)]
 
     def write(self, x, path):
         raise NotImplementedError('score writing needs music21 (outside this library)')

@@ -1,8 +1,8 @@
 """String-keyed factories for the encoder-training path (mirror of VQCPCB/getters.py:24-218, :431-516).
 
 Built: the branches reachable from ``main_encoder.py -t`` with ``training_method='vqcpc'`` and ``'student'`` (teacher +
-auxiliary decoder, getters.py:221-262, :444-482); the decoder / prior branches raise NotImplementedError with a pointer to
-SURVEY.md §8f.  Config keys that several shipped
+auxiliary decoder, getters.py:221-262, :444-482) and ``get_decoder`` for the relative decoders (getters.py:274-395; inference path,
+SURVEY.md §8f row 3); the prior branch raises NotImplementedError.  Config keys that several shipped
 configs omit (``c_net_kwargs['bidirectional']``, ``schedule_lr``) get the reference's de-facto defaults.
 """
 from .data_processor.bach_cpc_data_processor import BachCPCDataProcessor
@@ -24,7 +24,7 @@ def get_dataloader_generator(dataset, training_method, dataloader_generator_kwar
     """'bach' needs the music21 chorale corpus (absent offline); 'synthetic' is the in-scope producer with the same
     batch-dict contract."""
     kw = dataloader_generator_kwargs
-    if training_method.lower() == 'student':
+    if training_method.lower() in ('student', 'decoder', 'prior'):                    # getters.py:38-43: whole windows
         if dataset.lower() in ('synthetic', 'bach_synthetic'):
             return SyntheticDataloaderGenerator(sequences_size=kw['sequences_size'], vocab_size=kw.get('vocab_size', 64),
                                                 seed=kw.get('seed', 1234))
@@ -181,3 +181,32 @@ def get_auxiliary_decoder(auxiliary_decoder_type, auxiliary_decoder_kwargs):
                                     upscale_factors=k['upscale_factors'], n_head=k['n_head'], dim_feedforward=k['dim_feedforward'],
                                     list_of_num_layers=k['list_of_num_layers'], d_model=k['d_model'],
                                     num_tokens_bottleneck=k['num_tokens_bottleneck'], dropout=k['dropout'])
+
+
+_DECODER_TYPES = {   # getters.py:309-393: decoder_type -> (encoder attention, cross attention) of the relative transformer
+    'transformer_relative': ('anticausal', 'anticausal'),
+    'transformer_relative_fullCross': ('anticausal', 'full'),
+    'transformer_relative_diagonal': ('anticausal', 'diagonal'),
+    'transformer_relative_full': ('full', 'full'),
+}
+
+
+def get_decoder(model_dir, dataloader_generator, data_processor, encoder, decoder_type, decoder_kwargs):
+    """getters.py:274-395.  ``decoder_type='transformer'`` (absolute positional embeddings) is not built."""
+    import numpy as np
+    from .decoders.decoder import Decoder
+    if decoder_type not in _DECODER_TYPES:
+        raise NotImplementedError(f'decoder_type={decoder_type!r}: the relative decoders {sorted(_DECODER_TYPES)} are built')
+    enc_att, cross_att = _DECODER_TYPES[decoder_type]
+    num_channels_decoder, num_events_decoder = data_processor.num_channels, data_processor.num_events
+    num_channels_encoder = 1
+    num_events_encoder = int((num_events_decoder * num_channels_decoder) //
+                             (np.prod(encoder.downscaler.downscale_factors) * num_channels_encoder))
+    k = decoder_kwargs
+    return Decoder(model_dir=model_dir, dataloader_generator=dataloader_generator, data_processor=data_processor, encoder=encoder,
+                   transformer_type='relative', encoder_attention_type=enc_att, cross_attention_type=cross_att, d_model=k['d_model'],
+                   num_encoder_layers=k['num_encoder_layers'], num_decoder_layers=k['num_decoder_layers'], n_head=k['n_head'],
+                   dim_feedforward=k['dim_feedforward'], dropout=k['dropout'],
+                   positional_embedding_size=k['positional_embedding_size'], num_channels_encoder=num_channels_encoder,
+                   num_events_encoder=num_events_encoder, num_channels_decoder=num_channels_decoder,
+                   num_events_decoder=num_events_decoder)
