@@ -144,6 +144,11 @@ int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e2, cons
                         float* ds_scratch, float* d_qkv, void* d_qkv_hi, void* d_qkv_lo, float* d_e1, float* d_e2, int64_t P,
                         int L, int H, int head_dim, float q_scale, void* stream);
 
+/* vqcpc_attn_long_fwd with the decoder's attention masks (decoders/decoder.py:295-306): mask_mode 0 none, 1 causal (keys <= query),
+ * 2 anticausal (keys >= query); key tiles without a visible key are skipped.  fp32 output only. */
+int vqcpc_attn_long_fwd_masked(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L, int H,
+                               int head_dim, int mask_mode, void* stream);
+
 /* ---- general relative attention, forward only (decoder inference: decoders/decoder.py:431-543, :552-722;
  *      transformer_custom.py:355-384 decoder layer; multihead_attention_custom.py:168-353 incl. the encoder-decoder branch;
  *      subsampled_relative_attention.py:30-122 with seq_len_tgt != seq_len_src) -------------------------------------------

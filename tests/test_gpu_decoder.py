@@ -281,3 +281,32 @@ def test_main_decoder_generates_end_to_end(decoder_type, tmp_path):
     assert rec['original'].shape == (2, 16, 4) and rec['generated'].shape == (2, 16, 4)
     assert int(rec['generated'].min()) >= 0 and int(rec['generated'].max()) < 64
     assert rec['recoding'].shape == (3, 4) and int(rec['recoding'].max()) < 16          # [original; 2 generated] x 4 codes
+
+
+@pytest.mark.parametrize('L,mode', [(64, 1), (100, 1), (100, 2), (48, 2), (37, 0), (256, 1)])
+def test_attn_long_masked_vs_fp64(L, mode):
+    """vqcpc_attn_long_fwd_masked (tiled self-attention with the decoder's causal / anticausal masks, skipped key tiles) against
+    the fp64 oracle attention (literal relative bias + additive mask)."""
+    from VQCPCB import _native, ops
+    H, hd, P = 2, 64, 3
+    d = H * hd
+    g = torch.Generator().manual_seed(L * 10 + mode)
+    qkv = torch.randn(P, L, 3 * d, generator=g) * 0.5
+    e1 = torch.randn(H * L, hd, generator=g) * 0.3
+    e2 = torch.randn(H * L, hd, generator=g) * 0.3
+    q64, k64, v64 = (t.double() for t in qkv.split(d, dim=-1))
+    sp = lambda t: t.reshape(P, L, H, hd).transpose(1, 2).reshape(P * H, L, hd)      # noqa: E731
+    s = torch.bmm(sp(q64), sp(k64).transpose(1, 2)) + D.rel_bias_general(sp(q64), e1.double(), e2.double(), L, L)
+    if mode == 1:
+        s = s + D.causal_mask(L).double()
+    elif mode == 2:
+        s = s + D.causal_mask(L).t().double()
+    a = torch.softmax(s, dim=-1)
+    ref = torch.bmm(a, sp(v64)).reshape(P, H, L, hd).transpose(1, 2).reshape(P * L, d)
+    qc, e1c, e2c = qkv.reshape(P * L, 3 * d).cuda(), e1.cuda(), e2.cuda()
+    out = torch.empty(P * L, d, device='cuda')
+    probs = torch.full((P, H, L, L), 7.0, device='cuda')
+    _native.call('vqcpc_attn_long_fwd_masked', _pp(qc), _pp(e1c), _pp(e2c), _pp(out), _pp(probs), P, L, H, hd, mode, ops._stream())
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 3e-6
+    assert rel_err(probs, a.reshape(P, H, L, L)) < 3e-6

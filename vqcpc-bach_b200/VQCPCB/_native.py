@@ -44,6 +44,7 @@ SIGNATURES = {
     'vqcpc_attn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     'vqcpc_attn_long_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     'vqcpc_attn_long_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
+    'vqcpc_attn_long_fwd_masked': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_map_fwd': [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_decode_features': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     'vqcpc_linear_small': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P],

@@ -180,8 +180,16 @@ class Decoder(nn.Module):
             q = ops.linear_fwd(x_q, w[:d], b[:d], scale_cols=(scale, d))
             kv = ops.linear_fwd(x_kv, w[d:], b[d:])
             k, v, ldq, ldkv = kv, kv[:, d:], d, 2 * d
-        m1, m2 = device_maps(Lq, Lk, x_q.device)
         out = torch.empty(B * Lq, d, dtype=torch.float32, device=x_q.device)
+        if x_kv is None and Lq <= 1024 and mask in (None, 'causal', 'anticausal'):
+            # self-attention: the tiled full-sequence kernel (closed-form skewed bias = the maps for T == S, csrc/attn_long.cu)
+            mode = {None: 0, 'causal': 1, 'anticausal': 2}[mask]
+            _native.call('vqcpc_attn_long_fwd_masked', _p(qkv), _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(out), None, B, Lq, H, hd,
+                         mode, ops._stream())
+            return out
+        if isinstance(mask, str):
+            mask = _causal_mask(Lk, x_q.device) if mask == 'causal' else _anticausal_mask(Lk, x_q.device)
+        m1, m2 = device_maps(Lq, Lk, x_q.device)
         _native.call('vqcpc_attn_map_fwd', _p(q), ldq, _p(k), _p(v), ldkv, _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(m1), _p(m2),
                      _p(mask), _p(out), None, B, Lq, Lk, H, hd, ops._stream())
         return out
@@ -235,12 +243,7 @@ class Decoder(nn.Module):
             src = ops.linear_fwd(ops._f32c(source.to(dev)).reshape(-1, source.shape[-1]), self.source_embeddings.weight,
                                  self.source_embeddings.bias)
         S = src.shape[0] // B
-        if self.encoder_attention_type == 'full':
-            source_mask = None
-        elif self.encoder_attention_type == 'causal':
-            source_mask = _causal_mask(S, dev)
-        else:
-            source_mask = _anticausal_mask(S, dev)
+        source_mask = None if self.encoder_attention_type == 'full' else self.encoder_attention_type    # 'causal' | 'anticausal'
         x = src.contiguous()
         for lyr in self.transformer.encoder.layers:
             x = self._enc_layer(lyr, x, B, S, source_mask)
@@ -264,7 +267,7 @@ class Decoder(nn.Module):
         tgt = ops.linear_fwd(tgt.contiguous(), self.linear_target.weight, self.linear_target.bias).view(B, T, d)   # :469
         tgt = torch.cat([self.sos.expand(B, 1, d), tgt[:, :-1]], dim=1).reshape(B * T, d).contiguous()   # shift by one   :476-482
         memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None  # :487-496
-        target_mask = _causal_mask(T, dev)                                                               # :507
+        target_mask = 'causal'                                                                           # :507
         y = tgt
         for lyr in self.transformer.decoder.layers:
             y = self._dec_layer(lyr, y, memory, B, T, S, target_mask, memory_mask)

@@ -46,7 +46,7 @@ __device__ __forceinline__ const float* rel_row(const float* e1h, const float* e
 __global__ void __launch_bounds__(THREADS)
 attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1, const float* __restrict__ e2,
                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                     float* __restrict__ probs, int L, int H) {
+                     float* __restrict__ probs, int L, int H, int mask_mode) {
   extern __shared__ __align__(16) float sm[];
   float* qs = sm;                    // [R][64]
   float* sc = sm + R * HD;           // [R][L]
@@ -57,6 +57,9 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
   const float* e1h = e1 + (size_t)h * L * HD;
   const float* e2h = e2 + (size_t)h * L * HD;
   const int rows = min(R, L - i0);
+  // mask_mode 1 (causal: keys <= query, decoder.py:295-298) / 2 (anticausal: keys >= query, :300-306): only the key tiles that
+  // hold a visible key are visited; inside them hidden scores are -inf like the reference's additive mask
+  const int jlo = mask_mode == 2 ? (i0 / KT) * KT : 0, jhi = mask_mode == 1 ? min(L, i0 + rows) : L;
   for (int t = threadIdx.x; t < R * HD; t += THREADS) {
     const int i = t / HD, d = t % HD;
     qs[t] = (i < rows) ? base[(int64_t)(i0 + i) * ld + h * HD + d] : 0.f;
@@ -70,7 +73,7 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
     float* s1 = ks + KT * PADW;                     // [KT + R - 1][PADW]  e1 slab
     float* s2 = s1 + (KT + R - 1) * PADW;           // [KT + R - 1][PADW]  e2 slab
     const int ii = threadIdx.x >> 5, jj = threadIdx.x & 31;
-    for (int j0 = 0; j0 < L; j0 += KT) {
+    for (int j0 = jlo; j0 < jhi; j0 += KT) {
       const bool need1 = j0 <= i0 + R - 1, need2 = j0 + KT - 1 > i0;
       const int b1 = (L - 1 - i0 + j0) - (R - 1), b2 = (j0 - i0) - (R - 1);      // table row of slab row 0
       __syncthreads();
@@ -101,7 +104,8 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
           a0 += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
           a1 += q4.x * r4.x + q4.y * r4.y + q4.z * r4.z + q4.w * r4.w;
         }
-        sc[ii * L + j] = a0 + a1;
+        const bool hidden = (mask_mode == 1 && j > i0 + ii) || (mask_mode == 2 && j < i0 + ii);
+        sc[ii * L + j] = hidden ? -INFINITY : a0 + a1;
       }
     }
   }
@@ -111,10 +115,10 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
   if (warp < rows) {
     float* s = sc + warp * L;
     float m = -INFINITY;
-    for (int j = lane; j < L; j += 32) m = fmaxf(m, s[j]);
+    for (int j = jlo + lane; j < jhi; j += 32) m = fmaxf(m, s[j]);
     m = warp_max(m);
     float z = 0.f;
-    for (int j = lane; j < L; j += 32) {
+    for (int j = jlo + lane; j < jhi; j += 32) {
       const float ev = __expf(s[j] - m);
       s[j] = ev;
       z += ev;
@@ -122,10 +126,14 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
     z = warp_sum(z);
     const float inv = 1.f / z;
     float* pg = probs ? probs + ((p * H + h) * (int64_t)L + (i0 + warp)) * L : nullptr;
-    for (int j = lane; j < L; j += 32) {
+    for (int j = jlo + lane; j < jhi; j += 32) {
       const float a = s[j] * inv;
       s[j] = a;
       if (pg) pg[j] = a;
+    }
+    if (pg) {                                        // key tiles that were never visited
+      for (int j = lane; j < jlo; j += 32) pg[j] = 0.f;
+      for (int j = jhi + lane; j < L; j += 32) pg[j] = 0.f;
     }
   }
   __syncthreads();
@@ -137,7 +145,7 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
       const float* vb = base + (2 * H + h) * HD + d;
       float o0 = 0.f, o1 = 0.f;
 #pragma unroll 4
-      for (int j = 0; j < L; ++j) {
+      for (int j = jlo; j < jhi; ++j) {
         const float2 v2 = __ldg(reinterpret_cast<const float2*>(vb + (int64_t)j * ld));
         const float a = s[j];
         o0 += a * v2.x;
@@ -365,8 +373,8 @@ softmax_ce_kernel(const float* __restrict__ logits, int ld, const int64_t* __res
 
 }  // namespace
 
-VQ_API int vqcpc_attn_long_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
-                               float* probs, int64_t P, int L, int H, int head_dim, void* stream) {
+static int attn_long_fwd_launch(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                                float* probs, int64_t P, int L, int H, int head_dim, int mask_mode, void* stream) {
   VQ_CHECK_ARG(head_dim == HD, "attn_long_fwd: head_dim must be 64 (got %d)", head_dim);
   VQ_CHECK_ARG(L >= 1 && L <= 1024 && H >= 1 && H <= 64, "attn_long_fwd: bad shape L=%d H=%d", L, H);
   VQ_CHECK_ARG((out || out_hi) && ((out_hi == nullptr) == (out_lo == nullptr)), "attn_long_fwd: need out and/or (out_hi, out_lo)");
@@ -381,9 +389,21 @@ VQ_API int vqcpc_attn_long_fwd(const float* qkv, const float* e1, const float* e
   }
   dim3 grid((unsigned)vq_cdiv(L, R), (unsigned)H, (unsigned)P);
   attn_long_fwd_kernel<<<grid, THREADS, smem, vq_stream(stream)>>>(qkv, e1, e2, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                                    reinterpret_cast<__nv_bfloat16*>(out_lo), probs, L, H);
+                                                                    reinterpret_cast<__nv_bfloat16*>(out_lo), probs, L, H, mask_mode);
   VQ_CUDA_LAUNCH_CHECK("attn_long_fwd_kernel");
   return VQ_OK;
+}
+
+VQ_API int vqcpc_attn_long_fwd(const float* qkv, const float* e1, const float* e2, float* out, void* out_hi, void* out_lo,
+                               float* probs, int64_t P, int L, int H, int head_dim, void* stream) {
+  return attn_long_fwd_launch(qkv, e1, e2, out, out_hi, out_lo, probs, P, L, H, head_dim, 0, stream);
+}
+
+// the same with the decoder's attention masks (decoder.py:295-306): mask_mode 0 none, 1 causal (keys <= query), 2 anticausal
+VQ_API int vqcpc_attn_long_fwd_masked(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L,
+                                      int H, int head_dim, int mask_mode, void* stream) {
+  VQ_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2, "attn_long_fwd_masked: mask_mode 0 (none), 1 (causal), 2 (anticausal)");
+  return attn_long_fwd_launch(qkv, e1, e2, out, nullptr, nullptr, probs, P, L, H, head_dim, mask_mode, stream);
 }
 
 // d_qkv (fp32) and / or its bf16 split are overwritten; d_e1 / d_e2 are accumulated; ds_scratch: (P, H, L, L) floats.
