@@ -245,37 +245,54 @@ linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restri
   __syncthreads();                                 // the barrier initialisation is visible to the waiting threads
   ls_mbar_wait(bar, 0);
   if (LN) {
+    // warp w normalises rows w, w + 4, w + 8, w + 12 - all of them at once (independent reduction chains interleave)
+    constexpr int NR = (MT + 3) / 4;
     const float invK = 1.f / (float)K;
-    for (int b = warp; b < M; b += 4) {
-      float4* row = reinterpret_cast<float4*>(xs + (size_t)b * K);
-      float4 v[KV];
+    float4 v[NR][KV];
+    float mu[NR], rs[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int bb = warp + 4 * r;
       float t = 0.f;
 #pragma unroll
       for (int i = 0; i < KV; ++i) {
         const int c = i * 32 + lane;
-        v[i] = c < K4 ? row[c] : zero4;
-        t += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        v[r][i] = (bb < M && c < K4) ? reinterpret_cast<const float4*>(xs + (size_t)bb * K)[c] : zero4;
+        t += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
       }
-      const float mu = warp_sum(t) * invK;
-      t = 0.f;
+      mu[r] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) mu[r] = warp_sum(mu[r]) * invK;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float t = 0.f;
 #pragma unroll
       for (int i = 0; i < KV; ++i)
         if (i * 32 + lane < K4) {
-          const float a0 = v[i].x - mu, a1 = v[i].y - mu, a2 = v[i].z - mu, a3 = v[i].w - mu;
+          const float a0 = v[r][i].x - mu[r], a1 = v[r][i].y - mu[r], a2 = v[r][i].z - mu[r], a3 = v[r][i].w - mu[r];
           t += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
         }
-      const float rs = 1.0f / sqrtf(warp_sum(t) * invK + ln_eps);
+      rs[r] = t;
+    }
 #pragma unroll
-      for (int i = 0; i < KV; ++i) {
-        const int c = i * 32 + lane;
-        if (c < K4) {
-          float4 o;
-          o.x = (v[i].x - mu) * rs * g[i].x + be[i].x;
-          o.y = (v[i].y - mu) * rs * g[i].y + be[i].y;
-          o.z = (v[i].z - mu) * rs * g[i].z + be[i].z;
-          o.w = (v[i].w - mu) * rs * g[i].w + be[i].w;
-          row[c] = o;
-          if (ln_out && blockIdx.x == 0) *(reinterpret_cast<float4*>(ln_out + (size_t)b * K) + c) = o;
+    for (int r = 0; r < NR; ++r) rs[r] = 1.0f / sqrtf(warp_sum(rs[r]) * invK + ln_eps);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int bb = warp + 4 * r;
+      if (bb < M) {
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          const int c = i * 32 + lane;
+          if (c < K4) {
+            float4 o;
+            o.x = (v[r][i].x - mu[r]) * rs[r] * g[i].x + be[i].x;
+            o.y = (v[r][i].y - mu[r]) * rs[r] * g[i].y + be[i].y;
+            o.z = (v[r][i].z - mu[r]) * rs[r] * g[i].z + be[i].z;
+            o.w = (v[r][i].w - mu[r]) * rs[r] * g[i].w + be[i].w;
+            reinterpret_cast<float4*>(xs + (size_t)bb * K)[c] = o;
+            if (ln_out && blockIdx.x == 0) *(reinterpret_cast<float4*>(ln_out + (size_t)bb * K) + c) = o;
+          }
         }
       }
     }
