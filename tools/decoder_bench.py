@@ -69,6 +69,7 @@ def main():
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--full-tokens', type=int, default=32)
     ap.add_argument('--cpu-forwards', type=int, default=2)
+    ap.add_argument('--attn-split', type=int, default=0, help='keys split over a cluster of this many CTAs (0 = product heuristic)')
     ap.add_argument('--cross', default='anticausal', choices=['anticausal', 'full', 'diagonal'])
     ap.add_argument('--pdl', type=int, default=-1, help='programmatic dependent launch between the step kernels: 0 / 1 (A/B), -1 = the product heuristic')
     a = ap.parse_args()
@@ -77,6 +78,7 @@ def main():
     if a.pdl >= 0:
         os.environ['VQCPC_DECODE_PDL'] = str(a.pdl)
     CFG['cross_attention_type'] = a.cross
+    _native.call('vqcpc_attn_decode_set_split', a.attn_split)
     dec, S = build(CFG)
     shapes = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
     prm = D.make_decoder_params(shapes, seed=0)

@@ -864,12 +864,17 @@ VQ_API int vqcpc_attn_decode(const float* q, int ldq, const float* k_new, const 
   VQ_CHECK_ARG((map1 == nullptr) == (e1 == nullptr) && (map2 == nullptr) == (e2 == nullptr), "attn_decode: a map needs its table");
   VQ_CHECK_ARG((k_new == nullptr) == (v_new == nullptr) && (ldc % 4) == 0 && (k_new == nullptr || (ldn % 4) == 0), "attn_decode: bad cache arguments");
   VQ_CHECK_ARG(pos != nullptr, "attn_decode: position pointer missing");
-  // split the keys over a cluster so that a CTA (one key per thread) scores its chunk in one round of memory latency
+  // split the keys over a cluster: at most one CTA per 128 keys (one key per thread = one round of memory latency per chunk), and
+  // about 256 CTAs in flight for the whole launch - more only adds waves of latency-bound CTAs (measured on B200, 1024 keys, 8
+  // heads: batch 1 best with 8 splits, batch 16 with 2)
+  int ns_max = 1;
+  while (ns_max < AD_MAX_SPLIT && Lk > ns_max * AD_THREADS) ns_max *= 2;
   int ns = g_attn_decode_split;
   if (ns == 0) {
     ns = 1;
-    while (ns < AD_MAX_SPLIT && Lk > ns * AD_THREADS) ns *= 2;
+    while (ns < ns_max && (int64_t)H * P * ns * 2 <= 256) ns *= 2;
   }
+  ns = ns < ns_max ? ns : ns_max;
   const int chunk_max = (int)((vq_cdiv(Lk, ns) + 7) & ~7);
   const size_t smem = ((size_t)chunk_max + 9 * HD + 8 + 72 + AD_MAX_SPLIT * 72) * sizeof(float);
   const dim3 grid((unsigned)H, (unsigned)P, (unsigned)ns);
