@@ -14,7 +14,7 @@ run() {  # name file kexpr
   echo "$name rc=$rc $(tail -n 1 gpurun_out/$name.log)" | tee -a gpurun_out/summary.txt
   [ $rc -ne 0 ] && status=1
 }
-groups=${*:-kernels vq_tc gemm_fp32 gemm_tc enc_fp32 enc_tc}
+groups=${*:-kernels vq_tc gemm_fp32 gemm_tc enc_fp32 enc_tc decoder data}
 for g in $groups; do
   case $g in
     kernels)   run kernels tests/test_gpu_kernels.py "test" ;;
@@ -28,6 +28,8 @@ for g in $groups; do
     gemm_tc4)  VQCPC_GEMM_TILE=4 run gemm_tc4 tests/test_gpu_gemm.py "not fp32" ;;
     enc_fp32)  run enc_fp32 tests/test_gpu_encoder.py "fp32 or micro or eval or first_call or fused" ;;
     enc_tc)    run enc_tc tests/test_gpu_encoder.py "bf16x3" ;;
+    decoder)   run decoder tests/test_gpu_decoder.py "test" ;;
+    data)      run data tests/test_gpu_dataloader.py "test" ;;
   esac
 done
 exit $status
