@@ -118,7 +118,10 @@ def decoder_forward(source, target, prm, cfg):
     B, Ev, C = target.shape
     H = cfg['n_head']
     T = Ev * C
-    src = prm['source_embeddings.weight'][source]                                          # (B, S, d)
+    if source.is_floating_point():                                                         # NoQuantization: z vectors (:237-239)
+        src = F.linear(source, prm['source_embeddings.weight'], prm['source_embeddings.bias'])
+    else:
+        src = prm['source_embeddings.weight'][source]                                      # (B, S, d)
     S = src.shape[1]
     emb = torch.stack([prm[f'data_processor.embeddings.{c}.weight'][target[:, :, c]] for c in range(C)], dim=2)   # (B, Ev, C, E)
     tgt = emb.reshape(B, T, -1)

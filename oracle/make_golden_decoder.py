@@ -31,7 +31,15 @@ CASES = {
     'ac_diag': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=2, num_decoder_layers=2, num_events=16,
                              vocab=[20, 21, 22, 23], codebook_size=16, encoder_attention_type='anticausal',
                              cross_attention_type='diagonal'), B=3),
+    # encoder without quantization: the decoder consumes the z vectors through a Linear (decoder_relative_AC_D_C_*_noQuantization)
+    'diag_noq': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=1, num_decoder_layers=2, num_events=16,
+                              vocab=[20, 21, 22, 23], codebook_size=16, encoder_attention_type='anticausal',
+                              cross_attention_type='diagonal', no_quantization=True), B=2),
 }
+
+
+class NoQuantization:
+    codebook_dim = 3
 
 
 class StubEncoder(torch.nn.Module):
@@ -66,6 +74,8 @@ def main():
         C = len(c['vocab'])
         dp = BachDataProcessor(32, c['num_events'], list(c['vocab']))
         enc = StubEncoder(c['codebook_size'])
+        if c.get('no_quantization'):
+            enc.quantizer = NoQuantization()
         S = c['num_events'] * C // 16
         dec = Decoder(model_dir='/tmp/vqcpc_golden_decoder', dataloader_generator=None, data_processor=dp, encoder=enc,
                       transformer_type='relative', encoder_attention_type=c['encoder_attention_type'],
@@ -79,6 +89,8 @@ def main():
         dec.load_state_dict(prm, strict=True)
         g = torch.Generator().manual_seed(77)
         source = torch.randint(0, c['codebook_size'], (spec['B'], S), generator=g)
+        if c.get('no_quantization'):
+            source = torch.randn(spec['B'], S, 3, generator=g)
         target = torch.stack([torch.randint(0, v, (spec['B'], c['num_events']), generator=g) for v in c['vocab']], dim=2)
         with torch.no_grad():
             fp = dec.forward(source, target)

@@ -12,11 +12,16 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'decoder.pt')
 
 
+class NoQuantization:
+    codebook_dim = 3
+
+
 class _StubEncoder(torch.nn.Module):
-    def __init__(self, codebook_size):
+    def __init__(self, codebook_size, no_quantization=False):
         super().__init__()
         self.downscaler = types.SimpleNamespace(downscale_factors=[4, 4])
-        self.quantizer = types.SimpleNamespace(codebook_size=codebook_size, num_codebooks=1, codebook_dim=3)
+        self.quantizer = NoQuantization() if no_quantization else types.SimpleNamespace(codebook_size=codebook_size, num_codebooks=1,
+                                                                                        codebook_dim=3)
 
 
 def _build(c):
@@ -25,7 +30,8 @@ def _build(c):
     C = len(c['vocab'])
     dp = BachDataProcessor(32, c['num_events'], list(c['vocab']))
     S = c['num_events'] * C // 16
-    dec = Decoder(model_dir='/tmp/vqcpc_b200_decoder', dataloader_generator=None, data_processor=dp, encoder=_StubEncoder(c['codebook_size']),
+    dec = Decoder(model_dir='/tmp/vqcpc_b200_decoder', dataloader_generator=None, data_processor=dp,
+                  encoder=_StubEncoder(c['codebook_size'], c.get('no_quantization', False)),
                   transformer_type='relative', encoder_attention_type=c['encoder_attention_type'],
                   cross_attention_type=c['cross_attention_type'], d_model=c['d_model'], num_encoder_layers=c['num_encoder_layers'],
                   num_decoder_layers=c['num_decoder_layers'], n_head=c['n_head'], dim_feedforward=c['dim_feedforward'],
@@ -74,7 +80,7 @@ def test_attn_map_fwd_vs_oracle(Lq, Lk, masked):
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq'])
 def test_decoder_forward_vs_reference_golden(case, mode):
     """Decoder.forward on the CUDA path: the reference's own state_dict keys load strictly; logits and loss against the golden."""
     from VQCPCB import ops
@@ -165,7 +171,7 @@ def test_sample_step_vs_reference_golden():
         assert torch.equal(tokens.view(-1).cpu(), rec['logits'].argmax(dim=-1))
 
 
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq'])
 def test_cached_generation_equals_full_recompute(case):
     """The incremental path (key / value cache, CUDA graph per event, device sampling) against the reference's schedule (full
     forward per token) in exact-fp32 mode: greedy tokens identical; sampled tokens identical to the oracle sampler applied to the
