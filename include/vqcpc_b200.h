@@ -145,7 +145,8 @@ int vqcpc_attn_long_bwd(const float* qkv, const float* e1, const float* e2, cons
                         int L, int H, int head_dim, float q_scale, void* stream);
 
 /* vqcpc_attn_long_fwd with the decoder's attention masks (decoders/decoder.py:295-306): mask_mode 0 none, 1 causal (keys <= query),
- * 2 anticausal (keys >= query); key tiles without a visible key are skipped.  fp32 output only. */
+ * 2 anticausal (keys >= query); key tiles without a visible key are skipped.  fp32 output only; e1 == e2 == NULL: no relative bias
+ * (transformer_type 'absolute'). */
 int vqcpc_attn_long_fwd_masked(const float* qkv, const float* e1, const float* e2, float* out, float* probs, int64_t P, int L, int H,
                                int head_dim, int mask_mode, void* stream);
 
@@ -168,7 +169,10 @@ int vqcpc_attn_map_fwd(const float* q, int ldq, const float* k, const float* v, 
  * shifted right by one, :476-482); zeros at pos == 0.  tables: the per-channel embedding tables concatenated by rows,
  * table_off (C) int32 device = first row of each channel. */
 int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* tables, const int* table_off, const float* chan,
-                          const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe, void* stream);
+                          const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe, int pos_mode,
+                          void* stream);
+/* pos_mode 1 (transformer_type 'absolute', decoder.py:458-466): feat (B, E + pe) = [ embedding | chan[position] ] with chan the
+ * (T, pe) table of absolute positional embeddings; evt is not read. */
 /* nn.Linear on M <= 16 rows in exact fp32: out = [row0 if *pos == 0 else] relu?( (x W^T + bias) * scale on the first
  * scale_cols columns ) + residual.  W (N, K) row-major; bias / residual / row0 may be NULL. */
 int vqcpc_linear_small(const float* x, int ldx, const float* W, const float* bias, const float* residual, int ldr, float* out,
@@ -198,7 +202,7 @@ int vqcpc_sample_step(const float* logits, int ld, int V, float temperature, int
 int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float temperature, int top_k, float top_p, const double* u,
                               int u_stride, int64_t* tokens, int T, int* pos, int greedy, int B, const float* tables,
                               const int* table_off, const float* chan, const float* evt, float* feat, int C, int total_upscaling,
-                              int E, int pe, int* done, void* stream);
+                              int E, int pe, int* done, int pos_mode, void* stream);
 /* aligned ('diagonal') decoder layer, transformer_custom.py:389-479: its cross term is an MLP of the aligned memory event
  * (Linear, ELU, Linear - :428-432), i.e. a per-position constant add (B, T, d) during generation:
  * out (B, d) = LayerNorm(y) + add[:, *pos, :] (:447-449 norm1, :472 residual). */

@@ -79,7 +79,8 @@ def mha(xq, xkv, prm, pre, H, mask):
     s = torch.bmm(qh, kh.transpose(1, 2))
     if mask is not None:
         s = s + mask.unsqueeze(0)
-    s = s + rel_bias_general(qh, prm[pre + 'attn_bias.e1'], prm[pre + 'attn_bias.e2'], Lq, Lk)
+    if pre + 'attn_bias.e1' in prm:                                                        # absent for transformer_type='absolute'
+        s = s + rel_bias_general(qh, prm[pre + 'attn_bias.e1'], prm[pre + 'attn_bias.e2'], Lq, Lk)
     a = torch.softmax(s, dim=-1)
     o = torch.bmm(a, vh).reshape(B, H, Lq, hd).transpose(1, 2).reshape(B, Lq, d)
     return F.linear(o, prm[pre + 'out_proj.weight'], prm[pre + 'out_proj.bias'])
@@ -125,9 +126,14 @@ def decoder_forward(source, target, prm, cfg):
     S = src.shape[1]
     emb = torch.stack([prm[f'data_processor.embeddings.{c}.weight'][target[:, :, c]] for c in range(C)], dim=2)   # (B, Ev, C, E)
     tgt = emb.reshape(B, T, -1)
-    chan = prm['target_channel_embeddings'].repeat(B, T // C, 1)
-    evt = prm['target_events_positioning_embeddings'].repeat_interleave(C, dim=1).repeat(B, T // cfg['total_upscaling'], 1)
-    tgt = F.linear(torch.cat([tgt, chan, evt], dim=2), prm['linear_target.weight'], prm['linear_target.bias'])
+    if cfg.get('transformer_type', 'relative') == 'absolute':                              # decoder.py:458-466
+        src = torch.cat([src, prm['source_positional_embeddings'].repeat(B, 1, 1)], dim=2)
+        tgt = torch.cat([tgt, prm['target_positional_embeddings'].repeat(B, 1, 1)], dim=2)
+    else:
+        chan = prm['target_channel_embeddings'].repeat(B, T // C, 1)
+        evt = prm['target_events_positioning_embeddings'].repeat_interleave(C, dim=1).repeat(B, T // cfg['total_upscaling'], 1)
+        tgt = torch.cat([tgt, chan, evt], dim=2)
+    tgt = F.linear(tgt, prm['linear_target.weight'], prm['linear_target.bias'])
     tgt = torch.cat([prm['sos'].expand(B, 1, -1), tgt[:, :-1]], dim=1)
     dt = tgt.dtype
     anti = causal_mask(S, dt).t()

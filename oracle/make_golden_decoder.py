@@ -35,6 +35,10 @@ CASES = {
     'diag_noq': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=1, num_decoder_layers=2, num_events=16,
                               vocab=[20, 21, 22, 23], codebook_size=16, encoder_attention_type='anticausal',
                               cross_attention_type='diagonal', no_quantization=True), B=2),
+    # decoder_type 'transformer' (decoder_random.py / decoder_sameSeq.py): absolute positional embeddings, no relative bias
+    'absolute': dict(cfg=dict(d_model=128, n_head=2, dim_feedforward=256, num_encoder_layers=1, num_decoder_layers=2, num_events=16,
+                              vocab=[20, 21, 22, 23], codebook_size=16, encoder_attention_type='anticausal',
+                              cross_attention_type='full', transformer_type='absolute'), B=2),
 }
 
 
@@ -78,7 +82,7 @@ def main():
             enc.quantizer = NoQuantization()
         S = c['num_events'] * C // 16
         dec = Decoder(model_dir='/tmp/vqcpc_golden_decoder', dataloader_generator=None, data_processor=dp, encoder=enc,
-                      transformer_type='relative', encoder_attention_type=c['encoder_attention_type'],
+                      transformer_type=c.get('transformer_type', 'relative'), encoder_attention_type=c['encoder_attention_type'],
                       cross_attention_type=c['cross_attention_type'], d_model=c['d_model'],
                       num_encoder_layers=c['num_encoder_layers'], num_decoder_layers=c['num_decoder_layers'], n_head=c['n_head'],
                       dim_feedforward=c['dim_feedforward'], positional_embedding_size=8, num_channels_encoder=1,

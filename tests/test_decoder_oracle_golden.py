@@ -11,7 +11,7 @@ from oracle import decoder_oracle as D
 GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'decoder.pt')
 
 
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq', 'absolute'])
 def test_decoder_oracle_matches_reference_golden(case):
     rec = torch.load(GOLD)[case]
     prm = D.make_decoder_params(rec['shapes'], seed=0)

@@ -32,7 +32,7 @@ def _build(c):
     S = c['num_events'] * C // 16
     dec = Decoder(model_dir='/tmp/vqcpc_b200_decoder', dataloader_generator=None, data_processor=dp,
                   encoder=_StubEncoder(c['codebook_size'], c.get('no_quantization', False)),
-                  transformer_type='relative', encoder_attention_type=c['encoder_attention_type'],
+                  transformer_type=c.get('transformer_type', 'relative'), encoder_attention_type=c['encoder_attention_type'],
                   cross_attention_type=c['cross_attention_type'], d_model=c['d_model'], num_encoder_layers=c['num_encoder_layers'],
                   num_decoder_layers=c['num_decoder_layers'], n_head=c['n_head'], dim_feedforward=c['dim_feedforward'],
                   positional_embedding_size=8, num_channels_encoder=1, num_events_encoder=S, num_channels_decoder=C,
@@ -80,7 +80,7 @@ def test_attn_map_fwd_vs_oracle(Lq, Lk, masked):
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq', 'absolute'])
 def test_decoder_forward_vs_reference_golden(case, mode):
     """Decoder.forward on the CUDA path: the reference's own state_dict keys load strictly; logits and loss against the golden."""
     from VQCPCB import ops
@@ -171,7 +171,7 @@ def test_sample_step_vs_reference_golden():
         assert torch.equal(tokens.view(-1).cpu(), rec['logits'].argmax(dim=-1))
 
 
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq', 'absolute'])
 def test_cached_generation_equals_full_recompute(case):
     """The incremental path (key / value cache, CUDA graph per event, device sampling) against the reference's schedule (full
     forward per token) in exact-fp32 mode: greedy tokens identical; sampled tokens identical to the oracle sampler applied to the
@@ -240,7 +240,7 @@ def test_ln_linear_small_vs_fp64():
         assert rel_err(out, (ln @ w.double().t() + b.double()).clamp(min=0)) < 3e-6
 
 
-@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag'])
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'absolute'])
 def test_cached_generation_launch_modes(case, monkeypatch):
     """Graph replay with and without programmatic dependent launch at batch 1 / 3 / 5 (register and TMA-staged linears) against
     the full recompute.  Regression test: with overlapping kernels the activations / caches / position must be read through
@@ -266,7 +266,7 @@ def test_cached_generation_launch_modes(case, monkeypatch):
         ops.set_gemm_mode('bf16x3')
 
 
-@pytest.mark.parametrize('decoder_type', ['transformer_relative', 'transformer_relative_diagonal'])
+@pytest.mark.parametrize('decoder_type', ['transformer_relative', 'transformer_relative_diagonal', 'transformer'])
 def test_main_decoder_generates_end_to_end(decoder_type, tmp_path):
     """`main_decoder.py -c configs/decoder_relative.py` as a subprocess (the reference's inference entry point, main_decoder.py:
     16-160): real Encoder built by the getters (codes from its quantizer, `merge_codes`), decoder from `get_decoder`, a window from

@@ -46,7 +46,7 @@ SIGNATURES = {
     'vqcpc_attn_long_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P],
     'vqcpc_attn_long_fwd_masked': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     'vqcpc_attn_map_fwd': [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
-    'vqcpc_decode_features': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'vqcpc_decode_features': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'vqcpc_linear_small': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P],
     'vqcpc_attn_decode': [_P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _L, _I, _I, _P],
     'vqcpc_attn_decode_set_split': [_I],
@@ -54,7 +54,7 @@ SIGNATURES = {
     'vqcpc_decode_ln_add': [_P, _P, _P, _F, _P, _I, _P, _P, _I, _I, _P],
     'vqcpc_elu_fwd': [_P, _P, _L, _P],
     'vqcpc_ln_linear_small': [_P, _I, _P, _P, _F, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P],
-    'vqcpc_decode_sample_embed': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    'vqcpc_decode_sample_embed': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     'vqcpc_sample_step': [_P, _I, _I, _F, _I, _F, _P, _I, _P, _I, _P, _I, _I, _P],
     'vqcpc_decode_advance': [_P, _I, _P],
     'vqcpc_cpc_window_gather': [_P, _I, _L, _I, _I, _P, _L, _I, _I, _P, _P],

@@ -2,7 +2,8 @@
 (VQCPCB/decoders/decoder.py: constructor :24-247, ``forward`` :431-543, ``generate`` :552-722, ``init_generation`` :724-727;
 SURVEY.md §8f row 3, BASELINE config 5).
 
-Built: ``transformer_type='relative'`` with ``encoder_attention_type`` in {anticausal, causal, full} and ``cross_attention_type``
+Built: ``transformer_type`` 'relative' and 'absolute' (learnt absolute positional embeddings, no attention bias: decoder_type
+'transformer') with ``encoder_attention_type`` in {anticausal, causal, full} and ``cross_attention_type``
 in {anticausal, full, diagonal} (every shipped ``decoder_relative_*`` configuration; 'diagonal' = the aligned layer whose
 cross term is an MLP of the aligned memory event, transformer_custom.py:389-479), forward = teacher
 forced logits + cross-entropy, and autoregressive generation that recomputes the forward for every token exactly like the
@@ -33,29 +34,34 @@ class _Attn(nn.Module):
     """Parameters of ``MultiheadAttentionCustom`` (multihead_attention_custom.py:36-99): fused in-proj, out-proj, relative tables
     sized by the SOURCE length."""
 
-    def __init__(self, d_model, nhead, seq_len_src):
+    def __init__(self, d_model, nhead, seq_len_src, relative=True):
         super().__init__()
         mha = nn.MultiheadAttention(d_model, nhead)
         self.in_proj_weight = nn.Parameter(mha.in_proj_weight.detach().clone())
         self.in_proj_bias = nn.Parameter(mha.in_proj_bias.detach().clone())
         self.out_proj = _Linear(d_model, d_model)
-        ab = nn.Module()
-        ab.e1 = nn.Parameter(torch.randn(nhead * seq_len_src, d_model // nhead))
-        ab.e2 = nn.Parameter(torch.randn(nhead * seq_len_src, d_model // nhead))
-        self.attn_bias = ab
+        self.attn_bias = None                  # attention_bias_type=None (transformer_type 'absolute', :98-99)
+        if relative:
+            ab = nn.Module()
+            ab.e1 = nn.Parameter(torch.randn(nhead * seq_len_src, d_model // nhead))
+            ab.e2 = nn.Parameter(torch.randn(nhead * seq_len_src, d_model // nhead))
+            self.attn_bias = ab
+
+    def tables(self):
+        return (None, None) if self.attn_bias is None else (self.attn_bias.e1, self.attn_bias.e2)
 
 
-def _layer(d_model, nhead, dim_feedforward, seq_len_self, seq_len_src_cross=None, aligned=None):
+def _layer(d_model, nhead, dim_feedforward, seq_len_self, seq_len_src_cross=None, aligned=None, relative=True):
     """aligned = (num_channels_encoder, num_channels_decoder): the 'diagonal' layer (transformer_custom.py:389-479) whose cross
     term is ``cross_attn = Sequential(Linear(Ce * d, 2 d), ELU, Linear(2 d, d * Cd))`` of the aligned memory event (:428-432)."""
     m = nn.Module()
-    m.self_attn = _Attn(d_model, nhead, seq_len_self)
+    m.self_attn = _Attn(d_model, nhead, seq_len_self, relative)
     if aligned is not None:
         ce, cd = aligned
         m.cross_attn = nn.Sequential(_Linear(ce * d_model, 2 * d_model), nn.ELU(), _Linear(2 * d_model, d_model * cd))
         m.norm3 = nn.LayerNorm(d_model)
     elif seq_len_src_cross is not None:
-        m.multihead_attn = _Attn(d_model, nhead, seq_len_src_cross)
+        m.multihead_attn = _Attn(d_model, nhead, seq_len_src_cross, relative)
         m.norm3 = nn.LayerNorm(d_model)
     m.linear1 = _Linear(d_model, dim_feedforward)
     m.linear2 = _Linear(dim_feedforward, d_model)
@@ -102,8 +108,10 @@ class Decoder(nn.Module):
                  positional_embedding_size, num_channels_encoder, num_events_encoder, num_channels_decoder, num_events_decoder,
                  dropout):
         super().__init__()
-        if transformer_type != 'relative':
-            raise NotImplementedError("only transformer_type='relative' is built on the B200 path")
+        if transformer_type not in ('relative', 'absolute'):
+            raise NotImplementedError(f'transformer_type={transformer_type!r}')
+        if transformer_type == 'absolute' and cross_attention_type == 'diagonal':
+            raise NotImplementedError("the aligned layer is only used by the relative transformers (decoder.py:159-174)")
         assert encoder_attention_type in ('anticausal', 'causal', 'full')
         if cross_attention_type not in ('anticausal', 'full', 'diagonal'):
             raise NotImplementedError(f'cross_attention_type={cross_attention_type!r} (unimplemented in the reference as well, '
@@ -125,28 +133,35 @@ class Decoder(nn.Module):
         self.total_upscaling = int(np.prod(encoder.downscaler.downscale_factors))
         assert self.num_tokens_target % self.total_upscaling == 0
         assert self.num_tokens_target == num_channels_decoder * num_events_decoder
-        self.target_channel_embeddings = nn.Parameter(torch.randn((1, self.num_channels, positional_embedding_size)))
-        self.num_events_per_code = self.total_upscaling // self.num_channels
-        self.target_events_positioning_embeddings = nn.Parameter(torch.randn((1, self.num_events_per_code, positional_embedding_size)))
+        rel = transformer_type == 'relative'
+        if rel:
+            self.target_channel_embeddings = nn.Parameter(torch.randn((1, self.num_channels, positional_embedding_size)))
+            self.num_events_per_code = self.total_upscaling // self.num_channels
+            self.target_events_positioning_embeddings = nn.Parameter(torch.randn((1, self.num_events_per_code, positional_embedding_size)))
+        else:                                  # one learnt vector per absolute source / target position (decoder.py:88-102)
+            self.source_positional_embeddings = nn.Parameter(torch.randn((1, self.num_tokens_target // self.total_upscaling,
+                                                                          positional_embedding_size)))
+            self.target_positional_embeddings = nn.Parameter(torch.randn((1, self.num_tokens_target, positional_embedding_size)))
         S = num_channels_encoder * num_events_encoder
         T = num_channels_decoder * num_events_decoder
         self.seq_len_src, self.seq_len_tgt = S, T
         tr = nn.Module()
         tr.encoder = nn.Module()
-        tr.encoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, S) for _ in range(num_encoder_layers)])
+        tr.encoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, S, relative=rel) for _ in range(num_encoder_layers)])
         tr.decoder = nn.Module()
         self.num_channels_encoder, self.num_channels_decoder = num_channels_encoder, num_channels_decoder
         aligned = (num_channels_encoder, num_channels_decoder) if cross_attention_type == 'diagonal' else None
-        tr.decoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, T, S, aligned=aligned)
+        tr.decoder.layers = nn.ModuleList([_layer(d_model, n_head, dim_feedforward, T, S, aligned=aligned, relative=rel)
                                            for _ in range(num_decoder_layers)])
         self.transformer = tr
-        self.linear_target = _Linear(data_processor.embedding_size + positional_embedding_size * 2, d_model)
+        self.linear_target = _Linear(data_processor.embedding_size + positional_embedding_size * (2 if rel else 1), d_model)
         self.sos = nn.Parameter(torch.randn((1, 1, d_model)))
         q = encoder.quantizer
+        src_dim = d_model if rel else d_model - positional_embedding_size                        # :226-229
         if type(q).__name__ != 'NoQuantization':
-            self.source_embeddings = nn.Embedding(q.codebook_size ** q.num_codebooks, d_model)
+            self.source_embeddings = nn.Embedding(q.codebook_size ** q.num_codebooks, src_dim)
         else:
-            self.source_embeddings = _Linear(q.codebook_dim, d_model)
+            self.source_embeddings = _Linear(q.codebook_dim, src_dim)
 
         self.pre_softmaxes = nn.ModuleList([_Linear(d_model, n) for n in self.num_tokens_per_channel])
 
@@ -181,17 +196,17 @@ class Decoder(nn.Module):
             kv = ops.linear_fwd(x_kv, w[d:], b[d:])
             k, v, ldq, ldkv = kv, kv[:, d:], d, 2 * d
         out = torch.empty(B * Lq, d, dtype=torch.float32, device=x_q.device)
+        e1, e2 = a.tables()
         if x_kv is None and Lq <= 1024 and mask in (None, 'causal', 'anticausal'):
             # self-attention: the tiled full-sequence kernel (closed-form skewed bias = the maps for T == S, csrc/attn_long.cu)
             mode = {None: 0, 'causal': 1, 'anticausal': 2}[mask]
-            _native.call('vqcpc_attn_long_fwd_masked', _p(qkv), _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(out), None, B, Lq, H, hd,
-                         mode, ops._stream())
+            _native.call('vqcpc_attn_long_fwd_masked', _p(qkv), _p(e1), _p(e2), _p(out), None, B, Lq, H, hd, mode, ops._stream())
             return out
         if isinstance(mask, str):
             mask = _causal_mask(Lk, x_q.device) if mask == 'causal' else _anticausal_mask(Lk, x_q.device)
-        m1, m2 = device_maps(Lq, Lk, x_q.device)
-        _native.call('vqcpc_attn_map_fwd', _p(q), ldq, _p(k), _p(v), ldkv, _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(m1), _p(m2),
-                     _p(mask), _p(out), None, B, Lq, Lk, H, hd, ops._stream())
+        m1, m2 = device_maps(Lq, Lk, x_q.device) if e1 is not None else (None, None)
+        _native.call('vqcpc_attn_map_fwd', _p(q), ldq, _p(k), _p(v), ldkv, _p(e1), _p(e2), _p(m1), _p(m2), _p(mask), _p(out), None, B,
+                     Lq, Lk, H, hd, ops._stream())
         return out
 
     def _enc_layer(self, lyr, x, B, L, mask):
@@ -238,11 +253,14 @@ class Decoder(nn.Module):
         dev = self.sos.device
         d = self.d_model
         if isinstance(self.source_embeddings, nn.Embedding):
-            src = torch.nn.functional.embedding(source.to(dev).long(), self.source_embeddings.weight).reshape(-1, d)   # :440
+            src = torch.nn.functional.embedding(source.to(dev).long(), self.source_embeddings.weight)                 # :440
+            src = src.reshape(-1, src.shape[-1])
         else:
             src = ops.linear_fwd(ops._f32c(source.to(dev)).reshape(-1, source.shape[-1]), self.source_embeddings.weight,
                                  self.source_embeddings.bias)
         S = src.shape[0] // B
+        if self.transformer_type == 'absolute':                                                          # :458-461
+            src = torch.cat([src.view(B, S, -1), self.source_positional_embeddings.expand(B, S, -1)], dim=2).reshape(B * S, d)
         source_mask = None if self.encoder_attention_type == 'full' else self.encoder_attention_type    # 'causal' | 'anticausal'
         x = src.contiguous()
         for lyr in self.transformer.encoder.layers:
@@ -261,9 +279,12 @@ class Decoder(nn.Module):
         target = self.data_processor.preprocess(target)
         tgt = flatten(self.data_processor.embed(target))                                                 # (B, T, E)   :442-444
         T = tgt.size(1)
-        chan = self.target_channel_embeddings.repeat(B, T // C, 1)                                       # :451-453
-        evt = self.target_events_positioning_embeddings.repeat_interleave(C, dim=1).repeat(B, T // self.total_upscaling, 1)
-        tgt = torch.cat([tgt, chan, evt], dim=2).reshape(B * T, -1)                                      # :449-457
+        if self.transformer_type == 'absolute':
+            tgt = torch.cat([tgt, self.target_positional_embeddings.expand(B, T, -1)], dim=2).reshape(B * T, -1)      # :462-466
+        else:
+            chan = self.target_channel_embeddings.repeat(B, T // C, 1)                                   # :451-453
+            evt = self.target_events_positioning_embeddings.repeat_interleave(C, dim=1).repeat(B, T // self.total_upscaling, 1)
+            tgt = torch.cat([tgt, chan, evt], dim=2).reshape(B * T, -1)                                  # :449-457
         tgt = ops.linear_fwd(tgt.contiguous(), self.linear_target.weight, self.linear_target.bias).view(B, T, d)   # :469
         tgt = torch.cat([self.sos.expand(B, 1, d), tgt[:, :-1]], dim=1).reshape(B * T, d).contiguous()   # shift by one   :476-482
         memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None  # :487-496
@@ -383,17 +404,25 @@ class _DecodeSession:
         self.cross_add = [torch.empty(B * T, d, **f32) for _ in layers] if self.aligned else []
         kc = [torch.zeros(B * T, d, **f32) for _ in layers]
         vc = [torch.zeros(B * T, d, **f32) for _ in layers]
-        sm1, sm2 = device_maps(T, T, dev)
-        cm1, cm2 = (None, None) if self.aligned else device_maps(T, S, dev)
+        sm1, sm2 = (None, None) if dec.transformer_type == 'absolute' else device_maps(T, T, dev)
+        cm1, cm2 = (None, None) if (self.aligned or dec.transformer_type == 'absolute') else device_maps(T, S, dev)
         memory_mask = _anticausal_mask(S, dev, T) if dec.cross_attention_type == 'anticausal' else None
         tables = torch.cat([e.weight.detach() for e in dec.data_processor.embeddings], dim=0).contiguous()
         rows = [e.weight.shape[0] for e in dec.data_processor.embeddings]
         table_off = torch.tensor([sum(rows[:c]) for c in range(C)], dtype=torch.int32, device=dev)
         E = tables.shape[1]
-        pe = dec.target_channel_embeddings.shape[-1]
-        F = E + 2 * pe
-        chan = dec.target_channel_embeddings.detach().reshape(C, pe).contiguous()
-        evt = dec.target_events_positioning_embeddings.detach().reshape(-1, pe).contiguous()
+        absolute = dec.transformer_type == 'absolute'
+        pos_mode = int(absolute)
+        if absolute:                           # [embedding | positional embedding of the absolute position]
+            pe = dec.target_positional_embeddings.shape[-1]
+            F = E + pe
+            chan = dec.target_positional_embeddings.detach().reshape(T, pe).contiguous()
+            evt = chan
+        else:
+            pe = dec.target_channel_embeddings.shape[-1]
+            F = E + 2 * pe
+            chan = dec.target_channel_embeddings.detach().reshape(C, pe).contiguous()
+            evt = dec.target_events_positioning_embeddings.detach().reshape(-1, pe).contiguous()
         ff = layers[0].linear1.weight.shape[0]
         Vmax = max(dec.num_tokens_per_channel)
         self.tokens = tokens = torch.zeros(B, T, dtype=torch.int64, device=dev)
@@ -431,8 +460,9 @@ class _DecodeSession:
                     lin(x, d, a.in_proj_weight, a.in_proj_bias, None, qkv, 3 * d, 3 * d, d, sc=scale, sc_cols=d)
                 else:                                        # x = norm3 of the previous layer, applied while staging
                     ln_lin(y, layers[li - 1].norm3, x, a.in_proj_weight, a.in_proj_bias, qkv, 3 * d, 3 * d, sc=scale, sc_cols=d)
+                se1, se2 = a.tables()
                 call('vqcpc_attn_decode', _p(qkv), 3 * d, _p(qkv[:, d:]), _p(qkv[:, 2 * d:]), 3 * d, _p(kc[li]), _p(vc[li]), d, T,
-                     _p(a.attn_bias.e1), _p(a.attn_bias.e2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
+                     _p(se1), _p(se2), _p(sm1), _p(sm2), None, T, _p(pos), 1, _p(att), d, B, H, hd, st)
                 lin(att, d, a.out_proj.weight, a.out_proj.bias, x, y, d, d, d)
                 if self.aligned:                             # y2 = norm1(y) + the aligned memory term of this position
                     call('vqcpc_decode_ln_add', _p(y), _p(l.norm1.weight), _p(l.norm1.bias), float(l.norm1.eps),
@@ -442,8 +472,9 @@ class _DecodeSession:
                     a = l.multihead_attn
                     ln_lin(y, l.norm1, x1, a.in_proj_weight[:d], a.in_proj_bias[:d], qc, d, d, sc=scale, sc_cols=d)
                     ckv = self.cross_kv[li]
-                    call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(ckv), _p(ckv[:, d:]), 2 * d, S, _p(a.attn_bias.e1),
-                         _p(a.attn_bias.e2), _p(cm1), _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd, st)
+                    ce1, ce2 = a.tables()
+                    call('vqcpc_attn_decode', _p(qc), d, None, None, 0, _p(ckv), _p(ckv[:, d:]), 2 * d, S, _p(ce1), _p(ce2), _p(cm1),
+                         _p(cm2), _p(memory_mask), S, _p(pos), 0, _p(att), d, B, H, hd, st)
                     lin(att, d, a.out_proj.weight, a.out_proj.bias, x1, y, d, d, d)
                     y_mid = y
                 ln_lin(y_mid, l.norm2, x2, l.linear1.weight, l.linear1.bias, hmid, ff, ff, relu=1)
@@ -452,7 +483,8 @@ class _DecodeSession:
             ln_lin(y, layers[-1].norm3, None, dec.pre_softmaxes[c].weight, head_bias[c], logits, Vmax, V)
             # draw the token, write the feature row of the next position, advance the position
             call('vqcpc_decode_sample_embed', _p(logits), Vmax, V, float(temperature), int(top_k), float(top_p), _p(u), B, _p(tokens), T,
-                 _p(pos), int(bool(greedy)), B, _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), C, up, E, pe, _p(done), st)
+                 _p(pos), int(bool(greedy)), B, _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), C, up, E, pe, _p(done),
+                 pos_mode, st)
 
         def event():
             for c in range(C):

@@ -183,7 +183,8 @@ def get_auxiliary_decoder(auxiliary_decoder_type, auxiliary_decoder_kwargs):
                                     num_tokens_bottleneck=k['num_tokens_bottleneck'], dropout=k['dropout'])
 
 
-_DECODER_TYPES = {   # getters.py:309-393: decoder_type -> (encoder attention, cross attention) of the relative transformer
+_DECODER_TYPES = {   # getters.py:290-393: decoder_type -> (encoder attention, cross attention); 'transformer' = absolute positions
+    'transformer': ('anticausal', 'full'),
     'transformer_relative': ('anticausal', 'anticausal'),
     'transformer_relative_fullCross': ('anticausal', 'full'),
     'transformer_relative_diagonal': ('anticausal', 'diagonal'),
@@ -192,11 +193,11 @@ _DECODER_TYPES = {   # getters.py:309-393: decoder_type -> (encoder attention, c
 
 
 def get_decoder(model_dir, dataloader_generator, data_processor, encoder, decoder_type, decoder_kwargs):
-    """getters.py:274-395.  ``decoder_type='transformer'`` (absolute positional embeddings) is not built."""
+    """getters.py:274-395."""
     import numpy as np
     from .decoders.decoder import Decoder
     if decoder_type not in _DECODER_TYPES:
-        raise NotImplementedError(f'decoder_type={decoder_type!r}: the relative decoders {sorted(_DECODER_TYPES)} are built')
+        raise NotImplementedError(f'decoder_type={decoder_type!r}: one of {sorted(_DECODER_TYPES)}')
     enc_att, cross_att = _DECODER_TYPES[decoder_type]
     num_channels_decoder, num_events_decoder = data_processor.num_channels, data_processor.num_events
     num_channels_encoder = 1
@@ -204,7 +205,7 @@ def get_decoder(model_dir, dataloader_generator, data_processor, encoder, decode
                              (np.prod(encoder.downscaler.downscale_factors) * num_channels_encoder))
     k = decoder_kwargs
     return Decoder(model_dir=model_dir, dataloader_generator=dataloader_generator, data_processor=data_processor, encoder=encoder,
-                   transformer_type='relative', encoder_attention_type=enc_att, cross_attention_type=cross_att, d_model=k['d_model'],
+                   transformer_type='absolute' if decoder_type == 'transformer' else 'relative', encoder_attention_type=enc_att, cross_attention_type=cross_att, d_model=k['d_model'],
                    num_encoder_layers=k['num_encoder_layers'], num_decoder_layers=k['num_decoder_layers'], n_head=k['n_head'],
                    dim_feedforward=k['dim_feedforward'], dropout=k['dropout'],
                    positional_embedding_size=k['positional_embedding_size'], num_channels_encoder=num_channels_encoder,

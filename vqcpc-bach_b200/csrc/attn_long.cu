@@ -74,7 +74,7 @@ attn_long_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ e1
     float* s2 = s1 + (KT + R - 1) * PADW;           // [KT + R - 1][PADW]  e2 slab
     const int ii = threadIdx.x >> 5, jj = threadIdx.x & 31;
     for (int j0 = jlo; j0 < jhi; j0 += KT) {
-      const bool need1 = j0 <= i0 + R - 1, need2 = j0 + KT - 1 > i0;
+      const bool need1 = e1 != nullptr && j0 <= i0 + R - 1, need2 = e2 != nullptr && j0 + KT - 1 > i0;   // NULL tables: no bias
       const int b1 = (L - 1 - i0 + j0) - (R - 1), b2 = (j0 - i0) - (R - 1);      // table row of slab row 0
       __syncthreads();
       for (int t = threadIdx.x; t < KT * (HD / 4); t += THREADS) {

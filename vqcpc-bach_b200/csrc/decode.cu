@@ -46,20 +46,22 @@ __device__ __forceinline__ int ld_pos(const int* p) { return __ldcg(p); }
 __global__ void decode_features_kernel(const int64_t* __restrict__ tokens, const int* __restrict__ pos,
                                        const float* __restrict__ tables, const int* __restrict__ table_off,
                                        const float* __restrict__ chan, const float* __restrict__ evt, float* __restrict__ feat,
-                                       int T, int C, int up, int E, int pe) {
+                                       int T, int C, int up, int E, int pe, int pos_mode) {
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x, i = ld_pos(pos), F = E + 2 * pe;
+  const int b = blockIdx.x, i = ld_pos(pos), F = pos_mode ? E + pe : E + 2 * pe;
   float* f = feat + (size_t)b * F;
   if (i <= 0 || i >= T + 1) {
     for (int c = threadIdx.x; c < F; c += blockDim.x) f[c] = 0.f;
     return;
   }
-  const int t = i - 1, ch = t % C, ev = (t % up) / C;
+  // pos_mode 0: [embedding | channel embedding | event-in-code embedding] (relative transformer, decoder.py:449-457);
+  // pos_mode 1: [embedding | positional embedding of the absolute position] (chan = the (T, pe) table, decoder.py:458-466)
+  const int t = i - 1, ch = t % C, ev = (t % up) / C, pidx = pos_mode ? t : ch;
   const int64_t tok = __ldcg(tokens + (size_t)b * T + t);
   const float* row = tables + ((size_t)table_off[ch] + tok) * E;
   for (int c = threadIdx.x; c < F; c += blockDim.x)
-    f[c] = c < E ? row[c] : (c < E + pe ? chan[ch * pe + (c - E)] : evt[ev * pe + (c - E - pe)]);
+    f[c] = c < E ? row[c] : (c < E + pe ? chan[pidx * pe + (c - E)] : evt[ev * pe + (c - E - pe)]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -638,7 +640,8 @@ __global__ void __launch_bounds__(256)
 sample_embed_advance_kernel(const float* __restrict__ logits, int ld, int V, float temperature, int top_k, float top_p,
                             const double* __restrict__ u, int u_stride, int64_t* __restrict__ tokens, int T, int* pos, int greedy,
                             const float* __restrict__ tables, const int* __restrict__ table_off, const float* __restrict__ chan,
-                            const float* __restrict__ evt, float* __restrict__ feat, int C, int up, int E, int pe, int* done) {
+                            const float* __restrict__ evt, float* __restrict__ feat, int C, int up, int E, int pe, int* done,
+                            int pos_mode) {
   extern __shared__ __align__(16) float smf[];
   pdl_launch_dependents();
   pdl_wait();
@@ -646,10 +649,10 @@ sample_embed_advance_kernel(const float* __restrict__ logits, int ld, int V, flo
   if (i >= 0 && i < T) {
     const int tok = sample_row(logits + (size_t)b * ld, V, temperature, top_k, top_p, greedy ? 0.0 : u[(size_t)i * u_stride + b], greedy, smf);
     if (threadIdx.x == 0) tokens[(size_t)b * T + i] = tok;
-    const int ch = i % C, ev = (i % up) / C, F = E + 2 * pe;
+    const int ch = i % C, ev = (i % up) / C, F = pos_mode ? E + pe : E + 2 * pe, pidx = pos_mode ? i : ch;
     const float* row = tables + ((size_t)table_off[ch] + tok) * E;
     for (int c = threadIdx.x; c < F; c += blockDim.x)
-      feat[(size_t)b * F + c] = c < E ? row[c] : (c < E + pe ? chan[ch * pe + (c - E)] : evt[ev * pe + (c - E - pe)]);
+      feat[(size_t)b * F + c] = c < E ? row[c] : (c < E + pe ? chan[pidx * pe + (c - E)] : evt[ev * pe + (c - E - pe)]);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -752,11 +755,11 @@ VQ_API int vqcpc_decode_set_pdl(int on) {
 }
 
 VQ_API int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* tables, const int* table_off, const float* chan,
-                                 const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe,
+                                 const float* evt, float* feat, int B, int T, int C, int total_upscaling, int E, int pe, int pos_mode,
                                  void* stream) {
   VQ_CHECK_ARG(B >= 1 && T >= 1 && C >= 1 && total_upscaling % C == 0 && E >= 1 && pe >= 0, "decode_features: bad shape");
   VQ_CUDA_CALL(launch_step(decode_features_kernel, dim3(B), dim3(64), 0, vq_stream(stream), 0, tokens, pos, tables, table_off, chan, evt,
-                           feat, T, C, total_upscaling, E, pe));
+                           feat, T, C, total_upscaling, E, pe, pos_mode));
   return VQ_OK;
 }
 
@@ -906,7 +909,7 @@ VQ_API int vqcpc_sample_step(const float* logits, int ld, int V, float temperatu
 VQ_API int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float temperature, int top_k, float top_p, const double* u,
                                      int u_stride, int64_t* tokens, int T, int* pos, int greedy, int B, const float* tables,
                                      const int* table_off, const float* chan, const float* evt, float* feat, int C,
-                                     int total_upscaling, int E, int pe, int* done, void* stream) {
+                                     int total_upscaling, int E, int pe, int* done, int pos_mode, void* stream) {
   VQ_CHECK_ARG(V >= 1 && V <= 4096 && B >= 1 && temperature > 0.f, "decode_sample_embed: bad arguments V=%d B=%d", V, B);
   VQ_CHECK_ARG(greedy || u != nullptr, "decode_sample_embed: uniforms missing");
   VQ_CHECK_ARG(pos != nullptr && done != nullptr, "decode_sample_embed: position / counter pointer missing");
@@ -919,7 +922,7 @@ VQ_API int vqcpc_decode_sample_embed(const float* logits, int ld, int V, float t
   }
   VQ_CUDA_CALL(launch_step(sample_embed_advance_kernel, dim3(B), dim3(256), smem, vq_stream(stream), 0, logits, ld, V, temperature, top_k,
                            top_p, u, u_stride, tokens, T, pos, greedy, tables, table_off, chan, evt, feat, C, total_upscaling, E, pe,
-                           done));
+                           done, pos_mode));
   return VQ_OK;
 }
 
