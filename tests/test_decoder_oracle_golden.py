@@ -67,3 +67,47 @@ def test_relative_bias_rows_only_read_their_own_query(T, S):
     for m in (m1, m2):
         v = m >= 0
         assert bool((m[v] // S == rows.expand(T, S)[v]).all())
+
+
+@pytest.mark.parametrize('case', ['ac_ac', 'c_full', 'ac_diag', 'diag_noq', 'absolute'])
+def test_product_decoder_state_dict_is_the_references(case):
+    """Host side only: the product ``Decoder`` exposes exactly the parameter names and shapes of the reference module (recorded
+    by oracle/make_golden_decoder.py from the live reference), so its checkpoints load in either direction."""
+    import types
+    from VQCPCB.data_processor.bach_data_processor import BachDataProcessor
+    from VQCPCB.decoders.decoder import Decoder, top_k_top_p_filtering
+    rec = torch.load(GOLD)[case]
+    c = rec['cfg']
+
+    class NoQuantization:
+        codebook_dim = 3
+
+    enc = torch.nn.Module()
+    enc.downscaler = types.SimpleNamespace(downscale_factors=[4, 4])
+    enc.quantizer = NoQuantization() if c.get('no_quantization') else types.SimpleNamespace(codebook_size=c['codebook_size'],
+                                                                                            num_codebooks=1, codebook_dim=3)
+    C = len(c['vocab'])
+    dec = Decoder(model_dir='/tmp/x', dataloader_generator=None, data_processor=BachDataProcessor(32, c['num_events'], list(c['vocab'])),
+                  encoder=enc, transformer_type=c.get('transformer_type', 'relative'), encoder_attention_type=c['encoder_attention_type'],
+                  cross_attention_type=c['cross_attention_type'], d_model=c['d_model'], num_encoder_layers=c['num_encoder_layers'],
+                  num_decoder_layers=c['num_decoder_layers'], n_head=c['n_head'], dim_feedforward=c['dim_feedforward'],
+                  positional_embedding_size=8, num_channels_encoder=1, num_events_encoder=c['num_events'] * C // 16,
+                  num_channels_decoder=C, num_events_decoder=c['num_events'], dropout=0.0)
+    mine = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
+    ref = {k: tuple(v) for k, v in rec['shapes'].items()}
+    assert mine == ref, (sorted(set(mine) ^ set(ref))[:8])
+    # the batched filter of the full-recompute path equals the reference's per-row function restated in the oracle
+    g = torch.Generator().manual_seed(1)
+    lg = torch.randn(6, 40, generator=g) * 3
+    for top_k, top_p in [(0, 0.8), (7, 0.0), (5, 0.9)]:
+        want = torch.stack([D.top_k_top_p_filtering(r, top_k=top_k, top_p=top_p) for r in lg])
+        assert torch.equal(top_k_top_p_filtering(lg, top_k=top_k, top_p=top_p), want)
+
+
+def test_get_decoder_types_follow_the_reference_table():
+    """getters.py:290-393 of the reference: decoder_type -> (transformer type, encoder attention, cross attention)."""
+    from VQCPCB.getters import _DECODER_TYPES
+    assert _DECODER_TYPES == {'transformer': ('anticausal', 'full'), 'transformer_relative': ('anticausal', 'anticausal'),
+                              'transformer_relative_fullCross': ('anticausal', 'full'),
+                              'transformer_relative_diagonal': ('anticausal', 'diagonal'),
+                              'transformer_relative_full': ('full', 'full')}
