@@ -4,7 +4,7 @@
 
 Builds the encoder named by ``config['config_encoder']`` (default: the repo's ``encoder_vqcpc.py``), the decoder of
 ``config['decoder_type']``, optionally loads their checkpoints (``-l``; ``-o`` = over-fitted decoder weights) and generates
-``--num_examples`` batches with ``Decoder.generate`` (key / value cached, CUDA graph per event, sampling on the device).  Tokens
+``--num_examples`` batches with ``Decoder.generate`` (``--eval_batches N`` first prints the teacher-forced validation loss) (key / value cached, CUDA graph per event, sampling on the device).  Tokens
 are written as ``generation_<i>.pt`` = {'original', 'generated', 'recoding'} in the model directory; score writing
 (music21) and ``-t`` (decoder training), ``-r`` (reharmonisation) are outside the built path and say so."""
 import importlib.util
@@ -39,7 +39,8 @@ def _load_config(path):
 @click.option('--temperature', type=float, default=0.95)
 @click.option('--top_p', type=float, default=0.8)
 @click.option('--top_k', type=int, default=0)
-def main(train, load, overfitted, config, reharmonization, num_examples, batch_size, temperature, top_p, top_k):
+@click.option('--eval_batches', type=int, default=0, help='teacher-forced validation loss over this many batches')
+def main(train, load, overfitted, config, reharmonization, num_examples, batch_size, temperature, top_p, top_k, eval_batches):
     if train or reharmonization:
         raise NotImplementedError('decoder training / reharmonisation are outside the built path (inference: forward + generate)')
     if not torch.cuda.is_available():
@@ -72,6 +73,9 @@ def main(train, load, overfitted, config, reharmonization, num_examples, batch_s
     if load:
         decoder.load(early_stopped=not overfitted, device=device)
     os.makedirs(model_dir, exist_ok=True)
+    if eval_batches > 0:
+        _, val, _ = dataloader_generator.dataloaders(batch_size=config['batch_size'])
+        print('validation:', decoder.epoch(val, train=False, num_batches=eval_batches))
     for i in range(num_examples):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -277,10 +277,14 @@ def test_main_decoder_generates_end_to_end(decoder_type, tmp_path):
     env = dict(os.environ, VQCPC_BLOCKS='2', VQCPC_CODEBOOK='16', VQCPC_DECODER_BEATS='4', VQCPC_DECODER_TYPE=decoder_type,
                VQCPC_DATASET='synthetic')
     cfg = os.path.join(root, 'vqcpc-bach_b200', 'VQCPCB', 'configs', 'decoder_relative.py')
-    r = subprocess.run([sys.executable, os.path.join(root, 'main_decoder.py'), '-c', cfg, '--num_examples', '1', '--batch_size', '2'],
+    r = subprocess.run([sys.executable, os.path.join(root, 'main_decoder.py'), '-c', cfg, '--num_examples', '1', '--batch_size', '2',
+                        '--eval_batches', '2'],
                        cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert 'tokens/s' in r.stdout
+    import re
+    m = re.search(r"validation: \{'loss': ([0-9.eE+-]+)\}", r.stdout)
+    assert m and 0 < float(m.group(1)) < 100, r.stdout[-500:]
     models = os.listdir(tmp_path / 'models')
     assert len(models) == 1 and models[0].startswith('decoder_relative_')
     rec = torch.load(tmp_path / 'models' / models[0] / 'generation_0.pt')

@@ -302,6 +302,24 @@ class Decoder(nn.Module):
         loss = loss.mean()
         return {'loss': loss, 'weights_per_category': weights_per_category, 'monitored_quantities': {'loss': loss.item()}}
 
+    @torch.no_grad()
+    def epoch(self, data_loader, train=False, num_batches=None):
+        """Evaluation pass of decoder.py:310-370 (``train=False``): encode every window, teacher-forced forward, mean of the
+        monitored quantities.  The training branch (backward through the encoder-decoder transformer) is not built."""
+        if train:
+            raise NotImplementedError('decoder training is outside the built path (inference: forward, epoch(train=False), generate)')
+        from itertools import islice
+        self.eval()
+        means, n = None, 0
+        for tensor_dict in islice(data_loader, num_batches):
+            x = tensor_dict['x']
+            zs, encoding_indices, _ = self.encoder(x)
+            codes = zs if encoding_indices is None else self.encoder.merge_codes(encoding_indices)
+            mq = self.forward(codes, x)['monitored_quantities']
+            means = dict(mq) if means is None else {k: v + means[k] for k, v in mq.items()}
+            n += 1
+        return {k: v / n for k, v in means.items()}
+
     def init_generation(self, num_events):
         return torch.zeros(1, num_events, self.num_channels, dtype=torch.int64, device=self.sos.device)   # :724-727
 
