@@ -320,3 +320,33 @@ def test_attn_long_masked_vs_fp64(L, mode):
     torch.cuda.synchronize()
     assert rel_err(out, ref) < 3e-6
     assert rel_err(probs, a.reshape(P, H, L, L)) < 3e-6
+
+
+@pytest.mark.parametrize('case', ['ac_ac', 'ac_diag', 'absolute'])
+def test_long_generation_cached_equals_window_recompute(case):
+    """generate_from_code_long (decoder.py:729-829): a code sequence longer than the model window, decoded code by code from the
+    sliding window.  The cached path (one teacher-forced forward per code refills the key / value cache, then incremental
+    steps) against the reference's schedule (a full forward of the window per token), greedy and sampled from the same uniforms;
+    and the window arithmetic against the reference's table of cases."""
+    from VQCPCB import ops
+    rec = torch.load(GOLD)[case]
+    prm = D.make_decoder_params(rec['shapes'], seed=0)
+    ops.set_gemm_mode('fp32')
+    try:
+        dec = _build(rec['cfg'])
+        dec.load_state_dict({k: v.cuda() for k, v in prm.items()}, strict=True)
+        ops.bump_weight_version()
+        assert [dec.compute_start_end_times(t, 9, 4) for t in range(9)] == [
+            (0, 4, 0), (0, 4, 1), (0, 4, 2), (1, 5, 2), (2, 6, 2), (3, 7, 2), (4, 8, 2), (5, 9, 2), (5, 9, 3)]
+        g = torch.Generator().manual_seed(5)
+        codes = torch.randint(0, rec['cfg']['codebook_size'], (2, 9), generator=g).cuda()
+        full = dec.generate_from_code_long(codes, greedy=True, kv_cache=False)
+        cached = dec.generate_from_code_long(codes, greedy=True)
+        assert full.shape == (2, 36, 4) and torch.equal(full, cached)
+        u = torch.rand(5 * 16, 2, dtype=torch.float64, generator=g)
+        a = dec.generate_from_code_long(codes, temperature=0.9, top_p=0.9, code_index_start=2, code_index_end=7, uniforms=u,
+                                        kv_cache=False)
+        b = dec.generate_from_code_long(codes, temperature=0.9, top_p=0.9, code_index_start=2, code_index_end=7, uniforms=u)
+        assert a.shape == (2, 20, 4) and torch.equal(a, b)
+    finally:
+        ops.set_gemm_mode('bf16x3')

@@ -70,6 +70,7 @@ def main():
     ap.add_argument('--full-tokens', type=int, default=32)
     ap.add_argument('--cpu-forwards', type=int, default=2)
     ap.add_argument('--attn-split', type=int, default=0, help='keys split over a cluster of this many CTAs (0 = product heuristic)')
+    ap.add_argument('--long-codes', type=int, default=0, help='also time generate_from_code_long over this many codes')
     ap.add_argument('--cross', default='anticausal', choices=['anticausal', 'full', 'diagonal'])
     ap.add_argument('--pdl', type=int, default=-1, help='programmatic dependent launch between the step kernels: 0 / 1 (A/B), -1 = the product heuristic')
     a = ap.parse_args()
@@ -145,6 +146,23 @@ def main():
                parity=dict(greedy_tokens_equal=same, greedy_tokens_compared=n_cmp * B, logits_rel_err_vs_oracle=errs),
                config=dict(cross_attention_type=a.cross, workload='decoder_relative generation, 1024 tokens (256 events x 4 voices) from 64 codes, d=512, '
                                     '8 heads, 3+3 layers, FFN 1024, top-p 0.9', data='synthetic codes, random-init weights'))
+    if a.long_codes > 0:
+        # sliding-window decoding of a code sequence longer than the window (decoder.py:729-829)
+        lc = torch.randint(0, CFG['codebook_size'], (B, a.long_codes), generator=g).cuda()
+        dec.generate_from_code_long(lc[:, :S + 2], temperature=1.0, top_p=0.9, code_index_start=0, code_index_end=2)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        toks_long = dec.generate_from_code_long(lc, temperature=1.0, top_p=0.9)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_ref = 2
+        t0 = time.perf_counter()
+        dec.generate_from_code_long(lc, temperature=1.0, top_p=0.9, code_index_start=S, code_index_end=S + n_ref, kv_cache=False)
+        torch.cuda.synchronize()
+        dt_ref = (time.perf_counter() - t0) / (n_ref * 16)
+        out['long_generation'] = dict(codes=a.long_codes, tokens_per_sequence=toks_long.shape[1] * 4, seconds=dt,
+                                      tokens_per_sec=toks_long.numel() / dt, ms_per_code=dt / a.long_codes * 1e3,
+                                      window_recompute=dict(ms_per_token=dt_ref * 1e3, tokens_per_sec=B / dt_ref, codes_timed=n_ref))
     print(json.dumps(out))
 
 

@@ -183,7 +183,7 @@ class Decoder(nn.Module):
         ops.bump_weight_version()
 
     # ---- one attention block: multihead_attention_custom.py:154-353 (self: :168-171, encoder-decoder: :173-196) ----------------
-    def _attention(self, a, x_q, x_kv, B, Lq, Lk, mask):
+    def _attention(self, a, x_q, x_kv, B, Lq, Lk, mask, kv_sink=None):
         d, H = self.d_model, self.n_head
         hd = d // H
         scale = float(hd) ** -0.5
@@ -191,6 +191,9 @@ class Decoder(nn.Module):
         if x_kv is None:                      # self-attention: one fused projection, q third scaled after the bias (:247)
             qkv = ops.linear_fwd(x_q, w, b, scale_cols=(scale, d))
             q, k, v, ldq, ldkv = qkv, qkv[:, d:], qkv[:, 2 * d:], 3 * d, 3 * d
+            if kv_sink is not None:               # prefill of the generation cache (generate_from_code_long)
+                kv_sink[0].copy_(k[:, :d])
+                kv_sink[1].copy_(v[:, :d])
         else:                                 # q from the target, k / v from the memory through slices of the same matrix
             q = ops.linear_fwd(x_q, w[:d], b[:d], scale_cols=(scale, d))
             kv = ops.linear_fwd(x_kv, w[d:], b[d:])
@@ -230,10 +233,10 @@ class Decoder(nn.Module):
         rep = (T // cd) // em
         return o.unsqueeze(2).expand(B, em, rep, cd, d).reshape(B * T, d).contiguous()
 
-    def _dec_layer(self, lyr, x, memory, B, T, S, tgt_mask, memory_mask):
+    def _dec_layer(self, lyr, x, memory, B, T, S, tgt_mask, memory_mask, kv_sink=None):
         """transformer_custom.py:355-384: self-attention, encoder-decoder attention (or the aligned MLP term, :389-479),
         feed-forward, three post-LNs."""
-        o = self._attention(lyr.self_attn, x, None, B, T, T, tgt_mask)
+        o = self._attention(lyr.self_attn, x, None, B, T, T, tgt_mask, kv_sink=kv_sink)
         y = ops.linear_fwd(o, lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias, residual=x)
         x = ops.layernorm_fwd(y, lyr.norm1.weight, lyr.norm1.bias)[0]
         if self.cross_attention_type == 'diagonal':
@@ -272,10 +275,13 @@ class Decoder(nn.Module):
         """source: code indices (batch, S) (or (batch, S, codebook_dim) without quantization); target: tokens (batch, num_events,
         num_channels).  Returns the reference's dict: loss, weights_per_category (list of (batch, num_events, vocab_c)),
         monitored_quantities.  decoder.py:431-543."""
-        B = source.size(0)
+        memory, S = self._encode_memory(source)
+        return self._forward_from_memory(memory, S, target)
+
+    def _forward_from_memory(self, memory, S, target, kv_sinks=None, want_loss=True):
+        B = target.size(0)
         dev = self.sos.device
         d, C = self.d_model, self.num_channels
-        memory, S = self._encode_memory(source)
         target = self.data_processor.preprocess(target)
         tgt = flatten(self.data_processor.embed(target))                                                 # (B, T, E)   :442-444
         T = tgt.size(1)
@@ -290,8 +296,10 @@ class Decoder(nn.Module):
         memory_mask = _anticausal_mask(S, dev, T) if self.cross_attention_type == 'anticausal' else None  # :487-496
         target_mask = 'causal'                                                                           # :507
         y = tgt
-        for lyr in self.transformer.decoder.layers:
-            y = self._dec_layer(lyr, y, memory, B, T, S, target_mask, memory_mask)
+        for li, lyr in enumerate(self.transformer.decoder.layers):
+            y = self._dec_layer(lyr, y, memory, B, T, S, target_mask, memory_mask, kv_sink=None if kv_sinks is None else kv_sinks[li])
+        if not want_loss:
+            return None
         out = y.view(B * (T // C), C * d)
         weights_per_category = [ops.linear_fwd(out[:, c * d:(c + 1) * d], ps.weight, ps.bias).view(B, T // C, -1)
                                 for c, ps in enumerate(self.pre_softmaxes)]                              # :519-526
@@ -319,6 +327,83 @@ class Decoder(nn.Module):
             means = dict(mq) if means is None else {k: v + means[k] for k, v in mq.items()}
             n += 1
         return {k: v / n for k, v in means.items()}
+
+    def compute_start_end_times(self, t, num_blocks, num_blocks_model):
+        """decoder.py:831-854: the window of ``num_blocks_model`` codes used for code t of a sequence of ``num_blocks`` codes and the
+        position of t inside it (centred except near the two ends)."""
+        half = num_blocks_model // 2
+        if half <= t < num_blocks - half:
+            t_relative = half
+        elif t < half:
+            t_relative = t
+        else:
+            t_relative = num_blocks_model - (num_blocks - t)
+        t_begin = min(max(0, t - half), num_blocks - num_blocks_model)
+        return t_begin, t_begin + num_blocks_model, t_relative
+
+    def init_generation_chorale(self, num_events, start_index):
+        """decoder.py:1054-1062: PAD everywhere, START at event start_index - 1 (symbols from the dataset's dictionaries; zeros when
+        the loader has none, e.g. the synthetic one)."""
+        ds = getattr(self.dataloader_generator, 'dataset', None)
+        dicts = getattr(ds, 'note2index_dicts', None)
+        x = torch.zeros(1, num_events, self.num_channels, dtype=torch.int64, device=self.sos.device)
+        if dicts is not None and all('XX' in d_ and 'START' in d_ for d_ in dicts):
+            x[:] = torch.tensor([d_['XX'] for d_ in dicts], device=x.device)
+            if start_index >= 1:
+                x[0, start_index - 1] = torch.tensor([d_['START'] for d_ in dicts], device=x.device)
+        return x
+
+    @torch.no_grad()
+    def generate_from_code_long(self, encoding_indices, temperature=1.0, top_k=0, top_p=1., num_decodings=1, code_index_start=None,
+                                code_index_end=None, greedy=False, kv_cache=True, uniforms=None, generator=None, init_chorale=None):
+        """decoder.py:729-829 without the score writing: decode a code sequence LONGER than the model's window, code by code, each
+        from the window ``compute_start_end_times`` centres on it.  Returns tokens (batch * num_decodings, events, channels) of
+        the codes [code_index_start, code_index_end).
+
+        The reference runs one full forward of the window per token.  Here (``kv_cache=True``) the window is fixed for the
+        ``total_upscaling`` tokens of a code, so per code ONE teacher-forced forward of the window refills the key / value cache
+        (its QKV products are the cache rows) and the code's tokens are generated incrementally from it (csrc/decode.cu).
+        ``uniforms``: (tokens generated, batch) float64, consumed in generation order like the reference's ``np.random.choice``."""
+        self.eval()
+        dev = self.sos.device
+        size_encoding = encoding_indices.size(1)
+        up, C = self.total_upscaling, self.num_channels
+        epc = up // C                                        # events per code
+        num_codes_model = self.num_tokens_target // up
+        code_index_start = 0 if code_index_start is None else code_index_start
+        code_index_end = size_encoding if code_index_end is None else code_index_end
+        assert size_encoding >= num_codes_model and 0 <= code_index_start < code_index_end <= size_encoding
+        codes = encoding_indices.to(dev).repeat_interleave(num_decodings, dim=0)
+        B = codes.size(0)
+        assert B <= 16 or not kv_cache, 'at most 16 sequences per call on the cached path'
+        chorale = (self.init_generation_chorale(size_encoding * epc, code_index_start * epc) if init_chorale is None
+                   else init_chorale.to(dev).long()).repeat(B, 1, 1).contiguous()
+        n_tok = (code_index_end - code_index_start) * up
+        if uniforms is None and not greedy:
+            uniforms = torch.rand(n_tok, B, dtype=torch.float64, device=dev, generator=generator)
+        u = None if uniforms is None else torch.as_tensor(uniforms, dtype=torch.float64).to(dev)
+        sess = self._decode_session(B, temperature, top_k, top_p, greedy, None, True) if kv_cache else None
+        done = 0
+        for code_index in range(code_index_start, code_index_end):
+            t_begin, t_end, t_rel = self.compute_start_end_times(code_index, size_encoding, num_codes_model)
+            win_codes = codes[:, t_begin:t_end]
+            window = chorale[:, t_begin * epc:t_end * epc]
+            p0 = t_rel * up
+            if kv_cache:
+                new = sess.run_window(win_codes, window, p0, up, None if u is None else u[done:done + up])
+                window[:, t_rel * epc:(t_rel + 1) * epc] = new.view(B, epc, C)
+            else:
+                zero = torch.zeros(1, dtype=torch.int32, device=dev)
+                for k in range(up):                          # the reference's schedule: a full forward of the window per token
+                    e, c = divmod(p0 + k, C)
+                    logits = self.forward(win_codes, window)['weights_per_category'][c][:, e, :].contiguous()
+                    V = logits.shape[1]
+                    drawn = torch.empty(B, 1, dtype=torch.int64, device=dev)
+                    _native.call('vqcpc_sample_step', _p(logits), V, V, float(temperature), int(top_k), float(top_p),
+                                 None if u is None else _p(u[done + k]), B, _p(drawn), 1, _p(zero), int(bool(greedy)), B, ops._stream())
+                    window[:, e, c] = drawn[:, 0]
+            done += up
+        return chorale[:, code_index_start * epc:code_index_end * epc]
 
     def init_generation(self, num_events):
         return torch.zeros(1, num_events, self.num_channels, dtype=torch.int64, device=self.sos.device)   # :724-727
@@ -358,12 +443,7 @@ class Decoder(nn.Module):
                 x[:, event_index, channel_index] = new
         return x
 
-    def _generate_cached(self, codes, temperature, top_k, top_p, generator, greedy, uniforms, use_graph, exclude):
-        """<= 16 sequences through the incremental path.  The buffers, the launch sequence and its CUDA graph live in a
-        ``_DecodeSession`` cached per (batch, sampling settings): a later call only refreshes the memory keys / values and the
-        uniforms and replays."""
-        dev = self.sos.device
-        B, T = codes.size(0), self.num_tokens_target
+    def _decode_session(self, B, temperature, top_k, top_p, greedy, exclude, use_graph):
         ex_key = None if not exclude else tuple(sorted((c, tuple(sorted(v))) for c, v in exclude.items()))
         key = (B, float(temperature), int(top_k), float(top_p), bool(greedy), ex_key, bool(use_graph), self.sos.data_ptr(),
                ops.weight_version())
@@ -372,11 +452,19 @@ class Decoder(nn.Module):
             if len(cache) >= 4:
                 cache.clear()
             cache[key] = _DecodeSession(self, B, temperature, top_k, top_p, greedy, exclude, use_graph)
+        return cache[key]
+
+    def _generate_cached(self, codes, temperature, top_k, top_p, generator, greedy, uniforms, use_graph, exclude):
+        """<= 16 sequences through the incremental path.  The buffers, the launch sequence and its CUDA graph live in a
+        ``_DecodeSession`` cached per (batch, sampling settings): a later call only refreshes the memory keys / values and the
+        uniforms and replays."""
+        dev = self.sos.device
+        B, T = codes.size(0), self.num_tokens_target
+        sess = self._decode_session(B, temperature, top_k, top_p, greedy, exclude, use_graph)
         if uniforms is None:
             uniforms = torch.rand(T, B, dtype=torch.float64, device=dev, generator=generator)
         u = torch.as_tensor(uniforms, dtype=torch.float64).to(dev)
         assert u.shape == (T, B)
-        sess = cache[key]
         tokens = sess.run(codes, u)
         self.last_generation_launches = sess.launches_per_window
         return tokens
@@ -508,6 +596,11 @@ class _DecodeSession:
             for c in range(C):
                 step(c)
 
+        def features_now():                                  # feature row of the CURRENT position (a window entered mid-way)
+            call('vqcpc_decode_features', _p(tokens), _p(pos), _p(tables), _p(table_off), _p(chan), _p(evt), _p(feat), B, T, C, up, E,
+                 pe, pos_mode, ops._stream())
+
+        self._features_now = features_now
         self.event = event
         self.graph = None
         self.launches_per_window = T * (3 + (6 if self.aligned else 8) * len(layers))
@@ -518,6 +611,15 @@ class _DecodeSession:
         # the early-scheduled successors take SM slots from the attention waves); VQCPC_DECODE_PDL=0/1 overrides
         pdl = os.environ.get('VQCPC_DECODE_PDL')
         _native.call('vqcpc_decode_set_pdl', int(pdl) if pdl is not None else int(self.B <= 4))
+        self._project_memory(codes)
+        self.u.copy_(u)
+        self.tokens.zero_()
+        self.pos.zero_()
+        self._events(self.Ev)
+        return self.tokens.view(self.B, self.Ev, self.C).clone()
+
+    def _project_memory(self, codes):
+        dec, d = self.dec, self.dec.d_model
         memory, S = dec._encode_memory(codes)
         assert S == self.S
         for ckv, l in zip(self.cross_kv, self.layers):      # keys / values of the memory (multihead_attention_custom.py:173-196)
@@ -525,22 +627,42 @@ class _DecodeSession:
             ops.linear_fwd(memory, a.in_proj_weight[d:], a.in_proj_bias[d:], out=ckv)
         for add, l in zip(self.cross_add, self.layers):     # aligned layers: the memory term of every target position
             add.copy_(dec._aligned_cross(l, memory, self.B, self.T, S))
-        self.u.copy_(u)
-        self.tokens.zero_()
-        self.pos.zero_()
-        self.event()                                         # event 0 eagerly (also the warm-up a capture needs)
-        if self.Ev > 1:
-            if self.use_graph:
-                if self.graph is None:
-                    torch.cuda.synchronize()
-                    pos0 = self.pos.clone()
-                    self.graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(self.graph):
-                        self.event()
-                    self.pos.copy_(pos0)                      # capture does not execute
-                for _ in range(1, self.Ev):
-                    self.graph.replay()
-            else:
-                for _ in range(1, self.Ev):
-                    self.event()
-        return self.tokens.view(self.B, self.Ev, self.C).clone()
+        return memory
+
+    def _events(self, n):
+        """n events (C token steps each) from the current position: graph replays once the graph exists; the first event ever runs
+        eagerly (the warm-up a capture needs)."""
+        if not self.use_graph:
+            for _ in range(n):
+                self.event()
+            return
+        if self.graph is None:
+            self.event()
+            n -= 1
+            torch.cuda.synchronize()
+            pos0 = self.pos.clone()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.event()
+            self.pos.copy_(pos0)                              # capture does not execute
+        for _ in range(n):
+            self.graph.replay()
+
+    def run_window(self, codes, window_tokens, p0, n_tokens, u_rows):
+        """generate_from_code_long: refill the cache with ONE teacher-forced forward of the window (its self-attention QKV products
+        are the cache rows; rows >= p0 hold placeholders that the steps overwrite before any later row reads them), then draw
+        the tokens p0 .. p0 + n_tokens - 1 incrementally.  window_tokens (B, events, C) int64; returns (B, n_tokens)."""
+        dec, B, T, C = self.dec, self.B, self.T, self.C
+        assert p0 % C == 0 and n_tokens % C == 0 and p0 + n_tokens <= T
+        pdl = os.environ.get('VQCPC_DECODE_PDL')
+        _native.call('vqcpc_decode_set_pdl', int(pdl) if pdl is not None else int(B <= 4))
+        memory = self._project_memory(codes)
+        kc, vc = self._keep[0], self._keep[1]
+        dec._forward_from_memory(memory, self.S, window_tokens, kv_sinks=list(zip(kc, vc)), want_loss=False)
+        self.tokens.copy_(window_tokens.reshape(B, T))
+        if u_rows is not None:
+            self.u[p0:p0 + n_tokens].copy_(u_rows)
+        self.pos.fill_(p0)
+        self._features_now()
+        self._events(n_tokens // C)
+        return self.tokens[:, p0:p0 + n_tokens].clone()
