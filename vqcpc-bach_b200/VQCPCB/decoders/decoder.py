@@ -384,13 +384,17 @@ class Decoder(nn.Module):
         u = None if uniforms is None else torch.as_tensor(uniforms, dtype=torch.float64).to(dev)
         sess = self._decode_session(B, temperature, top_k, top_p, greedy, None, True) if kv_cache else None
         done = 0
+        prev = None                                          # (t_begin, next position) of the window the cache currently holds
         for code_index in range(code_index_start, code_index_end):
             t_begin, t_end, t_rel = self.compute_start_end_times(code_index, size_encoding, num_codes_model)
             win_codes = codes[:, t_begin:t_end]
             window = chorale[:, t_begin * epc:t_end * epc]
             p0 = t_rel * up
             if kv_cache:
-                new = sess.run_window(win_codes, window, p0, up, None if u is None else u[done:done + up])
+                # while the window does not move (both ends of the sequence) the cache simply continues
+                new = sess.run_window(win_codes, window, p0, up, None if u is None else u[done:done + up],
+                                      prefill=prev != (t_begin, p0))
+                prev = (t_begin, p0 + up)
                 window[:, t_rel * epc:(t_rel + 1) * epc] = new.view(B, epc, C)
             else:
                 zero = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -648,7 +652,7 @@ class _DecodeSession:
         for _ in range(n):
             self.graph.replay()
 
-    def run_window(self, codes, window_tokens, p0, n_tokens, u_rows):
+    def run_window(self, codes, window_tokens, p0, n_tokens, u_rows, prefill=True):
         """generate_from_code_long: refill the cache with ONE teacher-forced forward of the window (its self-attention QKV products
         are the cache rows; rows >= p0 hold placeholders that the steps overwrite before any later row reads them), then draw
         the tokens p0 .. p0 + n_tokens - 1 incrementally.  window_tokens (B, events, C) int64; returns (B, n_tokens)."""
@@ -656,13 +660,15 @@ class _DecodeSession:
         assert p0 % C == 0 and n_tokens % C == 0 and p0 + n_tokens <= T
         pdl = os.environ.get('VQCPC_DECODE_PDL')
         _native.call('vqcpc_decode_set_pdl', int(pdl) if pdl is not None else int(B <= 4))
-        memory = self._project_memory(codes)
-        kc, vc = self._keep[0], self._keep[1]
-        dec._forward_from_memory(memory, self.S, window_tokens, kv_sinks=list(zip(kc, vc)), want_loss=False)
-        self.tokens.copy_(window_tokens.reshape(B, T))
+        if prefill:
+            memory = self._project_memory(codes)
+            kc, vc = self._keep[0], self._keep[1]
+            dec._forward_from_memory(memory, self.S, window_tokens, kv_sinks=list(zip(kc, vc)), want_loss=False)
+            self.tokens.copy_(window_tokens.reshape(B, T))
+            self.pos.fill_(p0)
+            self._features_now()
+        # else: same window as the previous call and p0 is where it stopped - cache, tokens, position and feature row are current
         if u_rows is not None:
             self.u[p0:p0 + n_tokens].copy_(u_rows)
-        self.pos.fill_(p0)
-        self._features_now()
         self._events(n_tokens // C)
         return self.tokens[:, p0:p0 + n_tokens].clone()
