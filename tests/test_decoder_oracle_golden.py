@@ -111,3 +111,29 @@ def test_get_decoder_types_follow_the_reference_table():
                               'transformer_relative_fullCross': ('anticausal', 'full'),
                               'transformer_relative_diagonal': ('anticausal', 'diagonal'),
                               'transformer_relative_full': ('full', 'full')}
+
+
+def test_decoder_checkpoint_roundtrip(tmp_path):
+    """Decoder.save / load (decoder.py:274-292): `<model_dir>/{early_stopped,overfitted}/decoder` holds the state_dict."""
+    import types
+    from VQCPCB.data_processor.bach_data_processor import BachDataProcessor
+    from VQCPCB.decoders.decoder import Decoder
+    c = torch.load(GOLD)['ac_diag']['cfg']
+    enc = torch.nn.Module()
+    enc.downscaler = types.SimpleNamespace(downscale_factors=[4, 4])
+    enc.quantizer = types.SimpleNamespace(codebook_size=c['codebook_size'], num_codebooks=1, codebook_dim=3)
+
+    def make():
+        return Decoder(model_dir=str(tmp_path), dataloader_generator=None, data_processor=BachDataProcessor(32, c['num_events'], list(c['vocab'])),
+                       encoder=enc, transformer_type='relative', encoder_attention_type='anticausal', cross_attention_type='diagonal',
+                       d_model=c['d_model'], num_encoder_layers=2, num_decoder_layers=2, n_head=c['n_head'], dim_feedforward=256,
+                       positional_embedding_size=8, num_channels_encoder=1, num_events_encoder=4, num_channels_decoder=4,
+                       num_events_decoder=c['num_events'], dropout=0.0)
+    a, b = make(), make()
+    a.save(early_stopped=True)
+    a.save(early_stopped=False)
+    assert os.path.exists(tmp_path / 'early_stopped' / 'decoder') and os.path.exists(tmp_path / 'overfitted' / 'decoder')
+    assert any(not torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    b.load(early_stopped=True, device='cpu')
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    assert repr(a) == 'Decoder-relative-AC-D'
