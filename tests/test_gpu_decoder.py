@@ -350,3 +350,61 @@ def test_long_generation_cached_equals_window_recompute(case):
         assert a.shape == (2, 20, 4) and torch.equal(a, b)
     finally:
         ops.set_gemm_mode('bf16x3')
+
+
+@pytest.mark.parametrize('P,H,Lk,pos,mode', [(3, 2, 64, 37, 'self'), (40, 8, 512, 300, 'self'), (40, 8, 512, 511, 'self'),
+                                             (2, 8, 1024, 1000, 'self'), (5, 2, 16, 77, 'cross'), (40, 8, 64, 200, 'cross'),
+                                             (4, 2, 96, 50, 'nobias')])
+def test_attn_decode_kernel_vs_fp64(P, H, Lk, pos, mode):
+    """vqcpc_attn_decode on its own (both register variants: few CTAs -> value prefetch, P * H * splits > 2 x SMs -> the
+    occupancy variant; cluster splits 1..8): one query row over the cache with the relative bias through the map row, the
+    appended key / value, causal length or additive mask - against fp64."""
+    from VQCPCB import _native, ops
+    from VQCPCB.transformer.relative_maps import device_maps, relative_index_maps
+    hd = 64
+    d = H * hd
+    g = torch.Generator().manual_seed(P * 1000 + Lk + pos)
+    self_attn = mode != 'cross'
+    Lq = Lk if self_attn else Lk * 8                       # cross: T = 8 S
+    assert pos < Lq
+    q = (torch.randn(P, d, generator=g) * 0.4).cuda()
+    kc = (torch.randn(P * Lk, d, generator=g) * 0.5).cuda()
+    vc = torch.randn(P * Lk, d, generator=g).cuda()
+    kn, vn = (torch.randn(P, d, generator=g) * 0.5).cuda(), torch.randn(P, d, generator=g).cuda()
+    e1 = (torch.randn(H * Lk, hd, generator=g) * 0.3).cuda()
+    e2 = (torch.randn(H * Lk, hd, generator=g) * 0.3).cuda()
+    m1 = m2 = mask = None
+    if mode != 'nobias':
+        m1, m2 = device_maps(Lq, Lk, 'cuda')
+    if mode == 'cross':
+        mask = torch.repeat_interleave(D.causal_mask(Lk).t(), Lq // Lk, dim=0).contiguous().cuda()
+    posd = torch.tensor([pos], dtype=torch.int32, device='cuda')
+    out = torch.empty(P, d, device='cuda')
+    kc0, vc0 = kc.clone(), vc.clone()
+    _native.call('vqcpc_attn_decode', _pp(q), d, _pp(kn) if self_attn else None, _pp(vn) if self_attn else None, d, _pp(kc), _pp(vc), d, Lk,
+                 _pp(e1) if m1 is not None else None, _pp(e2) if m2 is not None else None, _pp(m1), _pp(m2), _pp(mask), Lk, _pp(posd),
+                 int(self_attn), _pp(out), d, P, H, hd, ops._stream())
+    torch.cuda.synchronize()
+    # fp64 reference
+    K, V = kc0.double().view(P, Lk, H, hd), vc0.double().view(P, Lk, H, hd)
+    if self_attn:                                           # the new row is appended at `pos`, keys 0 .. pos are visible
+        K[:, pos], V[:, pos] = kn.double().view(P, H, hd), vn.double().view(P, H, hd)
+        assert torch.equal(kc.view(P, Lk, d)[:, pos], kn) and torch.equal(vc.view(P, Lk, d)[:, pos], vn)
+        n = pos + 1
+    else:
+        n = Lk
+    qd = q.double().view(P, H, hd)
+    s = torch.einsum('phd,pjhd->phj', qd, K[:, :n])
+    if m1 is not None:
+        for mm, e in ((m1, e1), (m2, e2)):
+            row = mm[pos, :n].cpu().long()
+            eh = e.double().view(H, Lk, hd)
+            valid = row >= 0
+            assert bool((row[valid] // Lk == pos).all())
+            rel = torch.einsum('phd,hjd->phj', qd, eh[:, (row.clamp(min=0) % Lk).cuda()])
+            s = s + torch.where(valid.cuda(), rel, torch.where((row == -2).cuda(), -100.0, 0.0).double())
+    if mask is not None:
+        s = s + mask[pos, :n].double()
+    a = torch.softmax(s, dim=-1)
+    ref = torch.einsum('phj,pjhd->phd', a, V[:, :n]).reshape(P, d)
+    assert rel_err(out, ref) < 3e-6
