@@ -408,3 +408,37 @@ def test_attn_decode_kernel_vs_fp64(P, H, Lk, pos, mode):
     a = torch.softmax(s, dim=-1)
     ref = torch.einsum('phj,pjhd->phd', a, V[:, :n]).reshape(P, d)
     assert rel_err(out, ref) < 3e-6
+
+
+def test_reharmonisation_and_hand_written_codes():
+    """Host wrappers of decoder.py:856-1017 over generate_from_code_long: hand-written code sequences, reharmonisation of a token
+    tensor (window framing, glued codes, trimmed code range), plagiarism helpers."""
+    rec = torch.load(GOLD)['ac_ac']
+    prm = D.make_decoder_params(rec['shapes'], seed=0)
+    dec = _build(rec['cfg'])
+    dec.load_state_dict({k: v.cuda() for k, v in prm.items()}, strict=True)
+
+    class FakeEncoder(torch.nn.Module):               # 16 events x 4 voices -> 4 codes per window, one codebook
+        downscaler = types.SimpleNamespace(downscale_factors=[4, 4])
+        quantizer = types.SimpleNamespace(codebook_size=16, num_codebooks=1, codebook_dim=3)
+
+        def forward(self, x):
+            codes = x.cuda().long().view(x.shape[0], 4, 16).sum(-1) % 16
+            return None, codes.unsqueeze(-1), None
+
+        def merge_codes(self, c):
+            return c[:, :, 0]
+
+    dec.encoder = FakeEncoder()
+    out = dec.generate_alla_mano([1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12, 13, 14], temperature=1.0, num_decodings=2, greedy=True)
+    assert out.shape == (2, 24, 4) and torch.equal(out[0], out[1])
+    codes = torch.tensor([[1, 2, 3, 4, 9, 10, 11, 12, 13, 14, 5, 6, 7, 8]]).cuda()
+    want = dec.generate_from_code_long(codes, greedy=True, code_index_start=4, code_index_end=10, kv_cache=False)
+    assert torch.equal(out[:1], want)
+    # 40 events = 2.5 windows: [start frame][w0][w1][half window + END + PAD][PAD frame] -> 5 windows of 4 codes, 10 decoded
+    g = torch.Generator().manual_seed(2)
+    x = torch.stack([torch.randint(0, v, (1, 40), generator=g) for v in rec['cfg']['vocab']], dim=2)
+    re = dec.generate_reharmonisation(2, temperature=1.0, top_k=0, top_p=0.9, x=x, greedy=True)
+    assert re.shape == (2, 40, 4)
+    s, n = dec.check_duplicate(re[0].cpu(), re[1].cpu())
+    assert n == (len(dec.data_processor.dump(re[0].cpu())) - 1) / 3

@@ -409,6 +409,81 @@ class Decoder(nn.Module):
             done += up
         return chorale[:, code_index_start * epc:code_index_end * epc]
 
+    def _symbols(self):
+        """PAD / START / END token ids per channel from the dataset's dictionaries (zeros when the loader has none)."""
+        ds = getattr(self.dataloader_generator, 'dataset', None)
+        dicts = getattr(ds, 'note2index_dicts', None)
+        dev = self.sos.device
+        if dicts is not None and all(all(k in d_ for k in ('XX', 'START', 'END')) for d_ in dicts):
+            return tuple(torch.tensor([d_[k] for d_ in dicts], device=dev).view(1, 1, -1) for k in ('XX', 'START', 'END'))
+        z = torch.zeros(1, 1, self.num_channels, dtype=torch.int64, device=dev)
+        return z, z.clone(), z.clone()
+
+    @torch.no_grad()
+    def generate_alla_mano(self, start_codes, end_codes, body_codes, temperature, num_decodings=3, **sampling):
+        """decoder.py:960-981 without the score writing: decode a hand-written code sequence; tokens of the body codes."""
+        seq = list(start_codes) + list(body_codes)
+        code_index_start, code_index_end = len(start_codes), len(seq)
+        codes = torch.tensor(seq + list(end_codes), dtype=torch.int64, device=self.sos.device).unsqueeze(0)
+        return self.generate_from_code_long(codes, temperature=temperature, num_decodings=num_decodings,
+                                            code_index_start=code_index_start, code_index_end=code_index_end, **sampling)
+
+    @torch.no_grad()
+    def generate_reharmonisation(self, num_reharmonisations, temperature, top_k, top_p, x=None, **sampling):
+        """decoder.py:856-957 from a token tensor: ``x`` (1, events, channels) is cut into windows, framed by a [PAD.. START] window
+        and an END / PAD tail (:880-914), encoded window by window, the codes glued (:916-929) and decoded
+        ``num_reharmonisations`` times between the frame codes (:930-944).  The reference reads BWV 251 through music21 and
+        writes scores; here the caller supplies the tokens and gets tokens back."""
+        if x is None:
+            raise NotImplementedError('pass the chorale as tokens x (1, events, channels): reading the corpus needs music21')
+        dev = self.sos.device
+        x = x.to(dev).long()
+        n = self.data_processor.num_events
+        PAD, START, END = self._symbols()
+        chunks = list(x.split(n, 1))
+        last = chunks[-1]
+        completion = n - last.size(1)
+        start_chunk = torch.cat([PAD.repeat(1, n - 1, 1), START], 1)
+        if completion > 1:
+            last, end_chunk = torch.cat([last, END, PAD.repeat(1, completion - 1, 1)], 1), PAD.repeat(1, n, 1)
+        elif completion == 1:
+            last, end_chunk = torch.cat([last, END], 1), PAD.repeat(1, n, 1)
+        else:
+            end_chunk = torch.cat([END, PAD.repeat(1, n - 1, 1)], 1)
+        chunks[-1] = last
+        x_chunks = torch.cat([start_chunk] + chunks + [end_chunk], dim=0)
+        zs, stack, _ = self.encoder(x_chunks)
+        codes = zs if stack is None else self.encoder.merge_codes(stack)
+        codes = torch.cat(codes.split(1, 0), 1)                                                     # glue the windows
+        up = self.total_upscaling
+        code_index_start = n * self.num_channels // up
+        code_index_end = codes.size(1) - (n + completion) * self.num_channels // up
+        return self.generate_from_code_long(codes, temperature=temperature, top_k=top_k, top_p=top_p,
+                                            num_decodings=num_reharmonisations, code_index_start=code_index_start,
+                                            code_index_end=code_index_end, **sampling)
+
+    def check_duplicate(self, generation, original):
+        """decoder.py:983-991: longest common run of the two token dumps -> (matching string, number of tokens)."""
+        from difflib import SequenceMatcher
+        s1, s2 = self.data_processor.dump(generation), self.data_processor.dump(original)
+        m = SequenceMatcher(None, s1, s2).find_longest_match(0, len(s1), 0, len(s2))
+        return s1[m.a:m.a + m.size], (m.size - 1) / 3
+
+    def check_duplicate_all_corpus(self, generation, max_windows=None):
+        """decoder.py:993-1017: the training window sharing the longest token run with ``generation`` -> (window, tokens)."""
+        from difflib import SequenceMatcher
+        from itertools import islice
+        s1 = self.data_processor.dump(generation)
+        train, _, _ = self.dataloader_generator.dataloaders(batch_size=1, shuffle_val=True, shuffle_train=False)
+        best_x, best = None, 0
+        for tensor_dict in islice(train, max_windows):
+            x = tensor_dict['x']
+            s2 = self.data_processor.dump(x[0])
+            m = SequenceMatcher(None, s1, s2, autojunk=False).find_longest_match(0, len(s1), 0, len(s2))
+            if m.size > best:
+                best_x, best = x, m.size
+        return best_x, (best - 1) / 3
+
     def init_generation(self, num_events):
         return torch.zeros(1, num_events, self.num_channels, dtype=torch.int64, device=self.sos.device)   # :724-727
 
