@@ -442,3 +442,46 @@ def test_reharmonisation_and_hand_written_codes():
     assert re.shape == (2, 40, 4)
     s, n = dec.check_duplicate(re[0].cpu(), re[1].cpu())
     assert n == (len(dec.data_processor.dump(re[0].cpu())) - 1) / 3
+
+
+def test_decode_small_kernels_vs_torch():
+    """vqcpc_elu_fwd, vqcpc_decode_ln_add, vqcpc_decode_features (both feature modes), vqcpc_decode_advance on their own."""
+    from VQCPCB import _native, ops
+    g = torch.Generator().manual_seed(0)
+    st = ops._stream()
+    x = (torch.randn(1000, 37, generator=g) * 3).cuda()
+    out = torch.empty_like(x)
+    _native.call('vqcpc_elu_fwd', _pp(x), _pp(out), x.numel(), st)
+    assert rel_err(out, torch.nn.functional.elu(x.double())) < 1e-6
+    B, T, d = 5, 12, 192
+    y, add = (torch.randn(B, d, generator=g) * 2 + 0.5).cuda(), torch.randn(B, T, d, generator=g).cuda()
+    gam, bet = torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda()
+    pos = torch.tensor([7], dtype=torch.int32, device='cuda')
+    o = torch.empty(B, d, device='cuda')
+    _native.call('vqcpc_decode_ln_add', _pp(y), _pp(gam), _pp(bet), 1e-5, _pp(add), T, _pp(pos), _pp(o), B, d, st)
+    ref = torch.nn.functional.layer_norm(y.double(), (d,), gam.double(), bet.double(), 1e-5) + add[:, 7].double()
+    assert rel_err(o, ref) < 2e-6
+    # feature rows: [embedding of token pos-1 | channel | event-in-code] and [embedding | absolute position]
+    C, up, E, pe = 4, 16, 8, 3
+    vocab = [5, 6, 7, 8]
+    tables = torch.randn(sum(vocab), E, generator=g).cuda()
+    off = torch.tensor([0, 5, 11, 18], dtype=torch.int32, device='cuda')
+    T = 32
+    tokens = torch.stack([torch.randint(0, vocab[t % C], (B,), generator=g) for t in range(T)], dim=1).cuda()
+    chan, evt, tpos = torch.randn(C, pe, generator=g).cuda(), torch.randn(up // C, pe, generator=g).cuda(), torch.randn(T, pe, generator=g).cuda()
+    for p in (0, 1, 6, 31):
+        pos.fill_(p)
+        f0, f1 = torch.full((B, E + 2 * pe), 9.0, device='cuda'), torch.full((B, E + pe), 9.0, device='cuda')
+        _native.call('vqcpc_decode_features', _pp(tokens), _pp(pos), _pp(tables), _pp(off), _pp(chan), _pp(evt), _pp(f0), B, T, C, up, E,
+                     pe, 0, st)
+        _native.call('vqcpc_decode_features', _pp(tokens), _pp(pos), _pp(tables), _pp(off), _pp(tpos), _pp(tpos), _pp(f1), B, T, C, up, E,
+                     pe, 1, st)
+        if p == 0:
+            assert float(f0.abs().max()) == 0.0 and float(f1.abs().max()) == 0.0
+            continue
+        t = p - 1
+        emb = tables[off[t % C].long() + tokens[:, t]]
+        assert torch.equal(f0, torch.cat([emb, chan[t % C].expand(B, pe), evt[(t % up) // C].expand(B, pe)], dim=1))
+        assert torch.equal(f1, torch.cat([emb, tpos[t].expand(B, pe)], dim=1))
+    _native.call('vqcpc_decode_advance', _pp(pos), 3, st)
+    assert int(pos.item()) == 34
