@@ -77,7 +77,7 @@ class BachCPCDataloaderGenerator(CPCDataloaderGenerator):
 
         def stream(loader, off):
             for idx in loader:
-                rows = (idx + off).to(score.device, non_blocking=True)
+                rows = idx.to(score.device, non_blocking=True) + off          # pinned index view: asynchronous copy, offset on the device
                 yield {'x_left': self._window(score, rows, 0, KL * evb), 'x_right': self._window(score, rows, KL * evb, KR * evb),
                        # negatives of the right positions: all left blocks, then the right blocks but the k-th (:162-184)
                        'negative_samples': self._same_seq(score, rows, 0, KL, KL * evb, KR, KR, evb),
@@ -101,9 +101,9 @@ class BachCPCDataloaderGenerator(CPCDataloaderGenerator):
 
         def stream(lp, op, ln, on, lb, ob):
             for ip, i_n, ib in zip(lp, ln, lb):
-                rows = (ip + op).to(score.device, non_blocking=True)
-                rn = (i_n + on).to(score.device, non_blocking=True)
-                rb = (ib + ob).to(score.device, non_blocking=True)
+                rows = ip.to(score.device, non_blocking=True) + op
+                rn = i_n.to(score.device, non_blocking=True) + on
+                rb = ib.to(score.device, non_blocking=True) + ob
                 yield {'x_left': self._window(score, rows, 0, KL * evb), 'x_right': self._window(score, rows, KL * evb, KR * evb),
                        'negative_samples': self._window(neg, rn, 0, evb).view(batch_size, N, KR, evb, num_voices),
                        'negative_samples_back': self._window(neg, rb, 0, evb).view(batch_size, N, KR, evb, num_voices)}

@@ -27,7 +27,7 @@ class BachDataloaderGenerator:
 
         def stream(it, off):
             for idx in it:
-                rows = (idx + off).to(score.device, non_blocking=True)
+                rows = idx.to(score.device, non_blocking=True) + off          # pinned index view: asynchronous copy, offset on the device
                 yield {'x': BachCPCDataloaderGenerator._window(score, rows, 0, score.shape[2])}
 
         return [stream(it, o) for it, o in zip(iterators, offs)]
