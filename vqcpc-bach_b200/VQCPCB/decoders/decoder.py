@@ -561,7 +561,12 @@ class Decoder(nn.Module):
         x_original = tensor_dict['x'].repeat(batch_size, 1, 1)
         zs, encoding_indices, _ = self.encoder(x_original)
         encoding_indices = zs if encoding_indices is None else self.encoder.merge_codes(encoding_indices)
-        x = self.generate_from_codes(encoding_indices, temperature, top_k=top_k, top_p=top_p)
+        exclude = None
+        if kwargs.get('exclude_meta_symbols'):               # :624-629: START / END / PAD are never drawn
+            dicts = getattr(getattr(self.dataloader_generator, 'dataset', None), 'note2index_dicts', None)
+            if dicts is not None:
+                exclude = {c: [d_[k] for k in ('START', 'END', 'XX') if k in d_] for c, d_ in enumerate(dicts)}
+        x = self.generate_from_codes(encoding_indices, temperature, top_k=top_k, top_p=top_p, exclude=exclude)
         _, recoding, _ = self.encoder(torch.cat([tensor_dict['x'].to(x.device).long(), x], dim=0))
         recoding = None if recoding is None else self.encoder.merge_codes(recoding)
         return x_original, x, recoding
