@@ -173,7 +173,7 @@ int vqcpc_decode_features(const int64_t* tokens, const int* pos, const float* ta
                           void* stream);
 /* pos_mode 1 (transformer_type 'absolute', decoder.py:458-466): feat (B, E + pe) = [ embedding | chan[position] ] with chan the
  * (T, pe) table of absolute positional embeddings; evt is not read. */
-/* nn.Linear on M <= 16 rows in exact fp32: out = [row0 if *pos == 0 else] relu?( (x W^T + bias) * scale on the first
+/* nn.Linear on M <= 32 rows in exact fp32: out = [row0 if *pos == 0 else] relu?( (x W^T + bias) * scale on the first
  * scale_cols columns ) + residual.  W (N, K) row-major; bias / residual / row0 may be NULL. */
 int vqcpc_linear_small(const float* x, int ldx, const float* W, const float* bias, const float* residual, int ldr, float* out,
                        int ldo, int M, int N, int K, int relu, float scale, int scale_cols, const float* row0, const int* pos,

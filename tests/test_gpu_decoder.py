@@ -124,7 +124,8 @@ def _pp(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize('M,N,K', [(1, 512, 512), (3, 1536, 512), (8, 512, 1024), (16, 23, 48), (5, 130, 512)])
+@pytest.mark.parametrize('M,N,K', [(1, 512, 512), (3, 1536, 512), (8, 512, 1024), (16, 23, 48), (5, 130, 512), (20, 512, 512),
+                                   (32, 512, 1024), (27, 64, 48), (32, 96, 2048)])
 def test_linear_small_vs_fp64(M, N, K):
     """vqcpc_linear_small (bias, q-third scaling, ReLU, residual, start-row substitution) against fp64."""
     from VQCPCB import _native, ops
@@ -228,7 +229,7 @@ def test_ln_linear_small_vs_fp64():
     """vqcpc_ln_linear_small: LayerNorm on load + linear, normalised rows written once."""
     from VQCPCB import _native, ops
     g = torch.Generator().manual_seed(9)
-    for M, N, K in [(1, 512, 512), (7, 1536, 512), (16, 64, 512)]:
+    for M, N, K in [(1, 512, 512), (7, 1536, 512), (16, 64, 512), (24, 1024, 512), (32, 64, 128), (12, 96, 1024)]:
         x = (torch.randn(M, K, generator=g) * 3 + 1).cuda()
         w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         b, gam, bet = (torch.randn(n, generator=g).cuda() for n in (N, K, K))
@@ -254,7 +255,7 @@ def test_cached_generation_launch_modes(case, monkeypatch):
         dec.load_state_dict({k: v.cuda() for k, v in prm.items()}, strict=True)
         ops.bump_weight_version()
         S = rec['source'].shape[1]
-        for B in (1, 3, 5):
+        for B in (1, 3, 5) + ((21,) if case == 'ac_diag' else ()):
             src = torch.randint(0, rec['cfg']['codebook_size'], (B, S), generator=torch.Generator().manual_seed(B)).cuda()
             full = dec.generate_from_codes(src, greedy=True, kv_cache=False)
             for pdl in ('0', '1'):

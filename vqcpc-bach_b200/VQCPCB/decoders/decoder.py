@@ -30,6 +30,9 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_MAX_ROWS = 32          # sequences per decode session (vqcpc_linear_small takes up to 32 rows; d_model <= 512 above 16)
+
+
 class _Attn(nn.Module):
     """Parameters of ``MultiheadAttentionCustom`` (multihead_attention_custom.py:36-99): fused in-proj, out-proj, relative tables
     sized by the SOURCE length."""
@@ -375,7 +378,7 @@ class Decoder(nn.Module):
         assert size_encoding >= num_codes_model and 0 <= code_index_start < code_index_end <= size_encoding
         codes = encoding_indices.to(dev).repeat_interleave(num_decodings, dim=0)
         B = codes.size(0)
-        assert B <= 16 or not kv_cache, 'at most 16 sequences per call on the cached path'
+        assert B <= self._max_rows() or not kv_cache, f'at most {self._max_rows()} sequences per call on the cached path'
         chorale = (self.init_generation_chorale(size_encoding * epc, code_index_start * epc) if init_chorale is None
                    else init_chorale.to(dev).long()).repeat(B, 1, 1).contiguous()
         n_tok = (code_index_end - code_index_start) * up
@@ -503,9 +506,10 @@ class Decoder(nn.Module):
         self.eval()
         if kv_cache:
             B = encoding_indices.size(0)
-            outs = [self._generate_cached(encoding_indices[b0:b0 + 16], temperature, top_k, top_p, generator, greedy,
-                                          None if uniforms is None else uniforms[:, b0:b0 + 16], use_graph, exclude)
-                    for b0 in range(0, B, 16)]
+            R = self._max_rows()
+            outs = [self._generate_cached(encoding_indices[b0:b0 + R], temperature, top_k, top_p, generator, greedy,
+                                          None if uniforms is None else uniforms[:, b0:b0 + R], use_graph, exclude)
+                    for b0 in range(0, B, R)]
             return torch.cat(outs, dim=0)
         B = encoding_indices.size(0)
         x = self.init_generation(self.data_processor.num_events).repeat(B, 1, 1)
@@ -522,6 +526,10 @@ class Decoder(nn.Module):
                 x[:, event_index, channel_index] = new
         return x
 
+    def _max_rows(self):
+        """Sequences per decode session: LayerNorm-on-load keeps 32 rows in registers only up to d_model = 512."""
+        return _MAX_ROWS if self.d_model <= 512 else 16
+
     def _decode_session(self, B, temperature, top_k, top_p, greedy, exclude, use_graph):
         ex_key = None if not exclude else tuple(sorted((c, tuple(sorted(v))) for c, v in exclude.items()))
         key = (B, float(temperature), int(top_k), float(top_p), bool(greedy), ex_key, bool(use_graph), self.sos.data_ptr(),
@@ -534,7 +542,7 @@ class Decoder(nn.Module):
         return cache[key]
 
     def _generate_cached(self, codes, temperature, top_k, top_p, generator, greedy, uniforms, use_graph, exclude):
-        """<= 16 sequences through the incremental path.  The buffers, the launch sequence and its CUDA graph live in a
+        """<= _MAX_ROWS sequences through the incremental path.  The buffers, the launch sequence and its CUDA graph live in a
         ``_DecodeSession`` cached per (batch, sampling settings): a later call only refreshes the memory keys / values and the
         uniforms and replays."""
         dev = self.sos.device

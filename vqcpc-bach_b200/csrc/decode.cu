@@ -181,7 +181,7 @@ linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The same product for 3 <= M <= 16 rows: the M input rows are staged in shared memory by M bulk (TMA) copies that one thread
+// The same product for 3 <= M <= 32 rows: the M input rows are staged in shared memory by M bulk (TMA) copies that one thread
 // issues at kernel entry - ONE round of memory latency for the whole input, overlapped with every warp's W-row load - instead
 // of one round per group of rows.  LN: warp w normalises rows w, w + 4, .. in place once per CTA.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -247,7 +247,7 @@ linear_staged_kernel(const float* __restrict__ x, int ldx, const float* __restri
   __syncthreads();                                 // the barrier initialisation is visible to the waiting threads
   ls_mbar_wait(bar, 0);
   if (LN) {
-    // warp w normalises rows w, w + 4, w + 8, w + 12 - all of them at once (independent reduction chains interleave)
+    // warp w normalises rows w, w + 4, w + 8, ... - all of them at once (independent reduction chains interleave)
     constexpr int NR = (MT + 3) / 4;
     const float invK = 1.f / (float)K;
     float4 v[NR][KV];
@@ -766,7 +766,8 @@ VQ_API int vqcpc_decode_features(const int64_t* tokens, const int* pos, const fl
 static int linear_small_launch(const float* x, int ldx, const float* W, const float* bias, const float* residual, int ldr, float* out,
                                int ldo, int M, int N, int K, int relu, float scale, int scale_cols, const float* row0, const int* pos,
                                const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_out, void* stream) {
-  VQ_CHECK_ARG(M >= 1 && M <= 16, "linear_small: 1 <= M <= 16 rows per call (got %d)", M);
+  VQ_CHECK_ARG(M >= 1 && M <= 32, "linear_small: 1 <= M <= 32 rows per call (got %d)", M);
+  VQ_CHECK_ARG(!(ln_gamma != nullptr && M > 16 && K > 512), "linear_small: LayerNorm on load with more than 16 rows needs K <= 512");
   VQ_CHECK_ARG(N >= 1 && K >= 4 && (K % 4) == 0 && (ldx % 4) == 0 && K <= 2048, "linear_small: bad shape N=%d K=%d ldx=%d (K <= 2048)", N, K, ldx);
   VQ_CHECK_ARG(row0 == nullptr || pos != nullptr, "linear_small: row0 needs the position pointer");
   VQ_CHECK_ARG((ln_gamma == nullptr) == (ln_beta == nullptr) && (ln_out == nullptr || ln_gamma != nullptr), "linear_small: LayerNorm arguments");
@@ -778,10 +779,13 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
     const size_t smem = 16 + (size_t)M * K * sizeof(float);
     static bool attr_done = false;
 #define VQ_ST_ATTR(KVV, MTV, LNV) \
-  VQ_CUDA_CALL(cudaFuncSetAttribute(linear_staged_kernel<KVV, MTV, LNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 + 16 * 1024 * 4))
-    if (!attr_done) {
+  VQ_CUDA_CALL(cudaFuncSetAttribute(linear_staged_kernel<KVV, MTV, LNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 + MTV * 128 * KVV * 4))
+    if (!attr_done) {                              // the instantiations whose rows exceed the default 48 KB
       VQ_ST_ATTR(8, 16, true);
       VQ_ST_ATTR(8, 16, false);
+      VQ_ST_ATTR(8, 32, false);
+      VQ_ST_ATTR(4, 32, true);
+      VQ_ST_ATTR(4, 32, false);
       attr_done = true;
     }
 #undef VQ_ST_ATTR
@@ -792,7 +796,8 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
   do {                                       \
     if (M <= 4) VQ_ST(KVV, 4, LNV);          \
     else if (M <= 8) VQ_ST(KVV, 8, LNV);     \
-    else VQ_ST(KVV, 16, LNV);                \
+    else if (M <= 16) VQ_ST(KVV, 16, LNV);   \
+    else VQ_ST(KVV, 32, LNV);                \
   } while (0)
 #define VQ_ST_K(KVV)                         \
   do {                                       \
@@ -801,7 +806,11 @@ static int linear_small_launch(const float* x, int ldx, const float* W, const fl
   } while (0)
     if (K <= 128) VQ_ST_K(1);
     else if (K <= 512) VQ_ST_K(4);
-    else VQ_ST_K(8);
+    else if (ln) {                             // K <= 1024 with LayerNorm: at most 16 rows (checked above)
+      if (M <= 4) VQ_ST(8, 4, true);
+      else if (M <= 8) VQ_ST(8, 8, true);
+      else VQ_ST(8, 16, true);
+    } else VQ_ST_M(8, false);
 #undef VQ_ST_K
 #undef VQ_ST_M
 #undef VQ_ST
