@@ -636,6 +636,7 @@ class _DecodeSession:
                 bvec[list(exclude[c])] = -float('inf')
             head_bias.append(bvec)
         sos = dec.sos.detach().reshape(d).contiguous()
+        self.kc, self.vc = kc, vc                            # self-attention key / value caches, one (B * T, d) pair per layer
         self._keep = [kc, vc, sm1, sm2, cm1, cm2, memory_mask, tables, table_off, chan, evt, head_bias, sos, feat, x, x1, x2, y,
                       att, qc, qkv, hmid, logits, done]
         call = _native.call
@@ -750,7 +751,7 @@ class _DecodeSession:
         _native.call('vqcpc_decode_set_pdl', int(pdl) if pdl is not None else int(B <= 4))
         if prefill:
             memory = self._project_memory(codes)
-            kc, vc = self._keep[0], self._keep[1]
+            kc, vc = self.kc, self.vc
             dec._forward_from_memory(memory, self.S, window_tokens, kv_sinks=list(zip(kc, vc)), want_loss=False)
             self.tokens.copy_(window_tokens.reshape(B, T))
             self.pos.fill_(p0)
