@@ -1,7 +1,8 @@
 """Autoregressive generation over code sequences at BASELINE config 5 shapes (seq 1024 = 256 events x 4 voices from 64 codes,
 decoder_relative_AC_AC_C_*: d = 512, 8 heads, 3 + 3 layers, FFN 1024, positional embedding 8, embedding 32).
 
-    python tools/decoder_bench.py [--batch 1] [--reps 3] [--full-tokens 32] [--cpu-forwards 2]
+    python tools/decoder_bench.py [--batch 1] [--reps 3] [--full-tokens 32] [--cpu-forwards 2] [--cross anticausal|full|diagonal]
+                                  [--pdl -1|0|1] [--attn-split 0|1|2|4|8] [--long-codes N]
 
 Prints one JSON line:
   * tokens/s of ``Decoder.generate_from_codes`` on the incremental path (key / value cache + CUDA graph per event + device
@@ -11,7 +12,8 @@ Prints one JSON line:
   * the CPU oracle (oracle/decoder_oracle.py = the reference's forward restated) on the host cores: seconds per full forward =
     the reference's cost per generated token (decoder.py:611-614);
   * parity at this size: greedy tokens of the cached path against the full-recompute path over the first ``--full-tokens``
-    positions (fp32 mode), and teacher-forced logits of the product forward against the oracle forward."""
+    positions (fp32 mode), and teacher-forced logits of the product forward against the oracle forward;
+  * --long-codes N: sliding-window decoding of N codes (generate_from_code_long), cached vs the window recompute per token."""
 import argparse
 import json
 import os
